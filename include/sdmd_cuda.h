@@ -1,0 +1,282 @@
+/*
+ * sdmd_cuda.h — C-ABI of libsdmd_cuda.so, the B200 (sm_100a) implementation of sDMD's
+ * event-prediction / event-scheduling hot path.
+ *
+ * Plain C: pointers, sizes and PODs only.  Host code (the sDMD C driver, tests, bench) talks to the
+ * CUDA side exclusively through the functions declared here.  Every entry point names the reference
+ * interface it replaces (paths relative to the sDMD source tree, `src/`).
+ *
+ * Conventions
+ *   - atom ids are 1-based exactly like the reference (`atom[1..atomnum]`); every per-atom array in
+ *     `sdmd_host_view` has natom+1 elements and element 0 is unused.
+ *   - distances in the step tables are squared (the reference squares them at load time,
+ *     Initialization.c:1507,1515,1313-1330).
+ *   - all functions return 0 on success or a negative SDMD_ERR_* code; nothing here ever falls back to
+ *     a CPU implementation — when no CUDA device is usable the call fails.
+ */
+#ifndef SDMD_CUDA_H
+#define SDMD_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDMD_ABI_VERSION 1
+
+/* reference constants, DMD.h:25-30 */
+#define SDMD_INFINIT       1E8
+#define SDMD_ZERO          1E-8
+#define SDMD_INVALID       (-111)
+#define SDMD_NATOMTYPE     32
+#define SDMD_EXTEND_RATIO  0.90
+#define SDMD_MAX_STEPS     16     /* longest shipped table row has 13 steps */
+#define SDMD_NHBCLASS      12     /* potentialPairHB[12][33][33], DMD.h:550 */
+
+/* connection-map bits, DMD.h:59-63 */
+#define SDMD_BOND_CONNECT        0x01
+#define SDMD_CONSTRAINT_CONNECT  0x02
+#define SDMD_HB_CONNECT          0x04
+#define SDMD_NEIGHBOR_CONNECT    0x08
+
+/* enum EEventType, DMD.h:162-179 (values are part of the log / checkpoint format) */
+enum sdmd_event_type {
+    SDMD_EV_COLI = 0, SDMD_EV_BOND = 1, SDMD_EV_HB = 2, SDMD_EV_HBNE = 3, SDMD_EV_THER = 4,
+    SDMD_EV_WALL = 5, SDMD_EV_OBST = 6, SDMD_EV_TUNL = 7, SDMD_EV_CHRG = 8, SDMD_EV_SPHO = 9,
+    SDMD_EV_PCC = 10, SDMD_EV_CGSU = 11, SDMD_EV_LAGV = 12, SDMD_EV_TBD = 13, SDMD_EV_CACL = 14,
+    SDMD_EV_INVD = 15
+};
+
+/* enum EInteractionType, DMD.h:181-191 */
+enum sdmd_sub_event {
+    SDMD_SUB_CORECOLLI = 0, SDMD_SUB_WELLBOUNC = 1, SDMD_SUB_WELLCAPTR = 2, SDMD_SUB_WELLESCAP = 3,
+    SDMD_SUB_TBDCAPTR = 4, SDMD_SUB_TBDESCAP = 5, SDMD_SUB_TBDHBFORM = 6, SDMD_SUB_TBDHBBRIK = 7,
+    SDMD_SUB_INVALID = 8
+};
+
+/* enum EHBEventType, DMD.h:193-198 */
+enum sdmd_hb_event { SDMD_HB_NOEVENT = 0, SDMD_HB_FORM = 1, SDMD_HB_BREAK = 2, SDMD_HB_SKIP = 3 };
+
+enum sdmd_error {
+    SDMD_OK = 0,
+    SDMD_ERR_NO_DEVICE   = -1,   /* no usable CUDA device / kernel image (never a CPU fallback) */
+    SDMD_ERR_CUDA        = -2,   /* a CUDA runtime call failed; see sdmd_cuda_last_error() */
+    SDMD_ERR_BAD_ARG     = -3,
+    SDMD_ERR_UNSUPPORTED = -4,   /* feature outside the hot-path scope (walls, CG, tunnels, flow, ...) */
+    SDMD_ERR_TABLE       = -5,   /* a pair needed a potential table that does not exist (FindPair exit, ToolFunctions.c:114-117) */
+    SDMD_ERR_STATE       = -6,   /* device-side consistency check failed (link list / event type) */
+    SDMD_ERR_NCCL        = -7
+};
+
+/* One flattened ConstraintStr + its StepPotenStr chain (DMD.h:244-257).
+ * acc[k] is StepPotenStr.accumulated (ToolFunctions.c:897-919). */
+struct sdmd_step_table {
+    double dmin2;
+    double dmax2;                     /* 0 for collision tables */
+    int32_t nstep;
+    int32_t pad_;
+    double d2[SDMD_MAX_STEPS];
+    double e[SDMD_MAX_STEPS];
+    double acc[SDMD_MAX_STEPS];
+};
+
+/* Flattened, pointer-free view of the reference's process globals (DMD.h:475-613) that the hot path
+ * reads.  The host keeps ownership of everything; sdmd_cuda_create copies what it needs. */
+struct sdmd_host_view {
+    int32_t abi_version;              /* SDMD_ABI_VERSION */
+    int32_t natom;                    /* atomnum */
+    double  box[3];                   /* boxDimension[1..3] */
+    double  cutoffr;                  /* cutoffr */
+    double  thermoF;                  /* Thermo_Freq */
+    double  target_temperature;       /* targetTemperature (reduced) */
+    double  currenttime;              /* currenttime */
+    double  timestep;                 /* timestep = end of run */
+    int32_t thermostat_on;            /* strcmp(thermostatType,"no") != 0 */
+    int32_t method_ding;              /* strncmp(Methodtype,"Ding",1) == 0 */
+    int32_t hydrogen_bond;            /* built with HYDROGEN_BOND (DMD.h:23) */
+    int32_t gel_mode;                 /* built with GEL (no BondTime, SGThread.c:170) */
+    int64_t frame;                    /* executed events so far */
+
+    /* per atom, natom+1 entries */
+    double *x, *y, *z;                /* dynamic->coordinate[1..3] */
+    double *vx, *vy, *vz;             /* dynamic->velocity[1..3] */
+    double *mass;                     /* property->mass */
+    int32_t *type;                    /* property->typeofAtom (mutable: HB form/break) */
+    int32_t *aa_type;                 /* property->typeofAA */
+    int32_t *protein_num;             /* property->sequence.proteinNum */
+    int32_t *aa_num;                  /* property->sequence.aminoacidNum */
+    uint8_t *is_cons;                 /* extraProperty[1] == "_CONS" */
+    int32_t *hb_bond;                 /* dynamic->HB.bondConnection */
+    int32_t *hb_neighbor;             /* dynamic->HB.neighbor */
+    uint8_t *hb_role;                 /* dynamic->HB.role ('A','D','S' or 0) */
+    uint8_t *hb_itype;                /* dynamic->HB.interactionType */
+    int32_t *hbn_partner;             /* dynamic->HBNeighbor.neighborPartner, 5 ints per atom */
+    int32_t *hbn_partner_num;         /* dynamic->HBNeighbor.partnerNum */
+    int32_t *hbn_status;              /* dynamic->HBNeighbor.neighborStatus */
+    double  *ev_time;                 /* dynamic->event.* */
+    double  *ev_potential;
+    int32_t *ev_partner;
+    int64_t *ev_counter;
+    int64_t *ev_pcounter;
+    uint8_t *ev_type;
+    uint8_t *ev_sub;
+    int32_t *cell_idx;                /* dynamic->cellIndex[1..3], 3 ints per atom; may be NULL before the first cell build */
+
+    /* covalent / auxiliary bonds, property->bond in list order; CSR over atoms: bond_off[natom+2] */
+    int32_t *bond_off;
+    int32_t *bond_j;
+    double  *bond_dmin2, *bond_dmax2;
+    /* CONSTRn pairs, property->constr in list order; con_table indexes `tables` */
+    int32_t *con_off;
+    int32_t *con_j;
+    int32_t *con_table;
+    /* static bits of connectionMap (BOND / CONSTRAINT), CSR, row order ascending j */
+    int32_t *cm_off;
+    int32_t *cm_j;
+    int32_t *cm_flags;
+
+    /* potential tables */
+    int32_t ntable;
+    struct sdmd_step_table *tables;
+    int32_t *coll_index;              /* [33*33] potentialPairCollision after RightPair resolution (ToolFunctions.c:278-292); -1 = none */
+    int32_t *hb_index;                /* [12*33*33] potentialPairHB; -1 = empty entry */
+    double  hb_barrier[3];            /* HBPotential.BB_v, SS_v, BS_v (Events.c:1097-1119) */
+};
+
+/* counters mirroring the reference's global tallies (DMD.c:50-61) */
+struct sdmd_run_stats {
+    int64_t frame;                    /* committed events (frame, SGThread.c:100) */
+    int64_t iterations;               /* loop iterations incl. hazard-denied */
+    int64_t count_recal;              /* countReCal */
+    int64_t collision, bond, hb, hb_neighbor, thermostat, pcc;
+    int64_t warnings;                 /* warningsum */
+    int64_t pair_predictions;         /* CalculateParameters-equivalent evaluations */
+    int64_t gaussians_used;           /* thermostat RNG samples consumed */
+    double  currenttime;
+    int32_t stop_reason;              /* enum sdmd_stop_reason */
+    int32_t error;                    /* first device-side SDMD_ERR_* or 0 */
+};
+
+enum sdmd_stop_reason {
+    SDMD_STOP_TIME_END   = 0,         /* currenttime > timestep (loop condition SGThread.c:75) */
+    SDMD_STOP_T_UNTIL    = 1,         /* an executed event carried currenttime past t_until (output / exchange boundary) */
+    SDMD_STOP_MAX_ITER   = 2,
+    SDMD_STOP_NEED_RNG   = 3,         /* gaussian ring ran low; refill and call again */
+    SDMD_STOP_ERROR      = 4
+};
+
+/* one line of the DEBUG_PRINTF event log (SGThread.c:87-99) plus the time increment */
+struct sdmd_trace_rec {
+    int64_t frame;
+    int32_t target;
+    int32_t partner;                  /* target's event.partner (may be SDMD_INVALID) */
+    int32_t type;
+    int32_t sub;
+    int32_t executed;                 /* 1 executed, 0 denied */
+    int32_t pad_;
+    double  dt;
+};
+
+typedef struct sdmd_ctx sdmd_ctx;
+
+/* ---- lifetime --------------------------------------------------------------------------------- */
+/* Flatten-and-upload.  Replaces nothing in the reference; it is what a maintainer calls once after
+ * InputData() (DMD.c:196).  Computes the cell grid exactly like CreateCell (Initialization.c:1060-1073). */
+int  sdmd_cuda_create(const struct sdmd_host_view *view, int device, sdmd_ctx **out);
+void sdmd_cuda_destroy(sdmd_ctx *ctx);
+const char *sdmd_cuda_last_error(void);
+int  sdmd_cuda_device_count(void);
+
+/* CreateCell result: cellnum[1..3], cellsize[1..3] */
+int  sdmd_cuda_cell_grid(const sdmd_ctx *ctx, int cellnum[3], double cellsize[3]);
+
+/* ---- state transfer (host buffers <-> HBM) ------------------------------------------------------ */
+/* positions / velocities only: natom+1 doubles each, entry 0 ignored */
+int  sdmd_cuda_upload_coords(sdmd_ctx *ctx, const double *x, const double *y, const double *z,
+                             const double *vx, const double *vy, const double *vz);
+/* refresh every mutable per-atom array of `view` from the device (what SaveData/DoEvent need,
+ * SURVEY 8b "sync_to_host"); arrays that are NULL in `view` are skipped */
+int  sdmd_cuda_download(sdmd_ctx *ctx, struct sdmd_host_view *view);
+/* reference-format link list: celllist[natom + ncell + 1] (Events.c:125,152-153) */
+int  sdmd_cuda_download_celllist(sdmd_ctx *ctx, int32_t *celllist);
+/* CBT.node[2*natom], CBT.leaf[natom+1] (CBT.c:16-30) */
+int  sdmd_cuda_download_cbt(sdmd_ctx *ctx, int32_t *node, int32_t *leaf);
+
+/* ---- thermostat random stream ------------------------------------------------------------------- */
+/* Append standard-normal samples, in the order the reference would draw them from
+ * Maxwell_Boltzmann_Distribution (ToolFunctions.c:544-569).  The device consumes them sequentially. */
+int  sdmd_cuda_rng_feed(sdmd_ctx *ctx, const double *gauss, int64_t n);
+/* Generate n samples on the host with libc rand()/log()/sqrt() exactly as ToolFunctions.c:517-569 does
+ * and feed them.  Uses the process-global rand() stream the reference seeded with srand(seed). */
+int  sdmd_cuda_rng_fill_libc(sdmd_ctx *ctx, int64_t n);
+int64_t sdmd_cuda_rng_available(const sdmd_ctx *ctx);
+/* the host-side generator by itself (no ctx): one draw of Maxwell_Boltzmann_Distribution(0,1) */
+double sdmd_host_gaussian_libc(void);
+
+/* ---- the hot path, one call per reference function ----------------------------------------------- */
+/* PBC("full") Events.c:218-228 */
+int  sdmd_cuda_pbc_full(sdmd_ctx *ctx);
+/* LinkList("full") Events.c:121-156 — GPU counting sort; also produces the cell-sorted SoA tiles */
+int  sdmd_cuda_cell_build(sdmd_ctx *ctx);
+/* Prepare()'s Predict over all atoms, SGThread.c:47-52 → Predict SGThread.c:158-211.
+ * Consumes natom gaussians when the thermostat is on. */
+int  sdmd_cuda_predict_all(sdmd_ctx *ctx);
+/* Predict(renewList) SGThread.c:158-211; renew_list follows the reference layout:
+ * [0] = count, [1..count] = atom ids, 0-terminated */
+int  sdmd_cuda_predict(sdmd_ctx *ctx, const int32_t *renew_list);
+/* CreateCBT CBT.c:16-30 / UpdateCBT CBT.c:33-39 */
+int  sdmd_cuda_cbt_build(sdmd_ctx *ctx);
+int  sdmd_cuda_cbt_update(sdmd_ctx *ctx, const int32_t *renew_list);
+/* AssignJob SGThread.c:237-259: target = CBT.node[1], dt = its event time, partner (0 if none) */
+int  sdmd_cuda_assign_job(sdmd_ctx *ctx, int32_t *target, int32_t *partner, double *dt, int32_t *renew_list);
+/* UpdateData + TimeForward, ToolFunctions.c:23-36 (one fused sweep) */
+int  sdmd_cuda_advance(sdmd_ctx *ctx, double dt);
+/* HazardCheck SGThread.c:215-235; *hazard = 0 ok / -1 denied */
+int  sdmd_cuda_hazard_check(sdmd_ctx *ctx, int32_t target, int32_t partner, int32_t *hazard);
+/* PBCandCrossCellEvent Events.c:248-272 = PBC("part") + LinkList("part") for one atom */
+int  sdmd_cuda_cell_move(sdmd_ctx *ctx, int32_t atom);
+/* DoEvent Events.c:25-114 for the pending (target, partner) of the last assign_job, on the device */
+int  sdmd_cuda_do_event(sdmd_ctx *ctx);
+/* CalPotenE ToolFunctions.c:659-752 / CalKinetE :626-656 */
+int  sdmd_cuda_potential_energy(sdmd_ctx *ctx, double *energy);
+int  sdmd_cuda_kinetic_energy(sdmd_ctx *ctx, double *energy);
+
+/* SingleThreadRun / REMDRun event loop (SGThread.c:67-156, REMD.c:29-126) resident on the device:
+ * runs until currenttime > timestep, or an executed event reaches t_until, or max_iter iterations.
+ * trace (optional, capacity trace_cap records) receives one record per loop iteration. */
+int  sdmd_cuda_run(sdmd_ctx *ctx, double t_until, int64_t max_iter,
+                   struct sdmd_trace_rec *trace, int64_t trace_cap, struct sdmd_run_stats *stats);
+int  sdmd_cuda_get_stats(sdmd_ctx *ctx, struct sdmd_run_stats *stats);
+/* targetTemperature after a replica exchange (REMD.c:100) */
+int  sdmd_cuda_set_temperature(sdmd_ctx *ctx, double t_reduced);
+
+/* ---- REMD exchange (REMD.c:135-192 client + Server.c:121-211 server) ----------------------------- */
+struct sdmd_remd_temp { int32_t num; int32_t pad_; double T; };   /* struct REMDTempStr, DMD.h:377-380 */
+
+/* The sequential Metropolis sweep of Server.c:145-192 over nrep replicas (host arrays, in place).
+ * `u01` supplies the uniform draws of RANDOMVALUE(0,1) (Server.c:16-18) in order; *n_used returns how
+ * many were consumed.  accept/attempt (size nrep, may be NULL) accumulate Server.c's `probability`. */
+int  sdmd_remd_rearrange(double *epot, struct sdmd_remd_temp *T, int nrep,
+                         const double *u01, int n_u01, int *n_used,
+                         double *attempt, double *accept);
+
+/* NCCL communicator for the exchange step: one rank per GPU.  `unique_id` is the 128-byte
+ * ncclUniqueId produced by rank 0 (sdmd_remd_nccl_unique_id) and distributed by the launcher. */
+int  sdmd_remd_nccl_unique_id(unsigned char id[128]);
+int  sdmd_remd_nccl_init(sdmd_ctx *ctx, int nranks, int rank, const unsigned char id[128]);
+/* ReplicaExchange: all-gather (E, T, num) of every rank over NCCL, run the replicated sweep with the
+ * shared server seed stream, return this rank's new (T, num). */
+int  sdmd_remd_exchange(sdmd_ctx *ctx, double epot, struct sdmd_remd_temp *T, uint32_t server_seed_step);
+
+/* ---- measurement helpers ------------------------------------------------------------------------- */
+/* average device time (ms) of the last launch of each named kernel, measured with CUDA events on the
+ * context's stream; name in {"advance","predict_all","cell_build","cbt_build"}; <0 if never launched */
+double sdmd_cuda_kernel_ms(const sdmd_ctx *ctx, const char *name);
+int64_t sdmd_cuda_launch_count(const sdmd_ctx *ctx);
+void *sdmd_cuda_stream(const sdmd_ctx *ctx);   /* cudaStream_t */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDMD_CUDA_H */
