@@ -1,0 +1,112 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE — regenerate golden vectors from the UNMODIFIED reference.
+
+Runs oracle/_ref/ref_harness (reference objects + our dump harness, built by oracle/Makefile) on the
+reference's own inputs and stores what the reference computed as compressed .npz fixtures:
+
+  ala10        demo/Folding-style ala10.gro, T*=0.6, 3000 loop iterations from t=0
+  ala10_hb     same run, snapshot taken after 170000 iterations, then 8000 traced iterations
+               (contains HB form/break and HB-neighbour events)
+  gel10        GEL step-potential spheres, 10^3 simple-cubic lattice at 8 A (reference CreateGELCoordinate
+               layout, ToolFunctions.c:775-798), 3000 iterations
+
+usage: python oracle/make_golden.py [--out tests/golden] [--work oracle/_ref/work] [--only NAME]
+Also importable: run_case(name, workdir) returns the three snapshot paths for ad-hoc (uncommitted) runs.
+"""
+from __future__ import annotations
+
+import argparse
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from sdmd_b200.hostview import read_snapshot  # noqa: E402
+
+REFDIR = ROOT / "oracle" / "_ref"
+
+CASES = {
+    # name: (harness, coordinate file, max_iter, n_gauss, extra harness args, gel lattice n)
+    "ala10": ("ref_harness", "ala10.gro", 3000, 8000, [], 0),
+    "ala10_hb": ("ref_harness", "ala10.gro", 8000, 16000, ["--warm", "170000"], 0),
+    "gel10": ("ref_harness_gel", "GEL10.gro", 3000, 12000, [], 10),
+}
+
+
+def write_gel_gro(path: Path, n: int, a_nm: float = 0.8):
+    """Same text format as CreateGELCoordinate (ToolFunctions.c:775-798) for an n^3 lattice."""
+    with open(path, "w") as f:
+        f.write("Model\n%5i\n" % (n ** 3))
+        k = 1
+        for i in range(n):
+            for j in range(n):
+                for m in range(n):
+                    f.write("%5iGEL%5s%5i%8.3f%8.3f%8.3f\n" % (k, "GEL", k, (m + 0.5) * a_nm, (j + 0.5) * a_nm, (i + 0.5) * a_nm))
+                    k += 1
+        f.write("%10.5f%10.5f%10.5f\n" % (n * a_nm, n * a_nm, n * a_nm))
+
+
+def prepare_input(work: Path, time_units: float = 1000.0) -> Path:
+    """Writable copy of the reference input directory with the run length set."""
+    src = REFDIR / "input"
+    if not src.exists():
+        raise FileNotFoundError(f"{src} missing: run `make -C oracle ref` where /root/reference exists")
+    inp = work / "input"
+    if inp.exists():
+        shutil.rmtree(inp)
+    shutil.copytree(src, inp)
+    p = inp / "parameter.txt"
+    lines = p.read_text().splitlines()
+    lines[1] = "Time               %g" % time_units
+    p.write_text("\n".join(lines) + "\n")
+    (work / "out").mkdir(parents=True, exist_ok=True)
+    return inp
+
+
+def run_case(name: str, work: Path, harness=None, coord=None, max_iter=None, n_gauss=None, extra=None, gel_n=None):
+    spec = CASES.get(name)
+    if spec is not None:
+        harness, coord, max_iter, n_gauss, extra, gel_n = [s if o is None else o for s, o in
+                                                           zip(spec, (harness, coord, max_iter, n_gauss, extra, gel_n))]
+    work.mkdir(parents=True, exist_ok=True)
+    inp = prepare_input(work)
+    if gel_n:
+        write_gel_gro(inp / coord, gel_n)
+    prefix = work / name
+    cmd = [str(REFDIR / harness), str(prefix), str(max_iter), str(n_gauss), *extra, "--",
+           "-f", coord, "-i", str(inp), "-o", str(work / "out")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"{' '.join(cmd)} failed ({r.returncode}):\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+    return tuple(Path(f"{prefix}_{k}.snap") for k in ("pre", "post", "final"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=str(ROOT / "tests" / "golden"))
+    ap.add_argument("--work", default=str(REFDIR / "work" / "golden"))
+    ap.add_argument("--only", default=None)
+    a = ap.parse_args()
+    out = Path(a.out)
+    out.mkdir(parents=True, exist_ok=True)
+    for name in CASES:
+        if a.only and a.only != name:
+            continue
+        snaps = run_case(name, Path(a.work))
+        for tag, snap in zip(("pre", "post", "final"), snaps):
+            d = read_snapshot(snap)
+            if tag != "pre":
+                # tables / index maps are identical to the pre snapshot: keep fixtures small
+                for k in ("tables", "coll_index", "hb_index"):
+                    d[k] = d[k][:0]
+                d.pop("gauss", None)
+            np.savez_compressed(out / f"{name}_{tag}.npz", **d)
+        print(name, "->", [f"{name}_{t}.npz" for t in ("pre", "post", "final")])
+
+
+if __name__ == "__main__":
+    main()

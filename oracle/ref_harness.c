@@ -14,7 +14,11 @@
  * output and progress printing are left out.  `ref_harness ... --printf-log` prints the same lines as a
  * -DDEBUG_PRINTF build so the loop can be diffed against the stock binary.
  *
- * usage: ref_harness <out_prefix> <max_iter> <n_gauss> [--printf-log] -- <sDMD args...>
+ * With `--warm N` the harness first runs N loop iterations silently, then takes the "pre" snapshot from
+ * that mid-run state (slots, link list and counters included), rebuilds the CBT from the stored times the
+ * way a `continue` run does (Initialization.c:360-509 + CreateCBT), and traces from there.
+ *
+ * usage: ref_harness <out_prefix> <max_iter> <n_gauss> [--printf-log] [--no-sdmin] [--warm N] -- <sDMD args...>
  */
 #include "DMD.h"
 #include "sdmd_refglue.h"
@@ -48,74 +52,11 @@ static void put_cbt_and_cells(sdmd_snap *s) {
     }
 }
 
-int main(int argc, const char *argv[]) {
-    if (argc < 5) {
-        fprintf(stderr, "usage: %s <out_prefix> <max_iter> <n_gauss> [--printf-log] -- <sDMD args>\n", argv[0]);
-        return 2;
-    }
-    const char *prefix = argv[1];
-    long max_iter = atol(argv[2]);
-    long n_gauss = atol(argv[3]);
-    int printf_log = 0, skip_sdmin = 0;
-    int a = 4;
-    for (; a < argc && strcmp(argv[a], "--"); a++) {
-        if (!strcmp(argv[a], "--printf-log")) printf_log = 1;
-        if (!strcmp(argv[a], "--no-sdmin")) skip_sdmin = 1;
-    }
-    if (a >= argc) { fprintf(stderr, "missing -- before sDMD args\n"); return 2; }
-    argv[a] = argv[0];
-    InputData(argc - a, argv + a);
-
-    char path[1024];
-    struct sdmd_host_view view;
-
-    /* ---- Prepare(), SGThread.c:21-64, minus file output ---- */
-    atomList.ptr = (struct AtomStr **)calloc(atomnum + 1, sizeof(struct AtomStr *));
-    for (int i = 1; i <= atomnum; i++) atomList.ptr[i] = &atom[i];
-#ifndef GEL
-    if (!skip_sdmin) SDEnergyMin(20000, &atomList);
-#endif
-    PBC("full", NULL, &atomList);
-    LinkList("full", NULL, NULL, &atomList);
-
-    int rc = sdmd_glue_flatten(&view);
-    if (rc) { fprintf(stderr, "flatten failed: %d\n", rc); return 1; }
-
-    /* pre-draw the gaussian stream with the reference's own generator, then rewind */
-    char rng0[128];
-    rng_save(rng0);
-    double *gauss = malloc(sizeof(double) * (n_gauss > 0 ? n_gauss : 1));
-    for (long k = 0; k < n_gauss; k++) gauss[k] = Maxwell_Boltzmann_Distribution(0, 1);
-    rng_restore(rng0);
-
-    snprintf(path, sizeof(path), "%s_pre.snap", prefix);
-    sdmd_snap *s = sdmd_snap_open(path);
-    sdmd_snap_put_view(s, &view);
-    put_cbt_and_cells(s);
-    sdmd_snap_put(s, "gauss", "f8", gauss, n_gauss);
-    sdmd_snap_close(s);
-
-    int *renewAll = calloc(atomnum + 2, sizeof(int));
-    for (int i = 1; i <= atomnum; i++) renewAll[i] = i;
-    Predict(renewAll, &atomList);
-    free(renewAll);
-    CreateCBT();
-
-    sdmd_glue_gather_dynamic(&view);
-    snprintf(path, sizeof(path), "%s_post.snap", prefix);
-    s = sdmd_snap_open(path);
-    sdmd_snap_put_view(s, &view);
-    put_cbt_and_cells(s);
-    double epot = CalPotenE(), ekin = CalKinetE();
-    sdmd_snap_put(s, "epot", "f8", &epot, 1);
-    sdmd_snap_put(s, "ekin", "f8", &ekin, 1);
-    sdmd_snap_close(s);
-
-    /* ---- SingleThreadRun(), SGThread.c:67-156 ---- */
+/* SingleThreadRun(), SGThread.c:67-156, without file output / progress printing */
+static long run_loop(long max_iter, struct sdmd_trace_rec *trace, int printf_log) {
     int renewList[256] = {0};
     struct AtomListStr *thisList = &atomList;
     struct AtomStr *target, *partner;
-    struct sdmd_trace_rec *trace = calloc(max_iter > 0 ? max_iter : 1, sizeof(*trace));
     long iter = 0;
     while (currenttime <= timestep && iter < max_iter) {
         AssignJob(&target, &partner, renewList, thisList);
@@ -124,14 +65,17 @@ int main(int argc, const char *argv[]) {
         currenttime += thisList->timeInr;
         int hazard = HazardCheck(target, partner, thisList->ptr[target->dynamic->HB.neighbor],
                                  (partner != NULL ? thisList->ptr[partner->dynamic->HB.neighbor] : NULL), thisList);
-        struct sdmd_trace_rec *r = &trace[iter++];
-        r->frame = frame;
-        r->target = target->property->num;
-        r->partner = target->dynamic->event.partner;
-        r->type = target->dynamic->event.eventType;
-        r->sub = target->dynamic->event.subEventType;
-        r->dt = thisList->timeInr;
-        r->executed = !hazard;
+        if (trace) {
+            struct sdmd_trace_rec *r = &trace[iter];
+            r->frame = frame;
+            r->target = target->property->num;
+            r->partner = target->dynamic->event.partner;
+            r->type = target->dynamic->event.eventType;
+            r->sub = target->dynamic->event.subEventType;
+            r->dt = thisList->timeInr;
+            r->executed = !hazard;
+        }
+        iter++;
         if (printf_log)
             printf("frame = %4li, target atom = %5i, partner = %5i, %6s:%6s, type = %2i", frame, target->property->num,
                    target->dynamic->event.partner, target->property->name,
@@ -154,6 +98,94 @@ int main(int argc, const char *argv[]) {
             countReCal++;
         }
     }
+    return iter;
+}
+
+int main(int argc, const char *argv[]) {
+    if (argc < 5) {
+        fprintf(stderr, "usage: %s <out_prefix> <max_iter> <n_gauss> [--printf-log] -- <sDMD args>\n", argv[0]);
+        return 2;
+    }
+    const char *prefix = argv[1];
+    long max_iter = atol(argv[2]);
+    long n_gauss = atol(argv[3]);
+    int printf_log = 0, skip_sdmin = 0;
+    long warm = 0;
+    int a = 4;
+    for (; a < argc && strcmp(argv[a], "--"); a++) {
+        if (!strcmp(argv[a], "--printf-log")) printf_log = 1;
+        if (!strcmp(argv[a], "--no-sdmin")) skip_sdmin = 1;
+        if (!strcmp(argv[a], "--warm") && a + 1 < argc) warm = atol(argv[++a]);
+    }
+    if (a >= argc) { fprintf(stderr, "missing -- before sDMD args\n"); return 2; }
+    argv[a] = argv[0];
+    InputData(argc - a, argv + a);
+
+    char path[1024];
+    struct sdmd_host_view view;
+
+    /* ---- Prepare(), SGThread.c:21-64, minus file output ---- */
+    atomList.ptr = (struct AtomStr **)calloc(atomnum + 1, sizeof(struct AtomStr *));
+    for (int i = 1; i <= atomnum; i++) atomList.ptr[i] = &atom[i];
+#ifndef GEL
+    if (!skip_sdmin) SDEnergyMin(20000, &atomList);
+#endif
+    PBC("full", NULL, &atomList);
+    LinkList("full", NULL, NULL, &atomList);
+
+    if (warm > 0) {
+        /* run `warm` iterations first, then restart the bookkeeping from that state */
+        int *renewAll = calloc(atomnum + 2, sizeof(int));
+        for (int i = 1; i <= atomnum; i++) renewAll[i] = i;
+        Predict(renewAll, &atomList);
+        free(renewAll);
+        CreateCBT();
+        run_loop(warm, NULL, 0);
+        free(CBT.node); free(CBT.leaf); free(CBT.time);
+        CBT.node = NULL; CBT.leaf = NULL; CBT.count = 0;
+    }
+
+    int rc = sdmd_glue_flatten(&view);
+    if (rc) { fprintf(stderr, "flatten failed: %d\n", rc); return 1; }
+
+    /* pre-draw the gaussian stream with the reference's own generator, then rewind */
+    char rng0[128];
+    rng_save(rng0);
+    double *gauss = malloc(sizeof(double) * (n_gauss > 0 ? n_gauss : 1));
+    for (long k = 0; k < n_gauss; k++) gauss[k] = Maxwell_Boltzmann_Distribution(0, 1);
+    rng_restore(rng0);
+
+    int32_t warm_flag = warm > 0;
+    snprintf(path, sizeof(path), "%s_pre.snap", prefix);
+    sdmd_snap *s = sdmd_snap_open(path);
+    sdmd_snap_put_view(s, &view);
+    put_cbt_and_cells(s);
+    sdmd_snap_put(s, "gauss", "f8", gauss, n_gauss);
+    sdmd_snap_put(s, "warm", "i4", &warm_flag, 1);
+    sdmd_snap_close(s);
+
+    if (!warm) {
+        int *renewAll = calloc(atomnum + 2, sizeof(int));
+        for (int i = 1; i <= atomnum; i++) renewAll[i] = i;
+        Predict(renewAll, &atomList);
+        free(renewAll);
+    }
+    CreateCBT();
+
+    sdmd_glue_gather_dynamic(&view);
+    snprintf(path, sizeof(path), "%s_post.snap", prefix);
+    s = sdmd_snap_open(path);
+    sdmd_snap_put_view(s, &view);
+    put_cbt_and_cells(s);
+    double epot = CalPotenE(), ekin = CalKinetE();
+    sdmd_snap_put(s, "epot", "f8", &epot, 1);
+    sdmd_snap_put(s, "ekin", "f8", &ekin, 1);
+    sdmd_snap_close(s);
+
+    long frame0 = frame, recal0 = countReCal;
+    long base[6] = {collisioneventsum, bondeventsum, HBeventsum, HBNeighboreventsum, thermostateventsum, pbcandcrosseventsum};
+    struct sdmd_trace_rec *trace = calloc(max_iter > 0 ? max_iter : 1, sizeof(*trace));
+    long iter = run_loop(max_iter, trace, printf_log);
 
     sdmd_glue_gather_dynamic(&view);
     snprintf(path, sizeof(path), "%s_final.snap", prefix);
@@ -161,8 +193,9 @@ int main(int argc, const char *argv[]) {
     sdmd_snap_put_view(s, &view);
     put_cbt_and_cells(s);
     sdmd_snap_put(s, "trace", "u1", trace, (uint64_t)iter * sizeof(*trace));
-    int64_t stats[12] = {frame, iter, countReCal, collisioneventsum, bondeventsum, HBeventsum, HBNeighboreventsum,
-                         thermostateventsum, pbcandcrosseventsum, warningsum, 0, 0};
+    int64_t stats[12] = {frame, iter, countReCal - recal0, collisioneventsum - base[0], bondeventsum - base[1],
+                         HBeventsum - base[2], HBNeighboreventsum - base[3], thermostateventsum - base[4],
+                         pbcandcrosseventsum - base[5], warningsum, frame0, 0};
     sdmd_snap_put(s, "stats", "i8", stats, 12);
     epot = CalPotenE(); ekin = CalKinetE();
     sdmd_snap_put(s, "epot", "f8", &epot, 1);

@@ -1,0 +1,238 @@
+"""Host-side mirror of ``struct sdmd_host_view`` (include/sdmd_cuda.h) for Python callers.
+
+A :class:`HostView` owns numpy arrays laid out exactly as the C-ABI expects (1-based atoms, natom+1
+entries per per-atom array) and exposes a ctypes struct pointing into them.  It can be filled from a
+snapshot written by the reference glue (``sdmd_b200/host/sdmd_refglue.c``; format: ``SDMDSNP1`` tagged
+arrays) or from a synthetic generator (``sdmd_b200/synth.py``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import struct
+from pathlib import Path
+
+import numpy as np
+
+ABI_VERSION = 1
+NT = 33
+NHBCLASS = 12
+MAX_STEPS = 16
+INFINIT = 1e8
+INVALID = -111
+
+STEP_TABLE_DTYPE = np.dtype(
+    [("dmin2", "<f8"), ("dmax2", "<f8"), ("nstep", "<i4"), ("pad_", "<i4"),
+     ("d2", "<f8", (MAX_STEPS,)), ("e", "<f8", (MAX_STEPS,)), ("acc", "<f8", (MAX_STEPS,))]
+)
+assert STEP_TABLE_DTYPE.itemsize == 408
+
+TRACE_DTYPE = np.dtype(
+    [("frame", "<i8"), ("target", "<i4"), ("partner", "<i4"), ("type", "<i4"), ("sub", "<i4"),
+     ("executed", "<i4"), ("pad_", "<i4"), ("dt", "<f8")]
+)
+assert TRACE_DTYPE.itemsize == 40
+
+_P = C.POINTER
+
+
+class CHostView(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("natom", C.c_int32),
+        ("box", C.c_double * 3), ("cutoffr", C.c_double), ("thermoF", C.c_double),
+        ("target_temperature", C.c_double), ("currenttime", C.c_double), ("timestep", C.c_double),
+        ("thermostat_on", C.c_int32), ("method_ding", C.c_int32), ("hydrogen_bond", C.c_int32), ("gel_mode", C.c_int32),
+        ("frame", C.c_int64),
+        ("x", _P(C.c_double)), ("y", _P(C.c_double)), ("z", _P(C.c_double)),
+        ("vx", _P(C.c_double)), ("vy", _P(C.c_double)), ("vz", _P(C.c_double)),
+        ("mass", _P(C.c_double)), ("type", _P(C.c_int32)), ("aa_type", _P(C.c_int32)),
+        ("protein_num", _P(C.c_int32)), ("aa_num", _P(C.c_int32)), ("is_cons", _P(C.c_uint8)),
+        ("hb_bond", _P(C.c_int32)), ("hb_neighbor", _P(C.c_int32)), ("hb_role", _P(C.c_uint8)), ("hb_itype", _P(C.c_uint8)),
+        ("hbn_partner", _P(C.c_int32)), ("hbn_partner_num", _P(C.c_int32)), ("hbn_status", _P(C.c_int32)),
+        ("ev_time", _P(C.c_double)), ("ev_potential", _P(C.c_double)), ("ev_partner", _P(C.c_int32)),
+        ("ev_counter", _P(C.c_int64)), ("ev_pcounter", _P(C.c_int64)), ("ev_type", _P(C.c_uint8)), ("ev_sub", _P(C.c_uint8)),
+        ("cell_idx", _P(C.c_int32)),
+        ("bond_off", _P(C.c_int32)), ("bond_j", _P(C.c_int32)), ("bond_dmin2", _P(C.c_double)), ("bond_dmax2", _P(C.c_double)),
+        ("con_off", _P(C.c_int32)), ("con_j", _P(C.c_int32)), ("con_table", _P(C.c_int32)),
+        ("cm_off", _P(C.c_int32)), ("cm_j", _P(C.c_int32)), ("cm_flags", _P(C.c_int32)),
+        ("ntable", C.c_int32), ("tables", C.c_void_p),
+        ("coll_index", _P(C.c_int32)), ("hb_index", _P(C.c_int32)),
+        ("hb_barrier", C.c_double * 3),
+    ]
+
+
+class CRunStats(C.Structure):
+    _fields_ = [
+        ("frame", C.c_int64), ("iterations", C.c_int64), ("count_recal", C.c_int64),
+        ("collision", C.c_int64), ("bond", C.c_int64), ("hb", C.c_int64), ("hb_neighbor", C.c_int64),
+        ("thermostat", C.c_int64), ("pcc", C.c_int64), ("warnings", C.c_int64),
+        ("pair_predictions", C.c_int64), ("gaussians_used", C.c_int64),
+        ("currenttime", C.c_double), ("stop_reason", C.c_int32), ("error", C.c_int32),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class CRemdTemp(C.Structure):
+    _fields_ = [("num", C.c_int32), ("pad_", C.c_int32), ("T", C.c_double)]
+
+
+# (name, dtype, entries-per-atom or None for non per-atom)
+PER_ATOM = [
+    ("x", "f8", 1), ("y", "f8", 1), ("z", "f8", 1), ("vx", "f8", 1), ("vy", "f8", 1), ("vz", "f8", 1),
+    ("mass", "f8", 1), ("type", "i4", 1), ("aa_type", "i4", 1), ("protein_num", "i4", 1), ("aa_num", "i4", 1),
+    ("is_cons", "u1", 1), ("hb_bond", "i4", 1), ("hb_neighbor", "i4", 1), ("hb_role", "u1", 1), ("hb_itype", "u1", 1),
+    ("hbn_partner", "i4", 5), ("hbn_partner_num", "i4", 1), ("hbn_status", "i4", 1),
+    ("ev_time", "f8", 1), ("ev_potential", "f8", 1), ("ev_partner", "i4", 1), ("ev_counter", "i8", 1),
+    ("ev_pcounter", "i8", 1), ("ev_type", "u1", 1), ("ev_sub", "u1", 1), ("cell_idx", "i4", 3),
+]
+MUTABLE = ["x", "y", "z", "vx", "vy", "vz", "type", "hb_bond", "hb_itype", "hbn_partner", "hbn_partner_num",
+           "hbn_status", "ev_time", "ev_potential", "ev_partner", "ev_counter", "ev_pcounter", "ev_type", "ev_sub",
+           "cell_idx"]
+OTHER = [
+    ("bond_off", "i4"), ("bond_j", "i4"), ("bond_dmin2", "f8"), ("bond_dmax2", "f8"),
+    ("con_off", "i4"), ("con_j", "i4"), ("con_table", "i4"),
+    ("cm_off", "i4"), ("cm_j", "i4"), ("cm_flags", "i4"),
+    ("coll_index", "i4"), ("hb_index", "i4"),
+]
+_NP = {"f8": np.float64, "i4": np.int32, "i8": np.int64, "u1": np.uint8}
+_CT = {"f8": C.c_double, "i4": C.c_int32, "i8": C.c_int64, "u1": C.c_uint8}
+
+
+def read_snapshot(path) -> dict:
+    """Parse a ``SDMDSNP1`` file into {name: ndarray}."""
+    data = Path(path).read_bytes()
+    if data[:8] != b"SDMDSNP1":
+        raise ValueError(f"{path}: not a snapshot")
+    out, pos = {}, 8
+    while True:
+        name = data[pos:pos + 24].split(b"\0")[0].decode()
+        dt = data[pos + 24:pos + 32].split(b"\0")[0].decode()
+        (count,) = struct.unpack_from("<Q", data, pos + 32)
+        pos += 40
+        if name == "END":
+            break
+        nbytes = np.dtype(_NP[dt]).itemsize * count
+        out[name] = np.frombuffer(data, dtype=_NP[dt], count=count, offset=pos).copy()
+        pos += (nbytes + 7) // 8 * 8
+    return out
+
+
+class HostView:
+    """numpy-backed ``struct sdmd_host_view``."""
+
+    def __init__(self, natom: int):
+        self.natom = int(natom)
+        n1 = self.natom + 1
+        self.box = np.zeros(3)
+        self.cutoffr = 9.0
+        self.thermoF = 6.0
+        self.target_temperature = 0.6
+        self.currenttime = 0.0
+        self.timestep = 0.0
+        self.thermostat_on = 1
+        self.method_ding = 1
+        self.hydrogen_bond = 1
+        self.gel_mode = 0
+        self.frame = 0
+        self.hb_barrier = np.zeros(3)
+        for name, dt, k in PER_ATOM:
+            setattr(self, name, np.zeros(n1 * k, dtype=_NP[dt]))
+        for name in ("bond_off", "con_off", "cm_off"):
+            setattr(self, name, np.zeros(n1 + 1, dtype=np.int32))
+        for name, dt in OTHER:
+            if not hasattr(self, name):
+                setattr(self, name, np.zeros(1, dtype=_NP[dt]))
+        self.coll_index = np.full(NT * NT, -1, dtype=np.int32)
+        self.hb_index = np.full(NHBCLASS * NT * NT, -1, dtype=np.int32)
+        self.tables = np.zeros(0, dtype=STEP_TABLE_DTYPE)
+        self.extra = {}
+        self._c = None
+
+    # ------------------------------------------------------------------
+    @classmethod
+    def from_arrays(cls, d: dict) -> "HostView":
+        si, sf = d["scalars_i4"], d["scalars_f8"]
+        hv = cls(int(si[1]))
+        hv.thermostat_on, hv.method_ding, hv.hydrogen_bond, hv.gel_mode = (int(v) for v in si[2:6])
+        hv.box = sf[0:3].copy()
+        hv.cutoffr, hv.thermoF, hv.target_temperature, hv.currenttime, hv.timestep = (float(v) for v in sf[3:8])
+        hv.hb_barrier = sf[8:11].copy()
+        hv.frame = int(d["scalars_i8"][0])
+        for name, dt, _ in PER_ATOM:
+            setattr(hv, name, np.ascontiguousarray(d[name], dtype=_NP[dt]).copy())
+        for name, dt in OTHER:
+            arr = np.ascontiguousarray(d[name], dtype=_NP[dt]).copy()
+            setattr(hv, name, arr if arr.size else np.zeros(1, dtype=_NP[dt]))
+        hv.tables = np.frombuffer(d["tables"].tobytes(), dtype=STEP_TABLE_DTYPE).copy()
+        known = {n for n, _, _ in PER_ATOM} | {n for n, _ in OTHER} | {"scalars_i4", "scalars_f8", "scalars_i8", "tables"}
+        hv.extra = {k: v for k, v in d.items() if k not in known}
+        return hv
+
+    @classmethod
+    def from_snapshot(cls, path) -> "HostView":
+        p = Path(path)
+        if p.suffix == ".npz":
+            with np.load(p) as z:
+                return cls.from_arrays({k: z[k] for k in z.files})
+        return cls.from_arrays(read_snapshot(p))
+
+    def to_arrays(self) -> dict:
+        d = {
+            "scalars_i4": np.array([ABI_VERSION, self.natom, self.thermostat_on, self.method_ding, self.hydrogen_bond,
+                                    self.gel_mode, len(self.tables), 0], dtype=np.int32),
+            "scalars_f8": np.array([*self.box, self.cutoffr, self.thermoF, self.target_temperature, self.currenttime,
+                                    self.timestep, *self.hb_barrier, 0.0]),
+            "scalars_i8": np.array([self.frame], dtype=np.int64),
+            "tables": np.frombuffer(self.tables.tobytes(), dtype=np.uint8),
+        }
+        for name, _, _ in PER_ATOM:
+            d[name] = getattr(self, name)
+        for name, _ in OTHER:
+            d[name] = getattr(self, name)
+        d.update(self.extra)
+        return d
+
+    def copy(self) -> "HostView":
+        return HostView.from_arrays({k: np.array(v, copy=True) for k, v in self.to_arrays().items()})
+
+    def reset_slots(self):
+        """Event slots as the reference leaves them after calloc (Initialization.c:1012-1017)."""
+        for name in ("ev_time", "ev_potential", "ev_partner", "ev_counter", "ev_pcounter", "ev_type", "ev_sub"):
+            getattr(self, name)[:] = 0
+
+    # ------------------------------------------------------------------
+    def cstruct(self) -> CHostView:
+        """(Re)build the ctypes struct; pointers alias the numpy arrays (keep ``self`` alive)."""
+        c = CHostView()
+        c.abi_version = ABI_VERSION
+        c.natom = self.natom
+        c.box[:] = [float(v) for v in self.box]
+        c.cutoffr, c.thermoF = float(self.cutoffr), float(self.thermoF)
+        c.target_temperature, c.currenttime, c.timestep = float(self.target_temperature), float(self.currenttime), float(self.timestep)
+        c.thermostat_on, c.method_ding = int(self.thermostat_on), int(self.method_ding)
+        c.hydrogen_bond, c.gel_mode = int(self.hydrogen_bond), int(self.gel_mode)
+        c.frame = int(self.frame)
+        c.hb_barrier[:] = [float(v) for v in self.hb_barrier]
+        for name, dt, _ in PER_ATOM:
+            arr = getattr(self, name)
+            assert arr.flags["C_CONTIGUOUS"] and arr.dtype == _NP[dt], name
+            setattr(c, name, arr.ctypes.data_as(_P(_CT[dt])))
+        for name, dt in OTHER:
+            arr = getattr(self, name)
+            assert arr.flags["C_CONTIGUOUS"] and arr.dtype == _NP[dt], name
+            setattr(c, name, arr.ctypes.data_as(_P(_CT[dt])))
+        c.ntable = len(self.tables)
+        c.tables = self.tables.ctypes.data if len(self.tables) else None
+        self._c = c
+        return c
+
+    def sync_scalars_from_c(self):
+        if self._c is not None:
+            self.currenttime = self._c.currenttime
+            self.frame = self._c.frame
+            self.target_temperature = self._c.target_temperature
+
+    def slots(self) -> dict:
+        return {k: getattr(self, k).copy() for k in
+                ("ev_time", "ev_potential", "ev_partner", "ev_pcounter", "ev_counter", "ev_type", "ev_sub")}

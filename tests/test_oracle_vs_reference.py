@@ -1,0 +1,108 @@
+"""CPU: pin the oracle restatement (oracle/sdmd_oracle.c) against dumps of the unmodified reference.
+
+The committed fixtures under tests/golden/ were produced by oracle/make_golden.py from the reference
+itself (oracle/_ref/ref_harness).  When the compiled reference is present the longest case is also
+re-generated on this machine and compared, so the pin does not depend on the fixtures alone.
+"""
+import numpy as np
+import pytest
+
+from oracle.oracle_py import Oracle, remd_rearrange
+from tests.util import (REFDIR, SLOT_FIELDS, STATE_FIELDS, assert_fields_equal, assert_trace_equal, bits_equal,
+                        load_case, ref_trace)
+
+
+def _prepare(pre):
+    hv = pre.copy()
+    o = Oracle(hv)
+    o.rng_feed(pre.extra["gauss"])
+    return hv, o
+
+
+@pytest.mark.parametrize("case", ["ala10", "gel10"])
+def test_cell_grid_and_link_list(case):
+    pre, post, fin = load_case(case)
+    hv, o = _prepare(pre)
+    assert np.array_equal(o.cellnum, pre.extra["cellnum"])
+    assert bits_equal(o.cellsize, pre.extra["cellsize"])
+    hv.cell_idx[:] = 0
+    o.pbc_full()
+    o.cell_build()
+    assert np.array_equal(o.celllist(), pre.extra["celllist"])
+    assert_fields_equal(hv, pre, ("cell_idx", "x", "y", "z"))
+
+
+@pytest.mark.parametrize("case", ["ala10", "gel10"])
+def test_predict_all_and_cbt(case):
+    pre, post, fin = load_case(case)
+    hv, o = _prepare(pre)
+    o.set_celllist(pre.extra["celllist"])
+    o.predict_all()
+    assert_fields_equal(hv, post, SLOT_FIELDS, what="after Predict(all): ")
+    o.cbt_build()
+    node, leaf = o.cbt()
+    assert np.array_equal(node[1:], post.extra["cbt_node"][1:])
+    assert np.array_equal(leaf[1:], post.extra["cbt_leaf"][1:])
+    assert o.potential_energy() == post.extra["epot"][0]
+    assert o.kinetic_energy() == post.extra["ekin"][0]
+
+
+@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10"])
+def test_event_loop_trace(case):
+    pre, post, fin = load_case(case)
+    hv, o = _prepare(pre)
+    o.set_celllist(pre.extra["celllist"])
+    if not int(pre.extra.get("warm", [0])[0]):
+        o.predict_all()
+    o.cbt_build()
+    want = ref_trace(fin)
+    st, tr = o.run(max_iter=len(want), trace_cap=len(want))
+    assert st["error"] == 0
+    assert_trace_equal(tr, want)
+    assert_fields_equal(hv, fin, STATE_FIELDS, what="final state: ")
+    assert np.array_equal(o.celllist(), fin.extra["celllist"])
+    assert np.array_equal(o.cbt()[0][1:], fin.extra["cbt_node"][1:])
+    ref = fin.extra["stats"]
+    got = [st[k] for k in ("frame", "iterations", "count_recal", "collision", "bond", "hb", "hb_neighbor", "thermostat", "pcc")]
+    got[0] = st["frame"]  # absolute frame counter
+    assert got == [int(v) for v in ref[:9]]
+    assert o.potential_energy() == fin.extra["epot"][0]
+    if case == "ala10_hb":
+        assert st["hb"] > 0 and st["hb_neighbor"] > 0  # the fixture really exercises the HB paths
+
+
+@pytest.mark.refbin
+def test_long_run_against_live_reference(tmp_path):
+    """300k iterations of ala10 regenerated with the reference binary on this machine."""
+    if not (REFDIR / "ref_harness").exists():
+        pytest.skip("oracle/_ref/ref_harness not built (needs /root/reference at build time)")
+    from oracle.make_golden import run_case
+    from sdmd_b200.hostview import HostView
+    snaps = run_case("ala10_live", tmp_path, harness="ref_harness", coord="ala10.gro", max_iter=300000, n_gauss=600000,
+                     extra=[], gel_n=0)
+    pre, post, fin = (HostView.from_snapshot(p) for p in snaps)
+    hv, o = _prepare(pre)
+    o.set_celllist(pre.extra["celllist"])
+    o.predict_all()
+    o.cbt_build()
+    want = ref_trace(fin)
+    st, tr = o.run(max_iter=len(want), trace_cap=len(want))
+    assert_trace_equal(tr, want)
+    assert_fields_equal(hv, fin, STATE_FIELDS)
+    assert st["hb"] > 0
+
+
+def test_remd_rearrange_rule():
+    """Server.c:145-192: sequential, order dependent, pair (1,2) tried from both sides (hand-computed cases)."""
+    # i=0 (num 1) meets num 2: dE=(2-1/.6)(-20+10)<0 -> swap.  i=1 (now num 1) meets j=0 (num 2): dE=+3.33 -> one
+    # draw, 0.99 > exp(-3.33) -> reject.  i=2 (num 3) meets j=0 (num 2): dE=(1/.7-1/.6)(-10+30)<0 -> swap.
+    nums, temps, used, att, acc = remd_rearrange([-10.0, -20.0, -30.0], [1, 2, 3], [0.5, 0.6, 0.7], [0.99] * 8)
+    assert used == 1
+    assert nums == [3, 1, 2] and temps == [0.7, 0.5, 0.6]
+    assert att[:2] == [2.0, 1.0] and acc[:2] == [1.0, 1.0]
+    # same start, but the draw is small enough to accept the reverse swap
+    nums2, temps2, used2, _, _ = remd_rearrange([-10.0, -20.0], [1, 2], [0.5, 0.6], [0.01, 0.99])
+    assert used2 == 1 and nums2 == [1, 2] and temps2 == [0.5, 0.6]
+    # a finished replica (T == 0) is skipped entirely
+    nums3, _, used3, _, _ = remd_rearrange([-10.0, 0.0, -30.0], [1, 2, 3], [0.5, 0.0, 0.7], [0.5])
+    assert nums3 == [1, 2, 3] and used3 == 0
