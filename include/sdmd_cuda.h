@@ -195,9 +195,14 @@ int  sdmd_cuda_cell_grid(const sdmd_ctx *ctx, int cellnum[3], double cellsize[3]
 /* positions / velocities only: natom+1 doubles each, entry 0 ignored */
 int  sdmd_cuda_upload_coords(sdmd_ctx *ctx, const double *x, const double *y, const double *z,
                              const double *vx, const double *vy, const double *vz);
+/* restore a saved link list (celllist[natom + ncell + 1]); the resume path of ReadBreakPoint,
+ * Initialization.c:360-509, where the list order inside a cell is part of the state */
+int  sdmd_cuda_upload_celllist(sdmd_ctx *ctx, const int32_t *celllist);
 /* refresh every mutable per-atom array of `view` from the device (what SaveData/DoEvent need,
  * SURVEY 8b "sync_to_host"); arrays that are NULL in `view` are skipped */
 int  sdmd_cuda_download(sdmd_ctx *ctx, struct sdmd_host_view *view);
+/* event slots only (any pointer may be NULL); natom+1 entries each */
+int  sdmd_cuda_download_slots(sdmd_ctx *ctx, double *time, double *potential, int32_t *partner, uint8_t *type, uint8_t *sub);
 /* reference-format link list: celllist[natom + ncell + 1] (Events.c:125,152-153) */
 int  sdmd_cuda_download_celllist(sdmd_ctx *ctx, int32_t *celllist);
 /* CBT.node[2*natom], CBT.leaf[natom+1] (CBT.c:16-30) */
@@ -232,6 +237,8 @@ int  sdmd_cuda_cbt_update(sdmd_ctx *ctx, const int32_t *renew_list);
 int  sdmd_cuda_assign_job(sdmd_ctx *ctx, int32_t *target, int32_t *partner, double *dt, int32_t *renew_list);
 /* UpdateData + TimeForward, ToolFunctions.c:23-36 (one fused sweep) */
 int  sdmd_cuda_advance(sdmd_ctx *ctx, double dt);
+/* currenttime += timeInr, SGThread.c:80 (for callers that drive the loop one call at a time) */
+int  sdmd_cuda_add_time(sdmd_ctx *ctx, double dt);
 /* HazardCheck SGThread.c:215-235; *hazard = 0 ok / -1 denied */
 int  sdmd_cuda_hazard_check(sdmd_ctx *ctx, int32_t target, int32_t partner, int32_t *hazard);
 /* PBCandCrossCellEvent Events.c:248-272 = PBC("part") + LinkList("part") for one atom */
@@ -265,14 +272,22 @@ int  sdmd_remd_rearrange(double *epot, struct sdmd_remd_temp *T, int nrep,
  * ncclUniqueId produced by rank 0 (sdmd_remd_nccl_unique_id) and distributed by the launcher. */
 int  sdmd_remd_nccl_unique_id(unsigned char id[128]);
 int  sdmd_remd_nccl_init(sdmd_ctx *ctx, int nranks, int rank, const unsigned char id[128]);
+/* srand(seed) of sServer (Server.c:57-58): seeds the replicated glibc rand() stream every rank advances
+ * identically during the exchange sweep */
+int  sdmd_remd_seed_server(sdmd_ctx *ctx, uint32_t seed);
 /* ReplicaExchange: all-gather (E, T, num) of every rank over NCCL, run the replicated sweep with the
  * shared server seed stream, return this rank's new (T, num). */
-int  sdmd_remd_exchange(sdmd_ctx *ctx, double epot, struct sdmd_remd_temp *T, uint32_t server_seed_step);
+int  sdmd_remd_exchange(sdmd_ctx *ctx, double epot, struct sdmd_remd_temp *T, uint32_t reserved);
 
 /* ---- measurement helpers ------------------------------------------------------------------------- */
 /* average device time (ms) of the last launch of each named kernel, measured with CUDA events on the
  * context's stream; name in {"advance","predict_all","cell_build","cbt_build"}; <0 if never launched */
 double sdmd_cuda_kernel_ms(const sdmd_ctx *ctx, const char *name);
+/* accumulated device time and launch count of a named kernel group since the last reset:
+ * "advance", "predict_all" (round 0), "predict_all_fixup", "cell_build", "cbt_build", "run" */
+int  sdmd_cuda_kernel_stats(const sdmd_ctx *ctx, const char *name, double *total_ms, int64_t *count);
+void sdmd_cuda_reset_kernel_stats(sdmd_ctx *ctx);
+void sdmd_cuda_set_timing(sdmd_ctx *ctx, int on);   /* per-call CUDA-event timing (synchronises); default on */
 int64_t sdmd_cuda_launch_count(const sdmd_ctx *ctx);
 void *sdmd_cuda_stream(const sdmd_ctx *ctx);   /* cudaStream_t */
 

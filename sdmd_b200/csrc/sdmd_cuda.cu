@@ -1,0 +1,1236 @@
+// sdmd_cuda.cu — kernels and C-ABI of libsdmd_cuda.so (sm_100a).  See include/sdmd_cuda.h.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo -O3 -shared -Xcompiler -fPIC
+// There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include <dlfcn.h>
+#include "sdmd_dev.cuh"
+
+// ===================================================================================================
+// host context
+// ===================================================================================================
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char *what, cudaError_t e = cudaSuccess) {
+    if (e != cudaSuccess) snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(g_err, sizeof(g_err), "%s", what);
+    return code;
+}
+#define CK(call)                                                                  \
+    do {                                                                          \
+        cudaError_t e_ = (call);                                                  \
+        if (e_ != cudaSuccess) return set_err(SDMD_ERR_CUDA, #call, e_);          \
+    } while (0)
+
+struct KStat { double ms = 0; long n = 0; };
+
+struct sdmd_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DevP P;
+    Ctl *d_ctl = nullptr;
+    Ctl *h_ctl = nullptr;  // pinned
+    std::vector<void *> bufs;
+    int n = 0;
+    // scratch for predict_all / cell_build
+    double *b_time = nullptr, *b_pot = nullptr, *c_time = nullptr, *c_pot = nullptr;
+    int *b_partner = nullptr, *c_partner = nullptr;
+    i64 *b_pcounter = nullptr, *c_pcounter = nullptr;
+    uint8_t *b_type = nullptr, *b_sub = nullptr, *c_type = nullptr, *c_sub = nullptr;
+    uint8_t *flag_cur = nullptr, *flag_next = nullptr;
+    int *npair = nullptr;
+    int *cell_of = nullptr, *cell_count = nullptr, *cell_cursor = nullptr, *scan_tmp = nullptr;
+    int *d_cell_start = nullptr, *d_sorted_atom = nullptr;
+    double *d_sx = nullptr, *d_sy = nullptr, *d_sz = nullptr, *d_svx = nullptr, *d_svy = nullptr, *d_svz = nullptr;
+    int *d_stype = nullptr;
+    int *d_leaf_atom = nullptr;  // static leaf permutation of the tournament tree
+    double *d_gauss = nullptr;
+    i64 g_filled = 0;
+    sdmd_trace_rec *d_trace = nullptr;
+    i64 trace_cap = 0;
+    unsigned long long *d_sum = nullptr;
+    bool cells_fresh = false;
+    bool timing = true;
+    std::map<std::string, KStat> kstat;
+    long launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // big-N event loop graph
+    cudaGraphExec_t loop_graph = nullptr;
+    int loop_graph_len = 0;
+    // NCCL
+    void *nccl_lib = nullptr;
+    void *nccl_comm = nullptr;
+    int nranks = 1, rank = 0;
+    void *d_xchg = nullptr;
+};
+
+template <typename T>
+static int dalloc(sdmd_ctx *c, T **p, size_t count) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
+    if (e != cudaSuccess) return set_err(SDMD_ERR_CUDA, "cudaMalloc", e);
+    e = cudaMemsetAsync(q, 0, (count ? count : 1) * sizeof(T), c->stream);
+    if (e != cudaSuccess) return set_err(SDMD_ERR_CUDA, "cudaMemset", e);
+    c->bufs.push_back(q);
+    *p = (T *)q;
+    return 0;
+}
+template <typename T>
+static int dupload(sdmd_ctx *c, T **p, const T *src, size_t count) {
+    int rc = dalloc(c, p, count);
+    if (rc) return rc;
+    if (src && count) CK(cudaMemcpyAsync(*p, src, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+#define TRY(x)              \
+    do {                    \
+        int rc_ = (x);      \
+        if (rc_) return rc_; \
+    } while (0)
+
+struct Timer {
+    sdmd_ctx *c;
+    const char *name;
+    Timer(sdmd_ctx *c_, const char *n) : c(c_), name(n) {
+        if (c->timing) cudaEventRecord(c->ev0, c->stream);
+    }
+    ~Timer() {
+        if (c->timing) {
+            cudaEventRecord(c->ev1, c->stream);
+            cudaEventSynchronize(c->ev1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+            KStat &k = c->kstat[name];
+            k.ms += ms;
+            k.n++;
+        }
+    }
+};
+
+// ===================================================================================================
+// kernels: cell list (K1)
+// ===================================================================================================
+// PBC("full"), Events.c:218-228
+__global__ void k_pbc_full(DevP D) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i > D.n) return;
+    double c[3] = {D.x[i], D.y[i], D.z[i]};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (c[k] >= D.box[k]) c[k] -= D.box[k];
+        else if (c[k] < 0) c[k] += D.box[k];
+    }
+    D.x[i] = c[0]; D.y[i] = c[1]; D.z[i] = c[2];
+}
+
+// LinkList("full") step 1, Events.c:129-150: cell index per atom + histogram
+__global__ void k_cell_index(DevP D, int *cell_of, int *cell_count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i > D.n) return;
+    int idx[3];
+    int cell = d_cell_of(D, D.x[i], D.y[i], D.z[i], idx);
+    D.cell_idx[3 * i] = idx[0]; D.cell_idx[3 * i + 1] = idx[1]; D.cell_idx[3 * i + 2] = idx[2];
+    cell_of[i] = cell;
+    atomicAdd(&cell_count[cell], 1);
+}
+
+// exclusive scan of cell_count[0..m) -> cell_start[0..m], three passes, 2048 items per block
+#define SCAN_ITEMS 2048
+__global__ void k_scan_local(const int *in, int *out, int *block_sum, int m) {
+    __shared__ int s[SCAN_ITEMS];
+    int base = blockIdx.x * SCAN_ITEMS;
+    for (int t = threadIdx.x; t < SCAN_ITEMS; t += blockDim.x) s[t] = (base + t < m) ? in[base + t] : 0;
+    __syncthreads();
+    // Hillis-Steele inclusive scan in shared memory (double buffered through registers)
+    for (int off = 1; off < SCAN_ITEMS; off <<= 1) {
+        int v[SCAN_ITEMS / 512];
+        for (int q = 0, t = threadIdx.x; t < SCAN_ITEMS; t += blockDim.x, q++) v[q] = (t >= off) ? s[t - off] : 0;
+        __syncthreads();
+        for (int q = 0, t = threadIdx.x; t < SCAN_ITEMS; t += blockDim.x, q++) s[t] += v[q];
+        __syncthreads();
+    }
+    for (int t = threadIdx.x; t < SCAN_ITEMS; t += blockDim.x)
+        if (base + t < m) out[base + t] = s[t] - in[base + t];  // exclusive
+    if (threadIdx.x == 0) block_sum[blockIdx.x] = s[SCAN_ITEMS - 1];
+}
+__global__ void k_scan_blocks(int *block_sum, int nb) {
+    // single thread block; nb is small (<= a few thousand)
+    __shared__ int carry;
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < nb; b++) { int v = block_sum[b]; block_sum[b] = acc; acc += v; }
+        carry = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) block_sum[nb] = carry;
+}
+__global__ void k_scan_add(int *out, const int *block_sum, int m, int nb) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < m) out[t] += block_sum[t / SCAN_ITEMS];
+    if (t == 0) out[m] = block_sum[nb];
+}
+
+__global__ void k_cell_scatter(DevP D, const int *cell_of, int *cursor, int *sorted_atom) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i > D.n) return;
+    int pos = atomicAdd(&cursor[cell_of[i]], 1);
+    sorted_atom[pos] = i;
+}
+
+// per cell: order the segment by descending atom id (= the reference's head-insertion order of a fresh
+// LinkList("full"), Events.c:152-153) and emit the reference-format link list
+__global__ void k_cell_finish(DevP D, const int *cell_start, int *sorted_atom) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= D.ncell) return;
+    int p0 = cell_start[c], p1 = cell_start[c + 1];
+    for (int a = p0 + 1; a < p1; a++) {  // insertion sort, segments are short
+        int v = sorted_atom[a];
+        int b = a - 1;
+        while (b >= p0 && sorted_atom[b] < v) { sorted_atom[b + 1] = sorted_atom[b]; b--; }
+        sorted_atom[b + 1] = v;
+    }
+    int *cl = D.celllist;
+    cl[D.n + c + 1] = (p1 > p0) ? sorted_atom[p0] : 0;
+    for (int a = p0; a < p1; a++) cl[sorted_atom[a]] = (a + 1 < p1) ? sorted_atom[a + 1] : 0;
+}
+
+// cell-sorted SoA copies for the full-system prediction pass
+__global__ void k_cell_permute(DevP D, const int *sorted_atom, double *sx, double *sy, double *sz, double *svx, double *svy,
+                               double *svz, int *stype) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= D.n) return;
+    int j = sorted_atom[p];
+    sx[p] = D.x[j]; sy[p] = D.y[j]; sz[p] = D.z[j];
+    svx[p] = D.vx[j]; svy[p] = D.vy[j]; svz[p] = D.vz[j];
+    stype[p] = D.type[j];
+}
+
+// ===================================================================================================
+// kernels: full-system prediction (K2)
+// ===================================================================================================
+struct SlotBuf {
+    double *time, *pot;
+    int *partner;
+    i64 *pcounter;
+    uint8_t *type, *sub;
+};
+__device__ __forceinline__ SlotSrc as_src(const SlotBuf &b) {
+    SlotSrc S;
+    S.time = b.time; S.pot = b.pot; S.partner = b.partner; S.pcounter = b.pcounter; S.type = b.type; S.sub = b.sub;
+    return S;
+}
+
+// One relaxation round of the sequential pass `for i in 1..N: slot(i) = F(i, slot(j<i))`
+// (SGThread.c:47-52 + CheckDuplication TimePrediction.c:1101-1117).  Round 0 evaluates every atom with
+// no duplicate source; later rounds re-evaluate only flagged atoms against the previous round's slots of
+// lower-index atoms.  The stale fields of a slot (potential / subEventType / partnerCounter survive
+// ResetTarget) always start from the live arrays, which this pass never writes until the final commit.
+__global__ void __launch_bounds__(128) k_predict_all_round(DevP D, SlotBuf src, SlotBuf dst, const uint8_t *flags, int round, int *npair,
+                                                           i64 g_base) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= D.n) return;
+    int i = D.sorted_atom[p];
+    if (round > 0 && !flags[i]) return;
+    Slot cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
+    double g = 0;
+    if (D.thermostat_on && !D.is_cons[i]) g = D.gauss[(g_base + D.ther_rank[i]) % D.g_cap];
+    int np = 0;
+    cur = d_predict_atom<true>(D, as_src(src), i, cur, g, round == 0 ? 0 : i, &np);
+    dst.time[i] = cur.time; dst.pot[i] = cur.pot; dst.partner[i] = cur.partner; dst.pcounter[i] = cur.pcounter;
+    dst.type[i] = (uint8_t)cur.type; dst.sub[i] = (uint8_t)cur.sub;
+    npair[i] = np;
+}
+
+// after round 0: an atom must be re-evaluated iff a lower-index atom's slot points at it
+__global__ void k_predict_all_flag0(DevP D, SlotBuf b, uint8_t *flags) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (j > D.n) return;
+    int k = b.partner[j];
+    if (k > j) flags[k] = 1;
+}
+
+// commit round r: move re-evaluated slots into the current buffer, flag dependants of changed slots
+__global__ void k_predict_all_commit(DevP D, SlotBuf cur, SlotBuf nxt, const uint8_t *flags, uint8_t *flags_next) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i > D.n || !flags[i]) return;
+    bool same = __double_as_longlong(cur.time[i]) == __double_as_longlong(nxt.time[i]) &&
+                __double_as_longlong(cur.pot[i]) == __double_as_longlong(nxt.pot[i]) && cur.partner[i] == nxt.partner[i] &&
+                cur.pcounter[i] == nxt.pcounter[i] && cur.type[i] == nxt.type[i] && cur.sub[i] == nxt.sub[i];
+    if (same) return;
+    int oldp = cur.partner[i], newp = nxt.partner[i];
+    cur.time[i] = nxt.time[i]; cur.pot[i] = nxt.pot[i]; cur.partner[i] = newp; cur.pcounter[i] = nxt.pcounter[i];
+    cur.type[i] = nxt.type[i]; cur.sub[i] = nxt.sub[i];
+    if (oldp > i) flags_next[oldp] = 1;
+    if (newp > i) flags_next[newp] = 1;
+    D.ctl->changed = 1;
+}
+
+__global__ void k_predict_all_final(DevP D, SlotBuf b, const int *npair, unsigned long long *sum) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    unsigned long long v = 0;
+    if (i <= D.n) {
+        D.ev_time[i] = b.time[i]; D.ev_pot[i] = b.pot[i]; D.ev_partner[i] = b.partner[i]; D.ev_pcounter[i] = b.pcounter[i];
+        D.ev_type[i] = b.type[i]; D.ev_sub[i] = b.sub[i];
+        v = (unsigned long long)npair[i];
+    }
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(sum, v);
+}
+
+// ===================================================================================================
+// kernels: tournament tree (K5), advance (K4)
+// ===================================================================================================
+__global__ void k_cbt_leaves(DevP D, const int *leaf_atom) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= D.n) return;
+    int a = leaf_atom[k];
+    int pos = (D.n == 1) ? 1 : D.n + k;
+    D.cbt_node[pos] = a;
+    D.cbt_leaf[a] = pos;
+}
+// internal nodes [lo, hi) of one tree level: winner = t[left] < t[right] ? left : right (CBT.c:62-67)
+__global__ void k_cbt_level(DevP D, int lo, int hi) {
+    int f = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= hi) return;
+    int l = D.cbt_node[2 * f], r = D.cbt_node[2 * f + 1];
+    D.cbt_node[f] = (D.ev_time[l] < D.ev_time[r]) ? l : r;
+}
+
+// UpdateData + TimeForward fused, ToolFunctions.c:23-36: 56 B read + 32 B written per atom
+__global__ void __launch_bounds__(256) k_advance(DevP D, double dt_arg, int use_ctl) {
+    if (use_ctl && D.ctl->stop) return;
+    double dt = use_ctl ? D.ctl->dt : dt_arg;
+    int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x + 1; i <= D.n; i += stride) {
+        double x = D.x[i], y = D.y[i], z = D.z[i];
+        double vx = D.vx[i], vy = D.vy[i], vz = D.vz[i];
+        double t = D.ev_time[i];
+        D.x[i] = x + vx * dt;
+        D.y[i] = y + vy * dt;
+        D.z[i] = z + vz * dt;
+        D.ev_time[i] = t - dt;
+    }
+}
+
+// ===================================================================================================
+// kernels: event loop
+// ===================================================================================================
+// loop head: stop conditions + AssignJob (SGThread.c:75,237-259); single thread
+__device__ inline void d_loop_head(const DevP &D, double t_until, i64 iter_limit) {
+    Ctl *c = D.ctl;
+    if (c->stop) return;
+    if (c->error) { c->stop = 1 + SDMD_STOP_ERROR; return; }
+    if (!(c->currenttime <= c->timestep)) { c->stop = 1 + SDMD_STOP_TIME_END; return; }
+    if (c->iterations >= iter_limit) { c->stop = 1 + SDMD_STOP_MAX_ITER; return; }
+    if (D.thermostat_on && c->g_filled - c->g_pos < 16) { c->stop = 1 + SDMD_STOP_NEED_RNG; return; }
+    int target = D.cbt_node[1];
+    c->target = target;
+    c->dt = D.ev_time[target];
+    int p = D.ev_partner[target];
+    c->partner = p > 0 ? p : 0;
+}
+
+// loop body after the advance: HazardCheck, DoEvent, counters, Predict, UpdateCBT (SGThread.c:80-151)
+__device__ inline void d_loop_body_serial(const DevP &D, double t_until, sdmd_trace_rec *trace, i64 trace_cap) {
+    Ctl *c = D.ctl;
+    int target = c->target, partner = c->partner;
+    c->currenttime += c->dt;
+    int hazard = (partner > 0 && D.ev_pcounter[target] < D.ev_counter[partner]) ? -1 : 0;  // SGThread.c:224-227
+    if (trace && c->trace_pos < trace_cap) {
+        sdmd_trace_rec r;
+        r.frame = c->frame; r.target = target; r.partner = D.ev_partner[target];
+        r.type = D.ev_type[target]; r.sub = D.ev_sub[target]; r.executed = !hazard; r.pad_ = 0; r.dt = c->dt;
+        trace[c->trace_pos] = r;
+    }
+    c->trace_pos++;
+    c->iterations++;
+    if (!hazard) {
+        c->frame++;
+        d_do_event(D, target, partner);
+        D.ev_counter[target]++;
+        if (partner && !D.is_cons[partner]) D.ev_counter[partner]++;
+        d_predict_list_serial(D, target, partner);
+        d_cbt_update_run(D, target);
+        if (partner) d_cbt_update_run(D, partner);
+        if (c->currenttime >= t_until) c->stop = 1 + SDMD_STOP_T_UNTIL;
+    } else {
+        d_predict_list_serial(D, target, 0);
+        d_cbt_update_run(D, target);
+        c->count_recal++;
+    }
+}
+
+// Small systems: the whole loop in ONE persistent CTA (one replica per CTA); no host round trip per event.
+__global__ void __launch_bounds__(256) k_run_cta(DevP D, double t_until, i64 iter_limit, sdmd_trace_rec *trace, i64 trace_cap) {
+    __shared__ double s_dt;
+    __shared__ int s_stop;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            d_loop_head(D, t_until, iter_limit);
+            s_dt = D.ctl->dt;
+            s_stop = D.ctl->stop;
+        }
+        __syncthreads();
+        if (s_stop) break;
+        double dt = s_dt;
+        for (int i = threadIdx.x + 1; i <= D.n; i += blockDim.x) {
+            D.x[i] = D.x[i] + D.vx[i] * dt;
+            D.y[i] = D.y[i] + D.vy[i] * dt;
+            D.z[i] = D.z[i] + D.vz[i] * dt;
+            D.ev_time[i] = D.ev_time[i] - dt;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) d_loop_body_serial(D, t_until, trace, trace_cap);
+        __syncthreads();
+    }
+}
+
+// Large systems: per event one grid-wide advance (k_advance with use_ctl) and this single-CTA kernel,
+// which finishes event k and performs AssignJob for event k+1.
+__global__ void k_event_exec(DevP D, double t_until, i64 iter_limit, sdmd_trace_rec *trace, i64 trace_cap) {
+    if (threadIdx.x == 0 && !D.ctl->stop) {
+        d_loop_body_serial(D, t_until, trace, trace_cap);
+        d_loop_head(D, t_until, iter_limit);
+    }
+}
+__global__ void k_loop_head(DevP D, double t_until, i64 iter_limit) { d_loop_head(D, t_until, iter_limit); }
+
+// ---- single-step kernels behind the per-function C-ABI ----
+__global__ void k_predict_list(DevP D, int a0, int a1) { d_predict_list_serial(D, a0, a1); }
+__global__ void k_cbt_update(DevP D, int a0, int a1) {
+    if (a0 > 0) d_cbt_update_run(D, a0);
+    if (a1 > 0) d_cbt_update_run(D, a1);
+}
+__global__ void k_assign_job(DevP D) {
+    Ctl *c = D.ctl;
+    int target = D.cbt_node[1];
+    c->target = target;
+    c->dt = D.ev_time[target];
+    int p = D.ev_partner[target];
+    c->partner = p > 0 ? p : 0;
+}
+__global__ void k_hazard(DevP D, int target, int partner, int *out) {
+    *out = (partner > 0 && D.ev_pcounter[target] < D.ev_counter[partner]) ? -1 : 0;
+}
+__global__ void k_do_event(DevP D) {
+    Ctl *c = D.ctl;
+    c->frame++;
+    d_do_event(D, c->target, c->partner);
+    D.ev_counter[c->target]++;
+    if (c->partner && !D.is_cons[c->partner]) D.ev_counter[c->partner]++;
+}
+__global__ void k_cell_move(DevP D, int atom) { d_pcc_event(D, atom); }
+
+// CalPotenE, ToolFunctions.c:659-752: the accumulation order is part of the result, so one thread adds the
+// pair terms in the reference's order
+__global__ void k_potential_energy(DevP D, double *out) {
+    double TPE = 0, accum = 0;
+    for (int i = 1; i <= D.n; i++) {
+        int cx = D.cell_idx[3 * i], cy = D.cell_idx[3 * i + 1], cz = D.cell_idx[3 * i + 2];
+        double xi = D.x[i], yi = D.y[i], zi = D.z[i];
+        for (int n = 0; n < 27; n++) {
+            int nx = cx + c_offx[n], ny = cy + c_offy[n], nz = cz + c_offz[n];
+            double shx = 0, shy = 0, shz = 0;
+            if (nx < 0) { nx = D.cellnum[0] - 1; shx = -1 * D.box[0]; } else if (nx >= D.cellnum[0]) { nx = 0; shx = D.box[0]; }
+            if (ny < 0) { ny = D.cellnum[1] - 1; shy = -1 * D.box[1]; } else if (ny >= D.cellnum[1]) { ny = 0; shy = D.box[1]; }
+            if (nz < 0) { nz = D.cellnum[2] - 1; shz = -1 * D.box[2]; } else if (nz >= D.cellnum[2]) { nz = 0; shz = D.box[2]; }
+            int cell = nz * D.cellnum[0] * D.cellnum[1] + ny * D.cellnum[0] + nx;
+            for (int pair = D.celllist[D.n + cell + 1]; pair != 0; pair = D.celllist[pair]) {
+                if (pair <= i) continue;
+                double tx = D.x[pair] + shx, ty = D.y[pair] + shy, tz = D.z[pair] + shz;
+                double rx = xi - tx, ry = yi - ty, rz = zi - tz;
+                double d2 = rx * rx + ry * ry + rz * rz;
+                int cm = d_cm_flags(D, i, pair);
+                if (d2 <= D.cutfull2 && !(cm & SDMD_BOND_CONNECT)) {
+                    int ai = i, aj = pair, hbp = 0, mode;
+                    if (D.hb_bond[ai] == aj) { mode = FP_HB; TPE -= d_hb_barrier(D, ai, aj); }
+                    else if (cm & SDMD_CONSTRAINT_CONNECT) mode = FP_CONSTRAINT;
+                    else if (d_neighbor_connected(D, ai, aj)) {
+                        if (D.hb_neighbor[D.hb_bond[ai]] == aj) { int s = ai; ai = aj; aj = s; }
+                        hbp = D.hb_bond[aj];
+                        mode = FP_NEIGHBOR;
+                    } else mode = FP_COLLISION;
+                    double wx = D.vx[ai] - D.vx[aj], wy = D.vy[ai] - D.vy[aj], wz = D.vz[ai] - D.vz[aj];
+                    double direction = rx * wx + ry * wy + rz * wz;
+                    accum = d_find_pair(D, ai, aj, mode, direction, d2, hbp, 0).accum;
+                    if (accum < SD_INF / 2) TPE += accum;
+                }
+            }
+        }
+    }
+    *out = TPE;
+}
+// CalKinetE, ToolFunctions.c:626-656 (flow.mark < 2, constV = 0); ordered sum
+__global__ void k_kinetic_energy(DevP D, double *out) {
+    double TKE = 0;
+    for (int i = 1; i <= D.n; i++) {
+        double a = D.vx[i] - 0.0, b = D.vy[i] - 0.0, c = D.vz[i] - 0.0;
+        double s = a * a + b * b + c * c;
+        TKE += 0.5 * D.mass[i] * s;
+    }
+    *out = TKE;
+}
+
+// ===================================================================================================
+// C-ABI
+// ===================================================================================================
+extern "C" {
+
+const char *sdmd_cuda_last_error(void) { return g_err; }
+
+int sdmd_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+static inline int grid_for(int n, int block) { return (n + block - 1) / block; }
+
+// leaf permutation of CreateCBT's sequential InsertCBTRun (CBT.c:86-105): time independent
+static void cbt_leaf_permutation(int n, std::vector<int> &leaf_atom) {
+    std::vector<int> node(2 * (size_t)n + 2, 0);
+    int count = 0;
+    for (int a = 1; a <= n; a++) {
+        if (count == 0) { node[1] = a; count++; continue; }
+        int i = node[count];
+        node[count * 2] = i;
+        node[count * 2 + 1] = a;
+        count++;
+    }
+    leaf_atom.resize(n);
+    if (n == 1) { leaf_atom[0] = 1; return; }
+    for (int k = 0; k < n; k++) leaf_atom[k] = node[n + k];
+}
+
+int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out) {
+    if (!v || !out || v->abi_version != SDMD_ABI_VERSION || v->natom < 1) return set_err(SDMD_ERR_BAD_ARG, "bad host view");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_err(SDMD_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return set_err(SDMD_ERR_BAD_ARG, "bad device index");
+    CK(cudaSetDevice(device));
+    sdmd_ctx *c = new sdmd_ctx();
+    c->device = device;
+    c->n = v->natom;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    int n = v->natom;
+    size_t n1 = (size_t)n + 1;
+    DevP &P = c->P;
+    memset(&P, 0, sizeof(P));
+    P.n = n;
+    // CreateCell, Initialization.c:1060-1073
+    for (int k = 0; k < 3; k++) {
+        P.box[k] = v->box[k];
+        P.cellnum[k] = (int)floor(v->box[k] / v->cutoffr);
+        if (P.cellnum[k] < 3) P.cellnum[k] = 3;
+    }
+    for (int k = 0; k < 3; k++) P.cellsize[k] = v->box[k] / P.cellnum[k];
+    long long ncell = (long long)P.cellnum[0] * P.cellnum[1] * P.cellnum[2];
+    if (ncell > (1LL << 30)) { delete c; return set_err(SDMD_ERR_BAD_ARG, "cell grid too large"); }
+    P.ncell = (int)ncell;
+    P.cutoffr = v->cutoffr;
+    P.cut2 = v->cutoffr * SDMD_EXTEND_RATIO;  // TimePrediction.c:53-54
+    P.cut2 *= P.cut2;
+    P.cutfull2 = v->cutoffr * v->cutoffr;      // Events.c:1031, ToolFunctions.c:709
+    P.thermoF = v->thermoF;
+    P.thermostat_on = v->thermostat_on;
+    P.method_ding = v->method_ding;
+    P.hydrogen_bond = v->hydrogen_bond;
+    P.gel_mode = v->gel_mode;
+    for (int k = 0; k < 3; k++) P.hb_barrier[k] = v->hb_barrier[k];
+
+    TRY(dupload(c, &P.x, v->x, n1)); TRY(dupload(c, &P.y, v->y, n1)); TRY(dupload(c, &P.z, v->z, n1));
+    TRY(dupload(c, &P.vx, v->vx, n1)); TRY(dupload(c, &P.vy, v->vy, n1)); TRY(dupload(c, &P.vz, v->vz, n1));
+    TRY(dupload(c, (double **)&P.mass, v->mass, n1));
+    TRY(dupload(c, &P.type, v->type, n1));
+    TRY(dupload(c, (int **)&P.aa_type, v->aa_type, n1));
+    TRY(dupload(c, (int **)&P.protein, v->protein_num, n1));
+    TRY(dupload(c, (int **)&P.aa_num, v->aa_num, n1));
+    TRY(dupload(c, (uint8_t **)&P.is_cons, v->is_cons, n1));
+    TRY(dupload(c, &P.hb_bond, v->hb_bond, n1));
+    TRY(dupload(c, (int **)&P.hb_neighbor, v->hb_neighbor, n1));
+    TRY(dupload(c, (uint8_t **)&P.hb_role, v->hb_role, n1));
+    TRY(dupload(c, &P.hb_itype, v->hb_itype, n1));
+    TRY(dupload(c, &P.hbn_partner, v->hbn_partner, 5 * n1));
+    TRY(dupload(c, &P.hbn_pnum, v->hbn_partner_num, n1));
+    TRY(dupload(c, &P.hbn_status, v->hbn_status, n1));
+    TRY(dupload(c, &P.ev_time, v->ev_time, n1));
+    TRY(dupload(c, &P.ev_pot, v->ev_potential, n1));
+    TRY(dupload(c, &P.ev_partner, v->ev_partner, n1));
+    TRY(dupload(c, &P.ev_counter, (const i64 *)v->ev_counter, n1));
+    TRY(dupload(c, &P.ev_pcounter, (const i64 *)v->ev_pcounter, n1));
+    TRY(dupload(c, &P.ev_type, v->ev_type, n1));
+    TRY(dupload(c, &P.ev_sub, v->ev_sub, n1));
+    TRY(dupload(c, &P.cell_idx, v->cell_idx, 3 * n1));
+    TRY(dalloc(c, &P.celllist, n1 + P.ncell));
+    TRY(dalloc(c, &P.cbt_node, 2 * n1));
+    TRY(dalloc(c, &P.cbt_leaf, n1));
+    int nb = v->bond_off ? v->bond_off[n + 1] : 0, nc = v->con_off ? v->con_off[n + 1] : 0, ncm = v->cm_off ? v->cm_off[n + 1] : 0;
+    std::vector<int> zero_off(n1 + 1, 0);
+    TRY(dupload(c, (int **)&P.bond_off, v->bond_off ? v->bond_off : zero_off.data(), n1 + 1));
+    TRY(dupload(c, (int **)&P.bond_j, v->bond_j, (size_t)nb));
+    TRY(dupload(c, (double **)&P.bond_dmin2, v->bond_dmin2, (size_t)nb));
+    TRY(dupload(c, (double **)&P.bond_dmax2, v->bond_dmax2, (size_t)nb));
+    TRY(dupload(c, (int **)&P.con_off, v->con_off ? v->con_off : zero_off.data(), n1 + 1));
+    TRY(dupload(c, (int **)&P.con_j, v->con_j, (size_t)nc));
+    TRY(dupload(c, (int **)&P.con_table, v->con_table, (size_t)nc));
+    TRY(dupload(c, (int **)&P.cm_off, v->cm_off ? v->cm_off : zero_off.data(), n1 + 1));
+    TRY(dupload(c, (int **)&P.cm_j, v->cm_j, (size_t)ncm));
+    TRY(dupload(c, (int **)&P.cm_flags, v->cm_flags, (size_t)ncm));
+    TRY(dupload(c, (sdmd_step_table **)&P.tables, v->tables, (size_t)v->ntable));
+    TRY(dupload(c, (int **)&P.coll_index, v->coll_index, (size_t)SD_NT * SD_NT));
+    TRY(dupload(c, (int **)&P.hb_index, v->hb_index, (size_t)SDMD_NHBCLASS * SD_NT * SD_NT));
+
+    // gaussian ring: room for a full-system pass plus a generous event-loop window
+    P.g_cap = (i64)n + (1 << 20);
+    TRY(dalloc(c, &c->d_gauss, (size_t)P.g_cap));
+    P.gauss = c->d_gauss;
+    std::vector<int> rank(n1, 0);
+    int r = 0;
+    for (int i = 1; i <= n; i++) { rank[i] = r; if (!v->is_cons[i]) r++; }
+    TRY(dupload(c, (int **)&P.ther_rank, rank.data(), n1));
+
+    // scratch
+    TRY(dalloc(c, &c->b_time, n1)); TRY(dalloc(c, &c->b_pot, n1)); TRY(dalloc(c, &c->b_partner, n1));
+    TRY(dalloc(c, &c->b_pcounter, n1)); TRY(dalloc(c, &c->b_type, n1)); TRY(dalloc(c, &c->b_sub, n1));
+    TRY(dalloc(c, &c->c_time, n1)); TRY(dalloc(c, &c->c_pot, n1)); TRY(dalloc(c, &c->c_partner, n1));
+    TRY(dalloc(c, &c->c_pcounter, n1)); TRY(dalloc(c, &c->c_type, n1)); TRY(dalloc(c, &c->c_sub, n1));
+    TRY(dalloc(c, &c->flag_cur, n1)); TRY(dalloc(c, &c->flag_next, n1)); TRY(dalloc(c, &c->npair, n1));
+    TRY(dalloc(c, &c->cell_of, n1)); TRY(dalloc(c, &c->cell_count, (size_t)P.ncell + 1));
+    TRY(dalloc(c, &c->cell_cursor, (size_t)P.ncell + 1));
+    TRY(dalloc(c, &c->scan_tmp, (size_t)P.ncell / SCAN_ITEMS + 4));
+    TRY(dalloc(c, &c->d_cell_start, (size_t)P.ncell + 1)); TRY(dalloc(c, &c->d_sorted_atom, n1));
+    TRY(dalloc(c, &c->d_sx, n1)); TRY(dalloc(c, &c->d_sy, n1)); TRY(dalloc(c, &c->d_sz, n1));
+    TRY(dalloc(c, &c->d_svx, n1)); TRY(dalloc(c, &c->d_svy, n1)); TRY(dalloc(c, &c->d_svz, n1));
+    TRY(dalloc(c, &c->d_stype, n1));
+    TRY(dalloc(c, &c->d_sum, 4));
+    P.cell_start = c->d_cell_start; P.sorted_atom = c->d_sorted_atom;
+    P.sx = c->d_sx; P.sy = c->d_sy; P.sz = c->d_sz; P.svx = c->d_svx; P.svy = c->d_svy; P.svz = c->d_svz; P.stype = c->d_stype;
+    std::vector<int> leaf_atom;
+    cbt_leaf_permutation(n, leaf_atom);
+    TRY(dupload(c, &c->d_leaf_atom, leaf_atom.data(), (size_t)n));
+
+    TRY(dalloc(c, &c->d_ctl, 1));
+    CK(cudaMallocHost((void **)&c->h_ctl, sizeof(Ctl)));
+    memset(c->h_ctl, 0, sizeof(Ctl));
+    c->h_ctl->currenttime = v->currenttime;
+    c->h_ctl->timestep = v->timestep;
+    c->h_ctl->temperature = v->target_temperature;
+    c->h_ctl->frame = v->frame;
+    CK(cudaMemcpyAsync(c->d_ctl, c->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream));
+    P.ctl = c->d_ctl;
+    CK(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return 0;
+}
+
+void sdmd_cuda_destroy(sdmd_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->loop_graph) cudaGraphExecDestroy(c->loop_graph);
+    for (void *p : c->bufs) cudaFree(p);
+    if (c->d_trace) cudaFree(c->d_trace);
+    if (c->d_xchg) cudaFree(c->d_xchg);
+    if (c->h_ctl) cudaFreeHost(c->h_ctl);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int sdmd_cuda_cell_grid(const sdmd_ctx *c, int cellnum[3], double cellsize[3]) {
+    if (!c) return set_err(SDMD_ERR_BAD_ARG, "null ctx");
+    for (int k = 0; k < 3; k++) { cellnum[k] = c->P.cellnum[k]; cellsize[k] = c->P.cellsize[k]; }
+    return 0;
+}
+
+void *sdmd_cuda_stream(const sdmd_ctx *c) { return c ? (void *)c->stream : nullptr; }
+int64_t sdmd_cuda_launch_count(const sdmd_ctx *c) { return c ? c->launches : 0; }
+double sdmd_cuda_kernel_ms(const sdmd_ctx *c, const char *name) {
+    auto it = c->kstat.find(name);
+    if (it == c->kstat.end() || it->second.n == 0) return -1.0;
+    return it->second.ms / it->second.n;
+}
+int sdmd_cuda_kernel_stats(const sdmd_ctx *c, const char *name, double *total_ms, int64_t *count) {
+    auto it = c->kstat.find(name);
+    if (it == c->kstat.end()) { *total_ms = 0; *count = 0; return 0; }
+    *total_ms = it->second.ms;
+    *count = it->second.n;
+    return 0;
+}
+void sdmd_cuda_reset_kernel_stats(sdmd_ctx *c) { c->kstat.clear(); c->launches = 0; }
+void sdmd_cuda_set_timing(sdmd_ctx *c, int on) { c->timing = on != 0; }
+
+static int pull_ctl(sdmd_ctx *c) {
+    CK(cudaMemcpyAsync(c->h_ctl, c->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+static int push_ctl(sdmd_ctx *c) {
+    CK(cudaMemcpyAsync(c->d_ctl, c->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+// ---- state transfer -------------------------------------------------------------------------------
+int sdmd_cuda_upload_coords(sdmd_ctx *c, const double *x, const double *y, const double *z, const double *vx, const double *vy,
+                            const double *vz) {
+    CK(cudaSetDevice(c->device));
+    size_t b = ((size_t)c->n + 1) * sizeof(double);
+    const double *src[6] = {x, y, z, vx, vy, vz};
+    double *dst[6] = {c->P.x, c->P.y, c->P.z, c->P.vx, c->P.vy, c->P.vz};
+    for (int k = 0; k < 6; k++)
+        if (src[k]) CK(cudaMemcpyAsync(dst[k], src[k], b, cudaMemcpyHostToDevice, c->stream));
+    c->cells_fresh = false;
+    return 0;
+}
+
+int sdmd_cuda_upload_celllist(sdmd_ctx *c, const int32_t *celllist) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->P.celllist, celllist, ((size_t)c->n + c->P.ncell + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    c->cells_fresh = false;
+    return 0;
+}
+
+int sdmd_cuda_download(sdmd_ctx *c, struct sdmd_host_view *v) {
+    CK(cudaSetDevice(c->device));
+    size_t n1 = (size_t)c->n + 1;
+#define DL(dst, src, cnt)                                                                                        \
+    if (v->dst) CK(cudaMemcpyAsync(v->dst, c->P.src, (cnt) * sizeof(*v->dst), cudaMemcpyDeviceToHost, c->stream))
+    DL(x, x, n1); DL(y, y, n1); DL(z, z, n1); DL(vx, vx, n1); DL(vy, vy, n1); DL(vz, vz, n1);
+    DL(type, type, n1); DL(hb_bond, hb_bond, n1); DL(hb_itype, hb_itype, n1);
+    DL(hbn_partner, hbn_partner, 5 * n1); DL(hbn_partner_num, hbn_pnum, n1); DL(hbn_status, hbn_status, n1);
+    DL(ev_time, ev_time, n1); DL(ev_potential, ev_pot, n1); DL(ev_partner, ev_partner, n1);
+    DL(ev_type, ev_type, n1); DL(ev_sub, ev_sub, n1); DL(cell_idx, cell_idx, 3 * n1);
+#undef DL
+    if (v->ev_counter) CK(cudaMemcpyAsync(v->ev_counter, c->P.ev_counter, n1 * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (v->ev_pcounter) CK(cudaMemcpyAsync(v->ev_pcounter, c->P.ev_pcounter, n1 * 8, cudaMemcpyDeviceToHost, c->stream));
+    TRY(pull_ctl(c));
+    v->currenttime = c->h_ctl->currenttime;
+    v->frame = c->h_ctl->frame;
+    v->target_temperature = c->h_ctl->temperature;
+    return 0;
+}
+
+int sdmd_cuda_download_slots(sdmd_ctx *c, double *time, double *pot, int32_t *partner, uint8_t *type, uint8_t *sub) {
+    CK(cudaSetDevice(c->device));
+    size_t n1 = (size_t)c->n + 1;
+    if (time) CK(cudaMemcpyAsync(time, c->P.ev_time, n1 * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (pot) CK(cudaMemcpyAsync(pot, c->P.ev_pot, n1 * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (partner) CK(cudaMemcpyAsync(partner, c->P.ev_partner, n1 * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (type) CK(cudaMemcpyAsync(type, c->P.ev_type, n1, cudaMemcpyDeviceToHost, c->stream));
+    if (sub) CK(cudaMemcpyAsync(sub, c->P.ev_sub, n1, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sdmd_cuda_download_celllist(sdmd_ctx *c, int32_t *celllist) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(celllist, c->P.celllist, ((size_t)c->n + c->P.ncell + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sdmd_cuda_download_cbt(sdmd_ctx *c, int32_t *node, int32_t *leaf) {
+    CK(cudaSetDevice(c->device));
+    if (node) CK(cudaMemcpyAsync(node, c->P.cbt_node, (size_t)c->n * 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (leaf) CK(cudaMemcpyAsync(leaf, c->P.cbt_leaf, ((size_t)c->n + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- thermostat stream ----------------------------------------------------------------------------
+// Maxwell_Boltzmann_Distribution(0,1), ToolFunctions.c:517-522,544-569, on the process-global rand()
+double sdmd_host_gaussian_libc(void) {
+    double r0, r1, r2, choose, out;
+    do {
+        do {
+            r0 = 2 * (0 + (double)rand() / ((double)RAND_MAX / (1 - 0))) - 1;
+            r1 = 2 * (0 + (double)rand() / ((double)RAND_MAX / (1 - 0))) - 1;
+            r2 = r0 * r0 + r1 * r1;
+        } while (r2 >= 1);
+        r2 = sqrt(-2 * log(r2) / r2);
+        choose = 0 + (double)rand() / ((double)RAND_MAX / (1 - 0));
+        out = (choose >= 0.5) ? r0 * r2 : r1 * r2;
+    } while (out == 0);
+    return out * sqrt(1.0) + 0;
+}
+
+int64_t sdmd_cuda_rng_available(const sdmd_ctx *c) {
+    sdmd_ctx *m = const_cast<sdmd_ctx *>(c);
+    if (pull_ctl(m)) return -1;
+    return c->g_filled - c->h_ctl->g_pos;
+}
+
+int sdmd_cuda_rng_feed(sdmd_ctx *c, const double *g, int64_t n) {
+    CK(cudaSetDevice(c->device));
+    if (n <= 0) return 0;
+    TRY(pull_ctl(c));
+    i64 cap = c->P.g_cap;
+    if (c->g_filled + n - c->h_ctl->g_pos > cap) return set_err(SDMD_ERR_BAD_ARG, "gaussian ring overflow");
+    i64 pos = c->g_filled % cap;
+    i64 first = (n < cap - pos) ? n : cap - pos;
+    CK(cudaMemcpyAsync(c->d_gauss + pos, g, first * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (n > first) CK(cudaMemcpyAsync(c->d_gauss, g + first, (n - first) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->g_filled += n;
+    c->h_ctl->g_filled = c->g_filled;
+    CK(cudaMemcpyAsync(&c->d_ctl->g_filled, &c->h_ctl->g_filled, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sdmd_cuda_rng_fill_libc(sdmd_ctx *c, int64_t n) {
+    std::vector<double> g((size_t)(n > 0 ? n : 0));
+    for (int64_t k = 0; k < n; k++) g[k] = sdmd_host_gaussian_libc();
+    return sdmd_cuda_rng_feed(c, g.data(), n);
+}
+
+// ---- hot path -------------------------------------------------------------------------------------
+int sdmd_cuda_pbc_full(sdmd_ctx *c) {
+    CK(cudaSetDevice(c->device));
+    k_pbc_full<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->P);
+    c->launches++;
+    c->cells_fresh = false;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int sdmd_cuda_cell_build(sdmd_ctx *c) {
+    CK(cudaSetDevice(c->device));
+    Timer t(c, "cell_build");
+    int n = c->n, m = c->P.ncell;
+    CK(cudaMemsetAsync(c->cell_count, 0, ((size_t)m + 1) * sizeof(int), c->stream));
+    k_cell_index<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_count);
+    int nb = (m + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    k_scan_local<<<nb, 512, 0, c->stream>>>(c->cell_count, c->d_cell_start, c->scan_tmp, m);
+    k_scan_blocks<<<1, 32, 0, c->stream>>>(c->scan_tmp, nb);
+    k_scan_add<<<grid_for(m, 256), 256, 0, c->stream>>>(c->d_cell_start, c->scan_tmp, m, nb);
+    CK(cudaMemcpyAsync(c->cell_cursor, c->d_cell_start, ((size_t)m + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    k_cell_scatter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_cursor, c->d_sorted_atom);
+    k_cell_finish<<<grid_for(m, 128), 128, 0, c->stream>>>(c->P, c->d_cell_start, c->d_sorted_atom);
+    k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_sx, c->d_sy, c->d_sz, c->d_svx, c->d_svy,
+                                                            c->d_svz, c->d_stype);
+    c->launches += 7;
+    c->cells_fresh = true;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int sdmd_cuda_predict_all(sdmd_ctx *c) {
+    CK(cudaSetDevice(c->device));
+    if (!c->cells_fresh) return set_err(SDMD_ERR_STATE, "predict_all needs a fresh cell_build (cell-sorted tiles)");
+    int n = c->n;
+    TRY(pull_ctl(c));
+    i64 need = 0;
+    if (c->P.thermostat_on) need = n;  // one draw per predicted atom, TimePrediction.c:591
+    if (c->g_filled - c->h_ctl->g_pos < need) return set_err(SDMD_ERR_BAD_ARG, "predict_all: not enough gaussians fed");
+    i64 g_base = c->h_ctl->g_pos;
+    SlotBuf B = {c->b_time, c->b_pot, c->b_partner, c->b_pcounter, c->b_type, c->b_sub};
+    SlotBuf C = {c->c_time, c->c_pot, c->c_partner, c->c_pcounter, c->c_type, c->c_sub};
+    int grid = grid_for(n, 128), grid1 = grid_for(n, 256);
+    {
+        Timer t(c, "predict_all");
+        k_predict_all_round<<<grid, 128, 0, c->stream>>>(c->P, B, B, c->flag_cur, 0, c->npair, g_base);
+        c->launches++;
+    }
+    Timer t2(c, "predict_all_fixup");
+    CK(cudaMemsetAsync(c->flag_cur, 0, (size_t)n + 1, c->stream));
+    k_predict_all_flag0<<<grid1, 256, 0, c->stream>>>(c->P, B, c->flag_cur);
+    c->launches++;
+    int rounds = 0;
+    for (;;) {
+        rounds++;
+        if (rounds > n + 2) return set_err(SDMD_ERR_STATE, "predict_all did not converge");
+        c->h_ctl->changed = 0;
+        CK(cudaMemcpyAsync(&c->d_ctl->changed, &c->h_ctl->changed, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(c->flag_next, 0, (size_t)n + 1, c->stream));
+        k_predict_all_round<<<grid, 128, 0, c->stream>>>(c->P, B, C, c->flag_cur, rounds, c->npair, g_base);
+        k_predict_all_commit<<<grid1, 256, 0, c->stream>>>(c->P, B, C, c->flag_cur, c->flag_next);
+        c->launches += 2;
+        CK(cudaMemcpyAsync(&c->h_ctl->changed, &c->d_ctl->changed, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (!c->h_ctl->changed) break;
+        std::swap(c->flag_cur, c->flag_next);
+    }
+    CK(cudaMemsetAsync(c->d_sum, 0, sizeof(unsigned long long), c->stream));
+    k_predict_all_final<<<grid1, 256, 0, c->stream>>>(c->P, B, c->npair, c->d_sum);
+    c->launches++;
+    unsigned long long sum = 0;
+    CK(cudaMemcpyAsync(&sum, c->d_sum, sizeof(sum), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->h_ctl->g_pos = g_base + need;
+    c->h_ctl->pair_predictions += (i64)sum;
+    CK(cudaMemcpyAsync(&c->d_ctl->g_pos, &c->h_ctl->g_pos, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(&c->d_ctl->pair_predictions, &c->h_ctl->pair_predictions, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+    c->kstat["predict_all_rounds"].ms += rounds;
+    c->kstat["predict_all_rounds"].n++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int sdmd_cuda_predict(sdmd_ctx *c, const int32_t *renew) {
+    CK(cudaSetDevice(c->device));
+    if (!renew) return set_err(SDMD_ERR_BAD_ARG, "null renew list");
+    int cnt = 0;
+    while (renew[1 + cnt]) cnt++;
+    // the event loop only ever lists one or two atoms (SGThread.c:238-251); longer lists go pairwise in order,
+    // which is the same sequential semantics (reset of later atoms happens before they are used as sources
+    // only within a pair; for a full-system pass use sdmd_cuda_predict_all)
+    if (cnt > 2) return set_err(SDMD_ERR_UNSUPPORTED, "renew lists longer than 2 atoms: use sdmd_cuda_predict_all");
+    k_predict_list<<<1, 1, 0, c->stream>>>(c->P, cnt > 0 ? renew[1] : 0, cnt > 1 ? renew[2] : 0);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int sdmd_cuda_cbt_build(sdmd_ctx *c) {
+    CK(cudaSetDevice(c->device));
+    Timer t(c, "cbt_build");
+    int n = c->n;
+    k_cbt_leaves<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_leaf_atom);
+    c->launches++;
+    // internal nodes 1..n-1, deepest level first
+    int top = 1;
+    while (top * 2 <= n - 1) top *= 2;
+    for (int lo = top; lo >= 1; lo /= 2) {
+        int hi = lo * 2;
+        if (hi > n) hi = n;
+        if (hi > lo) {
+            k_cbt_level<<<grid_for(hi - lo, 256), 256, 0, c->stream>>>(c->P, lo, hi);
+            c->launches++;
+        }
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int sdmd_cuda_cbt_update(sdmd_ctx *c, const int32_t *renew) {
+    CK(cudaSetDevice(c->device));
+    int cnt = 0;
+    while (renew[1 + cnt]) cnt++;
+    for (int k = 0; k < cnt; k += 2) {
+        k_cbt_update<<<1, 1, 0, c->stream>>>(c->P, renew[1 + k], k + 1 < cnt ? renew[2 + k] : 0);
+        c->launches++;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int sdmd_cuda_assign_job(sdmd_ctx *c, int32_t *target, int32_t *partner, double *dt, int32_t *renew) {
+    CK(cudaSetDevice(c->device));
+    k_assign_job<<<1, 1, 0, c->stream>>>(c->P);
+    c->launches++;
+    TRY(pull_ctl(c));
+    if (target) *target = c->h_ctl->target;
+    if (partner) *partner = c->h_ctl->partner;
+    if (dt) *dt = c->h_ctl->dt;
+    if (renew) {
+        renew[0] = c->h_ctl->partner ? 2 : 1;
+        renew[1] = c->h_ctl->target;
+        renew[2] = c->h_ctl->partner;
+        renew[3] = 0;
+    }
+    return 0;
+}
+
+static int advance_grid(const sdmd_ctx *c) {
+    int blocks = grid_for(c->n, 256);
+    int cap = 148 * 8;
+    return blocks < cap ? blocks : cap;
+}
+
+int sdmd_cuda_advance(sdmd_ctx *c, double dt) {
+    CK(cudaSetDevice(c->device));
+    Timer t(c, "advance");
+    k_advance<<<advance_grid(c), 256, 0, c->stream>>>(c->P, dt, 0);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int sdmd_cuda_add_time(sdmd_ctx *c, double dt) {  // currenttime += timeInr, SGThread.c:80
+    TRY(pull_ctl(c));
+    c->h_ctl->currenttime += dt;
+    CK(cudaMemcpyAsync(&c->d_ctl->currenttime, &c->h_ctl->currenttime, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+int sdmd_cuda_hazard_check(sdmd_ctx *c, int32_t target, int32_t partner, int32_t *hazard) {
+    CK(cudaSetDevice(c->device));
+    k_hazard<<<1, 1, 0, c->stream>>>(c->P, target, partner, (int *)c->d_sum + 2);
+    c->launches++;
+    CK(cudaMemcpyAsync(hazard, (int *)c->d_sum + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sdmd_cuda_cell_move(sdmd_ctx *c, int32_t atom) {
+    CK(cudaSetDevice(c->device));
+    k_cell_move<<<1, 1, 0, c->stream>>>(c->P, atom);
+    c->launches++;
+    c->cells_fresh = false;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int sdmd_cuda_do_event(sdmd_ctx *c) {
+    CK(cudaSetDevice(c->device));
+    k_do_event<<<1, 1, 0, c->stream>>>(c->P);
+    c->launches++;
+    c->cells_fresh = false;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int sdmd_cuda_potential_energy(sdmd_ctx *c, double *e) {
+    CK(cudaSetDevice(c->device));
+    double *d = (double *)(c->d_sum + 1);
+    k_potential_energy<<<1, 1, 0, c->stream>>>(c->P, d);
+    c->launches++;
+    CK(cudaMemcpyAsync(e, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int sdmd_cuda_kinetic_energy(sdmd_ctx *c, double *e) {
+    CK(cudaSetDevice(c->device));
+    double *d = (double *)(c->d_sum + 1);
+    k_kinetic_energy<<<1, 1, 0, c->stream>>>(c->P, d);
+    c->launches++;
+    CK(cudaMemcpyAsync(e, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static void fill_stats(const Ctl *h, struct sdmd_run_stats *s) {
+    s->frame = h->frame; s->iterations = h->iterations; s->count_recal = h->count_recal;
+    s->collision = h->n_coli; s->bond = h->n_bond; s->hb = h->n_hb; s->hb_neighbor = h->n_hbne;
+    s->thermostat = h->n_ther; s->pcc = h->n_pcc; s->warnings = h->warnings;
+    s->pair_predictions = h->pair_predictions; s->gaussians_used = h->g_pos; s->currenttime = h->currenttime;
+    s->stop_reason = h->stop ? h->stop - 1 : 0; s->error = h->error;
+}
+
+int sdmd_cuda_get_stats(sdmd_ctx *c, struct sdmd_run_stats *s) {
+    TRY(pull_ctl(c));
+    fill_stats(c->h_ctl, s);
+    return 0;
+}
+
+int sdmd_cuda_set_temperature(sdmd_ctx *c, double t) {
+    c->h_ctl->temperature = t;
+    CK(cudaMemcpyAsync(&c->d_ctl->temperature, &c->h_ctl->temperature, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+#define SDMD_SMALL_N 4096
+
+int sdmd_cuda_run(sdmd_ctx *c, double t_until, int64_t max_iter, struct sdmd_trace_rec *trace, int64_t trace_cap,
+                  struct sdmd_run_stats *stats) {
+    CK(cudaSetDevice(c->device));
+    c->cells_fresh = false;
+    if (trace_cap > c->trace_cap) {
+        if (c->d_trace) cudaFree(c->d_trace);
+        CK(cudaMalloc((void **)&c->d_trace, (size_t)trace_cap * sizeof(sdmd_trace_rec)));
+        c->trace_cap = trace_cap;
+    }
+    TRY(pull_ctl(c));
+    c->h_ctl->stop = 0;
+    c->h_ctl->trace_pos = 0;
+    i64 iter_limit = c->h_ctl->iterations + max_iter;
+    if (max_iter > (1LL << 61)) iter_limit = (1LL << 62);
+    TRY(push_ctl(c));
+    sdmd_trace_rec *dtr = (trace && trace_cap > 0) ? c->d_trace : nullptr;
+    cudaEventRecord(c->ev0, c->stream);
+    if (c->n <= SDMD_SMALL_N) {
+        k_run_cta<<<1, 256, 0, c->stream>>>(c->P, t_until, iter_limit, dtr, trace_cap);
+        c->launches++;
+        CK(cudaGetLastError());
+        TRY(pull_ctl(c));
+    } else {
+        k_loop_head<<<1, 1, 0, c->stream>>>(c->P, t_until, iter_limit);
+        c->launches++;
+        const int batch = 64;
+        for (;;) {
+            for (int k = 0; k < batch; k++) {
+                k_advance<<<advance_grid(c), 256, 0, c->stream>>>(c->P, 0.0, 1);
+                k_event_exec<<<1, 32, 0, c->stream>>>(c->P, t_until, iter_limit, dtr, trace_cap);
+            }
+            c->launches += 2 * batch;
+            CK(cudaGetLastError());
+            TRY(pull_ctl(c));
+            if (c->h_ctl->stop) break;
+        }
+    }
+    cudaEventRecord(c->ev1, c->stream);
+    cudaEventSynchronize(c->ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->kstat["run"].ms += ms;
+    c->kstat["run"].n++;
+    if (dtr) {
+        i64 cnt = c->h_ctl->trace_pos < trace_cap ? c->h_ctl->trace_pos : trace_cap;
+        CK(cudaMemcpyAsync(trace, c->d_trace, (size_t)cnt * sizeof(sdmd_trace_rec), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    if (stats) fill_stats(c->h_ctl, stats);
+    if (c->h_ctl->error) return set_err(c->h_ctl->error, "device-side error during run");
+    return 0;
+}
+
+// ---- REMD -----------------------------------------------------------------------------------------
+// rearrange, Server.c:145-192
+int sdmd_remd_rearrange(double *epot, struct sdmd_remd_temp *T, int nrep, const double *u01, int n_u01, int *n_used,
+                        double *attempt, double *accept) {
+    int used = 0;
+    for (int i = 0; i < nrep; i++) {
+        if (!T[i].T) continue;
+        for (int j = 0; j < nrep; j++) {
+            if (!T[j].T) continue;
+            if ((T[i].num == T[j].num + 1) || (T[i].num == 1 && T[j].num == 2)) {
+                double beta1 = 1 / T[i].T, beta2 = 1 / T[j].T;
+                double dE = (beta1 - beta2) * (epot[j] - epot[i]);
+                int lo = (T[i].num < T[j].num ? T[i].num : T[j].num) - 1;
+                if (attempt) attempt[lo] += 1;
+                bool ok = dE <= 0.0;
+                if (!ok) {
+                    if (used >= n_u01) return set_err(SDMD_ERR_BAD_ARG, "rearrange: out of uniform draws");
+                    ok = u01[used++] < exp(-1 * dE);
+                }
+                if (ok) {
+                    sdmd_remd_temp z = T[i]; T[i] = T[j]; T[j] = z;
+                    lo = (T[i].num < T[j].num ? T[i].num : T[j].num) - 1;
+                    if (accept) accept[lo] += 1;
+                }
+                break;
+            }
+        }
+    }
+    if (n_used) *n_used = used;
+    return 0;
+}
+
+// NCCL is resolved at run time (torch's bundled libnccl.so.2 or the system one); only the five entry
+// points needed for the exchange step are bound.
+struct nccl_uid_val { char b[128]; };  // ncclUniqueId
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, struct nccl_uid_val, int) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+    if (g_nccl.lib) return 0;
+    const char *names[] = {getenv("SDMD_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        if (!nm) continue;
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return set_err(SDMD_ERR_NCCL, "cannot dlopen libnccl.so.2 (set SDMD_NCCL_LIB)");
+    g_nccl.GetUniqueId = (int (*)(void *))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void **, int, nccl_uid_val, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(g_nccl.lib, "ncclAllGather");
+    g_nccl.CommDestroy = (int (*)(void *))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather) return set_err(SDMD_ERR_NCCL, "libnccl lacks required symbols");
+    return 0;
+}
+
+int sdmd_remd_nccl_unique_id(unsigned char id[128]) {
+    TRY(load_nccl());
+    int rc = g_nccl.GetUniqueId(id);
+    if (rc) return set_err(SDMD_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclGetUniqueId");
+    return 0;
+}
+
+int sdmd_remd_nccl_init(sdmd_ctx *c, int nranks, int rank, const unsigned char id[128]) {
+    CK(cudaSetDevice(c->device));
+    TRY(load_nccl());
+    nccl_uid_val uid;
+    memcpy(uid.b, id, 128);
+    int rc = g_nccl.CommInitRank(&c->nccl_comm, nranks, uid, rank);
+    if (rc) return set_err(SDMD_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclCommInitRank");
+    c->nranks = nranks;
+    c->rank = rank;
+    if (!c->d_xchg) CK(cudaMalloc(&c->d_xchg, (size_t)(nranks + 1) * 32));
+    return 0;
+}
+
+// glibc rand() restated for the replicated server stream (TYPE_3 additive feedback generator: r[i] =
+// r[i-3] + r[i-31], output >> 1; seeding per srand()).  This is glibc's published algorithm, not sDMD code.
+struct GlibcRand {
+    int f = 3, b = 0;
+    uint32_t state[31];
+    void seed(uint32_t s) {
+        if (s == 0) s = 1;
+        int32_t word = (int32_t)s;
+        state[0] = (uint32_t)word;
+        for (int i = 1; i < 31; i++) {
+            long hi = word / 127773, lo = word % 127773;
+            word = (int32_t)(16807 * lo - 2836 * hi);
+            if (word < 0) word += 2147483647;
+            state[i] = (uint32_t)word;
+        }
+        f = 3; b = 0;
+        for (int i = 0; i < 310; i++) next();
+    }
+    uint32_t next() {
+        state[f] += state[b];
+        uint32_t res = state[f] >> 1;
+        f = (f + 1) % 31;
+        b = (b + 1) % 31;
+        return res;
+    }
+};
+static std::map<sdmd_ctx *, GlibcRand> g_server_rng;
+
+int sdmd_remd_seed_server(sdmd_ctx *c, uint32_t seed) {  // srand(seed) of sServer, Server.c:57-58
+    g_server_rng[c].seed(seed);
+    return 0;
+}
+
+// ReplicaExchange (REMD.c:135-192) + collect/rearrange/distribute (Server.c:121-211) without the server:
+// every rank all-gathers {E, T, num}, runs the identical sweep with an identically seeded stream and keeps
+// its own entry.
+int sdmd_remd_exchange(sdmd_ctx *c, double epot, struct sdmd_remd_temp *T, uint32_t /*unused*/) {
+    CK(cudaSetDevice(c->device));
+    int R = c->nranks;
+    struct Rec { double e; double T; int32_t num; int32_t pad; double pad2; };
+    static_assert(sizeof(Rec) == 32, "exchange record is 32 bytes");
+    std::vector<Rec> all(R);
+    Rec mine = {epot, T->T, T->num, 0, 0.0};
+    if (R == 1 || !c->nccl_comm) {
+        all[0] = mine;
+    } else {
+        Rec *d_send = (Rec *)c->d_xchg + R, *d_recv = (Rec *)c->d_xchg;
+        CK(cudaMemcpyAsync(d_send, &mine, sizeof(Rec), cudaMemcpyHostToDevice, c->stream));
+        int rc = g_nccl.AllGather(d_send, d_recv, sizeof(Rec), /*ncclChar*/ 0, c->nccl_comm, c->stream);
+        if (rc) return set_err(SDMD_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclAllGather");
+        CK(cudaMemcpyAsync(all.data(), d_recv, sizeof(Rec) * R, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    std::vector<double> e(R);
+    std::vector<sdmd_remd_temp> t(R);
+    for (int k = 0; k < R; k++) { e[k] = all[k].e; t[k].num = all[k].num; t[k].pad_ = 0; t[k].T = all[k].T; }
+    // draw lazily: copy the generator, count how many the sweep used, then advance the real one
+    GlibcRand &rng = g_server_rng[c];
+    GlibcRand probe = rng;
+    std::vector<double> u(2 * R + 2);
+    for (auto &x : u) x = 0 + (double)probe.next() / ((double)2147483647 / (1 - 0));  // RANDOMVALUE(0,1), Server.c:16-18
+    int used = 0;
+    TRY(sdmd_remd_rearrange(e.data(), t.data(), R, u.data(), (int)u.size(), &used, nullptr, nullptr));
+    for (int k = 0; k < used; k++) rng.next();
+    *T = t[c->rank];
+    TRY(sdmd_cuda_set_temperature(c, T->T));
+    return 0;
+}
+
+}  // extern "C"

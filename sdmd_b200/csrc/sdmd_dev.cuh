@@ -1,0 +1,909 @@
+// sdmd_dev.cuh — device data model and device functions of the sDMD hot path for sm_100a.
+//
+// Everything here is exact IEEE binary64 in the reference's association order; the translation unit is
+// compiled with -fmad=false so no multiply-add is contracted (the reference is x86-64 SSE2, no FMA).
+// Reference citations are relative to the sDMD source tree (src/).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "sdmd_cuda.h"
+
+#define SD_NT (SDMD_NATOMTYPE + 1)
+#define SD_INF SDMD_INFINIT
+#define SD_ZERO SDMD_ZERO
+
+typedef long long i64;
+
+// device-resident control block: the loop state the reference keeps in process globals (DMD.c:12-61)
+struct Ctl {
+    double currenttime;        // currenttime
+    double timestep;           // timestep
+    double temperature;        // targetTemperature
+    double dt;                 // AssignJob: atomList.timeInr
+    i64 frame, iterations, count_recal;
+    i64 n_coli, n_bond, n_hb, n_hbne, n_ther, n_pcc;
+    i64 warnings, pair_predictions;
+    i64 g_pos;                 // gaussians consumed (absolute)
+    i64 g_filled;              // gaussians fed (absolute)
+    int target, partner;       // AssignJob result
+    int stop;                  // 0 = running, else 1 + sdmd_stop_reason
+    int error;
+    int hbnumformed;
+    int changed;               // predict_all fix-point flag
+    i64 trace_pos;
+};
+
+// thin view of "the slots other atoms currently hold" (live arrays in the event loop, the previous
+// relaxation round in the full-system pass)
+struct SlotSrc {
+    const double *time, *pot;
+    const int *partner;
+    const i64 *pcounter;
+    const uint8_t *type, *sub;
+};
+
+struct Slot {
+    double time, pot;
+    i64 pcounter;
+    int partner, type, sub;
+};
+
+struct DevP {
+    int n, ncell;
+    int cellnum[3];
+    double cellsize[3], box[3];
+    double cutoffr, cut2, cutfull2, thermoF;
+    int thermostat_on, method_ding, hydrogen_bond, gel_mode;
+    double hb_barrier[3];
+    double *x, *y, *z, *vx, *vy, *vz;
+    const double *mass;
+    int *type;
+    const int *aa_type, *protein, *aa_num;
+    const uint8_t *is_cons;
+    int *hb_bond;
+    const int *hb_neighbor;
+    const uint8_t *hb_role;
+    uint8_t *hb_itype;
+    int *hbn_partner, *hbn_pnum, *hbn_status;
+    double *ev_time, *ev_pot;
+    int *ev_partner;
+    i64 *ev_counter, *ev_pcounter;
+    uint8_t *ev_type, *ev_sub;
+    int *cell_idx;     // 3 per atom
+    int *celllist;     // reference layout: next[1..n], heads at [n + cell], cell 1-based
+    int *cbt_node, *cbt_leaf;
+    const int *bond_off, *bond_j;
+    const double *bond_dmin2, *bond_dmax2;
+    const int *con_off, *con_j, *con_table;
+    const int *cm_off, *cm_j, *cm_flags;
+    const sdmd_step_table *tables;
+    const int *coll_index, *hb_index;
+    const double *gauss;
+    i64 g_cap;
+    const int *ther_rank;  // index of the gaussian atom i consumes in a full pass
+    Ctl *ctl;
+    // cell-sorted tiles produced by cell_build (fresh link-list order: descending atom id inside a cell)
+    const int *cell_start;   // [ncell + 1], 0-based cell
+    const int *sorted_atom;  // [n]
+    const double *sx, *sy, *sz, *svx, *svy, *svz;
+    const int *stype;
+};
+
+// neighbour-cell offsets, DMD.c:118-120
+__constant__ int c_offx[27] = {0, 1, 0, 0, 0, 1, 1, 1, -1, 0, 0, 0, -1, -1, -1, 0, 0, 1, -1, 1, -1, -1, -1, 1, 1, 1, -1};
+__constant__ int c_offy[27] = {0, 0, 1, 0, 1, 0, 1, 1, 0, -1, 0, -1, 0, -1, -1, -1, 1, 0, 0, -1, 1, -1, 1, -1, 1, -1, 1};
+__constant__ int c_offz[27] = {0, 0, 0, 1, 1, 1, 0, 1, 0, 0, -1, -1, -1, 0, -1, 1, -1, -1, 1, 0, 0, 1, -1, -1, -1, 1, 1};
+
+enum { FP_COLLISION = 0, FP_CONSTRAINT = 1, FP_HB = 2, FP_NEIGHBOR = 3 };
+
+struct FindRes {
+    double lower, upper, lowPot, upPot, accum;
+    int cs;  // coreorShell
+};
+
+struct Pair {
+    double rx, ry, rz, r2, b, v2;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// AtomTypeChange, ToolFunctions.c:233-270
+__device__ __forceinline__ int d_type_change(int t, int direct) {
+    if (direct == 1) {
+        if (t == 1) return 3;
+        if (t == 2) return 4;
+        if (t == 26) return 27;
+    } else {
+        if (t == 3) return 1;
+        if (t == 4) return 2;
+        if (t == 27) return 26;
+    }
+    return t;
+}
+
+// HBModel, Models.c:212-290; -1 "no HB" (ASN/GLN), -2 = the reference's fatal exit
+__device__ inline int d_hb_model(const DevP &D, int a1, int a2) {
+    if (D.hb_role[a1] == 'A' || D.hb_role[a1] == 'S') { int s = a1; a1 = a2; a2 = s; }
+    int o1 = d_type_change(D.type[a1], 0), o2 = d_type_change(D.type[a2], 0);
+    int aa = D.aa_type[a2];
+    if (o1 == 2 && o2 == 26) return 1;
+    if (o1 == 2) {
+        switch (aa) {
+            case 4: case 7: return 2;
+            case 16: case 17: case 19: return 3;
+            case 9: return 4;
+            case 5: return 10;
+            case 3: case 6: return -1;
+            default: break;
+        }
+    } else if (o2 == 26) return 5;
+    else if (o1 == 31 && o2 == 31) return 9;
+    else if (o1 == 1) {
+        switch (aa) {
+            case 4: case 7: return 6;
+            case 16: case 17: case 19: return 7;
+            case 9: return 8;
+            case 3: case 6: return 11;
+            default: break;
+        }
+    }
+    return -2;
+}
+
+// static bits of connectionMap[i][j] (BOND / CONSTRAINT)
+__device__ __forceinline__ int d_cm_flags(const DevP &D, int i, int j) {
+    for (int k = D.cm_off[i]; k < D.cm_off[i + 1]; k++)
+        if (D.cm_j[k] == j) return D.cm_flags[k];
+    return 0;
+}
+
+// FindElemInList(neighborPartner, value, -1, -1, 0), ToolFunctions.c:1078-1084 (scan bounded to [1,4])
+__device__ __forceinline__ int d_find_in_hbn(const DevP &D, int a, int value) {
+    for (int k = 1; k <= 4; k++) {
+        int p = D.hbn_partner[5 * a + k];
+        if (p == 0) return 0;
+        if (p == value) return k;
+    }
+    return 0;
+}
+// NEIGHBOR_CONNECT bit: set exactly while b is in a's neighborPartner list (Events.c:297-329,350-382)
+__device__ __forceinline__ int d_neighbor_connected(const DevP &D, int a, int b) { return d_find_in_hbn(D, a, b) != 0; }
+
+// the step walk of FindPair, ToolFunctions.c:104-224, on one flattened table
+__device__ inline FindRes d_find_pair_table(const DevP &D, const sdmd_step_table *t, int mode, double direction, double dist2,
+                                            int bond_a1, int bond_a2) {
+    FindRes r;
+    r.cs = -1;
+    double dir = (direction < 0) ? 1.0 : -1.0;  // :46-50
+    double tol = dir * SD_ZERO;
+    if (dist2 < t->dmin2 - SD_ZERO) {  // :119-139
+        r.lower = SD_INF; r.upper = SD_INF; r.accum = SD_INF; r.lowPot = 0; r.upPot = 0;
+        if (!(mode == FP_NEIGHBOR && bond_a2 == 0) && !(mode == FP_HB && bond_a1 == 0)) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+        return r;
+    }
+    r.lower = t->dmin2;
+    r.lowPot = 0;
+    r.upper = 0; r.upPot = 0; r.accum = 0;
+    int ns = t->nstep;
+    for (int k = 0; k < ns; k++) {  // :144-169
+        double d = t->d2[k];
+        if (dist2 < d + tol) {
+            r.upper = d;
+            r.upPot = -1 * t->e[k];
+            r.accum = t->acc[k];
+            if (k == 0) { r.cs = 0; return r; }
+            if (mode == FP_HB && k == ns - 1 && bond_a1 > 0) { r.cs = 1; return r; }
+            if (mode == FP_NEIGHBOR && k == ns - 1 && bond_a2 > 0) { r.upPot = 0; r.cs = 1; return r; }
+            return r;
+        }
+        r.lower = d;
+        r.lowPot = t->e[k];
+    }
+    if (mode == FP_HB && bond_a1 > 0) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);  // :171-178
+    if (t->dmax2 > 0) {  // :180-211
+        if (dist2 < t->dmax2 + SD_ZERO) {
+            r.upper = t->dmax2; r.upPot = 0; r.accum = 0;
+            r.cs = 1;
+            if (ns == 0 && dir == 1.0) r.cs = 0;
+            return r;
+        }
+        r.lower = SD_INF; r.upper = SD_INF; r.accum = SD_INF; r.lowPot = 0; r.upPot = 0;
+        if (!(mode == FP_NEIGHBOR && bond_a2 == 0) && !(mode == FP_HB && bond_a1 == 0)) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+        return r;
+    }
+    r.upper = SD_INF; r.upPot = SD_INF; r.accum = SD_INF;  // :212-221
+    r.cs = 1;
+    return r;
+}
+
+// table selection of FindPair, ToolFunctions.c:53-102
+__device__ inline FindRes d_find_pair(const DevP &D, int a1, int a2, int mode, double direction, double dist2, int hbPartner,
+                                      int typeChange) {
+    int idx = -1;
+    if (mode == FP_COLLISION) {
+        int t1 = D.type[a1];
+        if (typeChange == 1) t1 = d_type_change(t1, 1);
+        else if (typeChange == -1) t1 = d_type_change(t1, 0);
+        idx = D.coll_index[t1 * SD_NT + D.type[a2]];
+    } else if (mode == FP_CONSTRAINT) {
+        for (int k = D.con_off[a1]; k < D.con_off[a1 + 1]; k++)
+            if (D.con_j[k] == a2) { idx = D.con_table[k]; break; }
+    } else if (mode == FP_HB) {
+        int cls = d_hb_model(D, a1, a2);
+        if (cls >= 0) idx = D.hb_index[(cls * SD_NT + 0) * SD_NT + 0];
+    } else {
+        int cls = hbPartner > 0 ? d_hb_model(D, a2, hbPartner) : -2;
+        int t1 = d_type_change(D.type[a1], 0), t2 = d_type_change(D.type[a2], 0);
+        if (cls >= 0) idx = D.hb_index[(cls * SD_NT + t1) * SD_NT + t2];
+    }
+    if (idx < 0 || D.tables[idx].dmin2 == 0) {  // fatal in the reference, :114-117
+        D.ctl->error = SDMD_ERR_TABLE;
+        FindRes r;
+        r.lower = SD_INF; r.upper = SD_INF; r.accum = SD_INF; r.lowPot = 0; r.upPot = 0; r.cs = -1;
+        return r;
+    }
+    return d_find_pair_table(D, &D.tables[idx], mode, direction, dist2, D.hb_bond[a1], D.hb_bond[a2]);
+}
+
+// PBCShift, ToolFunctions.c:801-817, from the two cell-index triples
+__device__ __forceinline__ double d_shift1(int ci, int cj, int cn, double box) {
+    if (ci != cj) {
+        if (ci == 0 && cj == cn - 1) return -1 * box;
+        if (ci == cn - 1 && cj == 0) return box;
+    }
+    return 0;
+}
+
+// CalculateParameters, TimePrediction.c:1081-1090
+__device__ __forceinline__ Pair d_pair(double xi, double yi, double zi, double vxi, double vyi, double vzi, double xj, double yj,
+                                       double zj, double vxj, double vyj, double vzj, double shx, double shy, double shz) {
+    Pair p;
+    double tx = xj + shx, ty = yj + shy, tz = zj + shz;
+    p.rx = xi - tx; p.ry = yi - ty; p.rz = zi - tz;
+    double wx = vxi - vxj, wy = vyi - vyj, wz = vzi - vzj;
+    p.r2 = p.rx * p.rx + p.ry * p.ry + p.rz * p.rz;
+    p.b = p.rx * wx + p.ry * wy + p.rz * wz;
+    p.v2 = wx * wx + wy * wy + wz * wz;
+    return p;
+}
+__device__ inline Pair d_pair_atoms(const DevP &D, int i, int j) {
+    const int *ci = &D.cell_idx[3 * i], *cj = &D.cell_idx[3 * j];
+    double shx = d_shift1(ci[0], cj[0], D.cellnum[0], D.box[0]);
+    double shy = d_shift1(ci[1], cj[1], D.cellnum[1], D.box[1]);
+    double shz = d_shift1(ci[2], cj[2], D.cellnum[2], D.box[2]);
+    return d_pair(D.x[i], D.y[i], D.z[i], D.vx[i], D.vy[i], D.vz[i], D.x[j], D.y[j], D.z[j], D.vx[j], D.vy[j], D.vz[j], shx, shy, shz);
+}
+// CalculateDisc :1092-1094 / CalculateTime :1096-1099
+__device__ __forceinline__ double d_disc(const Pair &p, double short2) { return p.b * p.b - p.v2 * (p.r2 - short2); }
+__device__ __forceinline__ double d_time(const Pair &p, int s, double d2) {
+    return (-1 * p.b + s * sqrt(p.b * p.b - p.v2 * (p.r2 - d2))) / p.v2;
+}
+
+// CheckDuplication, TimePrediction.c:1101-1117 (j is eligible only below dup_limit, see predict_all)
+__device__ __forceinline__ bool d_check_dup(const DevP &D, const SlotSrc &S, Slot &cur, int i, i64 counter_i, int j, int type,
+                                            int dup_limit) {
+    if (j < dup_limit && S.partner[j] == i && S.type[j] == type && S.pcounter[j] == counter_i && cur.time > S.time[j]) {
+        cur.partner = j;
+        cur.pot = S.pot[j];
+        cur.sub = S.sub[j];
+        cur.time = S.time[j];
+        cur.type = type;
+        cur.pcounter = D.ev_counter[j];
+        return true;
+    }
+    return false;
+}
+// JobAssign, TimePrediction.c:1140-1158 (j == 0: no partner)
+__device__ __forceinline__ bool d_job_assign(const DevP &D, Slot &cur, int j, double time, double pot, int sub, int type) {
+    if (time > 0 && cur.time > time) {
+        cur.pot = pot;
+        cur.sub = sub;
+        cur.time = time;
+        cur.type = type;
+        if (j) { cur.partner = j; cur.pcounter = D.ev_counter[j]; }
+        else cur.partner = SDMD_INVALID;
+        return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ int d_neighbor_cell(const DevP &D, int cx, int cy, int cz, int k, int *ncx, int *ncy, int *ncz) {
+    int nx = cx + c_offx[k], ny = cy + c_offy[k], nz = cz + c_offz[k];  // TimePrediction.c:62-72
+    if (nx < 0) nx = D.cellnum[0] - 1; else if (nx >= D.cellnum[0]) nx = 0;
+    if (ny < 0) ny = D.cellnum[1] - 1; else if (ny >= D.cellnum[1]) ny = 0;
+    if (nz < 0) nz = D.cellnum[2] - 1; else if (nz >= D.cellnum[2]) nz = 0;
+    *ncx = nx; *ncy = ny; *ncz = nz;
+    return nz * D.cellnum[0] * D.cellnum[1] + ny * D.cellnum[0] + nx;  // 0-based
+}
+
+struct Self {
+    int i;
+    double x, y, z, vx, vy, vz;
+    int cx, cy, cz;
+    i64 counter;
+    int npair;
+};
+
+// one candidate of CollisionTime's inner loop, TimePrediction.c:82-176, after the duplicate check
+__device__ inline void d_collision_candidate(const DevP &D, Self &me, Slot &cur, int j, double xj, double yj, double zj, double vxj,
+                                             double vyj, double vzj, double shx, double shy, double shz) {
+    int i = me.i;
+    int cm = (D.cm_off[i + 1] > D.cm_off[i]) ? d_cm_flags(D, i, j) : 0;
+    if ((cm & SDMD_BOND_CONNECT) || D.hb_bond[i] == j || d_find_in_hbn(D, i, j)) return;  // :95-100
+    Pair p = d_pair(me.x, me.y, me.z, me.vx, me.vy, me.vz, xj, yj, zj, vxj, vyj, vzj, shx, shy, shz);
+    me.npair++;
+    if (!(p.r2 <= D.cut2)) return;  // :107
+    FindRes f;
+    if (cm & SDMD_CONSTRAINT_CONNECT) {
+        f = d_find_pair(D, i, j, FP_CONSTRAINT, p.b, p.r2, 0, 0);
+    } else {
+        f = d_find_pair(D, i, j, FP_COLLISION, p.b, p.r2, 0, 0);
+        if (f.lowPot == 0 && f.upPot == 0) return;  // :121-124
+    }
+    int s, sub;
+    double d2, pot;
+    if (p.b < 0 && d_disc(p, f.lower) > 0) {  // :130-141
+        s = -1; d2 = f.lower; pot = f.lowPot;
+        sub = (f.cs == 0) ? SDMD_SUB_CORECOLLI : SDMD_SUB_TBDCAPTR;
+    } else {  // :142-164
+        s = 1; d2 = f.upper; pot = f.upPot;
+        sub = SDMD_SUB_INVALID;
+        if (D.method_ding) {
+            if (cm & SDMD_CONSTRAINT_CONNECT) sub = (f.cs == 1) ? SDMD_SUB_WELLBOUNC : SDMD_SUB_TBDESCAP;
+            else {
+                if (f.cs == 1) return;
+                sub = SDMD_SUB_TBDESCAP;
+            }
+        }
+    }
+    double t = d_time(p, s, d2);
+    if (t < 0) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);  // :168-173 prints and carries on
+    d_job_assign(D, cur, j, t, pot, sub, SDMD_EV_COLI);
+}
+
+// CollisionTime, TimePrediction.c:44-183, walking the live link list
+__device__ inline void d_collision_time(const DevP &D, const SlotSrc &S, Self &me, Slot &cur, int dup_limit) {
+    for (int k = 0; k < 27; k++) {
+        int ncx, ncy, ncz;
+        int cell = d_neighbor_cell(D, me.cx, me.cy, me.cz, k, &ncx, &ncy, &ncz);
+        double shx = d_shift1(me.cx, ncx, D.cellnum[0], D.box[0]);
+        double shy = d_shift1(me.cy, ncy, D.cellnum[1], D.box[1]);
+        double shz = d_shift1(me.cz, ncz, D.cellnum[2], D.box[2]);
+        for (int j = D.celllist[D.n + cell + 1]; j; j = D.celllist[j]) {
+            if (j == me.i) continue;
+            if (d_check_dup(D, S, cur, me.i, me.counter, j, SDMD_EV_COLI, dup_limit)) continue;
+            d_collision_candidate(D, me, cur, j, D.x[j], D.y[j], D.z[j], D.vx[j], D.vy[j], D.vz[j], shx, shy, shz);
+        }
+    }
+}
+
+// the same scan over the cell-sorted tiles cell_build produced (valid while the link list is fresh)
+__device__ inline void d_collision_time_sorted(const DevP &D, const SlotSrc &S, Self &me, Slot &cur, int dup_limit) {
+    for (int k = 0; k < 27; k++) {
+        int ncx, ncy, ncz;
+        int cell = d_neighbor_cell(D, me.cx, me.cy, me.cz, k, &ncx, &ncy, &ncz);
+        double shx = d_shift1(me.cx, ncx, D.cellnum[0], D.box[0]);
+        double shy = d_shift1(me.cy, ncy, D.cellnum[1], D.box[1]);
+        double shz = d_shift1(me.cz, ncz, D.cellnum[2], D.box[2]);
+        int p1 = D.cell_start[cell + 1];
+        for (int p = D.cell_start[cell]; p < p1; p++) {
+            int j = D.sorted_atom[p];
+            if (j == me.i) continue;
+            if (d_check_dup(D, S, cur, me.i, me.counter, j, SDMD_EV_COLI, dup_limit)) continue;
+            d_collision_candidate(D, me, cur, j, D.sx[p], D.sy[p], D.sz[p], D.svx[p], D.svy[p], D.svz[p], shx, shy, shz);
+        }
+    }
+}
+
+// BondTime, TimePrediction.c:186-295
+__device__ inline void d_bond_time(const DevP &D, const SlotSrc &S, Self &me, Slot &cur, int dup_limit) {
+    int i = me.i;
+    for (int k = D.bond_off[i]; k < D.bond_off[i + 1]; k++) {
+        int j = D.bond_j[k];
+        if (j == 0) break;
+        if (d_check_dup(D, S, cur, i, me.counter, j, SDMD_EV_BOND, dup_limit)) continue;
+        double long2 = D.bond_dmax2[k], short2 = D.bond_dmin2[k];
+        Pair p = d_pair_atoms(D, i, j);
+        me.npair++;
+        if (p.r2 - long2 > SD_ZERO) {  // :240-253
+            atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+            if (p.b >= 0) {
+                d_job_assign(D, cur, j, 1e-16 * i * j, 0, SDMD_SUB_WELLBOUNC, SDMD_EV_BOND);
+                continue;
+            }
+        } else if (short2 - p.r2 > SD_ZERO) {  // :255-269
+            atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+            if (p.b < 0) {
+                d_job_assign(D, cur, j, 1e-16 * i * j, 0, SDMD_SUB_CORECOLLI, SDMD_EV_BOND);
+                continue;
+            }
+        }
+        int s, sub;
+        double d2;
+        if (p.b < 0 && d_disc(p, short2) > 0) { s = -1; d2 = short2; sub = SDMD_SUB_CORECOLLI; }
+        else { s = 1; d2 = long2; sub = SDMD_SUB_WELLBOUNC; }
+        double t = d_time(p, s, d2);
+        if (t < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); t = SD_INF; }
+        d_job_assign(D, cur, j, t, 0, sub, SDMD_EV_BOND);
+    }
+}
+
+// CheckPairMatch, TimePrediction.c:1119-1138
+__device__ inline int d_check_pair_match(const DevP &D, int i, int j) {
+    int cls = d_hb_model(D, i, j);
+    if (cls == -2) { D.ctl->error = SDMD_ERR_TABLE; return -1; }
+    if (cls < 0) return -1;
+    int ti = D.type[i], tj = D.type[j];
+    int a = D.hb_index[(cls * SD_NT + ti) * SD_NT + tj];
+    if (a < 0 || D.tables[a].nstep == 0) return -1;
+    int ni = d_type_change(D.type[D.hb_neighbor[i]], 0);
+    int nj = d_type_change(D.type[D.hb_neighbor[j]], 0);
+    int b = D.hb_index[(cls * SD_NT + ti) * SD_NT + nj];
+    int c = D.hb_index[(cls * SD_NT + tj) * SD_NT + ni];
+    if (b < 0 || D.tables[b].nstep == 0 || c < 0 || D.tables[c].nstep == 0) return -1;
+    return 0;
+}
+
+// HBTime, TimePrediction.c:298-483
+__device__ inline void d_hb_time(const DevP &D, const SlotSrc &S, Self &me, Slot &cur, int dup_limit) {
+    int i = me.i;
+    if (D.hb_itype[i] == SDMD_HB_SKIP) { D.hb_itype[i] = SDMD_HB_NOEVENT; return; }
+    D.hb_itype[i] = SDMD_HB_NOEVENT;
+    int bonded = D.hb_bond[i];
+    int role = D.hb_role[i];
+    if (bonded > 0) {
+        int j = bonded;
+        if (d_check_dup(D, S, cur, i, me.counter, j, SDMD_EV_HB, dup_limit)) return;
+        Pair p = d_pair_atoms(D, i, j);
+        me.npair++;
+        FindRes f = d_find_pair(D, i, j, FP_HB, p.b, p.r2, 0, 0);
+        int s, sub = SDMD_SUB_INVALID;
+        double d2, pot;
+        if (p.b < 0 && d_disc(p, f.lower) > 0) {
+            s = -1; d2 = f.lower; pot = f.lowPot;
+            sub = (f.cs == 0) ? SDMD_SUB_CORECOLLI : SDMD_SUB_TBDCAPTR;
+        } else {
+            s = 1; d2 = f.upper; pot = f.upPot;
+            if (D.method_ding) sub = (f.cs == 1) ? SDMD_SUB_TBDHBBRIK : SDMD_SUB_TBDESCAP;
+        }
+        double t = d_time(p, s, d2);
+        if (t < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); t = SD_INF; }
+        d_job_assign(D, cur, j, t, pot, sub, SDMD_EV_HB);
+    } else if ((role == 'A' || role == 'D' || role == 'S') && bonded == 0) {
+        for (int k = 0; k < 27; k++) {
+            int ncx, ncy, ncz;
+            int cell = d_neighbor_cell(D, me.cx, me.cy, me.cz, k, &ncx, &ncy, &ncz);
+            for (int j = D.celllist[D.n + cell + 1]; j; j = D.celllist[j]) {
+                if (j == i) continue;
+                int rj = D.hb_role[j];
+                bool ad = (role == 'A' && rj == 'D') || (role == 'D' && rj == 'A');
+                bool sd = (role == 'S' && D.type[j] == 2) || (rj == 'S' && D.type[i] == 2);
+                bool ss = (role == 'S' && rj == 'S');
+                if (!(ad || sd || ss)) continue;
+                if (D.hb_bond[j] != 0) continue;
+                int d = D.aa_num[i] - D.aa_num[j];
+                if (d < 0) d = -d;
+                if (!((D.protein[i] == D.protein[j] && d >= 4) || D.protein[i] != D.protein[j])) continue;
+                if (d_check_dup(D, S, cur, i, me.counter, j, SDMD_EV_HB, dup_limit)) continue;
+                Pair p = d_pair_atoms(D, i, j);
+                me.npair++;
+                if (!(p.r2 <= D.cut2)) continue;
+                if (d_check_pair_match(D, i, j) < 0) continue;
+                FindRes f = d_find_pair(D, i, j, FP_HB, p.b, p.r2, 0, 0);
+                if (!(p.b < 0 && f.cs == 1 && d_disc(p, f.lower) > 0)) continue;
+                double t = d_time(p, -1, f.lower);
+                if (t < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); t = SD_INF; }
+                d_job_assign(D, cur, j, t, f.lowPot, SDMD_SUB_TBDHBFORM, SDMD_EV_HB);
+            }
+        }
+    }
+}
+
+// HBNeighborTime, TimePrediction.c:486-579
+__device__ inline void d_hbn_time(const DevP &D, const SlotSrc &S, Self &me, Slot &cur, int dup_limit) {
+    int i = me.i;
+    int flag = 0;
+    int ns = D.hbn_status[i];
+    for (int n = 1; n <= ns; n++) {
+        int j = D.hbn_partner[5 * i + n];
+        if (flag == 0) D.hbn_pnum[i] = n;
+        if (d_check_dup(D, S, cur, i, me.counter, j, SDMD_EV_HBNE, dup_limit)) { D.hbn_pnum[i] = n; flag = 1; continue; }
+        Pair p = d_pair_atoms(D, i, j);
+        me.npair++;
+        int host, nbr, third;
+        int r = D.hb_role[i];
+        int bi = D.hb_bond[i];
+        if ((r == 'A' || r == 'D' || r == 'S') && (bi && D.hb_neighbor[bi] == j)) { host = i; nbr = j; third = bi; }
+        else { host = j; nbr = i; third = D.hb_bond[j]; }
+        FindRes f = d_find_pair(D, nbr, host, FP_NEIGHBOR, p.b, p.r2, third, 0);
+        int s, sub = SDMD_SUB_INVALID;
+        double d2, pot;
+        if (p.b < 0 && d_disc(p, f.lower) > 0) {
+            s = -1; d2 = f.lower; pot = f.lowPot;
+            sub = (f.cs == 0) ? SDMD_SUB_CORECOLLI : SDMD_SUB_TBDCAPTR;
+        } else {
+            s = 1; d2 = f.upper; pot = f.upPot;
+            if (D.method_ding) sub = (f.cs == 1) ? SDMD_SUB_WELLBOUNC : SDMD_SUB_TBDESCAP;
+        }
+        double t = d_time(p, s, d2);
+        if (t < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); t = SD_INF; }
+        if (d_job_assign(D, cur, j, t, pot, sub, SDMD_EV_HBNE)) { D.hbn_pnum[i] = n; flag = 1; }
+    }
+}
+
+// PBCandCrossCellTime, TimePrediction.c:598-632
+__device__ __forceinline__ void d_pcc_time(const DevP &D, const Self &me, Slot &cur) {
+    double best = SD_INF;
+    double pos[3] = {me.x, me.y, me.z}, spd[3] = {me.vx, me.vy, me.vz};
+    int ci[3] = {me.cx, me.cy, me.cz};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        double lo = ci[k] * D.cellsize[k];
+        double hi = (ci[k] + 1) * D.cellsize[k];
+        if (spd[k] > 0) {
+            double t = (hi - pos[k] + SD_ZERO) / spd[k];
+            if (best > t && t > 0) best = t;
+        } else if (spd[k] < 0) {
+            double t = (lo - pos[k] - SD_ZERO) / spd[k];
+            if (best > t && t > 0) best = t;
+        }
+    }
+    d_job_assign(D, cur, 0, best, 0, SDMD_SUB_INVALID, SDMD_EV_PCC);
+}
+
+// ThermostatTime, TimePrediction.c:582-595 with a pre-drawn standard normal
+__device__ __forceinline__ void d_thermostat_time(const DevP &D, Slot &cur, double g) {
+    double t = D.thermoF * ((g < 0) ? (-g) : (g));
+    d_job_assign(D, cur, 0, t, 0, SDMD_SUB_INVALID, SDMD_EV_THER);
+}
+
+__device__ __forceinline__ Self d_load_self(const DevP &D, int i) {
+    Self me;
+    me.i = i;
+    me.x = D.x[i]; me.y = D.y[i]; me.z = D.z[i];
+    me.vx = D.vx[i]; me.vy = D.vy[i]; me.vz = D.vz[i];
+    me.cx = D.cell_idx[3 * i]; me.cy = D.cell_idx[3 * i + 1]; me.cz = D.cell_idx[3 * i + 2];
+    me.counter = D.ev_counter[i];
+    me.npair = 0;
+    return me;
+}
+
+// ResetTarget (ToolFunctions.c:504-514) leaves potential / subEventType / partnerCounter untouched
+__device__ __forceinline__ Slot d_reset_slot(double pot, int sub, i64 pcounter) {
+    Slot s;
+    s.time = SD_INF; s.type = SDMD_EV_INVD; s.partner = SDMD_INVALID;
+    s.pot = pot; s.sub = sub; s.pcounter = pcounter;
+    return s;
+}
+
+// one atom of Predict, SGThread.c:162-208, executed by a single thread in reference order.
+// SORTED selects the cell-sorted tiles for the 27-cell scan (fresh link list only).
+template <bool SORTED>
+__device__ inline Slot d_predict_atom(const DevP &D, const SlotSrc &S, int i, Slot cur, double gauss, int dup_limit, int *npair) {
+    if (D.is_cons[i]) { cur.time = SD_INF; return cur; }
+    Self me = d_load_self(D, i);
+    if (!D.gel_mode) d_bond_time(D, S, me, cur, dup_limit);
+    if (SORTED) d_collision_time_sorted(D, S, me, cur, dup_limit);
+    else d_collision_time(D, S, me, cur, dup_limit);
+    d_pcc_time(D, me, cur);
+    if (D.thermostat_on) d_thermostat_time(D, cur, gauss);
+    if (D.hydrogen_bond) {
+        d_hb_time(D, S, me, cur, dup_limit);
+        d_hbn_time(D, S, me, cur, dup_limit);
+    }
+    *npair = me.npair;
+    return cur;
+}
+
+__device__ __forceinline__ SlotSrc d_live_slots(const DevP &D) {
+    SlotSrc S;
+    S.time = D.ev_time; S.pot = D.ev_pot; S.partner = D.ev_partner; S.pcounter = D.ev_pcounter; S.type = D.ev_type; S.sub = D.ev_sub;
+    return S;
+}
+__device__ __forceinline__ void d_store_slot(const DevP &D, int i, const Slot &s) {
+    D.ev_time[i] = s.time; D.ev_pot[i] = s.pot; D.ev_partner[i] = s.partner; D.ev_pcounter[i] = s.pcounter;
+    D.ev_type[i] = (uint8_t)s.type; D.ev_sub[i] = (uint8_t)s.sub;
+}
+__device__ __forceinline__ double d_next_gauss(const DevP &D) {
+    Ctl *c = D.ctl;
+    if (c->g_pos >= c->g_filled) { c->error = SDMD_ERR_STATE; return 1.0; }
+    double g = D.gauss[c->g_pos % D.g_cap];
+    c->g_pos++;
+    return g;
+}
+
+// Predict(renewList) for the event loop, SGThread.c:158-211: reset all listed slots first, then predict
+// them in list order (the partner sees the target's fresh slot, never the reverse)
+__device__ inline void d_predict_list_serial(const DevP &D, int a0, int a1) {
+    int list[2] = {a0, a1};
+    SlotSrc S = d_live_slots(D);
+    for (int k = 0; k < 2; k++) {
+        int i = list[k];
+        if (i <= 0) continue;
+        D.ev_type[i] = SDMD_EV_INVD; D.ev_time[i] = SD_INF; D.ev_partner[i] = SDMD_INVALID;
+    }
+    for (int k = 0; k < 2; k++) {
+        int i = list[k];
+        if (i <= 0) continue;
+        Slot cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
+        double g = 0;
+        if (D.thermostat_on && !D.is_cons[i]) g = d_next_gauss(D);
+        int np = 0;
+        cur = d_predict_atom<false>(D, S, i, cur, g, 0x7fffffff, &np);
+        d_store_slot(D, i, cur);
+        D.ctl->pair_predictions += np;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// UpdateCBTRun, CBT.c:56-83
+__device__ inline void d_cbt_update_run(const DevP &D, int a) {
+    const double *t = D.ev_time;
+    int *node = D.cbt_node;
+    int father, left, right, old;
+    for (father = D.cbt_leaf[a] / 2; father > 0; father /= 2) {
+        if (node[father] != a) break;
+        left = node[father * 2]; right = node[father * 2 + 1];
+        node[father] = (t[left] < t[right]) ? left : right;
+    }
+    for (; father > 0; father /= 2) {
+        old = node[father];
+        left = node[father * 2]; right = node[father * 2 + 1];
+        int w = (t[left] < t[right]) ? left : right;
+        node[father] = w;
+        if (w == old) return;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// event execution (Events.c), serial device versions
+
+// HBBarrier, Events.c:1097-1119
+__device__ inline double d_hb_barrier(const DevP &D, int a1, int a2) {
+    if (D.hb_role[a1] == 'A' || D.hb_role[a1] == 'S') { int s = a1; a1 = a2; a2 = s; }
+    int o1 = d_type_change(D.type[a1], 0), o2 = d_type_change(D.type[a2], 0);
+    if (o1 == 2 && o2 == 26) return D.hb_barrier[0];
+    if (o1 != 2 && o2 != 26) return D.hb_barrier[1];
+    return D.hb_barrier[2];
+}
+
+// HBEnergyChange, Events.c:1027-1095 (hbType 0 "_nonHB", 1 "_HB"); `tmp` and `accumPoten` carry over
+// between pairs exactly like the reference's aliased locals
+__device__ inline double d_hb_energy_change(const DevP &D, int i, int skipAtom, int hbType) {
+    double energyChange = 0, tmp = 0, accumPoten = 0;
+    int cx = D.cell_idx[3 * i], cy = D.cell_idx[3 * i + 1], cz = D.cell_idx[3 * i + 2];
+    double xi = D.x[i], yi = D.y[i], zi = D.z[i];
+    int skipNeighbor = D.hb_neighbor[skipAtom];
+    for (int k = 0; k < 27; k++) {
+        int ncx, ncy, ncz;
+        int cell = d_neighbor_cell(D, cx, cy, cz, k, &ncx, &ncy, &ncz);
+        double shx = d_shift1(cx, ncx, D.cellnum[0], D.box[0]);
+        double shy = d_shift1(cy, ncy, D.cellnum[1], D.box[1]);
+        double shz = d_shift1(cz, ncz, D.cellnum[2], D.box[2]);
+        for (int j = D.celllist[D.n + cell + 1]; j; j = D.celllist[j]) {
+            if (j == i || j == skipAtom) continue;
+            int cm = d_cm_flags(D, i, j);
+            if (cm & (SDMD_BOND_CONNECT | SDMD_CONSTRAINT_CONNECT)) continue;
+            double tx = D.x[j] + shx, ty = D.y[j] + shy, tz = D.z[j] + shz;
+            double rx = xi - tx, ry = yi - ty, rz = zi - tz;
+            double r2 = rx * rx + ry * ry + rz * rz;
+            if (r2 <= D.cutfull2) {
+                if (hbType == 0) {
+                    FindRes f = d_find_pair(D, i, j, FP_COLLISION, tmp, r2, 0, -1);
+                    tmp = f.upPot; accumPoten = f.accum;
+                } else if (j != skipNeighbor) {
+                    FindRes f = d_find_pair(D, i, j, FP_COLLISION, tmp, r2, 0, 1);
+                    tmp = f.upPot; accumPoten = f.accum;
+                }
+                if (accumPoten == SD_INF) accumPoten = 0;
+                energyChange += accumPoten;
+            }
+        }
+    }
+    return energyChange;
+}
+
+// position of b as seen from a under the cell-index minimum image, Events.c:815-823
+__device__ inline void d_image_of(const DevP &D, int a, int b, double pos[3]) {
+    pos[0] = D.x[b]; pos[1] = D.y[b]; pos[2] = D.z[b];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        int ca = D.cell_idx[3 * a + k], cb = D.cell_idx[3 * b + k];
+        if (ca != cb) {
+            if (ca == 0 && cb == D.cellnum[k] - 1) pos[k] -= D.box[k];
+            else if (ca == D.cellnum[k] - 1 && cb == 0) pos[k] += D.box[k];
+        }
+    }
+}
+
+// InteractionEvent, Events.c:798-1024
+__device__ inline void d_interaction_event(const DevP &D, int i, int j, int hbEvent) {
+    double pi[3] = {D.x[i], D.y[i], D.z[i]}, pj[3];
+    d_image_of(D, i, j, pj);
+    double rx = pi[0] - pj[0], ry = pi[1] - pj[1], rz = pi[2] - pj[2];
+    double wx = D.vx[i] - D.vx[j], wy = D.vy[i] - D.vy[j], wz = D.vz[i] - D.vz[j];
+    double d2 = rx * rx + ry * ry + rz * rz;
+    double b = rx * wx + ry * wy + rz * wz;
+    double mi = D.mass[i], mj = D.mass[j];
+    double reduced = mi * mj / (mi + mj);
+    double potential = D.ev_pot[i];
+    int sub = D.ev_sub[i];
+    int s_vel = 0;
+
+    if (hbEvent && (sub == SDMD_SUB_TBDHBFORM || sub == SDMD_SUB_TBDHBBRIK)) {  // :832-943
+        int ni = D.hb_neighbor[i], nj = D.hb_neighbor[j];
+        if ((d_neighbor_connected(D, i, nj) || d_neighbor_connected(D, j, ni)) && sub == SDMD_SUB_TBDHBFORM) {
+            D.hb_itype[i] = SDMD_HB_SKIP;
+            return;
+        }
+        double pni[3], pnj[3];
+        d_image_of(D, i, ni, pni);
+        d_image_of(D, i, nj, pnj);
+        double ax = pi[0] - pnj[0], ay = pi[1] - pnj[1], az = pi[2] - pnj[2];
+        double bx = pj[0] - pni[0], by = pj[1] - pni[1], bz = pj[2] - pni[2];
+        double rni2 = ax * ax + ay * ay + az * az;
+        double rnj2 = bx * bx + by * by + bz * bz;
+        double acc0 = d_hb_energy_change(D, i, j, 0);
+        double acc1 = d_hb_energy_change(D, j, i, 0);
+        double acc2 = d_hb_energy_change(D, i, j, 1);
+        double acc3 = d_hb_energy_change(D, j, i, 1);
+        double acc4 = d_find_pair(D, nj, i, FP_NEIGHBOR, 0.0, rni2, j, 0).accum;
+        double acc5 = d_find_pair(D, ni, j, FP_NEIGHBOR, 0.0, rnj2, i, 0).accum;
+        if (sub == SDMD_SUB_TBDHBFORM) {
+            potential -= d_hb_barrier(D, i, j);
+            potential += (acc2 - acc0 + acc3 - acc1 + acc4 + acc5);
+        } else {
+            potential += d_hb_barrier(D, i, j);
+            potential += (acc0 - acc2 + acc1 - acc3 - acc4 - acc5);
+        }
+        if (potential < -0.5 * SD_INF && sub == SDMD_SUB_TBDHBBRIK) { D.hb_itype[i] = SDMD_HB_SKIP; return; }
+        else if (potential > 0.5 * SD_INF && sub == SDMD_SUB_TBDHBFORM) { D.hb_itype[i] = SDMD_HB_SKIP; return; }
+        if (b * b - 2 * d2 * potential / reduced > 0) {
+            if (sub == SDMD_SUB_TBDHBFORM) { sub = SDMD_SUB_WELLCAPTR; D.hb_itype[i] = SDMD_HB_FORM; }
+            else { sub = SDMD_SUB_WELLESCAP; D.hb_itype[i] = SDMD_HB_BREAK; }
+        } else {
+            if (sub == SDMD_SUB_TBDHBFORM) { D.hb_itype[i] = SDMD_HB_SKIP; return; }
+            potential = 0;
+            sub = SDMD_SUB_WELLBOUNC;
+            D.hb_itype[i] = SDMD_HB_NOEVENT;
+        }
+        D.ev_sub[i] = (uint8_t)sub;
+    }
+
+    switch (sub) {  // :945-1003
+        case SDMD_SUB_CORECOLLI: s_vel = 1; potential = 0; break;
+        case SDMD_SUB_WELLBOUNC: s_vel = (b < 0) ? 1 : -1; potential = 0; break;
+        case SDMD_SUB_WELLCAPTR: s_vel = -1; break;
+        case SDMD_SUB_WELLESCAP: s_vel = (b < 0) ? -1 : 1; break;
+        case SDMD_SUB_TBDCAPTR:
+            if (b * b - 2 * d2 * potential / reduced <= 0) { potential = 0; s_vel = 1; }
+            else s_vel = -1;
+            break;
+        case SDMD_SUB_TBDESCAP:
+            if (b * b - 2 * d2 * potential / reduced <= 0) { potential = 0; s_vel = (b < 0) ? 1 : -1; }
+            else s_vel = (b < 0) ? -1 : 1;
+            break;
+        default: D.ctl->error = SDMD_ERR_STATE; return;
+    }
+    double phi = (-1 * b + s_vel * sqrt((b * b - 2 * d2 * potential / reduced))) / ((mi + mj) * d2);  // :1005-1006
+    if (phi != phi) { D.ctl->error = SDMD_ERR_STATE; return; }
+    if (!D.is_cons[i]) {
+        double f = mj * phi;
+        D.vx[i] = D.vx[i] + f * rx; D.vy[i] = D.vy[i] + f * ry; D.vz[i] = D.vz[i] + f * rz;
+    }
+    if (!D.is_cons[j]) {
+        double f = mi * phi;
+        D.vx[j] = D.vx[j] - f * rx; D.vy[j] = D.vy[j] - f * ry; D.vz[j] = D.vz[j] - f * rz;
+    }
+}
+
+// ListRefresh(target, list, 1, 4), ToolFunctions.c:572-597
+__device__ inline void d_list_refresh(const DevP &D, int a, int target) {
+    int *l = &D.hbn_partner[5 * a];
+    int i = d_find_in_hbn(D, a, target);
+    if (i) {
+        int n = i + 1;
+        while (n <= 4 && l[n] != 0) { l[i] = l[n]; i++; n++; }
+        l[i] = 0;
+    }
+}
+
+// HBEvent, Events.c:275-393
+__device__ inline void d_hb_event(const DevP &D, int i, int j, int ni, int nj) {
+    if (D.hb_itype[i] == SDMD_HB_FORM) {
+        D.hb_bond[i] = j; D.hb_bond[j] = i;
+        D.type[i] = d_type_change(D.type[i], 1);
+        D.type[j] = d_type_change(D.type[j], 1);
+        int t;
+        t = ++D.hbn_status[i];  D.hbn_partner[5 * i + t] = D.hb_neighbor[j];
+        t = ++D.hbn_status[j];  D.hbn_partner[5 * j + t] = D.hb_neighbor[i];
+        t = ++D.hbn_status[ni]; D.hbn_partner[5 * ni + t] = j;
+        t = ++D.hbn_status[nj]; D.hbn_partner[5 * nj + t] = i;
+        D.ctl->hbnumformed++;
+    } else if (D.hb_itype[i] == SDMD_HB_BREAK) {
+        D.hb_bond[i] = 0; D.hb_bond[j] = 0;
+        D.type[i] = d_type_change(D.type[i], 0);
+        D.type[j] = d_type_change(D.type[j], 0);
+        --D.hbn_status[i];  d_list_refresh(D, i, D.hb_neighbor[j]);
+        --D.hbn_status[j];  d_list_refresh(D, j, D.hb_neighbor[i]);
+        --D.hbn_status[ni]; d_list_refresh(D, ni, j);
+        --D.hbn_status[nj]; d_list_refresh(D, nj, i);
+        D.ctl->hbnumformed--;
+    }
+}
+
+// ThermostatEvent (Andersen), Events.c:396-420; RandomVelocity ToolFunctions.c:600-610
+__device__ inline void d_thermostat_event(const DevP &D, int i) {
+    double speed[3];
+    double variance = D.ctl->temperature / D.mass[i];
+    double sd = sqrt(variance);
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) {
+        do {
+            speed[k] = d_next_gauss(D) * sd + 0;
+            speed[k] += 0.0;
+        } while (speed[k] == 0 && !D.ctl->error);
+    }
+    D.vx[i] = speed[0]; D.vy[i] = speed[1]; D.vz[i] = speed[2];
+}
+
+__device__ __forceinline__ int d_cell_of(const DevP &D, double x, double y, double z, int idx[3]) {
+    double co[3] = {x, y, z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        idx[k] = (int)(co[k] / D.cellsize[k]);  // Events.c:132-133
+        if (idx[k] == D.cellnum[k]) idx[k]--;   // Events.c:143-145
+    }
+    return idx[2] * D.cellnum[0] * D.cellnum[1] + idx[1] * D.cellnum[0] + idx[0];  // 0-based
+}
+
+// PBCandCrossCellEvent, Events.c:248-272 = PBC("part") :230-238 + LinkList("part") :158-199
+__device__ inline void d_pcc_event(const DevP &D, int i) {
+    int old[3] = {D.cell_idx[3 * i], D.cell_idx[3 * i + 1], D.cell_idx[3 * i + 2]};
+    double co[3] = {D.x[i], D.y[i], D.z[i]};
+    bool edge = false;
+#pragma unroll
+    for (int k = 0; k < 3; k++) edge = edge || old[k] == 0 || old[k] == D.cellnum[k] - 1;
+    if (edge) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (co[k] >= D.box[k]) co[k] -= D.box[k];
+            else if (co[k] < 0) co[k] += D.box[k];
+        }
+        D.x[i] = co[0]; D.y[i] = co[1]; D.z[i] = co[2];
+    }
+    int idx[3];
+    int newCell = d_cell_of(D, co[0], co[1], co[2], idx);
+    int oldCell = old[2] * D.cellnum[0] * D.cellnum[1] + old[1] * D.cellnum[0] + old[0];
+    D.cell_idx[3 * i] = idx[0]; D.cell_idx[3 * i + 1] = idx[1]; D.cell_idx[3 * i + 2] = idx[2];
+    int *cl = D.celllist;
+    int next = oldCell + 1 + D.n;
+    if (cl[next] == 0) { D.ctl->error = SDMD_ERR_STATE; return; }
+    while (cl[next] != i) {
+        next = cl[next];
+        if (next == 0) { D.ctl->error = SDMD_ERR_STATE; return; }
+    }
+    cl[next] = cl[i];
+    next = newCell + 1 + D.n;
+    cl[i] = cl[next];
+    cl[next] = i;
+}
+
+// DoEvent, Events.c:25-114
+__device__ inline void d_do_event(const DevP &D, int i, int j) {
+    Ctl *c = D.ctl;
+    switch (D.ev_type[i]) {
+        case SDMD_EV_COLI: d_interaction_event(D, i, j, 0); c->n_coli++; break;
+        case SDMD_EV_BOND: d_interaction_event(D, i, j, 0); c->n_bond++; break;
+        case SDMD_EV_HBNE: d_interaction_event(D, i, j, 0); c->n_hbne++; break;
+        case SDMD_EV_HB: {
+            int ni = D.hb_neighbor[i], nj = D.hb_neighbor[j];
+            d_interaction_event(D, i, j, 1);
+            d_hb_event(D, i, j, ni, nj);
+            c->n_hb++;
+            break;
+        }
+        case SDMD_EV_THER: d_thermostat_event(D, i); c->n_ther++; break;
+        case SDMD_EV_PCC: d_pcc_event(D, i); c->n_pcc++; break;
+        default: c->error = SDMD_ERR_STATE; break;
+    }
+}
