@@ -1,0 +1,479 @@
+#!/usr/bin/env python
+"""bench.py — sDMD hot path on B200: one JSON line per run (see the contract in the task statement).
+
+Workloads (``--workload``):
+  pass1m  (default) BASELINE.json configs[4] / BASELINE.md C5(i): synthetic 1M-particle GEL box (hard core 4.0 A +
+          step at 6.5 A, simple-cubic 8 A lattice + 0.3 A jitter, T*=0.6, Andersen 6.0).  One step = one
+          full-system pass of the hot path: PBC("full") + LinkList("full") + Predict(all atoms) + CreateCBT.
+          metric = pair time-predictions/s (CalculateParameters-equivalent pair evaluations).
+  loop    C5(ii): the device-resident event loop on the same box; one step = 256 loop iterations;
+          metric = DMD events/s (committed events).
+  remd    configs[1]: ala10 replica exchange, one replica per GPU, temperatures of demo/REMD/REMDConfig.txt,
+          ExchangeRate 50; one step = run to the next exchange boundary + CalPotenE + exchange (NCCL all-gather);
+          metric = REMD replica-events/s (sum over replicas).
+
+``--impl reference`` times the reference's CPU implementation of the same path on the host cores: the oracle
+port (oracle/sdmd_oracle.c, pinned bit-exact against the reference) for the 1M box — the reference itself
+cannot allocate its (N+1)^2 connectionMap there — and the compiled reference (oracle/_ref) for ala10.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+REMD_TEMPS_K = [236.5, 250, 263.5, 277.5, 292.5, 308, 324.5, 341]  # first 8 of demo/REMD/REMDConfig.txt
+KB = 0.0019872041  # REMDExec.c:19
+
+
+def reduced_T(kelvin: float) -> float:
+    return float("%lf" % (kelvin * KB))  # sREMD prints "%lf", the replica parses it with atof
+
+
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.samples.append([s.strip() for s in line.split(",")])
+                if self.stop_flag.is_set():
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(s[1]) for s in self.samples if len(s) > 7 and s[1].replace(".", "").isdigit()]
+        mx = [float(s[2]) for s in self.samples if len(s) > 7 and s[2].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            if len(s) > 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class Dist:
+    """torch.distributed plumbing: rendezvous, barrier, max-over-ranks."""
+
+    def __init__(self, want_gpus: int, backend: str | None = None):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.torch = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            self.torch, self.dist = torch, dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            if backend is None:
+                backend = "nccl" if torch.cuda.is_available() else "gloo"
+            if backend == "nccl":
+                torch.cuda.set_device(self.local_rank)
+            dist.init_process_group(backend=backend)
+            self.backend = backend
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def _tensor(self, vals):
+        t = self.torch.tensor(vals, dtype=self.torch.float64)
+        return t.cuda() if self.backend == "nccl" else t
+
+    def max(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self._tensor([x])
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self._tensor([x])
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def bcast_bytes(self, b: bytes | None, n: int) -> bytes:
+        if self.world == 1:
+            return b
+        t = self.torch.zeros(n, dtype=self.torch.uint8)
+        if self.rank == 0:
+            t = self.torch.frombuffer(bytearray(b), dtype=self.torch.uint8).clone()
+        if self.backend == "nccl":
+            t = t.cuda()
+        self.dist.broadcast(t, src=0)
+        return bytes(t.cpu().numpy().tobytes())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------
+# workload: pass1m
+# ----------------------------------------------------------------------------------------------------
+def make_box(n_axis, rank):
+    from sdmd_b200.synth import gel_box
+    hv, rng = gel_box(n_axis, a=8.0, jitter=0.3, seed=1575263273 + rank)
+    gauss = rng.standard_normal(hv.natom)
+    return hv, gauss
+
+
+def cuda_pass(args, dist):
+    from sdmd_b200 import capi
+    capi.build()
+    n_axis = args.n_axis
+    hv, gauss = make_box(n_axis, dist.rank)
+    n = hv.natom
+    rep = capi.Replica(hv, device=dist.local_rank)
+    rep.rng_feed(gauss)
+
+    def one_pass():
+        rep.rng_seek(0)
+        rep.pbc_full(); rep.cell_build(); rep.predict_all(); rep.cbt_build()
+
+    # -------- device-resident timing (`value`) --------
+    for _ in range(args.warmup):
+        one_pass()
+    rep.synchronize()
+    pairs0 = rep.stats()["pair_predictions"]
+    rep.reset_kernel_stats()
+    sampler = ClockSampler(dist.local_rank)
+    sampler.start()
+    dist.barrier()
+    rep.timer_begin()
+    for _ in range(args.steps):
+        one_pass()
+    ms = rep.timer_end()
+    dist.barrier()
+    clocks = sampler.finish()
+    ms = dist.max(ms)
+    launches = rep.launch_count()
+    pairs = rep.stats()["pair_predictions"] - pairs0
+    total_pairs = dist.sum(float(pairs))
+    kst = {k: rep.kernel_stats(k) for k in ("predict_all", "predict_all_fixup", "cell_build", "cbt_build", "predict_all_rounds")}
+
+    # -------- end to end through the C-ABI with HOST buffers (`e2e`) --------
+    host = [np.ascontiguousarray(a.copy()) for a in (hv.x, hv.y, hv.z, hv.vx, hv.vy, hv.vz)]
+    g_host = np.ascontiguousarray(gauss.copy())
+    for a in host + [g_host]:
+        capi.host_register(a)
+    hv_e2e = hv  # arrays used by upload_coords
+    hv_e2e.x, hv_e2e.y, hv_e2e.z, hv_e2e.vx, hv_e2e.vy, hv_e2e.vz = host
+    h2d = sum(a.nbytes for a in host) + g_host.nbytes
+    d2h = 120 + 24  # sdmd_run_stats + AssignJob result
+
+    def one_e2e():
+        rep.upload_coords(hv_e2e)
+        rep.rng_refeed(g_host)
+        rep.pbc_full(); rep.cell_build(); rep.predict_all(); rep.cbt_build()
+        rep.assign_job()
+        return rep.stats()
+
+    for _ in range(max(1, args.warmup // 2)):
+        one_e2e()
+    pairs0 = rep.stats()["pair_predictions"]
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_e2e()
+    rep.synchronize()
+    e2e_s = dist.max(time.perf_counter() - t0)
+    e2e_pairs = dist.sum(float(rep.stats()["pair_predictions"] - pairs0))
+    for a in host + [g_host]:
+        capi.host_unregister(a)
+
+    # -------- extras: advance roofline + event loop on the same box --------
+    rep.reset_kernel_stats()
+    for _ in range(50):
+        rep.advance(1e-7)
+    adv_ms, adv_n = rep.kernel_stats("advance")
+    extra = {"advance_us": 1e3 * adv_ms / adv_n, "advance_GBps": 88.0 * n / (adv_ms / adv_n) / 1e6}
+    rep.rng_refeed(np.random.default_rng(7).standard_normal(n + 200000))
+    rep.cell_build(); rep.predict_all(); rep.cbt_build()
+    st0 = rep.stats()
+    t0 = time.perf_counter()
+    st1, _ = rep.run(max_iter=2048)
+    loop_s = time.perf_counter() - t0
+    extra["loop_events_per_s_1M"] = (st1["frame"] - st0["frame"]) / loop_s
+    extra["loop_iterations_per_s_1M"] = (st1["iterations"] - st0["iterations"]) / loop_s
+
+    peak, peak_src = load_peaks()
+    pa_ms, pa_n = kst["predict_all"]
+    per_launch_ms = pa_ms / max(pa_n, 1)
+    alg_bytes = 88.0 * n  # 56 B own state read + 32 B slot written per atom
+    achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "k_predict_all_round (round 0)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+            "kernel_ms": per_launch_ms, "kernel_share_of_step": pa_ms / ms if ms else None,
+            "pairs_per_s_kernel": (pairs / max(pa_n, 1)) / (per_launch_ms * 1e-3)}
+    step_ms = ms / args.steps
+    out = {
+        "metric": "pair time-predictions/s", "value": total_pairs / (ms * 1e-3), "unit": "pairs/s", "n_gpus": dist.world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C5(i) synthetic 1M-particle GEL hard-sphere+step box: full-system pass PBC+LinkList+Predict(all)+CreateCBT",
+                   "natom_per_gpu": n, "lattice": f"{n_axis}^3 simple cubic, a=8.0 A, jitter 0.3 A", "T_reduced": 0.6,
+                   "cutoff_A": 9.0, "parallelism": f"replicas x{dist.world} (one independent box per GPU, no collective)",
+                   "l2": "working set ~190 MB per pass > 126 MB L2 (no explicit flush)"},
+        "e2e": {"value": e2e_pairs / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_s / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+        "kernels_ms_per_step": {k: v[0] / args.steps for k, v in kst.items() if k != "predict_all_rounds"},
+        "predict_all_rounds": kst["predict_all_rounds"][0] / max(kst["predict_all_rounds"][1], 1),
+        "extra": extra,
+    }
+    if dist.rank == 0 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_pass_baseline(args)
+    rep.close()
+    return out
+
+
+def cpu_pass_baseline(args, n_axis=None, steps=1):
+    """The oracle port (reference algorithm, plain C, 1 thread) on the same synthetic box."""
+    from oracle.oracle_py import Oracle
+    n_axis = n_axis or args.n_axis
+    hv, gauss = make_box(n_axis, 0)
+    o = Oracle(hv)
+    t_best, pairs = None, 0
+    for _ in range(steps):
+        hv.reset_slots()
+        o.rng_feed(gauss)
+        p0 = o.stats()["pair_predictions"]
+        t0 = time.perf_counter()
+        o.pbc_full(); o.cell_build(); o.predict_all(); o.cbt_build()
+        dt = time.perf_counter() - t0
+        pairs = o.stats()["pair_predictions"] - p0
+        t_best = dt if t_best is None else min(t_best, dt)
+    return {"value": pairs / t_best, "unit": "pairs/s", "cores": 1, "kind": "port",
+            "sample": f"one full-system pass over the same {hv.natom}-atom box ({pairs} pair evaluations, {t_best:.2f} s); the "
+                      "reference itself cannot allocate its (N+1)^2 connectionMap at this size, the port is pinned bit-exact to it",
+            "seconds": t_best}
+
+
+def reference_pass(args, dist):
+    if dist.rank != 0:
+        return None
+    t0 = time.perf_counter()
+    per = []
+    pairs = 0
+    from oracle.oracle_py import Oracle
+    hv, gauss = make_box(args.n_axis, 0)
+    o = Oracle(hv)
+    for k in range(args.warmup + args.steps):
+        hv.reset_slots()
+        o.rng_feed(gauss)
+        p0 = o.stats()["pair_predictions"]
+        t1 = time.perf_counter()
+        o.pbc_full(); o.cell_build(); o.predict_all(); o.cbt_build()
+        dt = time.perf_counter() - t1
+        if k >= args.warmup:
+            per.append(dt)
+            pairs += o.stats()["pair_predictions"] - p0
+        if time.perf_counter() - t0 > 150 and len(per) >= 1:
+            break
+    tot = sum(per)
+    v = pairs / tot
+    return {
+        "impl": "reference", "metric": "pair time-predictions/s", "value": v, "unit": "pairs/s", "n_gpus": dist.world,
+        "steps": len(per), "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(per), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C5(i) synthetic 1M-particle GEL hard-sphere+step box: full-system pass PBC+LinkList+Predict(all)+CreateCBT",
+                   "natom_per_gpu": hv.natom},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": 1, "kind": "port",
+                         "sample": f"{len(per)} full passes over the {hv.natom}-atom box; reference algorithm restated in C "
+                                   "(oracle/sdmd_oracle.c), single thread like the reference"},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+# ----------------------------------------------------------------------------------------------------
+# workload: remd (ala10, one replica per GPU)
+# ----------------------------------------------------------------------------------------------------
+def ala10_view(rank):
+    from sdmd_b200.hostview import HostView
+    pre = HostView.from_snapshot(ROOT / "tests" / "golden" / "ala10_pre.npz")
+    hv = pre.copy()
+    hv.target_temperature = reduced_T(REMD_TEMPS_K[rank % len(REMD_TEMPS_K)])
+    hv.timestep = 1e12
+    return hv
+
+
+def cuda_remd(args, dist):
+    from sdmd_b200 import capi
+    capi.build()
+    hv = ala10_view(dist.rank)
+    rep = capi.Replica(hv, device=dist.local_rank)
+    if dist.world > 1:
+        uid = capi.nccl_unique_id() if dist.rank == 0 else None
+        uid = dist.bcast_bytes(uid, 128)
+        rep.remd_init(dist.world, dist.rank, uid, server_seed=12345)
+    else:
+        rep.remd_seed_server(12345)
+    np.random.seed(1 + dist.rank)
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1575263273 + dist.rank)
+    rep.rng_fill_libc(hv.natom + 400000)
+    rep.pbc_full(); rep.cell_build(); rep.predict_all(); rep.cbt_build()
+    num, T = dist.rank + 1, hv.target_temperature
+    rate = float(args.exchange_rate)
+    next_x = rate
+    state = {"num": num, "T": T, "next": next_x}
+
+    def one_step():
+        if rep.rng_available() < 300000:
+            rep.rng_fill_libc(300000)
+        st, _ = rep.run(t_until=state["next"])
+        e = rep.potential_energy()
+        state["num"], state["T"] = rep.remd_exchange(e, state["num"], state["T"])
+        state["next"] += rate
+        return st
+
+    for _ in range(args.warmup):
+        one_step()
+    f0 = rep.stats()["frame"]
+    it0 = rep.stats()["iterations"]
+    sampler = ClockSampler(dist.local_rank)
+    sampler.start()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st = one_step()
+    rep.synchronize()
+    dt = time.perf_counter() - t0
+    dist.barrier()
+    clocks = sampler.finish()
+    dt = dist.max(dt)
+    ev = dist.sum(float(st["frame"] - f0))
+    its = dist.sum(float(st["iterations"] - it0))
+    run_ms, run_n = rep.kernel_stats("run")
+    peak, peak_src = load_peaks()
+    out = {
+        "metric": "REMD replica-events/s", "value": ev / dt, "unit": "events/s", "n_gpus": dist.world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "ala10 (tests/golden/ala10_pre.npz, from the reference's input/ala10.gro)",
+        "config": {"workload": "ala10 REMD, one replica per GPU", "temperatures_K": REMD_TEMPS_K[:dist.world],
+                   "exchange_rate_tu": rate, "natom": hv.natom, "parallelism": f"replica-parallel x{dist.world}, NCCL all-gather exchange"},
+        "e2e": {"value": ev / dt, "unit": "events/s", "h2d_bytes_per_step": 8 * 300000, "d2h_bytes_per_step": 120 + 8},
+        "iterations_per_s": its / dt, "gpu_launches": rep.launch_count(), "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_run_cta (persistent single-CTA event loop, latency bound)", "achieved": None,
+                     "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
+                     "us_per_iteration": 1e3 * run_ms / max(its / dist.world, 1)},
+    }
+    rep.close()
+    return out
+
+
+def reference_remd(args, dist):
+    """The unmodified reference (oracle/_ref/sDMD_ref) on ala10, one process per replica on the host cores."""
+    if dist.rank != 0:
+        return None
+    ref = ROOT / "oracle" / "_ref" / "sDMD_ref"
+    if not ref.exists():
+        return {"impl": "reference", "unavailable": "oracle/_ref/sDMD_ref not built"}
+    import shutil
+    import tempfile
+    R = dist.world
+    tu = float(args.exchange_rate) * (args.steps + args.warmup)
+    procs, dirs = [], []
+    t0 = time.perf_counter()
+    for r in range(R):
+        d = Path(tempfile.mkdtemp(prefix=f"sdmd_ref_{r}_"))
+        shutil.copytree(ROOT / "oracle" / "_ref" / "input", d / "input")
+        p = d / "input" / "parameter.txt"
+        lines = p.read_text().splitlines()
+        lines[1] = "Time               %g" % tu
+        lines[2] = "T(reduced)         %g" % reduced_T(REMD_TEMPS_K[r % 8])
+        p.write_text("\n".join(lines) + "\n")
+        (d / "out").mkdir()
+        procs.append(subprocess.Popen([str(ref), "-f", "ala10.gro", "-i", str(d / "input"), "-o", str(d / "out")],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))
+        dirs.append(d)
+    events = 0
+    for p in procs:
+        out, _ = p.communicate()
+        for line in out.replace("\r", "\n").splitlines():
+            if line.startswith("Calculate event times:"):
+                events += int(line.split(":")[1])
+    dt = time.perf_counter() - t0
+    for d in dirs:
+        shutil.rmtree(d, ignore_errors=True)
+    v = events / dt
+    return {"impl": "reference", "metric": "REMD replica-events/s", "value": v, "unit": "events/s", "n_gpus": R,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps + args.warmup, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "ala10",
+            "config": {"workload": "ala10 REMD, one replica per GPU", "temperatures_K": REMD_TEMPS_K[:R]},
+            "cpu_baseline": {"value": v, "unit": "events/s", "cores": R, "kind": "reference",
+                             "sample": f"{R} unmodified sDMD processes x {tu:g} time units incl. start-up (SDEnergyMin); no exchange server"},
+            "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="pass1m", choices=["pass1m", "remd"])
+    ap.add_argument("--n-axis", type=int, default=100, help="lattice points per axis of the synthetic box (100 -> 1M atoms)")
+    ap.add_argument("--exchange-rate", type=float, default=50.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
+
+    dist = Dist(args.gpus, backend="gloo" if args.impl == "reference" else None)
+    try:
+        if args.impl == "reference":
+            out = reference_pass(args, dist) if args.workload == "pass1m" else reference_remd(args, dist)
+        else:
+            out = cuda_pass(args, dist) if args.workload == "pass1m" else cuda_remd(args, dist)
+        if dist.rank == 0 and out is not None:
+            print(json.dumps(out))
+            sys.stdout.flush()
+    finally:
+        dist.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -216,6 +216,10 @@ int  sdmd_cuda_rng_feed(sdmd_ctx *ctx, const double *gauss, int64_t n);
  * and feed them.  Uses the process-global rand() stream the reference seeded with srand(seed). */
 int  sdmd_cuda_rng_fill_libc(sdmd_ctx *ctx, int64_t n);
 int64_t sdmd_cuda_rng_available(const sdmd_ctx *ctx);
+/* move the consumption cursor back/forward inside the fed window (benchmarks replay one synthetic stream) */
+int  sdmd_cuda_rng_seek(sdmd_ctx *ctx, int64_t pos);
+/* drop everything fed so far and start a fresh stream */
+int  sdmd_cuda_rng_reset(sdmd_ctx *ctx);
 /* the host-side generator by itself (no ctx): one draw of Maxwell_Boltzmann_Distribution(0,1) */
 double sdmd_host_gaussian_libc(void);
 
@@ -287,7 +291,14 @@ double sdmd_cuda_kernel_ms(const sdmd_ctx *ctx, const char *name);
  * "advance", "predict_all" (round 0), "predict_all_fixup", "cell_build", "cbt_build", "run" */
 int  sdmd_cuda_kernel_stats(const sdmd_ctx *ctx, const char *name, double *total_ms, int64_t *count);
 void sdmd_cuda_reset_kernel_stats(sdmd_ctx *ctx);
-void sdmd_cuda_set_timing(sdmd_ctx *ctx, int on);   /* per-call CUDA-event timing (synchronises); default on */
+/* device-time bracket (CUDA events on the context's stream) around any sequence of calls */
+int  sdmd_cuda_timer_begin(sdmd_ctx *ctx);
+int  sdmd_cuda_timer_end(sdmd_ctx *ctx, double *ms);
+int  sdmd_cuda_synchronize(sdmd_ctx *ctx);
+/* page-lock caller-owned host buffers used with upload_* / download_* / rng_feed */
+int  sdmd_cuda_host_register(void *ptr, size_t bytes);
+int  sdmd_cuda_host_unregister(void *ptr);
+void sdmd_cuda_set_timing(sdmd_ctx *ctx, int on);   /* per-launch CUDA-event brackets (asynchronous, resolved on query); default on */
 int64_t sdmd_cuda_launch_count(const sdmd_ctx *ctx);
 void *sdmd_cuda_stream(const sdmd_ctx *ctx);   /* cudaStream_t */
 

@@ -29,7 +29,8 @@ ABI_SYMBOLS = [
     "sdmd_cuda_create", "sdmd_cuda_destroy", "sdmd_cuda_last_error", "sdmd_cuda_device_count", "sdmd_cuda_cell_grid",
     "sdmd_cuda_upload_coords", "sdmd_cuda_upload_celllist", "sdmd_cuda_download", "sdmd_cuda_download_slots",
     "sdmd_cuda_download_celllist", "sdmd_cuda_download_cbt",
-    "sdmd_cuda_rng_feed", "sdmd_cuda_rng_fill_libc", "sdmd_cuda_rng_available", "sdmd_host_gaussian_libc",
+    "sdmd_cuda_rng_feed", "sdmd_cuda_rng_fill_libc", "sdmd_cuda_rng_available", "sdmd_cuda_rng_seek", "sdmd_cuda_rng_reset", "sdmd_host_gaussian_libc",
+    "sdmd_cuda_timer_begin", "sdmd_cuda_timer_end", "sdmd_cuda_synchronize", "sdmd_cuda_host_register", "sdmd_cuda_host_unregister",
     "sdmd_cuda_pbc_full", "sdmd_cuda_cell_build", "sdmd_cuda_predict_all", "sdmd_cuda_predict", "sdmd_cuda_cbt_build",
     "sdmd_cuda_cbt_update", "sdmd_cuda_assign_job", "sdmd_cuda_advance", "sdmd_cuda_add_time", "sdmd_cuda_hazard_check",
     "sdmd_cuda_cell_move", "sdmd_cuda_do_event", "sdmd_cuda_potential_energy", "sdmd_cuda_kinetic_energy",
@@ -88,6 +89,13 @@ def lib():
     L.sdmd_cuda_rng_available.argtypes = [vp]
     L.sdmd_cuda_rng_available.restype = C.c_int64
     L.sdmd_host_gaussian_libc.restype = C.c_double
+    L.sdmd_cuda_rng_seek.argtypes = [vp, C.c_int64]
+    L.sdmd_cuda_rng_reset.argtypes = [vp]
+    L.sdmd_cuda_timer_begin.argtypes = [vp]
+    L.sdmd_cuda_timer_end.argtypes = [vp, dp]
+    L.sdmd_cuda_synchronize.argtypes = [vp]
+    L.sdmd_cuda_host_register.argtypes = [vp, C.c_size_t]
+    L.sdmd_cuda_host_unregister.argtypes = [vp]
     for f in ("pbc_full", "cell_build", "predict_all", "cbt_build", "do_event"):
         getattr(L, "sdmd_cuda_" + f).argtypes = [vp]
     L.sdmd_cuda_predict.argtypes = [vp, i32p]
@@ -218,6 +226,20 @@ class Replica:
     def rng_available(self):
         return int(self.L.sdmd_cuda_rng_available(self.h))
 
+    def rng_seek(self, pos): _check(self.L.sdmd_cuda_rng_seek(self.h, int(pos)), "rng_seek")
+
+    def rng_refeed(self, g):
+        """Fresh stream: drop what was fed, then feed ``g``."""
+        _check(self.L.sdmd_cuda_rng_reset(self.h), "rng_reset")
+        self.rng_feed(g)
+    def synchronize(self): _check(self.L.sdmd_cuda_synchronize(self.h), "synchronize")
+    def timer_begin(self): _check(self.L.sdmd_cuda_timer_begin(self.h), "timer_begin")
+
+    def timer_end(self) -> float:
+        ms = C.c_double()
+        _check(self.L.sdmd_cuda_timer_end(self.h, C.byref(ms)), "timer_end")
+        return ms.value
+
     # ---- hot path, reference names ----
     def pbc_full(self): _check(self.L.sdmd_cuda_pbc_full(self.h), "pbc_full")
     def cell_build(self): _check(self.L.sdmd_cuda_cell_build(self.h), "cell_build")
@@ -297,6 +319,14 @@ class Replica:
         t = CRemdTemp(int(num), 0, float(T))
         _check(self.L.sdmd_remd_exchange(self.h, float(epot), C.byref(t), 0), "remd_exchange")
         return t.num, t.T
+
+
+def host_register(arr: np.ndarray):
+    _check(lib().sdmd_cuda_host_register(arr.ctypes.data, arr.nbytes), "host_register")
+
+
+def host_unregister(arr: np.ndarray):
+    lib().sdmd_cuda_host_unregister(arr.ctypes.data)
 
 
 def nccl_unique_id() -> bytes:

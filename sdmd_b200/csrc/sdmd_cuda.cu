@@ -28,6 +28,7 @@ static int set_err(int code, const char *what, cudaError_t e = cudaSuccess) {
     } while (0)
 
 struct KStat { double ms = 0; long n = 0; };
+struct PendingEv { std::string name; cudaEvent_t a, b; };
 
 struct sdmd_ctx {
     int device = 0;
@@ -57,8 +58,10 @@ struct sdmd_ctx {
     bool cells_fresh = false;
     bool timing = true;
     std::map<std::string, KStat> kstat;
+    std::vector<PendingEv> pending;      // launched, not yet resolved (kept asynchronous)
+    std::vector<cudaEvent_t> ev_pool;
     long launches = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
     // big-N event loop graph
     cudaGraphExec_t loop_graph = nullptr;
     int loop_graph_len = 0;
@@ -93,21 +96,43 @@ static int dupload(sdmd_ctx *c, T **p, const T *src, size_t count) {
         if (rc_) return rc_; \
     } while (0)
 
+static cudaEvent_t pool_get(sdmd_ctx *c) {
+    if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+// resolve every pending (begin, end) event pair into the per-kernel accumulators
+static void resolve_pending(sdmd_ctx *c) {
+    for (PendingEv &p : c->pending) {
+        cudaEventSynchronize(p.b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, p.a, p.b);
+        KStat &k = c->kstat[p.name];
+        k.ms += ms;
+        k.n++;
+        c->ev_pool.push_back(p.a);
+        c->ev_pool.push_back(p.b);
+    }
+    c->pending.clear();
+}
+// CUDA-event bracket on the launching stream; does not synchronise (resolved lazily)
 struct Timer {
     sdmd_ctx *c;
-    const char *name;
-    Timer(sdmd_ctx *c_, const char *n) : c(c_), name(n) {
-        if (c->timing) cudaEventRecord(c->ev0, c->stream);
+    PendingEv p;
+    Timer(sdmd_ctx *c_, const char *n) : c(c_) {
+        if (c->timing) {
+            p.name = n;
+            p.a = pool_get(c);
+            p.b = pool_get(c);
+            cudaEventRecord(p.a, c->stream);
+        }
     }
     ~Timer() {
         if (c->timing) {
-            cudaEventRecord(c->ev1, c->stream);
-            cudaEventSynchronize(c->ev1);
-            float ms = 0;
-            cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-            KStat &k = c->kstat[name];
-            k.ms += ms;
-            k.n++;
+            cudaEventRecord(p.b, c->stream);
+            c->pending.push_back(p);
+            if (c->pending.size() > 4096) resolve_pending(c);
         }
     }
 };
@@ -519,6 +544,8 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
+    CK(cudaEventCreate(&c->evt0));
+    CK(cudaEventCreate(&c->evt1));
     int n = v->natom;
     size_t n1 = (size_t)n + 1;
     DevP &P = c->P;
@@ -639,8 +666,12 @@ void sdmd_cuda_destroy(sdmd_ctx *c) {
     if (c->d_trace) cudaFree(c->d_trace);
     if (c->d_xchg) cudaFree(c->d_xchg);
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
+    resolve_pending(c);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    cudaEventDestroy(c->evt0);
+    cudaEventDestroy(c->evt1);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -654,18 +685,52 @@ int sdmd_cuda_cell_grid(const sdmd_ctx *c, int cellnum[3], double cellsize[3]) {
 void *sdmd_cuda_stream(const sdmd_ctx *c) { return c ? (void *)c->stream : nullptr; }
 int64_t sdmd_cuda_launch_count(const sdmd_ctx *c) { return c ? c->launches : 0; }
 double sdmd_cuda_kernel_ms(const sdmd_ctx *c, const char *name) {
+    resolve_pending(const_cast<sdmd_ctx *>(c));
     auto it = c->kstat.find(name);
     if (it == c->kstat.end() || it->second.n == 0) return -1.0;
     return it->second.ms / it->second.n;
 }
 int sdmd_cuda_kernel_stats(const sdmd_ctx *c, const char *name, double *total_ms, int64_t *count) {
+    resolve_pending(const_cast<sdmd_ctx *>(c));
     auto it = c->kstat.find(name);
     if (it == c->kstat.end()) { *total_ms = 0; *count = 0; return 0; }
     *total_ms = it->second.ms;
     *count = it->second.n;
     return 0;
 }
-void sdmd_cuda_reset_kernel_stats(sdmd_ctx *c) { c->kstat.clear(); c->launches = 0; }
+void sdmd_cuda_reset_kernel_stats(sdmd_ctx *c) { resolve_pending(c); c->kstat.clear(); c->launches = 0; }
+// device-time bracket on the context's stream for callers (bench.py): begin records, end synchronises
+int sdmd_cuda_timer_begin(sdmd_ctx *c) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventRecord(c->evt0, c->stream));
+    return 0;
+}
+int sdmd_cuda_timer_end(sdmd_ctx *c, double *ms) {
+    CK(cudaEventRecord(c->evt1, c->stream));
+    CK(cudaEventSynchronize(c->evt1));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, c->evt0, c->evt1));
+    *ms = f;
+    return 0;
+}
+int sdmd_cuda_synchronize(sdmd_ctx *c) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+// page-lock a caller-owned host buffer so H2D/D2H copies run at full PCIe rate and asynchronously
+int sdmd_cuda_host_register(void *ptr, size_t bytes) {
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess && e != cudaErrorHostMemoryAlreadyRegistered) return set_err(SDMD_ERR_CUDA, "cudaHostRegister", e);
+    cudaGetLastError();
+    return 0;
+}
+int sdmd_cuda_host_unregister(void *ptr) {
+    cudaHostUnregister(ptr);
+    cudaGetLastError();
+    return 0;
+}
 void sdmd_cuda_set_timing(sdmd_ctx *c, int on) { c->timing = on != 0; }
 
 static int pull_ctl(sdmd_ctx *c) {
@@ -782,6 +847,26 @@ int sdmd_cuda_rng_feed(sdmd_ctx *c, const double *g, int64_t n) {
     c->h_ctl->g_filled = c->g_filled;
     CK(cudaMemcpyAsync(&c->d_ctl->g_filled, &c->h_ctl->g_filled, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// move the consumption cursor (benchmarks replay the same synthetic stream; must stay within the ring)
+int sdmd_cuda_rng_seek(sdmd_ctx *c, int64_t pos) {
+    TRY(pull_ctl(c));
+    if (pos < 0 || pos > c->g_filled || c->g_filled - pos > c->P.g_cap) return set_err(SDMD_ERR_BAD_ARG, "rng_seek out of range");
+    c->h_ctl->g_pos = pos;
+    CK(cudaMemcpyAsync(&c->d_ctl->g_pos, &c->h_ctl->g_pos, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+// forget everything fed so far (fresh stream)
+int sdmd_cuda_rng_reset(sdmd_ctx *c) {
+    TRY(pull_ctl(c));
+    c->g_filled = 0;
+    c->h_ctl->g_filled = 0;
+    c->h_ctl->g_pos = 0;
+    CK(cudaMemcpyAsync(&c->d_ctl->g_filled, &c->h_ctl->g_filled, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(&c->d_ctl->g_pos, &c->h_ctl->g_pos, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
     return 0;
 }
 

@@ -104,7 +104,7 @@ def test_large_gel_box_against_oracle(capi):
     from oracle.oracle_py import Oracle
     from sdmd_b200.synth import gel_box
     hv0, rng = gel_box(32, jitter=0.3)
-    gauss = rng.standard_normal(hv0.natom + 8000)
+    gauss = rng.standard_normal(hv0.natom + 20000)
     ho = hv0.copy(); o = Oracle(ho); o.rng_feed(gauss)
     hg = hv0.copy(); r = capi.Replica(hg, device=0); r.rng_feed(gauss)
     o.pbc_full(); o.cell_build(); o.predict_all(); o.cbt_build()
