@@ -390,8 +390,52 @@ __device__ inline void d_loop_body_serial(const DevP &D, double t_until, sdmd_tr
     }
 }
 
+// loop body after the advance, executed by the whole CTA: HazardCheck, DoEvent, counters (thread 0), then the
+// CTA-parallel Predict and the warp-assisted UpdateCBT (SGThread.c:80-151)
+__device__ inline void d_loop_body_cta(const DevP &D, PredShared &sh, double t_until, sdmd_trace_rec *trace, i64 trace_cap) {
+    Ctl *c = D.ctl;
+    if (threadIdx.x == 0) {
+        int target = c->target, partner = c->partner;
+        c->currenttime += c->dt;
+        int hazard = (partner > 0 && D.ev_pcounter[target] < D.ev_counter[partner]) ? -1 : 0;  // SGThread.c:224-227
+        if (trace && c->trace_pos < trace_cap) {
+            sdmd_trace_rec r;
+            r.frame = c->frame; r.target = target; r.partner = D.ev_partner[target];
+            r.type = D.ev_type[target]; r.sub = D.ev_sub[target]; r.executed = !hazard; r.pad_ = 0; r.dt = c->dt;
+            trace[c->trace_pos] = r;
+        }
+        c->trace_pos++;
+        c->iterations++;
+        if (!hazard) {
+            c->frame++;
+            d_do_event(D, target, partner);
+            D.ev_counter[target]++;
+            if (partner && !D.is_cons[partner]) D.ev_counter[partner]++;
+            sh.natoms = partner ? 2 : 1;
+            sh.atom[0] = target; sh.atom[1] = partner;
+            if (c->currenttime >= t_until) c->stop = 1 + SDMD_STOP_T_UNTIL;
+        } else {
+            sh.natoms = 1;
+            sh.atom[0] = target; sh.atom[1] = 0;
+            c->count_recal++;
+        }
+        for (int a = 0; a < sh.natoms; a++) {   // one thermostat draw per predicted atom, in list order
+            sh.gauss[a] = 0;
+            if (D.thermostat_on && !D.is_cons[sh.atom[a]]) sh.gauss[a] = d_next_gauss(D);
+        }
+    }
+    __syncthreads();
+    d_predict_cta(D, sh);
+    if (threadIdx.x < 32) {
+        d_cbt_update_warp(D, sh, sh.atom[0]);
+        if (sh.natoms > 1) d_cbt_update_warp(D, sh, sh.atom[1]);
+    }
+    __syncthreads();
+}
+
 // Small systems: the whole loop in ONE persistent CTA (one replica per CTA); no host round trip per event.
-__global__ void __launch_bounds__(256) k_run_cta(DevP D, double t_until, i64 iter_limit, sdmd_trace_rec *trace, i64 trace_cap) {
+__global__ void __launch_bounds__(256, 1) k_run_cta(DevP D, double t_until, i64 iter_limit, sdmd_trace_rec *trace, i64 trace_cap) {
+    __shared__ PredShared sh;
     __shared__ double s_dt;
     __shared__ int s_stop;
     for (;;) {
@@ -410,18 +454,20 @@ __global__ void __launch_bounds__(256) k_run_cta(DevP D, double t_until, i64 ite
             D.ev_time[i] = D.ev_time[i] - dt;
         }
         __syncthreads();
-        if (threadIdx.x == 0) d_loop_body_serial(D, t_until, trace, trace_cap);
-        __syncthreads();
+        d_loop_body_cta(D, sh, t_until, trace, trace_cap);
     }
 }
 
 // Large systems: per event one grid-wide advance (k_advance with use_ctl) and this single-CTA kernel,
 // which finishes event k and performs AssignJob for event k+1.
-__global__ void k_event_exec(DevP D, double t_until, i64 iter_limit, sdmd_trace_rec *trace, i64 trace_cap) {
-    if (threadIdx.x == 0 && !D.ctl->stop) {
-        d_loop_body_serial(D, t_until, trace, trace_cap);
-        d_loop_head(D, t_until, iter_limit);
-    }
+__global__ void __launch_bounds__(256, 1) k_event_exec(DevP D, double t_until, i64 iter_limit, sdmd_trace_rec *trace, i64 trace_cap) {
+    __shared__ PredShared sh;
+    __shared__ int s_stop;
+    if (threadIdx.x == 0) s_stop = D.ctl->stop;
+    __syncthreads();
+    if (s_stop) return;
+    d_loop_body_cta(D, sh, t_until, trace, trace_cap);
+    if (threadIdx.x == 0) d_loop_head(D, t_until, iter_limit);
 }
 __global__ void k_loop_head(DevP D, double t_until, i64 iter_limit) { d_loop_head(D, t_until, iter_limit); }
 
@@ -1143,7 +1189,7 @@ int sdmd_cuda_run(sdmd_ctx *c, double t_until, int64_t max_iter, struct sdmd_tra
         for (;;) {
             for (int k = 0; k < batch; k++) {
                 k_advance<<<advance_grid(c), 256, 0, c->stream>>>(c->P, 0.0, 1);
-                k_event_exec<<<1, 32, 0, c->stream>>>(c->P, t_until, iter_limit, dtr, trace_cap);
+                k_event_exec<<<1, 256, 0, c->stream>>>(c->P, t_until, iter_limit, dtr, trace_cap);
             }
             c->launches += 2 * batch;
             CK(cudaGetLastError());

@@ -907,3 +907,545 @@ __device__ inline void d_do_event(const DevP &D, int i, int j) {
         default: c->error = SDMD_ERR_STATE; break;
     }
 }
+
+// ===================================================================================================
+// CTA-parallel re-prediction of the dirty atoms (K3).
+//
+// Predict(renewList) (SGThread.c:158-211) for the 1-2 atoms of an event, executed by one thread block:
+// every candidate of every predictor (bond partners, the 27-cell scan of CollisionTime, PCC, thermostat,
+// bonded / free HB partners, HB neighbours) becomes one entry of a candidate array laid out in the exact
+// order the reference visits them; all threads evaluate entries in parallel (own-side time, potential,
+// sub-event), and the per-atom earliest-event fold (JobAssign, strict '<', first wins) is then taken over
+// that array.  CheckDuplication couples the fold to the running best, so entries whose partner's slot
+// points back at this atom are resolved in order by one thread; when there is none the fold is a parallel
+// lexicographic (time, position) minimum.
+// ===================================================================================================
+#define PC_MAXC 448          // candidates per atom held in shared memory; larger neighbourhoods use the serial path
+enum { CK_BOND = 0, CK_COLL = 1, CK_PCC = 2, CK_THER = 3, CK_HB = 4, CK_HBFREE = 5, CK_HBNE = 6 };
+#define CF_VALID 1           // own-side event exists and its time is > 0
+#define CF_COUNTED 2         // a CalculateParameters-equivalent evaluation happened on the own-side path
+#define CF_ELIGIBLE 4        // partner's slot points back (CheckDuplication's first three conditions)
+
+struct PredShared {
+    int natoms;
+    int atom[2];
+    double gauss[2];
+    int use_serial[2];
+    int ncand[2];
+    int cell_cnt[2][27];
+    int cell_off[2][28];
+    int hb_free[2];           // free donor/acceptor scan active
+    int n_bond[2], n_coll[2], n_hbne[2];
+    int off_coll[2], off_pcc[2], off_ther[2], off_hb[2], off_hbne[2];
+    Slot result[2];
+    int winner_pos[2];
+    int npair[2];
+    int any_elig[2];
+    // candidate arrays: atom a occupies [a * PC_MAXC, (a + 1) * PC_MAXC)
+    int cj[2 * PC_MAXC];
+    unsigned char ckind[2 * PC_MAXC];
+    unsigned char caux[2 * PC_MAXC];   // neighbour-cell slot k / HB-neighbour index n
+    unsigned char csub[2 * PC_MAXC];
+    unsigned char cflag[2 * PC_MAXC];
+    double ctime[2 * PC_MAXC];
+    double cpot[2 * PC_MAXC];
+    // tournament-tree repair scratch
+    int path_old[40], path_sib[40];
+    double path_tsib[40];
+};
+
+__device__ __forceinline__ int d_kind_event(int kind) {
+    switch (kind) {
+        case CK_BOND: return SDMD_EV_BOND;
+        case CK_COLL: return SDMD_EV_COLI;
+        case CK_PCC: return SDMD_EV_PCC;
+        case CK_THER: return SDMD_EV_THER;
+        case CK_HBNE: return SDMD_EV_HBNE;
+        default: return SDMD_EV_HB;
+    }
+}
+
+// FindPair's step walk with every table load issued up front (same comparisons, same first match)
+__device__ __forceinline__ FindRes d_find_pair_table_fast(const DevP &D, const sdmd_step_table *t, int mode, double direction,
+                                                          double dist2, int bond_a1, int bond_a2) {
+    FindRes r;
+    r.cs = -1;
+    double dir = (direction < 0) ? 1.0 : -1.0;
+    double tol = dir * SD_ZERO;
+    double dmin2 = __ldg(&t->dmin2), dmax2 = __ldg(&t->dmax2);
+    int ns = __ldg(&t->nstep);
+    if (dist2 < dmin2 - SD_ZERO) {
+        r.lower = SD_INF; r.upper = SD_INF; r.accum = SD_INF; r.lowPot = 0; r.upPot = 0;
+        if (!(mode == FP_NEIGHBOR && bond_a2 == 0) && !(mode == FP_HB && bond_a1 == 0)) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+        return r;
+    }
+    int kk = ns;
+#pragma unroll
+    for (int k = SDMD_MAX_STEPS - 1; k >= 0; k--) {
+        double d = (k < ns) ? __ldg(&t->d2[k]) : 0.0;
+        if (k < ns && dist2 < d + tol) kk = k;
+    }
+    r.lower = dmin2; r.lowPot = 0; r.upper = 0; r.upPot = 0; r.accum = 0;
+    if (kk > 0) { r.lower = __ldg(&t->d2[kk - 1]); r.lowPot = __ldg(&t->e[kk - 1]); }
+    if (kk < ns) {
+        r.upper = __ldg(&t->d2[kk]);
+        r.upPot = -1 * __ldg(&t->e[kk]);
+        r.accum = __ldg(&t->acc[kk]);
+        if (kk == 0) { r.cs = 0; return r; }
+        if (mode == FP_HB && kk == ns - 1 && bond_a1 > 0) { r.cs = 1; return r; }
+        if (mode == FP_NEIGHBOR && kk == ns - 1 && bond_a2 > 0) { r.upPot = 0; r.cs = 1; return r; }
+        return r;
+    }
+    if (mode == FP_HB && bond_a1 > 0) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+    if (dmax2 > 0) {
+        if (dist2 < dmax2 + SD_ZERO) {
+            r.upper = dmax2; r.upPot = 0; r.accum = 0;
+            r.cs = 1;
+            if (ns == 0 && dir == 1.0) r.cs = 0;
+            return r;
+        }
+        r.lower = SD_INF; r.upper = SD_INF; r.accum = SD_INF; r.lowPot = 0; r.upPot = 0;
+        if (!(mode == FP_NEIGHBOR && bond_a2 == 0) && !(mode == FP_HB && bond_a1 == 0)) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+        return r;
+    }
+    r.upper = SD_INF; r.upPot = SD_INF; r.accum = SD_INF;
+    r.cs = 1;
+    return r;
+}
+
+__device__ inline FindRes d_find_pair_fast(const DevP &D, int a1, int a2, int mode, double direction, double dist2, int hbPartner) {
+    int idx = -1;
+    if (mode == FP_COLLISION) {
+        idx = __ldg(&D.coll_index[D.type[a1] * SD_NT + D.type[a2]]);
+    } else if (mode == FP_CONSTRAINT) {
+        for (int k = D.con_off[a1]; k < D.con_off[a1 + 1]; k++)
+            if (D.con_j[k] == a2) { idx = D.con_table[k]; break; }
+    } else if (mode == FP_HB) {
+        int cls = d_hb_model(D, a1, a2);
+        if (cls >= 0) idx = __ldg(&D.hb_index[(cls * SD_NT + 0) * SD_NT + 0]);
+    } else {
+        int cls = hbPartner > 0 ? d_hb_model(D, a2, hbPartner) : -2;
+        int t1 = d_type_change(D.type[a1], 0), t2 = d_type_change(D.type[a2], 0);
+        if (cls >= 0) idx = __ldg(&D.hb_index[(cls * SD_NT + t1) * SD_NT + t2]);
+    }
+    if (idx < 0 || D.tables[idx].dmin2 == 0) {
+        D.ctl->error = SDMD_ERR_TABLE;
+        FindRes r;
+        r.lower = SD_INF; r.upper = SD_INF; r.accum = SD_INF; r.lowPot = 0; r.upPot = 0; r.cs = -1;
+        return r;
+    }
+    return d_find_pair_table_fast(D, &D.tables[idx], mode, direction, dist2, D.hb_bond[a1], D.hb_bond[a2]);
+}
+
+// ---- phase A: lay out the candidate array of predict-atom `a` (called by all threads) ----
+__device__ inline void d_pc_gather(const DevP &D, PredShared &sh, int a) {
+    int i = sh.atom[a];
+    int tid = threadIdx.x;
+    int base = a * PC_MAXC;
+    int cx = D.cell_idx[3 * i], cy = D.cell_idx[3 * i + 1], cz = D.cell_idx[3 * i + 2];
+    // 27 threads walk the 27 neighbour-cell lists (count pass)
+    if (tid < 27) {
+        int ncx, ncy, ncz;
+        int cell = d_neighbor_cell(D, cx, cy, cz, tid, &ncx, &ncy, &ncz);
+        int cnt = 0;
+        for (int j = D.celllist[D.n + cell + 1]; j; j = D.celllist[j]) cnt += (j != i);
+        sh.cell_cnt[a][tid] = cnt;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int off = 0;
+        for (int k = 0; k < 27; k++) { sh.cell_off[a][k] = off; off += sh.cell_cnt[a][k]; }
+        sh.cell_off[a][27] = off;
+        int ncoll = off;
+        int nb = D.gel_mode ? 0 : (D.bond_off[i + 1] - D.bond_off[i]);
+        int role = D.hb_role[i];
+        int itype = D.hb_itype[i];
+        int bonded = D.hb_bond[i];
+        int nhb = 0, hbfree = 0, nhbne = 0;
+        if (D.hydrogen_bond) {
+            if (itype != SDMD_HB_SKIP) {   // TimePrediction.c:309-327
+                if (bonded > 0) nhb = 1;
+                else if ((role == 'A' || role == 'D' || role == 'S') && bonded == 0) { hbfree = 1; nhb = ncoll; }
+            }
+            nhbne = D.hbn_status[i];
+        }
+        int pos = 0;
+        sh.n_bond[a] = nb; pos += nb;
+        sh.off_coll[a] = pos; sh.n_coll[a] = ncoll; pos += ncoll;
+        sh.off_pcc[a] = pos; pos += 1;
+        sh.off_ther[a] = pos; pos += D.thermostat_on ? 1 : 0;
+        sh.off_hb[a] = pos; pos += nhb;
+        sh.off_hbne[a] = pos; sh.n_hbne[a] = nhbne; pos += nhbne;
+        sh.hb_free[a] = hbfree;
+        sh.ncand[a] = pos;
+        sh.use_serial[a] = (pos > PC_MAXC);
+    }
+    __syncthreads();
+    if (sh.use_serial[a]) return;
+    // fill pass
+    if (tid < 27) {
+        int ncx, ncy, ncz;
+        int cell = d_neighbor_cell(D, cx, cy, cz, tid, &ncx, &ncy, &ncz);
+        int p = base + sh.off_coll[a] + sh.cell_off[a][tid];
+        int q = base + sh.off_hb[a] + sh.cell_off[a][tid];
+        int hbfree = sh.hb_free[a];
+        for (int j = D.celllist[D.n + cell + 1]; j; j = D.celllist[j]) {
+            if (j == i) continue;
+            sh.cj[p] = j; sh.ckind[p] = CK_COLL; sh.caux[p] = (unsigned char)tid; p++;
+            if (hbfree) { sh.cj[q] = j; sh.ckind[q] = CK_HBFREE; sh.caux[q] = (unsigned char)tid; q++; }
+        }
+    } else if (tid >= 32 && tid < 32 + 16) {
+        int k = tid - 32;
+        if (k < sh.n_bond[a]) {
+            int p = base + k;
+            sh.cj[p] = D.bond_j[D.bond_off[i] + k]; sh.ckind[p] = CK_BOND; sh.caux[p] = (unsigned char)k;
+        }
+    } else if (tid == 64) {
+        int p = base + sh.off_pcc[a];
+        sh.cj[p] = 0; sh.ckind[p] = CK_PCC; sh.caux[p] = 0;
+        if (D.thermostat_on) { p = base + sh.off_ther[a]; sh.cj[p] = 0; sh.ckind[p] = CK_THER; sh.caux[p] = 0; }
+        if (!sh.hb_free[a] && sh.off_hbne[a] > sh.off_hb[a]) {
+            p = base + sh.off_hb[a];
+            sh.cj[p] = D.hb_bond[i]; sh.ckind[p] = CK_HB; sh.caux[p] = 0;
+        }
+        for (int n = 1; n <= sh.n_hbne[a]; n++) {
+            p = base + sh.off_hbne[a] + n - 1;
+            sh.cj[p] = D.hbn_partner[5 * i + n]; sh.ckind[p] = CK_HBNE; sh.caux[p] = (unsigned char)n;
+        }
+    }
+}
+
+// ---- phase B: own-side evaluation of one candidate entry (any thread) ----
+__device__ inline void d_pc_eval(const DevP &D, PredShared &sh, int a, int p, const Self &me) {
+    int q = a * PC_MAXC + p;
+    int kind = sh.ckind[q];
+    int j = sh.cj[q];
+    int i = me.i;
+    int flag = 0, sub = SDMD_SUB_INVALID;
+    double time = SD_INF, pot = 0;
+    if (kind == CK_PCC) {
+        Slot tmp = d_reset_slot(0, 0, 0);
+        d_pcc_time(D, me, tmp);
+        if (tmp.type == SDMD_EV_PCC) { time = tmp.time; flag = CF_VALID; }
+    } else if (kind == CK_THER) {
+        double g = sh.gauss[a];
+        time = D.thermoF * ((g < 0) ? (-g) : (g));
+        if (time > 0) flag = CF_VALID;
+    } else {
+        // cell-index minimum image (PBCShift) — for cell-scan entries j's cell is the scanned neighbour cell
+        Pair pr;
+        bool do_pair = true;
+        int cm = 0;
+        if (kind == CK_COLL) {
+            cm = (D.cm_off[i + 1] > D.cm_off[i]) ? d_cm_flags(D, i, j) : 0;
+            if ((cm & SDMD_BOND_CONNECT) || D.hb_bond[i] == j || d_find_in_hbn(D, i, j)) do_pair = false;
+        } else if (kind == CK_HBFREE) {
+            int role = D.hb_role[i], rj = D.hb_role[j];
+            bool ad = (role == 'A' && rj == 'D') || (role == 'D' && rj == 'A');
+            bool sd = (role == 'S' && D.type[j] == 2) || (rj == 'S' && D.type[i] == 2);
+            bool ss = (role == 'S' && rj == 'S');
+            int d = D.aa_num[i] - D.aa_num[j];
+            if (d < 0) d = -d;
+            if (!(ad || sd || ss) || D.hb_bond[j] != 0 ||
+                !((D.protein[i] == D.protein[j] && d >= 4) || D.protein[i] != D.protein[j]))
+                do_pair = false;
+        }
+        // eligibility for CheckDuplication (TimePrediction.c:1102-1104); HB free pairs test it after their filters
+        bool elig_ok = (kind != CK_HBFREE) || do_pair;
+        if (elig_ok && D.ev_partner[j] == i && D.ev_type[j] == d_kind_event(kind) && D.ev_pcounter[j] == me.counter) flag |= CF_ELIGIBLE;
+        if (do_pair) {
+            pr = d_pair_atoms(D, i, j);
+            flag |= CF_COUNTED;
+            if (kind == CK_BOND) {
+                int k = D.bond_off[i] + sh.caux[q];
+                double long2 = D.bond_dmax2[k], short2 = D.bond_dmin2[k];
+                bool done = false;
+                if (pr.r2 - long2 > SD_ZERO) {
+                    atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+                    if (pr.b >= 0) { time = 1e-16 * i * j; sub = SDMD_SUB_WELLBOUNC; done = true; }
+                } else if (short2 - pr.r2 > SD_ZERO) {
+                    atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+                    if (pr.b < 0) { time = 1e-16 * i * j; sub = SDMD_SUB_CORECOLLI; done = true; }
+                }
+                if (!done) {
+                    int s; double d2;
+                    if (pr.b < 0 && d_disc(pr, short2) > 0) { s = -1; d2 = short2; sub = SDMD_SUB_CORECOLLI; }
+                    else { s = 1; d2 = long2; sub = SDMD_SUB_WELLBOUNC; }
+                    time = d_time(pr, s, d2);
+                    if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); time = SD_INF; }
+                }
+                pot = 0;
+                if (time > 0) flag |= CF_VALID;
+            } else if (kind == CK_COLL) {
+                if (pr.r2 <= D.cut2) {
+                    FindRes f;
+                    bool skip = false;
+                    if (cm & SDMD_CONSTRAINT_CONNECT) f = d_find_pair_fast(D, i, j, FP_CONSTRAINT, pr.b, pr.r2, 0);
+                    else {
+                        f = d_find_pair_fast(D, i, j, FP_COLLISION, pr.b, pr.r2, 0);
+                        if (f.lowPot == 0 && f.upPot == 0) skip = true;
+                    }
+                    if (!skip) {
+                        int s; double d2;
+                        if (pr.b < 0 && d_disc(pr, f.lower) > 0) {
+                            s = -1; d2 = f.lower; pot = f.lowPot;
+                            sub = (f.cs == 0) ? SDMD_SUB_CORECOLLI : SDMD_SUB_TBDCAPTR;
+                        } else {
+                            s = 1; d2 = f.upper; pot = f.upPot;
+                            if (D.method_ding) {
+                                if (cm & SDMD_CONSTRAINT_CONNECT) sub = (f.cs == 1) ? SDMD_SUB_WELLBOUNC : SDMD_SUB_TBDESCAP;
+                                else { if (f.cs == 1) skip = true; sub = SDMD_SUB_TBDESCAP; }
+                            }
+                        }
+                        if (!skip) {
+                            time = d_time(pr, s, d2);
+                            if (time < 0) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+                            if (time > 0) flag |= CF_VALID;
+                        }
+                    }
+                }
+            } else if (kind == CK_HB) {
+                FindRes f = d_find_pair_fast(D, i, j, FP_HB, pr.b, pr.r2, 0);
+                int s; double d2;
+                if (pr.b < 0 && d_disc(pr, f.lower) > 0) {
+                    s = -1; d2 = f.lower; pot = f.lowPot;
+                    sub = (f.cs == 0) ? SDMD_SUB_CORECOLLI : SDMD_SUB_TBDCAPTR;
+                } else {
+                    s = 1; d2 = f.upper; pot = f.upPot;
+                    if (D.method_ding) sub = (f.cs == 1) ? SDMD_SUB_TBDHBBRIK : SDMD_SUB_TBDESCAP;
+                }
+                time = d_time(pr, s, d2);
+                if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); time = SD_INF; }
+                if (time > 0) flag |= CF_VALID;
+            } else if (kind == CK_HBFREE) {
+                if (pr.r2 <= D.cut2 && d_check_pair_match(D, i, j) >= 0) {
+                    FindRes f = d_find_pair_fast(D, i, j, FP_HB, pr.b, pr.r2, 0);
+                    if (pr.b < 0 && f.cs == 1 && d_disc(pr, f.lower) > 0) {
+                        time = d_time(pr, -1, f.lower);
+                        pot = f.lowPot; sub = SDMD_SUB_TBDHBFORM;
+                        if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); time = SD_INF; }
+                        if (time > 0) flag |= CF_VALID;
+                    }
+                }
+            } else {  // CK_HBNE
+                int host, nbr, third;
+                int r = D.hb_role[i];
+                int bi = D.hb_bond[i];
+                if ((r == 'A' || r == 'D' || r == 'S') && (bi && D.hb_neighbor[bi] == j)) { host = i; nbr = j; third = bi; }
+                else { host = j; nbr = i; third = D.hb_bond[j]; }
+                FindRes f = d_find_pair_fast(D, nbr, host, FP_NEIGHBOR, pr.b, pr.r2, third);
+                int s; double d2;
+                if (pr.b < 0 && d_disc(pr, f.lower) > 0) {
+                    s = -1; d2 = f.lower; pot = f.lowPot;
+                    sub = (f.cs == 0) ? SDMD_SUB_CORECOLLI : SDMD_SUB_TBDCAPTR;
+                } else {
+                    s = 1; d2 = f.upper; pot = f.upPot;
+                    if (D.method_ding) sub = (f.cs == 1) ? SDMD_SUB_WELLBOUNC : SDMD_SUB_TBDESCAP;
+                }
+                time = d_time(pr, s, d2);
+                if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); time = SD_INF; }
+                if (time > 0) flag |= CF_VALID;
+            }
+        }
+    }
+    sh.ctime[q] = time; sh.cpot[q] = pot; sh.csub[q] = (unsigned char)sub; sh.cflag[q] = (unsigned char)flag;
+}
+
+// ---- phase C: the ordered fold of atom `a` (warp 0) ----
+__device__ inline void d_pc_fold(const DevP &D, PredShared &sh, int a) {
+    int lane = threadIdx.x & 31;
+    int i = sh.atom[a];
+    int base = a * PC_MAXC;
+    int nc = sh.ncand[a];
+    // refresh eligibility against live slots (the co-predicted atom's slot may have just been written)
+    i64 counter_i = D.ev_counter[i];
+    bool any = false;
+    double bt = SD_INF;
+    int bp = 0x7fffffff;
+    for (int p = lane; p < nc; p += 32) {
+        int q = base + p;
+        int kind = sh.ckind[q];
+        int f = sh.cflag[q];
+        if (kind != CK_PCC && kind != CK_THER) {
+            int j = sh.cj[q];
+            bool was = (f & CF_ELIGIBLE) != 0;
+            bool could = was || j == sh.atom[0] || j == sh.atom[1];
+            if (could) {
+                bool el = D.ev_partner[j] == i && D.ev_type[j] == d_kind_event(kind) && D.ev_pcounter[j] == counter_i;
+                if (kind == CK_HBFREE && !(f & CF_COUNTED)) el = false;
+                f = el ? (f | CF_ELIGIBLE) : (f & ~CF_ELIGIBLE);
+                sh.cflag[q] = (unsigned char)f;
+            }
+        }
+        if (f & CF_ELIGIBLE) any = true;
+        if (f & CF_VALID) {
+            double t = sh.ctime[q];
+            if (t < bt) { bt = t; bp = p; }   // p ascending within a lane: first wins on ties
+        }
+    }
+    any = __any_sync(0xffffffffu, any);
+    Slot cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
+    int win = -1, npair = 0;
+    if (!any) {
+        // JobAssign leaves partnerCounter untouched for partner-less events (TimePrediction.c:1148-1153), so when
+        // PCC / thermostat wins, the slot keeps the counter of the last pair candidate that was a running best:
+        // the first-min of the sections in front of PCC (bonds + cell scan)
+        double pt = SD_INF;
+        int pp = 0x7fffffff;
+        int npre = sh.off_pcc[a];
+        for (int p = lane; p < npre; p += 32) {
+            int q = base + p;
+            if (sh.cflag[q] & CF_VALID) {
+                double t = sh.ctime[q];
+                if (t < pt) { pt = t; pp = p; }
+            }
+        }
+        // parallel lexicographic (time, position) minimum
+        for (int o = 16; o; o >>= 1) {
+            double ot = __shfl_down_sync(0xffffffffu, bt, o);
+            int op = __shfl_down_sync(0xffffffffu, bp, o);
+            if (ot < bt || (ot == bt && op < bp)) { bt = ot; bp = op; }
+            ot = __shfl_down_sync(0xffffffffu, pt, o);
+            op = __shfl_down_sync(0xffffffffu, pp, o);
+            if (ot < pt || (ot == pt && op < pp)) { pt = ot; pp = op; }
+        }
+        int cnt = 0;
+        for (int p = lane; p < nc; p += 32) cnt += (sh.cflag[base + p] & CF_COUNTED) ? 1 : 0;
+        for (int o = 16; o; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+        if (lane == 0) {
+            npair = cnt;
+            if (bp != 0x7fffffff && cur.time > bt) {
+                int q = base + bp;
+                int j = sh.cj[q];
+                if (j == 0 && pp != 0x7fffffff && cur.time > pt) cur.pcounter = D.ev_counter[sh.cj[base + pp]];
+                d_job_assign(D, cur, j, bt, sh.cpot[q], sh.csub[q], d_kind_event(sh.ckind[q]));
+                win = bp;
+            }
+        }
+    } else if (lane == 0) {
+        SlotSrc S = d_live_slots(D);
+        for (int p = 0; p < nc; p++) {
+            int q = base + p;
+            int f = sh.cflag[q];
+            int j = sh.cj[q];
+            int ev = d_kind_event(sh.ckind[q]);
+            if ((f & CF_ELIGIBLE) && cur.time > S.time[j]) {   // CheckDuplication copies the partner's slot
+                cur.partner = j; cur.pot = S.pot[j]; cur.sub = S.sub[j]; cur.time = S.time[j]; cur.type = ev;
+                cur.pcounter = D.ev_counter[j];
+                win = p;
+                continue;
+            }
+            if (f & CF_COUNTED) npair++;
+            if ((f & CF_VALID) && d_job_assign(D, cur, j, sh.ctime[q], sh.cpot[q], sh.csub[q], ev)) win = p;
+        }
+    }
+    if (lane == 0) {
+        sh.result[a] = cur;
+        sh.winner_pos[a] = win;
+        sh.npair[a] = npair;
+    }
+}
+
+// Predict(renewList) by the whole CTA.  sh.natoms / sh.atom[] / sh.gauss[] are set by the caller (thread 0)
+// before a __syncthreads; on return (after a final __syncthreads) the slots are stored.
+__device__ inline void d_predict_cta(const DevP &D, PredShared &sh) {
+    int tid = threadIdx.x;
+    int na = sh.natoms;
+    // ResetTarget for every listed atom first (ToolFunctions.c:504-514)
+    if (tid < na) {
+        int i = sh.atom[tid];
+        D.ev_type[i] = SDMD_EV_INVD; D.ev_time[i] = SD_INF; D.ev_partner[i] = SDMD_INVALID;
+    }
+    __syncthreads();
+    for (int a = 0; a < na; a++) d_pc_gather(D, sh, a);
+    __syncthreads();
+    // evaluate every candidate of every atom in parallel
+    {
+        int n0 = (na > 0 && !sh.use_serial[0] && !D.is_cons[sh.atom[0]]) ? sh.ncand[0] : 0;
+        int n1 = (na > 1 && !sh.use_serial[1] && !D.is_cons[sh.atom[1]]) ? sh.ncand[1] : 0;
+        int total = n0 + n1;
+        if (total > 0) {
+            Self me0 = d_load_self(D, sh.atom[0]);
+            Self me1 = (na > 1) ? d_load_self(D, sh.atom[1]) : me0;
+            for (int w = tid; w < total; w += blockDim.x) {
+                if (w < n0) d_pc_eval(D, sh, 0, w, me0);
+                else d_pc_eval(D, sh, 1, w - n0, me1);
+            }
+        }
+    }
+    __syncthreads();
+    for (int a = 0; a < na; a++) {
+        int i = sh.atom[a];
+        if (tid < 32) {
+            if (D.is_cons[i]) {
+                if (tid == 0) { D.ev_time[i] = SD_INF; }
+            } else if (sh.use_serial[a]) {
+                if (tid == 0) {
+                    SlotSrc S = d_live_slots(D);
+                    Slot cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
+                    int np = 0;
+                    cur = d_predict_atom<false>(D, S, i, cur, sh.gauss[a], 0x7fffffff, &np);
+                    d_store_slot(D, i, cur);
+                    D.ctl->pair_predictions += np;
+                }
+            } else {
+                d_pc_fold(D, sh, a);
+                if (tid == 0) {
+                    d_store_slot(D, i, sh.result[a]);
+                    D.ctl->pair_predictions += sh.npair[a];
+                    if (D.hydrogen_bond) {
+                        D.hb_itype[i] = SDMD_HB_NOEVENT;                       // TimePrediction.c:325,329
+                        int ns = sh.n_hbne[a];
+                        if (ns > 0) {                                           // partnerNum, TimePrediction.c:504-511,574-577
+                            int w = sh.winner_pos[a];
+                            D.hbn_pnum[i] = (w >= sh.off_hbne[a]) ? (w - sh.off_hbne[a] + 1) : ns;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// UpdateCBTRun (CBT.c:56-83) with the root path's nodes, siblings and sibling times fetched by parallel lanes
+// first; the two-phase walk itself (which decides where to stop) is replayed in order by lane 0.
+__device__ inline void d_cbt_update_warp(const DevP &D, PredShared &sh, int a) {
+    int lane = threadIdx.x & 31;
+    int leaf = D.cbt_leaf[a];
+    int depth = 0;
+    for (int f = leaf / 2; f > 0; f /= 2) depth++;
+    for (int k = lane; k < depth; k += 32) {
+        int child = leaf >> k;          // node on the path at level k (k = 0: the leaf)
+        int f = child >> 1;
+        int sib = D.cbt_node[child ^ 1];
+        sh.path_old[k] = D.cbt_node[f];
+        sh.path_sib[k] = sib;
+        sh.path_tsib[k] = D.ev_time[sib];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double ta = D.ev_time[a];
+        int w = a;              // current winner coming up the path
+        double tw = ta;
+        bool phase1 = true;
+        for (int k = 0; k < depth; k++) {
+            int child = leaf >> k;
+            int f = child >> 1;
+            int old = sh.path_old[k];
+            if (phase1 && old != a) phase1 = false;
+            int sib = sh.path_sib[k];
+            double ts = sh.path_tsib[k];
+            // left child = node[2f], right = node[2f+1]; winner = t[left] < t[right] ? left : right
+            bool w_is_left = (child & 1) == 0;
+            int nw;
+            double ntw;
+            if (w_is_left) { if (tw < ts) { nw = w; ntw = tw; } else { nw = sib; ntw = ts; } }
+            else { if (ts < tw) { nw = sib; ntw = ts; } else { nw = w; ntw = tw; } }
+            D.cbt_node[f] = nw;
+            if (!phase1 && nw == old) break;
+            w = nw; tw = ntw;
+        }
+    }
+    __syncwarp();
+}
