@@ -300,6 +300,8 @@ int  sdmd_cuda_host_register(void *ptr, size_t bytes);
 int  sdmd_cuda_host_unregister(void *ptr);
 void sdmd_cuda_set_timing(sdmd_ctx *ctx, int on);   /* per-launch CUDA-event brackets (asynchronous, resolved on query); default on */
 int64_t sdmd_cuda_launch_count(const sdmd_ctx *ctx);
+/* debug: accumulated SM cycles per event-loop phase {head, advance, event, gather, eval, fold, cbt, iterations} */
+int  sdmd_cuda_phase_cycles(sdmd_ctx *ctx, int64_t out[12]);
 void *sdmd_cuda_stream(const sdmd_ctx *ctx);   /* cudaStream_t */
 
 #ifdef __cplusplus

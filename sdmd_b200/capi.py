@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "sdmd_cuda_run", "sdmd_cuda_get_stats", "sdmd_cuda_set_temperature",
     "sdmd_remd_rearrange", "sdmd_remd_nccl_unique_id", "sdmd_remd_nccl_init", "sdmd_remd_seed_server", "sdmd_remd_exchange",
     "sdmd_cuda_kernel_ms", "sdmd_cuda_kernel_stats", "sdmd_cuda_reset_kernel_stats", "sdmd_cuda_set_timing",
-    "sdmd_cuda_launch_count", "sdmd_cuda_stream",
+    "sdmd_cuda_launch_count", "sdmd_cuda_stream", "sdmd_cuda_phase_cycles",
 ]
 
 
@@ -124,6 +124,7 @@ def lib():
     L.sdmd_cuda_set_timing.restype = None
     L.sdmd_cuda_launch_count.argtypes = [vp]
     L.sdmd_cuda_launch_count.restype = C.c_int64
+    L.sdmd_cuda_phase_cycles.argtypes = [vp, C.POINTER(C.c_int64)]
     L.sdmd_cuda_stream.argtypes = [vp]
     L.sdmd_cuda_stream.restype = vp
     _lib = L
@@ -307,6 +308,13 @@ class Replica:
     def set_timing(self, on): self.L.sdmd_cuda_set_timing(self.h, int(bool(on)))
     def launch_count(self): return int(self.L.sdmd_cuda_launch_count(self.h))
     def stream(self): return self.L.sdmd_cuda_stream(self.h)
+
+    def phase_cycles(self):
+        out = (C.c_int64 * 12)()
+        _check(self.L.sdmd_cuda_phase_cycles(self.h, out), "phase_cycles")
+        names = ["head", "advance", "event", "gather", "eval", "fold", "cbt", "iterations", "event_thread0", "x9",
+                 "x10", "x11"]
+        return dict(zip(names, out[:12]))
 
     # ---- REMD ----
     def remd_init(self, nranks, rank, unique_id: bytes, server_seed: int):

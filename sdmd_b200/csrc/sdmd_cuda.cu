@@ -43,8 +43,9 @@ struct sdmd_ctx {
     int *b_partner = nullptr, *c_partner = nullptr;
     i64 *b_pcounter = nullptr, *c_pcounter = nullptr;
     uint8_t *b_type = nullptr, *b_sub = nullptr, *c_type = nullptr, *c_sub = nullptr;
-    uint8_t *flag_cur = nullptr, *flag_next = nullptr;
-    int *npair = nullptr;
+    uint8_t *copyflag = nullptr;
+    int *npair = nullptr, *pcount = nullptr, *pwho = nullptr, *queue_a = nullptr, *queue_b = nullptr, *nqueue = nullptr;
+    double *second = nullptr;
     int *cell_of = nullptr, *cell_count = nullptr, *cell_cursor = nullptr, *scan_tmp = nullptr;
     int *d_cell_start = nullptr, *d_sorted_atom = nullptr;
     double *d_sx = nullptr, *d_sy = nullptr, *d_sz = nullptr, *d_svx = nullptr, *d_svy = nullptr, *d_svz = nullptr;
@@ -220,8 +221,18 @@ __global__ void k_cell_finish(DevP D, const int *cell_start, int *sorted_atom) {
         sorted_atom[b + 1] = v;
     }
     int *cl = D.celllist;
+    D.cell_cnt[c] = p1 - p0;
     cl[D.n + c + 1] = (p1 > p0) ? sorted_atom[p0] : 0;
     for (int a = p0; a < p1; a++) cl[sorted_atom[a]] = (a + 1 < p1) ? sorted_atom[a + 1] : 0;
+}
+
+// occupancy of every cell from an uploaded link list
+__global__ void k_cell_count(DevP D) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= D.ncell) return;
+    int cnt = 0;
+    for (int j = D.celllist[D.n + c + 1]; j; j = D.celllist[j]) cnt++;
+    D.cell_cnt[c] = cnt;
 }
 
 // cell-sorted SoA copies for the full-system prediction pass
@@ -250,39 +261,114 @@ __device__ __forceinline__ SlotSrc as_src(const SlotBuf &b) {
     return S;
 }
 
-// One relaxation round of the sequential pass `for i in 1..N: slot(i) = F(i, slot(j<i))`
-// (SGThread.c:47-52 + CheckDuplication TimePrediction.c:1101-1117).  Round 0 evaluates every atom with
-// no duplicate source; later rounds re-evaluate only flagged atoms against the previous round's slots of
-// lower-index atoms.  The stale fields of a slot (potential / subEventType / partnerCounter survive
-// ResetTarget) always start from the live arrays, which this pass never writes until the final commit.
-__global__ void __launch_bounds__(128) k_predict_all_round(DevP D, SlotBuf src, SlotBuf dst, const uint8_t *flags, int round, int *npair,
-                                                           i64 g_base) {
+// Full-system Predict (SGThread.c:47-52) = the recursion slot(i) = F(i, slot(j < i)): atom i copies the slot of a
+// lower-index partner that points back at it (CheckDuplication, TimePrediction.c:1101-1117).  It is solved exactly:
+//   round 0   every atom folds its candidates with no duplicate source and also records the value of its
+//             second-best candidate (m2);
+//   resolve   an atom pointed at by exactly ONE lower-index collision slot j is settled without re-evaluation:
+//               j is not my own best and t_j > my best            -> my round-0 slot stands
+//               j is my own best (same type) and t_j < m2          -> my slot is a copy of j's
+//             (proof sketch in DESIGN.md); anything else — several pointers, other event types, near ties — is
+//             queued for re-evaluation;
+//   rounds    queued atoms are re-evaluated against the current slots of lower-index atoms until nothing changes;
+//             a changed slot queues the higher-index atoms it pointed / points at.
+// The stale fields of a slot (potential / subEventType / partnerCounter survive ResetTarget) always start from the
+// live arrays, which this pass never writes until the final commit.
+__global__ void __launch_bounds__(128) k_predict_all_round(DevP D, SlotBuf src, SlotBuf dst, const int *queue, int nqueue, int round,
+                                                           int *npair, double *second, i64 g_base) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= D.n) return;
-    int i = D.sorted_atom[p];
-    if (round > 0 && !flags[i]) return;
+    int i;
+    if (round == 0) {
+        if (p >= D.n) return;
+        i = D.sorted_atom[p];
+    } else {
+        if (p >= nqueue) return;
+        i = queue[p];
+    }
     Slot cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
     double g = 0;
     if (D.thermostat_on && !D.is_cons[i]) g = D.gauss[(g_base + D.ther_rank[i]) % D.g_cap];
     int np = 0;
-    cur = d_predict_atom<true>(D, as_src(src), i, cur, g, round == 0 ? 0 : i, &np);
+    double m2 = SD_INF;
+    cur = d_predict_atom<true>(D, as_src(src), i, cur, g, round == 0 ? 0 : i, &np, round == 0 ? &m2 : nullptr);
     dst.time[i] = cur.time; dst.pot[i] = cur.pot; dst.partner[i] = cur.partner; dst.pcounter[i] = cur.pcounter;
     dst.type[i] = (uint8_t)cur.type; dst.sub[i] = (uint8_t)cur.sub;
     npair[i] = np;
+    if (round == 0) second[i] = m2;
 }
 
-// after round 0: an atom must be re-evaluated iff a lower-index atom's slot points at it
-__global__ void k_predict_all_flag0(DevP D, SlotBuf b, uint8_t *flags) {
+// who points at whom after round 0: count and remember one lower-index pointer per atom
+__global__ void k_predict_all_point(DevP D, SlotBuf b, int *pcount, int *pwho) {
     int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (j > D.n) return;
     int k = b.partner[j];
-    if (k > j) flags[k] = 1;
+    if (k > j) {
+        atomicAdd(&pcount[k], 1);
+        pwho[k] = j;
+    }
 }
 
-// commit round r: move re-evaluated slots into the current buffer, flag dependants of changed slots
-__global__ void k_predict_all_commit(DevP D, SlotBuf cur, SlotBuf nxt, const uint8_t *flags, uint8_t *flags_next) {
+// scan slot (0..26) of neighbour cell offset (dx,dy,dz), inverse of the DMD.c:118-120 tables
+__constant__ int c_kinv[27] = {14, 11, 23, 12, 10, 17, 22, 16, 24, 13, 9, 19, 8, 0, 1, 20, 2, 6, 21, 15, 25, 18, 3, 5, 26, 4, 7};
+__device__ __forceinline__ int d_scan_slot(const DevP &D, int i, int a) {
+    int k = 0;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        int diff = D.cell_idx[3 * a + d] - D.cell_idx[3 * i + d];
+        int cn = D.cellnum[d];
+        if (diff == cn - 1) diff = -1;          // wrapped below
+        else if (diff == 1 - cn) diff = 1;      // wrapped above
+        k += (diff + 1) * (d == 0 ? 1 : d == 1 ? 3 : 9);
+    }
+    return c_kinv[k];
+}
+
+// settle atoms with a single lower-index pointer, queue the ambiguous ones
+__global__ void k_predict_all_resolve(DevP D, SlotBuf b, const int *pcount, const int *pwho, const double *second, int *queue,
+                                      int *nqueue, uint8_t *copyflag) {
     int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (i > D.n || !flags[i]) return;
+    if (i > D.n) return;
+    int cnt = pcount[i];
+    copyflag[i] = 0;
+    if (cnt == 0) return;
+    bool ambiguous = true;
+    if (cnt == 1) {
+        int j = pwho[i];
+        double tj = b.time[j];
+        // only plain collision pairs with a live counter match take the shortcut
+        if (b.type[j] == SDMD_EV_COLI && b.pcounter[j] == D.ev_counter[i]) {
+            double m1 = b.time[i];
+            bool j_is_best = (b.partner[i] == j && b.type[i] == SDMD_EV_COLI);
+            if (!j_is_best) {
+                // my own winner q must be a collision candidate visited BEFORE j: then the running best at j is
+                // already <= m1 < t_j, CheckDuplication cannot fire and both slot and evaluation count stand
+                int q = b.partner[i];
+                if (tj > m1 && q > 0 && b.type[i] == SDMD_EV_COLI) {
+                    int kq = d_scan_slot(D, i, q), kj = d_scan_slot(D, i, j);
+                    if (kq < kj || (kq == kj && q > j)) ambiguous = false;   // inside a cell: descending atom id
+                }
+            }
+            else if (tj < second[i]) { copyflag[i] = 1; ambiguous = false; }
+        } else if (b.pcounter[j] != D.ev_counter[i]) ambiguous = false;  // CheckDuplication can never fire
+    }
+    if (ambiguous) queue[atomicAdd(nqueue, 1)] = i;
+}
+
+// apply the copies (second kernel: every source slot j is an atom whose own slot the resolve step left alone)
+__global__ void k_predict_all_copy(DevP D, SlotBuf b, const int *pwho, const uint8_t *copyflag, int *npair) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i > D.n || !copyflag[i]) return;
+    int j = pwho[i];
+    b.partner[i] = j; b.pot[i] = b.pot[j]; b.sub[i] = b.sub[j]; b.time[i] = b.time[j]; b.type[i] = SDMD_EV_COLI;
+    b.pcounter[i] = D.ev_counter[j];
+    npair[i] -= 1;   // the duplicate is copied, not evaluated (TimePrediction.c:87-90)
+}
+
+// commit round r: move re-evaluated slots into the current buffer, queue dependants of changed slots
+__global__ void k_predict_all_commit(DevP D, SlotBuf cur, SlotBuf nxt, const int *queue, int nqueue, int *queue_next, int *nqueue_next) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nqueue) return;
+    int i = queue[p];
     bool same = __double_as_longlong(cur.time[i]) == __double_as_longlong(nxt.time[i]) &&
                 __double_as_longlong(cur.pot[i]) == __double_as_longlong(nxt.pot[i]) && cur.partner[i] == nxt.partner[i] &&
                 cur.pcounter[i] == nxt.pcounter[i] && cur.type[i] == nxt.type[i] && cur.sub[i] == nxt.sub[i];
@@ -290,9 +376,8 @@ __global__ void k_predict_all_commit(DevP D, SlotBuf cur, SlotBuf nxt, const uin
     int oldp = cur.partner[i], newp = nxt.partner[i];
     cur.time[i] = nxt.time[i]; cur.pot[i] = nxt.pot[i]; cur.partner[i] = newp; cur.pcounter[i] = nxt.pcounter[i];
     cur.type[i] = nxt.type[i]; cur.sub[i] = nxt.sub[i];
-    if (oldp > i) flags_next[oldp] = 1;
-    if (newp > i) flags_next[newp] = 1;
-    D.ctl->changed = 1;
+    if (oldp > i) queue_next[atomicAdd(nqueue_next, 1)] = oldp;
+    if (newp > i && newp != oldp) queue_next[atomicAdd(nqueue_next, 1)] = newp;
 }
 
 __global__ void k_predict_all_final(DevP D, SlotBuf b, const int *npair, unsigned long long *sum) {
@@ -390,12 +475,27 @@ __device__ inline void d_loop_body_serial(const DevP &D, double t_until, sdmd_tr
     }
 }
 
-// loop body after the advance, executed by the whole CTA: HazardCheck, DoEvent, counters (thread 0), then the
-// CTA-parallel Predict and the warp-assisted UpdateCBT (SGThread.c:80-151)
+// publish the AssignJob result to the block (thread 0, before a barrier)
+__device__ __forceinline__ void d_publish_job(const DevP &D, PredShared &sh) {
+    Ctl *c = D.ctl;
+    int target = c->target, partner = c->partner;
+    sh.atom[0] = target;
+    sh.atom[1] = partner;
+    int type = D.ev_type[target];
+    // candidate gathering may overlap the event unless the event itself edits what gathering reads:
+    // the link list (PCC) or the HB lists / types (HB)
+    sh.gathered = (type != SDMD_EV_PCC && type != SDMD_EV_HB);
+}
+
+// loop body after the advance, executed by the whole CTA: HazardCheck, DoEvent, counters (thread 0) overlapped
+// with the candidate layout of the dirty atoms (warps 1-2), then the CTA-parallel Predict and the warp-assisted
+// UpdateCBT (SGThread.c:80-151).  Precondition: d_publish_job + __syncthreads.
 __device__ inline void d_loop_body_cta(const DevP &D, PredShared &sh, double t_until, sdmd_trace_rec *trace, i64 trace_cap) {
     Ctl *c = D.ctl;
+    long long t0 = clock64();
+    int spec = sh.gathered;
     if (threadIdx.x == 0) {
-        int target = c->target, partner = c->partner;
+        int target = sh.atom[0], partner = sh.atom[1];
         c->currenttime += c->dt;
         int hazard = (partner > 0 && D.ev_pcounter[target] < D.ev_counter[partner]) ? -1 : 0;  // SGThread.c:224-227
         if (trace && c->trace_pos < trace_cap) {
@@ -406,31 +506,48 @@ __device__ inline void d_loop_body_cta(const DevP &D, PredShared &sh, double t_u
         }
         c->trace_pos++;
         c->iterations++;
+        int na;
         if (!hazard) {
             c->frame++;
             d_do_event(D, target, partner);
             D.ev_counter[target]++;
             if (partner && !D.is_cons[partner]) D.ev_counter[partner]++;
-            sh.natoms = partner ? 2 : 1;
-            sh.atom[0] = target; sh.atom[1] = partner;
+            na = partner ? 2 : 1;
             if (c->currenttime >= t_until) c->stop = 1 + SDMD_STOP_T_UNTIL;
         } else {
-            sh.natoms = 1;
-            sh.atom[0] = target; sh.atom[1] = 0;
+            na = 1;
             c->count_recal++;
         }
-        for (int a = 0; a < sh.natoms; a++) {   // one thermostat draw per predicted atom, in list order
+        sh.natoms = na;
+        for (int a = 0; a < na; a++) {
+            int i = sh.atom[a];
+            // ResetTarget for every listed atom first (ToolFunctions.c:504-514)
+            D.ev_type[i] = SDMD_EV_INVD; D.ev_time[i] = SD_INF; D.ev_partner[i] = SDMD_INVALID;
+            // one thermostat draw per predicted atom, in list order
             sh.gauss[a] = 0;
-            if (D.thermostat_on && !D.is_cons[sh.atom[a]]) sh.gauss[a] = d_next_gauss(D);
+            if (D.thermostat_on && !D.is_cons[i]) sh.gauss[a] = d_next_gauss(D);
         }
+        c->phase_cycles[8] += clock64() - t0;
+    } else if (spec) {
+        d_predict_gather(D, sh, 1, sh.atom[1] > 0 ? 2 : 1);
     }
     __syncthreads();
+    long long t1 = d_clock_after(&sh.natoms);
+    if (!spec) {
+        d_predict_gather(D, sh, 1, sh.natoms);
+        __syncthreads();
+    }
+    long long t1b = d_clock_after(&sh.natoms);
     d_predict_cta(D, sh);
+    long long t2 = clock64();
     if (threadIdx.x < 32) {
         d_cbt_update_warp(D, sh, sh.atom[0]);
         if (sh.natoms > 1) d_cbt_update_warp(D, sh, sh.atom[1]);
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        c->phase_cycles[2] += t1 - t0; c->phase_cycles[3] += t1b - t1; c->phase_cycles[6] += d_clock_after(&sh.natoms) - t2; c->phase_cycles[7] += 1;
+    }
 }
 
 // Small systems: the whole loop in ONE persistent CTA (one replica per CTA); no host round trip per event.
@@ -439,13 +556,16 @@ __global__ void __launch_bounds__(256, 1) k_run_cta(DevP D, double t_until, i64 
     __shared__ double s_dt;
     __shared__ int s_stop;
     for (;;) {
+        long long h0 = clock64();
         if (threadIdx.x == 0) {
             d_loop_head(D, t_until, iter_limit);
             s_dt = D.ctl->dt;
             s_stop = D.ctl->stop;
+            if (!s_stop) d_publish_job(D, sh);
         }
         __syncthreads();
         if (s_stop) break;
+        long long h1 = d_clock_after(&s_stop);
         double dt = s_dt;
         for (int i = threadIdx.x + 1; i <= D.n; i += blockDim.x) {
             D.x[i] = D.x[i] + D.vx[i] * dt;
@@ -454,6 +574,7 @@ __global__ void __launch_bounds__(256, 1) k_run_cta(DevP D, double t_until, i64 
             D.ev_time[i] = D.ev_time[i] - dt;
         }
         __syncthreads();
+        if (threadIdx.x == 0) { D.ctl->phase_cycles[0] += h1 - h0; D.ctl->phase_cycles[1] += d_clock_after(&s_stop) - h1; }
         d_loop_body_cta(D, sh, t_until, trace, trace_cap);
     }
 }
@@ -463,7 +584,10 @@ __global__ void __launch_bounds__(256, 1) k_run_cta(DevP D, double t_until, i64 
 __global__ void __launch_bounds__(256, 1) k_event_exec(DevP D, double t_until, i64 iter_limit, sdmd_trace_rec *trace, i64 trace_cap) {
     __shared__ PredShared sh;
     __shared__ int s_stop;
-    if (threadIdx.x == 0) s_stop = D.ctl->stop;
+    if (threadIdx.x == 0) {
+        s_stop = D.ctl->stop;
+        if (!s_stop) d_publish_job(D, sh);
+    }
     __syncthreads();
     if (s_stop) return;
     d_loop_body_cta(D, sh, t_until, trace, trace_cap);
@@ -656,6 +780,16 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     TRY(dupload(c, (int **)&P.cm_off, v->cm_off ? v->cm_off : zero_off.data(), n1 + 1));
     TRY(dupload(c, (int **)&P.cm_j, v->cm_j, (size_t)ncm));
     TRY(dupload(c, (int **)&P.cm_flags, v->cm_flags, (size_t)ncm));
+    {   // constraint table of every CONSTRAINT_CONNECT entry, resolved once from the constr list (ToolFunctions.c:70-77)
+        std::vector<int> cmt((size_t)ncm + 1, 0);
+        for (int i = 1; i <= n && ncm; i++)
+            for (int e = v->cm_off[i]; e < v->cm_off[i + 1]; e++)
+                if (v->cm_flags[e] & SDMD_CONSTRAINT_CONNECT)
+                    for (int k = v->con_off[i]; k < v->con_off[i + 1]; k++)
+                        if (v->con_j[k] == v->cm_j[e]) { cmt[e] = v->con_table[k]; break; }
+        TRY(dupload(c, (int **)&P.cm_table, cmt.data(), (size_t)ncm));
+    }
+    TRY(dalloc(c, &P.cell_cnt, (size_t)P.ncell + 1));
     TRY(dupload(c, (sdmd_step_table **)&P.tables, v->tables, (size_t)v->ntable));
     TRY(dupload(c, (int **)&P.coll_index, v->coll_index, (size_t)SD_NT * SD_NT));
     TRY(dupload(c, (int **)&P.hb_index, v->hb_index, (size_t)SDMD_NHBCLASS * SD_NT * SD_NT));
@@ -674,7 +808,8 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     TRY(dalloc(c, &c->b_pcounter, n1)); TRY(dalloc(c, &c->b_type, n1)); TRY(dalloc(c, &c->b_sub, n1));
     TRY(dalloc(c, &c->c_time, n1)); TRY(dalloc(c, &c->c_pot, n1)); TRY(dalloc(c, &c->c_partner, n1));
     TRY(dalloc(c, &c->c_pcounter, n1)); TRY(dalloc(c, &c->c_type, n1)); TRY(dalloc(c, &c->c_sub, n1));
-    TRY(dalloc(c, &c->flag_cur, n1)); TRY(dalloc(c, &c->flag_next, n1)); TRY(dalloc(c, &c->npair, n1));
+    TRY(dalloc(c, &c->copyflag, n1)); TRY(dalloc(c, &c->npair, n1)); TRY(dalloc(c, &c->pcount, n1)); TRY(dalloc(c, &c->pwho, n1));
+    TRY(dalloc(c, &c->queue_a, 2 * n1 + 2)); TRY(dalloc(c, &c->queue_b, 2 * n1 + 2)); TRY(dalloc(c, &c->nqueue, 4)); TRY(dalloc(c, &c->second, n1));
     TRY(dalloc(c, &c->cell_of, n1)); TRY(dalloc(c, &c->cell_count, (size_t)P.ncell + 1));
     TRY(dalloc(c, &c->cell_cursor, (size_t)P.ncell + 1));
     TRY(dalloc(c, &c->scan_tmp, (size_t)P.ncell / SCAN_ITEMS + 4));
@@ -805,6 +940,8 @@ int sdmd_cuda_upload_coords(sdmd_ctx *c, const double *x, const double *y, const
 int sdmd_cuda_upload_celllist(sdmd_ctx *c, const int32_t *celllist) {
     CK(cudaSetDevice(c->device));
     CK(cudaMemcpyAsync(c->P.celllist, celllist, ((size_t)c->n + c->P.ncell + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    k_cell_count<<<(c->P.ncell + 255) / 256, 256, 0, c->stream>>>(c->P);
+    c->launches++;
     c->cells_fresh = false;
     return 0;
 }
@@ -967,31 +1104,41 @@ int sdmd_cuda_predict_all(sdmd_ctx *c) {
     int grid = grid_for(n, 128), grid1 = grid_for(n, 256);
     {
         Timer t(c, "predict_all");
-        k_predict_all_round<<<grid, 128, 0, c->stream>>>(c->P, B, B, c->flag_cur, 0, c->npair, g_base);
+        k_predict_all_round<<<grid, 128, 0, c->stream>>>(c->P, B, B, nullptr, 0, 0, c->npair, c->second, g_base);
         c->launches++;
     }
-    Timer t2(c, "predict_all_fixup");
-    CK(cudaMemsetAsync(c->flag_cur, 0, (size_t)n + 1, c->stream));
-    k_predict_all_flag0<<<grid1, 256, 0, c->stream>>>(c->P, B, c->flag_cur);
-    c->launches++;
-    int rounds = 0;
-    for (;;) {
-        rounds++;
-        if (rounds > n + 2) return set_err(SDMD_ERR_STATE, "predict_all did not converge");
-        c->h_ctl->changed = 0;
-        CK(cudaMemcpyAsync(&c->d_ctl->changed, &c->h_ctl->changed, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemsetAsync(c->flag_next, 0, (size_t)n + 1, c->stream));
-        k_predict_all_round<<<grid, 128, 0, c->stream>>>(c->P, B, C, c->flag_cur, rounds, c->npair, g_base);
-        k_predict_all_commit<<<grid1, 256, 0, c->stream>>>(c->P, B, C, c->flag_cur, c->flag_next);
-        c->launches += 2;
-        CK(cudaMemcpyAsync(&c->h_ctl->changed, &c->d_ctl->changed, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    int rounds = 0, requeued = 0;
+    int hq[2] = {0, 0};
+    {
+        Timer t2(c, "predict_all_fixup");
+        CK(cudaMemsetAsync(c->pcount, 0, ((size_t)n + 1) * sizeof(int), c->stream));
+        CK(cudaMemsetAsync(c->nqueue, 0, 2 * sizeof(int), c->stream));
+        k_predict_all_point<<<grid1, 256, 0, c->stream>>>(c->P, B, c->pcount, c->pwho);
+        k_predict_all_resolve<<<grid1, 256, 0, c->stream>>>(c->P, B, c->pcount, c->pwho, c->second, c->queue_a, c->nqueue, c->copyflag);
+        k_predict_all_copy<<<grid1, 256, 0, c->stream>>>(c->P, B, c->pwho, c->copyflag, c->npair);
+        c->launches += 3;
+        CK(cudaMemcpyAsync(hq, c->nqueue, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        if (!c->h_ctl->changed) break;
-        std::swap(c->flag_cur, c->flag_next);
+        int *qa = c->queue_a, *qb = c->queue_b;
+        int nq = hq[0];
+        requeued = nq;
+        while (nq > 0) {
+            rounds++;
+            if (rounds > n + 2) return set_err(SDMD_ERR_STATE, "predict_all did not converge");
+            CK(cudaMemsetAsync(c->nqueue + 1, 0, sizeof(int), c->stream));
+            k_predict_all_round<<<grid_for(nq, 128), 128, 0, c->stream>>>(c->P, B, C, qa, nq, rounds, c->npair, c->second, g_base);
+            k_predict_all_commit<<<grid_for(nq, 256), 256, 0, c->stream>>>(c->P, B, C, qa, nq, qb, c->nqueue + 1);
+            c->launches += 2;
+            CK(cudaMemcpyAsync(hq, c->nqueue + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            nq = hq[0];
+            if (nq > 2 * n) return set_err(SDMD_ERR_STATE, "predict_all queue overflow");
+            std::swap(qa, qb);
+        }
+        CK(cudaMemsetAsync(c->d_sum, 0, sizeof(unsigned long long), c->stream));
+        k_predict_all_final<<<grid1, 256, 0, c->stream>>>(c->P, B, c->npair, c->d_sum);
+        c->launches++;
     }
-    CK(cudaMemsetAsync(c->d_sum, 0, sizeof(unsigned long long), c->stream));
-    k_predict_all_final<<<grid1, 256, 0, c->stream>>>(c->P, B, c->npair, c->d_sum);
-    c->launches++;
     unsigned long long sum = 0;
     CK(cudaMemcpyAsync(&sum, c->d_sum, sizeof(sum), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -1001,6 +1148,8 @@ int sdmd_cuda_predict_all(sdmd_ctx *c) {
     CK(cudaMemcpyAsync(&c->d_ctl->pair_predictions, &c->h_ctl->pair_predictions, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
     c->kstat["predict_all_rounds"].ms += rounds;
     c->kstat["predict_all_rounds"].n++;
+    c->kstat["predict_all_requeued"].ms += requeued;
+    c->kstat["predict_all_requeued"].n++;
     CK(cudaGetLastError());
     return 0;
 }
@@ -1149,6 +1298,13 @@ static void fill_stats(const Ctl *h, struct sdmd_run_stats *s) {
 int sdmd_cuda_get_stats(sdmd_ctx *c, struct sdmd_run_stats *s) {
     TRY(pull_ctl(c));
     fill_stats(c->h_ctl, s);
+    return 0;
+}
+
+// debug: accumulated clock64() cycles of the loop phases {head, advance, event, gather, eval, fold, cbt, count}
+int sdmd_cuda_phase_cycles(sdmd_ctx *c, int64_t out[12]) {
+    TRY(pull_ctl(c));
+    for (int k = 0; k < 12; k++) out[k] = c->h_ctl->phase_cycles[k];
     return 0;
 }
 

@@ -31,6 +31,7 @@ struct Ctl {
     int hbnumformed;
     int changed;               // predict_all fix-point flag
     i64 trace_pos;
+    i64 phase_cycles[12];      // clock64() per loop phase (thread 0): head, advance, event, gather, eval, fold, cbt
 };
 
 // thin view of "the slots other atoms currently hold" (live arrays in the event loop, the previous
@@ -44,6 +45,7 @@ struct SlotSrc {
 
 struct Slot {
     double time, pot;
+    double m2;      // value of the best candidate that did NOT win (used by the full-system pass)
     i64 pcounter;
     int partner, type, sub;
 };
@@ -76,6 +78,8 @@ struct DevP {
     const double *bond_dmin2, *bond_dmax2;
     const int *con_off, *con_j, *con_table;
     const int *cm_off, *cm_j, *cm_flags;
+    const int *cm_table;   // constraint table of a CONSTRAINT_CONNECT entry (resolved from the constr list at create)
+    int *cell_cnt;         // atoms per cell, kept in step with the link list
     const sdmd_step_table *tables;
     const int *coll_index, *hb_index;
     const double *gauss;
@@ -294,7 +298,9 @@ __device__ __forceinline__ bool d_check_dup(const DevP &D, const SlotSrc &S, Slo
 }
 // JobAssign, TimePrediction.c:1140-1158 (j == 0: no partner)
 __device__ __forceinline__ bool d_job_assign(const DevP &D, Slot &cur, int j, double time, double pot, int sub, int type) {
+    if (time > 0 && !(cur.time > time) && time < cur.m2) cur.m2 = time;
     if (time > 0 && cur.time > time) {
+        cur.m2 = cur.time;
         cur.pot = pot;
         cur.sub = sub;
         cur.time = time;
@@ -307,7 +313,10 @@ __device__ __forceinline__ bool d_job_assign(const DevP &D, Slot &cur, int j, do
 }
 
 __device__ __forceinline__ int d_neighbor_cell(const DevP &D, int cx, int cy, int cz, int k, int *ncx, int *ncy, int *ncz) {
-    int nx = cx + c_offx[k], ny = cy + c_offy[k], nz = cz + c_offz[k];  // TimePrediction.c:62-72
+    // DMD.c:118-120 offsets, 2 bits per slot (value + 1) packed per axis, so a warp whose lanes take different k
+    // does not serialise on the constant bank
+    const unsigned long long PX = 0xa80894054a959ULL, PY = 0x2222160111a665ULL, PZ = 0x28096084059a95ULL;
+    int nx = cx + (int)((PX >> (2 * k)) & 3) - 1, ny = cy + (int)((PY >> (2 * k)) & 3) - 1, nz = cz + (int)((PZ >> (2 * k)) & 3) - 1;  // TimePrediction.c:62-72
     if (nx < 0) nx = D.cellnum[0] - 1; else if (nx >= D.cellnum[0]) nx = 0;
     if (ny < 0) ny = D.cellnum[1] - 1; else if (ny >= D.cellnum[1]) ny = 0;
     if (nz < 0) nz = D.cellnum[2] - 1; else if (nz >= D.cellnum[2]) nz = 0;
@@ -570,7 +579,7 @@ __device__ __forceinline__ Self d_load_self(const DevP &D, int i) {
 // ResetTarget (ToolFunctions.c:504-514) leaves potential / subEventType / partnerCounter untouched
 __device__ __forceinline__ Slot d_reset_slot(double pot, int sub, i64 pcounter) {
     Slot s;
-    s.time = SD_INF; s.type = SDMD_EV_INVD; s.partner = SDMD_INVALID;
+    s.time = SD_INF; s.type = SDMD_EV_INVD; s.partner = SDMD_INVALID; s.m2 = SD_INF;
     s.pot = pot; s.sub = sub; s.pcounter = pcounter;
     return s;
 }
@@ -578,7 +587,8 @@ __device__ __forceinline__ Slot d_reset_slot(double pot, int sub, i64 pcounter) 
 // one atom of Predict, SGThread.c:162-208, executed by a single thread in reference order.
 // SORTED selects the cell-sorted tiles for the 27-cell scan (fresh link list only).
 template <bool SORTED>
-__device__ inline Slot d_predict_atom(const DevP &D, const SlotSrc &S, int i, Slot cur, double gauss, int dup_limit, int *npair) {
+__device__ inline Slot d_predict_atom(const DevP &D, const SlotSrc &S, int i, Slot cur, double gauss, int dup_limit, int *npair,
+                                      double *second = nullptr) {
     if (D.is_cons[i]) { cur.time = SD_INF; return cur; }
     Self me = d_load_self(D, i);
     if (!D.gel_mode) d_bond_time(D, S, me, cur, dup_limit);
@@ -591,6 +601,7 @@ __device__ inline Slot d_predict_atom(const DevP &D, const SlotSrc &S, int i, Sl
         d_hbn_time(D, S, me, cur, dup_limit);
     }
     *npair = me.npair;
+    if (second) *second = cur.m2;
     return cur;
 }
 
@@ -886,6 +897,8 @@ __device__ inline void d_pcc_event(const DevP &D, int i) {
     next = newCell + 1 + D.n;
     cl[i] = cl[next];
     cl[next] = i;
+    D.cell_cnt[oldCell]--;
+    D.cell_cnt[newCell]++;
 }
 
 // DoEvent, Events.c:25-114
@@ -916,35 +929,48 @@ __device__ inline void d_do_event(const DevP &D, int i, int j) {
 // bonded / free HB partners, HB neighbours) becomes one entry of a candidate array laid out in the exact
 // order the reference visits them; all threads evaluate entries in parallel (own-side time, potential,
 // sub-event), and the per-atom earliest-event fold (JobAssign, strict '<', first wins) is then taken over
-// that array.  CheckDuplication couples the fold to the running best, so entries whose partner's slot
-// points back at this atom are resolved in order by one thread; when there is none the fold is a parallel
-// lexicographic (time, position) minimum.
+// that array.  CheckDuplication couples the fold to the running best, so the array is cut at the entries
+// whose partner's slot points back at this atom; the pieces in between collapse to their first minimum
+// (warp REDUX), and one lane replays the few pieces in order.
+//
+// The loop is latency bound (one event at a time), so everything an entry needs that depends only on the
+// predicted atom — minimum-image shifts of the 27 neighbour cells, its connectionMap row, its row of the
+// collision-table index, its HB lists — is staged in shared memory by the warp that lays the array out.
 // ===================================================================================================
 #define PC_MAXC 448          // candidates per atom held in shared memory; larger neighbourhoods use the serial path
-enum { CK_BOND = 0, CK_COLL = 1, CK_PCC = 2, CK_THER = 3, CK_HB = 4, CK_HBFREE = 5, CK_HBNE = 6 };
+#define PC_MAXADJ 64         // connectionMap row entries staged in shared memory
+enum { CK_BOND = 0, CK_COLL = 1, CK_PCC = 2, CK_THER = 3, CK_HB = 4, CK_HBFREE = 5, CK_HBNE = 6, CK_NONE = 7 };
 #define CF_VALID 1           // own-side event exists and its time is > 0
 #define CF_COUNTED 2         // a CalculateParameters-equivalent evaluation happened on the own-side path
 #define CF_ELIGIBLE 4        // partner's slot points back (CheckDuplication's first three conditions)
+#define PC_MAXE 3            // eligible entries handled by the segmented fold (more: serial replay)
 
 struct PredShared {
     int natoms;
     int atom[2];
     double gauss[2];
+    int gathered;             // candidate arrays already laid out (overlapped with the event)
     int use_serial[2];
     int ncand[2];
-    int cell_cnt[2][27];
-    int cell_off[2][28];
-    int hb_free[2];           // free donor/acceptor scan active
+    int hb_free[2];
     int n_bond[2], n_coll[2], n_hbne[2];
     int off_coll[2], off_pcc[2], off_ther[2], off_hb[2], off_hbne[2];
     Slot result[2];
     int winner_pos[2];
     int npair[2];
-    int any_elig[2];
+    int n_adj[2];
+    int adj_j[2][PC_MAXADJ];
+    int adj_f[2][PC_MAXADJ];     // connectionMap flags | (constraint table index << 8)
+    int hbn[2][4];               // neighborPartner[1..4]
+    int hb_bond[2];
+    int coll_row[2][SD_NT];      // coll_index[type_i][*]
+    double shift[2][27][3];      // minimum-image shift of neighbour-cell slot k (PBCShift, ToolFunctions.c:801-817)
+    int elig_n[2];
+    int elig_pos[2][8];
     // candidate arrays: atom a occupies [a * PC_MAXC, (a + 1) * PC_MAXC)
     int cj[2 * PC_MAXC];
     unsigned char ckind[2 * PC_MAXC];
-    unsigned char caux[2 * PC_MAXC];   // neighbour-cell slot k / HB-neighbour index n
+    unsigned char caux[2 * PC_MAXC];   // neighbour-cell slot k / bond slot / HB-neighbour index n
     unsigned char csub[2 * PC_MAXC];
     unsigned char cflag[2 * PC_MAXC];
     double ctime[2 * PC_MAXC];
@@ -954,15 +980,18 @@ struct PredShared {
     double path_tsib[40];
 };
 
+// clock64() that cannot issue before a shared-memory word is read back: BAR.SYNC is deferred-blocking, so a bare
+// clock read right after __syncthreads() samples the barrier's ISSUE time, not its release
+__device__ __forceinline__ long long d_clock_after(const int *smem_word) {
+    int v = *(volatile const int *)smem_word;
+    long long t;
+    asm volatile("{ .reg .b32 d; mov.b32 d, %1; mov.u64 %0, %%clock64; }" : "=l"(t) : "r"(v) : "memory");
+    return t;
+}
+
 __device__ __forceinline__ int d_kind_event(int kind) {
-    switch (kind) {
-        case CK_BOND: return SDMD_EV_BOND;
-        case CK_COLL: return SDMD_EV_COLI;
-        case CK_PCC: return SDMD_EV_PCC;
-        case CK_THER: return SDMD_EV_THER;
-        case CK_HBNE: return SDMD_EV_HBNE;
-        default: return SDMD_EV_HB;
-    }
+    return kind == CK_BOND ? SDMD_EV_BOND : kind == CK_COLL ? SDMD_EV_COLI : kind == CK_PCC ? SDMD_EV_PCC
+         : kind == CK_THER ? SDMD_EV_THER : kind == CK_HBNE ? SDMD_EV_HBNE : SDMD_EV_HB;
 }
 
 // FindPair's step walk with every table load issued up front (same comparisons, same first match)
@@ -974,6 +1003,7 @@ __device__ __forceinline__ FindRes d_find_pair_table_fast(const DevP &D, const s
     double tol = dir * SD_ZERO;
     double dmin2 = __ldg(&t->dmin2), dmax2 = __ldg(&t->dmax2);
     int ns = __ldg(&t->nstep);
+    if (dmin2 == 0) D.ctl->error = SDMD_ERR_TABLE;   // fatal in the reference, ToolFunctions.c:114-117
     if (dist2 < dmin2 - SD_ZERO) {
         r.lower = SD_INF; r.upper = SD_INF; r.accum = SD_INF; r.lowPot = 0; r.upPot = 0;
         if (!(mode == FP_NEIGHBOR && bond_a2 == 0) && !(mode == FP_HB && bond_a1 == 0)) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
@@ -1028,7 +1058,7 @@ __device__ inline FindRes d_find_pair_fast(const DevP &D, int a1, int a2, int mo
         int t1 = d_type_change(D.type[a1], 0), t2 = d_type_change(D.type[a2], 0);
         if (cls >= 0) idx = __ldg(&D.hb_index[(cls * SD_NT + t1) * SD_NT + t2]);
     }
-    if (idx < 0 || D.tables[idx].dmin2 == 0) {
+    if (idx < 0) {
         D.ctl->error = SDMD_ERR_TABLE;
         FindRes r;
         r.lower = SD_INF; r.upper = SD_INF; r.accum = SD_INF; r.lowPot = 0; r.upPot = 0; r.cs = -1;
@@ -1037,88 +1067,184 @@ __device__ inline FindRes d_find_pair_fast(const DevP &D, int a1, int a2, int mo
     return d_find_pair_table_fast(D, &D.tables[idx], mode, direction, dist2, D.hb_bond[a1], D.hb_bond[a2]);
 }
 
-// ---- phase A: lay out the candidate array of predict-atom `a` (called by all threads) ----
-__device__ inline void d_pc_gather(const DevP &D, PredShared &sh, int a) {
+// ---- phase A: lay out the candidate array of predict-atom `a` (executed by ONE warp per atom) ----
+// Per-cell occupancy counts (maintained next to the link list) give every neighbour cell's offset with one
+// warp scan, so each list is walked exactly once.
+__device__ inline void d_pc_gather_warp(const DevP &D, PredShared &sh, int a) {
+    int lane = threadIdx.x & 31;
     int i = sh.atom[a];
-    int tid = threadIdx.x;
     int base = a * PC_MAXC;
     int cx = D.cell_idx[3 * i], cy = D.cell_idx[3 * i + 1], cz = D.cell_idx[3 * i + 2];
-    // 27 threads walk the 27 neighbour-cell lists (count pass)
-    if (tid < 27) {
+    int cell = 0, cnt = 0;
+    if (lane < 27) {
         int ncx, ncy, ncz;
-        int cell = d_neighbor_cell(D, cx, cy, cz, tid, &ncx, &ncy, &ncz);
-        int cnt = 0;
-        for (int j = D.celllist[D.n + cell + 1]; j; j = D.celllist[j]) cnt += (j != i);
-        sh.cell_cnt[a][tid] = cnt;
+        cell = d_neighbor_cell(D, cx, cy, cz, lane, &ncx, &ncy, &ncz);
+        cnt = D.cell_cnt[cell] - (lane == 0 ? 1 : 0);   // offset 0 is the atom's own cell
+        sh.shift[a][lane][0] = d_shift1(cx, ncx, D.cellnum[0], D.box[0]);
+        sh.shift[a][lane][1] = d_shift1(cy, ncy, D.cellnum[1], D.box[1]);
+        sh.shift[a][lane][2] = d_shift1(cz, ncz, D.cellnum[2], D.box[2]);
     }
-    __syncthreads();
-    if (tid == 0) {
-        int off = 0;
-        for (int k = 0; k < 27; k++) { sh.cell_off[a][k] = off; off += sh.cell_cnt[a][k]; }
-        sh.cell_off[a][27] = off;
-        int ncoll = off;
-        int nb = D.gel_mode ? 0 : (D.bond_off[i + 1] - D.bond_off[i]);
-        int role = D.hb_role[i];
+    int incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    int ncoll = __shfl_sync(0xffffffffu, incl, 31);
+    int off = incl - cnt;
+    // section layout (every lane computes the same small thing from broadcast loads)
+    int nb = D.gel_mode ? 0 : (D.bond_off[i + 1] - D.bond_off[i]);
+    int nhb = 0, hbfree = 0, nhbne = 0;
+    int role = 0, bonded = 0;
+    if (D.hydrogen_bond) {
+        role = D.hb_role[i];
+        bonded = D.hb_bond[i];
         int itype = D.hb_itype[i];
-        int bonded = D.hb_bond[i];
-        int nhb = 0, hbfree = 0, nhbne = 0;
-        if (D.hydrogen_bond) {
-            if (itype != SDMD_HB_SKIP) {   // TimePrediction.c:309-327
-                if (bonded > 0) nhb = 1;
-                else if ((role == 'A' || role == 'D' || role == 'S') && bonded == 0) { hbfree = 1; nhb = ncoll; }
-            }
-            nhbne = D.hbn_status[i];
+        if (itype != SDMD_HB_SKIP) {   // TimePrediction.c:309-327
+            if (bonded > 0) nhb = 1;
+            else if ((role == 'A' || role == 'D' || role == 'S') && bonded == 0) { hbfree = 1; nhb = ncoll; }
         }
-        int pos = 0;
-        sh.n_bond[a] = nb; pos += nb;
-        sh.off_coll[a] = pos; sh.n_coll[a] = ncoll; pos += ncoll;
-        sh.off_pcc[a] = pos; pos += 1;
-        sh.off_ther[a] = pos; pos += D.thermostat_on ? 1 : 0;
-        sh.off_hb[a] = pos; pos += nhb;
-        sh.off_hbne[a] = pos; sh.n_hbne[a] = nhbne; pos += nhbne;
-        sh.hb_free[a] = hbfree;
-        sh.ncand[a] = pos;
-        sh.use_serial[a] = (pos > PC_MAXC);
+        nhbne = D.hbn_status[i];
     }
-    __syncthreads();
-    if (sh.use_serial[a]) return;
-    // fill pass
-    if (tid < 27) {
-        int ncx, ncy, ncz;
-        int cell = d_neighbor_cell(D, cx, cy, cz, tid, &ncx, &ncy, &ncz);
-        int p = base + sh.off_coll[a] + sh.cell_off[a][tid];
-        int q = base + sh.off_hb[a] + sh.cell_off[a][tid];
-        int hbfree = sh.hb_free[a];
+    int off_coll = nb;
+    int off_pcc = off_coll + ncoll;
+    int off_ther = off_pcc + 1;
+    int off_hb = off_ther + (D.thermostat_on ? 1 : 0);
+    int off_hbne = off_hb + nhb;
+    int total = off_hbne + nhbne;
+    int ncm = D.cm_off[i + 1] - D.cm_off[i];
+    bool serial = total > PC_MAXC || ncm > PC_MAXADJ || nb > 27;
+    if (lane == 0) {
+        sh.n_bond[a] = nb; sh.n_coll[a] = ncoll; sh.n_hbne[a] = nhbne; sh.hb_free[a] = hbfree;
+        sh.off_coll[a] = off_coll; sh.off_pcc[a] = off_pcc; sh.off_ther[a] = off_ther; sh.off_hb[a] = off_hb;
+        sh.off_hbne[a] = off_hbne; sh.ncand[a] = total; sh.use_serial[a] = serial; sh.n_adj[a] = ncm;
+        sh.hb_bond[a] = bonded;
+    }
+    if (serial) return;
+    if (lane < 27) {
+        int p = base + off_coll + off;
+        int q = base + off_hb + off;
+        int ti = D.type[i], pi = D.protein[i], ai = D.aa_num[i];
         for (int j = D.celllist[D.n + cell + 1]; j; j = D.celllist[j]) {
             if (j == i) continue;
-            sh.cj[p] = j; sh.ckind[p] = CK_COLL; sh.caux[p] = (unsigned char)tid; p++;
-            if (hbfree) { sh.cj[q] = j; sh.ckind[q] = CK_HBFREE; sh.caux[q] = (unsigned char)tid; q++; }
+            sh.cj[p] = j; sh.ckind[p] = CK_COLL; sh.caux[p] = (unsigned char)lane; p++;
+            if (hbfree) {
+                // role / bonded / sequence-separation filters of the free-HB scan, TimePrediction.c:418-429
+                int rj = D.hb_role[j];
+                bool ad = (role == 'A' && rj == 'D') || (role == 'D' && rj == 'A');
+                bool sd = (role == 'S' && D.type[j] == 2) || (rj == 'S' && ti == 2);
+                bool ss = (role == 'S' && rj == 'S');
+                int d = ai - D.aa_num[j];
+                if (d < 0) d = -d;
+                bool pass = (ad || sd || ss) && D.hb_bond[j] == 0 && ((pi == D.protein[j] && d >= 4) || pi != D.protein[j]);
+                sh.cj[q] = j; sh.ckind[q] = pass ? CK_HBFREE : CK_NONE; sh.caux[q] = (unsigned char)lane;
+                sh.cflag[q] = 0; sh.ctime[q] = SD_INF;
+                q++;
+            }
         }
-    } else if (tid >= 32 && tid < 32 + 16) {
-        int k = tid - 32;
-        if (k < sh.n_bond[a]) {
-            int p = base + k;
-            sh.cj[p] = D.bond_j[D.bond_off[i] + k]; sh.ckind[p] = CK_BOND; sh.caux[p] = (unsigned char)k;
-        }
-    } else if (tid == 64) {
-        int p = base + sh.off_pcc[a];
+    }
+    if (lane < nb) {
+        int p = base + lane;
+        sh.cj[p] = D.bond_j[D.bond_off[i] + lane]; sh.ckind[p] = CK_BOND; sh.caux[p] = (unsigned char)lane;
+    }
+    if (lane == 31) {
+        int p = base + off_pcc;
         sh.cj[p] = 0; sh.ckind[p] = CK_PCC; sh.caux[p] = 0;
-        if (D.thermostat_on) { p = base + sh.off_ther[a]; sh.cj[p] = 0; sh.ckind[p] = CK_THER; sh.caux[p] = 0; }
-        if (!sh.hb_free[a] && sh.off_hbne[a] > sh.off_hb[a]) {
-            p = base + sh.off_hb[a];
-            sh.cj[p] = D.hb_bond[i]; sh.ckind[p] = CK_HB; sh.caux[p] = 0;
+        if (D.thermostat_on) { p = base + off_ther; sh.cj[p] = 0; sh.ckind[p] = CK_THER; sh.caux[p] = 0; }
+        if (!hbfree && nhb == 1) { p = base + off_hb; sh.cj[p] = bonded; sh.ckind[p] = CK_HB; sh.caux[p] = 0; }
+    }
+    if (lane >= 27 && lane < 31) {
+        int n = lane - 27 + 1;
+        int hp = D.hydrogen_bond ? D.hbn_partner[5 * i + n] : 0;
+        sh.hbn[a][n - 1] = hp;
+        if (n <= nhbne) {
+            int p = base + off_hbne + n - 1;
+            sh.cj[p] = hp; sh.ckind[p] = CK_HBNE; sh.caux[p] = (unsigned char)n;
         }
-        for (int n = 1; n <= sh.n_hbne[a]; n++) {
-            p = base + sh.off_hbne[a] + n - 1;
-            sh.cj[p] = D.hbn_partner[5 * i + n]; sh.ckind[p] = CK_HBNE; sh.caux[p] = (unsigned char)n;
-        }
+    }
+    for (int k = lane; k < ncm; k += 32) {
+        int e = D.cm_off[i] + k;
+        sh.adj_j[a][k] = D.cm_j[e];
+        sh.adj_f[a][k] = D.cm_flags[e] | (D.cm_table[e] << 8);
+    }
+    {
+        int ti = D.type[i];
+        for (int k = lane; k < SD_NT; k += 32) sh.coll_row[a][k] = __ldg(&D.coll_index[ti * SD_NT + k]);
     }
 }
 
 // ---- phase B: own-side evaluation of one candidate entry (any thread) ----
+// lean path for the cell-scan entries of CollisionTime (TimePrediction.c:82-176)
+__device__ __forceinline__ void d_pc_eval_coll(const DevP &D, PredShared &sh, int a, int p, const Self &me) {
+    int q = a * PC_MAXC + p;
+    int j = sh.cj[q];
+    int k = sh.caux[q];
+    int i = me.i;
+    int flag = 0, sub = SDMD_SUB_INVALID;
+    double time = SD_INF, pot = 0;
+    // independent loads first
+    double xj = D.x[j], yj = D.y[j], zj = D.z[j], vxj = D.vx[j], vyj = D.vy[j], vzj = D.vz[j];
+    int pj = D.ev_partner[j];
+    int tyj = D.ev_type[j];
+    i64 pcj = D.ev_pcounter[j];
+    int typej = D.type[j];
+    double shx = sh.shift[a][k][0], shy = sh.shift[a][k][1], shz = sh.shift[a][k][2];
+    int cm = 0, con_tbl = 0;
+    int na_ = sh.n_adj[a];
+    for (int e = 0; e < na_; e++) {
+        int aj = sh.adj_j[a][e];
+        int af = sh.adj_f[a][e];
+        if (aj == j) { cm = af & 0xff; con_tbl = af >> 8; }
+    }
+    bool skip = (cm & SDMD_BOND_CONNECT) || sh.hb_bond[a] == j;
+    // FindElemInList over neighborPartner stops at the first 0 (ToolFunctions.c:1078-1084)
+    {
+        int h0 = sh.hbn[a][0], h1 = sh.hbn[a][1], h2 = sh.hbn[a][2], h3 = sh.hbn[a][3];
+        bool in = (h0 == j) || (h0 != 0 && (h1 == j || (h1 != 0 && (h2 == j || (h2 != 0 && h3 == j)))));
+        skip = skip || in;
+    }
+    if (pj == i && tyj == SDMD_EV_COLI && pcj == me.counter) flag |= CF_ELIGIBLE;
+    if (!skip) {
+        Pair pr = d_pair(me.x, me.y, me.z, me.vx, me.vy, me.vz, xj, yj, zj, vxj, vyj, vzj, shx, shy, shz);
+        flag |= CF_COUNTED;
+        if (pr.r2 <= D.cut2) {
+            FindRes f;
+            bool none = false;
+            if (cm & SDMD_CONSTRAINT_CONNECT) {
+                f = d_find_pair_table_fast(D, &D.tables[con_tbl], FP_CONSTRAINT, pr.b, pr.r2, 0, 0);
+            } else {
+                int idx = sh.coll_row[a][typej];
+                if (idx < 0) { D.ctl->error = SDMD_ERR_TABLE; idx = 0; }
+                f = d_find_pair_table_fast(D, &D.tables[idx], FP_COLLISION, pr.b, pr.r2, 0, 0);
+                if (f.lowPot == 0 && f.upPot == 0) none = true;
+            }
+            if (!none) {
+                int s; double d2;
+                if (pr.b < 0 && d_disc(pr, f.lower) > 0) {
+                    s = -1; d2 = f.lower; pot = f.lowPot;
+                    sub = (f.cs == 0) ? SDMD_SUB_CORECOLLI : SDMD_SUB_TBDCAPTR;
+                } else {
+                    s = 1; d2 = f.upper; pot = f.upPot;
+                    if (D.method_ding) {
+                        if (cm & SDMD_CONSTRAINT_CONNECT) sub = (f.cs == 1) ? SDMD_SUB_WELLBOUNC : SDMD_SUB_TBDESCAP;
+                        else { if (f.cs == 1) none = true; sub = SDMD_SUB_TBDESCAP; }
+                    }
+                }
+                if (!none) {
+                    time = d_time(pr, s, d2);
+                    if (time < 0) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+                    if (time > 0) flag |= CF_VALID;
+                }
+            }
+        }
+    }
+    sh.ctime[q] = time; sh.cpot[q] = pot; sh.csub[q] = (unsigned char)sub; sh.cflag[q] = (unsigned char)flag;
+}
+
+// every other predictor's entries
 __device__ inline void d_pc_eval(const DevP &D, PredShared &sh, int a, int p, const Self &me) {
     int q = a * PC_MAXC + p;
     int kind = sh.ckind[q];
+    if (kind == CK_NONE) return;
     int j = sh.cj[q];
     int i = me.i;
     int flag = 0, sub = SDMD_SUB_INVALID;
@@ -1132,123 +1258,86 @@ __device__ inline void d_pc_eval(const DevP &D, PredShared &sh, int a, int p, co
         time = D.thermoF * ((g < 0) ? (-g) : (g));
         if (time > 0) flag = CF_VALID;
     } else {
-        // cell-index minimum image (PBCShift) — for cell-scan entries j's cell is the scanned neighbour cell
-        Pair pr;
-        bool do_pair = true;
-        int cm = 0;
-        if (kind == CK_COLL) {
-            cm = (D.cm_off[i + 1] > D.cm_off[i]) ? d_cm_flags(D, i, j) : 0;
-            if ((cm & SDMD_BOND_CONNECT) || D.hb_bond[i] == j || d_find_in_hbn(D, i, j)) do_pair = false;
-        } else if (kind == CK_HBFREE) {
-            int role = D.hb_role[i], rj = D.hb_role[j];
-            bool ad = (role == 'A' && rj == 'D') || (role == 'D' && rj == 'A');
-            bool sd = (role == 'S' && D.type[j] == 2) || (rj == 'S' && D.type[i] == 2);
-            bool ss = (role == 'S' && rj == 'S');
-            int d = D.aa_num[i] - D.aa_num[j];
-            if (d < 0) d = -d;
-            if (!(ad || sd || ss) || D.hb_bond[j] != 0 ||
-                !((D.protein[i] == D.protein[j] && d >= 4) || D.protein[i] != D.protein[j]))
-                do_pair = false;
-        }
-        // eligibility for CheckDuplication (TimePrediction.c:1102-1104); HB free pairs test it after their filters
-        bool elig_ok = (kind != CK_HBFREE) || do_pair;
-        if (elig_ok && D.ev_partner[j] == i && D.ev_type[j] == d_kind_event(kind) && D.ev_pcounter[j] == me.counter) flag |= CF_ELIGIBLE;
-        if (do_pair) {
-            pr = d_pair_atoms(D, i, j);
-            flag |= CF_COUNTED;
-            if (kind == CK_BOND) {
-                int k = D.bond_off[i] + sh.caux[q];
-                double long2 = D.bond_dmax2[k], short2 = D.bond_dmin2[k];
-                bool done = false;
-                if (pr.r2 - long2 > SD_ZERO) {
-                    atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
-                    if (pr.b >= 0) { time = 1e-16 * i * j; sub = SDMD_SUB_WELLBOUNC; done = true; }
-                } else if (short2 - pr.r2 > SD_ZERO) {
-                    atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
-                    if (pr.b < 0) { time = 1e-16 * i * j; sub = SDMD_SUB_CORECOLLI; done = true; }
-                }
-                if (!done) {
-                    int s; double d2;
-                    if (pr.b < 0 && d_disc(pr, short2) > 0) { s = -1; d2 = short2; sub = SDMD_SUB_CORECOLLI; }
-                    else { s = 1; d2 = long2; sub = SDMD_SUB_WELLBOUNC; }
-                    time = d_time(pr, s, d2);
-                    if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); time = SD_INF; }
-                }
-                pot = 0;
-                if (time > 0) flag |= CF_VALID;
-            } else if (kind == CK_COLL) {
-                if (pr.r2 <= D.cut2) {
-                    FindRes f;
-                    bool skip = false;
-                    if (cm & SDMD_CONSTRAINT_CONNECT) f = d_find_pair_fast(D, i, j, FP_CONSTRAINT, pr.b, pr.r2, 0);
-                    else {
-                        f = d_find_pair_fast(D, i, j, FP_COLLISION, pr.b, pr.r2, 0);
-                        if (f.lowPot == 0 && f.upPot == 0) skip = true;
-                    }
-                    if (!skip) {
-                        int s; double d2;
-                        if (pr.b < 0 && d_disc(pr, f.lower) > 0) {
-                            s = -1; d2 = f.lower; pot = f.lowPot;
-                            sub = (f.cs == 0) ? SDMD_SUB_CORECOLLI : SDMD_SUB_TBDCAPTR;
-                        } else {
-                            s = 1; d2 = f.upper; pot = f.upPot;
-                            if (D.method_ding) {
-                                if (cm & SDMD_CONSTRAINT_CONNECT) sub = (f.cs == 1) ? SDMD_SUB_WELLBOUNC : SDMD_SUB_TBDESCAP;
-                                else { if (f.cs == 1) skip = true; sub = SDMD_SUB_TBDESCAP; }
-                            }
-                        }
-                        if (!skip) {
-                            time = d_time(pr, s, d2);
-                            if (time < 0) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
-                            if (time > 0) flag |= CF_VALID;
-                        }
-                    }
-                }
-            } else if (kind == CK_HB) {
-                FindRes f = d_find_pair_fast(D, i, j, FP_HB, pr.b, pr.r2, 0);
-                int s; double d2;
-                if (pr.b < 0 && d_disc(pr, f.lower) > 0) {
-                    s = -1; d2 = f.lower; pot = f.lowPot;
-                    sub = (f.cs == 0) ? SDMD_SUB_CORECOLLI : SDMD_SUB_TBDCAPTR;
-                } else {
-                    s = 1; d2 = f.upper; pot = f.upPot;
-                    if (D.method_ding) sub = (f.cs == 1) ? SDMD_SUB_TBDHBBRIK : SDMD_SUB_TBDESCAP;
-                }
-                time = d_time(pr, s, d2);
-                if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); time = SD_INF; }
-                if (time > 0) flag |= CF_VALID;
-            } else if (kind == CK_HBFREE) {
-                if (pr.r2 <= D.cut2 && d_check_pair_match(D, i, j) >= 0) {
-                    FindRes f = d_find_pair_fast(D, i, j, FP_HB, pr.b, pr.r2, 0);
-                    if (pr.b < 0 && f.cs == 1 && d_disc(pr, f.lower) > 0) {
-                        time = d_time(pr, -1, f.lower);
-                        pot = f.lowPot; sub = SDMD_SUB_TBDHBFORM;
-                        if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); time = SD_INF; }
-                        if (time > 0) flag |= CF_VALID;
-                    }
-                }
-            } else {  // CK_HBNE
-                int host, nbr, third;
-                int r = D.hb_role[i];
-                int bi = D.hb_bond[i];
-                if ((r == 'A' || r == 'D' || r == 'S') && (bi && D.hb_neighbor[bi] == j)) { host = i; nbr = j; third = bi; }
-                else { host = j; nbr = i; third = D.hb_bond[j]; }
-                FindRes f = d_find_pair_fast(D, nbr, host, FP_NEIGHBOR, pr.b, pr.r2, third);
-                int s; double d2;
-                if (pr.b < 0 && d_disc(pr, f.lower) > 0) {
-                    s = -1; d2 = f.lower; pot = f.lowPot;
-                    sub = (f.cs == 0) ? SDMD_SUB_CORECOLLI : SDMD_SUB_TBDCAPTR;
-                } else {
-                    s = 1; d2 = f.upper; pot = f.upPot;
-                    if (D.method_ding) sub = (f.cs == 1) ? SDMD_SUB_WELLBOUNC : SDMD_SUB_TBDESCAP;
-                }
-                time = d_time(pr, s, d2);
-                if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); time = SD_INF; }
-                if (time > 0) flag |= CF_VALID;
+        // eligibility for CheckDuplication (TimePrediction.c:1102-1104)
+        if (D.ev_partner[j] == i && D.ev_type[j] == d_kind_event(kind) && D.ev_pcounter[j] == me.counter) flag |= CF_ELIGIBLE;
+        Pair pr = d_pair_atoms(D, i, j);
+        flag |= CF_COUNTED;
+        if (kind == CK_BOND) {
+            int k = D.bond_off[i] + sh.caux[q];
+            double long2 = D.bond_dmax2[k], short2 = D.bond_dmin2[k];
+            bool done = false;
+            if (pr.r2 - long2 > SD_ZERO) {
+                atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+                if (pr.b >= 0) { time = 1e-16 * i * j; sub = SDMD_SUB_WELLBOUNC; done = true; }
+            } else if (short2 - pr.r2 > SD_ZERO) {
+                atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+                if (pr.b < 0) { time = 1e-16 * i * j; sub = SDMD_SUB_CORECOLLI; done = true; }
             }
+            if (!done) {
+                int s; double d2;
+                if (pr.b < 0 && d_disc(pr, short2) > 0) { s = -1; d2 = short2; sub = SDMD_SUB_CORECOLLI; }
+                else { s = 1; d2 = long2; sub = SDMD_SUB_WELLBOUNC; }
+                time = d_time(pr, s, d2);
+                if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); time = SD_INF; }
+            }
+            pot = 0;
+            if (time > 0) flag |= CF_VALID;
+        } else if (kind == CK_HB) {
+            FindRes f = d_find_pair_fast(D, i, j, FP_HB, pr.b, pr.r2, 0);
+            int s; double d2;
+            if (pr.b < 0 && d_disc(pr, f.lower) > 0) {
+                s = -1; d2 = f.lower; pot = f.lowPot;
+                sub = (f.cs == 0) ? SDMD_SUB_CORECOLLI : SDMD_SUB_TBDCAPTR;
+            } else {
+                s = 1; d2 = f.upper; pot = f.upPot;
+                if (D.method_ding) sub = (f.cs == 1) ? SDMD_SUB_TBDHBBRIK : SDMD_SUB_TBDESCAP;
+            }
+            time = d_time(pr, s, d2);
+            if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); time = SD_INF; }
+            if (time > 0) flag |= CF_VALID;
+        } else if (kind == CK_HBFREE) {
+            if (pr.r2 <= D.cut2 && d_check_pair_match(D, i, j) >= 0) {
+                FindRes f = d_find_pair_fast(D, i, j, FP_HB, pr.b, pr.r2, 0);
+                if (pr.b < 0 && f.cs == 1 && d_disc(pr, f.lower) > 0) {
+                    time = d_time(pr, -1, f.lower);
+                    pot = f.lowPot; sub = SDMD_SUB_TBDHBFORM;
+                    if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); time = SD_INF; }
+                    if (time > 0) flag |= CF_VALID;
+                }
+            }
+        } else {  // CK_HBNE
+            int host, nbr, third;
+            int r = D.hb_role[i];
+            int bi = D.hb_bond[i];
+            if ((r == 'A' || r == 'D' || r == 'S') && (bi && D.hb_neighbor[bi] == j)) { host = i; nbr = j; third = bi; }
+            else { host = j; nbr = i; third = D.hb_bond[j]; }
+            FindRes f = d_find_pair_fast(D, nbr, host, FP_NEIGHBOR, pr.b, pr.r2, third);
+            int s; double d2;
+            if (pr.b < 0 && d_disc(pr, f.lower) > 0) {
+                s = -1; d2 = f.lower; pot = f.lowPot;
+                sub = (f.cs == 0) ? SDMD_SUB_CORECOLLI : SDMD_SUB_TBDCAPTR;
+            } else {
+                s = 1; d2 = f.upper; pot = f.upPot;
+                if (D.method_ding) sub = (f.cs == 1) ? SDMD_SUB_WELLBOUNC : SDMD_SUB_TBDESCAP;
+            }
+            time = d_time(pr, s, d2);
+            if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); time = SD_INF; }
+            if (time > 0) flag |= CF_VALID;
         }
     }
     sh.ctime[q] = time; sh.cpot[q] = pot; sh.csub[q] = (unsigned char)sub; sh.cflag[q] = (unsigned char)flag;
+}
+
+// warp-wide lexicographic (time, position) minimum with three REDUX steps; times are positive doubles, so
+// their bit patterns order like unsigned integers.  Result is uniform across the warp; pos = INT_MAX if empty.
+__device__ __forceinline__ void d_warp_firstmin(double &t, int &p) {
+    unsigned long long bits = (p == 0x7fffffff) ? 0xffffffffffffffffULL : (unsigned long long)__double_as_longlong(t);
+    unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+    unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    unsigned mp = __reduce_min_sync(0xffffffffu, (hi == mh && lo == ml) ? (unsigned)p : 0x7fffffffu);
+    p = (int)mp;
+    t = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
 }
 
 // ---- phase C: the ordered fold of atom `a` (warp 0) ----
@@ -1257,79 +1346,115 @@ __device__ inline void d_pc_fold(const DevP &D, PredShared &sh, int a) {
     int i = sh.atom[a];
     int base = a * PC_MAXC;
     int nc = sh.ncand[a];
-    // refresh eligibility against live slots (the co-predicted atom's slot may have just been written)
     i64 counter_i = D.ev_counter[i];
-    bool any = false;
-    double bt = SD_INF;
-    int bp = 0x7fffffff;
-    for (int p = lane; p < nc; p += 32) {
-        int q = base + p;
-        int kind = sh.ckind[q];
-        int f = sh.cflag[q];
-        if (kind != CK_PCC && kind != CK_THER) {
-            int j = sh.cj[q];
-            bool was = (f & CF_ELIGIBLE) != 0;
-            bool could = was || j == sh.atom[0] || j == sh.atom[1];
-            if (could) {
-                bool el = D.ev_partner[j] == i && D.ev_type[j] == d_kind_event(kind) && D.ev_pcounter[j] == counter_i;
-                if (kind == CK_HBFREE && !(f & CF_COUNTED)) el = false;
-                f = el ? (f | CF_ELIGIBLE) : (f & ~CF_ELIGIBLE);
-                sh.cflag[q] = (unsigned char)f;
-            }
-        }
-        if (f & CF_ELIGIBLE) any = true;
-        if (f & CF_VALID) {
-            double t = sh.ctime[q];
-            if (t < bt) { bt = t; bp = p; }   // p ascending within a lane: first wins on ties
-        }
-    }
-    any = __any_sync(0xffffffffu, any);
-    Slot cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
-    int win = -1, npair = 0;
-    if (!any) {
-        // JobAssign leaves partnerCounter untouched for partner-less events (TimePrediction.c:1148-1153), so when
-        // PCC / thermostat wins, the slot keeps the counter of the last pair candidate that was a running best:
-        // the first-min of the sections in front of PCC (bonds + cell scan)
-        double pt = SD_INF;
-        int pp = 0x7fffffff;
-        int npre = sh.off_pcc[a];
-        for (int p = lane; p < npre; p += 32) {
-            int q = base + p;
-            if (sh.cflag[q] & CF_VALID) {
-                double t = sh.ctime[q];
-                if (t < pt) { pt = t; pp = p; }
-            }
-        }
-        // parallel lexicographic (time, position) minimum
-        for (int o = 16; o; o >>= 1) {
-            double ot = __shfl_down_sync(0xffffffffu, bt, o);
-            int op = __shfl_down_sync(0xffffffffu, bp, o);
-            if (ot < bt || (ot == bt && op < bp)) { bt = ot; bp = op; }
-            ot = __shfl_down_sync(0xffffffffu, pt, o);
-            op = __shfl_down_sync(0xffffffffu, pp, o);
-            if (ot < pt || (ot == pt && op < pp)) { pt = ot; pp = op; }
-        }
-        int cnt = 0;
-        for (int p = lane; p < nc; p += 32) cnt += (sh.cflag[base + p] & CF_COUNTED) ? 1 : 0;
-        for (int o = 16; o; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
-        if (lane == 0) {
-            npair = cnt;
-            if (bp != 0x7fffffff && cur.time > bt) {
-                int q = base + bp;
-                int j = sh.cj[q];
-                if (j == 0 && pp != 0x7fffffff && cur.time > pt) cur.pcounter = D.ev_counter[sh.cj[base + pp]];
-                d_job_assign(D, cur, j, bt, sh.cpot[q], sh.csub[q], d_kind_event(sh.ckind[q]));
-                win = bp;
-            }
-        }
-    } else if (lane == 0) {
-        SlotSrc S = d_live_slots(D);
-        for (int p = 0; p < nc; p++) {
+    int other = sh.atom[a ^ 1];
+    int npre = sh.off_pcc[a];
+    // pass 1: refresh eligibility of entries whose partner is the co-predicted atom (its slot may just have been
+    // written), collect eligible positions, count pair evaluations
+    int cnt = 0;
+    for (int p0 = 0; p0 < nc; p0 += 32) {
+        int p = p0 + lane;
+        bool el = false;
+        if (p < nc) {
             int q = base + p;
             int f = sh.cflag[q];
             int j = sh.cj[q];
+            int kind = sh.ckind[q];
+            if (j == other && j != 0 && kind != CK_NONE) {
+                bool e2 = D.ev_partner[j] == i && D.ev_type[j] == d_kind_event(kind) && D.ev_pcounter[j] == counter_i;
+                f = e2 ? (f | CF_ELIGIBLE) : (f & ~CF_ELIGIBLE);
+                sh.cflag[q] = (unsigned char)f;
+            }
+            el = (f & CF_ELIGIBLE) != 0;
+            cnt += (f & CF_COUNTED) ? 1 : 0;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, el);
+        if (m) {   // append eligible positions in scan order
+            int n_before = sh.elig_n[a];
+            if (el) {
+                int slot = n_before + __popc(m & ((1u << lane) - 1));
+                if (slot < 8) sh.elig_pos[a][slot] = p;
+            }
+            __syncwarp();
+            if (lane == 0) sh.elig_n[a] = n_before + __popc(m);
+            __syncwarp();
+        }
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    int ne = sh.elig_n[a];
+    Slot cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
+    int win = -1, npair = cnt;
+    SlotSrc S = d_live_slots(D);
+    bool need_serial = ne > PC_MAXE;
+    if (!need_serial) {
+        int e0 = ne > 0 ? sh.elig_pos[a][0] : 0x7fffffff;
+        int e1 = ne > 1 ? sh.elig_pos[a][1] : 0x7fffffff;
+        int e2 = ne > 2 ? sh.elig_pos[a][2] : 0x7fffffff;
+        // segments between eligible entries: first minimum of own-side values; plus the first minimum of the
+        // pair sections in front of PCC (for the partnerCounter carry-over when a partner-less entry wins)
+        double t0 = SD_INF, t1 = SD_INF, t2 = SD_INF, t3 = SD_INF, tp = SD_INF;
+        int p0_ = 0x7fffffff, p1_ = 0x7fffffff, p2_ = 0x7fffffff, p3_ = 0x7fffffff, pp = 0x7fffffff;
+        for (int p = lane; p < nc; p += 32) {
+            int q = base + p;
+            if (!(sh.cflag[q] & CF_VALID)) continue;
+            if (p == e0 || p == e1 || p == e2) continue;
+            double t = sh.ctime[q];
+            if (p < e0) { if (t < t0) { t0 = t; p0_ = p; } }
+            else if (p < e1) { if (t < t1) { t1 = t; p1_ = p; } }
+            else if (p < e2) { if (t < t2) { t2 = t; p2_ = p; } }
+            else { if (t < t3) { t3 = t; p3_ = p; } }
+            if (p < npre && t < tp) { tp = t; pp = p; }
+        }
+        d_warp_firstmin(t0, p0_);
+        if (ne > 0) d_warp_firstmin(t1, p1_);
+        if (ne > 1) d_warp_firstmin(t2, p2_);
+        if (ne > 2) d_warp_firstmin(t3, p3_);
+        if (ne == 0) d_warp_firstmin(tp, pp);
+        if (lane == 0) {
+            double st[4] = {t0, t1, t2, t3};
+            int spos[4] = {p0_, p1_, p2_, p3_};
+            int epos[3] = {e0, e1, e2};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (k <= ne && spos[k] != 0x7fffffff) {
+                    int q = base + spos[k];
+                    if (d_job_assign(D, cur, sh.cj[q], st[k], sh.cpot[q], sh.csub[q], d_kind_event(sh.ckind[q]))) win = spos[k];
+                }
+                if (k < 3 && k < ne) {
+                    int p = epos[k];
+                    int q = base + p;
+                    int f = sh.cflag[q];
+                    int j = sh.cj[q];
+                    int ev = d_kind_event(sh.ckind[q]);
+                    if (cur.time > S.time[j]) {   // CheckDuplication copies the partner's slot
+                        cur.partner = j; cur.pot = S.pot[j]; cur.sub = S.sub[j]; cur.time = S.time[j]; cur.type = ev;
+                        cur.pcounter = D.ev_counter[j];
+                        win = p;
+                        if (f & CF_COUNTED) npair--;
+                    } else if ((f & CF_VALID) && d_job_assign(D, cur, j, sh.ctime[q], sh.cpot[q], sh.csub[q], ev)) win = p;
+                }
+            }
+            // partner-less winner: partnerCounter keeps the counter of the last pair entry that was a running best
+            if (win >= 0 && sh.cj[base + win] == 0) {
+                if (ne == 0) {
+                    if (pp != 0x7fffffff && tp < SD_INF) cur.pcounter = D.ev_counter[sh.cj[base + pp]];
+                } else need_serial = true;
+            }
+        }
+        need_serial = __shfl_sync(0xffffffffu, (int)need_serial, 0) != 0;
+    }
+    if (need_serial && lane == 0) {
+        // exact in-order replay (rare: many eligible entries, or eligible entries with a partner-less winner)
+        cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
+        win = -1;
+        npair = 0;
+        for (int p = 0; p < nc; p++) {
+            int q = base + p;
+            int f = sh.cflag[q];
+            if (sh.ckind[q] == CK_NONE) continue;
+            int j = sh.cj[q];
             int ev = d_kind_event(sh.ckind[q]);
-            if ((f & CF_ELIGIBLE) && cur.time > S.time[j]) {   // CheckDuplication copies the partner's slot
+            if ((f & CF_ELIGIBLE) && cur.time > S.time[j]) {
                 cur.partner = j; cur.pot = S.pot[j]; cur.sub = S.sub[j]; cur.time = S.time[j]; cur.type = ev;
                 cur.pcounter = D.ev_counter[j];
                 win = p;
@@ -1346,37 +1471,71 @@ __device__ inline void d_pc_fold(const DevP &D, PredShared &sh, int a) {
     }
 }
 
-// Predict(renewList) by the whole CTA.  sh.natoms / sh.atom[] / sh.gauss[] are set by the caller (thread 0)
-// before a __syncthreads; on return (after a final __syncthreads) the slots are stored.
+// evaluate the entries [lo, hi) of both atoms with the thread group [g0, g0 + gsize)
+template <bool COLL>
+__device__ __forceinline__ void d_pc_eval_group(const DevP &D, PredShared &sh, const Self &me0, const Self &me1, int lo0, int hi0,
+                                                int lo1, int hi1, int g0, int gsize) {
+    int gt = (int)threadIdx.x - g0;
+    if (gt < 0 || gt >= gsize) return;
+    int n0 = hi0 - lo0, n1 = hi1 - lo1;
+    for (int w = gt; w < n0 + n1; w += gsize) {
+        int a = (w < n0) ? 0 : 1;
+        int p = a ? lo1 + (w - n0) : lo0 + w;
+        if (COLL) d_pc_eval_coll(D, sh, a, p, a ? me1 : me0);
+        else d_pc_eval(D, sh, a, p, a ? me1 : me0);
+    }
+}
+
+// candidate layout for all listed atoms: warp w lays out atom w (call with all threads, no barrier inside)
+__device__ __forceinline__ void d_predict_gather(const DevP &D, PredShared &sh, int first_warp, int natoms) {
+    int w = (int)(threadIdx.x >> 5) - first_warp;
+    if (w >= 0 && w < natoms) {
+        if ((threadIdx.x & 31) == 0) sh.elig_n[w] = 0;
+        d_pc_gather_warp(D, sh, w);
+    }
+}
+
+// Predict(renewList) by the whole CTA.  sh.natoms / sh.atom[] / sh.gauss[] are set and the candidate arrays laid
+// out (d_predict_gather) before the barrier that precedes this call; returns with warp 0 holding the stored slots
+// (other warps run ahead to the caller's next barrier).
 __device__ inline void d_predict_cta(const DevP &D, PredShared &sh) {
     int tid = threadIdx.x;
     int na = sh.natoms;
-    // ResetTarget for every listed atom first (ToolFunctions.c:504-514)
-    if (tid < na) {
-        int i = sh.atom[tid];
-        D.ev_type[i] = SDMD_EV_INVD; D.ev_time[i] = SD_INF; D.ev_partner[i] = SDMD_INVALID;
-    }
-    __syncthreads();
-    for (int a = 0; a < na; a++) d_pc_gather(D, sh, a);
-    __syncthreads();
-    // evaluate every candidate of every atom in parallel
+    long long pc1 = d_clock_after(&sh.natoms);
     {
-        int n0 = (na > 0 && !sh.use_serial[0] && !D.is_cons[sh.atom[0]]) ? sh.ncand[0] : 0;
-        int n1 = (na > 1 && !sh.use_serial[1] && !D.is_cons[sh.atom[1]]) ? sh.ncand[1] : 0;
-        int total = n0 + n1;
-        if (total > 0) {
+        bool on0 = na > 0 && !sh.use_serial[0] && !D.is_cons[sh.atom[0]];
+        bool on1 = na > 1 && !sh.use_serial[1] && !D.is_cons[sh.atom[1]];
+        if (on0 || on1) {
             Self me0 = d_load_self(D, sh.atom[0]);
             Self me1 = (na > 1) ? d_load_self(D, sh.atom[1]) : me0;
-            for (int w = tid; w < total; w += blockDim.x) {
-                if (w < n0) d_pc_eval(D, sh, 0, w, me0);
-                else d_pc_eval(D, sh, 1, w - n0, me1);
+            int nthr = blockDim.x;
+            // kind-uniform thread groups keep warps from diverging across predictors
+            int gc = nthr - 96;   // cell-scan group
+            d_pc_eval_group<true>(D, sh, me0, me1, on0 ? sh.off_coll[0] : 0, on0 ? sh.off_pcc[0] : 0, on1 ? sh.off_coll[1] : 0,
+                                  on1 ? sh.off_pcc[1] : 0, 0, gc);
+            d_pc_eval_group<false>(D, sh, me0, me1, 0, on0 ? sh.n_bond[0] : 0, 0, on1 ? sh.n_bond[1] : 0, gc, 32);
+            // PCC, thermostat, bonded HB partner, HB neighbours
+            {
+                int m0 = on0 ? sh.off_pcc[0] : 0, m0e = on0 ? (sh.hb_free[0] ? sh.off_hb[0] : sh.off_hbne[0]) : 0;
+                int m1 = on1 ? sh.off_pcc[1] : 0, m1e = on1 ? (sh.hb_free[1] ? sh.off_hb[1] : sh.off_hbne[1]) : 0;
+                d_pc_eval_group<false>(D, sh, me0, me1, m0, m0e, m1, m1e, gc + 32, 16);
+                d_pc_eval_group<false>(D, sh, me0, me1, on0 ? sh.off_hbne[0] : 0, on0 ? sh.ncand[0] : 0, on1 ? sh.off_hbne[1] : 0,
+                                       on1 ? sh.ncand[1] : 0, gc + 48, 16);
+            }
+            // free-HB scan entries that passed the role filters
+            {
+                int f0 = (on0 && sh.hb_free[0]) ? sh.off_hb[0] : 0, f0e = (on0 && sh.hb_free[0]) ? sh.off_hbne[0] : 0;
+                int f1 = (on1 && sh.hb_free[1]) ? sh.off_hb[1] : 0, f1e = (on1 && sh.hb_free[1]) ? sh.off_hbne[1] : 0;
+                d_pc_eval_group<false>(D, sh, me0, me1, f0, f0e, f1, f1e, gc + 64, 32);
             }
         }
     }
     __syncthreads();
-    for (int a = 0; a < na; a++) {
-        int i = sh.atom[a];
-        if (tid < 32) {
+    long long pc2 = d_clock_after(&sh.natoms);
+    if (tid == 0) D.ctl->phase_cycles[4] += pc2 - pc1;
+    if (tid < 32) {
+        for (int a = 0; a < na; a++) {
+            int i = sh.atom[a];
             if (D.is_cons[i]) {
                 if (tid == 0) { D.ev_time[i] = SD_INF; }
             } else if (sh.use_serial[a]) {
@@ -1403,8 +1562,9 @@ __device__ inline void d_predict_cta(const DevP &D, PredShared &sh) {
                     }
                 }
             }
+            __syncwarp();
         }
-        __syncthreads();
+        if (tid == 0) D.ctl->phase_cycles[5] += clock64() - pc2;
     }
 }
 
