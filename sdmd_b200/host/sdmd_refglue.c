@@ -83,8 +83,24 @@ void sdmd_glue_gather_dynamic(struct sdmd_host_view *v) {
     }
 }
 
+/* HB_CONNECT / NEIGHBOR_CONNECT bits of connectionMap follow the HB lists (HBEvent flips them together,
+ * Events.c:297-329,350-382): clear what the previous lists set, set what the new lists say. */
+static void rebuild_hb_bits(const struct sdmd_host_view *v) {
+    int n = v->natom;
+    for (int i = 1; i <= n; i++) {
+        struct DynamicStr *d = atom[i].dynamic;
+        if (d->HB.bondConnection > 0) connectionMap[i][d->HB.bondConnection] &= ~HB_CONNECT;
+        for (int k = 1; k <= 4 && d->HBNeighbor.neighborPartner[k]; k++) connectionMap[i][d->HBNeighbor.neighborPartner[k]] &= ~NEIGHBOR_CONNECT;
+    }
+    for (int i = 1; i <= n; i++) {
+        if (v->hb_bond[i] > 0) connectionMap[i][v->hb_bond[i]] |= HB_CONNECT;
+        for (int k = 1; k <= 4 && v->hbn_partner[5 * i + k]; k++) connectionMap[i][v->hbn_partner[5 * i + k]] |= NEIGHBOR_CONNECT;
+    }
+}
+
 void sdmd_glue_scatter_dynamic(const struct sdmd_host_view *v) {
     int n = v->natom;
+    rebuild_hb_bits(v);
     for (int i = 1; i <= n; i++) {
         struct DynamicStr *d = atom[i].dynamic;
         struct PropertyStr *p = atom[i].property;
