@@ -279,6 +279,8 @@ int  sdmd_remd_nccl_init(sdmd_ctx *ctx, int nranks, int rank, const unsigned cha
 /* srand(seed) of sServer (Server.c:57-58): seeds the replicated glibc rand() stream every rank advances
  * identically during the exchange sweep */
 int  sdmd_remd_seed_server(sdmd_ctx *ctx, uint32_t seed);
+/* n outputs of glibc's rand() after srand(seed), from the library's restatement of the TYPE_3 generator */
+int  sdmd_host_glibc_rand(uint32_t seed, int64_t n, uint32_t *out);
 /* ReplicaExchange: all-gather (E, T, num) of every rank over NCCL, run the replicated sweep with the
  * shared server seed stream, return this rank's new (T, num). */
 int  sdmd_remd_exchange(sdmd_ctx *ctx, double epot, struct sdmd_remd_temp *T, uint32_t reserved);

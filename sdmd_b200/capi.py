@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "sdmd_cuda_cbt_update", "sdmd_cuda_assign_job", "sdmd_cuda_advance", "sdmd_cuda_add_time", "sdmd_cuda_hazard_check",
     "sdmd_cuda_cell_move", "sdmd_cuda_do_event", "sdmd_cuda_potential_energy", "sdmd_cuda_kinetic_energy",
     "sdmd_cuda_run", "sdmd_cuda_get_stats", "sdmd_cuda_set_temperature",
-    "sdmd_remd_rearrange", "sdmd_remd_nccl_unique_id", "sdmd_remd_nccl_init", "sdmd_remd_seed_server", "sdmd_remd_exchange",
+    "sdmd_remd_rearrange", "sdmd_remd_nccl_unique_id", "sdmd_remd_nccl_init", "sdmd_remd_seed_server", "sdmd_remd_exchange", "sdmd_host_glibc_rand",
     "sdmd_cuda_kernel_ms", "sdmd_cuda_kernel_stats", "sdmd_cuda_reset_kernel_stats", "sdmd_cuda_set_timing",
     "sdmd_cuda_launch_count", "sdmd_cuda_stream", "sdmd_cuda_phase_cycles",
 ]
@@ -115,6 +115,7 @@ def lib():
     L.sdmd_remd_nccl_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     L.sdmd_remd_seed_server.argtypes = [vp, C.c_uint32]
     L.sdmd_remd_exchange.argtypes = [vp, C.c_double, C.POINTER(CRemdTemp), C.c_uint32]
+    L.sdmd_host_glibc_rand.argtypes = [C.c_uint32, C.c_int64, C.POINTER(C.c_uint32)]
     L.sdmd_cuda_kernel_ms.argtypes = [vp, C.c_char_p]
     L.sdmd_cuda_kernel_ms.restype = C.c_double
     L.sdmd_cuda_kernel_stats.argtypes = [vp, C.c_char_p, dp, C.POINTER(C.c_int64)]
@@ -335,6 +336,13 @@ def host_register(arr: np.ndarray):
 
 def host_unregister(arr: np.ndarray):
     lib().sdmd_cuda_host_unregister(arr.ctypes.data)
+
+
+def glibc_rand(seed: int, n: int) -> np.ndarray:
+    """n outputs of glibc rand() after srand(seed) (the library's restatement; no process-global state touched)."""
+    out = np.zeros(n, dtype=np.uint32)
+    _check(lib().sdmd_host_glibc_rand(int(seed), int(n), out.ctypes.data_as(C.POINTER(C.c_uint32))), "glibc_rand")
+    return out
 
 
 def nccl_unique_id() -> bytes:

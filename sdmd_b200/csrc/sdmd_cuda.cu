@@ -1479,6 +1479,14 @@ struct GlibcRand {
 };
 static std::map<sdmd_ctx *, GlibcRand> g_server_rng;
 
+// the restated generator by itself (tests compare it with libc rand() for 10^6 draws)
+int sdmd_host_glibc_rand(uint32_t seed, int64_t n, uint32_t *out) {
+    GlibcRand r;
+    r.seed(seed);
+    for (int64_t k = 0; k < n; k++) out[k] = r.next();
+    return 0;
+}
+
 int sdmd_remd_seed_server(sdmd_ctx *c, uint32_t seed) {  // srand(seed) of sServer, Server.c:57-58
     g_server_rng[c].seed(seed);
     return 0;

@@ -161,3 +161,40 @@ def test_round_trip_properties_1m(capi):
     assert mutual.sum() > 1000
     assert np.array_equal(t[mutual].view(np.int64), t[p[mutual]].view(np.int64))
     assert np.all(t[1:] > 0)
+
+
+def test_remd_ensemble_gpu_matches_oracle(capi):
+    """Three ala10 replicas on one GPU coupled by the Server.c sweep: exchange log and final states equal the same
+    ensemble run on the CPU oracle."""
+    from oracle.oracle_py import Oracle
+    from sdmd_b200.remd import RemdEnsemble, reduced_temperature
+    pre, _, _ = load_case("ala10")
+    temps = [reduced_temperature(t) for t in (236.5, 250, 263.5)]
+
+    def build(kind):
+        reps, views = [], []
+        for k in range(3):
+            hv = pre.copy(); hv.timestep = 1e12
+            g = np.random.default_rng(50 + k).standard_normal(150000)
+            r = Oracle(hv) if kind == "cpu" else capi.Replica(hv, device=0)
+            r.rng_feed(g)
+            if kind == "cpu":
+                r.set_celllist(pre.extra["celllist"])
+            else:
+                r.upload_celllist(pre.extra["celllist"])
+            r.predict_all() if kind == "cpu" else (r.cell_build(), r.predict_all())
+            r.cbt_build()
+            reps.append(r); views.append(hv)
+        return RemdEnsemble(reps, temps, 3.0, 2024), views
+
+    cpu, cpu_views = build("cpu")
+    gpu, gpu_views = build("gpu")
+    for _ in range(10):
+        ec = cpu.step()
+        eg = gpu.step()
+        assert ec == eg   # CalPotenE bit-equal on every replica at every exchange
+    for k in range(3):
+        assert cpu.log[k] == gpu.log[k]
+        gpu.reps[k].download(gpu_views[k])
+        assert_fields_equal(gpu_views[k], cpu_views[k], STATE_FIELDS, what=f"replica {k}: ")
+    assert any(rec[2] != k + 1 for k in range(3) for rec in gpu.log[k])
