@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(128) k_predict_all_round(DevP D, SlotBuf src, 
     if (D.thermostat_on && !D.is_cons[i]) g = D.gauss[(g_base + D.ther_rank[i]) % D.g_cap];
     int np = 0;
     double m2 = SD_INF;
-    cur = d_predict_atom<true>(D, as_src(src), i, cur, g, round == 0 ? 0 : i, &np, round == 0 ? &m2 : nullptr);
+    if (round == 0) cur = d_predict_atom<true, true>(D, as_src(src), i, cur, g, 0, &np, &m2);
+    else cur = d_predict_atom<true, false>(D, as_src(src), i, cur, g, i, &np, nullptr);
     dst.time[i] = cur.time; dst.pot[i] = cur.pot; dst.partner[i] = cur.partner; dst.pcounter[i] = cur.pcounter;
     dst.type[i] = (uint8_t)cur.type; dst.sub[i] = (uint8_t)cur.sub;
     npair[i] = np;

@@ -109,6 +109,10 @@ struct Pair {
     double rx, ry, rz, r2, b, v2;
 };
 
+struct DevP;
+__device__ __forceinline__ FindRes d_find_pair_table_fast(const DevP &D, const sdmd_step_table *t, int mode, double direction,
+                                                          double dist2, int bond_a1, int bond_a2);
+
 // ---------------------------------------------------------------------------------------------------
 // AtomTypeChange, ToolFunctions.c:233-270
 __device__ __forceinline__ int d_type_change(int t, int direct) {
@@ -403,6 +407,119 @@ __device__ inline void d_collision_time_sorted(const DevP &D, const SlotSrc &S, 
     }
 }
 
+// CollisionTime for the full-system pass, round 0 (no duplicate source): the 27-cell scan is split into
+//   stage 1  a uniform loop over the cell-sorted tiles that applies the skip filters (TimePrediction.c:95-100),
+//            counts the pair evaluation (:105) and keeps only candidates inside the 0.9*cutoff sphere (:107);
+//   stage 2  the expensive step-table walk + quadratic root, run on the compacted survivors only.
+// Candidates are still folded in exact scan order, so the result is the sequential one; the split only removes
+// the per-candidate divergence that left ~9 of 32 lanes active in the fused loop.
+#define R0_MAXSURV 20
+#define R0_DUPFLAG 0x80   // survivor entry whose partner's slot points back: resolved in order in stage 2
+__device__ __forceinline__ void d_r0_flush(const DevP &D, const SlotSrc &S, Self &me, Slot &cur, const int *surv_p,
+                                           const unsigned char *surv_k, int ns, bool has_cm, int type_i, int hb_i, int h0, int h1,
+                                           int h2, int h3) {
+    for (int s = 0; s < ns; s++) {
+        int p = surv_p[s];
+        int k = surv_k[s] & 0x1f;
+        int j = D.sorted_atom[p];
+        int ncx, ncy, ncz;
+        d_neighbor_cell(D, me.cx, me.cy, me.cz, k, &ncx, &ncy, &ncz);
+        double shx = d_shift1(me.cx, ncx, D.cellnum[0], D.box[0]);   // PBCShift via the scanned neighbour cell
+        double shy = d_shift1(me.cy, ncy, D.cellnum[1], D.box[1]);
+        double shz = d_shift1(me.cz, ncz, D.cellnum[2], D.box[2]);
+        int cm = has_cm ? d_cm_flags(D, me.i, j) : 0;
+        if (surv_k[s] & R0_DUPFLAG) {
+            // CheckDuplication (TimePrediction.c:1101-1117) at this candidate's place in the scan
+            if (cur.time > S.time[j]) {
+                cur.partner = j; cur.pot = S.pot[j]; cur.sub = S.sub[j]; cur.time = S.time[j]; cur.type = SDMD_EV_COLI;
+                cur.pcounter = D.ev_counter[j];
+                continue;
+            }
+            // not copied: the candidate goes down the ordinary path (skip filters, evaluation count, distance test)
+            if ((cm & SDMD_BOND_CONNECT) || hb_i == j) continue;
+            if ((h0 == j) || (h0 != 0 && (h1 == j || (h1 != 0 && (h2 == j || (h2 != 0 && h3 == j)))))) continue;
+            me.npair++;
+        }
+        Pair pr = d_pair(me.x, me.y, me.z, me.vx, me.vy, me.vz, D.sx[p], D.sy[p], D.sz[p], D.svx[p], D.svy[p], D.svz[p], shx, shy, shz);
+        if (!(pr.r2 <= D.cut2)) continue;
+        FindRes f;
+        if (cm & SDMD_CONSTRAINT_CONNECT) {
+            f = d_find_pair(D, me.i, j, FP_CONSTRAINT, pr.b, pr.r2, 0, 0);
+        } else {
+            int idx = __ldg(&D.coll_index[type_i * SD_NT + D.stype[p]]);
+            if (idx < 0) { D.ctl->error = SDMD_ERR_TABLE; continue; }
+            f = d_find_pair_table_fast(D, &D.tables[idx], FP_COLLISION, pr.b, pr.r2, 0, 0);
+            if (f.lowPot == 0 && f.upPot == 0) continue;
+        }
+        int sgn, sub;
+        double d2, pot;
+        if (pr.b < 0 && d_disc(pr, f.lower) > 0) {
+            sgn = -1; d2 = f.lower; pot = f.lowPot;
+            sub = (f.cs == 0) ? SDMD_SUB_CORECOLLI : SDMD_SUB_TBDCAPTR;
+        } else {
+            sgn = 1; d2 = f.upper; pot = f.upPot;
+            sub = SDMD_SUB_INVALID;
+            if (D.method_ding) {
+                if (cm & SDMD_CONSTRAINT_CONNECT) sub = (f.cs == 1) ? SDMD_SUB_WELLBOUNC : SDMD_SUB_TBDESCAP;
+                else {
+                    if (f.cs == 1) continue;
+                    sub = SDMD_SUB_TBDESCAP;
+                }
+            }
+        }
+        double t = d_time(pr, sgn, d2);
+        if (t < 0) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+        d_job_assign(D, cur, j, t, pot, sub, SDMD_EV_COLI);
+    }
+}
+
+template <bool DUP>
+__device__ inline void d_collision_time_2stage(const DevP &D, const SlotSrc &S, Self &me, Slot &cur, int dup_limit) {
+    int surv_p[R0_MAXSURV];
+    unsigned char surv_k[R0_MAXSURV];
+    int ns = 0;
+    int i = me.i;
+    bool has_cm = D.cm_off[i + 1] > D.cm_off[i];
+    int hb_i = D.hb_bond[i];
+    int h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+    if (D.hydrogen_bond) { h0 = D.hbn_partner[5 * i + 1]; h1 = D.hbn_partner[5 * i + 2]; h2 = D.hbn_partner[5 * i + 3]; h3 = D.hbn_partner[5 * i + 4]; }
+    int type_i = D.type[i];
+    int npair = 0;
+    for (int k = 0; k < 27; k++) {
+        int ncx, ncy, ncz;
+        int cell = d_neighbor_cell(D, me.cx, me.cy, me.cz, k, &ncx, &ncy, &ncz);
+        double shx = d_shift1(me.cx, ncx, D.cellnum[0], D.box[0]);
+        double shy = d_shift1(me.cy, ncy, D.cellnum[1], D.box[1]);
+        double shz = d_shift1(me.cz, ncz, D.cellnum[2], D.box[2]);
+        int p1 = D.cell_start[cell + 1];
+        for (int p = D.cell_start[cell]; p < p1; p++) {
+            int j = D.sorted_atom[p];
+            if (j == i) continue;
+            bool keep;
+            unsigned char tag = (unsigned char)k;
+            if (DUP && j < dup_limit && S.partner[j] == i && S.type[j] == SDMD_EV_COLI && S.pcounter[j] == me.counter) {
+                keep = true;            // outcome depends on the running best: decide in order, in stage 2
+                tag |= R0_DUPFLAG;
+            } else {
+                if (has_cm && (d_cm_flags(D, i, j) & SDMD_BOND_CONNECT)) continue;
+                if (hb_i == j) continue;
+                if ((h0 == j) || (h0 != 0 && (h1 == j || (h1 != 0 && (h2 == j || (h2 != 0 && h3 == j)))))) continue;
+                npair++;
+                double tx = D.sx[p] + shx, ty = D.sy[p] + shy, tz = D.sz[p] + shz;
+                double rx = me.x - tx, ry = me.y - ty, rz = me.z - tz;
+                double r2 = rx * rx + ry * ry + rz * rz;
+                keep = r2 <= D.cut2;
+            }
+            if (keep) {
+                if (ns == R0_MAXSURV) { d_r0_flush(D, S, me, cur, surv_p, surv_k, ns, has_cm, type_i, hb_i, h0, h1, h2, h3); ns = 0; }
+                surv_p[ns] = p; surv_k[ns] = tag; ns++;
+            }
+        }
+    }
+    d_r0_flush(D, S, me, cur, surv_p, surv_k, ns, has_cm, type_i, hb_i, h0, h1, h2, h3);
+    me.npair += npair;
+}
+
 // BondTime, TimePrediction.c:186-295
 __device__ inline void d_bond_time(const DevP &D, const SlotSrc &S, Self &me, Slot &cur, int dup_limit) {
     int i = me.i;
@@ -586,13 +703,14 @@ __device__ __forceinline__ Slot d_reset_slot(double pot, int sub, i64 pcounter) 
 
 // one atom of Predict, SGThread.c:162-208, executed by a single thread in reference order.
 // SORTED selects the cell-sorted tiles for the 27-cell scan (fresh link list only).
-template <bool SORTED>
+template <bool SORTED, bool R0 = false>
 __device__ inline Slot d_predict_atom(const DevP &D, const SlotSrc &S, int i, Slot cur, double gauss, int dup_limit, int *npair,
                                       double *second = nullptr) {
     if (D.is_cons[i]) { cur.time = SD_INF; return cur; }
     Self me = d_load_self(D, i);
     if (!D.gel_mode) d_bond_time(D, S, me, cur, dup_limit);
-    if (SORTED) d_collision_time_sorted(D, S, me, cur, dup_limit);
+    if (R0) d_collision_time_2stage<false>(D, S, me, cur, 0);
+    else if (SORTED) d_collision_time_2stage<true>(D, S, me, cur, dup_limit);
     else d_collision_time(D, S, me, cur, dup_limit);
     d_pcc_time(D, me, cur);
     if (D.thermostat_on) d_thermostat_time(D, cur, gauss);
