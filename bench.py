@@ -189,7 +189,7 @@ def cuda_pass(args, dist):
     launches = rep.launch_count()
     pairs = rep.stats()["pair_predictions"] - pairs0
     total_pairs = dist.sum(float(pairs))
-    kst = {k: rep.kernel_stats(k) for k in ("predict_all", "predict_all_fixup", "cell_build", "cbt_build", "predict_all_rounds")}
+    kst = {k: rep.kernel_stats(k) for k in ("predict_all", "predict_all_fixup", "cell_build", "cbt_build", "predict_all_rounds", "predict_all_requeued")}
 
     # -------- end to end through the C-ABI with HOST buffers (`e2e`) --------
     host = [np.ascontiguousarray(a.copy()) for a in (hv.x, hv.y, hv.z, hv.vx, hv.vy, hv.vz)]
@@ -257,7 +257,8 @@ def cuda_pass(args, dist):
         "e2e": {"value": e2e_pairs / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / args.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,
-        "kernels_ms_per_step": {k: v[0] / args.steps for k, v in kst.items() if k != "predict_all_rounds"},
+        "kernels_ms_per_step": {k: v[0] / args.steps for k, v in kst.items() if not k.startswith("predict_all_r")},
+        "predict_all_requeued_atoms": kst["predict_all_requeued"][0] / max(kst["predict_all_requeued"][1], 1),
         "predict_all_rounds": kst["predict_all_rounds"][0] / max(kst["predict_all_rounds"][1], 1),
         "extra": extra,
     }

@@ -43,9 +43,9 @@ struct sdmd_ctx {
     int *b_partner = nullptr, *c_partner = nullptr;
     i64 *b_pcounter = nullptr, *c_pcounter = nullptr;
     uint8_t *b_type = nullptr, *b_sub = nullptr, *c_type = nullptr, *c_sub = nullptr;
-    uint8_t *copyflag = nullptr;
     int *npair = nullptr, *pcount = nullptr, *pwho = nullptr, *queue_a = nullptr, *queue_b = nullptr, *nqueue = nullptr;
-    double *second = nullptr;
+    double *second = nullptr, *bp_time = nullptr;
+    int *bp_j = nullptr;
     int *cell_of = nullptr, *cell_count = nullptr, *cell_cursor = nullptr, *scan_tmp = nullptr;
     int *d_cell_start = nullptr, *d_sorted_atom = nullptr;
     double *d_sx = nullptr, *d_sy = nullptr, *d_sz = nullptr, *d_svx = nullptr, *d_svy = nullptr, *d_svz = nullptr;
@@ -274,38 +274,36 @@ __device__ __forceinline__ SlotSrc as_src(const SlotBuf &b) {
 //             a changed slot queues the higher-index atoms it pointed / points at.
 // The stale fields of a slot (potential / subEventType / partnerCounter survive ResetTarget) always start from the
 // live arrays, which this pass never writes until the final commit.
-__global__ void __launch_bounds__(128) k_predict_all_round(DevP D, SlotBuf src, SlotBuf dst, const int *queue, int nqueue, int round,
-                                                           int *npair, double *second, i64 g_base) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    int i;
-    if (round == 0) {
-        if (p >= D.n) return;
-        i = D.sorted_atom[p];
-    } else {
-        if (p >= nqueue) return;
-        i = queue[p];
-    }
-    Slot cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
-    double g = 0;
-    if (D.thermostat_on && !D.is_cons[i]) g = D.gauss[(g_base + D.ther_rank[i]) % D.g_cap];
-    int np = 0;
-    double m2 = SD_INF;
-    if (round == 0) cur = d_predict_atom<true, true>(D, as_src(src), i, cur, g, 0, &np, &m2);
-    else cur = d_predict_atom<true, false>(D, as_src(src), i, cur, g, i, &np, nullptr);
-    dst.time[i] = cur.time; dst.pot[i] = cur.pot; dst.partner[i] = cur.partner; dst.pcounter[i] = cur.pcounter;
-    dst.type[i] = (uint8_t)cur.type; dst.sub[i] = (uint8_t)cur.sub;
-    npair[i] = np;
-    if (round == 0) second[i] = m2;
-}
-
-// who points at whom after round 0: count and remember one lower-index pointer per atom
-__global__ void k_predict_all_point(DevP D, SlotBuf b, int *pcount, int *pwho) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (j > D.n) return;
-    int k = b.partner[j];
-    if (k > j) {
-        atomicAdd(&pcount[k], 1);
-        pwho[k] = j;
+__global__ void __launch_bounds__(128) k_predict_all_round(DevP D, SlotBuf src, SlotBuf dst, const int *queue, const int *nqueue_ptr,
+                                                           int round, int *npair, double *second, double *bp_time, int *bp_j,
+                                                           int *pcount, int *pwho, unsigned long long *pair_sum, i64 g_base) {
+    int total = (round == 0) ? D.n : *nqueue_ptr;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+        int i = (round == 0) ? D.sorted_atom[p] : queue[p];
+        Slot cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
+        double g = 0;
+        if (D.thermostat_on && !D.is_cons[i]) g = D.gauss[(g_base + D.ther_rank[i]) % D.g_cap];
+        int np = 0;
+        double m2 = SD_INF;
+        PairBest pb;
+        if (round == 0) cur = d_predict_atom<true, true>(D, as_src(src), i, cur, g, 0, &np, &m2, &pb);
+        else cur = d_predict_atom<true, false>(D, as_src(src), i, cur, g, i, &np, nullptr);
+        dst.time[i] = cur.time; dst.pot[i] = cur.pot; dst.partner[i] = cur.partner; dst.pcounter[i] = cur.pcounter;
+        dst.type[i] = (uint8_t)cur.type; dst.sub[i] = (uint8_t)cur.sub;
+        if (round == 0) {
+            npair[i] = np;
+            // a partner-less winner is settled against its best PAIR candidate instead (see k_predict_all_resolve)
+            bool pairwin = cur.partner > 0;
+            second[i] = pairwin ? m2 : pb.sp_time;
+            bp_time[i] = pb.bp_time;
+            bp_j[i] = pb.bp_j;
+            // who points at whom: count and remember one lower-index pointer per atom
+            if (cur.partner > i) { atomicAdd(&pcount[cur.partner], 1); pwho[cur.partner] = i; }
+        } else {
+            int old = npair[i];
+            npair[i] = np;
+            if (np != old) atomicAdd(pair_sum, (unsigned long long)(long long)(np - old));
+        }
     }
 }
 
@@ -325,14 +323,13 @@ __device__ __forceinline__ int d_scan_slot(const DevP &D, int i, int a) {
 }
 
 // settle atoms with a single lower-index pointer, queue the ambiguous ones
-__global__ void k_predict_all_resolve(DevP D, SlotBuf b, const int *pcount, const int *pwho, const double *second, int *queue,
-                                      int *nqueue, uint8_t *copyflag) {
+__global__ void k_predict_all_resolve(DevP D, SlotBuf b, const int *pcount, const int *pwho, const double *second, const double *bp_time,
+                                      const int *bp_j, int *queue, int *nqueue, int *npair, unsigned long long *pair_sum) {
     int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (i > D.n) return;
-    int cnt = pcount[i];
-    copyflag[i] = 0;
-    if (cnt == 0) return;
-    bool ambiguous = true;
+    int copy = 0;
+    int cnt = (i <= D.n) ? pcount[i] : 0;
+    bool ambiguous = cnt > 0;
+    if (cnt > 0) {
     if (cnt == 1) {
         int j = pwho[i];
         double tj = b.time[j];
@@ -340,7 +337,26 @@ __global__ void k_predict_all_resolve(DevP D, SlotBuf b, const int *pcount, cons
         if (b.type[j] == SDMD_EV_COLI && b.pcounter[j] == D.ev_counter[i]) {
             double m1 = b.time[i];
             bool j_is_best = (b.partner[i] == j && b.type[i] == SDMD_EV_COLI);
-            if (!j_is_best) {
+            if (b.partner[i] <= 0) {
+                // partner-less winner W (PCC / thermostat, visited after the whole cell scan): it still wins iff t_j > m1.
+                // Its partnerCounter is the counter of the last pair candidate that was a running best = the best pair
+                // candidate q of the sections in front of PCC.
+                int q = bp_j[i];
+                if (tj > m1 && q > 0) {
+                    if (q != j) {
+                        // q visited before j and t_j > t_q: the copy cannot fire, nothing changes
+                        if (tj > bp_time[i]) {
+                            int kq = d_scan_slot(D, i, q), kj = d_scan_slot(D, i, j);
+                            if (kq < kj || (kq == kj && q > j)) ambiguous = false;
+                        }
+                    } else if (tj < second[i]) {
+                        // j is that best pair candidate: the copy fires at j (T_before >= second-best pair > t_j), the
+                        // record still carries counter(j), W still wins; only the evaluation of j is saved
+                        copy = 2;
+                        ambiguous = false;
+                    }
+                }
+            } else if (!j_is_best) {
                 // my own winner q must be a collision candidate visited BEFORE j: then the running best at j is
                 // already <= m1 < t_j, CheckDuplication cannot fire and both slot and evaluation count stand
                 int q = b.partner[i];
@@ -349,48 +365,47 @@ __global__ void k_predict_all_resolve(DevP D, SlotBuf b, const int *pcount, cons
                     if (kq < kj || (kq == kj && q > j)) ambiguous = false;   // inside a cell: descending atom id
                 }
             }
-            else if (tj < second[i]) { copyflag[i] = 1; ambiguous = false; }
+            else if (tj < second[i]) { copy = 1; ambiguous = false; }
         } else if (b.pcounter[j] != D.ev_counter[i]) ambiguous = false;  // CheckDuplication can never fire
     }
-    if (ambiguous) queue[atomicAdd(nqueue, 1)] = i;
-}
-
-// apply the copies (second kernel: every source slot j is an atom whose own slot the resolve step left alone)
-__global__ void k_predict_all_copy(DevP D, SlotBuf b, const int *pwho, const uint8_t *copyflag, int *npair) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (i > D.n || !copyflag[i]) return;
-    int j = pwho[i];
-    b.partner[i] = j; b.pot[i] = b.pot[j]; b.sub[i] = b.sub[j]; b.time[i] = b.time[j]; b.type[i] = SDMD_EV_COLI;
-    b.pcounter[i] = D.ev_counter[j];
-    npair[i] -= 1;   // the duplicate is copied, not evaluated (TimePrediction.c:87-90)
+    }
+    unsigned long long v = 0;
+    if (i <= D.n) {
+        int np = npair[i];
+        if (copy) {
+            // the duplicate is copied, not evaluated (TimePrediction.c:87-90).  The source slot j is never itself a
+            // copy target (its own winner is i > j), so applying the copy here is race free.
+            np -= 1;
+            npair[i] = np;
+            if (copy == 1) {
+                int j = pwho[i];
+                b.partner[i] = j; b.pot[i] = b.pot[j]; b.sub[i] = b.sub[j]; b.time[i] = b.time[j]; b.type[i] = SDMD_EV_COLI;
+                b.pcounter[i] = D.ev_counter[j];
+            }
+        }
+        if (ambiguous) queue[atomicAdd(nqueue, 1)] = i;
+        v = (unsigned long long)np;
+    }
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(pair_sum, v);
 }
 
 // commit round r: move re-evaluated slots into the current buffer, queue dependants of changed slots
-__global__ void k_predict_all_commit(DevP D, SlotBuf cur, SlotBuf nxt, const int *queue, int nqueue, int *queue_next, int *nqueue_next) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= nqueue) return;
+__global__ void k_predict_all_commit(DevP D, SlotBuf cur, SlotBuf nxt, const int *queue, const int *nqueue_ptr, int *queue_next,
+                                     int *nqueue_next) {
+    int nqueue = *nqueue_ptr;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nqueue; p += gridDim.x * blockDim.x) {
     int i = queue[p];
     bool same = __double_as_longlong(cur.time[i]) == __double_as_longlong(nxt.time[i]) &&
                 __double_as_longlong(cur.pot[i]) == __double_as_longlong(nxt.pot[i]) && cur.partner[i] == nxt.partner[i] &&
                 cur.pcounter[i] == nxt.pcounter[i] && cur.type[i] == nxt.type[i] && cur.sub[i] == nxt.sub[i];
-    if (same) return;
+    if (same) continue;
     int oldp = cur.partner[i], newp = nxt.partner[i];
     cur.time[i] = nxt.time[i]; cur.pot[i] = nxt.pot[i]; cur.partner[i] = newp; cur.pcounter[i] = nxt.pcounter[i];
     cur.type[i] = nxt.type[i]; cur.sub[i] = nxt.sub[i];
     if (oldp > i) queue_next[atomicAdd(nqueue_next, 1)] = oldp;
     if (newp > i && newp != oldp) queue_next[atomicAdd(nqueue_next, 1)] = newp;
-}
-
-__global__ void k_predict_all_final(DevP D, SlotBuf b, const int *npair, unsigned long long *sum) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    unsigned long long v = 0;
-    if (i <= D.n) {
-        D.ev_time[i] = b.time[i]; D.ev_pot[i] = b.pot[i]; D.ev_partner[i] = b.partner[i]; D.ev_pcounter[i] = b.pcounter[i];
-        D.ev_type[i] = b.type[i]; D.ev_sub[i] = b.sub[i];
-        v = (unsigned long long)npair[i];
     }
-    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(sum, v);
 }
 
 // ===================================================================================================
@@ -410,6 +425,39 @@ __global__ void k_cbt_level(DevP D, int lo, int hi) {
     if (f >= hi) return;
     int l = D.cbt_node[2 * f], r = D.cbt_node[2 * f + 1];
     D.cbt_node[f] = (D.ev_time[l] < D.ev_time[r]) ? l : r;
+}
+
+// bottom-up tournament inside one subtree per block: root f0 = 2^L + blockIdx.x, internal nodes of relative depth
+// dmax..0, one __syncthreads per level (a block's writes are visible to its own threads after the barrier)
+__global__ void __launch_bounds__(256) k_cbt_subtrees(DevP D, int L, int dmax) {
+    int f0 = (1 << L) + blockIdx.x;
+    if (f0 >= D.n) return;
+    for (int d = dmax; d >= 0; d--) {
+        int base = f0 << d;
+        int cnt = 1 << d;
+        for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+            int f = base + t;
+            if (f < D.n) {
+                int l = D.cbt_node[2 * f], r = D.cbt_node[2 * f + 1];
+                D.cbt_node[f] = (D.ev_time[l] < D.ev_time[r]) ? l : r;
+            }
+        }
+        __syncthreads();
+    }
+}
+// the levels above the subtree roots (nodes 1 .. 2^L - 1), one block
+__global__ void __launch_bounds__(256) k_cbt_top(DevP D, int L) {
+    for (int lv = L - 1; lv >= 0; lv--) {
+        int base = 1 << lv;
+        for (int t = threadIdx.x; t < base; t += blockDim.x) {
+            int f = base + t;
+            if (f < D.n) {
+                int l = D.cbt_node[2 * f], r = D.cbt_node[2 * f + 1];
+                D.cbt_node[f] = (D.ev_time[l] < D.ev_time[r]) ? l : r;
+            }
+        }
+        __syncthreads();
+    }
 }
 
 // UpdateData + TimeForward fused, ToolFunctions.c:23-36: 56 B read + 32 B written per atom
@@ -809,8 +857,8 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     TRY(dalloc(c, &c->b_pcounter, n1)); TRY(dalloc(c, &c->b_type, n1)); TRY(dalloc(c, &c->b_sub, n1));
     TRY(dalloc(c, &c->c_time, n1)); TRY(dalloc(c, &c->c_pot, n1)); TRY(dalloc(c, &c->c_partner, n1));
     TRY(dalloc(c, &c->c_pcounter, n1)); TRY(dalloc(c, &c->c_type, n1)); TRY(dalloc(c, &c->c_sub, n1));
-    TRY(dalloc(c, &c->copyflag, n1)); TRY(dalloc(c, &c->npair, n1)); TRY(dalloc(c, &c->pcount, n1)); TRY(dalloc(c, &c->pwho, n1));
-    TRY(dalloc(c, &c->queue_a, 2 * n1 + 2)); TRY(dalloc(c, &c->queue_b, 2 * n1 + 2)); TRY(dalloc(c, &c->nqueue, 4)); TRY(dalloc(c, &c->second, n1));
+    TRY(dalloc(c, &c->npair, n1)); TRY(dalloc(c, &c->pcount, n1)); TRY(dalloc(c, &c->pwho, n1));
+    TRY(dalloc(c, &c->queue_a, 2 * n1 + 2)); TRY(dalloc(c, &c->queue_b, 2 * n1 + 2)); TRY(dalloc(c, &c->nqueue, 32)); TRY(dalloc(c, &c->second, n1)); TRY(dalloc(c, &c->bp_time, n1)); TRY(dalloc(c, &c->bp_j, n1));
     TRY(dalloc(c, &c->cell_of, n1)); TRY(dalloc(c, &c->cell_count, (size_t)P.ncell + 1));
     TRY(dalloc(c, &c->cell_cursor, (size_t)P.ncell + 1));
     TRY(dalloc(c, &c->scan_tmp, (size_t)P.ncell / SCAN_ITEMS + 4));
@@ -1103,48 +1151,58 @@ int sdmd_cuda_predict_all(sdmd_ctx *c) {
     SlotBuf B = {c->b_time, c->b_pot, c->b_partner, c->b_pcounter, c->b_type, c->b_sub};
     SlotBuf C = {c->c_time, c->c_pot, c->c_partner, c->c_pcounter, c->c_type, c->c_sub};
     int grid = grid_for(n, 128), grid1 = grid_for(n, 256);
+    const int NQ = 16;   // queue-length slots, one per relaxation round
+    CK(cudaMemsetAsync(c->pcount, 0, ((size_t)n + 1) * sizeof(int), c->stream));
+    CK(cudaMemsetAsync(c->nqueue, 0, NQ * sizeof(int), c->stream));
+    CK(cudaMemsetAsync(c->d_sum, 0, sizeof(unsigned long long), c->stream));
     {
         Timer t(c, "predict_all");
-        k_predict_all_round<<<grid, 128, 0, c->stream>>>(c->P, B, B, nullptr, 0, 0, c->npair, c->second, g_base);
+        k_predict_all_round<<<grid, 128, 0, c->stream>>>(c->P, B, B, nullptr, nullptr, 0, c->npair, c->second, c->bp_time, c->bp_j,
+                                                         c->pcount, c->pwho, c->d_sum, g_base);
         c->launches++;
     }
     int rounds = 0, requeued = 0;
-    int hq[2] = {0, 0};
+    struct { int nq[16]; unsigned long long sum; } h;
     {
         Timer t2(c, "predict_all_fixup");
-        CK(cudaMemsetAsync(c->pcount, 0, ((size_t)n + 1) * sizeof(int), c->stream));
-        CK(cudaMemsetAsync(c->nqueue, 0, 2 * sizeof(int), c->stream));
-        k_predict_all_point<<<grid1, 256, 0, c->stream>>>(c->P, B, c->pcount, c->pwho);
-        k_predict_all_resolve<<<grid1, 256, 0, c->stream>>>(c->P, B, c->pcount, c->pwho, c->second, c->queue_a, c->nqueue, c->copyflag);
-        k_predict_all_copy<<<grid1, 256, 0, c->stream>>>(c->P, B, c->pwho, c->copyflag, c->npair);
-        c->launches += 3;
-        CK(cudaMemcpyAsync(hq, c->nqueue, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        int *qa = c->queue_a, *qb = c->queue_b;
-        int nq = hq[0];
-        requeued = nq;
-        while (nq > 0) {
-            rounds++;
-            if (rounds > n + 2) return set_err(SDMD_ERR_STATE, "predict_all did not converge");
-            CK(cudaMemsetAsync(c->nqueue + 1, 0, sizeof(int), c->stream));
-            k_predict_all_round<<<grid_for(nq, 128), 128, 0, c->stream>>>(c->P, B, C, qa, nq, rounds, c->npair, c->second, g_base);
-            k_predict_all_commit<<<grid_for(nq, 256), 256, 0, c->stream>>>(c->P, B, C, qa, nq, qb, c->nqueue + 1);
-            c->launches += 2;
-            CK(cudaMemcpyAsync(hq, c->nqueue + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaStreamSynchronize(c->stream));
-            nq = hq[0];
-            if (nq > 2 * n) return set_err(SDMD_ERR_STATE, "predict_all queue overflow");
-            std::swap(qa, qb);
-        }
-        CK(cudaMemsetAsync(c->d_sum, 0, sizeof(unsigned long long), c->stream));
-        k_predict_all_final<<<grid1, 256, 0, c->stream>>>(c->P, B, c->npair, c->d_sum);
+        k_predict_all_resolve<<<grid1, 256, 0, c->stream>>>(c->P, B, c->pcount, c->pwho, c->second, c->bp_time, c->bp_j, c->queue_a,
+                                                            c->nqueue, c->npair, c->d_sum);
         c->launches++;
+        int *qa = c->queue_a, *qb = c->queue_b;
+        int qgrid = 148 * 4;
+        int slot = 0;
+        for (;;) {
+            // a few relaxation rounds back to back (queue lengths stay on the device), then one look at the result
+            int burst = (slot == 0) ? 2 : 3;
+            for (int r = 0; r < burst && slot + 1 < NQ; r++, slot++) {
+                k_predict_all_round<<<qgrid, 128, 0, c->stream>>>(c->P, B, C, qa, c->nqueue + slot, slot + 1, c->npair, c->second, c->bp_time,
+                                                                  c->bp_j, c->pcount, c->pwho, c->d_sum, g_base);
+                k_predict_all_commit<<<qgrid, 256, 0, c->stream>>>(c->P, B, C, qa, c->nqueue + slot, qb, c->nqueue + slot + 1);
+                c->launches += 2;
+                std::swap(qa, qb);
+            }
+            CK(cudaMemcpyAsync(h.nq, c->nqueue, NQ * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(&h.sum, c->d_sum, sizeof(h.sum), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            requeued = h.nq[0];
+            for (int k = 0; k <= slot; k++)
+                if (h.nq[k] > 2 * n) return set_err(SDMD_ERR_STATE, "predict_all queue overflow");
+            rounds = 0;
+            for (int k = 0; k < slot; k++) rounds += h.nq[k] > 0;
+            if (h.nq[slot] == 0) break;
+            if (slot + 1 >= NQ) {   // very long dependency chain: restart the slot counter, keep the last queue
+                int last = h.nq[slot];
+                CK(cudaMemsetAsync(c->nqueue, 0, NQ * sizeof(int), c->stream));
+                CK(cudaMemcpyAsync(c->nqueue, &last, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+                slot = 0;
+            }
+        }
     }
-    unsigned long long sum = 0;
-    CK(cudaMemcpyAsync(&sum, c->d_sum, sizeof(sum), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    // the relaxed buffer becomes the live slot arrays (pointer swap, no copy)
+    std::swap(c->P.ev_time, c->b_time); std::swap(c->P.ev_pot, c->b_pot); std::swap(c->P.ev_partner, c->b_partner);
+    std::swap(c->P.ev_pcounter, c->b_pcounter); std::swap(c->P.ev_type, c->b_type); std::swap(c->P.ev_sub, c->b_sub);
     c->h_ctl->g_pos = g_base + need;
-    c->h_ctl->pair_predictions += (i64)sum;
+    c->h_ctl->pair_predictions += (i64)h.sum;
     CK(cudaMemcpyAsync(&c->d_ctl->g_pos, &c->h_ctl->g_pos, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(&c->d_ctl->pair_predictions, &c->h_ctl->pair_predictions, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
     c->kstat["predict_all_rounds"].ms += rounds;
@@ -1176,14 +1234,16 @@ int sdmd_cuda_cbt_build(sdmd_ctx *c) {
     int n = c->n;
     k_cbt_leaves<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_leaf_atom);
     c->launches++;
-    // internal nodes 1..n-1, deepest level first
-    int top = 1;
-    while (top * 2 <= n - 1) top *= 2;
-    for (int lo = top; lo >= 1; lo /= 2) {
-        int hi = lo * 2;
-        if (hi > n) hi = n;
-        if (hi > lo) {
-            k_cbt_level<<<grid_for(hi - lo, 256), 256, 0, c->stream>>>(c->P, lo, hi);
+    if (n > 1) {
+        // internal nodes 1..n-1: subtrees of height <= 11 bottom-up in one launch, then the few levels above them
+        int depth = 0;
+        while ((2 << depth) <= n - 1) depth++;          // level of the deepest internal node
+        int L = depth > 10 ? depth - 10 : 0;
+        int nsub = 1 << L;
+        k_cbt_subtrees<<<nsub, 256, 0, c->stream>>>(c->P, L, depth - L);
+        c->launches++;
+        if (L > 0) {
+            k_cbt_top<<<1, 256, 0, c->stream>>>(c->P, L);
             c->launches++;
         }
     }

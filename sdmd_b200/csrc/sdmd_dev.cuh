@@ -46,6 +46,8 @@ struct SlotSrc {
 struct Slot {
     double time, pot;
     double m2;      // value of the best candidate that did NOT win (used by the full-system pass)
+    double bp_time, sp_time;   // best / second-best PAIR candidate seen so far (full-system pass)
+    int bp_j;
     i64 pcounter;
     int partner, type, sub;
 };
@@ -303,6 +305,10 @@ __device__ __forceinline__ bool d_check_dup(const DevP &D, const SlotSrc &S, Slo
 // JobAssign, TimePrediction.c:1140-1158 (j == 0: no partner)
 __device__ __forceinline__ bool d_job_assign(const DevP &D, Slot &cur, int j, double time, double pot, int sub, int type) {
     if (time > 0 && !(cur.time > time) && time < cur.m2) cur.m2 = time;
+    if (time > 0 && j != 0) {
+        if (time < cur.bp_time) { cur.sp_time = cur.bp_time; cur.bp_time = time; cur.bp_j = j; }
+        else if (time < cur.sp_time) cur.sp_time = time;
+    }
     if (time > 0 && cur.time > time) {
         cur.m2 = cur.time;
         cur.pot = pot;
@@ -696,22 +702,24 @@ __device__ __forceinline__ Self d_load_self(const DevP &D, int i) {
 // ResetTarget (ToolFunctions.c:504-514) leaves potential / subEventType / partnerCounter untouched
 __device__ __forceinline__ Slot d_reset_slot(double pot, int sub, i64 pcounter) {
     Slot s;
-    s.time = SD_INF; s.type = SDMD_EV_INVD; s.partner = SDMD_INVALID; s.m2 = SD_INF;
+    s.time = SD_INF; s.type = SDMD_EV_INVD; s.partner = SDMD_INVALID; s.m2 = SD_INF; s.bp_time = SD_INF; s.sp_time = SD_INF; s.bp_j = 0;
     s.pot = pot; s.sub = sub; s.pcounter = pcounter;
     return s;
 }
 
 // one atom of Predict, SGThread.c:162-208, executed by a single thread in reference order.
 // SORTED selects the cell-sorted tiles for the 27-cell scan (fresh link list only).
+struct PairBest { double bp_time, sp_time; int bp_j; };
 template <bool SORTED, bool R0 = false>
 __device__ inline Slot d_predict_atom(const DevP &D, const SlotSrc &S, int i, Slot cur, double gauss, int dup_limit, int *npair,
-                                      double *second = nullptr) {
+                                      double *second = nullptr, PairBest *pb = nullptr) {
     if (D.is_cons[i]) { cur.time = SD_INF; return cur; }
     Self me = d_load_self(D, i);
     if (!D.gel_mode) d_bond_time(D, S, me, cur, dup_limit);
     if (R0) d_collision_time_2stage<false>(D, S, me, cur, 0);
     else if (SORTED) d_collision_time_2stage<true>(D, S, me, cur, dup_limit);
     else d_collision_time(D, S, me, cur, dup_limit);
+    if (pb) { pb->bp_time = cur.bp_time; pb->sp_time = cur.sp_time; pb->bp_j = cur.bp_j; }   // pair records in front of PCC
     d_pcc_time(D, me, cur);
     if (D.thermostat_on) d_thermostat_time(D, cur, gauss);
     if (D.hydrogen_bond) {
