@@ -258,6 +258,10 @@ int  sdmd_cuda_kinetic_energy(sdmd_ctx *ctx, double *energy);
  * trace (optional, capacity trace_cap records) receives one record per loop iteration. */
 int  sdmd_cuda_run(sdmd_ctx *ctx, double t_until, int64_t max_iter,
                    struct sdmd_trace_rec *trace, int64_t trace_cap, struct sdmd_run_stats *stats);
+/* Many replicas on one GPU (REMD ensembles: the reference runs one sDMD process per replica, REMDExec.c:111-138):
+ * the same loop for n contexts concurrently, one persistent thread block each, one launch.  stats: n entries. */
+int  sdmd_cuda_run_many(sdmd_ctx **ctxs, int n, const double *t_until, int64_t max_iter, struct sdmd_run_stats *stats);
+int  sdmd_cuda_potential_energy_many(sdmd_ctx **ctxs, int n, double *energy);
 int  sdmd_cuda_get_stats(sdmd_ctx *ctx, struct sdmd_run_stats *stats);
 /* targetTemperature after a replica exchange (REMD.c:100) */
 int  sdmd_cuda_set_temperature(sdmd_ctx *ctx, double t_reduced);

@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "sdmd_cuda_pbc_full", "sdmd_cuda_cell_build", "sdmd_cuda_predict_all", "sdmd_cuda_predict", "sdmd_cuda_cbt_build",
     "sdmd_cuda_cbt_update", "sdmd_cuda_assign_job", "sdmd_cuda_advance", "sdmd_cuda_add_time", "sdmd_cuda_hazard_check",
     "sdmd_cuda_cell_move", "sdmd_cuda_do_event", "sdmd_cuda_potential_energy", "sdmd_cuda_kinetic_energy",
-    "sdmd_cuda_run", "sdmd_cuda_get_stats", "sdmd_cuda_set_temperature",
+    "sdmd_cuda_run", "sdmd_cuda_run_many", "sdmd_cuda_potential_energy_many", "sdmd_cuda_get_stats", "sdmd_cuda_set_temperature",
     "sdmd_remd_rearrange", "sdmd_remd_nccl_unique_id", "sdmd_remd_nccl_init", "sdmd_remd_seed_server", "sdmd_remd_exchange", "sdmd_host_glibc_rand",
     "sdmd_cuda_kernel_ms", "sdmd_cuda_kernel_stats", "sdmd_cuda_reset_kernel_stats", "sdmd_cuda_set_timing",
     "sdmd_cuda_launch_count", "sdmd_cuda_stream", "sdmd_cuda_phase_cycles",
@@ -109,6 +109,8 @@ def lib():
     L.sdmd_cuda_kinetic_energy.argtypes = [vp, dp]
     L.sdmd_cuda_run.argtypes = [vp, C.c_double, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(CRunStats)]
     L.sdmd_cuda_get_stats.argtypes = [vp, C.POINTER(CRunStats)]
+    L.sdmd_cuda_run_many.argtypes = [C.POINTER(vp), C.c_int, dp, C.c_int64, C.POINTER(CRunStats)]
+    L.sdmd_cuda_potential_energy_many.argtypes = [C.POINTER(vp), C.c_int, dp]
     L.sdmd_cuda_set_temperature.argtypes = [vp, C.c_double]
     L.sdmd_remd_rearrange.argtypes = [dp, C.POINTER(CRemdTemp), C.c_int, dp, C.c_int, C.POINTER(C.c_int), dp, dp]
     L.sdmd_remd_nccl_unique_id.argtypes = [C.c_char_p]
@@ -328,6 +330,24 @@ class Replica:
         t = CRemdTemp(int(num), 0, float(T))
         _check(self.L.sdmd_remd_exchange(self.h, float(epot), C.byref(t), 0), "remd_exchange")
         return t.num, t.T
+
+
+def run_many(reps, t_until, max_iter=1 << 62):
+    """Run several replicas resident on one GPU concurrently (one persistent thread block each)."""
+    n = len(reps)
+    hs = (C.c_void_p * n)(*[r.h for r in reps])
+    tu = np.ascontiguousarray(np.broadcast_to(np.asarray(t_until, dtype=np.float64), (n,)).copy())
+    st = (CRunStats * n)()
+    _check(lib().sdmd_cuda_run_many(hs, n, _dp(tu), int(max_iter), st), "run_many")
+    return [s.as_dict() for s in st]
+
+
+def potential_energy_many(reps):
+    n = len(reps)
+    hs = (C.c_void_p * n)(*[r.h for r in reps])
+    e = np.zeros(n)
+    _check(lib().sdmd_cuda_potential_energy_many(hs, n, _dp(e)), "potential_energy_many")
+    return e.tolist()
 
 
 def host_register(arr: np.ndarray):

@@ -628,6 +628,49 @@ __global__ void __launch_bounds__(256, 1) k_run_cta(DevP D, double t_until, i64 
     }
 }
 
+// Many replicas per GPU (REMD ensembles, parameter sweeps): one persistent CTA per replica, all in one launch.
+// Each block copies its replica's descriptor into shared memory and runs the same loop as k_run_cta.
+struct MultiArg {
+    DevP P;
+    double t_until;
+    i64 iter_limit;
+};
+__global__ void __launch_bounds__(256, 2) k_run_cta_multi(const MultiArg *args) {
+    __shared__ PredShared sh;
+    __shared__ MultiArg sA;
+    __shared__ double s_dt;
+    __shared__ int s_stop;
+    {
+        const int *src = (const int *)&args[blockIdx.x];
+        int *dst = (int *)&sA;
+        for (int k = threadIdx.x; k < (int)(sizeof(MultiArg) / sizeof(int)); k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
+    const DevP &D = sA.P;
+    double t_until = sA.t_until;
+    i64 iter_limit = sA.iter_limit;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            d_loop_head(D, t_until, iter_limit);
+            s_dt = D.ctl->dt;
+            s_stop = D.ctl->stop;
+            if (!s_stop) d_publish_job(D, sh);
+        }
+        __syncthreads();
+        if (s_stop) break;
+        double dt = s_dt;
+        for (int i = threadIdx.x + 1; i <= D.n; i += blockDim.x) {
+            D.x[i] = D.x[i] + D.vx[i] * dt;
+            D.y[i] = D.y[i] + D.vy[i] * dt;
+            D.z[i] = D.z[i] + D.vz[i] * dt;
+            D.ev_time[i] = D.ev_time[i] - dt;
+        }
+        __syncthreads();
+        d_loop_body_cta(D, sh, t_until, nullptr, 0);
+    }
+}
+__global__ void k_potential_energy_multi(const MultiArg *args, double *out);
+
 // Large systems: per event one grid-wide advance (k_advance with use_ctl) and this single-CTA kernel,
 // which finishes event k and performs AssignJob for event k+1.
 __global__ void __launch_bounds__(256, 1) k_event_exec(DevP D, double t_until, i64 iter_limit, sdmd_trace_rec *trace, i64 trace_cap) {
@@ -672,7 +715,7 @@ __global__ void k_cell_move(DevP D, int atom) { d_pcc_event(D, atom); }
 
 // CalPotenE, ToolFunctions.c:659-752: the accumulation order is part of the result, so one thread adds the
 // pair terms in the reference's order
-__global__ void k_potential_energy(DevP D, double *out) {
+__device__ inline double d_potential_energy(const DevP &D) {
     double TPE = 0, accum = 0;
     for (int i = 1; i <= D.n; i++) {
         int cx = D.cell_idx[3 * i], cy = D.cell_idx[3 * i + 1], cz = D.cell_idx[3 * i + 2];
@@ -707,8 +750,10 @@ __global__ void k_potential_energy(DevP D, double *out) {
             }
         }
     }
-    *out = TPE;
+    return TPE;
 }
+__global__ void k_potential_energy(DevP D, double *out) { *out = d_potential_energy(D); }
+__global__ void k_potential_energy_multi(const MultiArg *args, double *out) { out[blockIdx.x] = d_potential_energy(args[blockIdx.x].P); }
 // CalKinetE, ToolFunctions.c:626-656 (flow.mark < 2, constV = 0); ordered sum
 __global__ void k_kinetic_energy(DevP D, double *out) {
     double TKE = 0;
@@ -734,6 +779,7 @@ int sdmd_cuda_device_count(void) {
 }
 
 static inline int grid_for(int n, int block) { return (n + block - 1) / block; }
+#define SDMD_SMALL_N 4096   /* up to here the whole event loop runs in one persistent CTA */
 
 // leaf permutation of CreateCBT's sequential InsertCBTRun (CBT.c:86-105): time independent
 static void cbt_leaf_permutation(int n, std::vector<int> &leaf_atom) {
@@ -1375,8 +1421,6 @@ int sdmd_cuda_set_temperature(sdmd_ctx *c, double t) {
     return 0;
 }
 
-#define SDMD_SMALL_N 4096
-
 int sdmd_cuda_run(sdmd_ctx *c, double t_until, int64_t max_iter, struct sdmd_trace_rec *trace, int64_t trace_cap,
                   struct sdmd_run_stats *stats) {
     CK(cudaSetDevice(c->device));
@@ -1427,6 +1471,71 @@ int sdmd_cuda_run(sdmd_ctx *c, double t_until, int64_t max_iter, struct sdmd_tra
     }
     if (stats) fill_stats(c->h_ctl, stats);
     if (c->h_ctl->error) return set_err(c->h_ctl->error, "device-side error during run");
+    return 0;
+}
+
+// Run n replicas (all on the same device) concurrently, one persistent CTA each, until every one of them stops
+// (its own t_until / max_iter / RNG low / end of run).  Systems larger than SDMD_SMALL_N are not eligible.
+int sdmd_cuda_run_many(sdmd_ctx **ctxs, int n, const double *t_until, int64_t max_iter, struct sdmd_run_stats *stats) {
+    if (n <= 0 || !ctxs) return set_err(SDMD_ERR_BAD_ARG, "run_many: no replicas");
+    sdmd_ctx *c0 = ctxs[0];
+    CK(cudaSetDevice(c0->device));
+    std::vector<MultiArg> args((size_t)n);
+    for (int k = 0; k < n; k++) {
+        sdmd_ctx *c = ctxs[k];
+        if (c->device != c0->device) return set_err(SDMD_ERR_BAD_ARG, "run_many: replicas on different devices");
+        if (c->n > SDMD_SMALL_N) return set_err(SDMD_ERR_UNSUPPORTED, "run_many: system too large for the one-CTA loop");
+        c->cells_fresh = false;
+        TRY(pull_ctl(c));
+        c->h_ctl->stop = 0;
+        c->h_ctl->trace_pos = 0;
+        TRY(push_ctl(c));
+        CK(cudaStreamSynchronize(c->stream));
+        args[k].P = c->P;
+        args[k].t_until = t_until[k];
+        args[k].iter_limit = (max_iter > (1LL << 61)) ? (1LL << 62) : c->h_ctl->iterations + max_iter;
+    }
+    MultiArg *d_args = nullptr;
+    CK(cudaMalloc((void **)&d_args, sizeof(MultiArg) * n));
+    CK(cudaMemcpyAsync(d_args, args.data(), sizeof(MultiArg) * n, cudaMemcpyHostToDevice, c0->stream));
+    cudaEventRecord(c0->ev0, c0->stream);
+    k_run_cta_multi<<<n, 256, 0, c0->stream>>>(d_args);
+    c0->launches++;
+    cudaEventRecord(c0->ev1, c0->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c0->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c0->ev0, c0->ev1);
+    c0->kstat["run_many"].ms += ms;
+    c0->kstat["run_many"].n++;
+    cudaFree(d_args);
+    int rc = 0;
+    for (int k = 0; k < n; k++) {
+        TRY(pull_ctl(ctxs[k]));
+        if (stats) fill_stats(ctxs[k]->h_ctl, &stats[k]);
+        if (ctxs[k]->h_ctl->error) rc = set_err(ctxs[k]->h_ctl->error, "device-side error during run_many");
+    }
+    return rc;
+}
+
+// CalPotenE of n replicas in one launch
+int sdmd_cuda_potential_energy_many(sdmd_ctx **ctxs, int n, double *energy) {
+    if (n <= 0 || !ctxs) return set_err(SDMD_ERR_BAD_ARG, "potential_energy_many: no replicas");
+    sdmd_ctx *c0 = ctxs[0];
+    CK(cudaSetDevice(c0->device));
+    std::vector<MultiArg> args((size_t)n);
+    for (int k = 0; k < n; k++) { CK(cudaStreamSynchronize(ctxs[k]->stream)); args[k].P = ctxs[k]->P; args[k].t_until = 0; args[k].iter_limit = 0; }
+    MultiArg *d_args = nullptr;
+    double *d_out = nullptr;
+    CK(cudaMalloc((void **)&d_args, sizeof(MultiArg) * n));
+    CK(cudaMalloc((void **)&d_out, sizeof(double) * n));
+    CK(cudaMemcpyAsync(d_args, args.data(), sizeof(MultiArg) * n, cudaMemcpyHostToDevice, c0->stream));
+    k_potential_energy_multi<<<n, 1, 0, c0->stream>>>(d_args, d_out);
+    c0->launches++;
+    CK(cudaMemcpyAsync(energy, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, c0->stream));
+    CK(cudaStreamSynchronize(c0->stream));
+    cudaFree(d_args);
+    cudaFree(d_out);
     return 0;
 }
 

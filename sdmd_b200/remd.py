@@ -55,8 +55,9 @@ def exchange_sweep(epot, nums, temps, stream: ServerStream):
 class RemdEnsemble:
     """All replicas in one process (one GPU holding several replicas, or the test oracle)."""
 
-    def __init__(self, replicas, temps_reduced, exchange_rate: float, server_seed: int, refill=None):
+    def __init__(self, replicas, temps_reduced, exchange_rate: float, server_seed: int, refill=None, batched=None):
         self.reps = list(replicas)
+        self.batched = all(isinstance(r, capi.Replica) for r in self.reps) if batched is None else batched
         self.nums = list(range(1, len(self.reps) + 1))
         self.temps = [float(t) for t in temps_reduced]
         self.rate = float(exchange_rate)
@@ -67,8 +68,34 @@ class RemdEnsemble:
         for r, t in zip(self.reps, self.temps):
             r.set_temperature(t)
 
+    def _step_batched(self):
+        """All replicas are GPU contexts on one device: advance them concurrently (one thread block each)."""
+        n = len(self.reps)
+        pending = list(range(n))
+        times = [0.0] * n
+        while pending:
+            if self.refill:
+                for k in pending:
+                    self.refill(k, self.reps[k])
+            stats = capi.run_many([self.reps[k] for k in pending], self.next_x)
+            nxt = []
+            for k, st in zip(pending, stats):
+                times[k] = st["currenttime"]
+                if st["stop_reason"] == 3:       # SDMD_STOP_NEED_RNG
+                    nxt.append(k)
+            pending = nxt
+        return capi.potential_energy_many(self.reps), times
+
     def step(self):
         """Advance every replica to the next exchange boundary, then exchange."""
+        if self.batched:
+            e, times = self._step_batched()
+            self.nums, self.temps = exchange_sweep(e, self.nums, self.temps, self.stream)
+            for k, r in enumerate(self.reps):
+                r.set_temperature(self.temps[k])
+                self.log[k].append((times[k], self.temps[k], self.nums[k]))
+            self.next_x += self.rate
+            return e
         e, times = [], []
         for k, r in enumerate(self.reps):
             while True:
