@@ -885,6 +885,15 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
         TRY(dupload(c, (int **)&P.cm_table, cmt.data(), (size_t)ncm));
     }
     TRY(dalloc(c, &P.cell_cnt, (size_t)P.ncell + 1));
+    // per-atom candidate-list cache for the event loop (small and medium systems)
+    P.cc_per_atom = (n <= 65536);
+    P.cc_cap = (n <= 8192) ? 256 : (n <= 65536 ? 128 : 256);
+    {
+        size_t rows = P.cc_per_atom ? n1 : 2;
+        TRY(dalloc(c, &P.cc_stamp, n1)); TRY(dalloc(c, &P.cc_n, n1));
+        TRY(dalloc(c, &P.cc_j, (size_t)P.cc_cap * rows)); TRY(dalloc(c, &P.cc_k, (size_t)P.cc_cap * rows));
+        TRY(dalloc(c, &P.cc_pass, (size_t)P.cc_cap * rows));
+    }
     TRY(dupload(c, (sdmd_step_table **)&P.tables, v->tables, (size_t)v->ntable));
     TRY(dupload(c, (int **)&P.coll_index, v->coll_index, (size_t)SD_NT * SD_NT));
     TRY(dupload(c, (int **)&P.hb_index, v->hb_index, (size_t)SDMD_NHBCLASS * SD_NT * SD_NT));
@@ -926,6 +935,7 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     c->h_ctl->timestep = v->timestep;
     c->h_ctl->temperature = v->target_temperature;
     c->h_ctl->frame = v->frame;
+    c->h_ctl->cc_epoch = 1;
     CK(cudaMemcpyAsync(c->d_ctl, c->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream));
     P.ctl = c->d_ctl;
     CK(cudaStreamSynchronize(c->stream));
@@ -1009,6 +1019,7 @@ int sdmd_cuda_host_unregister(void *ptr) {
 }
 void sdmd_cuda_set_timing(sdmd_ctx *c, int on) { c->timing = on != 0; }
 
+static int bump_epoch(sdmd_ctx *c);
 static int pull_ctl(sdmd_ctx *c) {
     CK(cudaMemcpyAsync(c->h_ctl, c->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -1016,6 +1027,13 @@ static int pull_ctl(sdmd_ctx *c) {
 }
 static int push_ctl(sdmd_ctx *c) {
     CK(cudaMemcpyAsync(c->d_ctl, c->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+// invalidate every cached candidate list (link list rebuilt / replaced from the host)
+static int bump_epoch(sdmd_ctx *c) {
+    TRY(pull_ctl(c));
+    c->h_ctl->cc_epoch++;
+    CK(cudaMemcpyAsync(&c->d_ctl->cc_epoch, &c->h_ctl->cc_epoch, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     return 0;
 }
 
@@ -1037,6 +1055,7 @@ int sdmd_cuda_upload_celllist(sdmd_ctx *c, const int32_t *celllist) {
     CK(cudaMemcpyAsync(c->P.celllist, celllist, ((size_t)c->n + c->P.ncell + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     k_cell_count<<<(c->P.ncell + 255) / 256, 256, 0, c->stream>>>(c->P);
     c->launches++;
+    TRY(bump_epoch(c));
     c->cells_fresh = false;
     return 0;
 }
@@ -1180,6 +1199,7 @@ int sdmd_cuda_cell_build(sdmd_ctx *c) {
     k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_sx, c->d_sy, c->d_sz, c->d_svx, c->d_svy,
                                                             c->d_svz, c->d_stype);
     c->launches += 7;
+    TRY(bump_epoch(c));
     c->cells_fresh = true;
     CK(cudaGetLastError());
     return 0;

@@ -31,6 +31,8 @@ struct Ctl {
     int hbnumformed;
     int changed;               // predict_all fix-point flag
     i64 trace_pos;
+    int cc_epoch;              // candidate-list cache epoch: bumped whenever the link list or HB state changes
+    int pad_;
     i64 phase_cycles[12];      // clock64() per loop phase (thread 0): head, advance, event, gather, eval, fold, cbt
 };
 
@@ -82,6 +84,11 @@ struct DevP {
     const int *cm_off, *cm_j, *cm_flags;
     const int *cm_table;   // constraint table of a CONSTRAINT_CONNECT entry (resolved from the constr list at create)
     int *cell_cnt;         // atoms per cell, kept in step with the link list
+    // per-atom cache of the 27-cell candidate list (scan order), valid while cc_stamp[i] == ctl->cc_epoch
+    int *cc_stamp, *cc_n, *cc_j;
+    unsigned char *cc_k, *cc_pass;
+    int cc_cap;            // entries per row
+    int cc_per_atom;       // 1: one row per atom, reused across events; 0: two scratch rows, rebuilt every event (huge systems)
     const sdmd_step_table *tables;
     const int *coll_index, *hb_index;
     const double *gauss;
@@ -340,6 +347,7 @@ struct Self {
     int cx, cy, cz;
     i64 counter;
     int npair;
+    int type, cm0, cm1;
 };
 
 // one candidate of CollisionTime's inner loop, TimePrediction.c:82-176, after the duplicate check
@@ -696,6 +704,8 @@ __device__ __forceinline__ Self d_load_self(const DevP &D, int i) {
     me.cx = D.cell_idx[3 * i]; me.cy = D.cell_idx[3 * i + 1]; me.cz = D.cell_idx[3 * i + 2];
     me.counter = D.ev_counter[i];
     me.npair = 0;
+    me.type = D.type[i];
+    me.cm0 = D.cm_off[i]; me.cm1 = D.cm_off[i + 1];
     return me;
 }
 
@@ -956,6 +966,7 @@ __device__ inline void d_hb_event(const DevP &D, int i, int j, int ni, int nj) {
         t = ++D.hbn_status[ni]; D.hbn_partner[5 * ni + t] = j;
         t = ++D.hbn_status[nj]; D.hbn_partner[5 * nj + t] = i;
         D.ctl->hbnumformed++;
+        D.ctl->cc_epoch++;
     } else if (D.hb_itype[i] == SDMD_HB_BREAK) {
         D.hb_bond[i] = 0; D.hb_bond[j] = 0;
         D.type[i] = d_type_change(D.type[i], 0);
@@ -965,6 +976,7 @@ __device__ inline void d_hb_event(const DevP &D, int i, int j, int ni, int nj) {
         --D.hbn_status[ni]; d_list_refresh(D, ni, j);
         --D.hbn_status[nj]; d_list_refresh(D, nj, i);
         D.ctl->hbnumformed--;
+        D.ctl->cc_epoch++;
     }
 }
 
@@ -1025,6 +1037,7 @@ __device__ inline void d_pcc_event(const DevP &D, int i) {
     cl[next] = i;
     D.cell_cnt[oldCell]--;
     D.cell_cnt[newCell]++;
+    D.ctl->cc_epoch++;
 }
 
 // DoEvent, Events.c:25-114
@@ -1089,6 +1102,7 @@ struct PredShared {
     int adj_f[2][PC_MAXADJ];     // connectionMap flags | (constraint table index << 8)
     int hbn[2][4];               // neighborPartner[1..4]
     int hb_bond[2];
+    int cc_row[2];
     int coll_row[2][SD_NT];      // coll_index[type_i][*]
     double shift[2][27][3];      // minimum-image shift of neighbour-cell slot k (PBCShift, ToolFunctions.c:801-817)
     int elig_n[2];
@@ -1194,42 +1208,77 @@ __device__ inline FindRes d_find_pair_fast(const DevP &D, int a1, int a2, int mo
 }
 
 // ---- phase A: lay out the candidate array of predict-atom `a` (executed by ONE warp per atom) ----
-// Per-cell occupancy counts (maintained next to the link list) give every neighbour cell's offset with one
-// warp scan, so each list is walked exactly once.
+// The 27-cell candidate list of an atom only changes when the link list or the HB state changes (PCC / HB
+// events, < 1 % of events on proteins), so it is cached per atom in HBM (L1/L2 resident for small systems) and
+// re-walked only when its epoch stamp is stale.  On a miss, per-cell occupancy counts give every neighbour
+// cell's offset with one warp scan, so each list is walked exactly once.
 __device__ inline void d_pc_gather_warp(const DevP &D, PredShared &sh, int a) {
     int lane = threadIdx.x & 31;
     int i = sh.atom[a];
     int base = a * PC_MAXC;
     int cx = D.cell_idx[3 * i], cy = D.cell_idx[3 * i + 1], cz = D.cell_idx[3 * i + 2];
-    int cell = 0, cnt = 0;
+    int cap = D.cc_cap;
+    int epoch = D.ctl->cc_epoch;
+    int row = D.cc_per_atom ? i : a;
+    bool hit = D.cc_per_atom && D.cc_stamp[i] == epoch;
+    int role = 0, bonded = 0, itype = 0, nhbne = 0;
+    if (D.hydrogen_bond) {
+        role = D.hb_role[i];
+        bonded = D.hb_bond[i];
+        itype = D.hb_itype[i];
+        nhbne = D.hbn_status[i];
+    }
+    bool can_hbfree = D.hydrogen_bond && (role == 'A' || role == 'D' || role == 'S');
+    int cell = 0;
     if (lane < 27) {
         int ncx, ncy, ncz;
         cell = d_neighbor_cell(D, cx, cy, cz, lane, &ncx, &ncy, &ncz);
-        cnt = D.cell_cnt[cell] - (lane == 0 ? 1 : 0);   // offset 0 is the atom's own cell
         sh.shift[a][lane][0] = d_shift1(cx, ncx, D.cellnum[0], D.box[0]);
         sh.shift[a][lane][1] = d_shift1(cy, ncy, D.cellnum[1], D.box[1]);
         sh.shift[a][lane][2] = d_shift1(cz, ncz, D.cellnum[2], D.box[2]);
     }
-    int incl = cnt;
-    for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    int ncoll = __shfl_sync(0xffffffffu, incl, 31);
-    int off = incl - cnt;
-    // section layout (every lane computes the same small thing from broadcast loads)
-    int nb = D.gel_mode ? 0 : (D.bond_off[i + 1] - D.bond_off[i]);
-    int nhb = 0, hbfree = 0, nhbne = 0;
-    int role = 0, bonded = 0;
-    if (D.hydrogen_bond) {
-        role = D.hb_role[i];
-        bonded = D.hb_bond[i];
-        int itype = D.hb_itype[i];
-        if (itype != SDMD_HB_SKIP) {   // TimePrediction.c:309-327
-            if (bonded > 0) nhb = 1;
-            else if ((role == 'A' || role == 'D' || role == 'S') && bonded == 0) { hbfree = 1; nhb = ncoll; }
+    int ncoll;
+    if (hit) {
+        ncoll = D.cc_n[i];
+    } else {
+        int cnt = (lane < 27) ? D.cell_cnt[cell] - (lane == 0 ? 1 : 0) : 0;   // offset 0 is the atom's own cell
+        int incl = cnt;
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
-        nhbne = D.hbn_status[i];
+        ncoll = __shfl_sync(0xffffffffu, incl, 31);
+        int off = incl - cnt;
+        if (ncoll <= cap) {
+            if (lane < 27) {
+                int w = row * cap + off;
+                int ti = D.type[i], pi = D.protein[i], ai = D.aa_num[i];
+                for (int j = D.celllist[D.n + cell + 1]; j; j = D.celllist[j]) {
+                    if (j == i) continue;
+                    unsigned char pass = 0;
+                    if (can_hbfree) {
+                        // role / bonded / sequence-separation filters of the free-HB scan, TimePrediction.c:418-429
+                        int rj = D.hb_role[j];
+                        bool ad = (role == 'A' && rj == 'D') || (role == 'D' && rj == 'A');
+                        bool sd = (role == 'S' && D.type[j] == 2) || (rj == 'S' && ti == 2);
+                        bool ss = (role == 'S' && rj == 'S');
+                        int d = ai - D.aa_num[j];
+                        if (d < 0) d = -d;
+                        pass = (ad || sd || ss) && D.hb_bond[j] == 0 && ((pi == D.protein[j] && d >= 4) || pi != D.protein[j]);
+                    }
+                    D.cc_j[w] = j; D.cc_k[w] = (unsigned char)lane; D.cc_pass[w] = pass;
+                    w++;
+                }
+            }
+            if (lane == 0 && D.cc_per_atom) { D.cc_n[i] = ncoll; D.cc_stamp[i] = epoch; }
+        }
+    }
+    // section layout (every lane computes the same small thing)
+    int nb = D.gel_mode ? 0 : (D.bond_off[i + 1] - D.bond_off[i]);
+    int nhb = 0, hbfree = 0;
+    if (D.hydrogen_bond && itype != SDMD_HB_SKIP) {   // TimePrediction.c:309-327
+        if (bonded > 0) nhb = 1;
+        else if (can_hbfree && bonded == 0) { hbfree = 1; nhb = ncoll; }
     }
     int off_coll = nb;
     int off_pcc = off_coll + ncoll;
@@ -1237,37 +1286,15 @@ __device__ inline void d_pc_gather_warp(const DevP &D, PredShared &sh, int a) {
     int off_hb = off_ther + (D.thermostat_on ? 1 : 0);
     int off_hbne = off_hb + nhb;
     int total = off_hbne + nhbne;
-    int ncm = D.cm_off[i + 1] - D.cm_off[i];
-    bool serial = total > PC_MAXC || ncm > PC_MAXADJ || nb > 27;
+    bool serial = total > PC_MAXC || nb > 27 || ncoll > cap;
     if (lane == 0) {
         sh.n_bond[a] = nb; sh.n_coll[a] = ncoll; sh.n_hbne[a] = nhbne; sh.hb_free[a] = hbfree;
         sh.off_coll[a] = off_coll; sh.off_pcc[a] = off_pcc; sh.off_ther[a] = off_ther; sh.off_hb[a] = off_hb;
-        sh.off_hbne[a] = off_hbne; sh.ncand[a] = total; sh.use_serial[a] = serial; sh.n_adj[a] = ncm;
+        sh.off_hbne[a] = off_hbne; sh.ncand[a] = total; sh.use_serial[a] = serial;
         sh.hb_bond[a] = bonded;
+        sh.cc_row[a] = row;
     }
     if (serial) return;
-    if (lane < 27) {
-        int p = base + off_coll + off;
-        int q = base + off_hb + off;
-        int ti = D.type[i], pi = D.protein[i], ai = D.aa_num[i];
-        for (int j = D.celllist[D.n + cell + 1]; j; j = D.celllist[j]) {
-            if (j == i) continue;
-            sh.cj[p] = j; sh.ckind[p] = CK_COLL; sh.caux[p] = (unsigned char)lane; p++;
-            if (hbfree) {
-                // role / bonded / sequence-separation filters of the free-HB scan, TimePrediction.c:418-429
-                int rj = D.hb_role[j];
-                bool ad = (role == 'A' && rj == 'D') || (role == 'D' && rj == 'A');
-                bool sd = (role == 'S' && D.type[j] == 2) || (rj == 'S' && ti == 2);
-                bool ss = (role == 'S' && rj == 'S');
-                int d = ai - D.aa_num[j];
-                if (d < 0) d = -d;
-                bool pass = (ad || sd || ss) && D.hb_bond[j] == 0 && ((pi == D.protein[j] && d >= 4) || pi != D.protein[j]);
-                sh.cj[q] = j; sh.ckind[q] = pass ? CK_HBFREE : CK_NONE; sh.caux[q] = (unsigned char)lane;
-                sh.cflag[q] = 0; sh.ctime[q] = SD_INF;
-                q++;
-            }
-        }
-    }
     if (lane < nb) {
         int p = base + lane;
         sh.cj[p] = D.bond_j[D.bond_off[i] + lane]; sh.ckind[p] = CK_BOND; sh.caux[p] = (unsigned char)lane;
@@ -1287,24 +1314,17 @@ __device__ inline void d_pc_gather_warp(const DevP &D, PredShared &sh, int a) {
             sh.cj[p] = hp; sh.ckind[p] = CK_HBNE; sh.caux[p] = (unsigned char)n;
         }
     }
-    for (int k = lane; k < ncm; k += 32) {
-        int e = D.cm_off[i] + k;
-        sh.adj_j[a][k] = D.cm_j[e];
-        sh.adj_f[a][k] = D.cm_flags[e] | (D.cm_table[e] << 8);
-    }
-    {
-        int ti = D.type[i];
-        for (int k = lane; k < SD_NT; k += 32) sh.coll_row[a][k] = __ldg(&D.coll_index[ti * SD_NT + k]);
-    }
 }
 
 // ---- phase B: own-side evaluation of one candidate entry (any thread) ----
 // lean path for the cell-scan entries of CollisionTime (TimePrediction.c:82-176)
 __device__ __forceinline__ void d_pc_eval_coll(const DevP &D, PredShared &sh, int a, int p, const Self &me) {
     int q = a * PC_MAXC + p;
-    int j = sh.cj[q];
-    int k = sh.caux[q];
     int i = me.i;
+    int ce = sh.cc_row[a] * D.cc_cap + (p - sh.off_coll[a]);
+    int j = D.cc_j[ce];
+    int k = D.cc_k[ce];
+    sh.cj[q] = j; sh.ckind[q] = CK_COLL; sh.caux[q] = (unsigned char)k;
     int flag = 0, sub = SDMD_SUB_INVALID;
     double time = SD_INF, pot = 0;
     // independent loads first
@@ -1315,11 +1335,8 @@ __device__ __forceinline__ void d_pc_eval_coll(const DevP &D, PredShared &sh, in
     int typej = D.type[j];
     double shx = sh.shift[a][k][0], shy = sh.shift[a][k][1], shz = sh.shift[a][k][2];
     int cm = 0, con_tbl = 0;
-    int na_ = sh.n_adj[a];
-    for (int e = 0; e < na_; e++) {
-        int aj = sh.adj_j[a][e];
-        int af = sh.adj_f[a][e];
-        if (aj == j) { cm = af & 0xff; con_tbl = af >> 8; }
+    for (int e = me.cm0; e < me.cm1; e++) {   // static connectionMap row (BOND / CONSTRAINT bits + constraint table)
+        if (D.cm_j[e] == j) { cm = D.cm_flags[e]; con_tbl = D.cm_table[e]; }
     }
     bool skip = (cm & SDMD_BOND_CONNECT) || sh.hb_bond[a] == j;
     // FindElemInList over neighborPartner stops at the first 0 (ToolFunctions.c:1078-1084)
@@ -1338,7 +1355,7 @@ __device__ __forceinline__ void d_pc_eval_coll(const DevP &D, PredShared &sh, in
             if (cm & SDMD_CONSTRAINT_CONNECT) {
                 f = d_find_pair_table_fast(D, &D.tables[con_tbl], FP_CONSTRAINT, pr.b, pr.r2, 0, 0);
             } else {
-                int idx = sh.coll_row[a][typej];
+                int idx = __ldg(&D.coll_index[me.type * SD_NT + typej]);
                 if (idx < 0) { D.ctl->error = SDMD_ERR_TABLE; idx = 0; }
                 f = d_find_pair_table_fast(D, &D.tables[idx], FP_COLLISION, pr.b, pr.r2, 0, 0);
                 if (f.lowPot == 0 && f.upPot == 0) none = true;
@@ -1369,10 +1386,18 @@ __device__ __forceinline__ void d_pc_eval_coll(const DevP &D, PredShared &sh, in
 // every other predictor's entries
 __device__ inline void d_pc_eval(const DevP &D, PredShared &sh, int a, int p, const Self &me) {
     int q = a * PC_MAXC + p;
+    int i = me.i;
+    if (sh.hb_free[a] && p >= sh.off_hb[a] && p < sh.off_hbne[a]) {
+        // free-HB scan entry: same candidate list as the collision scan, filter result cached with it
+        int ce = sh.cc_row[a] * D.cc_cap + (p - sh.off_hb[a]);
+        int pass = D.cc_pass[ce];
+        sh.cj[q] = D.cc_j[ce]; sh.caux[q] = D.cc_k[ce];
+        sh.ckind[q] = pass ? CK_HBFREE : CK_NONE;
+        if (!pass) { sh.cflag[q] = 0; sh.ctime[q] = SD_INF; return; }
+    }
     int kind = sh.ckind[q];
     if (kind == CK_NONE) return;
     int j = sh.cj[q];
-    int i = me.i;
     int flag = 0, sub = SDMD_SUB_INVALID;
     double time = SD_INF, pot = 0;
     if (kind == CK_PCC) {
