@@ -893,6 +893,20 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
         TRY(dalloc(c, &P.cc_stamp, n1)); TRY(dalloc(c, &P.cc_n, n1));
         TRY(dalloc(c, &P.cc_j, (size_t)P.cc_cap * rows)); TRY(dalloc(c, &P.cc_k, (size_t)P.cc_cap * rows));
         TRY(dalloc(c, &P.cc_pass, (size_t)P.cc_cap * rows));
+        TRY(dalloc(c, &P.cc_passidx, 32 * rows)); TRY(dalloc(c, &P.cc_npass, rows));
+    }
+    P.cm_dense = nullptr;
+    if (n <= 2048) {   // dense static connection matrix: one load instead of a row search in the candidate evaluation
+        std::vector<unsigned> dense(n1 * n1, 0u);
+        for (int i = 1; i <= n && ncm; i++)
+            for (int e = v->cm_off[i]; e < v->cm_off[i + 1]; e++) {
+                unsigned tbl = 0;
+                if (v->cm_flags[e] & SDMD_CONSTRAINT_CONNECT)
+                    for (int k = v->con_off[i]; k < v->con_off[i + 1]; k++)
+                        if (v->con_j[k] == v->cm_j[e]) { tbl = (unsigned)v->con_table[k]; break; }
+                dense[(size_t)i * n1 + v->cm_j[e]] = (unsigned)(v->cm_flags[e] & 0xff) | (tbl << 8);
+            }
+        TRY(dupload(c, (unsigned **)&P.cm_dense, dense.data(), n1 * n1));
     }
     TRY(dupload(c, (sdmd_step_table **)&P.tables, v->tables, (size_t)v->ntable));
     TRY(dupload(c, (int **)&P.coll_index, v->coll_index, (size_t)SD_NT * SD_NT));

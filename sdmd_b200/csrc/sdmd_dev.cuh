@@ -88,6 +88,9 @@ struct DevP {
     int *cc_stamp, *cc_n, *cc_j;
     unsigned char *cc_k, *cc_pass;
     int cc_cap;            // entries per row
+    unsigned short *cc_passidx;   // positions (within the row) of entries that pass the free-HB filters, 32 per row
+    int *cc_npass;
+    const unsigned int *cm_dense; // (n+1)^2 entries flags | table << 8 for small systems, else NULL
     int cc_per_atom;       // 1: one row per atom, reused across events; 0: two scratch rows, rebuilt every event (huge systems)
     const sdmd_step_table *tables;
     const int *coll_index, *hb_index;
@@ -1103,6 +1106,7 @@ struct PredShared {
     int hbn[2][4];               // neighborPartner[1..4]
     int hb_bond[2];
     int cc_row[2];
+    int n_pass[2];
     int coll_row[2][SD_NT];      // coll_index[type_i][*]
     double shift[2][27][3];      // minimum-image shift of neighbour-cell slot k (PBCShift, ToolFunctions.c:801-817)
     int elig_n[2];
@@ -1270,9 +1274,28 @@ __device__ inline void d_pc_gather_warp(const DevP &D, PredShared &sh, int a) {
                     w++;
                 }
             }
-            if (lane == 0 && D.cc_per_atom) { D.cc_n[i] = ncoll; D.cc_stamp[i] = epoch; }
+            __syncwarp();
+            // compact list of the entries that pass the free-HB filters (positions in scan order)
+            int npass = 0;
+            if (can_hbfree) {
+                for (int p0 = 0; p0 < ncoll; p0 += 32) {
+                    int p = p0 + lane;
+                    bool ps = p < ncoll && D.cc_pass[row * cap + p];
+                    unsigned m = __ballot_sync(0xffffffffu, ps);
+                    if (ps) {
+                        int slot = npass + __popc(m & ((1u << lane) - 1));
+                        if (slot < 32) D.cc_passidx[row * 32 + slot] = (unsigned short)p;
+                    }
+                    npass += __popc(m);
+                }
+            }
+            if (lane == 0) {
+                D.cc_npass[row] = npass;
+                if (D.cc_per_atom) { D.cc_n[i] = ncoll; D.cc_stamp[i] = epoch; }
+            }
         }
     }
+    __syncwarp();
     // section layout (every lane computes the same small thing)
     int nb = D.gel_mode ? 0 : (D.bond_off[i + 1] - D.bond_off[i]);
     int nhb = 0, hbfree = 0;
@@ -1286,13 +1309,15 @@ __device__ inline void d_pc_gather_warp(const DevP &D, PredShared &sh, int a) {
     int off_hb = off_ther + (D.thermostat_on ? 1 : 0);
     int off_hbne = off_hb + nhb;
     int total = off_hbne + nhbne;
-    bool serial = total > PC_MAXC || nb > 27 || ncoll > cap;
+    int npass_row = hbfree ? D.cc_npass[row] : 0;
+    bool serial = total > PC_MAXC || nb > 27 || ncoll > cap || npass_row > 32;
     if (lane == 0) {
         sh.n_bond[a] = nb; sh.n_coll[a] = ncoll; sh.n_hbne[a] = nhbne; sh.hb_free[a] = hbfree;
         sh.off_coll[a] = off_coll; sh.off_pcc[a] = off_pcc; sh.off_ther[a] = off_ther; sh.off_hb[a] = off_hb;
         sh.off_hbne[a] = off_hbne; sh.ncand[a] = total; sh.use_serial[a] = serial;
         sh.hb_bond[a] = bonded;
         sh.cc_row[a] = row;
+        sh.n_pass[a] = npass_row;
     }
     if (serial) return;
     if (lane < nb) {
@@ -1335,8 +1360,12 @@ __device__ __forceinline__ void d_pc_eval_coll(const DevP &D, PredShared &sh, in
     int typej = D.type[j];
     double shx = sh.shift[a][k][0], shy = sh.shift[a][k][1], shz = sh.shift[a][k][2];
     int cm = 0, con_tbl = 0;
-    for (int e = me.cm0; e < me.cm1; e++) {   // static connectionMap row (BOND / CONSTRAINT bits + constraint table)
-        if (D.cm_j[e] == j) { cm = D.cm_flags[e]; con_tbl = D.cm_table[e]; }
+    if (D.cm_dense) {   // static connectionMap entry (BOND / CONSTRAINT bits + constraint table), dense for small systems
+        unsigned v = __ldg(&D.cm_dense[(size_t)i * (D.n + 1) + j]);
+        cm = v & 0xff; con_tbl = v >> 8;
+    } else {
+        for (int e = me.cm0; e < me.cm1; e++)
+            if (D.cm_j[e] == j) { cm = D.cm_flags[e]; con_tbl = D.cm_table[e]; }
     }
     bool skip = (cm & SDMD_BOND_CONNECT) || sh.hb_bond[a] == j;
     // FindElemInList over neighborPartner stops at the first 0 (ToolFunctions.c:1078-1084)
@@ -1388,12 +1417,10 @@ __device__ inline void d_pc_eval(const DevP &D, PredShared &sh, int a, int p, co
     int q = a * PC_MAXC + p;
     int i = me.i;
     if (sh.hb_free[a] && p >= sh.off_hb[a] && p < sh.off_hbne[a]) {
-        // free-HB scan entry: same candidate list as the collision scan, filter result cached with it
+        // free-HB scan entry (passed the role filters): same candidate list as the collision scan
         int ce = sh.cc_row[a] * D.cc_cap + (p - sh.off_hb[a]);
-        int pass = D.cc_pass[ce];
         sh.cj[q] = D.cc_j[ce]; sh.caux[q] = D.cc_k[ce];
-        sh.ckind[q] = pass ? CK_HBFREE : CK_NONE;
-        if (!pass) { sh.cflag[q] = 0; sh.ctime[q] = SD_INF; return; }
+        sh.ckind[q] = CK_HBFREE;
     }
     int kind = sh.ckind[q];
     if (kind == CK_NONE) return;
@@ -1673,11 +1700,23 @@ __device__ inline void d_predict_cta(const DevP &D, PredShared &sh) {
                 d_pc_eval_group<false>(D, sh, me0, me1, on0 ? sh.off_hbne[0] : 0, on0 ? sh.ncand[0] : 0, on1 ? sh.off_hbne[1] : 0,
                                        on1 ? sh.ncand[1] : 0, gc + 48, 16);
             }
-            // free-HB scan entries that passed the role filters
-            {
-                int f0 = (on0 && sh.hb_free[0]) ? sh.off_hb[0] : 0, f0e = (on0 && sh.hb_free[0]) ? sh.off_hbne[0] : 0;
-                int f1 = (on1 && sh.hb_free[1]) ? sh.off_hb[1] : 0, f1e = (on1 && sh.hb_free[1]) ? sh.off_hbne[1] : 0;
-                d_pc_eval_group<false>(D, sh, me0, me1, f0, f0e, f1, f1e, gc + 64, 32);
+            // free-HB scan: one warp blanks the section, then evaluates only the entries that passed the role filters
+            if (tid >= gc + 64 && tid < gc + 96) {
+                int lane = tid & 31;
+                for (int a = 0; a < na; a++) {
+                    bool on = (a == 0) ? on0 : on1;
+                    if (!on || !sh.hb_free[a]) continue;
+                    int b0 = a * PC_MAXC;
+                    for (int p = sh.off_hb[a] + lane; p < sh.off_hbne[a]; p += 32) {
+                        sh.ckind[b0 + p] = CK_NONE; sh.cflag[b0 + p] = 0; sh.ctime[b0 + p] = SD_INF; sh.cj[b0 + p] = 0;
+                    }
+                    __syncwarp();
+                    if (lane < sh.n_pass[a]) {
+                        int p = sh.off_hb[a] + D.cc_passidx[sh.cc_row[a] * 32 + lane];
+                        d_pc_eval(D, sh, a, p, a ? me1 : me0);
+                    }
+                    __syncwarp();
+                }
             }
         }
     }
