@@ -274,6 +274,11 @@ __device__ __forceinline__ SlotSrc as_src(const SlotBuf &b) {
 //             a changed slot queues the higher-index atoms it pointed / points at.
 // The stale fields of a slot (potential / subEventType / partnerCounter survive ResetTarget) always start from the
 // live arrays, which this pass never writes until the final commit.
+__global__ void __launch_bounds__(256) k_predict_all_filter(DevP D) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < D.n) d_r0_filter(D, p);
+}
+
 __global__ void __launch_bounds__(128) k_predict_all_round(DevP D, SlotBuf src, SlotBuf dst, const int *queue, const int *nqueue_ptr,
                                                            int round, int *npair, double *second, double *bp_time, int *bp_j,
                                                            int *pcount, int *pwho, unsigned long long *pair_sum, i64 g_base) {
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(128) k_predict_all_round(DevP D, SlotBuf src, 
         int np = 0;
         double m2 = SD_INF;
         PairBest pb;
-        if (round == 0) cur = d_predict_atom<true, true>(D, as_src(src), i, cur, g, 0, &np, &m2, &pb);
+        if (round == 0) cur = d_predict_atom<true, true>(D, as_src(src), i, cur, g, 0, &np, &m2, &pb, D.surv ? p : -1);
         else cur = d_predict_atom<true, false>(D, as_src(src), i, cur, g, i, &np, nullptr);
         dst.time[i] = cur.time; dst.pot[i] = cur.pot; dst.partner[i] = cur.partner; dst.pcounter[i] = cur.pcounter;
         dst.type[i] = (uint8_t)cur.type; dst.sub[i] = (uint8_t)cur.sub;
@@ -936,6 +941,10 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     TRY(dalloc(c, &c->d_svx, n1)); TRY(dalloc(c, &c->d_svy, n1)); TRY(dalloc(c, &c->d_svz, n1));
     TRY(dalloc(c, &c->d_stype, n1));
     TRY(dalloc(c, &c->d_sum, 4));
+    P.surv = nullptr; P.surv_n = nullptr; P.surv_np = nullptr;
+    if (n < (1 << 27)) {
+        TRY(dalloc(c, &P.surv, (size_t)R0_SURV_CAP * n1)); TRY(dalloc(c, &P.surv_n, n1)); TRY(dalloc(c, &P.surv_np, n1));
+    }
     P.cell_start = c->d_cell_start; P.sorted_atom = c->d_sorted_atom;
     P.sx = c->d_sx; P.sy = c->d_sy; P.sz = c->d_sz; P.svx = c->d_svx; P.svy = c->d_svy; P.svz = c->d_svz; P.stype = c->d_stype;
     std::vector<int> leaf_atom;
@@ -1237,6 +1246,10 @@ int sdmd_cuda_predict_all(sdmd_ctx *c) {
     CK(cudaMemsetAsync(c->d_sum, 0, sizeof(unsigned long long), c->stream));
     {
         Timer t(c, "predict_all");
+        if (c->P.surv) {
+            k_predict_all_filter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P);
+            c->launches++;
+        }
         k_predict_all_round<<<grid, 128, 0, c->stream>>>(c->P, B, B, nullptr, nullptr, 0, c->npair, c->second, c->bp_time, c->bp_j,
                                                          c->pcount, c->pwho, c->d_sum, g_base);
         c->launches++;

@@ -103,6 +103,10 @@ struct DevP {
     const int *sorted_atom;  // [n]
     const double *sx, *sy, *sz, *svx, *svy, *svz;
     const int *stype;
+    // round-0 filter output: per sorted position up to R0_SURV_CAP candidates inside the scan sphere
+    unsigned int *surv;      // (sorted position of j) | (scan slot k << 27)
+    int *surv_n;             // count, or -1 when the list overflowed (atom re-scanned in the evaluation kernel)
+    int *surv_np;            // pair evaluations counted by the filter
 };
 
 // neighbour-cell offsets, DMD.c:118-120
@@ -431,6 +435,7 @@ __device__ inline void d_collision_time_sorted(const DevP &D, const SlotSrc &S, 
 // Candidates are still folded in exact scan order, so the result is the sequential one; the split only removes
 // the per-candidate divergence that left ~9 of 32 lanes active in the fused loop.
 #define R0_MAXSURV 20
+#define R0_SURV_CAP 32
 #define R0_DUPFLAG 0x80   // survivor entry whose partner's slot points back: resolved in order in stage 2
 __device__ __forceinline__ void d_r0_flush(const DevP &D, const SlotSrc &S, Self &me, Slot &cur, const int *surv_p,
                                            const unsigned char *surv_k, int ns, bool has_cm, int type_i, int hb_i, int h0, int h1,
@@ -535,6 +540,64 @@ __device__ inline void d_collision_time_2stage(const DevP &D, const SlotSrc &S, 
     }
     d_r0_flush(D, S, me, cur, surv_p, surv_k, ns, has_cm, type_i, hb_i, h0, h1, h2, h3);
     me.npair += npair;
+}
+
+// Round-0 stage 1 as its own light kernel body: skip filters, evaluation count, 0.9*cutoff sphere test over the
+// cell-sorted tiles; survivors go to HBM in scan order (they are few: ~6 of ~41 candidates at 8 A spacing).
+__device__ inline void d_r0_filter(const DevP &D, int p_self) {
+    int i = D.sorted_atom[p_self];
+    double x = D.sx[p_self], y = D.sy[p_self], z = D.sz[p_self];
+    int cx = D.cell_idx[3 * i], cy = D.cell_idx[3 * i + 1], cz = D.cell_idx[3 * i + 2];
+    bool has_cm = D.cm_off[i + 1] > D.cm_off[i];
+    int hb_i = D.hb_bond[i];
+    int h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+    if (D.hydrogen_bond) { h0 = D.hbn_partner[5 * i + 1]; h1 = D.hbn_partner[5 * i + 2]; h2 = D.hbn_partner[5 * i + 3]; h3 = D.hbn_partner[5 * i + 4]; }
+    bool need_j = has_cm || hb_i != 0 || h0 != 0;
+    unsigned int *out = D.surv + (size_t)p_self * R0_SURV_CAP;
+    int ns = 0, npair = 0;
+    for (int k = 0; k < 27; k++) {
+        int ncx, ncy, ncz;
+        int cell = d_neighbor_cell(D, cx, cy, cz, k, &ncx, &ncy, &ncz);
+        double shx = d_shift1(cx, ncx, D.cellnum[0], D.box[0]);
+        double shy = d_shift1(cy, ncy, D.cellnum[1], D.box[1]);
+        double shz = d_shift1(cz, ncz, D.cellnum[2], D.box[2]);
+        int p1 = D.cell_start[cell + 1];
+        for (int p = D.cell_start[cell]; p < p1; p++) {
+            if (p == p_self) continue;
+            if (need_j) {
+                int j = D.sorted_atom[p];
+                if (has_cm && (d_cm_flags(D, i, j) & SDMD_BOND_CONNECT)) continue;
+                if (hb_i == j) continue;
+                if ((h0 == j) || (h0 != 0 && (h1 == j || (h1 != 0 && (h2 == j || (h2 != 0 && h3 == j)))))) continue;
+            }
+            npair++;
+            double tx = D.sx[p] + shx, ty = D.sy[p] + shy, tz = D.sz[p] + shz;
+            double rx = x - tx, ry = y - ty, rz = z - tz;
+            double r2 = rx * rx + ry * ry + rz * rz;
+            if (r2 <= D.cut2) {
+                if (ns < R0_SURV_CAP) out[ns] = (unsigned)p | ((unsigned)k << 27);
+                ns++;
+            }
+        }
+    }
+    D.surv_n[p_self] = (ns <= R0_SURV_CAP) ? ns : -1;
+    D.surv_np[p_self] = npair;
+}
+
+// Round-0 stage 2 from the filter's list
+__device__ inline void d_collision_time_from_list(const DevP &D, const SlotSrc &S, Self &me, Slot &cur, int p_self) {
+    int ns = D.surv_n[p_self];
+    const unsigned int *in = D.surv + (size_t)p_self * R0_SURV_CAP;
+    bool has_cm = D.cm_off[me.i + 1] > D.cm_off[me.i];
+    int type_i = D.type[me.i];
+    int surv_p[R0_MAXSURV];
+    unsigned char surv_k[R0_MAXSURV];
+    for (int s0 = 0; s0 < ns; s0 += R0_MAXSURV) {
+        int m = ns - s0 < R0_MAXSURV ? ns - s0 : R0_MAXSURV;
+        for (int s = 0; s < m; s++) { unsigned v = in[s0 + s]; surv_p[s] = (int)(v & 0x7ffffffu); surv_k[s] = (unsigned char)(v >> 27); }
+        d_r0_flush(D, S, me, cur, surv_p, surv_k, m, has_cm, type_i, 0, 0, 0, 0, 0);
+    }
+    me.npair += D.surv_np[p_self];
 }
 
 // BondTime, TimePrediction.c:186-295
@@ -725,11 +788,12 @@ __device__ __forceinline__ Slot d_reset_slot(double pot, int sub, i64 pcounter) 
 struct PairBest { double bp_time, sp_time; int bp_j; };
 template <bool SORTED, bool R0 = false>
 __device__ inline Slot d_predict_atom(const DevP &D, const SlotSrc &S, int i, Slot cur, double gauss, int dup_limit, int *npair,
-                                      double *second = nullptr, PairBest *pb = nullptr) {
+                                      double *second = nullptr, PairBest *pb = nullptr, int surv_pos = -1) {
     if (D.is_cons[i]) { cur.time = SD_INF; return cur; }
     Self me = d_load_self(D, i);
     if (!D.gel_mode) d_bond_time(D, S, me, cur, dup_limit);
-    if (R0) d_collision_time_2stage<false>(D, S, me, cur, 0);
+    if (R0 && surv_pos >= 0 && D.surv_n[surv_pos] >= 0) d_collision_time_from_list(D, S, me, cur, surv_pos);
+    else if (R0) d_collision_time_2stage<false>(D, S, me, cur, 0);
     else if (SORTED) d_collision_time_2stage<true>(D, S, me, cur, dup_limit);
     else d_collision_time(D, S, me, cur, dup_limit);
     if (pb) { pb->bp_time = cur.bp_time; pb->sp_time = cur.sp_time; pb->bp_j = cur.bp_j; }   // pair records in front of PCC
