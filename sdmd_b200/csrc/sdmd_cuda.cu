@@ -241,6 +241,7 @@ __global__ void k_cell_permute(DevP D, const int *sorted_atom, double *sx, doubl
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= D.n) return;
     int j = sorted_atom[p];
+    D.spos[j] = p;
     sx[p] = D.x[j]; sy[p] = D.y[j]; sz[p] = D.z[j];
     svx[p] = D.vx[j]; svy[p] = D.vy[j]; svz[p] = D.vz[j];
     stype[p] = D.type[j];
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(128) k_predict_all_round(DevP D, SlotBuf src, 
         double m2 = SD_INF;
         PairBest pb;
         if (round == 0) cur = d_predict_atom<true, true>(D, as_src(src), i, cur, g, 0, &np, &m2, &pb, D.surv ? p : -1);
-        else cur = d_predict_atom<true, false>(D, as_src(src), i, cur, g, i, &np, nullptr);
+        else cur = d_predict_atom<true, false>(D, as_src(src), i, cur, g, i, &np, nullptr, nullptr, D.surv ? D.spos[i] : -1);
         dst.time[i] = cur.time; dst.pot[i] = cur.pot; dst.partner[i] = cur.partner; dst.pcounter[i] = cur.pcounter;
         dst.type[i] = (uint8_t)cur.type; dst.sub[i] = (uint8_t)cur.sub;
         if (round == 0) {
@@ -942,6 +943,8 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     TRY(dalloc(c, &c->d_stype, n1));
     TRY(dalloc(c, &c->d_sum, 4));
     P.surv = nullptr; P.surv_n = nullptr; P.surv_np = nullptr;
+    TRY(dalloc(c, &P.spos, n1));
+    P.cut2_loose = P.cut2 * (1.0 + 1e-9);
     if (n < (1 << 27)) {
         TRY(dalloc(c, &P.surv, (size_t)R0_SURV_CAP * n1)); TRY(dalloc(c, &P.surv_n, n1)); TRY(dalloc(c, &P.surv_np, n1));
     }

@@ -107,6 +107,8 @@ struct DevP {
     unsigned int *surv;      // (sorted position of j) | (scan slot k << 27)
     int *surv_n;             // count, or -1 when the list overflowed (atom re-scanned in the evaluation kernel)
     int *surv_np;            // pair evaluations counted by the filter
+    int *spos;               // sorted position of every atom (inverse of sorted_atom)
+    double cut2_loose;       // cut2 * (1 + 1e-9): the filter keeps a superset, the evaluation re-tests exactly
 };
 
 // neighbour-cell offsets, DMD.c:118-120
@@ -574,7 +576,7 @@ __device__ inline void d_r0_filter(const DevP &D, int p_self) {
             double tx = D.sx[p] + shx, ty = D.sy[p] + shy, tz = D.sz[p] + shz;
             double rx = x - tx, ry = y - ty, rz = z - tz;
             double r2 = rx * rx + ry * ry + rz * rz;
-            if (r2 <= D.cut2) {
+            if (r2 <= D.cut2_loose) {
                 if (ns < R0_SURV_CAP) out[ns] = (unsigned)p | ((unsigned)k << 27);
                 ns++;
             }
@@ -584,20 +586,41 @@ __device__ inline void d_r0_filter(const DevP &D, int p_self) {
     D.surv_np[p_self] = npair;
 }
 
-// Round-0 stage 2 from the filter's list
-__device__ inline void d_collision_time_from_list(const DevP &D, const SlotSrc &S, Self &me, Slot &cur, int p_self) {
+// Stage 2 from the filter's list.  With DUP, entries whose partner's slot points back at this atom are tagged for
+// the in-order CheckDuplication test; such a partner is always in the list (it saw this atom inside the scan
+// sphere from its side, and the list is a superset of the sphere).
+template <bool DUP>
+__device__ inline void d_collision_time_from_list(const DevP &D, const SlotSrc &S, Self &me, Slot &cur, int p_self, int dup_limit) {
     int ns = D.surv_n[p_self];
     const unsigned int *in = D.surv + (size_t)p_self * R0_SURV_CAP;
-    bool has_cm = D.cm_off[me.i + 1] > D.cm_off[me.i];
-    int type_i = D.type[me.i];
+    int i = me.i;
+    bool has_cm = D.cm_off[i + 1] > D.cm_off[i];
+    int type_i = D.type[i];
+    int hb_i = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+    if (DUP) {
+        hb_i = D.hb_bond[i];
+        if (D.hydrogen_bond) { h0 = D.hbn_partner[5 * i + 1]; h1 = D.hbn_partner[5 * i + 2]; h2 = D.hbn_partner[5 * i + 3]; h3 = D.hbn_partner[5 * i + 4]; }
+    }
     int surv_p[R0_MAXSURV];
     unsigned char surv_k[R0_MAXSURV];
+    int ndup = 0;
     for (int s0 = 0; s0 < ns; s0 += R0_MAXSURV) {
         int m = ns - s0 < R0_MAXSURV ? ns - s0 : R0_MAXSURV;
-        for (int s = 0; s < m; s++) { unsigned v = in[s0 + s]; surv_p[s] = (int)(v & 0x7ffffffu); surv_k[s] = (unsigned char)(v >> 27); }
-        d_r0_flush(D, S, me, cur, surv_p, surv_k, m, has_cm, type_i, 0, 0, 0, 0, 0);
+        for (int s = 0; s < m; s++) {
+            unsigned v = in[s0 + s];
+            int p = (int)(v & 0x7ffffffu);
+            unsigned char tag = (unsigned char)(v >> 27);
+            if (DUP) {
+                int j = D.sorted_atom[p];
+                if (j < dup_limit && S.partner[j] == i && S.type[j] == SDMD_EV_COLI && S.pcounter[j] == me.counter) { tag |= R0_DUPFLAG; ndup++; }
+            }
+            surv_p[s] = p; surv_k[s] = tag;
+        }
+        d_r0_flush(D, S, me, cur, surv_p, surv_k, m, has_cm, type_i, hb_i, h0, h1, h2, h3);
     }
-    me.npair += D.surv_np[p_self];
+    // the filter counted every candidate that passes the skip filters; d_r0_flush re-counts tagged entries that were
+    // not copied, so take the tagged ones out once
+    me.npair += D.surv_np[p_self] - ndup;
 }
 
 // BondTime, TimePrediction.c:186-295
@@ -792,8 +815,9 @@ __device__ inline Slot d_predict_atom(const DevP &D, const SlotSrc &S, int i, Sl
     if (D.is_cons[i]) { cur.time = SD_INF; return cur; }
     Self me = d_load_self(D, i);
     if (!D.gel_mode) d_bond_time(D, S, me, cur, dup_limit);
-    if (R0 && surv_pos >= 0 && D.surv_n[surv_pos] >= 0) d_collision_time_from_list(D, S, me, cur, surv_pos);
+    if (R0 && surv_pos >= 0 && D.surv_n[surv_pos] >= 0) d_collision_time_from_list<false>(D, S, me, cur, surv_pos, 0);
     else if (R0) d_collision_time_2stage<false>(D, S, me, cur, 0);
+    else if (SORTED && surv_pos >= 0 && D.surv_n[surv_pos] >= 0) d_collision_time_from_list<true>(D, S, me, cur, surv_pos, dup_limit);
     else if (SORTED) d_collision_time_2stage<true>(D, S, me, cur, dup_limit);
     else d_collision_time(D, S, me, cur, dup_limit);
     if (pb) { pb->bp_time = cur.bp_time; pb->sp_time = cur.sp_time; pb->bp_j = cur.bp_j; }   // pair records in front of PCC
