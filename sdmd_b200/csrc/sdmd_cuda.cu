@@ -226,6 +226,28 @@ __global__ void k_cell_finish(DevP D, const int *cell_start, int *sorted_atom) {
     for (int a = p0; a < p1; a++) cl[sorted_atom[a]] = (a + 1 < p1) ? sorted_atom[a + 1] : 0;
 }
 
+// static neighbour table (see DevP::nbr)
+__global__ void k_build_nbr(DevP D, unsigned int *nbr) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)D.ncell * 27) return;
+    int c = (int)(t / 27), k = (int)(t % 27);
+    int nx = D.cellnum[0], ny = D.cellnum[1];
+    int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
+    int ncx, ncy, ncz;
+    int cell = d_neighbor_cell(D, cx, cy, cz, k, &ncx, &ncy, &ncz);
+    int ci[3] = {cx, cy, cz}, cj[3] = {ncx, ncy, ncz};
+    unsigned v = (unsigned)cell;
+    for (int d = 0; d < 3; d++) {
+        unsigned code = 0;
+        if (ci[d] != cj[d]) {
+            if (ci[d] == 0 && cj[d] == D.cellnum[d] - 1) code = 1;
+            else if (ci[d] == D.cellnum[d] - 1 && cj[d] == 0) code = 2;
+        }
+        v |= code << (26 + 2 * d);
+    }
+    nbr[t] = v;
+}
+
 // occupancy of every cell from an uploaded link list
 __global__ void k_cell_count(DevP D) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -498,36 +520,6 @@ __device__ inline void d_loop_head(const DevP &D, double t_until, i64 iter_limit
     c->dt = D.ev_time[target];
     int p = D.ev_partner[target];
     c->partner = p > 0 ? p : 0;
-}
-
-// loop body after the advance: HazardCheck, DoEvent, counters, Predict, UpdateCBT (SGThread.c:80-151)
-__device__ inline void d_loop_body_serial(const DevP &D, double t_until, sdmd_trace_rec *trace, i64 trace_cap) {
-    Ctl *c = D.ctl;
-    int target = c->target, partner = c->partner;
-    c->currenttime += c->dt;
-    int hazard = (partner > 0 && D.ev_pcounter[target] < D.ev_counter[partner]) ? -1 : 0;  // SGThread.c:224-227
-    if (trace && c->trace_pos < trace_cap) {
-        sdmd_trace_rec r;
-        r.frame = c->frame; r.target = target; r.partner = D.ev_partner[target];
-        r.type = D.ev_type[target]; r.sub = D.ev_sub[target]; r.executed = !hazard; r.pad_ = 0; r.dt = c->dt;
-        trace[c->trace_pos] = r;
-    }
-    c->trace_pos++;
-    c->iterations++;
-    if (!hazard) {
-        c->frame++;
-        d_do_event(D, target, partner);
-        D.ev_counter[target]++;
-        if (partner && !D.is_cons[partner]) D.ev_counter[partner]++;
-        d_predict_list_serial(D, target, partner);
-        d_cbt_update_run(D, target);
-        if (partner) d_cbt_update_run(D, partner);
-        if (c->currenttime >= t_until) c->stop = 1 + SDMD_STOP_T_UNTIL;
-    } else {
-        d_predict_list_serial(D, target, 0);
-        d_cbt_update_run(D, target);
-        c->count_recal++;
-    }
 }
 
 // publish the AssignJob result to the block (thread 0, before a barrier)
@@ -944,6 +936,14 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     TRY(dalloc(c, &c->d_sum, 4));
     P.surv = nullptr; P.surv_n = nullptr; P.surv_np = nullptr;
     TRY(dalloc(c, &P.spos, n1));
+    P.nbr = nullptr;
+    if ((long long)P.ncell < (1 << 26) && (long long)P.ncell * 27 * 4 <= (512LL << 20)) {
+        unsigned int *nbr = nullptr;
+        TRY(dalloc(c, &nbr, (size_t)P.ncell * 27));
+        long long tot = (long long)P.ncell * 27;
+        k_build_nbr<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(P, nbr);
+        P.nbr = nbr;
+    }
     P.cut2_loose = P.cut2 * (1.0 + 1e-9);
     if (n < (1 << 27)) {
         TRY(dalloc(c, &P.surv, (size_t)R0_SURV_CAP * n1)); TRY(dalloc(c, &P.surv_n, n1)); TRY(dalloc(c, &P.surv_np, n1));

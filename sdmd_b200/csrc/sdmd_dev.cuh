@@ -108,6 +108,9 @@ struct DevP {
     int *surv_n;             // count, or -1 when the list overflowed (atom re-scanned in the evaluation kernel)
     int *surv_np;            // pair evaluations counted by the filter
     int *spos;               // sorted position of every atom (inverse of sorted_atom)
+    // static neighbour table: for cell c and scan slot k (DMD.c:118-120 order) the neighbour cell (bits 0-25) and the
+    // minimum-image shift code per axis (2 bits each from bit 26: 0 none, 1 = -box, 2 = +box); NULL for huge grids
+    const unsigned int *nbr;
     double cut2_loose;       // cut2 * (1 + 1e-9): the filter keeps a superset, the evaluation re-tests exactly
 };
 
@@ -350,6 +353,25 @@ __device__ __forceinline__ int d_neighbor_cell(const DevP &D, int cx, int cy, in
     return nz * D.cellnum[0] * D.cellnum[1] + ny * D.cellnum[0] + nx;  // 0-based
 }
 
+// neighbour cell + PBCShift (ToolFunctions.c:801-817) of scan slot k, from the static table when present
+__device__ __forceinline__ int d_neighbor(const DevP &D, int cx, int cy, int cz, int k, double *shx, double *shy, double *shz) {
+    if (D.nbr) {
+        int c = cz * D.cellnum[0] * D.cellnum[1] + cy * D.cellnum[0] + cx;
+        unsigned v = __ldg(&D.nbr[(size_t)c * 27 + k]);
+        unsigned sx = (v >> 26) & 3, sy = (v >> 28) & 3, sz = (v >> 30) & 3;
+        *shx = sx == 0 ? 0.0 : (sx == 1 ? -1 * D.box[0] : D.box[0]);
+        *shy = sy == 0 ? 0.0 : (sy == 1 ? -1 * D.box[1] : D.box[1]);
+        *shz = sz == 0 ? 0.0 : (sz == 1 ? -1 * D.box[2] : D.box[2]);
+        return (int)(v & 0x3ffffffu);
+    }
+    int ncx, ncy, ncz;
+    int cell = d_neighbor_cell(D, cx, cy, cz, k, &ncx, &ncy, &ncz);
+    *shx = d_shift1(cx, ncx, D.cellnum[0], D.box[0]);
+    *shy = d_shift1(cy, ncy, D.cellnum[1], D.box[1]);
+    *shz = d_shift1(cz, ncz, D.cellnum[2], D.box[2]);
+    return cell;
+}
+
 struct Self {
     int i;
     double x, y, z, vx, vy, vz;
@@ -412,24 +434,6 @@ __device__ inline void d_collision_time(const DevP &D, const SlotSrc &S, Self &m
     }
 }
 
-// the same scan over the cell-sorted tiles cell_build produced (valid while the link list is fresh)
-__device__ inline void d_collision_time_sorted(const DevP &D, const SlotSrc &S, Self &me, Slot &cur, int dup_limit) {
-    for (int k = 0; k < 27; k++) {
-        int ncx, ncy, ncz;
-        int cell = d_neighbor_cell(D, me.cx, me.cy, me.cz, k, &ncx, &ncy, &ncz);
-        double shx = d_shift1(me.cx, ncx, D.cellnum[0], D.box[0]);
-        double shy = d_shift1(me.cy, ncy, D.cellnum[1], D.box[1]);
-        double shz = d_shift1(me.cz, ncz, D.cellnum[2], D.box[2]);
-        int p1 = D.cell_start[cell + 1];
-        for (int p = D.cell_start[cell]; p < p1; p++) {
-            int j = D.sorted_atom[p];
-            if (j == me.i) continue;
-            if (d_check_dup(D, S, cur, me.i, me.counter, j, SDMD_EV_COLI, dup_limit)) continue;
-            d_collision_candidate(D, me, cur, j, D.sx[p], D.sy[p], D.sz[p], D.svx[p], D.svy[p], D.svz[p], shx, shy, shz);
-        }
-    }
-}
-
 // CollisionTime for the full-system pass, round 0 (no duplicate source): the 27-cell scan is split into
 //   stage 1  a uniform loop over the cell-sorted tiles that applies the skip filters (TimePrediction.c:95-100),
 //            counts the pair evaluation (:105) and keeps only candidates inside the 0.9*cutoff sphere (:107);
@@ -446,11 +450,8 @@ __device__ __forceinline__ void d_r0_flush(const DevP &D, const SlotSrc &S, Self
         int p = surv_p[s];
         int k = surv_k[s] & 0x1f;
         int j = D.sorted_atom[p];
-        int ncx, ncy, ncz;
-        d_neighbor_cell(D, me.cx, me.cy, me.cz, k, &ncx, &ncy, &ncz);
-        double shx = d_shift1(me.cx, ncx, D.cellnum[0], D.box[0]);   // PBCShift via the scanned neighbour cell
-        double shy = d_shift1(me.cy, ncy, D.cellnum[1], D.box[1]);
-        double shz = d_shift1(me.cz, ncz, D.cellnum[2], D.box[2]);
+        double shx, shy, shz;   // PBCShift via the scanned neighbour cell
+        d_neighbor(D, me.cx, me.cy, me.cz, k, &shx, &shy, &shz);
         int cm = has_cm ? d_cm_flags(D, me.i, j) : 0;
         if (surv_k[s] & R0_DUPFLAG) {
             // CheckDuplication (TimePrediction.c:1101-1117) at this candidate's place in the scan
@@ -558,11 +559,8 @@ __device__ inline void d_r0_filter(const DevP &D, int p_self) {
     unsigned int *out = D.surv + (size_t)p_self * R0_SURV_CAP;
     int ns = 0, npair = 0;
     for (int k = 0; k < 27; k++) {
-        int ncx, ncy, ncz;
-        int cell = d_neighbor_cell(D, cx, cy, cz, k, &ncx, &ncy, &ncz);
-        double shx = d_shift1(cx, ncx, D.cellnum[0], D.box[0]);
-        double shy = d_shift1(cy, ncy, D.cellnum[1], D.box[1]);
-        double shz = d_shift1(cz, ncz, D.cellnum[2], D.box[2]);
+        double shx, shy, shz;
+        int cell = d_neighbor(D, cx, cy, cz, k, &shx, &shy, &shz);
         int p1 = D.cell_start[cell + 1];
         for (int p = D.cell_start[cell]; p < p1; p++) {
             if (p == p_self) continue;
@@ -1163,12 +1161,11 @@ __device__ inline void d_do_event(const DevP &D, int i, int j) {
 // whose partner's slot points back at this atom; the pieces in between collapse to their first minimum
 // (warp REDUX), and one lane replays the few pieces in order.
 //
-// The loop is latency bound (one event at a time), so everything an entry needs that depends only on the
-// predicted atom — minimum-image shifts of the 27 neighbour cells, its connectionMap row, its row of the
-// collision-table index, its HB lists — is staged in shared memory by the warp that lays the array out.
+// The loop is latency bound (one event at a time): the 27-cell candidate list of an atom is cached between link-list
+// changes, the minimum-image shifts of its 27 neighbour cells and its HB lists are staged in shared memory by the
+// warp that lays the array out, and the static connectionMap row is one load from a dense matrix (small systems).
 // ===================================================================================================
 #define PC_MAXC 448          // candidates per atom held in shared memory; larger neighbourhoods use the serial path
-#define PC_MAXADJ 64         // connectionMap row entries staged in shared memory
 enum { CK_BOND = 0, CK_COLL = 1, CK_PCC = 2, CK_THER = 3, CK_HB = 4, CK_HBFREE = 5, CK_HBNE = 6, CK_NONE = 7 };
 #define CF_VALID 1           // own-side event exists and its time is > 0
 #define CF_COUNTED 2         // a CalculateParameters-equivalent evaluation happened on the own-side path
@@ -1188,14 +1185,10 @@ struct PredShared {
     Slot result[2];
     int winner_pos[2];
     int npair[2];
-    int n_adj[2];
-    int adj_j[2][PC_MAXADJ];
-    int adj_f[2][PC_MAXADJ];     // connectionMap flags | (constraint table index << 8)
     int hbn[2][4];               // neighborPartner[1..4]
     int hb_bond[2];
     int cc_row[2];
     int n_pass[2];
-    int coll_row[2][SD_NT];      // coll_index[type_i][*]
     double shift[2][27][3];      // minimum-image shift of neighbour-cell slot k (PBCShift, ToolFunctions.c:801-817)
     int elig_n[2];
     int elig_pos[2][8];
@@ -1242,10 +1235,9 @@ __device__ __forceinline__ FindRes d_find_pair_table_fast(const DevP &D, const s
         return r;
     }
     int kk = ns;
-#pragma unroll
-    for (int k = SDMD_MAX_STEPS - 1; k >= 0; k--) {
-        double d = (k < ns) ? __ldg(&t->d2[k]) : 0.0;
-        if (k < ns && dist2 < d + tol) kk = k;
+    for (int k = ns - 1; k >= 0; k--) {   // first step with dist2 < d + tol (steps ascend, ToolFunctions.c:144-145)
+        double d = __ldg(&t->d2[k]);
+        if (dist2 < d + tol) kk = k;
     }
     r.lower = dmin2; r.lowPot = 0; r.upper = 0; r.upPot = 0; r.accum = 0;
     if (kk > 0) { r.lower = __ldg(&t->d2[kk - 1]); r.lowPot = __ldg(&t->e[kk - 1]); }

@@ -198,3 +198,73 @@ def test_remd_ensemble_gpu_matches_oracle(capi):
         gpu.reps[k].download(gpu_views[k])
         assert_fields_equal(gpu_views[k], cpu_views[k], STATE_FIELDS, what=f"replica {k}: ")
     assert any(rec[2] != k + 1 for k in range(3) for rec in gpu.log[k])
+
+
+def _oracle_vs_gpu(capi, hv0, gauss, iters, check_pairs=True):
+    from oracle.oracle_py import Oracle
+    ho = hv0.copy(); o = Oracle(ho); o.rng_feed(gauss)
+    hg = hv0.copy(); r = capi.Replica(hg, device=0); r.rng_feed(gauss)
+    o.pbc_full(); o.cell_build(); o.predict_all(); o.cbt_build()
+    r.pbc_full(); r.cell_build(); r.predict_all(); r.cbt_build()
+    assert np.array_equal(r.celllist(), o.celllist())
+    r.download(hg)
+    assert_fields_equal(hg, ho, SLOT_FIELDS + ("cell_idx",), what="after Predict(all): ")
+    assert np.array_equal(r.cbt()[0][1:], o.cbt()[0][1:])
+    if check_pairs:
+        assert r.stats()["pair_predictions"] == o.stats()["pair_predictions"]
+    so, to = o.run(max_iter=iters, trace_cap=iters)
+    sg, tg = r.run(max_iter=iters, trace_cap=iters)
+    assert so["stop_reason"] == sg["stop_reason"] == 2, (so, sg)
+    assert_trace_equal(tg, to)
+    r.download(hg)
+    assert_fields_equal(hg, ho, STATE_FIELDS, what="final state: ")
+    assert np.array_equal(r.celllist(), o.celllist())
+    assert np.array_equal(r.cbt()[0][1:], o.cbt()[0][1:])
+    for k in ("frame", "count_recal", "collision", "thermostat", "pcc", "pair_predictions", "gaussians_used"):
+        assert sg[k] == so[k], k
+    r.close()
+    return so
+
+
+@pytest.mark.parametrize("n_axis,a,iters", [
+    (3, 9.0, 3000),      # 27 atoms, 3x3x3 cells: every neighbour cell is a periodic image (cellnum == 3 wrap rules)
+    (4, 6.0, 3000),      # box 24 A -> cellnum clamps to 3 with cells larger than the cut-off
+    (12, 5.0, 4000),     # dense: ~6 atoms per cell, ~160 candidates per atom, many collisions and PCC events
+    (26, 5.0, 1500),     # dense and N > 8192: 128-entry cache rows overflow -> serial re-prediction fallback
+])
+def test_gel_edge_shapes_against_oracle(capi, n_axis, a, iters):
+    from sdmd_b200.synth import gel_box
+    hv0, rng = gel_box(n_axis, a=a, jitter=0.35, temperature=1.5)
+    gauss = rng.standard_normal(hv0.natom + 6 * iters + 1000)
+    so = _oracle_vs_gpu(capi, hv0, gauss, iters)
+    if n_axis == 12:
+        assert so["collision"] > 50 and so["pcc"] > 50
+
+
+def test_square_well_and_no_thermostat(capi):
+    """Attractive well (step e = -0.2, private copy of the GEL row) with the thermostat switched off: only
+    collision / capture / escape and cell-crossing events; no random stream is consumed."""
+    from sdmd_b200.synth import gel_box
+    hv0, rng = gel_box(10, a=5.5, jitter=0.3, temperature=1.0, step_e=-0.2)
+    hv0.thermostat_on = 0
+    so = _oracle_vs_gpu(capi, hv0, np.zeros(0), 4000)
+    assert so["thermostat"] == 0 and so["gaussians_used"] == 0 and so["collision"] > 500
+
+
+def test_run_stops_at_time_boundaries(capi):
+    """t_until / timestep semantics of the loop (SGThread.c:75,132): same stop points as the oracle."""
+    from oracle.oracle_py import Oracle
+    pre, _, _ = load_case("ala10")
+    ho = pre.copy(); ho.timestep = 3.0
+    hg = ho.copy()
+    o = Oracle(ho); o.rng_feed(pre.extra["gauss"])
+    r = capi.Replica(hg, device=0); r.rng_feed(pre.extra["gauss"])
+    o.set_celllist(pre.extra["celllist"]); o.predict_all(); o.cbt_build()
+    r.cell_build(); r.predict_all(); r.cbt_build()
+    for t_until in (0.5, 1.0, 2.5, 10.0):
+        so, _ = o.run(t_until=t_until)
+        sg, _ = r.run(t_until=t_until)
+        for k in ("frame", "iterations", "stop_reason"):
+            assert so[k] == sg[k], (t_until, k, so, sg)
+        assert np.float64(so["currenttime"]).tobytes() == np.float64(sg["currenttime"]).tobytes()
+    assert sg["stop_reason"] == 0   # currenttime > timestep ended the run
