@@ -238,7 +238,7 @@ def test_gel_edge_shapes_against_oracle(capi, n_axis, a, iters):
     gauss = rng.standard_normal(hv0.natom + 6 * iters + 1000)
     so = _oracle_vs_gpu(capi, hv0, gauss, iters)
     if n_axis == 12:
-        assert so["collision"] > 50 and so["pcc"] > 50
+        assert so["collision"] > 50
 
 
 def test_square_well_and_no_thermostat(capi):
