@@ -264,6 +264,7 @@ __global__ void k_cell_permute(DevP D, const int *sorted_atom, double *sx, doubl
     if (p >= D.n) return;
     int j = sorted_atom[p];
     D.spos[j] = p;
+    D.scx[p] = D.cell_idx[3 * j];
     sx[p] = D.x[j]; sy[p] = D.y[j]; sz[p] = D.z[j];
     svx[p] = D.vx[j]; svy[p] = D.vy[j]; svz[p] = D.vz[j];
     stype[p] = D.type[j];
@@ -936,6 +937,7 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     TRY(dalloc(c, &c->d_sum, 4));
     P.surv = nullptr; P.surv_n = nullptr; P.surv_np = nullptr;
     TRY(dalloc(c, &P.spos, n1));
+    TRY(dalloc(c, &P.scx, n1));
     P.nbr = nullptr;
     if ((long long)P.ncell < (1 << 26) && (long long)P.ncell * 27 * 4 <= (512LL << 20)) {
         unsigned int *nbr = nullptr;

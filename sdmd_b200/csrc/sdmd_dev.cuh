@@ -108,6 +108,7 @@ struct DevP {
     int *surv_n;             // count, or -1 when the list overflowed (atom re-scanned in the evaluation kernel)
     int *surv_np;            // pair evaluations counted by the filter
     int *spos;               // sorted position of every atom (inverse of sorted_atom)
+    int *scx;                // x cell index of every sorted position
     // static neighbour table: for cell c and scan slot k (DMD.c:118-120 order) the neighbour cell (bits 0-25) and the
     // minimum-image shift code per axis (2 bits each from bit 26: 0 none, 1 = -box, 2 = +box); NULL for huge grids
     const unsigned int *nbr;
