@@ -34,6 +34,9 @@ CASES = {
     "ala10": ("ref_harness", "ala10.gro", 3000, 8000, [], 0),
     "ala10_hb": ("ref_harness", "ala10.gro", 8000, 16000, ["--warm", "170000"], 0),
     "gel10": ("ref_harness_gel", "GEL10.gro", 3000, 12000, [], 10),
+    # 8 ala10 chains on a 2x2x2 grid (stand-in for the multi-peptide aggregation config: inter-chain collisions and
+    # hydrogen bonds, several proteins, N = 472); 4000 iterations
+    "ala10x8": ("ref_harness", "ala10x8.gro", 4000, 16000, [], -8),
 }
 
 
@@ -48,6 +51,27 @@ def write_gel_gro(path: Path, n: int, a_nm: float = 0.8):
                     f.write("%5iGEL%5s%5i%8.3f%8.3f%8.3f\n" % (k, "GEL", k, (m + 0.5) * a_nm, (j + 0.5) * a_nm, (i + 0.5) * a_nm))
                     k += 1
         f.write("%10.5f%10.5f%10.5f\n" % (n * a_nm, n * a_nm, n * a_nm))
+
+
+def write_multi_ala10(path: Path, src: Path, copies_per_axis: int = 2, spacing_nm: float = 2.4, box_nm: float = 9.0):
+    """copies_per_axis^3 translated copies of the reference's ala10.gro; residue numbers restart per chain, which
+    is how the reference's .gro reader tells chains apart (Initialization.c:949-960)."""
+    lines = src.read_text().splitlines()
+    atoms = lines[2:2 + int(lines[1])]
+    xyz = np.array([[float(a[20:28]), float(a[28:36]), float(a[36:44])] for a in atoms])
+    xyz -= xyz.mean(axis=0)
+    out, serial = [], 1
+    for cz in range(copies_per_axis):
+        for cy in range(copies_per_axis):
+            for cx in range(copies_per_axis):
+                shift = (np.array([cx, cy, cz]) + 0.5) * spacing_nm + (box_nm - copies_per_axis * spacing_nm) / 2
+                for a, p in zip(atoms, xyz + shift):
+                    out.append("%s%5d%8.3f%8.3f%8.3f" % (a[:15], serial, p[0], p[1], p[2]))
+                    serial += 1
+    with open(path, "w") as f:
+        f.write("8 x ala10\n%5d\n" % len(out))
+        f.write("\n".join(out) + "\n")
+        f.write("%10.5f%10.5f%10.5f\n" % (box_nm, box_nm, box_nm))
 
 
 def prepare_input(work: Path, time_units: float = 1000.0) -> Path:
@@ -74,8 +98,10 @@ def run_case(name: str, work: Path, harness=None, coord=None, max_iter=None, n_g
                                                            zip(spec, (harness, coord, max_iter, n_gauss, extra, gel_n))]
     work.mkdir(parents=True, exist_ok=True)
     inp = prepare_input(work)
-    if gel_n:
+    if gel_n and gel_n > 0:
         write_gel_gro(inp / coord, gel_n)
+    elif gel_n and gel_n < 0:
+        write_multi_ala10(inp / coord, inp / "ala10.gro")
     prefix = work / name
     cmd = [str(REFDIR / harness), str(prefix), str(max_iter), str(n_gauss), *extra, "--",
            "-f", coord, "-i", str(inp), "-o", str(work / "out")]

@@ -885,8 +885,13 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     }
     TRY(dalloc(c, &P.cell_cnt, (size_t)P.ncell + 1));
     // per-atom candidate-list cache for the event loop (small and medium systems)
-    P.cc_per_atom = (n <= 65536);
-    P.cc_cap = (n <= 8192) ? 256 : (n <= 65536 ? 128 : 256);
+    {
+        // row capacity from the mean neighbourhood size (27 cells) with head-room; one row per atom while that fits 8 GB
+        double need = 27.0 * (double)n / (double)P.ncell * 1.6 + 24.0;
+        P.cc_cap = need <= 64 ? 64 : (need <= 128 ? 128 : 256);
+        P.cc_per_atom = ((double)n1 * P.cc_cap * 6.0 <= 8.0e9);
+        if (!P.cc_per_atom) P.cc_cap = 256;
+    }
     {
         size_t rows = P.cc_per_atom ? n1 : 2;
         TRY(dalloc(c, &P.cc_stamp, n1)); TRY(dalloc(c, &P.cc_n, n1));

@@ -22,7 +22,7 @@ def _replica(capi, pre):
     return hv, r
 
 
-@pytest.mark.parametrize("case", ["ala10", "gel10"])
+@pytest.mark.parametrize("case", ["ala10", "gel10", "ala10x8"])
 def test_cell_build_matches_reference(capi, case):
     pre, post, fin = load_case(case)
     hv, r = _replica(capi, pre)
@@ -34,7 +34,7 @@ def test_cell_build_matches_reference(capi, case):
     assert_fields_equal(hv, pre, ("cell_idx", "x", "y", "z"))
 
 
-@pytest.mark.parametrize("case", ["ala10", "gel10"])
+@pytest.mark.parametrize("case", ["ala10", "gel10", "ala10x8"])
 def test_predict_all_and_cbt_match_reference(capi, case):
     pre, post, fin = load_case(case)
     hv, r = _replica(capi, pre)
@@ -50,7 +50,7 @@ def test_predict_all_and_cbt_match_reference(capi, case):
     assert r.kinetic_energy() == post.extra["ekin"][0]
 
 
-@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10"])
+@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8"])
 def test_device_event_loop_matches_reference(capi, case):
     pre, post, fin = load_case(case)
     hv, r = _replica(capi, pre)

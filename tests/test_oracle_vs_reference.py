@@ -19,7 +19,7 @@ def _prepare(pre):
     return hv, o
 
 
-@pytest.mark.parametrize("case", ["ala10", "gel10"])
+@pytest.mark.parametrize("case", ["ala10", "gel10", "ala10x8"])
 def test_cell_grid_and_link_list(case):
     pre, post, fin = load_case(case)
     hv, o = _prepare(pre)
@@ -32,7 +32,7 @@ def test_cell_grid_and_link_list(case):
     assert_fields_equal(hv, pre, ("cell_idx", "x", "y", "z"))
 
 
-@pytest.mark.parametrize("case", ["ala10", "gel10"])
+@pytest.mark.parametrize("case", ["ala10", "gel10", "ala10x8"])
 def test_predict_all_and_cbt(case):
     pre, post, fin = load_case(case)
     hv, o = _prepare(pre)
@@ -47,7 +47,7 @@ def test_predict_all_and_cbt(case):
     assert o.kinetic_energy() == post.extra["ekin"][0]
 
 
-@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10"])
+@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8"])
 def test_event_loop_trace(case):
     pre, post, fin = load_case(case)
     hv, o = _prepare(pre)
