@@ -1,97 +1,161 @@
 /*
  * sdmd_dropin.c — the reference's driver with the hot path on the GPU.
  *
- * Compiled together with the UNMODIFIED reference sources (see sdmd_b200/host/Makefile): the only change to the
- * reference build is `-DSingleThread=sdmd_reference_SingleThread` on SGThread.c, so that ThreadProcess()
- * (ToolFunctions.c:12-20) reaches the SingleThread() defined here instead.  Everything around the hot path — CLI,
- * parameter.txt / .gro parsing, force-field library, SDEnergyMin, every output file — is the reference's own code.
+ * Compiled together with the UNMODIFIED reference sources (see sdmd_b200/host/Makefile).  The only change to the
+ * reference build is two renames on the compiler command line: SGThread.c gets -DSingleThread=sdmd_reference_SingleThread
+ * and REMD.c gets -DREMD=sdmd_reference_REMD, so that ThreadProcess() (ToolFunctions.c:12-20) reaches the
+ * SingleThread() / REMD() defined here.  Everything around the hot path — CLI, parameter.txt / .gro parsing,
+ * force-field library, SDEnergyMin, checkpoint reader, every output file, the REMD socket client and the sServer /
+ * sREMD programs — is the reference's own code.
  *
- * SingleThread() below = Prepare() + SingleThreadRun() (SGThread.c:15-156) with
- *   PBC("full") / LinkList("full") / Predict(all) / CreateCBT        -> sdmd_cuda_pbc_full / cell_build / predict_all / cbt_build
- *   the while-loop (AssignJob ... UpdateCBT, DoEvent included)        -> sdmd_cuda_run(ctx, outputrecord, ...)
- *   SaveData(...) every outputrate                                    -> unchanged, after sdmd_cuda_download + scatter
+ *   Prepare()           SGThread.c:21-64   PBC/LinkList/Predict(all)/CreateCBT -> sdmd_cuda_pbc_full / cell_build /
+ *                                          predict_all / cbt_build ("continue": upload_celllist + cbt_build)
+ *   SingleThreadRun()   SGThread.c:67-156  the while-loop incl. DoEvent        -> sdmd_cuda_run(ctx, next boundary)
+ *   REMDRun()           REMD.c:29-126      + CalPotenE                          -> sdmd_cuda_potential_energy
+ *                                          + ReplicaExchange (reference's socket client, unchanged)
+ *   SaveData(...)                          unchanged, after sdmd_cuda_download + scatter
  */
 #include "DMD.h"
 #include "sdmd_refglue.h"
+
+/* the reference's socket client, REMD.c:135-192 (external linkage there, no prototype in DMD.h) */
+void ReplicaExchange(double *E, struct REMDTempStr *T, char *serverName, int *port_number);
+
+static struct sdmd_host_view view;
+static sdmd_ctx *ctx;
+static long base_counts[8];
 
 static void die(const char *what, int rc) {
     printf("!!ERROR!!: %s failed (%d): %s\n", what, rc, sdmd_cuda_last_error());
     exit(EXIT_FAILURE);
 }
 
-static void sync_to_reference(sdmd_ctx *ctx, struct sdmd_host_view *v) {
-    int rc = sdmd_cuda_download(ctx, v);
+static void sync_to_reference(void) {
+    int rc = sdmd_cuda_download(ctx, &view);
     if (rc) die("sdmd_cuda_download", rc);
-    sdmd_glue_scatter_dynamic(v);
+    sdmd_glue_scatter_dynamic(&view);
     rc = sdmd_cuda_download_celllist(ctx, celllist);
     if (rc) die("sdmd_cuda_download_celllist", rc);
     struct sdmd_run_stats st;
     sdmd_cuda_get_stats(ctx, &st);
     frame = st.frame;
     currenttime = st.currenttime;
-    countReCal = st.count_recal;
-    collisioneventsum = st.collision; bondeventsum = st.bond; HBeventsum = st.hb; HBNeighboreventsum = st.hb_neighbor;
-    thermostateventsum = st.thermostat; pbcandcrosseventsum = st.pcc;
+    countReCal = base_counts[0] + st.count_recal;
+    collisioneventsum = base_counts[1] + st.collision;
+    bondeventsum = base_counts[2] + st.bond;
+    HBeventsum = base_counts[3] + st.hb;
+    HBNeighboreventsum = base_counts[4] + st.hb_neighbor;
+    thermostateventsum = base_counts[5] + st.thermostat;
+    pbcandcrosseventsum = base_counts[6] + st.pcc;
 }
 
-void SingleThread(void) {
-    /* ---- Prepare(), SGThread.c:21-64 ---- */
+/* Prepare(), SGThread.c:21-64 */
+static void prepare_cuda(void) {
     char *extraName = REMDInfo.flag ? REMDInfo.REMD_ExtraName : NULL;
     InitializeFiles(extraName, fileList);
     SaveData(lgf, fileList);
     atomList.ptr = (struct AtomStr **)calloc(atomnum + 1, sizeof(struct AtomStr *));
     for (int i = 1; i <= atomnum; i++) atomList.ptr[i] = &atom[i];
-    if (strcmp("new", neworcontinue) != 0) {
-        printf("!!ERROR!!: the CUDA drop-in starts \"new\" runs only\n");
+    int fresh = strcmp("new", neworcontinue) == 0;
+    if (fresh) {
+        SaveData(sysInfo, fileList);
+#ifndef GEL
+        SDEnergyMin(20000, &atomList);
+#endif
+    } else if (strcmp("continue", neworcontinue) == 0) {
+        outputrecord = currenttime + outputrate;
+    } else {
+        printf("!!ERROR!!: the simulation configuration is invalid!\n");
         exit(EXIT_FAILURE);
     }
-    SaveData(sysInfo, fileList);
-#ifndef GEL
-    SDEnergyMin(20000, &atomList);
-#endif
+    base_counts[0] = countReCal; base_counts[1] = collisioneventsum; base_counts[2] = bondeventsum;
+    base_counts[3] = HBeventsum; base_counts[4] = HBNeighboreventsum; base_counts[5] = thermostateventsum;
+    base_counts[6] = pbcandcrosseventsum;
 
-    struct sdmd_host_view view;
     int rc = sdmd_glue_flatten(&view);
     if (rc) die("sdmd_glue_flatten (feature outside the hot-path scope?)", rc);
-    sdmd_ctx *ctx = NULL;
     rc = sdmd_cuda_create(&view, 0, &ctx);
     if (rc) die("sdmd_cuda_create", rc);
     int cn[3];
     double cs[3];
     sdmd_cuda_cell_grid(ctx, cn, cs);
     if (cn[0] != cellnum[1] || cn[1] != cellnum[2] || cn[2] != cellnum[3]) die("cell grid mismatch with CreateCell", -1);
-    INT_CALLOC(celllist, (atomnum + cellnum[1] * cellnum[2] * cellnum[3] + 1));
-
-    if ((rc = sdmd_cuda_pbc_full(ctx))) die("pbc_full", rc);
-    if ((rc = sdmd_cuda_cell_build(ctx))) die("cell_build", rc);
-    if ((rc = sdmd_cuda_rng_fill_libc(ctx, atomnum))) die("rng_fill", rc);   /* ThermostatTime draws of Predict(all) */
-    if ((rc = sdmd_cuda_predict_all(ctx))) die("predict_all", rc);
+    if (fresh) {
+        INT_CALLOC(celllist, (atomnum + cellnum[1] * cellnum[2] * cellnum[3] + 1));
+        if ((rc = sdmd_cuda_pbc_full(ctx))) die("pbc_full", rc);
+        if ((rc = sdmd_cuda_cell_build(ctx))) die("cell_build", rc);
+        if ((rc = sdmd_cuda_rng_fill_libc(ctx, atomnum))) die("rng_fill", rc);   /* ThermostatTime draws of Predict(all) */
+        if ((rc = sdmd_cuda_predict_all(ctx))) die("predict_all", rc);
+    } else {
+        /* savedData.dat carries every atom's pending event and the link list (Initialization.c:360-509) */
+        if ((rc = sdmd_cuda_upload_celllist(ctx, celllist))) die("upload_celllist", rc);
+    }
     if ((rc = sdmd_cuda_cbt_build(ctx))) die("cbt_build", rc);
+}
 
-    /* ---- SingleThreadRun(), SGThread.c:67-156 ---- */
+static void save_outputs(void) {
+    sync_to_reference();
+    for (int i = 0; i < lenFileType; i++)
+        if (fileList[i].mark) SaveData(i, fileList);
+    outputrecord += outputrate;
+}
+
+/* run to `boundary`; returns the stop reason once it is TIME_END or T_UNTIL */
+static int run_to(double boundary, struct sdmd_run_stats *st, double *gap) {
     const int64_t chunk = 200000;        /* gaussians generated ahead per refill */
+    for (;;) {
+        int rc;
+        if (sdmd_cuda_rng_available(ctx) < chunk / 2 && (rc = sdmd_cuda_rng_fill_libc(ctx, chunk))) die("rng_fill", rc);
+        rc = sdmd_cuda_run(ctx, boundary, (int64_t)1 << 40, NULL, 0, st);
+        if (rc) die("sdmd_cuda_run", rc);
+        currenttime = st->currenttime;
+        double processratio = (currenttime - oldcurrenttime) / (timestep - oldcurrenttime) * 100;
+        if (processratio >= *gap + 0.01) { printf("Process=%8.2lf%%\r", processratio); fflush(stdout); *gap = processratio; }
+        if (st->stop_reason == SDMD_STOP_NEED_RNG) continue;
+        if (st->stop_reason == SDMD_STOP_T_UNTIL || st->stop_reason == SDMD_STOP_TIME_END) return st->stop_reason;
+        die("unexpected stop", st->stop_reason);
+    }
+}
+
+/* SingleThread(), SGThread.c:15-19 */
+void SingleThread(void) {
+    prepare_cuda();
+    struct sdmd_run_stats st;
+    memset(&st, 0, sizeof(st));
+    double gap = 0;
+    while (run_to(outputrecord, &st, &gap) == SDMD_STOP_T_UNTIL) save_outputs();   /* SGThread.c:132-139 */
+    sync_to_reference();
+    warningsum += st.warnings;
+    sdmd_cuda_destroy(ctx);
+}
+
+/* REMD(), REMD.c:24-126 */
+void REMD(void) {
+    prepare_cuda();
+    int outputRate = REMDInfo.REMD_OutputRate;
+    int rate = ((int)(currenttime / outputRate) + 1) * outputRate;      /* REMD.c:32 */
     struct sdmd_run_stats st;
     memset(&st, 0, sizeof(st));
     double gap = 0;
     for (;;) {
-        if (sdmd_cuda_rng_available(ctx) < chunk / 2 && (rc = sdmd_cuda_rng_fill_libc(ctx, chunk))) die("rng_fill", rc);
-        rc = sdmd_cuda_run(ctx, outputrecord, (int64_t)1 << 40, NULL, 0, &st);
-        if (rc) die("sdmd_cuda_run", rc);
-        currenttime = st.currenttime;
-        double processratio = (currenttime - oldcurrenttime) / (timestep - oldcurrenttime) * 100;
-        if (processratio >= gap + 0.01) { printf("Process=%8.2lf%%\r", processratio); fflush(stdout); gap = processratio; }
-        if (st.stop_reason == SDMD_STOP_T_UNTIL) {      /* currenttime >= outputrecord, SGThread.c:132-139 */
-            sync_to_reference(ctx, &view);
-            for (int i = 0; i < lenFileType; i++)
-                if (fileList[i].mark) SaveData(i, fileList);
-            outputrecord += outputrate;
-        } else if (st.stop_reason == SDMD_STOP_TIME_END) {
-            break;
-        } else if (st.stop_reason != SDMD_STOP_NEED_RNG) {
-            die("unexpected stop", st.stop_reason);
+        double boundary = outputrecord < rate ? outputrecord : (double)rate;
+        if (run_to(boundary, &st, &gap) != SDMD_STOP_T_UNTIL) break;
+        if (currenttime >= outputrecord) save_outputs();                 /* REMD.c:88-95 */
+        if (currenttime >= rate) {                                       /* REMD.c:97-104 */
+            double potenEnergy;
+            int rc = sdmd_cuda_potential_energy(ctx, &potenEnergy);
+            if (rc) die("potential_energy", rc);
+            ReplicaExchange(&potenEnergy, &REMDInfo.REMD_Temperature, REMDInfo.REMD_ServerName, &REMDInfo.REMD_PortNum);
+            targetTemperature = REMDInfo.REMD_Temperature.T;
+            sdmd_cuda_set_temperature(ctx, targetTemperature);
+            SaveData(RE, fileList);
+            rate += outputRate;
         }
     }
-    sync_to_reference(ctx, &view);
+    sync_to_reference();
     warningsum += st.warnings;
+    tmpDouble = 0.0;                                                     /* REMD.c:119-122 */
+    REMDInfo.REMD_Temperature.T = 0.0;
+    ReplicaExchange(&tmpDouble, &REMDInfo.REMD_Temperature, REMDInfo.REMD_ServerName, &REMDInfo.REMD_PortNum);
     sdmd_cuda_destroy(ctx);
 }

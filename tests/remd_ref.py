@@ -37,7 +37,7 @@ def remd_args(port, T, num, rate, rid):
     return ["-REMD", "localhost", str(port), "%lf" % T, str(num), str(int(rate)), str(rid)]
 
 
-def run_reference_remd(work: Path, nrep: int, rate: float, time_units: float, server_seed: int):
+def run_reference_remd(work: Path, nrep: int, rate: float, time_units: float, server_seed: int, binary=None):
     """Returns the text of out_REMD<id>.txt per replica (SaveRE, DataSave.c:687-700)."""
     port = free_port()
     server = subprocess.Popen([str(REF / "sServer"), str(port), str(nrep), str(server_seed)], stdout=subprocess.PIPE,
@@ -48,7 +48,7 @@ def run_reference_remd(work: Path, nrep: int, rate: float, time_units: float, se
         d = work / f"ref{r}"
         inp = _input_dir(d, time_units)
         T = reduced_temperature(TEMPS_K[r])
-        procs.append(subprocess.Popen([str(REF / "sDMD_ref"), "-i", str(inp), "-f", "ala10.gro", "-o", str(d / "out"),
+        procs.append(subprocess.Popen([str(binary or REF / "sDMD_ref"), "-i", str(inp), "-f", "ala10.gro", "-o", str(d / "out"),
                                        *remd_args(port, T, r + 1, rate, r)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
         time.sleep(1.0)   # sREMD staggers the replicas the same way (REMDExec.c:133): connection order = replica id
     for p in procs:

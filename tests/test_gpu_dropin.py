@@ -47,3 +47,49 @@ def test_dropin_driver_writes_identical_outputs(tmp_path):
                 "PBC&CC times"):
         assert _counter(ref_out, key) == _counter(gpu_out, key), key
     assert _counter(gpu_out, "bond times") > 100000
+
+
+def _set_param(work, line_no, text):
+    p = work / "input" / "parameter.txt"
+    lines = p.read_text().splitlines()
+    lines[line_no] = text
+    p.write_text("\n".join(lines) + "\n")
+
+
+def test_dropin_continue_run_matches_reference(tmp_path):
+    """`continue` runs (parameter.txt line 1, the annealing schedule of demo/Folding/fold.bash): 100 time units new,
+    then continued to 200 from savedData.dat — the drop-in's second leg must write what the reference's writes."""
+    if not (REF / "sDMD_ref").exists() or not DROPIN.exists():
+        pytest.skip("needs oracle/_ref/sDMD_ref and the drop-in driver")
+    outs = {}
+    for tag, binary in (("ref", REF / "sDMD_ref"), ("gpu", DROPIN)):
+        work = tmp_path / tag
+        _run(REF / "sDMD_ref", work, 100)          # identical first leg from the stock binary
+        _set_param(work, 0, "Continue?          continue")
+        _set_param(work, 1, "Time               200")
+        r = subprocess.run([str(binary), "-f", "ala10.gro", "-i", str(work / "input"), "-o", str(work / "out")],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs[tag] = r.stdout.replace("\r", "\n")
+    for name in ("out_trj.gro", "out_cnt.txt"):
+        a = (tmp_path / "ref" / "out" / name).read_bytes()
+        b = (tmp_path / "gpu" / "out" / name).read_bytes()
+        assert len(a) > 1000 and a == b, name
+    for key in ("collision times", "bond times", "thermostat times", "PBC&CC times"):
+        assert _counter(outs["ref"], key) == _counter(outs["gpu"], key), key
+
+
+def test_dropin_remd_with_reference_server(tmp_path):
+    """demo/REMD-style run with the reference's own sServer: three replica processes of the drop-in driver (sharing
+    the GPU) must log the same temperature walk (out_REMD<id>.txt) and trajectories as three stock sDMD processes."""
+    if not (REF / "sServer").exists() or not DROPIN.exists():
+        pytest.skip("needs oracle/_ref and the drop-in driver")
+    from tests.remd_ref import run_reference_remd
+    ref_logs, _ = run_reference_remd(tmp_path / "r", 3, 5.0, 40.0, 99)
+    gpu_logs, _ = run_reference_remd(tmp_path / "g", 3, 5.0, 40.0, 99, binary=DROPIN)
+    assert ref_logs == gpu_logs
+    assert len(ref_logs[0].splitlines()) >= 7
+    for k in range(3):
+        a = (tmp_path / "r" / f"ref{k}" / "out").glob("out_trj*")
+        b = (tmp_path / "g" / f"ref{k}" / "out").glob("out_trj*")
+        assert next(a).read_bytes() == next(b).read_bytes()
