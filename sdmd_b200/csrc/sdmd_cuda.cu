@@ -599,10 +599,15 @@ __device__ inline void d_loop_body_cta(const DevP &D, PredShared &sh, double t_u
 }
 
 // Small systems: the whole loop in ONE persistent CTA (one replica per CTA); no host round trip per event.
-__global__ void __launch_bounds__(256, 1) k_run_cta(DevP D, double t_until, i64 iter_limit, sdmd_trace_rec *trace, i64 trace_cap) {
+__global__ void __launch_bounds__(256, 1) k_run_cta(DevP Dg, double t_until, i64 iter_limit, sdmd_trace_rec *trace, i64 trace_cap) {
     __shared__ PredShared sh;
+    __shared__ Ctl s_ctl;      // the loop state lives in shared memory while the kernel runs (written back on exit)
     __shared__ double s_dt;
     __shared__ int s_stop;
+    for (int k = threadIdx.x; k < (int)(sizeof(Ctl) / sizeof(int)); k += blockDim.x) ((int *)&s_ctl)[k] = ((const int *)Dg.ctl)[k];
+    __syncthreads();
+    DevP D = Dg;
+    D.ctl = &s_ctl;
     for (;;) {
         long long h0 = clock64();
         if (threadIdx.x == 0) {
@@ -625,6 +630,8 @@ __global__ void __launch_bounds__(256, 1) k_run_cta(DevP D, double t_until, i64 
         if (threadIdx.x == 0) { D.ctl->phase_cycles[0] += h1 - h0; D.ctl->phase_cycles[1] += d_clock_after(&s_stop) - h1; }
         d_loop_body_cta(D, sh, t_until, trace, trace_cap);
     }
+    __syncthreads();
+    for (int k = threadIdx.x; k < (int)(sizeof(Ctl) / sizeof(int)); k += blockDim.x) ((int *)Dg.ctl)[k] = ((const int *)&s_ctl)[k];
 }
 
 // Many replicas per GPU (REMD ensembles, parameter sweeps): one persistent CTA per replica, all in one launch.
@@ -644,6 +651,12 @@ __global__ void __launch_bounds__(256, 2) k_run_cta_multi(const MultiArg *args) 
         int *dst = (int *)&sA;
         for (int k = threadIdx.x; k < (int)(sizeof(MultiArg) / sizeof(int)); k += blockDim.x) dst[k] = src[k];
     }
+    __syncthreads();
+    __shared__ Ctl s_ctl;
+    Ctl *g_ctl = sA.P.ctl;
+    for (int k = threadIdx.x; k < (int)(sizeof(Ctl) / sizeof(int)); k += blockDim.x) ((int *)&s_ctl)[k] = ((const int *)g_ctl)[k];
+    __syncthreads();
+    if (threadIdx.x == 0) sA.P.ctl = &s_ctl;
     __syncthreads();
     const DevP &D = sA.P;
     double t_until = sA.t_until;
@@ -667,6 +680,8 @@ __global__ void __launch_bounds__(256, 2) k_run_cta_multi(const MultiArg *args) 
         __syncthreads();
         d_loop_body_cta(D, sh, t_until, nullptr, 0);
     }
+    __syncthreads();
+    for (int k = threadIdx.x; k < (int)(sizeof(Ctl) / sizeof(int)); k += blockDim.x) ((int *)g_ctl)[k] = ((const int *)&s_ctl)[k];
 }
 __global__ void k_potential_energy_multi(const MultiArg *args, double *out);
 
