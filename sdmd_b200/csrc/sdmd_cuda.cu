@@ -729,46 +729,95 @@ __global__ void k_cell_move(DevP D, int atom) { d_pcc_event(D, atom); }
 
 // CalPotenE, ToolFunctions.c:659-752: the accumulation order is part of the result, so one thread adds the
 // pair terms in the reference's order
-__device__ inline double d_potential_energy(const DevP &D) {
-    double TPE = 0, accum = 0;
-    for (int i = 1; i <= D.n; i++) {
-        int cx = D.cell_idx[3 * i], cy = D.cell_idx[3 * i + 1], cz = D.cell_idx[3 * i + 2];
-        double xi = D.x[i], yi = D.y[i], zi = D.z[i];
-        for (int n = 0; n < 27; n++) {
-            int nx = cx + c_offx[n], ny = cy + c_offy[n], nz = cz + c_offz[n];
-            double shx = 0, shy = 0, shz = 0;
-            if (nx < 0) { nx = D.cellnum[0] - 1; shx = -1 * D.box[0]; } else if (nx >= D.cellnum[0]) { nx = 0; shx = D.box[0]; }
-            if (ny < 0) { ny = D.cellnum[1] - 1; shy = -1 * D.box[1]; } else if (ny >= D.cellnum[1]) { ny = 0; shy = D.box[1]; }
-            if (nz < 0) { nz = D.cellnum[2] - 1; shz = -1 * D.box[2]; } else if (nz >= D.cellnum[2]) { nz = 0; shz = D.box[2]; }
-            int cell = nz * D.cellnum[0] * D.cellnum[1] + ny * D.cellnum[0] + nx;
-            for (int pair = D.celllist[D.n + cell + 1]; pair != 0; pair = D.celllist[pair]) {
-                if (pair <= i) continue;
-                double tx = D.x[pair] + shx, ty = D.y[pair] + shy, tz = D.z[pair] + shz;
-                double rx = xi - tx, ry = yi - ty, rz = zi - tz;
-                double d2 = rx * rx + ry * ry + rz * rz;
-                int cm = d_cm_flags(D, i, pair);
-                if (d2 <= D.cutfull2 && !(cm & SDMD_BOND_CONNECT)) {
-                    int ai = i, aj = pair, hbp = 0, mode;
-                    if (D.hb_bond[ai] == aj) { mode = FP_HB; TPE -= d_hb_barrier(D, ai, aj); }
-                    else if (cm & SDMD_CONSTRAINT_CONNECT) mode = FP_CONSTRAINT;
-                    else if (d_neighbor_connected(D, ai, aj)) {
-                        if (D.hb_neighbor[D.hb_bond[ai]] == aj) { int s = ai; ai = aj; aj = s; }
-                        hbp = D.hb_bond[aj];
-                        mode = FP_NEIGHBOR;
-                    } else mode = FP_COLLISION;
-                    double wx = D.vx[ai] - D.vx[aj], wy = D.vy[ai] - D.vy[aj], wz = D.vz[ai] - D.vz[aj];
-                    double direction = rx * wx + ry * wy + rz * wz;
-                    accum = d_find_pair(D, ai, aj, mode, direction, d2, hbp, 0).accum;
-                    if (accum < SD_INF / 2) TPE += accum;
-                }
+// The addends atom i contributes to CalPotenE (ToolFunctions.c:678-749), in the reference's order.  The energy is a
+// running sum over all of them in atom order, so the ORDER is part of the result: WRITE = false counts the non-zero
+// addends, WRITE = true stores them (adding +-0.0 never changes a sum that started at +0.0, so zeros are dropped).
+template <bool WRITE>
+__device__ inline int d_potential_terms(const DevP &D, int i, double *out) {
+    int cnt = 0;
+    double accum = 0;
+    int cx = D.cell_idx[3 * i], cy = D.cell_idx[3 * i + 1], cz = D.cell_idx[3 * i + 2];
+    double xi = D.x[i], yi = D.y[i], zi = D.z[i];
+    for (int n = 0; n < 27; n++) {
+        int nx = cx + c_offx[n], ny = cy + c_offy[n], nz = cz + c_offz[n];
+        double shx = 0, shy = 0, shz = 0;
+        if (nx < 0) { nx = D.cellnum[0] - 1; shx = -1 * D.box[0]; } else if (nx >= D.cellnum[0]) { nx = 0; shx = D.box[0]; }
+        if (ny < 0) { ny = D.cellnum[1] - 1; shy = -1 * D.box[1]; } else if (ny >= D.cellnum[1]) { ny = 0; shy = D.box[1]; }
+        if (nz < 0) { nz = D.cellnum[2] - 1; shz = -1 * D.box[2]; } else if (nz >= D.cellnum[2]) { nz = 0; shz = D.box[2]; }
+        int cell = nz * D.cellnum[0] * D.cellnum[1] + ny * D.cellnum[0] + nx;
+        for (int pair = D.celllist[D.n + cell + 1]; pair != 0; pair = D.celllist[pair]) {
+            if (pair <= i) continue;
+            double tx = D.x[pair] + shx, ty = D.y[pair] + shy, tz = D.z[pair] + shz;
+            double rx = xi - tx, ry = yi - ty, rz = zi - tz;
+            double d2 = rx * rx + ry * ry + rz * rz;
+            int cm = d_cm_flags(D, i, pair);
+            if (d2 <= D.cutfull2 && !(cm & SDMD_BOND_CONNECT)) {
+                int ai = i, aj = pair, hbp = 0, mode;
+                if (D.hb_bond[ai] == aj) {
+                    mode = FP_HB;
+                    double bar = d_hb_barrier(D, ai, aj);
+                    if (bar != 0) { if (WRITE) out[cnt] = -bar; cnt++; }     // TPE -= HBBarrier(...)
+                } else if (cm & SDMD_CONSTRAINT_CONNECT) mode = FP_CONSTRAINT;
+                else if (d_neighbor_connected(D, ai, aj)) {
+                    if (D.hb_neighbor[D.hb_bond[ai]] == aj) { int s = ai; ai = aj; aj = s; }
+                    hbp = D.hb_bond[aj];
+                    mode = FP_NEIGHBOR;
+                } else mode = FP_COLLISION;
+                double wx = D.vx[ai] - D.vx[aj], wy = D.vy[ai] - D.vy[aj], wz = D.vz[ai] - D.vz[aj];
+                double direction = rx * wx + ry * wy + rz * wz;
+                accum = d_find_pair(D, ai, aj, mode, direction, d2, hbp, 0).accum;
+                if (accum < SD_INF / 2 && accum != 0) { if (WRITE) out[cnt] = accum; cnt++; }
             }
+        }
+    }
+    return cnt;
+}
+
+// small systems: one thread walks everything in order
+__device__ inline double d_potential_energy(const DevP &D) {
+    double TPE = 0;
+    double buf[64];
+    for (int i = 1; i <= D.n; i++) {
+        int cnt = d_potential_terms<false>(D, i, nullptr);
+        if (cnt <= 64) {
+            d_potential_terms<true>(D, i, buf);
+            for (int k = 0; k < cnt; k++) TPE += buf[k];
+        } else {
+            D.ctl->error = SDMD_ERR_STATE;   // more addends than any physical neighbourhood produces
         }
     }
     return TPE;
 }
+// large systems: addends produced by one thread per atom (count, scan, write), summed in order by one warp
+__global__ void k_pe_count(DevP D, int *count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i <= D.n) count[i - 1] = d_potential_terms<false>(D, i, nullptr);
+}
+__global__ void k_pe_write(DevP D, const int *offset, double *terms) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i <= D.n) d_potential_terms<true>(D, i, terms + offset[i - 1]);
+}
+__global__ void k_ordered_sum(const double *terms, const int *total_ptr, long long total_direct, double *out) {
+    long long total = total_ptr ? (long long)*total_ptr : total_direct;
+    int lane = threadIdx.x;
+    double s = 0;
+    for (long long base = 0; base < total; base += 32) {
+        double v = (base + lane < total) ? terms[base + lane] : 0.0;
+        int m = (total - base < 32) ? (int)(total - base) : 32;
+        for (int l = 0; l < m; l++) s += __shfl_sync(0xffffffffu, v, l);   // every lane carries the same ordered sum
+    }
+    if (lane == 0) *out = s;
+}
 __global__ void k_potential_energy(DevP D, double *out) { *out = d_potential_energy(D); }
 __global__ void k_potential_energy_multi(const MultiArg *args, double *out) { out[blockIdx.x] = d_potential_energy(args[blockIdx.x].P); }
 // CalKinetE, ToolFunctions.c:626-656 (flow.mark < 2, constV = 0); ordered sum
+__global__ void k_ke_terms(DevP D, double *terms) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i > D.n) return;
+    double a = D.vx[i] - 0.0, b = D.vy[i] - 0.0, c = D.vz[i] - 0.0;   // CalKinetE, ToolFunctions.c:631-635
+    double s = a * a + b * b + c * c;
+    terms[i - 1] = 0.5 * D.mass[i] * s;
+}
 __global__ void k_kinetic_energy(DevP D, double *out) {
     double TKE = 0;
     for (int i = 1; i <= D.n; i++) {
@@ -1450,8 +1499,35 @@ int sdmd_cuda_do_event(sdmd_ctx *c) {
 int sdmd_cuda_potential_energy(sdmd_ctx *c, double *e) {
     CK(cudaSetDevice(c->device));
     double *d = (double *)(c->d_sum + 1);
-    k_potential_energy<<<1, 1, 0, c->stream>>>(c->P, d);
-    c->launches++;
+    int n = c->n;
+    if (n <= 2048) {
+        k_potential_energy<<<1, 1, 0, c->stream>>>(c->P, d);
+        c->launches++;
+    } else {
+        // ordered parallel form: per-atom addend lists (count -> exclusive scan -> write), then one in-order sum
+        int *cnt = c->cell_of;                       // scratch int[n+1]
+        int *off = c->pcount;                        // scratch int[n+1]
+        int nb = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
+        int *blk = nullptr;
+        CK(cudaMalloc((void **)&blk, ((size_t)nb + 2) * sizeof(int)));
+        k_pe_count<<<grid_for(n, 128), 128, 0, c->stream>>>(c->P, cnt);
+        k_scan_local<<<nb, 512, 0, c->stream>>>(cnt, off, blk, n);
+        k_scan_blocks<<<1, 32, 0, c->stream>>>(blk, nb);
+        k_scan_add<<<grid_for(n, 256), 256, 0, c->stream>>>(off, blk, n, nb);
+        int total = 0;
+        CK(cudaMemcpyAsync(&total, off + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        double *terms = nullptr;
+        CK(cudaMalloc((void **)&terms, ((size_t)total + 32) * sizeof(double)));
+        k_pe_write<<<grid_for(n, 128), 128, 0, c->stream>>>(c->P, off, terms);
+        k_ordered_sum<<<1, 32, 0, c->stream>>>(terms, nullptr, total, d);
+        c->launches += 6;
+        CK(cudaMemcpyAsync(e, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(terms);
+        cudaFree(blk);
+        return 0;
+    }
     CK(cudaMemcpyAsync(e, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
@@ -1459,8 +1535,15 @@ int sdmd_cuda_potential_energy(sdmd_ctx *c, double *e) {
 int sdmd_cuda_kinetic_energy(sdmd_ctx *c, double *e) {
     CK(cudaSetDevice(c->device));
     double *d = (double *)(c->d_sum + 1);
-    k_kinetic_energy<<<1, 1, 0, c->stream>>>(c->P, d);
-    c->launches++;
+    if (c->n <= 2048) {
+        k_kinetic_energy<<<1, 1, 0, c->stream>>>(c->P, d);
+        c->launches++;
+    } else {
+        double *terms = c->second;                   // scratch double[n+1]
+        k_ke_terms<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->P, terms);
+        k_ordered_sum<<<1, 32, 0, c->stream>>>(terms, nullptr, c->n, d);
+        c->launches += 2;
+    }
     CK(cudaMemcpyAsync(e, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;

@@ -122,6 +122,8 @@ def test_large_gel_box_against_oracle(capi):
     assert np.array_equal(r.celllist(), o.celllist())
     for k in ("frame", "count_recal", "collision", "thermostat", "pcc", "pair_predictions", "gaussians_used"):
         assert sg[k] == so[k], k
+    assert np.float64(r.potential_energy()).tobytes() == np.float64(o.potential_energy()).tobytes()
+    assert np.float64(r.kinetic_energy()).tobytes() == np.float64(o.kinetic_energy()).tobytes()
 
 
 def test_round_trip_properties_1m(capi):
@@ -222,6 +224,9 @@ def _oracle_vs_gpu(capi, hv0, gauss, iters, check_pairs=True):
     assert np.array_equal(r.cbt()[0][1:], o.cbt()[0][1:])
     for k in ("frame", "count_recal", "collision", "thermostat", "pcc", "pair_predictions", "gaussians_used"):
         assert sg[k] == so[k], k
+    # CalPotenE / CalKinetE: ordered sums, bit-equal (large systems take the parallel addend-list path)
+    assert np.float64(r.potential_energy()).tobytes() == np.float64(o.potential_energy()).tobytes()
+    assert np.float64(r.kinetic_energy()).tobytes() == np.float64(o.kinetic_energy()).tobytes()
     r.close()
     return so
 
