@@ -336,6 +336,84 @@ def reference_pass(args, dist):
 
 
 # ----------------------------------------------------------------------------------------------------
+# workload: loop (C5(ii): device-resident event loop on the synthetic box)
+# ----------------------------------------------------------------------------------------------------
+LOOP_ITERS = 256
+
+
+def cuda_loop(args, dist):
+    from sdmd_b200 import capi
+    capi.build()
+    hv, gauss = make_box(args.n_axis, dist.rank)
+    n = hv.natom
+    rng = np.random.default_rng(99 + dist.rank)
+    rep = capi.Replica(hv, device=dist.local_rank)
+    rep.rng_feed(gauss)
+    rep.pbc_full(); rep.cell_build(); rep.predict_all(); rep.cbt_build()
+    g_step = np.ascontiguousarray(rng.standard_normal(8 * LOOP_ITERS))
+    capi.host_register(g_step)
+
+    def one_step():
+        rep.rng_feed(g_step)                       # host -> device: this step's thermostat draws
+        st, _ = rep.run(max_iter=LOOP_ITERS)       # device -> host: sdmd_run_stats
+        return st
+
+    sampler = ClockSampler(dist.local_rank)
+    sampler.start()
+    for _ in range(args.warmup):
+        one_step()
+    st0 = rep.stats()
+    rep.reset_kernel_stats()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st = one_step()
+    rep.synchronize()
+    dt = dist.max(time.perf_counter() - t0)
+    dist.barrier()
+    run_ms, _ = rep.kernel_stats("run")          # CUDA events around the launches of sdmd_cuda_run
+    run_ms = dist.max(run_ms)
+    clocks = sampler.finish()
+    ev = dist.sum(float(st["frame"] - st0["frame"]))
+    its = dist.sum(float(st["iterations"] - st0["iterations"]))
+    launches = rep.launch_count()
+    rep.reset_kernel_stats()
+    for _ in range(50):
+        rep.advance(1e-9)
+    adv_ms, adv_n = rep.kernel_stats("advance")
+    adv = adv_ms / adv_n
+    peak, peak_src = load_peaks()
+    alg = 88.0 * n
+    out = {
+        "metric": "DMD events/s", "value": ev / (run_ms * 1e-3), "unit": "events/s", "n_gpus": dist.world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": run_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C5(ii) device-resident event loop on the synthetic {n}-atom GEL box, {LOOP_ITERS} loop iterations per step",
+                   "natom_per_gpu": n, "parallelism": f"replicas x{dist.world} (one independent box per GPU, no collective)",
+                   "l2": "per-event working set 88 MB > L2 is streamed by k_advance"},
+        "e2e": {"value": ev / dt, "unit": "events/s", "h2d_bytes_per_step": g_step.nbytes, "d2h_bytes_per_step": 120},
+        "iterations_per_s": its / (run_ms * 1e-3), "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_advance (UpdateData+TimeForward, once per event)", "achieved": alg / (adv * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": alg / (adv * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg, "kernel_ms": adv,
+                     "kernel_share_of_step": adv * (its / dist.world) / run_ms if run_ms else None},
+    }
+    if dist.rank == 0 and not args.no_cpu_baseline:
+        from oracle.oracle_py import Oracle
+        ho, go = make_box(args.n_axis, 0)
+        o = Oracle(ho)
+        o.rng_feed(np.concatenate([go, np.random.default_rng(5).standard_normal(4096)]))
+        o.pbc_full(); o.cell_build(); o.predict_all(); o.cbt_build()
+        t1 = time.perf_counter()
+        so, _ = o.run(max_iter=200)
+        t2 = time.perf_counter() - t1
+        out["cpu_baseline"] = {"value": so["frame"] / t2, "unit": "events/s", "cores": 1, "kind": "port",
+                               "sample": f"200 loop iterations of the same box with the oracle port ({t2:.2f} s); the O(N) UpdateData/TimeForward sweeps dominate"}
+    rep.close()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
 # workload: remd (ala10, one replica per GPU)
 # ----------------------------------------------------------------------------------------------------
 def ala10_view(rank):
@@ -475,7 +553,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--workload", default="pass1m", choices=["pass1m", "remd"])
+    ap.add_argument("--workload", default="pass1m", choices=["pass1m", "loop", "remd"])
     ap.add_argument("--n-axis", type=int, default=100, help="lattice points per axis of the synthetic box (100 -> 1M atoms)")
     ap.add_argument("--exchange-rate", type=float, default=50.0)
     ap.add_argument("--replicas-per-gpu", type=int, default=1, help="remd workload: independent REMD ensembles packed on each GPU")
@@ -488,7 +566,7 @@ def main():
         if args.impl == "reference":
             out = reference_pass(args, dist) if args.workload == "pass1m" else reference_remd(args, dist)
         else:
-            out = cuda_pass(args, dist) if args.workload == "pass1m" else cuda_remd(args, dist)
+            out = {"pass1m": cuda_pass, "loop": cuda_loop, "remd": cuda_remd}[args.workload](args, dist)
         if dist.rank == 0 and out is not None:
             print(json.dumps(out))
             sys.stdout.flush()
