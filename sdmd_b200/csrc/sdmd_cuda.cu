@@ -703,6 +703,25 @@ __global__ void k_loop_head(DevP D, double t_until, i64 iter_limit) { d_loop_hea
 
 // ---- single-step kernels behind the per-function C-ABI ----
 __global__ void k_predict_list(DevP D, int a0, int a1) { d_predict_list_serial(D, a0, a1); }
+// Predict(renewList) for lists of any length (the reference builds them for CG residues, SGThread.c:106-117):
+// ResetTarget over the whole list first, then the atoms in list order, one thread
+__global__ void k_predict_list_n(DevP D, const int *list, int cnt) {
+    SlotSrc S = d_live_slots(D);
+    for (int k = 0; k < cnt; k++) {
+        int i = list[k];
+        D.ev_type[i] = SDMD_EV_INVD; D.ev_time[i] = SD_INF; D.ev_partner[i] = SDMD_INVALID;
+    }
+    for (int k = 0; k < cnt; k++) {
+        int i = list[k];
+        Slot cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
+        double g = 0;
+        if (D.thermostat_on && !D.is_cons[i]) g = d_next_gauss(D);
+        int np = 0;
+        cur = d_predict_atom<false>(D, S, i, cur, g, 0x7fffffff, &np);
+        d_store_slot(D, i, cur);
+        D.ctl->pair_predictions += np;
+    }
+}
 __global__ void k_cbt_update(DevP D, int a0, int a1) {
     if (a0 > 0) d_cbt_update_run(D, a0);
     if (a1 > 0) d_cbt_update_run(D, a1);
@@ -1385,10 +1404,18 @@ int sdmd_cuda_predict(sdmd_ctx *c, const int32_t *renew) {
     if (!renew) return set_err(SDMD_ERR_BAD_ARG, "null renew list");
     int cnt = 0;
     while (renew[1 + cnt]) cnt++;
-    // the event loop only ever lists one or two atoms (SGThread.c:238-251); longer lists go pairwise in order,
-    // which is the same sequential semantics (reset of later atoms happens before they are used as sources
-    // only within a pair; for a full-system pass use sdmd_cuda_predict_all)
-    if (cnt > 2) return set_err(SDMD_ERR_UNSUPPORTED, "renew lists longer than 2 atoms: use sdmd_cuda_predict_all");
+    // the event loop only ever lists one or two atoms (SGThread.c:238-251); longer lists take the generic serial kernel
+    if (cnt > 2) {
+        int *d_list = nullptr;
+        CK(cudaMalloc((void **)&d_list, sizeof(int) * cnt));
+        CK(cudaMemcpyAsync(d_list, renew + 1, sizeof(int) * cnt, cudaMemcpyHostToDevice, c->stream));
+        k_predict_list_n<<<1, 1, 0, c->stream>>>(c->P, d_list, cnt);
+        c->launches++;
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(d_list);
+        CK(cudaGetLastError());
+        return 0;
+    }
     k_predict_list<<<1, 1, 0, c->stream>>>(c->P, cnt > 0 ? renew[1] : 0, cnt > 1 ? renew[2] : 0);
     c->launches++;
     CK(cudaGetLastError());

@@ -273,3 +273,20 @@ def test_run_stops_at_time_boundaries(capi):
             assert so[k] == sg[k], (t_until, k, so, sg)
         assert np.float64(so["currenttime"]).tobytes() == np.float64(sg["currenttime"]).tobytes()
     assert sg["stop_reason"] == 0   # currenttime > timestep ended the run
+
+
+def test_predict_arbitrary_renew_list(capi):
+    """Predict(renewList) with a longer list (what FixAssignRenewList / CGResidueRenew build): reset all, then in order."""
+    from oracle.oracle_py import Oracle
+    pre, _, _ = load_case("ala10")
+    ho, hg = pre.copy(), pre.copy()
+    o = Oracle(ho); o.rng_feed(pre.extra["gauss"])
+    r = capi.Replica(hg, device=0); r.rng_feed(pre.extra["gauss"])
+    o.set_celllist(pre.extra["celllist"]); o.predict_all(); o.cbt_build()
+    r.cell_build(); r.predict_all(); r.cbt_build()
+    atoms = [7, 3, 30, 31, 12, 55]
+    o.predict(atoms); o.cbt_update(atoms)
+    r.predict(atoms); r.cbt_update(atoms)
+    r.download(hg)
+    assert_fields_equal(hg, ho, SLOT_FIELDS)
+    assert np.array_equal(r.cbt()[0][1:], o.cbt()[0][1:])
