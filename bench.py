@@ -210,9 +210,7 @@ def cuda_pass(args, dist):
     d2h = 120 + 24  # sdmd_run_stats + AssignJob result
 
     def one_e2e():
-        rep.upload_coords(hv_e2e)
-        rep.rng_refeed(g_host)
-        rep.pbc_full(); rep.cell_build(); rep.predict_all(); rep.cbt_build()
+        rep.prepare(hv_e2e, g_host)     # upload + PBC + LinkList + Predict(all) + CreateCBT, one C-ABI call
         rep.assign_job()
         return rep.stats()
 

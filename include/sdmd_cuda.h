@@ -236,6 +236,13 @@ int  sdmd_cuda_predict_all(sdmd_ctx *ctx);
 int  sdmd_cuda_predict(sdmd_ctx *ctx, const int32_t *renew_list);
 /* CreateCBT CBT.c:16-30 / UpdateCBT CBT.c:33-39 */
 int  sdmd_cuda_cbt_build(sdmd_ctx *ctx);
+/* Prepare() SGThread.c:44-62 from HOST inputs in one call: upload coordinates and a fresh thermostat stream
+ * (gauss[0..n_gauss), n_gauss >= natom when the thermostat is on), then PBC("full"), LinkList("full"), Predict(all),
+ * CreateCBT.  Same results as upload_coords + rng_reset + rng_feed + pbc_full + cell_build + predict_all + cbt_build;
+ * velocities and gaussians travel on a second stream while the cell list and the neighbour filter already run.
+ * Arrays are 1-based (natom+1 entries); page-locked host memory (sdmd_host_register) makes the copies asynchronous. */
+int  sdmd_cuda_prepare(sdmd_ctx *ctx, const double *x, const double *y, const double *z, const double *vx,
+                       const double *vy, const double *vz, const double *gauss, int64_t n_gauss);
 int  sdmd_cuda_cbt_update(sdmd_ctx *ctx, const int32_t *renew_list);
 /* AssignJob SGThread.c:237-259: target = CBT.node[1], dt = its event time, partner (0 if none) */
 int  sdmd_cuda_assign_job(sdmd_ctx *ctx, int32_t *target, int32_t *partner, double *dt, int32_t *renew_list);

@@ -63,6 +63,8 @@ struct sdmd_ctx {
     std::vector<cudaEvent_t> ev_pool;
     long launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
+    cudaStream_t copy_stream = nullptr;  // second stream of sdmd_cuda_prepare (velocities + gaussians overlap the cell build)
+    cudaEvent_t ev_copy = nullptr, ev_main = nullptr;
     // big-N event loop graph
     cudaGraphExec_t loop_graph = nullptr;
     int loop_graph_len = 0;
@@ -258,16 +260,19 @@ __global__ void k_cell_count(DevP D) {
 }
 
 // cell-sorted SoA copies for the full-system prediction pass
+// parts: bit 0 = positions, types and index maps, bit 1 = velocities (sdmd_cuda_prepare sorts them once their upload lands)
 __global__ void k_cell_permute(DevP D, const int *sorted_atom, double *sx, double *sy, double *sz, double *svx, double *svy,
-                               double *svz, int *stype) {
+                               double *svz, int *stype, int parts) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= D.n) return;
     int j = sorted_atom[p];
-    D.spos[j] = p;
-    D.scx[p] = D.cell_idx[3 * j];
-    sx[p] = D.x[j]; sy[p] = D.y[j]; sz[p] = D.z[j];
-    svx[p] = D.vx[j]; svy[p] = D.vy[j]; svz[p] = D.vz[j];
-    stype[p] = D.type[j];
+    if (parts & 1) {
+        D.spos[j] = p;
+        D.scx[p] = D.cell_idx[3 * j];
+        sx[p] = D.x[j]; sy[p] = D.y[j]; sz[p] = D.z[j];
+        stype[p] = D.type[j];
+    }
+    if (parts & 2) { svx[p] = D.vx[j]; svy[p] = D.vy[j]; svz[p] = D.vz[j]; }
 }
 
 // ===================================================================================================
@@ -1074,6 +1079,9 @@ void sdmd_cuda_destroy(sdmd_ctx *c) {
     cudaEventDestroy(c->ev1);
     cudaEventDestroy(c->evt0);
     cudaEventDestroy(c->evt1);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1299,8 +1307,7 @@ int sdmd_cuda_pbc_full(sdmd_ctx *c) {
     return 0;
 }
 
-int sdmd_cuda_cell_build(sdmd_ctx *c) {
-    CK(cudaSetDevice(c->device));
+static int cell_build_impl(sdmd_ctx *c, int parts, bool bump) {
     Timer t(c, "cell_build");
     int n = c->n, m = c->P.ncell;
     CK(cudaMemsetAsync(c->cell_count, 0, ((size_t)m + 1) * sizeof(int), c->stream));
@@ -1313,19 +1320,22 @@ int sdmd_cuda_cell_build(sdmd_ctx *c) {
     k_cell_scatter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_cursor, c->d_sorted_atom);
     k_cell_finish<<<grid_for(m, 128), 128, 0, c->stream>>>(c->P, c->d_cell_start, c->d_sorted_atom);
     k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_sx, c->d_sy, c->d_sz, c->d_svx, c->d_svy,
-                                                            c->d_svz, c->d_stype);
+                                                            c->d_svz, c->d_stype, parts);
     c->launches += 7;
-    TRY(bump_epoch(c));
+    if (bump) TRY(bump_epoch(c));
     c->cells_fresh = true;
     CK(cudaGetLastError());
     return 0;
 }
-
-int sdmd_cuda_predict_all(sdmd_ctx *c) {
+int sdmd_cuda_cell_build(sdmd_ctx *c) {
     CK(cudaSetDevice(c->device));
-    if (!c->cells_fresh) return set_err(SDMD_ERR_STATE, "predict_all needs a fresh cell_build (cell-sorted tiles)");
+    return cell_build_impl(c, 3, true);
+}
+
+// `late` (optional): an event the evaluation stage has to wait for — velocities and gaussians still in flight on the
+// copy stream while the position-only neighbour filter runs (sdmd_cuda_prepare); h_ctl must be current
+static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
     int n = c->n;
-    TRY(pull_ctl(c));
     i64 need = 0;
     if (c->P.thermostat_on) need = n;  // one draw per predicted atom, TimePrediction.c:591
     if (c->g_filled - c->h_ctl->g_pos < need) return set_err(SDMD_ERR_BAD_ARG, "predict_all: not enough gaussians fed");
@@ -1341,6 +1351,12 @@ int sdmd_cuda_predict_all(sdmd_ctx *c) {
         Timer t(c, "predict_all");
         if (c->P.surv) {
             k_predict_all_filter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P);
+            c->launches++;
+        }
+        if (late) {
+            CK(cudaStreamWaitEvent(c->stream, late, 0));
+            k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_sx, c->d_sy, c->d_sz, c->d_svx, c->d_svy,
+                                                                    c->d_svz, c->d_stype, 2);
             c->launches++;
         }
         k_predict_all_round<<<grid, 128, 0, c->stream>>>(c->P, B, B, nullptr, nullptr, 0, c->npair, c->second, c->bp_time, c->bp_j,
@@ -1398,6 +1414,12 @@ int sdmd_cuda_predict_all(sdmd_ctx *c) {
     CK(cudaGetLastError());
     return 0;
 }
+int sdmd_cuda_predict_all(sdmd_ctx *c) {
+    CK(cudaSetDevice(c->device));
+    if (!c->cells_fresh) return set_err(SDMD_ERR_STATE, "predict_all needs a fresh cell_build (cell-sorted tiles)");
+    TRY(pull_ctl(c));
+    return predict_all_impl(c, nullptr);
+}
 
 int sdmd_cuda_predict(sdmd_ctx *c, const int32_t *renew) {
     CK(cudaSetDevice(c->device));
@@ -1443,6 +1465,43 @@ int sdmd_cuda_cbt_build(sdmd_ctx *c) {
     }
     CK(cudaGetLastError());
     return 0;
+}
+
+// Prepare() of the reference (SGThread.c:44-62) from host inputs in one call.  Positions go up first on the replica's
+// stream; velocities and the thermostat stream follow on a second stream while PBC("full"), LinkList("full") and the
+// position-only neighbour filter of Predict(all) already run; the evaluation stage waits for them.
+int sdmd_cuda_prepare(sdmd_ctx *c, const double *x, const double *y, const double *z, const double *vx, const double *vy,
+                      const double *vz, const double *gauss, int64_t n_gauss) {
+    CK(cudaSetDevice(c->device));
+    if (!x || !y || !z || !vx || !vy || !vz) return set_err(SDMD_ERR_BAD_ARG, "prepare: null coordinate array");
+    if (n_gauss < 0 || n_gauss > c->P.g_cap || (n_gauss && !gauss)) return set_err(SDMD_ERR_BAD_ARG, "prepare: gaussian count");
+    if (!c->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+    }
+    TRY(pull_ctl(c));                                   // also drains earlier work that may still read the arrays
+    size_t b = ((size_t)c->n + 1) * sizeof(double);
+    CK(cudaMemcpyAsync(c->P.x, x, b, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->P.y, y, b, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->P.z, z, b, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->P.vx, vx, b, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaMemcpyAsync(c->P.vy, vy, b, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaMemcpyAsync(c->P.vz, vz, b, cudaMemcpyHostToDevice, c->copy_stream));
+    if (n_gauss) CK(cudaMemcpyAsync(c->d_gauss, gauss, n_gauss * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaEventRecord(c->ev_copy, c->copy_stream));
+    c->g_filled = n_gauss;                              // fresh thermostat stream: drop what was fed before
+    c->h_ctl->g_filled = n_gauss;
+    c->h_ctl->g_pos = 0;
+    c->h_ctl->cc_epoch++;                               // new link list: cached candidate lists are void
+    CK(cudaMemcpyAsync(&c->d_ctl->g_filled, &c->h_ctl->g_filled, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(&c->d_ctl->g_pos, &c->h_ctl->g_pos, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(&c->d_ctl->cc_epoch, &c->h_ctl->cc_epoch, sizeof(c->h_ctl->cc_epoch), cudaMemcpyHostToDevice, c->stream));
+    k_pbc_full<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->P);
+    c->launches++;
+    TRY(cell_build_impl(c, 1, false));
+    TRY(predict_all_impl(c, c->ev_copy));
+    return sdmd_cuda_cbt_build(c);
 }
 
 int sdmd_cuda_cbt_update(sdmd_ctx *c, const int32_t *renew) {

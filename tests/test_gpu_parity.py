@@ -290,3 +290,22 @@ def test_predict_arbitrary_renew_list(capi):
     r.download(hg)
     assert_fields_equal(hg, ho, SLOT_FIELDS)
     assert np.array_equal(r.cbt()[0][1:], o.cbt()[0][1:])
+
+
+@pytest.mark.parametrize("case", ["ala10", "gel10"])
+def test_prepare_one_call_equals_stepwise(capi, case):
+    """sdmd_cuda_prepare (overlapped upload) == upload_coords + rng + pbc_full + cell_build + predict_all + cbt_build."""
+    pre, post, _ = load_case(case)
+    ha, hb = pre.copy(), pre.copy()
+    a = capi.Replica(ha, device=0); b = capi.Replica(hb, device=0)
+    g = pre.extra["gauss"]
+    a.upload_coords(); a.rng_refeed(g); a.pbc_full(); a.cell_build(); a.predict_all(); a.cbt_build()
+    for _ in range(2):                       # twice: the second call replaces live state
+        b.prepare(None, g)
+    a.download(ha); b.download(hb)
+    assert_fields_equal(hb, ha, tuple(SLOT_FIELDS) + ("x", "y", "z", "vx", "vy", "vz"))
+    assert_fields_equal(hb, post, SLOT_FIELDS)
+    assert np.array_equal(a.celllist(), b.celllist())
+    assert np.array_equal(a.cbt()[0][1:], b.cbt()[0][1:])
+    sa, sb = a.run(max_iter=300, trace_cap=300), b.run(max_iter=300, trace_cap=300)
+    assert sa[1].tobytes() == sb[1].tobytes()
