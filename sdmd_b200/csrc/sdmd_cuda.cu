@@ -48,7 +48,8 @@ struct sdmd_ctx {
     int *bp_j = nullptr;
     int *cell_of = nullptr, *cell_count = nullptr, *cell_cursor = nullptr, *scan_tmp = nullptr;
     int *d_cell_start = nullptr, *d_sorted_atom = nullptr;
-    double *d_sx = nullptr, *d_sy = nullptr, *d_sz = nullptr, *d_svx = nullptr, *d_svy = nullptr, *d_svz = nullptr;
+    double *d_sx = nullptr, *d_sy = nullptr, *d_sz = nullptr;
+    SRec *d_srec = nullptr;
     int *d_stype = nullptr;
     int *d_leaf_atom = nullptr;  // static leaf permutation of the tournament tree
     double *d_gauss = nullptr;
@@ -261,18 +262,26 @@ __global__ void k_cell_count(DevP D) {
 
 // cell-sorted SoA copies for the full-system prediction pass
 // parts: bit 0 = positions, types and index maps, bit 1 = velocities (sdmd_cuda_prepare sorts them once their upload lands)
-__global__ void k_cell_permute(DevP D, const int *sorted_atom, double *sx, double *sy, double *sz, double *svx, double *svy,
-                               double *svz, int *stype, int parts) {
+__global__ void k_cell_permute(DevP D, const int *sorted_atom, double *sx, double *sy, double *sz, SRec *srec, int *stype, int parts) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= D.n) return;
     int j = sorted_atom[p];
+    double2 *rp = reinterpret_cast<double2 *>(&srec[p]);
     if (parts & 1) {
         D.spos[j] = p;
         D.scx[p] = D.cell_idx[3 * j];
-        sx[p] = D.x[j]; sy[p] = D.y[j]; sz[p] = D.z[j];
-        stype[p] = D.type[j];
+        double x = D.x[j], y = D.y[j], z = D.z[j];
+        int t = D.type[j];
+        sx[p] = x; sy[p] = y; sz[p] = z;
+        stype[p] = t;
+        rp[0] = make_double2(x, y);
+        srec[p].z = z;
+        *reinterpret_cast<int2 *>(rp + 3) = make_int2(t, j);
     }
-    if (parts & 2) { svx[p] = D.vx[j]; svy[p] = D.vy[j]; svz[p] = D.vz[j]; }
+    if (parts & 2) {
+        srec[p].vx = D.vx[j];
+        rp[2] = make_double2(D.vy[j], D.vz[j]);
+    }
 }
 
 // ===================================================================================================
@@ -316,7 +325,10 @@ __global__ void __launch_bounds__(128) k_predict_all_round(DevP D, SlotBuf src, 
         int i = (round == 0) ? D.sorted_atom[p] : queue[p];
         Slot cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
         double g = 0;
-        if (D.thermostat_on && !D.is_cons[i]) g = D.gauss[(g_base + D.ther_rank[i]) % D.g_cap];
+        if (D.thermostat_on && !D.is_cons[i]) {
+            i64 gi = g_base + D.ther_rank[i];        // g_base < g_cap (host reduces it), rank < n <= g_cap
+            g = D.gauss[gi >= D.g_cap ? gi - D.g_cap : gi];
+        }
         int np = 0;
         double m2 = SD_INF;
         PairBest pb;
@@ -1025,7 +1037,7 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     TRY(dalloc(c, &c->scan_tmp, (size_t)P.ncell / SCAN_ITEMS + 4));
     TRY(dalloc(c, &c->d_cell_start, (size_t)P.ncell + 1)); TRY(dalloc(c, &c->d_sorted_atom, n1));
     TRY(dalloc(c, &c->d_sx, n1)); TRY(dalloc(c, &c->d_sy, n1)); TRY(dalloc(c, &c->d_sz, n1));
-    TRY(dalloc(c, &c->d_svx, n1)); TRY(dalloc(c, &c->d_svy, n1)); TRY(dalloc(c, &c->d_svz, n1));
+    TRY(dalloc(c, &c->d_srec, n1));
     TRY(dalloc(c, &c->d_stype, n1));
     TRY(dalloc(c, &c->d_sum, 4));
     P.surv = nullptr; P.surv_n = nullptr; P.surv_np = nullptr;
@@ -1044,7 +1056,7 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
         TRY(dalloc(c, &P.surv, (size_t)R0_SURV_CAP * n1)); TRY(dalloc(c, &P.surv_n, n1)); TRY(dalloc(c, &P.surv_np, n1));
     }
     P.cell_start = c->d_cell_start; P.sorted_atom = c->d_sorted_atom;
-    P.sx = c->d_sx; P.sy = c->d_sy; P.sz = c->d_sz; P.svx = c->d_svx; P.svy = c->d_svy; P.svz = c->d_svz; P.stype = c->d_stype;
+    P.sx = c->d_sx; P.sy = c->d_sy; P.sz = c->d_sz; P.srec = c->d_srec; P.stype = c->d_stype;
     std::vector<int> leaf_atom;
     cbt_leaf_permutation(n, leaf_atom);
     TRY(dupload(c, &c->d_leaf_atom, leaf_atom.data(), (size_t)n));
@@ -1319,8 +1331,7 @@ static int cell_build_impl(sdmd_ctx *c, int parts, bool bump) {
     CK(cudaMemcpyAsync(c->cell_cursor, c->d_cell_start, ((size_t)m + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
     k_cell_scatter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_cursor, c->d_sorted_atom);
     k_cell_finish<<<grid_for(m, 128), 128, 0, c->stream>>>(c->P, c->d_cell_start, c->d_sorted_atom);
-    k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_sx, c->d_sy, c->d_sz, c->d_svx, c->d_svy,
-                                                            c->d_svz, c->d_stype, parts);
+    k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_sx, c->d_sy, c->d_sz, c->d_srec, c->d_stype, parts);
     c->launches += 7;
     if (bump) TRY(bump_epoch(c));
     c->cells_fresh = true;
@@ -1339,7 +1350,8 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
     i64 need = 0;
     if (c->P.thermostat_on) need = n;  // one draw per predicted atom, TimePrediction.c:591
     if (c->g_filled - c->h_ctl->g_pos < need) return set_err(SDMD_ERR_BAD_ARG, "predict_all: not enough gaussians fed");
-    i64 g_base = c->h_ctl->g_pos;
+    i64 g_pos0 = c->h_ctl->g_pos;
+    i64 g_base = g_pos0 % c->P.g_cap;       // ring offset of the first draw
     SlotBuf B = {c->b_time, c->b_pot, c->b_partner, c->b_pcounter, c->b_type, c->b_sub};
     SlotBuf C = {c->c_time, c->c_pot, c->c_partner, c->c_pcounter, c->c_type, c->c_sub};
     int grid = grid_for(n, 128), grid1 = grid_for(n, 256);
@@ -1355,8 +1367,7 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
         }
         if (late) {
             CK(cudaStreamWaitEvent(c->stream, late, 0));
-            k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_sx, c->d_sy, c->d_sz, c->d_svx, c->d_svy,
-                                                                    c->d_svz, c->d_stype, 2);
+            k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_sx, c->d_sy, c->d_sz, c->d_srec, c->d_stype, 2);
             c->launches++;
         }
         k_predict_all_round<<<grid, 128, 0, c->stream>>>(c->P, B, B, nullptr, nullptr, 0, c->npair, c->second, c->bp_time, c->bp_j,
@@ -1403,7 +1414,7 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
     // the relaxed buffer becomes the live slot arrays (pointer swap, no copy)
     std::swap(c->P.ev_time, c->b_time); std::swap(c->P.ev_pot, c->b_pot); std::swap(c->P.ev_partner, c->b_partner);
     std::swap(c->P.ev_pcounter, c->b_pcounter); std::swap(c->P.ev_type, c->b_type); std::swap(c->P.ev_sub, c->b_sub);
-    c->h_ctl->g_pos = g_base + need;
+    c->h_ctl->g_pos = g_pos0 + need;
     c->h_ctl->pair_predictions += (i64)h.sum;
     CK(cudaMemcpyAsync(&c->d_ctl->g_pos, &c->h_ctl->g_pos, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(&c->d_ctl->pair_predictions, &c->h_ctl->pair_predictions, sizeof(i64), cudaMemcpyHostToDevice, c->stream));

@@ -54,6 +54,14 @@ struct Slot {
     int partner, type, sub;
 };
 
+// One cell-sorted atom as the evaluation stage of Predict(all) wants it: a survivor costs one 64-byte gather (two
+// sectors, four 16-byte loads) instead of eight scattered 4/8-byte loads
+struct __align__(16) SRec {
+    double x, y, z, vx, vy, vz;
+    int type, atom;
+    double pad;
+};
+
 struct DevP {
     int n, ncell;
     int cellnum[3];
@@ -101,8 +109,9 @@ struct DevP {
     // cell-sorted tiles produced by cell_build (fresh link-list order: descending atom id inside a cell)
     const int *cell_start;   // [ncell + 1], 0-based cell
     const int *sorted_atom;  // [n]
-    const double *sx, *sy, *sz, *svx, *svy, *svz;
+    const double *sx, *sy, *sz;   // positions alone: what the neighbour filter streams
     const int *stype;
+    const struct SRec *srec;      // full record per sorted position: what the evaluation stage gathers
     // round-0 filter output: per sorted position up to R0_SURV_CAP candidates inside the scan sphere
     unsigned int *surv;      // (sorted position of j) | (scan slot k << 27)
     int *surv_n;             // count, or -1 when the list overflowed (atom re-scanned in the evaluation kernel)
@@ -450,9 +459,18 @@ __device__ __forceinline__ void d_r0_flush(const DevP &D, const SlotSrc &S, Self
     for (int s = 0; s < ns; s++) {
         int p = surv_p[s];
         int k = surv_k[s] & 0x1f;
-        int j = D.sorted_atom[p];
-        double shx, shy, shz;   // PBCShift via the scanned neighbour cell
-        d_neighbor(D, me.cx, me.cy, me.cz, k, &shx, &shy, &shz);
+        const double2 *rp = reinterpret_cast<const double2 *>(&D.srec[p]);
+        double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2v = __ldg(rp + 2);
+        int2 ta = __ldg(reinterpret_cast<const int2 *>(rp + 3));
+        int j = ta.y;
+        double shx, shy, shz;   // PBCShift via the scanned neighbour cell (arithmetic, no table: keeps the load chain short)
+        {
+            int ncx, ncy, ncz;
+            d_neighbor_cell(D, me.cx, me.cy, me.cz, k, &ncx, &ncy, &ncz);
+            shx = d_shift1(me.cx, ncx, D.cellnum[0], D.box[0]);
+            shy = d_shift1(me.cy, ncy, D.cellnum[1], D.box[1]);
+            shz = d_shift1(me.cz, ncz, D.cellnum[2], D.box[2]);
+        }
         int cm = has_cm ? d_cm_flags(D, me.i, j) : 0;
         if (surv_k[s] & R0_DUPFLAG) {
             // CheckDuplication (TimePrediction.c:1101-1117) at this candidate's place in the scan
@@ -466,13 +484,13 @@ __device__ __forceinline__ void d_r0_flush(const DevP &D, const SlotSrc &S, Self
             if ((h0 == j) || (h0 != 0 && (h1 == j || (h1 != 0 && (h2 == j || (h2 != 0 && h3 == j)))))) continue;
             me.npair++;
         }
-        Pair pr = d_pair(me.x, me.y, me.z, me.vx, me.vy, me.vz, D.sx[p], D.sy[p], D.sz[p], D.svx[p], D.svy[p], D.svz[p], shx, shy, shz);
+        Pair pr = d_pair(me.x, me.y, me.z, me.vx, me.vy, me.vz, r0.x, r0.y, r1.x, r1.y, r2v.x, r2v.y, shx, shy, shz);
         if (!(pr.r2 <= D.cut2)) continue;
         FindRes f;
         if (cm & SDMD_CONSTRAINT_CONNECT) {
             f = d_find_pair(D, me.i, j, FP_CONSTRAINT, pr.b, pr.r2, 0, 0);
         } else {
-            int idx = __ldg(&D.coll_index[type_i * SD_NT + D.stype[p]]);
+            int idx = __ldg(&D.coll_index[type_i * SD_NT + ta.x]);
             if (idx < 0) { D.ctl->error = SDMD_ERR_TABLE; continue; }
             f = d_find_pair_table_fast(D, &D.tables[idx], FP_COLLISION, pr.b, pr.r2, 0, 0);
             if (f.lowPot == 0 && f.upPot == 0) continue;
