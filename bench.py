@@ -425,7 +425,94 @@ def ala10_view(rank):
     return hv
 
 
+def remd_ladder_K(n):
+    """Temperature ladder: the demo's own first 8 values, or a geometric ladder over the same span for larger ensembles."""
+    if n <= len(REMD_TEMPS_K):
+        return list(REMD_TEMPS_K[:n])
+    return [float("%.2f" % t) for t in np.geomspace(REMD_TEMPS_K[0], REMD_TEMPS_K[-1], n)]
+
+
+def cuda_remd_many(args, dist):
+    """One REMD ensemble of R ala10 replicas per GPU: every replica is a persistent thread block (sdmd_cuda_run_many),
+    CalPotenE for all of them in one launch, the Server.c sweep on the host.  GPUs hold independent ensembles."""
+    from sdmd_b200 import capi
+    from sdmd_b200.remd import RemdEnsemble
+    capi.build()
+    R = args.replicas_per_gpu
+    temps_K = remd_ladder_K(R)
+    rate = float(args.exchange_rate)
+    per_step = 260000                                   # gaussians one replica may consume per exchange interval (generous)
+    rng = np.random.default_rng(1575263273 + dist.rank)
+    pool = np.ascontiguousarray(rng.standard_normal(per_step * 4 + 8 * 1024 * 1024))   # synthetic thermostat stream, host memory
+    capi.host_register(pool)
+    reps = []
+    for k in range(R):
+        hv = ala10_view(0)
+        hv.target_temperature = reduced_T(temps_K[k])
+        rep = capi.Replica(hv, device=dist.local_rank)
+        rep.set_timing(0)
+        off = int(rng.integers(0, 8 * 1024 * 1024))
+        rep.rng_feed(pool[off:off + per_step * 2])
+        rep.pbc_full(); rep.cell_build(); rep.predict_all(); rep.cbt_build()
+        reps.append(rep)
+    fed = [0]
+
+    def refill(k, rep):
+        if rep.rng_available() < per_step:
+            off = int(rng.integers(0, 8 * 1024 * 1024))
+            rep.rng_feed(pool[off:off + per_step])     # host -> device inside the timed region
+            fed[0] += per_step * 8
+
+    ens = RemdEnsemble(reps, [reduced_T(t) for t in temps_K], rate, server_seed=12345 + dist.rank, refill=refill)
+
+    def totals():
+        st = [r.stats() for r in reps]
+        return sum(s["frame"] for s in st), sum(s["iterations"] for s in st)
+
+    for _ in range(args.warmup):
+        ens.step()
+    f0, it0 = totals()
+    fed[0] = 0
+    l0 = sum(r.launch_count() for r in reps)
+    sampler = ClockSampler(dist.local_rank)
+    sampler.start()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ens.step()
+    reps[0].synchronize()
+    dt = time.perf_counter() - t0
+    dist.barrier()
+    clocks = sampler.finish()
+    dt = dist.max(dt)
+    f1, it1 = totals()
+    ev = dist.sum(float(f1 - f0))
+    its = dist.sum(float(it1 - it0))
+    launches = sum(r.launch_count() for r in reps) - l0
+    peak, peak_src = load_peaks()
+    out = {
+        "metric": "REMD replica-events/s", "value": ev / dt, "unit": "events/s", "n_gpus": dist.world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "ala10 (tests/golden/ala10_pre.npz, from the reference's input/ala10.gro); thermostat stream synthetic N(0,1)",
+        "config": {"workload": f"ala10 REMD, {R} replicas per GPU (one persistent thread block each), one ensemble per GPU",
+                   "replicas_per_gpu": R, "temperatures_K": [temps_K[0], temps_K[-1]], "exchange_rate_tu": rate, "natom": 59,
+                   "parallelism": f"replica-parallel {R} x {dist.world} GPUs, host-side Server.c sweep per GPU, no collective"},
+        "e2e": {"value": ev / dt, "unit": "events/s", "h2d_bytes_per_step": fed[0] // max(args.steps, 1),
+                "d2h_bytes_per_step": R * (120 + 8)},
+        "iterations_per_s": its / dt, "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_run_cta_multi (one persistent CTA per replica, latency bound per CTA)", "achieved": None,
+                     "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
+                     "us_per_iteration_per_replica": 1e6 * dt * R * dist.world / max(its, 1)},
+    }
+    capi.host_unregister(pool)
+    for r in reps:
+        r.close()
+    return out
+
+
 def cuda_remd(args, dist):
+    if args.replicas_per_gpu > 1:
+        return cuda_remd_many(args, dist)
     from sdmd_b200 import capi
     capi.build()
     hv = ala10_view(dist.rank)
@@ -501,7 +588,8 @@ def reference_remd(args, dist):
         return {"impl": "reference", "unavailable": "oracle/_ref/sDMD_ref not built"}
     import shutil
     import tempfile
-    R = dist.world
+    R = dist.world * max(1, args.replicas_per_gpu)
+    ladder = remd_ladder_K(args.replicas_per_gpu) if args.replicas_per_gpu > 1 else REMD_TEMPS_K
     tu = float(args.exchange_rate) * (args.steps + args.warmup)
 
     def run_all(time_units):
@@ -513,7 +601,7 @@ def reference_remd(args, dist):
             p = d / "input" / "parameter.txt"
             lines = p.read_text().splitlines()
             lines[1] = "Time               %g" % time_units
-            lines[2] = "T(reduced)         %g" % reduced_T(REMD_TEMPS_K[r % 8])
+            lines[2] = "T(reduced)         %g" % reduced_T(ladder[r % len(ladder)])
             p.write_text("\n".join(lines) + "\n")
             (d / "out").mkdir()
             procs.append(subprocess.Popen([str(ref), "-f", "ala10.gro", "-i", str(d / "input"), "-o", str(d / "out")],
@@ -537,11 +625,13 @@ def reference_remd(args, dist):
     events = ev1 - ev0
     dt = max(t_full - t_start, 1e-9)
     v = events / dt
-    return {"impl": "reference", "metric": "REMD replica-events/s", "value": v, "unit": "events/s", "n_gpus": R,
+    return {"impl": "reference", "metric": "REMD replica-events/s", "value": v, "unit": "events/s", "n_gpus": dist.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps + args.warmup, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "ala10",
-            "config": {"workload": "ala10 REMD, one replica per GPU", "temperatures_K": REMD_TEMPS_K[:R]},
-            "cpu_baseline": {"value": v, "unit": "events/s", "cores": R, "kind": "reference",
+            "config": {"workload": "ala10 REMD, one replica per GPU" if args.replicas_per_gpu <= 1 else
+                       f"ala10 REMD, {args.replicas_per_gpu} replicas per GPU (one persistent thread block each), one ensemble per GPU",
+                       "temperatures_K": ladder[:R] if args.replicas_per_gpu <= 1 else [ladder[0], ladder[-1]]},
+            "cpu_baseline": {"value": v, "unit": "events/s", "cores": min(R, os.cpu_count() or 1), "kind": "reference",
                              "sample": f"{R} unmodified sDMD processes x {tu:g} time units, start-up ({t_start:.2f} s: parsing + SDEnergyMin) "
                                        f"measured by a 0.05-time-unit run and subtracted; no exchange server"},
             "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}

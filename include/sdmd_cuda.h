@@ -311,7 +311,7 @@ int  sdmd_cuda_synchronize(sdmd_ctx *ctx);
 /* page-lock caller-owned host buffers used with upload_* / download_* / rng_feed */
 int  sdmd_cuda_host_register(void *ptr, size_t bytes);
 int  sdmd_cuda_host_unregister(void *ptr);
-void sdmd_cuda_set_timing(sdmd_ctx *ctx, int on);   /* per-launch CUDA-event brackets (asynchronous, resolved on query); default on */
+void sdmd_cuda_set_timing(sdmd_ctx *ctx, int on);   /* CUDA-event brackets per stage (asynchronous, resolved on query): 0 off, 1 default, 2 also predict_all's fix-up sub-stages */
 int64_t sdmd_cuda_launch_count(const sdmd_ctx *ctx);
 /* debug: accumulated SM cycles per event-loop phase {head, advance, event, gather, eval, fold, cbt, iterations} */
 int  sdmd_cuda_phase_cycles(sdmd_ctx *ctx, int64_t out[12]);

@@ -1,0 +1,20 @@
+"""Fine-grained CUDA-event breakdown of the full-system pass on the 1M-atom box (timing level 2)."""
+import sys, time
+sys.path.insert(0, ".")
+import numpy as np
+from sdmd_b200 import capi, synth
+
+n_axis = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+hv, rng = synth.gel_box(n_axis, a=8.0, jitter=0.3, seed=1575263273)
+g = rng.standard_normal(hv.natom)
+r = capi.Replica(hv, device=0)
+r.set_timing(2)
+r.rng_feed(g)
+for it in range(8):
+    if it == 3: r.reset_kernel_stats()
+    r.rng_seek(0)
+    r.pbc_full(); r.cell_build(); r.predict_all(); r.cbt_build()
+r.synchronize()
+for k in ("cell_build", "predict_all", "predict_all_fixup", "fixup_resolve", "fixup_round1", "fixup_later", "cbt_build"):
+    v = r.kernel_stats(k)
+    print(f"{k:28s} total {v[0]:9.4f} ms  n={v[1]:4d}  avg {v[0]/max(v[1],1)*1e3:9.2f} us")

@@ -315,7 +315,7 @@ class Replica:
         return ms.value, n.value
 
     def reset_kernel_stats(self): self.L.sdmd_cuda_reset_kernel_stats(self.h)
-    def set_timing(self, on): self.L.sdmd_cuda_set_timing(self.h, int(bool(on)))
+    def set_timing(self, on): self.L.sdmd_cuda_set_timing(self.h, int(on))   # 0 off, 1 stages, 2 + fix-up sub-stages
     def launch_count(self): return int(self.L.sdmd_cuda_launch_count(self.h))
     def stream(self): return self.L.sdmd_cuda_stream(self.h)
 

@@ -50,7 +50,6 @@ struct sdmd_ctx {
     int *d_cell_start = nullptr, *d_sorted_atom = nullptr;
     double *d_sx = nullptr, *d_sy = nullptr, *d_sz = nullptr;
     SRec *d_srec = nullptr;
-    int *d_stype = nullptr;
     int *d_leaf_atom = nullptr;  // static leaf permutation of the tournament tree
     double *d_gauss = nullptr;
     i64 g_filled = 0;
@@ -58,7 +57,7 @@ struct sdmd_ctx {
     i64 trace_cap = 0;
     unsigned long long *d_sum = nullptr;
     bool cells_fresh = false;
-    bool timing = true;
+    int timing = 1;                      // 0 off, 1 per stage, 2 also the sub-stages of predict_all's fix-up
     std::map<std::string, KStat> kstat;
     std::vector<PendingEv> pending;      // launched, not yet resolved (kept asynchronous)
     std::vector<cudaEvent_t> ev_pool;
@@ -124,8 +123,9 @@ static void resolve_pending(sdmd_ctx *c) {
 struct Timer {
     sdmd_ctx *c;
     PendingEv p;
-    Timer(sdmd_ctx *c_, const char *n) : c(c_) {
-        if (c->timing) {
+    bool on;
+    Timer(sdmd_ctx *c_, const char *n, int level = 1) : c(c_), on(c_->timing >= level) {
+        if (on) {
             p.name = n;
             p.a = pool_get(c);
             p.b = pool_get(c);
@@ -133,7 +133,7 @@ struct Timer {
         }
     }
     ~Timer() {
-        if (c->timing) {
+        if (on) {
             cudaEventRecord(p.b, c->stream);
             c->pending.push_back(p);
             if (c->pending.size() > 4096) resolve_pending(c);
@@ -262,7 +262,7 @@ __global__ void k_cell_count(DevP D) {
 
 // cell-sorted SoA copies for the full-system prediction pass
 // parts: bit 0 = positions, types and index maps, bit 1 = velocities (sdmd_cuda_prepare sorts them once their upload lands)
-__global__ void k_cell_permute(DevP D, const int *sorted_atom, double *sx, double *sy, double *sz, SRec *srec, int *stype, int parts) {
+__global__ void k_cell_permute(DevP D, const int *sorted_atom, double *sx, double *sy, double *sz, SRec *srec, int parts) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= D.n) return;
     int j = sorted_atom[p];
@@ -273,12 +273,13 @@ __global__ void k_cell_permute(DevP D, const int *sorted_atom, double *sx, doubl
         double x = D.x[j], y = D.y[j], z = D.z[j];
         int t = D.type[j];
         sx[p] = x; sy[p] = y; sz[p] = z;
-        stype[p] = t;
         rp[0] = make_double2(x, y);
-        srec[p].z = z;
         *reinterpret_cast<int2 *>(rp + 3) = make_int2(t, j);
-    }
-    if (parts & 2) {
+        if (parts & 2) {
+            rp[1] = make_double2(z, D.vx[j]);
+            rp[2] = make_double2(D.vy[j], D.vz[j]);
+        } else srec[p].z = z;
+    } else if (parts & 2) {
         srec[p].vx = D.vx[j];
         rp[2] = make_double2(D.vy[j], D.vz[j]);
     }
@@ -312,16 +313,32 @@ __device__ __forceinline__ SlotSrc as_src(const SlotBuf &b) {
 //             a changed slot queues the higher-index atoms it pointed / points at.
 // The stale fields of a slot (potential / subEventType / partnerCounter survive ResetTarget) always start from the
 // live arrays, which this pass never writes until the final commit.
-__global__ void __launch_bounds__(256) k_predict_all_filter(DevP D) {
+#ifndef K2F_MINBLOCKS
+#define K2F_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(256, K2F_MINBLOCKS) k_predict_all_filter(DevP D) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < D.n) d_r0_filter(D, p);
 }
 
-__global__ void __launch_bounds__(128) k_predict_all_round(DevP D, SlotBuf src, SlotBuf dst, const int *queue, const int *nqueue_ptr,
+#ifndef QSPREAD
+#define QSPREAD 8
+#endif
+#ifndef K2_MINBLOCKS
+#define K2_MINBLOCKS 6
+#endif
+__global__ void __launch_bounds__(128, K2_MINBLOCKS) k_predict_all_round(DevP D, SlotBuf src, SlotBuf dst, const int *queue, const int *nqueue_ptr,
                                                            int round, int *npair, double *second, double *bp_time, int *bp_j,
                                                            int *pcount, int *pwho, unsigned long long *pair_sum, i64 g_base) {
     int total = (round == 0) ? D.n : *nqueue_ptr;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+    // re-evaluation rounds are a few thousand atoms with divergent, DRAM-latency-bound paths: give each its own
+    // group of QSPREAD lanes so a warp serialises 32/QSPREAD paths instead of 32
+    int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    if (round != 0) {
+        if (gtid % QSPREAD) return;
+        gtid /= QSPREAD; gsz /= QSPREAD;
+    }
+    for (int p = gtid; p < total; p += gsz) {
         int i = (round == 0) ? D.sorted_atom[p] : queue[p];
         Slot cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
         double g = 0;
@@ -442,13 +459,16 @@ __global__ void k_predict_all_commit(DevP D, SlotBuf cur, SlotBuf nxt, const int
     int nqueue = *nqueue_ptr;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nqueue; p += gridDim.x * blockDim.x) {
     int i = queue[p];
-    bool same = __double_as_longlong(cur.time[i]) == __double_as_longlong(nxt.time[i]) &&
-                __double_as_longlong(cur.pot[i]) == __double_as_longlong(nxt.pot[i]) && cur.partner[i] == nxt.partner[i] &&
-                cur.pcounter[i] == nxt.pcounter[i] && cur.type[i] == nxt.type[i] && cur.sub[i] == nxt.sub[i];
-    if (same) continue;
+    // all twelve loads up front (no short-circuit: each would be its own DRAM round trip)
+    long long ct = __double_as_longlong(cur.time[i]), nt = __double_as_longlong(nxt.time[i]);
+    long long cp = __double_as_longlong(cur.pot[i]), np = __double_as_longlong(nxt.pot[i]);
     int oldp = cur.partner[i], newp = nxt.partner[i];
-    cur.time[i] = nxt.time[i]; cur.pot[i] = nxt.pot[i]; cur.partner[i] = newp; cur.pcounter[i] = nxt.pcounter[i];
-    cur.type[i] = nxt.type[i]; cur.sub[i] = nxt.sub[i];
+    i64 cc = cur.pcounter[i], nc = nxt.pcounter[i];
+    uint8_t cty = cur.type[i], nty = nxt.type[i], csb = cur.sub[i], nsb = nxt.sub[i];
+    bool same = (ct == nt) & (cp == np) & (oldp == newp) & (cc == nc) & (cty == nty) & (csb == nsb);
+    if (same) continue;
+    cur.time[i] = __longlong_as_double(nt); cur.pot[i] = __longlong_as_double(np); cur.partner[i] = newp; cur.pcounter[i] = nc;
+    cur.type[i] = nty; cur.sub[i] = nsb;
     if (oldp > i) queue_next[atomicAdd(nqueue_next, 1)] = oldp;
     if (newp > i && newp != oldp) queue_next[atomicAdd(nqueue_next, 1)] = newp;
     }
@@ -1038,7 +1058,6 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     TRY(dalloc(c, &c->d_cell_start, (size_t)P.ncell + 1)); TRY(dalloc(c, &c->d_sorted_atom, n1));
     TRY(dalloc(c, &c->d_sx, n1)); TRY(dalloc(c, &c->d_sy, n1)); TRY(dalloc(c, &c->d_sz, n1));
     TRY(dalloc(c, &c->d_srec, n1));
-    TRY(dalloc(c, &c->d_stype, n1));
     TRY(dalloc(c, &c->d_sum, 4));
     P.surv = nullptr; P.surv_n = nullptr; P.surv_np = nullptr;
     TRY(dalloc(c, &P.spos, n1));
@@ -1056,7 +1075,7 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
         TRY(dalloc(c, &P.surv, (size_t)R0_SURV_CAP * n1)); TRY(dalloc(c, &P.surv_n, n1)); TRY(dalloc(c, &P.surv_np, n1));
     }
     P.cell_start = c->d_cell_start; P.sorted_atom = c->d_sorted_atom;
-    P.sx = c->d_sx; P.sy = c->d_sy; P.sz = c->d_sz; P.srec = c->d_srec; P.stype = c->d_stype;
+    P.sx = c->d_sx; P.sy = c->d_sy; P.sz = c->d_sz; P.srec = c->d_srec;
     std::vector<int> leaf_atom;
     cbt_leaf_permutation(n, leaf_atom);
     TRY(dupload(c, &c->d_leaf_atom, leaf_atom.data(), (size_t)n));
@@ -1153,7 +1172,7 @@ int sdmd_cuda_host_unregister(void *ptr) {
     cudaGetLastError();
     return 0;
 }
-void sdmd_cuda_set_timing(sdmd_ctx *c, int on) { c->timing = on != 0; }
+void sdmd_cuda_set_timing(sdmd_ctx *c, int on) { c->timing = on < 0 ? 0 : on; }
 
 static int bump_epoch(sdmd_ctx *c);
 static int pull_ctl(sdmd_ctx *c) {
@@ -1331,7 +1350,7 @@ static int cell_build_impl(sdmd_ctx *c, int parts, bool bump) {
     CK(cudaMemcpyAsync(c->cell_cursor, c->d_cell_start, ((size_t)m + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
     k_cell_scatter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_cursor, c->d_sorted_atom);
     k_cell_finish<<<grid_for(m, 128), 128, 0, c->stream>>>(c->P, c->d_cell_start, c->d_sorted_atom);
-    k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_sx, c->d_sy, c->d_sz, c->d_srec, c->d_stype, parts);
+    k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_sx, c->d_sy, c->d_sz, c->d_srec, parts);
     c->launches += 7;
     if (bump) TRY(bump_epoch(c));
     c->cells_fresh = true;
@@ -1367,7 +1386,7 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
         }
         if (late) {
             CK(cudaStreamWaitEvent(c->stream, late, 0));
-            k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_sx, c->d_sy, c->d_sz, c->d_srec, c->d_stype, 2);
+            k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_sx, c->d_sy, c->d_sz, c->d_srec, 2);
             c->launches++;
         }
         k_predict_all_round<<<grid, 128, 0, c->stream>>>(c->P, B, B, nullptr, nullptr, 0, c->npair, c->second, c->bp_time, c->bp_j,
@@ -1378,8 +1397,11 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
     struct { int nq[16]; unsigned long long sum; } h;
     {
         Timer t2(c, "predict_all_fixup");
-        k_predict_all_resolve<<<grid1, 256, 0, c->stream>>>(c->P, B, c->pcount, c->pwho, c->second, c->bp_time, c->bp_j, c->queue_a,
-                                                            c->nqueue, c->npair, c->d_sum);
+        {
+            Timer t3(c, "fixup_resolve", 2);
+            k_predict_all_resolve<<<grid1, 256, 0, c->stream>>>(c->P, B, c->pcount, c->pwho, c->second, c->bp_time, c->bp_j, c->queue_a,
+                                                                c->nqueue, c->npair, c->d_sum);
+        }
         c->launches++;
         int *qa = c->queue_a, *qb = c->queue_b;
         int qgrid = 148 * 4;
@@ -1388,6 +1410,7 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
             // a few relaxation rounds back to back (queue lengths stay on the device), then one look at the result
             int burst = (slot == 0) ? 2 : 3;
             for (int r = 0; r < burst && slot + 1 < NQ; r++, slot++) {
+                Timer t4(c, slot == 0 ? "fixup_round1" : "fixup_later", 2);
                 k_predict_all_round<<<qgrid, 128, 0, c->stream>>>(c->P, B, C, qa, c->nqueue + slot, slot + 1, c->npair, c->second, c->bp_time,
                                                                   c->bp_j, c->pcount, c->pwho, c->d_sum, g_base);
                 k_predict_all_commit<<<qgrid, 256, 0, c->stream>>>(c->P, B, C, qa, c->nqueue + slot, qb, c->nqueue + slot + 1);
