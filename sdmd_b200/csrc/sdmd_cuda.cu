@@ -168,24 +168,73 @@ __global__ void k_cell_index(DevP D, int *cell_of, int *cell_count) {
     atomicAdd(&cell_count[cell], 1);
 }
 
-// exclusive scan of cell_count[0..m) -> cell_start[0..m], three passes, 2048 items per block
+// exclusive scan of cell_count[0..m) -> cell_start[0..m], 2048 items per block:
+//   k_scan_local   per-block exclusive scan (4 items per thread, shuffle scan per warp, one pass over the warp sums)
+//   k_scan_finish  every block sums the totals of the blocks before it (a few hundred values), adds the offset and also
+//                  fills the scatter cursors; for very large grids (> SCAN_DIRECT_BLOCKS blocks) the block totals are
+//                  scanned by k_scan_blocks and added by k_scan_add instead
 #define SCAN_ITEMS 2048
-__global__ void k_scan_local(const int *in, int *out, int *block_sum, int m) {
-    __shared__ int s[SCAN_ITEMS];
-    int base = blockIdx.x * SCAN_ITEMS;
-    for (int t = threadIdx.x; t < SCAN_ITEMS; t += blockDim.x) s[t] = (base + t < m) ? in[base + t] : 0;
-    __syncthreads();
-    // Hillis-Steele inclusive scan in shared memory (double buffered through registers)
-    for (int off = 1; off < SCAN_ITEMS; off <<= 1) {
-        int v[SCAN_ITEMS / 512];
-        for (int q = 0, t = threadIdx.x; t < SCAN_ITEMS; t += blockDim.x, q++) v[q] = (t >= off) ? s[t - off] : 0;
-        __syncthreads();
-        for (int q = 0, t = threadIdx.x; t < SCAN_ITEMS; t += blockDim.x, q++) s[t] += v[q];
-        __syncthreads();
+#define SCAN_DIRECT_BLOCKS 2048
+__device__ __forceinline__ int d_block_scan_excl(int v, int *total) {   // 512 threads
+    __shared__ int wsum[16];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += t;
     }
-    for (int t = threadIdx.x; t < SCAN_ITEMS; t += blockDim.x)
-        if (base + t < m) out[base + t] = s[t] - in[base + t];  // exclusive
-    if (threadIdx.x == 0) block_sum[blockIdx.x] = s[SCAN_ITEMS - 1];
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < 16 ? wsum[lane] : 0;
+#pragma unroll
+        for (int off = 1; off < 16; off <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, s, off);
+            if (lane >= off) s += t;
+        }
+        if (lane < 16) wsum[lane] = s;   // inclusive over warps
+    }
+    __syncthreads();
+    int before = w ? wsum[w - 1] : 0;
+    *total = wsum[15];
+    return before + inc - v;
+}
+__global__ void __launch_bounds__(512) k_scan_local(const int *in, int *out, int *block_sum, int m) {
+    int t0 = blockIdx.x * SCAN_ITEMS + threadIdx.x * 4;
+    int v[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) v[q] = (t0 + q < m) ? in[t0 + q] : 0;
+    int total;
+    int ex = d_block_scan_excl(v[0] + v[1] + v[2] + v[3], &total);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (t0 + q < m) out[t0 + q] = ex;
+        ex += v[q];
+    }
+    if (threadIdx.x == 0) block_sum[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(512) k_scan_finish(int *out, int *cursor, const int *block_sum, int m, int nb) {
+    __shared__ int red[16];
+    __shared__ int s_off;
+    int part = 0;
+    for (int q = threadIdx.x; q < (int)blockIdx.x; q += blockDim.x) part += block_sum[q];
+#pragma unroll
+    for (int off = 16; off; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int q = 0; q < 16; q++) s += red[q];
+        s_off = s;
+        if ((int)blockIdx.x == nb - 1) { int tot = s + block_sum[nb - 1]; out[m] = tot; cursor[m] = tot; }
+    }
+    __syncthreads();
+    int off = s_off;
+    int t0 = blockIdx.x * SCAN_ITEMS + threadIdx.x * 4;
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (t0 + q < m) { int v = out[t0 + q] + off; out[t0 + q] = v; cursor[t0 + q] = v; }
 }
 __global__ void k_scan_blocks(int *block_sum, int nb) {
     // single thread block; nb is small (<= a few thousand)
@@ -1185,10 +1234,10 @@ static int push_ctl(sdmd_ctx *c) {
     return 0;
 }
 // invalidate every cached candidate list (link list rebuilt / replaced from the host)
-static int bump_epoch(sdmd_ctx *c) {
-    TRY(pull_ctl(c));
-    c->h_ctl->cc_epoch++;
-    CK(cudaMemcpyAsync(&c->d_ctl->cc_epoch, &c->h_ctl->cc_epoch, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+__global__ void k_bump_epoch(Ctl *ctl) { ctl->cc_epoch++; }
+static int bump_epoch(sdmd_ctx *c) {   // on the device, in stream order: no host round trip
+    k_bump_epoch<<<1, 1, 0, c->stream>>>(c->d_ctl);
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -1345,9 +1394,14 @@ static int cell_build_impl(sdmd_ctx *c, int parts, bool bump) {
     k_cell_index<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_count);
     int nb = (m + SCAN_ITEMS - 1) / SCAN_ITEMS;
     k_scan_local<<<nb, 512, 0, c->stream>>>(c->cell_count, c->d_cell_start, c->scan_tmp, m);
-    k_scan_blocks<<<1, 32, 0, c->stream>>>(c->scan_tmp, nb);
-    k_scan_add<<<grid_for(m, 256), 256, 0, c->stream>>>(c->d_cell_start, c->scan_tmp, m, nb);
-    CK(cudaMemcpyAsync(c->cell_cursor, c->d_cell_start, ((size_t)m + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    if (nb <= SCAN_DIRECT_BLOCKS) {
+        k_scan_finish<<<nb, 512, 0, c->stream>>>(c->d_cell_start, c->cell_cursor, c->scan_tmp, m, nb);
+        c->launches -= 1;
+    } else {
+        k_scan_blocks<<<1, 32, 0, c->stream>>>(c->scan_tmp, nb);
+        k_scan_add<<<grid_for(m, 256), 256, 0, c->stream>>>(c->d_cell_start, c->scan_tmp, m, nb);
+        CK(cudaMemcpyAsync(c->cell_cursor, c->d_cell_start, ((size_t)m + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    }
     k_cell_scatter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_cursor, c->d_sorted_atom);
     k_cell_finish<<<grid_for(m, 128), 128, 0, c->stream>>>(c->P, c->d_cell_start, c->d_sorted_atom);
     k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_sx, c->d_sy, c->d_sz, c->d_srec, parts);
@@ -1527,13 +1581,11 @@ int sdmd_cuda_prepare(sdmd_ctx *c, const double *x, const double *y, const doubl
     c->g_filled = n_gauss;                              // fresh thermostat stream: drop what was fed before
     c->h_ctl->g_filled = n_gauss;
     c->h_ctl->g_pos = 0;
-    c->h_ctl->cc_epoch++;                               // new link list: cached candidate lists are void
     CK(cudaMemcpyAsync(&c->d_ctl->g_filled, &c->h_ctl->g_filled, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(&c->d_ctl->g_pos, &c->h_ctl->g_pos, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(&c->d_ctl->cc_epoch, &c->h_ctl->cc_epoch, sizeof(c->h_ctl->cc_epoch), cudaMemcpyHostToDevice, c->stream));
     k_pbc_full<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->P);
     c->launches++;
-    TRY(cell_build_impl(c, 1, false));
+    TRY(cell_build_impl(c, 1, true));
     TRY(predict_all_impl(c, c->ev_copy));
     return sdmd_cuda_cbt_build(c);
 }
