@@ -57,6 +57,7 @@ struct sdmd_ctx {
     i64 trace_cap = 0;
     unsigned long long *d_sum = nullptr;
     bool cells_fresh = false;
+    bool counters_known = false;         // h_ctl's g_pos / pair_predictions match the device (nothing consumed since the last pull)
     int timing = 1;                      // 0 off, 1 per stage, 2 also the sub-stages of predict_all's fix-up
     std::map<std::string, KStat> kstat;
     std::vector<PendingEv> pending;      // launched, not yet resolved (kept asynchronous)
@@ -1227,8 +1228,12 @@ static int bump_epoch(sdmd_ctx *c);
 static int pull_ctl(sdmd_ctx *c) {
     CK(cudaMemcpyAsync(c->h_ctl, c->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    c->counters_known = true;
     return 0;
 }
+// the gaussian cursor and the evaluation counter only move on the device inside Predict(list) / DoEvent / the event loop;
+// between those the host copy is current and the full-system pass needs no round trip to read them
+static int need_counters(sdmd_ctx *c) { return c->counters_known ? 0 : pull_ctl(c); }
 static int push_ctl(sdmd_ctx *c) {
     CK(cudaMemcpyAsync(c->d_ctl, c->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream));
     return 0;
@@ -1337,7 +1342,7 @@ int64_t sdmd_cuda_rng_available(const sdmd_ctx *c) {
 int sdmd_cuda_rng_feed(sdmd_ctx *c, const double *g, int64_t n) {
     CK(cudaSetDevice(c->device));
     if (n <= 0) return 0;
-    TRY(pull_ctl(c));
+    TRY(need_counters(c));
     i64 cap = c->P.g_cap;
     if (c->g_filled + n - c->h_ctl->g_pos > cap) return set_err(SDMD_ERR_BAD_ARG, "gaussian ring overflow");
     i64 pos = c->g_filled % cap;
@@ -1353,7 +1358,7 @@ int sdmd_cuda_rng_feed(sdmd_ctx *c, const double *g, int64_t n) {
 
 // move the consumption cursor (benchmarks replay the same synthetic stream; must stay within the ring)
 int sdmd_cuda_rng_seek(sdmd_ctx *c, int64_t pos) {
-    TRY(pull_ctl(c));
+    TRY(need_counters(c));
     if (pos < 0 || pos > c->g_filled || c->g_filled - pos > c->P.g_cap) return set_err(SDMD_ERR_BAD_ARG, "rng_seek out of range");
     c->h_ctl->g_pos = pos;
     CK(cudaMemcpyAsync(&c->d_ctl->g_pos, &c->h_ctl->g_pos, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
@@ -1362,7 +1367,7 @@ int sdmd_cuda_rng_seek(sdmd_ctx *c, int64_t pos) {
 
 // forget everything fed so far (fresh stream)
 int sdmd_cuda_rng_reset(sdmd_ctx *c) {
-    TRY(pull_ctl(c));
+    TRY(need_counters(c));
     c->g_filled = 0;
     c->h_ctl->g_filled = 0;
     c->h_ctl->g_pos = 0;
@@ -1505,7 +1510,7 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
 int sdmd_cuda_predict_all(sdmd_ctx *c) {
     CK(cudaSetDevice(c->device));
     if (!c->cells_fresh) return set_err(SDMD_ERR_STATE, "predict_all needs a fresh cell_build (cell-sorted tiles)");
-    TRY(pull_ctl(c));
+    TRY(need_counters(c));
     return predict_all_impl(c, nullptr);
 }
 
@@ -1519,6 +1524,7 @@ int sdmd_cuda_predict(sdmd_ctx *c, const int32_t *renew) {
         int *d_list = nullptr;
         CK(cudaMalloc((void **)&d_list, sizeof(int) * cnt));
         CK(cudaMemcpyAsync(d_list, renew + 1, sizeof(int) * cnt, cudaMemcpyHostToDevice, c->stream));
+        c->counters_known = false;
         k_predict_list_n<<<1, 1, 0, c->stream>>>(c->P, d_list, cnt);
         c->launches++;
         CK(cudaStreamSynchronize(c->stream));
@@ -1526,6 +1532,7 @@ int sdmd_cuda_predict(sdmd_ctx *c, const int32_t *renew) {
         CK(cudaGetLastError());
         return 0;
     }
+    c->counters_known = false;
     k_predict_list<<<1, 1, 0, c->stream>>>(c->P, cnt > 0 ? renew[1] : 0, cnt > 1 ? renew[2] : 0);
     c->launches++;
     CK(cudaGetLastError());
@@ -1568,7 +1575,9 @@ int sdmd_cuda_prepare(sdmd_ctx *c, const double *x, const double *y, const doubl
         CK(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     }
-    TRY(pull_ctl(c));                                   // also drains earlier work that may still read the arrays
+    TRY(need_counters(c));
+    CK(cudaEventRecord(c->ev_main, c->stream));         // the copy stream must not overwrite what earlier work still reads
+    CK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
     size_t b = ((size_t)c->n + 1) * sizeof(double);
     CK(cudaMemcpyAsync(c->P.x, x, b, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->P.y, y, b, cudaMemcpyHostToDevice, c->stream));
@@ -1661,6 +1670,7 @@ int sdmd_cuda_cell_move(sdmd_ctx *c, int32_t atom) {
 
 int sdmd_cuda_do_event(sdmd_ctx *c) {
     CK(cudaSetDevice(c->device));
+    c->counters_known = false;
     k_do_event<<<1, 1, 0, c->stream>>>(c->P);
     c->launches++;
     c->cells_fresh = false;
@@ -1766,11 +1776,13 @@ int sdmd_cuda_run(sdmd_ctx *c, double t_until, int64_t max_iter, struct sdmd_tra
     sdmd_trace_rec *dtr = (trace && trace_cap > 0) ? c->d_trace : nullptr;
     cudaEventRecord(c->ev0, c->stream);
     if (c->n <= SDMD_SMALL_N) {
+        c->counters_known = false;
         k_run_cta<<<1, 256, 0, c->stream>>>(c->P, t_until, iter_limit, dtr, trace_cap);
         c->launches++;
         CK(cudaGetLastError());
         TRY(pull_ctl(c));
     } else {
+        c->counters_known = false;
         k_loop_head<<<1, 1, 0, c->stream>>>(c->P, t_until, iter_limit);
         c->launches++;
         const int batch = 64;
@@ -1826,6 +1838,7 @@ int sdmd_cuda_run_many(sdmd_ctx **ctxs, int n, const double *t_until, int64_t ma
     CK(cudaMalloc((void **)&d_args, sizeof(MultiArg) * n));
     CK(cudaMemcpyAsync(d_args, args.data(), sizeof(MultiArg) * n, cudaMemcpyHostToDevice, c0->stream));
     cudaEventRecord(c0->ev0, c0->stream);
+    for (int k = 0; k < n; k++) ctxs[k]->counters_known = false;
     k_run_cta_multi<<<n, 256, 0, c0->stream>>>(d_args);
     c0->launches++;
     cudaEventRecord(c0->ev1, c0->stream);
