@@ -1003,6 +1003,18 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     P.thermostat_on = v->thermostat_on;
     P.method_ding = v->method_ding;
     P.hydrogen_bond = v->hydrogen_bond;
+    if (P.hydrogen_bond) {
+        // HBTime / HBNeighborTime (TimePrediction.c:292-578) do nothing for an atom with no donor/acceptor role, no bond,
+        // no neighbour entries and interactionType already NoEvent; a system made only of such atoms (GEL boxes) can
+        // never create any, so the HB stages are switched off for it instead of re-reading four arrays per prediction
+        bool any = false;
+        for (int i = 1; i <= v->natom && !any; i++) {
+            int r = v->hb_role ? v->hb_role[i] : 0;
+            any = r == 'A' || r == 'D' || r == 'S' || (v->hb_bond && v->hb_bond[i]) || (v->hbn_status && v->hbn_status[i]) ||
+                  (v->hb_itype && v->hb_itype[i] != SDMD_HB_NOEVENT);
+        }
+        if (!any) P.hydrogen_bond = 0;
+    }
     P.gel_mode = v->gel_mode;
     for (int k = 0; k < 3; k++) P.hb_barrier[k] = v->hb_barrier[k];
 
