@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "sdmd_cuda_cell_move", "sdmd_cuda_do_event", "sdmd_cuda_potential_energy", "sdmd_cuda_kinetic_energy",
     "sdmd_cuda_run", "sdmd_cuda_run_many", "sdmd_cuda_potential_energy_many", "sdmd_cuda_get_stats", "sdmd_cuda_set_temperature",
     "sdmd_remd_rearrange", "sdmd_remd_nccl_unique_id", "sdmd_remd_nccl_init", "sdmd_remd_seed_server", "sdmd_remd_exchange", "sdmd_host_glibc_rand",
-    "sdmd_cuda_kernel_ms", "sdmd_cuda_kernel_stats", "sdmd_cuda_reset_kernel_stats", "sdmd_cuda_set_timing",
+    "sdmd_cuda_kernel_ms", "sdmd_cuda_kernel_stats", "sdmd_cuda_reset_kernel_stats", "sdmd_cuda_set_timing", "sdmd_cuda_set_loop_mode",
     "sdmd_cuda_launch_count", "sdmd_cuda_stream", "sdmd_cuda_phase_cycles",
 ]
 
@@ -125,6 +125,7 @@ def lib():
     L.sdmd_cuda_reset_kernel_stats.argtypes = [vp]
     L.sdmd_cuda_reset_kernel_stats.restype = None
     L.sdmd_cuda_set_timing.argtypes = [vp, C.c_int]
+    L.sdmd_cuda_set_loop_mode.argtypes = [vp, C.c_int]
     L.sdmd_cuda_set_timing.restype = None
     L.sdmd_cuda_launch_count.argtypes = [vp]
     L.sdmd_cuda_launch_count.restype = C.c_int64
@@ -316,6 +317,7 @@ class Replica:
 
     def reset_kernel_stats(self): self.L.sdmd_cuda_reset_kernel_stats(self.h)
     def set_timing(self, on): self.L.sdmd_cuda_set_timing(self.h, int(on))   # 0 off, 1 stages, 2 + fix-up sub-stages
+    def set_loop_mode(self, mode): _check(self.L.sdmd_cuda_set_loop_mode(self.h, int(mode)), "set_loop_mode")   # 0 auto, 1 one CTA, 2 sweep
     def launch_count(self): return int(self.L.sdmd_cuda_launch_count(self.h))
     def stream(self): return self.L.sdmd_cuda_stream(self.h)
 

@@ -57,6 +57,7 @@ struct sdmd_ctx {
     i64 trace_cap = 0;
     unsigned long long *d_sum = nullptr;
     bool cells_fresh = false;
+    int loop_mode = SDMD_LOOP_AUTO;
     bool counters_known = false;         // h_ctl's g_pos / pair_predictions match the device (nothing consumed since the last pull)
     int timing = 1;                      // 0 off, 1 per stage, 2 also the sub-stages of predict_all's fix-up
     std::map<std::string, KStat> kstat;
@@ -1234,6 +1235,12 @@ int sdmd_cuda_host_unregister(void *ptr) {
     cudaGetLastError();
     return 0;
 }
+int sdmd_cuda_set_loop_mode(sdmd_ctx *c, int mode) {
+    if (mode != SDMD_LOOP_AUTO && mode != SDMD_LOOP_ONE_CTA && mode != SDMD_LOOP_SWEEP) return set_err(SDMD_ERR_BAD_ARG, "loop mode");
+    if (mode == SDMD_LOOP_ONE_CTA && c->n > SDMD_SMALL_N) return set_err(SDMD_ERR_UNSUPPORTED, "one-CTA loop: system too large");
+    c->loop_mode = mode;
+    return 0;
+}
 void sdmd_cuda_set_timing(sdmd_ctx *c, int on) { c->timing = on < 0 ? 0 : on; }
 
 static int bump_epoch(sdmd_ctx *c);
@@ -1787,7 +1794,7 @@ int sdmd_cuda_run(sdmd_ctx *c, double t_until, int64_t max_iter, struct sdmd_tra
     TRY(push_ctl(c));
     sdmd_trace_rec *dtr = (trace && trace_cap > 0) ? c->d_trace : nullptr;
     cudaEventRecord(c->ev0, c->stream);
-    if (c->n <= SDMD_SMALL_N) {
+    if (c->loop_mode == SDMD_LOOP_ONE_CTA || (c->loop_mode == SDMD_LOOP_AUTO && c->n <= SDMD_SMALL_N)) {
         c->counters_known = false;
         k_run_cta<<<1, 256, 0, c->stream>>>(c->P, t_until, iter_limit, dtr, trace_cap);
         c->launches++;

@@ -51,9 +51,13 @@ def test_predict_all_and_cbt_match_reference(capi, case):
 
 
 @pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8"])
-def test_device_event_loop_matches_reference(capi, case):
+@pytest.mark.parametrize("loop_mode", [0, 2], ids=["one_cta", "sweep"])
+def test_device_event_loop_matches_reference(capi, case, loop_mode):
+    """loop_mode 2 forces the large-system driver (grid-wide advance + one event block per event) onto the protein
+    cases too, so both loop drivers are pinned to the reference trace with bonds, HB and HB-neighbour events."""
     pre, post, fin = load_case(case)
     hv, r = _replica(capi, pre)
+    r.set_loop_mode(loop_mode)
     if int(pre.extra.get("warm", [0])[0]):
         r.upload_celllist(pre.extra["celllist"])
     else:
