@@ -320,12 +320,12 @@ __global__ void k_cell_permute(DevP D, const int *sorted_atom, double *sx, doubl
     double2 *rp = reinterpret_cast<double2 *>(&srec[p]);
     if (parts & 1) {
         D.spos[j] = p;
-        D.scx[p] = D.cell_idx[3 * j];
         double x = D.x[j], y = D.y[j], z = D.z[j];
         int t = D.type[j];
+        int cx = D.cell_idx[3 * j], cy = D.cell_idx[3 * j + 1], cz = D.cell_idx[3 * j + 2];
         sx[p] = x; sy[p] = y; sz[p] = z;
         rp[0] = make_double2(x, y);
-        *reinterpret_cast<int2 *>(rp + 3) = make_int2(t, j);
+        *reinterpret_cast<int4 *>(rp + 3) = make_int4(t, j, (int)((unsigned)cx | ((unsigned)cy << 16)), cz);
         if (parts & 2) {
             rp[1] = make_double2(z, D.vx[j]);
             rp[2] = make_double2(D.vy[j], D.vz[j]);
@@ -991,6 +991,7 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
         P.box[k] = v->box[k];
         P.cellnum[k] = (int)floor(v->box[k] / v->cutoffr);
         if (P.cellnum[k] < 3) P.cellnum[k] = 3;
+        if (P.cellnum[k] > 65535) { delete c; return set_err(SDMD_ERR_UNSUPPORTED, "more than 65535 cells along one axis"); }
     }
     for (int k = 0; k < 3; k++) P.cellsize[k] = v->box[k] / P.cellnum[k];
     long long ncell = (long long)P.cellnum[0] * P.cellnum[1] * P.cellnum[2];
@@ -1124,7 +1125,6 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     TRY(dalloc(c, &c->d_sum, 4));
     P.surv = nullptr; P.surv_n = nullptr; P.surv_np = nullptr;
     TRY(dalloc(c, &P.spos, n1));
-    TRY(dalloc(c, &P.scx, n1));
     P.nbr = nullptr;
     if ((long long)P.ncell < (1 << 26) && (long long)P.ncell * 27 * 4 <= (512LL << 20)) {
         unsigned int *nbr = nullptr;

@@ -59,7 +59,7 @@ struct Slot {
 struct __align__(16) SRec {
     double x, y, z, vx, vy, vz;
     int type, atom;
-    double pad;
+    unsigned cxy, cz;            // cell index: x | y << 16, z
 };
 
 struct DevP {
@@ -117,7 +117,6 @@ struct DevP {
     int *surv_n;             // count, or -1 when the list overflowed (atom re-scanned in the evaluation kernel)
     int *surv_np;            // pair evaluations counted by the filter
     int *spos;               // sorted position of every atom (inverse of sorted_atom)
-    int *scx;                // x cell index of every sorted position
     // static neighbour table: for cell c and scan slot k (DMD.c:118-120 order) the neighbour cell (bits 0-25) and the
     // minimum-image shift code per axis (2 bits each from bit 26: 0 none, 1 = -box, 2 = +box); NULL for huge grids
     const unsigned int *nbr;
@@ -569,11 +568,11 @@ __device__ inline void d_collision_time_2stage(const DevP &D, const SlotSrc &S, 
 __device__ inline void d_r0_filter(const DevP &D, int p_self) {
     int i = D.sorted_atom[p_self];
     double x = D.sx[p_self], y = D.sy[p_self], z = D.sz[p_self];
-    int cx = D.cell_idx[3 * i], cy = D.cell_idx[3 * i + 1], cz = D.cell_idx[3 * i + 2];
+    int cx = D.cell_idx[3 * i], cy = D.cell_idx[3 * i + 1], cz = D.cell_idx[3 * i + 2];   // (the 16-byte record tail measured slower here)
     bool has_cm = D.cm_off[i + 1] > D.cm_off[i];
-    int hb_i = D.hb_bond[i];
+    int hb_i = 0;
     int h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-    if (D.hydrogen_bond) { h0 = D.hbn_partner[5 * i + 1]; h1 = D.hbn_partner[5 * i + 2]; h2 = D.hbn_partner[5 * i + 3]; h3 = D.hbn_partner[5 * i + 4]; }
+    if (D.hydrogen_bond) { hb_i = D.hb_bond[i]; h0 = D.hbn_partner[5 * i + 1]; h1 = D.hbn_partner[5 * i + 2]; h2 = D.hbn_partner[5 * i + 3]; h3 = D.hbn_partner[5 * i + 4]; }
     bool need_j = has_cm || hb_i != 0 || h0 != 0;
     unsigned int *out = D.surv + (size_t)p_self * R0_SURV_CAP;
     int ns = 0, npair = 0;
@@ -611,8 +610,8 @@ __device__ inline void d_collision_time_from_list(const DevP &D, const SlotSrc &
     int ns = D.surv_n[p_self];
     const unsigned int *in = D.surv + (size_t)p_self * R0_SURV_CAP;
     int i = me.i;
-    bool has_cm = D.cm_off[i + 1] > D.cm_off[i];
-    int type_i = D.type[i];
+    bool has_cm = me.cm1 > me.cm0;
+    int type_i = me.type;
     int hb_i = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0;
     if (DUP) {
         hb_i = D.hb_bond[i];
@@ -815,6 +814,23 @@ __device__ __forceinline__ Self d_load_self(const DevP &D, int i) {
     return me;
 }
 
+// the same from the cell-sorted record at position p: one coalesced 64-byte read instead of ten gathers by atom id
+__device__ __forceinline__ Self d_load_self_sorted(const DevP &D, int p) {
+    const double2 *rp = reinterpret_cast<const double2 *>(&D.srec[p]);
+    double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
+    int4 q = __ldg(reinterpret_cast<const int4 *>(rp + 3));
+    Self me;
+    me.i = q.y;
+    me.x = r0.x; me.y = r0.y; me.z = r1.x;
+    me.vx = r1.y; me.vy = r2.x; me.vz = r2.y;
+    me.cx = (int)((unsigned)q.z & 0xffffu); me.cy = (int)((unsigned)q.z >> 16); me.cz = q.w;
+    me.counter = D.ev_counter[q.y];
+    me.npair = 0;
+    me.type = q.x;
+    me.cm0 = D.cm_off[q.y]; me.cm1 = D.cm_off[q.y + 1];
+    return me;
+}
+
 // ResetTarget (ToolFunctions.c:504-514) leaves potential / subEventType / partnerCounter untouched
 __device__ __forceinline__ Slot d_reset_slot(double pot, int sub, i64 pcounter) {
     Slot s;
@@ -830,7 +846,7 @@ template <bool SORTED, bool R0 = false>
 __device__ inline Slot d_predict_atom(const DevP &D, const SlotSrc &S, int i, Slot cur, double gauss, int dup_limit, int *npair,
                                       double *second = nullptr, PairBest *pb = nullptr, int surv_pos = -1) {
     if (D.is_cons[i]) { cur.time = SD_INF; return cur; }
-    Self me = d_load_self(D, i);
+    Self me = (SORTED && surv_pos >= 0) ? d_load_self_sorted(D, surv_pos) : d_load_self(D, i);
     if (!D.gel_mode) d_bond_time(D, S, me, cur, dup_limit);
     if (R0 && surv_pos >= 0 && D.surv_n[surv_pos] >= 0) d_collision_time_from_list<false>(D, S, me, cur, surv_pos, 0);
     else if (R0) d_collision_time_2stage<false>(D, S, me, cur, 0);
