@@ -110,7 +110,6 @@ struct DevP {
     const int *cell_start;   // [ncell + 1], 0-based cell
     const int *sorted_atom;  // [n]
     const double *sx, *sy, *sz;   // positions alone: what the neighbour filter streams
-    const int *stype;
     const struct SRec *srec;      // full record per sorted position: what the evaluation stage gathers
     // round-0 filter output: per sorted position up to R0_SURV_CAP candidates inside the scan sphere
     unsigned int *surv;      // (sorted position of j) | (scan slot k << 27)
@@ -121,6 +120,12 @@ struct DevP {
     // minimum-image shift code per axis (2 bits each from bit 26: 0 none, 1 = -box, 2 = +box); NULL for huge grids
     const unsigned int *nbr;
     double cut2_loose;       // cut2 * (1 + 1e-9): the filter keeps a superset, the evaluation re-tests exactly
+    // single-precision working set of the neighbour filter: position relative to the atom's own cell corner (so a
+    // neighbour cell is just an offset of whole cells, periodic wrap included) + the atom id; home cell per position
+    const float4 *sloc;
+    const int *scell;
+    float cut2_f32;          // cut2 * (1 + 1e-4), rounded up: superset sphere of the single-precision test
+    float cellsize_f[3];
 };
 
 // neighbour-cell offsets, DMD.c:118-120
@@ -565,10 +570,14 @@ __device__ inline void d_collision_time_2stage(const DevP &D, const SlotSrc &S, 
 
 // Round-0 stage 1 as its own light kernel body: skip filters, evaluation count, 0.9*cutoff sphere test over the
 // cell-sorted tiles; survivors go to HBM in scan order (they are few: ~6 of ~41 candidates at 8 A spacing).
+// The filter only has to keep a SUPERSET of the candidates inside the scan sphere (the evaluation stage re-tests every
+// survivor in double precision with the reference's arithmetic), so it works in single precision on cell-local
+// coordinates: |coordinate| < 2 cells, error of r2 below 1e-3 A^2 against a margin of 1e-4 * cut2 (~7e-3 A^2 at 9 A).
+// Relative to the own cell corner a neighbour cell is an offset of whole cells; no PBCShift is needed.
 __device__ inline void d_r0_filter(const DevP &D, int p_self) {
-    int i = D.sorted_atom[p_self];
-    double x = D.sx[p_self], y = D.sy[p_self], z = D.sz[p_self];
-    int cx = D.cell_idx[3 * i], cy = D.cell_idx[3 * i + 1], cz = D.cell_idx[3 * i + 2];   // (the 16-byte record tail measured slower here)
+    float4 me = __ldg(&D.sloc[p_self]);
+    int i = __float_as_int(me.w);
+    int c = D.scell[p_self];
     bool has_cm = D.cm_off[i + 1] > D.cm_off[i];
     int hb_i = 0;
     int h0 = 0, h1 = 0, h2 = 0, h3 = 0;
@@ -576,23 +585,32 @@ __device__ inline void d_r0_filter(const DevP &D, int p_self) {
     bool need_j = has_cm || hb_i != 0 || h0 != 0;
     unsigned int *out = D.surv + (size_t)p_self * R0_SURV_CAP;
     int ns = 0, npair = 0;
+    const unsigned long long PX = 0xa80894054a959ULL, PY = 0x2222160111a665ULL, PZ = 0x28096084059a95ULL;   // DMD.c:118-120
+    int cx = 0, cy = 0, cz = 0;
+    if (!D.nbr) { cx = c % D.cellnum[0]; cy = (c / D.cellnum[0]) % D.cellnum[1]; cz = c / (D.cellnum[0] * D.cellnum[1]); }
+    const float cut2 = D.cut2_f32;
     for (int k = 0; k < 27; k++) {
-        double shx, shy, shz;
-        int cell = d_neighbor(D, cx, cy, cz, k, &shx, &shy, &shz);
+        int cell;
+        if (D.nbr) cell = (int)(__ldg(&D.nbr[(size_t)c * 27 + k]) & 0x3ffffffu);
+        else { int a, b, e; cell = d_neighbor_cell(D, cx, cy, cz, k, &a, &b, &e); }
+        // my position as seen from the neighbour cell's corner
+        float mx = me.x - (float)((int)((PX >> (2 * k)) & 3) - 1) * D.cellsize_f[0];
+        float my = me.y - (float)((int)((PY >> (2 * k)) & 3) - 1) * D.cellsize_f[1];
+        float mz = me.z - (float)((int)((PZ >> (2 * k)) & 3) - 1) * D.cellsize_f[2];
         int p1 = D.cell_start[cell + 1];
         for (int p = D.cell_start[cell]; p < p1; p++) {
             if (p == p_self) continue;
+            float4 q = __ldg(&D.sloc[p]);
             if (need_j) {
-                int j = D.sorted_atom[p];
+                int j = __float_as_int(q.w);
                 if (has_cm && (d_cm_flags(D, i, j) & SDMD_BOND_CONNECT)) continue;
                 if (hb_i == j) continue;
                 if ((h0 == j) || (h0 != 0 && (h1 == j || (h1 != 0 && (h2 == j || (h2 != 0 && h3 == j)))))) continue;
             }
             npair++;
-            double tx = D.sx[p] + shx, ty = D.sy[p] + shy, tz = D.sz[p] + shz;
-            double rx = x - tx, ry = y - ty, rz = z - tz;
-            double r2 = rx * rx + ry * ry + rz * rz;
-            if (r2 <= D.cut2_loose) {
+            float rx = mx - q.x, ry = my - q.y, rz = mz - q.z;
+            float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
+            if (r2 <= cut2) {
                 if (ns < R0_SURV_CAP) out[ns] = (unsigned)p | ((unsigned)k << 27);
                 ns++;
             }
