@@ -570,6 +570,13 @@ __device__ inline void d_collision_time_2stage(const DevP &D, const SlotSrc &S, 
 
 // Round-0 stage 1 as its own light kernel body: skip filters, evaluation count, 0.9*cutoff sphere test over the
 // cell-sorted tiles; survivors go to HBM in scan order (they are few: ~6 of ~41 candidates at 8 A spacing).
+// neighbour-cell offsets of scan slot k (DMD.c:118-120) as floats: the loop counter is warp-uniform, so these are
+// constant-bank operands
+__constant__ float c_koff[27][3] = {
+    {0, 0, 0},   {1, 0, 0},   {0, 1, 0},   {0, 0, 1},   {0, 1, 1},   {1, 0, 1},  {1, 1, 0},   {1, 1, 1},   {-1, 0, 0},
+    {0, -1, 0},  {0, 0, -1},  {0, -1, -1}, {-1, 0, -1}, {-1, -1, 0}, {-1, -1, -1}, {0, -1, 1}, {0, 1, -1},  {1, 0, -1},
+    {-1, 0, 1},  {1, -1, 0},  {-1, 1, 0},  {-1, -1, 1}, {-1, 1, -1}, {1, -1, -1}, {1, 1, -1},  {1, -1, 1},  {-1, 1, 1}};
+
 // The filter only has to keep a SUPERSET of the candidates inside the scan sphere (the evaluation stage re-tests every
 // survivor in double precision with the reference's arithmetic), so it works in single precision on cell-local
 // coordinates: |coordinate| < 2 cells, error of r2 below 1e-3 A^2 against a margin of 1e-4 * cut2 (~7e-3 A^2 at 9 A).
@@ -585,18 +592,16 @@ __device__ inline void d_r0_filter(const DevP &D, int p_self) {
     bool need_j = has_cm || hb_i != 0 || h0 != 0;
     unsigned int *out = D.surv + (size_t)p_self * R0_SURV_CAP;
     int ns = 0, npair = 0;
-    const unsigned long long PX = 0xa80894054a959ULL, PY = 0x2222160111a665ULL, PZ = 0x28096084059a95ULL;   // DMD.c:118-120
     int cx = 0, cy = 0, cz = 0;
     if (!D.nbr) { cx = c % D.cellnum[0]; cy = (c / D.cellnum[0]) % D.cellnum[1]; cz = c / (D.cellnum[0] * D.cellnum[1]); }
     const float cut2 = D.cut2_f32;
+    const float ncsx = -D.cellsize_f[0], ncsy = -D.cellsize_f[1], ncsz = -D.cellsize_f[2];
     for (int k = 0; k < 27; k++) {
         int cell;
         if (D.nbr) cell = (int)(__ldg(&D.nbr[(size_t)c * 27 + k]) & 0x3ffffffu);
         else { int a, b, e; cell = d_neighbor_cell(D, cx, cy, cz, k, &a, &b, &e); }
         // my position as seen from the neighbour cell's corner
-        float mx = me.x - (float)((int)((PX >> (2 * k)) & 3) - 1) * D.cellsize_f[0];
-        float my = me.y - (float)((int)((PY >> (2 * k)) & 3) - 1) * D.cellsize_f[1];
-        float mz = me.z - (float)((int)((PZ >> (2 * k)) & 3) - 1) * D.cellsize_f[2];
+        float mx = fmaf(c_koff[k][0], ncsx, me.x), my = fmaf(c_koff[k][1], ncsy, me.y), mz = fmaf(c_koff[k][2], ncsz, me.z);
         int p1 = D.cell_start[cell + 1];
         for (int p = D.cell_start[cell]; p < p1; p++) {
             if (p == p_self) continue;
