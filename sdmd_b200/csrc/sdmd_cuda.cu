@@ -400,8 +400,8 @@ __global__ void __launch_bounds__(128, K2_MINBLOCKS) k_predict_all_round(DevP D,
         int i = (round == 0) ? D.sorted_atom[p] : queue[p];
         Slot cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
         double g = 0;
-        if (D.thermostat_on && !D.is_cons[i]) {
-            i64 gi = g_base + D.ther_rank[i];        // g_base < g_cap (host reduces it), rank < n <= g_cap
+        if (D.thermostat_on && (D.no_cons || !D.is_cons[i])) {
+            i64 gi = g_base + (D.no_cons ? i - 1 : D.ther_rank[i]);   // g_base < g_cap (host reduces it), rank < n <= g_cap
             g = D.gauss[gi >= D.g_cap ? gi - D.g_cap : gi];
         }
         int np = 0;
@@ -1114,6 +1114,7 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     std::vector<int> rank(n1, 0);
     int r = 0;
     for (int i = 1; i <= n; i++) { rank[i] = r; if (!v->is_cons[i]) r++; }
+    P.no_cons = (r == n);   // nobody is constrained: draw index of atom i is simply i - 1
     TRY(dupload(c, (int **)&P.ther_rank, rank.data(), n1));
 
     // scratch

@@ -105,6 +105,7 @@ struct DevP {
     const double *gauss;
     i64 g_cap;
     const int *ther_rank;  // index of the gaussian atom i consumes in a full pass
+    int no_cons;           // no constrained atom at all: ther_rank[i] == i - 1
     Ctl *ctl;
     // cell-sorted tiles produced by cell_build (fresh link-list order: descending atom id inside a cell)
     const int *cell_start;   // [ncell + 1], 0-based cell
@@ -460,6 +461,8 @@ __device__ inline void d_collision_time(const DevP &D, const SlotSrc &S, Self &m
 __device__ __forceinline__ void d_r0_flush(const DevP &D, const SlotSrc &S, Self &me, Slot &cur, const int *surv_p,
                                            const unsigned char *surv_k, int ns, bool has_cm, int type_i, int hb_i, int h0, int h1,
                                            int h2, int h3) {
+    const bool seam = me.cx == 0 || me.cy == 0 || me.cz == 0 || me.cx == D.cellnum[0] - 1 || me.cy == D.cellnum[1] - 1 ||
+                      me.cz == D.cellnum[2] - 1;
     for (int s = 0; s < ns; s++) {
         int p = surv_p[s];
         int k = surv_k[s] & 0x1f;
@@ -467,8 +470,8 @@ __device__ __forceinline__ void d_r0_flush(const DevP &D, const SlotSrc &S, Self
         double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2v = __ldg(rp + 2);
         int2 ta = __ldg(reinterpret_cast<const int2 *>(rp + 3));
         int j = ta.y;
-        double shx, shy, shz;   // PBCShift via the scanned neighbour cell (arithmetic, no table: keeps the load chain short)
-        {
+        double shx = 0, shy = 0, shz = 0;   // PBCShift via the scanned neighbour cell; only atoms in a boundary cell can need one
+        if (seam) {
             int ncx, ncy, ncz;
             d_neighbor_cell(D, me.cx, me.cy, me.cz, k, &ncx, &ncy, &ncz);
             shx = d_shift1(me.cx, ncx, D.cellnum[0], D.box[0]);
@@ -868,7 +871,7 @@ struct PairBest { double bp_time, sp_time; int bp_j; };
 template <bool SORTED, bool R0 = false>
 __device__ inline Slot d_predict_atom(const DevP &D, const SlotSrc &S, int i, Slot cur, double gauss, int dup_limit, int *npair,
                                       double *second = nullptr, PairBest *pb = nullptr, int surv_pos = -1) {
-    if (D.is_cons[i]) { cur.time = SD_INF; return cur; }
+    if (!D.no_cons && D.is_cons[i]) { cur.time = SD_INF; return cur; }
     Self me = (SORTED && surv_pos >= 0) ? d_load_self_sorted(D, surv_pos) : d_load_self(D, i);
     if (!D.gel_mode) d_bond_time(D, S, me, cur, dup_limit);
     if (R0 && surv_pos >= 0 && D.surv_n[surv_pos] >= 0) d_collision_time_from_list<false>(D, S, me, cur, surv_pos, 0);
