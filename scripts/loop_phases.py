@@ -17,7 +17,7 @@ st, _ = r.run(max_iter=iters)
 p1 = np.array(list(r.phase_cycles().values()))
 d = p1 - p0
 n = max(d[7], 1)
-names = ["head", "advance", "event||gather", "gather(after)", "evaluate", "fold", "cbt", "(count)", "event only"]
+names = ["pick-up", "next AssignJob", "event||gather", "gather(after)", "evaluate", "fold", "cbt", "(count)", "event only"]
 for k, nm in enumerate(names):
     if k != 7: print(f"{nm:16s} {d[k] / n:9.0f} cycles/iteration")
 ms, cnt = r.kernel_stats("run")

@@ -60,6 +60,7 @@ struct sdmd_ctx {
     unsigned long long *d_sum = nullptr;
     bool cells_fresh = false;
     int loop_mode = SDMD_LOOP_AUTO;
+    double *x2 = nullptr, *y2 = nullptr, *z2 = nullptr, *t2 = nullptr;   // second coordinate/time buffer of the overlapped sweep
     bool counters_known = false;         // h_ctl's g_pos / pair_predictions match the device (nothing consumed since the last pull)
     int timing = 1;                      // 0 off, 1 per stage, 2 also the sub-stages of predict_all's fix-up
     std::map<std::string, KStat> kstat;
@@ -613,7 +614,7 @@ __device__ inline void d_loop_head(const DevP &D, double t_until, i64 iter_limit
     if (D.thermostat_on && c->g_filled - c->g_pos < 16) { c->stop = 1 + SDMD_STOP_NEED_RNG; return; }
     int target = D.cbt_node[1];
     c->target = target;
-    c->dt = D.ev_time[target];
+    c->dt = d_rt(D, target);
     int p = D.ev_partner[target];
     c->partner = p > 0 ? p : 0;
 }
@@ -782,19 +783,142 @@ __global__ void k_potential_energy_multi(const MultiArg *args, double *out);
 
 // Large systems: per event one grid-wide advance (k_advance with use_ctl) and this single-CTA kernel,
 // which finishes event k and performs AssignJob for event k+1.
-__global__ void __launch_bounds__(256, 1) k_event_exec(DevP D, double t_until, i64 iter_limit, sdmd_trace_rec *trace, i64 trace_cap) {
+__global__ void __launch_bounds__(256, 1) k_event_exec(DevP Dg, double t_until, i64 iter_limit, sdmd_trace_rec *trace, i64 trace_cap) {
     __shared__ PredShared sh;
-    __shared__ int s_stop;
-    if (threadIdx.x == 0) {
-        s_stop = D.ctl->stop;
-        if (!s_stop) d_publish_job(D, sh);
-    }
+    __shared__ Ctl s_ctl;      // loop state in shared memory while the block works, written back at the end
+    if (Dg.ctl->stop) return;
+    for (int k = threadIdx.x; k < (int)(sizeof(Ctl) / sizeof(int)); k += blockDim.x) ((int *)&s_ctl)[k] = ((const int *)Dg.ctl)[k];
     __syncthreads();
-    if (s_stop) return;
+    DevP D = Dg;
+    D.ctl = &s_ctl;
+    if (threadIdx.x == 0) d_publish_job(D, sh);
+    __syncthreads();
     d_loop_body_cta(D, sh, t_until, trace, trace_cap);
     if (threadIdx.x == 0) d_loop_head(D, t_until, iter_limit);
+    __syncthreads();
+    for (int k = threadIdx.x; k < (int)(sizeof(Ctl) / sizeof(int)); k += blockDim.x) ((int *)Dg.ctl)[k] = ((const int *)&s_ctl)[k];
 }
 __global__ void k_loop_head(DevP D, double t_until, i64 iter_limit) { d_loop_head(D, t_until, iter_limit); }
+
+// ---- overlapped sweep -----------------------------------------------------------------------------------------
+// One launch per loop iteration.  Block 0 is the event block (HazardCheck, DoEvent, Predict, UpdateCBT and the next
+// AssignJob); all other blocks are the UpdateData/TimeForward sweep of the SAME iteration, reading buffer lz_* and
+// writing buffer x/y/z/ev_time.  The event block does not wait for the sweep: it writes the two atoms of the event into
+// the new buffer itself and reads everybody else through d_rx..d_rt (see DevP).  The sweep skips those two atoms.
+__device__ __forceinline__ void d_publish_next_job(const DevP &D, int slot) {
+    Ctl *c = D.ctl;
+    Ctl::Job j;
+    j.dt = c->dt; j.seq = c->iterations; j.target = c->target; j.partner = c->partner; j.go = c->stop ? 0 : 1; j.pad_ = 0;
+    c->job[slot] = j;
+}
+__global__ void k_loop_head_job(DevP D, double t_until, i64 iter_limit, int slot) {
+    d_loop_head(D, t_until, iter_limit);
+    d_publish_next_job(D, slot);
+}
+__global__ void __launch_bounds__(256, 2) k_sweep_event(DevP Dg, int slot, i64 seq, double t_until, i64 iter_limit, sdmd_trace_rec *trace, i64 trace_cap) {
+    __shared__ PredShared sh;
+    // programmatic dependent launch: the blocks of the NEXT iteration's launch may already be resident while this one
+    // finishes; nothing the previous launch produced is read before this point
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (blockIdx.x == 0) asm volatile("griddepcontrol.launch_dependents;");
+    Ctl::Job job = Dg.ctl->job[slot];
+    if (job.seq != seq) job.go = 0;   // a slot left over from before a stop: this launch has nothing to do
+    if (blockIdx.x != 0) {
+        if (!job.go) return;
+        const double dt = job.dt;
+        const int a = job.target, b = job.partner, n = Dg.n;
+        const int stride = (gridDim.x - 1) * blockDim.x;
+        // two atoms per trip: fourteen independent loads in flight per thread
+        for (int i = (blockIdx.x - 1) * blockDim.x + threadIdx.x + 1; i <= n; i += 2 * stride) {
+            int i2 = i + stride;
+            bool ok2 = i2 <= n;
+            // streaming (evict-first) accesses: the sweep must not push the event block's working set out of L2
+            double x = __ldcs(&Dg.lz_x[i]), y = __ldcs(&Dg.lz_y[i]), z = __ldcs(&Dg.lz_z[i]), t = __ldcs(&Dg.lz_t[i]);
+            double vx = __ldcs(&Dg.vx[i]), vy = __ldcs(&Dg.vy[i]), vz = __ldcs(&Dg.vz[i]);
+            double x2 = 0, y2 = 0, z2 = 0, vx2 = 0, vy2 = 0, vz2 = 0, t2 = 0;
+            if (ok2) {
+                x2 = __ldcs(&Dg.lz_x[i2]); y2 = __ldcs(&Dg.lz_y[i2]); z2 = __ldcs(&Dg.lz_z[i2]); t2 = __ldcs(&Dg.lz_t[i2]);
+                vx2 = __ldcs(&Dg.vx[i2]); vy2 = __ldcs(&Dg.vy[i2]); vz2 = __ldcs(&Dg.vz[i2]);
+            }
+            if (i != a && i != b) {
+                __stcs(&Dg.x[i], x + vx * dt); __stcs(&Dg.y[i], y + vy * dt); __stcs(&Dg.z[i], z + vz * dt); __stcs(&Dg.ev_time[i], t - dt);
+            }
+            if (ok2 && i2 != a && i2 != b) {
+                __stcs(&Dg.x[i2], x2 + vx2 * dt); __stcs(&Dg.y[i2], y2 + vy2 * dt); __stcs(&Dg.z[i2], z2 + vz2 * dt); __stcs(&Dg.ev_time[i2], t2 - dt);
+            }
+        }
+        return;
+    }
+    if (!job.go) return;
+    long long k0 = clock64();
+    // the loop state lives in shared memory while the block works (thread 0 touches it dozens of times per iteration);
+    // meanwhile threads 32.. fetch what thread 0 needs next, so the pick-up is one round trip to memory, not four
+    __shared__ Ctl s_ctl;
+    __shared__ int s_type0;
+    for (int k = threadIdx.x; k < (int)(sizeof(Ctl) / sizeof(int)); k += blockDim.x) ((int *)&s_ctl)[k] = ((const int *)Dg.ctl)[k];
+    if (threadIdx.x >= 128 && threadIdx.x < 136) {
+        int q = (threadIdx.x - 128) >> 2, f = (threadIdx.x - 128) & 3;
+        int i = q ? job.partner : job.target;
+        if (i > 0) {
+            const double *src = f == 0 ? Dg.lz_x : f == 1 ? Dg.lz_y : f == 2 ? Dg.lz_z : Dg.lz_t;
+            double v = src[i];
+            // the event's own atoms move to the new buffer now (same arithmetic as the sweep)
+            if (f == 0) v = v + Dg.vx[i] * job.dt; else if (f == 1) v = v + Dg.vy[i] * job.dt; else if (f == 2) v = v + Dg.vz[i] * job.dt; else v = v - job.dt;
+            double *dst = f == 0 ? Dg.x : f == 1 ? Dg.y : f == 2 ? Dg.z : Dg.ev_time;
+            dst[i] = v;
+        }
+    }
+    if (threadIdx.x == 160) s_type0 = Dg.ev_type[job.target];
+    // warm this SM's L1 with what thread 0 is about to read one dependent load at a time
+    __shared__ volatile double s_sink[32];
+    if (threadIdx.x >= 192 && threadIdx.x < 224) {
+        int l = threadIdx.x - 192, i = (l & 16) ? job.partner : job.target;
+        double v = 0;
+        if (i > 0) {
+            switch (l & 15) {
+                case 0: v = Dg.mass[i]; break;
+                case 1: v = (double)Dg.ev_counter[i]; break;
+                case 2: v = (double)Dg.ev_pcounter[i]; break;
+                case 3: v = (double)Dg.is_cons[i]; break;
+                case 4: v = (double)Dg.ev_partner[i]; break;
+                case 5: v = (double)Dg.ev_sub[i]; break;
+                case 6: v = Dg.vx[i]; break;
+                case 7: v = Dg.vy[i]; break;
+                case 8: v = Dg.vz[i]; break;
+                case 9: v = Dg.ev_pot[i]; break;
+                case 10: v = (double)Dg.cell_idx[3 * i]; break;
+                case 11: v = (double)Dg.type[i]; break;
+                case 12: v = Dg.gauss[Dg.ctl->g_pos % Dg.g_cap]; break;
+                case 13: v = Dg.gauss[(Dg.ctl->g_pos + 4) % Dg.g_cap]; break;
+                case 14: v = (double)Dg.cbt_leaf[i]; break;
+                default: break;
+            }
+        }
+        s_sink[l] = v;
+    }
+    __syncthreads();
+    DevP D = Dg;
+    D.ctl = &s_ctl;
+    D.lz_dt = job.dt; D.lz_a = job.target; D.lz_b = job.partner;
+    if (threadIdx.x == 0) {
+        s_ctl.live = slot ^ 1;
+        sh.atom[0] = job.target;
+        sh.atom[1] = job.partner;
+        sh.gathered = (s_type0 != SDMD_EV_PCC && s_type0 != SDMD_EV_HB);   // as d_publish_job
+    }
+    __syncthreads();
+    long long k1 = d_clock_after(&sh.atom[0]);
+    d_loop_body_cta(D, sh, t_until, trace, trace_cap);
+    if (threadIdx.x == 0) {
+        long long k2 = clock64();
+        d_loop_head(D, t_until, iter_limit);
+        d_publish_next_job(D, slot ^ 1);
+        s_ctl.phase_cycles[0] += k1 - k0;               // job pick-up: state to shared memory, own atoms to the new buffer
+        s_ctl.phase_cycles[1] += clock64() - k2;        // next AssignJob
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < (int)(sizeof(Ctl) / sizeof(int)); k += blockDim.x) ((int *)Dg.ctl)[k] = ((const int *)&s_ctl)[k];
+}
 
 // ---- single-step kernels behind the per-function C-ABI ----
 __global__ void k_predict_list(DevP D, int a0, int a1) { d_predict_list_serial(D, a0, a1); }
@@ -1247,7 +1371,7 @@ int sdmd_cuda_host_unregister(void *ptr) {
     return 0;
 }
 int sdmd_cuda_set_loop_mode(sdmd_ctx *c, int mode) {
-    if (mode != SDMD_LOOP_AUTO && mode != SDMD_LOOP_ONE_CTA && mode != SDMD_LOOP_SWEEP) return set_err(SDMD_ERR_BAD_ARG, "loop mode");
+    if (mode != SDMD_LOOP_AUTO && mode != SDMD_LOOP_ONE_CTA && mode != SDMD_LOOP_SWEEP && mode != SDMD_LOOP_SWEEP_SERIAL) return set_err(SDMD_ERR_BAD_ARG, "loop mode");
     if (mode == SDMD_LOOP_ONE_CTA && c->n > SDMD_SMALL_N) return set_err(SDMD_ERR_UNSUPPORTED, "one-CTA loop: system too large");
     c->loop_mode = mode;
     return 0;
@@ -1658,6 +1782,12 @@ int sdmd_cuda_assign_job(sdmd_ctx *c, int32_t *target, int32_t *partner, double 
     return 0;
 }
 
+// sweep blocks of the overlapped kernel: two blocks fit per SM next to the event block (register use of the event role)
+static int sweep_grid(const sdmd_ctx *c) {
+    int blocks = grid_for(c->n, 256);
+    int cap = 148 * 8;   // measured flat between 1 and 16 blocks per SM: the iteration is bound by the event block
+    return blocks < cap ? blocks : cap;
+}
 static int advance_grid(const sdmd_ctx *c) {
     int blocks = grid_for(c->n, 256);
     int cap = 148 * 8;
@@ -1800,6 +1930,7 @@ int sdmd_cuda_run(sdmd_ctx *c, double t_until, int64_t max_iter, struct sdmd_tra
     TRY(pull_ctl(c));
     c->h_ctl->stop = 0;
     c->h_ctl->trace_pos = 0;
+    c->h_ctl->live = 0;
     i64 iter_limit = c->h_ctl->iterations + max_iter;
     if (max_iter > (1LL << 61)) iter_limit = (1LL << 62);
     TRY(push_ctl(c));
@@ -1811,7 +1942,7 @@ int sdmd_cuda_run(sdmd_ctx *c, double t_until, int64_t max_iter, struct sdmd_tra
         c->launches++;
         CK(cudaGetLastError());
         TRY(pull_ctl(c));
-    } else {
+    } else if (c->loop_mode == SDMD_LOOP_SWEEP_SERIAL) {
         c->counters_known = false;
         k_loop_head<<<1, 1, 0, c->stream>>>(c->P, t_until, iter_limit);
         c->launches++;
@@ -1825,6 +1956,43 @@ int sdmd_cuda_run(sdmd_ctx *c, double t_until, int64_t max_iter, struct sdmd_tra
             CK(cudaGetLastError());
             TRY(pull_ctl(c));
             if (c->h_ctl->stop) break;
+        }
+    } else {
+        // overlapped sweep: one launch per iteration, event block and sweep blocks side by side (k_sweep_event)
+        size_t n1 = (size_t)c->n + 1;
+        if (!c->x2) { TRY(dalloc(c, &c->x2, n1)); TRY(dalloc(c, &c->y2, n1)); TRY(dalloc(c, &c->z2, n1)); TRY(dalloc(c, &c->t2, n1)); }
+        DevP Pw[2];   // Pw[r]: reads buffer r, writes buffer r ^ 1; buffer 0 = the live arrays at entry
+        double *bx[2] = {c->P.x, c->x2}, *by[2] = {c->P.y, c->y2}, *bz[2] = {c->P.z, c->z2}, *bt[2] = {c->P.ev_time, c->t2};
+        for (int r = 0; r < 2; r++) {
+            Pw[r] = c->P;
+            Pw[r].x = bx[r ^ 1]; Pw[r].y = by[r ^ 1]; Pw[r].z = bz[r ^ 1]; Pw[r].ev_time = bt[r ^ 1];
+            Pw[r].lz_x = bx[r]; Pw[r].lz_y = by[r]; Pw[r].lz_z = bz[r]; Pw[r].lz_t = bt[r];
+            Pw[r].lz_on = 1;
+        }
+        c->counters_known = false;
+        k_loop_head_job<<<1, 1, 0, c->stream>>>(c->P, t_until, iter_limit, 0);
+        c->launches++;
+        const int batch = 64;
+        int r = 0;
+        i64 seq = c->h_ctl->iterations;   // iteration index the next launch executes
+        for (;;) {
+            for (int k = 0; k < batch; k++, r ^= 1, seq++)
+            {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(1 + sweep_grid(c)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                CK(cudaLaunchKernelEx(&cfg, k_sweep_event, Pw[r], r, seq, t_until, iter_limit, dtr, trace_cap));
+            }
+            c->launches += batch;
+            CK(cudaGetLastError());
+            TRY(pull_ctl(c));
+            if (c->h_ctl->stop) break;
+        }
+        if (c->h_ctl->live == 1) {   // the state ended up in the spare buffer: it becomes the live one
+            std::swap(c->P.x, c->x2); std::swap(c->P.y, c->y2); std::swap(c->P.z, c->z2); std::swap(c->P.ev_time, c->t2);
         }
     }
     cudaEventRecord(c->ev1, c->stream);

@@ -32,8 +32,11 @@ struct Ctl {
     int changed;               // predict_all fix-point flag
     i64 trace_pos;
     int cc_epoch;              // candidate-list cache epoch: bumped whenever the link list or HB state changes
-    int pad_;
+    int live;                  // overlapped sweep: which of the two coordinate/time buffers holds the current state
     i64 phase_cycles[12];      // clock64() per loop phase (thread 0): head, advance, event, gather, eval, fold, cbt
+    // overlapped sweep: AssignJob result per launch parity.  The event block of launch n publishes the job of launch
+    // n+1 in the other slot while sweep blocks of launch n may still be reading theirs.
+    struct Job { double dt; i64 seq; int target, partner, go, pad_; } job[2];   // seq = loop iteration the job belongs to
 };
 
 // thin view of "the slots other atoms currently hold" (live arrays in the event loop, the previous
@@ -127,7 +130,22 @@ struct DevP {
     const int *scell;
     float cut2_f32;          // cut2 * (1 + 1e-4), rounded up: superset sphere of the single-precision test
     float cellsize_f[3];
+    // Overlapped sweep (large-system loop): while the grid-wide UpdateData/TimeForward sweep of event n is still
+    // running, the event block already works on event n.  x/y/z/ev_time above are then the buffer the sweep WRITES;
+    // lz_* is the buffer it reads (state before the sweep).  The event block reads every atom other than the event's
+    // own two through d_rx/d_ry/d_rz/d_rt, which apply the sweep's arithmetic (x + v*dt, t - dt) on the fly — the same
+    // two roundings, so the same bits; the event's own atoms are written to the new buffer up front and live there.
+    const double *lz_x, *lz_y, *lz_z, *lz_t;
+    double lz_dt;
+    int lz_on, lz_a, lz_b;
 };
+__device__ __forceinline__ bool d_lz(const DevP &D, int j) { return D.lz_on && j != D.lz_a && j != D.lz_b; }
+__device__ __forceinline__ double d_rx(const DevP &D, int j) { return d_lz(D, j) ? D.lz_x[j] + D.vx[j] * D.lz_dt : D.x[j]; }
+__device__ __forceinline__ double d_ry(const DevP &D, int j) { return d_lz(D, j) ? D.lz_y[j] + D.vy[j] * D.lz_dt : D.y[j]; }
+__device__ __forceinline__ double d_rz(const DevP &D, int j) { return d_lz(D, j) ? D.lz_z[j] + D.vz[j] * D.lz_dt : D.z[j]; }
+__device__ __forceinline__ double d_rt(const DevP &D, int j) { return d_lz(D, j) ? D.lz_t[j] - D.lz_dt : D.ev_time[j]; }
+// event time of another atom's slot: the live slots go through d_rt, the relaxation buffers of Predict(all) do not
+__device__ __forceinline__ double d_stime(const DevP &D, const SlotSrc &S, int j) { return S.time == D.ev_time ? d_rt(D, j) : S.time[j]; }
 
 // neighbour-cell offsets, DMD.c:118-120
 __constant__ int c_offx[27] = {0, 1, 0, 0, 0, 1, 1, 1, -1, 0, 0, 0, -1, -1, -1, 0, 0, 1, -1, 1, -1, -1, -1, 1, 1, 1, -1};
@@ -314,7 +332,7 @@ __device__ inline Pair d_pair_atoms(const DevP &D, int i, int j) {
     double shx = d_shift1(ci[0], cj[0], D.cellnum[0], D.box[0]);
     double shy = d_shift1(ci[1], cj[1], D.cellnum[1], D.box[1]);
     double shz = d_shift1(ci[2], cj[2], D.cellnum[2], D.box[2]);
-    return d_pair(D.x[i], D.y[i], D.z[i], D.vx[i], D.vy[i], D.vz[i], D.x[j], D.y[j], D.z[j], D.vx[j], D.vy[j], D.vz[j], shx, shy, shz);
+    return d_pair(d_rx(D, i), d_ry(D, i), d_rz(D, i), D.vx[i], D.vy[i], D.vz[i], d_rx(D, j), d_ry(D, j), d_rz(D, j), D.vx[j], D.vy[j], D.vz[j], shx, shy, shz);
 }
 // CalculateDisc :1092-1094 / CalculateTime :1096-1099
 __device__ __forceinline__ double d_disc(const Pair &p, double short2) { return p.b * p.b - p.v2 * (p.r2 - short2); }
@@ -325,11 +343,11 @@ __device__ __forceinline__ double d_time(const Pair &p, int s, double d2) {
 // CheckDuplication, TimePrediction.c:1101-1117 (j is eligible only below dup_limit, see predict_all)
 __device__ __forceinline__ bool d_check_dup(const DevP &D, const SlotSrc &S, Slot &cur, int i, i64 counter_i, int j, int type,
                                             int dup_limit) {
-    if (j < dup_limit && S.partner[j] == i && S.type[j] == type && S.pcounter[j] == counter_i && cur.time > S.time[j]) {
+    if (j < dup_limit && S.partner[j] == i && S.type[j] == type && S.pcounter[j] == counter_i && cur.time > d_stime(D, S, j)) {
         cur.partner = j;
         cur.pot = S.pot[j];
         cur.sub = S.sub[j];
-        cur.time = S.time[j];
+        cur.time = d_stime(D, S, j);
         cur.type = type;
         cur.pcounter = D.ev_counter[j];
         return true;
@@ -444,7 +462,7 @@ __device__ inline void d_collision_time(const DevP &D, const SlotSrc &S, Self &m
         for (int j = D.celllist[D.n + cell + 1]; j; j = D.celllist[j]) {
             if (j == me.i) continue;
             if (d_check_dup(D, S, cur, me.i, me.counter, j, SDMD_EV_COLI, dup_limit)) continue;
-            d_collision_candidate(D, me, cur, j, D.x[j], D.y[j], D.z[j], D.vx[j], D.vy[j], D.vz[j], shx, shy, shz);
+            d_collision_candidate(D, me, cur, j, d_rx(D, j), d_ry(D, j), d_rz(D, j), D.vx[j], D.vy[j], D.vz[j], shx, shy, shz);
         }
     }
 }
@@ -481,8 +499,8 @@ __device__ __forceinline__ void d_r0_flush(const DevP &D, const SlotSrc &S, Self
         int cm = has_cm ? d_cm_flags(D, me.i, j) : 0;
         if (surv_k[s] & R0_DUPFLAG) {
             // CheckDuplication (TimePrediction.c:1101-1117) at this candidate's place in the scan
-            if (cur.time > S.time[j]) {
-                cur.partner = j; cur.pot = S.pot[j]; cur.sub = S.sub[j]; cur.time = S.time[j]; cur.type = SDMD_EV_COLI;
+            if (cur.time > d_stime(D, S, j)) {
+                cur.partner = j; cur.pot = S.pot[j]; cur.sub = S.sub[j]; cur.time = d_stime(D, S, j); cur.type = SDMD_EV_COLI;
                 cur.pcounter = D.ev_counter[j];
                 continue;
             }
@@ -830,7 +848,7 @@ __device__ __forceinline__ void d_thermostat_time(const DevP &D, Slot &cur, doub
 __device__ __forceinline__ Self d_load_self(const DevP &D, int i) {
     Self me;
     me.i = i;
-    me.x = D.x[i]; me.y = D.y[i]; me.z = D.z[i];
+    me.x = d_rx(D, i); me.y = d_ry(D, i); me.z = d_rz(D, i);
     me.vx = D.vx[i]; me.vy = D.vy[i]; me.vz = D.vz[i];
     me.cx = D.cell_idx[3 * i]; me.cy = D.cell_idx[3 * i + 1]; me.cz = D.cell_idx[3 * i + 2];
     me.counter = D.ev_counter[i];
@@ -934,18 +952,17 @@ __device__ inline void d_predict_list_serial(const DevP &D, int a0, int a1) {
 // ---------------------------------------------------------------------------------------------------
 // UpdateCBTRun, CBT.c:56-83
 __device__ inline void d_cbt_update_run(const DevP &D, int a) {
-    const double *t = D.ev_time;
     int *node = D.cbt_node;
     int father, left, right, old;
     for (father = D.cbt_leaf[a] / 2; father > 0; father /= 2) {
         if (node[father] != a) break;
         left = node[father * 2]; right = node[father * 2 + 1];
-        node[father] = (t[left] < t[right]) ? left : right;
+        node[father] = (d_rt(D, left) < d_rt(D, right)) ? left : right;
     }
     for (; father > 0; father /= 2) {
         old = node[father];
         left = node[father * 2]; right = node[father * 2 + 1];
-        int w = (t[left] < t[right]) ? left : right;
+        int w = (d_rt(D, left) < d_rt(D, right)) ? left : right;
         node[father] = w;
         if (w == old) return;
     }
@@ -968,7 +985,7 @@ __device__ inline double d_hb_barrier(const DevP &D, int a1, int a2) {
 __device__ inline double d_hb_energy_change(const DevP &D, int i, int skipAtom, int hbType) {
     double energyChange = 0, tmp = 0, accumPoten = 0;
     int cx = D.cell_idx[3 * i], cy = D.cell_idx[3 * i + 1], cz = D.cell_idx[3 * i + 2];
-    double xi = D.x[i], yi = D.y[i], zi = D.z[i];
+    double xi = d_rx(D, i), yi = d_ry(D, i), zi = d_rz(D, i);
     int skipNeighbor = D.hb_neighbor[skipAtom];
     for (int k = 0; k < 27; k++) {
         int ncx, ncy, ncz;
@@ -980,7 +997,7 @@ __device__ inline double d_hb_energy_change(const DevP &D, int i, int skipAtom, 
             if (j == i || j == skipAtom) continue;
             int cm = d_cm_flags(D, i, j);
             if (cm & (SDMD_BOND_CONNECT | SDMD_CONSTRAINT_CONNECT)) continue;
-            double tx = D.x[j] + shx, ty = D.y[j] + shy, tz = D.z[j] + shz;
+            double tx = d_rx(D, j) + shx, ty = d_ry(D, j) + shy, tz = d_rz(D, j) + shz;
             double rx = xi - tx, ry = yi - ty, rz = zi - tz;
             double r2 = rx * rx + ry * ry + rz * rz;
             if (r2 <= D.cutfull2) {
@@ -1001,7 +1018,7 @@ __device__ inline double d_hb_energy_change(const DevP &D, int i, int skipAtom, 
 
 // position of b as seen from a under the cell-index minimum image, Events.c:815-823
 __device__ inline void d_image_of(const DevP &D, int a, int b, double pos[3]) {
-    pos[0] = D.x[b]; pos[1] = D.y[b]; pos[2] = D.z[b];
+    pos[0] = d_rx(D, b); pos[1] = d_ry(D, b); pos[2] = d_rz(D, b);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         int ca = D.cell_idx[3 * a + k], cb = D.cell_idx[3 * b + k];
@@ -1014,7 +1031,7 @@ __device__ inline void d_image_of(const DevP &D, int a, int b, double pos[3]) {
 
 // InteractionEvent, Events.c:798-1024
 __device__ inline void d_interaction_event(const DevP &D, int i, int j, int hbEvent) {
-    double pi[3] = {D.x[i], D.y[i], D.z[i]}, pj[3];
+    double pi[3] = {d_rx(D, i), d_ry(D, i), d_rz(D, i)}, pj[3];
     d_image_of(D, i, j, pj);
     double rx = pi[0] - pj[0], ry = pi[1] - pj[1], rz = pi[2] - pj[2];
     double wx = D.vx[i] - D.vx[j], wy = D.vy[i] - D.vy[j], wz = D.vz[i] - D.vz[j];
@@ -1494,7 +1511,7 @@ __device__ __forceinline__ void d_pc_eval_coll(const DevP &D, PredShared &sh, in
     int flag = 0, sub = SDMD_SUB_INVALID;
     double time = SD_INF, pot = 0;
     // independent loads first
-    double xj = D.x[j], yj = D.y[j], zj = D.z[j], vxj = D.vx[j], vyj = D.vy[j], vzj = D.vz[j];
+    double xj = d_rx(D, j), yj = d_ry(D, j), zj = d_rz(D, j), vxj = D.vx[j], vyj = D.vy[j], vzj = D.vz[j];
     int pj = D.ev_partner[j];
     int tyj = D.ev_type[j];
     i64 pcj = D.ev_pcounter[j];
@@ -1745,8 +1762,8 @@ __device__ inline void d_pc_fold(const DevP &D, PredShared &sh, int a) {
                     int f = sh.cflag[q];
                     int j = sh.cj[q];
                     int ev = d_kind_event(sh.ckind[q]);
-                    if (cur.time > S.time[j]) {   // CheckDuplication copies the partner's slot
-                        cur.partner = j; cur.pot = S.pot[j]; cur.sub = S.sub[j]; cur.time = S.time[j]; cur.type = ev;
+                    if (cur.time > d_stime(D, S, j)) {   // CheckDuplication copies the partner's slot
+                        cur.partner = j; cur.pot = S.pot[j]; cur.sub = S.sub[j]; cur.time = d_stime(D, S, j); cur.type = ev;
                         cur.pcounter = D.ev_counter[j];
                         win = p;
                         if (f & CF_COUNTED) npair--;
@@ -1773,8 +1790,8 @@ __device__ inline void d_pc_fold(const DevP &D, PredShared &sh, int a) {
             if (sh.ckind[q] == CK_NONE) continue;
             int j = sh.cj[q];
             int ev = d_kind_event(sh.ckind[q]);
-            if ((f & CF_ELIGIBLE) && cur.time > S.time[j]) {
-                cur.partner = j; cur.pot = S.pot[j]; cur.sub = S.sub[j]; cur.time = S.time[j]; cur.type = ev;
+            if ((f & CF_ELIGIBLE) && cur.time > d_stime(D, S, j)) {
+                cur.partner = j; cur.pot = S.pot[j]; cur.sub = S.sub[j]; cur.time = d_stime(D, S, j); cur.type = ev;
                 cur.pcounter = D.ev_counter[j];
                 win = p;
                 continue;
@@ -1912,11 +1929,11 @@ __device__ inline void d_cbt_update_warp(const DevP &D, PredShared &sh, int a) {
         int sib = D.cbt_node[child ^ 1];
         sh.path_old[k] = D.cbt_node[f];
         sh.path_sib[k] = sib;
-        sh.path_tsib[k] = D.ev_time[sib];
+        sh.path_tsib[k] = d_rt(D, sib);
     }
     __syncwarp();
     if (lane == 0) {
-        double ta = D.ev_time[a];
+        double ta = d_rt(D, a);
         int w = a;              // current winner coming up the path
         double tw = ta;
         bool phase1 = true;

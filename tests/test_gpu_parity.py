@@ -51,10 +51,11 @@ def test_predict_all_and_cbt_match_reference(capi, case):
 
 
 @pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8"])
-@pytest.mark.parametrize("loop_mode", [0, 2], ids=["one_cta", "sweep"])
+@pytest.mark.parametrize("loop_mode", [0, 2, 3], ids=["one_cta", "sweep_overlapped", "sweep_serial"])
 def test_device_event_loop_matches_reference(capi, case, loop_mode):
-    """loop_mode 2 forces the large-system driver (grid-wide advance + one event block per event) onto the protein
-    cases too, so both loop drivers are pinned to the reference trace with bonds, HB and HB-neighbour events."""
+    """loop_mode 2 / 3 force the large-system drivers (grid-wide sweep overlapped with / followed by one event block per
+    iteration) onto the protein cases too, so every loop driver is pinned to the reference trace with bonds, HB and
+    HB-neighbour events."""
     pre, post, fin = load_case(case)
     hv, r = _replica(capi, pre)
     r.set_loop_mode(loop_mode)
