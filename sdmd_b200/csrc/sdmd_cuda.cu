@@ -869,8 +869,20 @@ __global__ void __launch_bounds__(256, 2) k_sweep_event(DevP Dg, int slot, i64 s
         }
     }
     if (threadIdx.x == 160) s_type0 = Dg.ev_type[job.target];
-    // warm this SM's L1 with what thread 0 is about to read one dependent load at a time
-    __shared__ volatile double s_sink[32];
+    __shared__ volatile double s_sink[64];
+    __syncthreads();
+    DevP D = Dg;
+    D.ctl = &s_ctl;
+    D.lz_dt = job.dt; D.lz_a = job.target; D.lz_b = job.partner;
+    if (threadIdx.x == 0) {
+        s_ctl.live = slot ^ 1;
+        sh.atom[0] = job.target;
+        sh.atom[1] = job.partner;
+        sh.gathered = (s_type0 != SDMD_EV_PCC && s_type0 != SDMD_EV_HB);   // as d_publish_job
+    }
+    __syncthreads();
+    long long k1 = d_clock_after(&sh.atom[0]);
+    // idle warps warm this SM's L1 with what thread 0 is about to read one dependent load at a time ...
     if (threadIdx.x >= 192 && threadIdx.x < 224) {
         int l = threadIdx.x - 192, i = (l & 16) ? job.partner : job.target;
         double v = 0;
@@ -894,20 +906,24 @@ __global__ void __launch_bounds__(256, 2) k_sweep_event(DevP Dg, int slot, i64 s
                 default: break;
             }
         }
-        s_sink[l] = v;
+        s_sink[32 + l] = v;
     }
-    __syncthreads();
-    DevP D = Dg;
-    D.ctl = &s_ctl;
-    D.lz_dt = job.dt; D.lz_a = job.target; D.lz_b = job.partner;
-    if (threadIdx.x == 0) {
-        s_ctl.live = slot ^ 1;
-        sh.atom[0] = job.target;
-        sh.atom[1] = job.partner;
-        sh.gathered = (s_type0 != SDMD_EV_PCC && s_type0 != SDMD_EV_HB);   // as d_publish_job
+    if (threadIdx.x >= 224) {
+        // ... and walk the tournament-tree paths of the event's atoms now (leaf -> siblings -> their times),
+        // so that UpdateCBT at the end of the iteration finds them in this SM's L1
+        int lane = threadIdx.x - 224;
+        double acc = 0;
+        for (int q = 0; q < 2; q++) {
+            int i = q ? job.partner : job.target;
+            if (i <= 0) continue;
+            int child = Dg.cbt_leaf[i] >> lane;
+            if (child > 1) {
+                int sib = Dg.cbt_node[child ^ 1];
+                acc += (double)Dg.cbt_node[child >> 1] + Dg.lz_t[sib] + (double)Dg.ev_partner[sib];
+            }
+        }
+        s_sink[lane] = acc;
     }
-    __syncthreads();
-    long long k1 = d_clock_after(&sh.atom[0]);
     d_loop_body_cta(D, sh, t_until, trace, trace_cap);
     if (threadIdx.x == 0) {
         long long k2 = clock64();
