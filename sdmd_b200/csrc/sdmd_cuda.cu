@@ -283,28 +283,6 @@ __global__ void k_cell_finish(DevP D, const int *cell_start, int *sorted_atom) {
     for (int a = p0; a < p1; a++) cl[sorted_atom[a]] = (a + 1 < p1) ? sorted_atom[a + 1] : 0;
 }
 
-// static neighbour table (see DevP::nbr)
-__global__ void k_build_nbr(DevP D, unsigned int *nbr) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)D.ncell * 27) return;
-    int c = (int)(t / 27), k = (int)(t % 27);
-    int nx = D.cellnum[0], ny = D.cellnum[1];
-    int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
-    int ncx, ncy, ncz;
-    int cell = d_neighbor_cell(D, cx, cy, cz, k, &ncx, &ncy, &ncz);
-    int ci[3] = {cx, cy, cz}, cj[3] = {ncx, ncy, ncz};
-    unsigned v = (unsigned)cell;
-    for (int d = 0; d < 3; d++) {
-        unsigned code = 0;
-        if (ci[d] != cj[d]) {
-            if (ci[d] == 0 && cj[d] == D.cellnum[d] - 1) code = 1;
-            else if (ci[d] == D.cellnum[d] - 1 && cj[d] == 0) code = 2;
-        }
-        v |= code << (26 + 2 * d);
-    }
-    nbr[t] = v;
-}
-
 // occupancy of every cell from an uploaded link list
 __global__ void k_cell_count(DevP D) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1273,14 +1251,6 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     TRY(dalloc(c, &c->d_sum, 4));
     P.surv = nullptr; P.surv_n = nullptr; P.surv_np = nullptr;
     TRY(dalloc(c, &P.spos, n1));
-    P.nbr = nullptr;
-    if ((long long)P.ncell < (1 << 26) && (long long)P.ncell * 27 * 4 <= (512LL << 20)) {
-        unsigned int *nbr = nullptr;
-        TRY(dalloc(c, &nbr, (size_t)P.ncell * 27));
-        long long tot = (long long)P.ncell * 27;
-        k_build_nbr<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(P, nbr);
-        P.nbr = nbr;
-    }
     P.cut2_loose = P.cut2 * (1.0 + 1e-9);
     P.cut2_f32 = nextafterf((float)(P.cut2 * (1.0 + 1e-4)), INFINITY);
     for (int k = 0; k < 3; k++) P.cellsize_f[k] = (float)P.cellsize[k];

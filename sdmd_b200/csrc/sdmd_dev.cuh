@@ -120,9 +120,6 @@ struct DevP {
     int *surv_n;             // count, or -1 when the list overflowed (atom re-scanned in the evaluation kernel)
     int *surv_np;            // pair evaluations counted by the filter
     int *spos;               // sorted position of every atom (inverse of sorted_atom)
-    // static neighbour table: for cell c and scan slot k (DMD.c:118-120 order) the neighbour cell (bits 0-25) and the
-    // minimum-image shift code per axis (2 bits each from bit 26: 0 none, 1 = -box, 2 = +box); NULL for huge grids
-    const unsigned int *nbr;
     double cut2_loose;       // cut2 * (1 + 1e-9): the filter keeps a superset, the evaluation re-tests exactly
     // single-precision working set of the neighbour filter: position relative to the atom's own cell corner (so a
     // neighbour cell is just an offset of whole cells, periodic wrap included) + the atom id; home cell per position
@@ -388,15 +385,6 @@ __device__ __forceinline__ int d_neighbor_cell(const DevP &D, int cx, int cy, in
 
 // neighbour cell + PBCShift (ToolFunctions.c:801-817) of scan slot k, from the static table when present
 __device__ __forceinline__ int d_neighbor(const DevP &D, int cx, int cy, int cz, int k, double *shx, double *shy, double *shz) {
-    if (D.nbr) {
-        int c = cz * D.cellnum[0] * D.cellnum[1] + cy * D.cellnum[0] + cx;
-        unsigned v = __ldg(&D.nbr[(size_t)c * 27 + k]);
-        unsigned sx = (v >> 26) & 3, sy = (v >> 28) & 3, sz = (v >> 30) & 3;
-        *shx = sx == 0 ? 0.0 : (sx == 1 ? -1 * D.box[0] : D.box[0]);
-        *shy = sy == 0 ? 0.0 : (sy == 1 ? -1 * D.box[1] : D.box[1]);
-        *shz = sz == 0 ? 0.0 : (sz == 1 ? -1 * D.box[2] : D.box[2]);
-        return (int)(v & 0x3ffffffu);
-    }
     int ncx, ncy, ncz;
     int cell = d_neighbor_cell(D, cx, cy, cz, k, &ncx, &ncy, &ncz);
     *shx = d_shift1(cx, ncx, D.cellnum[0], D.box[0]);
@@ -614,13 +602,13 @@ __device__ inline void d_r0_filter(const DevP &D, int p_self) {
     unsigned int *out = D.surv + (size_t)p_self * R0_SURV_CAP;
     int ns = 0, npair = 0;
     int cx = 0, cy = 0, cz = 0;
-    if (!D.nbr) { cx = c % D.cellnum[0]; cy = (c / D.cellnum[0]) % D.cellnum[1]; cz = c / (D.cellnum[0] * D.cellnum[1]); }
+    // neighbour cells by arithmetic: a per-cell table of the 27 ids (tried) costs a dependent load per cell and 108 B/cell of traffic
+    cx = c % D.cellnum[0]; cy = (c / D.cellnum[0]) % D.cellnum[1]; cz = c / (D.cellnum[0] * D.cellnum[1]);
     const float cut2 = D.cut2_f32;
     const float ncsx = -D.cellsize_f[0], ncsy = -D.cellsize_f[1], ncsz = -D.cellsize_f[2];
     for (int k = 0; k < 27; k++) {
-        int cell;
-        if (D.nbr) cell = (int)(__ldg(&D.nbr[(size_t)c * 27 + k]) & 0x3ffffffu);
-        else { int a, b, e; cell = d_neighbor_cell(D, cx, cy, cz, k, &a, &b, &e); }
+        int na, nb2, nc;
+        int cell = d_neighbor_cell(D, cx, cy, cz, k, &na, &nb2, &nc);
         // my position as seen from the neighbour cell's corner
         float mx = fmaf(c_koff[k][0], ncsx, me.x), my = fmaf(c_koff[k][1], ncsy, me.y), mz = fmaf(c_koff[k][2], ncsz, me.z);
         int p1 = D.cell_start[cell + 1];
