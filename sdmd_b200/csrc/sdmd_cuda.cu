@@ -1716,12 +1716,14 @@ int sdmd_cuda_prepare(sdmd_ctx *c, const double *x, const double *y, const doubl
         CK(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     }
     TRY(need_counters(c));
-    CK(cudaEventRecord(c->ev_main, c->stream));         // the copy stream must not overwrite what earlier work still reads
-    CK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
     size_t b = ((size_t)c->n + 1) * sizeof(double);
     CK(cudaMemcpyAsync(c->P.x, x, b, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->P.y, y, b, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->P.z, z, b, cudaMemcpyHostToDevice, c->stream));
+    // the second stream starts once the positions have landed: it must not overwrite what earlier work still reads, and
+    // positions should have the link to themselves so the cell build can begin as early as possible
+    CK(cudaEventRecord(c->ev_main, c->stream));
+    CK(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
     CK(cudaMemcpyAsync(c->P.vx, vx, b, cudaMemcpyHostToDevice, c->copy_stream));
     CK(cudaMemcpyAsync(c->P.vy, vy, b, cudaMemcpyHostToDevice, c->copy_stream));
     CK(cudaMemcpyAsync(c->P.vz, vz, b, cudaMemcpyHostToDevice, c->copy_stream));
