@@ -351,7 +351,7 @@ __device__ __forceinline__ SlotSrc as_src(const SlotBuf &b) {
 // The stale fields of a slot (potential / subEventType / partnerCounter survive ResetTarget) always start from the
 // live arrays, which this pass never writes until the final commit.
 #ifndef K2F_MINBLOCKS
-#define K2F_MINBLOCKS 6
+#define K2F_MINBLOCKS 5
 #endif
 __global__ void __launch_bounds__(256, K2F_MINBLOCKS) k_predict_all_filter(DevP D) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;

@@ -602,15 +602,28 @@ __device__ inline void d_r0_filter(const DevP &D, int p_self) {
     unsigned int *out = D.surv + (size_t)p_self * R0_SURV_CAP;
     int ns = 0, npair = 0;
     int cx = 0, cy = 0, cz = 0;
-    // neighbour cells by arithmetic: a per-cell table of the 27 ids (tried) costs a dependent load per cell and 108 B/cell of traffic
+    // neighbour cells by arithmetic (a per-cell table of the 27 ids costs a dependent load per cell and 108 B/cell of
+    // traffic).  The loop over the scan slots is fully unrolled so every offset is an immediate: a neighbour cell id is
+    // the own id plus a constant plus at most three per-atom periodic-wrap corrections.
     cx = c % D.cellnum[0]; cy = (c / D.cellnum[0]) % D.cellnum[1]; cz = c / (D.cellnum[0] * D.cellnum[1]);
+    const int nx = D.cellnum[0], nxy = D.cellnum[0] * D.cellnum[1];
+    const int wxm = cx == 0 ? nx : 0, wxp = cx == nx - 1 ? -nx : 0;                                  // wrap when stepping -1 / +1 in x
+    const int wym = cy == 0 ? nxy : 0, wyp = cy == D.cellnum[1] - 1 ? -nxy : 0;
+    const int wzm = cz == 0 ? nxy * D.cellnum[2] : 0, wzp = cz == D.cellnum[2] - 1 ? -nxy * D.cellnum[2] : 0;
     const float cut2 = D.cut2_f32;
-    const float ncsx = -D.cellsize_f[0], ncsy = -D.cellsize_f[1], ncsz = -D.cellsize_f[2];
+    const float csx = D.cellsize_f[0], csy = D.cellsize_f[1], csz = D.cellsize_f[2];
+#pragma unroll
     for (int k = 0; k < 27; k++) {
-        int na, nb2, nc;
-        int cell = d_neighbor_cell(D, cx, cy, cz, k, &na, &nb2, &nc);
+        constexpr int KX[27] = {0, 1, 0, 0, 0, 1, 1, 1, -1, 0, 0, 0, -1, -1, -1, 0, 0, 1, -1, 1, -1, -1, -1, 1, 1, 1, -1};   // DMD.c:118-120
+        constexpr int KY[27] = {0, 0, 1, 0, 1, 0, 1, 1, 0, -1, 0, -1, 0, -1, -1, -1, 1, 0, 0, -1, 1, -1, 1, -1, 1, -1, 1};
+        constexpr int KZ[27] = {0, 0, 0, 1, 1, 1, 0, 1, 0, 0, -1, -1, -1, 0, -1, 1, -1, -1, 1, 0, 0, 1, -1, -1, -1, 1, 1};
+        const int dx = KX[k], dy = KY[k], dz = KZ[k];
+        int cell = c + dx + dy * nx + dz * nxy + (dx < 0 ? wxm : dx > 0 ? wxp : 0) + (dy < 0 ? wym : dy > 0 ? wyp : 0) +
+                   (dz < 0 ? wzm : dz > 0 ? wzp : 0);
         // my position as seen from the neighbour cell's corner
-        float mx = fmaf(c_koff[k][0], ncsx, me.x), my = fmaf(c_koff[k][1], ncsy, me.y), mz = fmaf(c_koff[k][2], ncsz, me.z);
+        float mx = dx == 0 ? me.x : (dx > 0 ? me.x - csx : me.x + csx);
+        float my = dy == 0 ? me.y : (dy > 0 ? me.y - csy : me.y + csy);
+        float mz = dz == 0 ? me.z : (dz > 0 ? me.z - csz : me.z + csz);
         int p1 = D.cell_start[cell + 1];
         for (int p = D.cell_start[cell]; p < p1; p++) {
             if (p == p_self) continue;
