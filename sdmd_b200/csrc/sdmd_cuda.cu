@@ -48,7 +48,6 @@ struct sdmd_ctx {
     int *bp_j = nullptr;
     int *cell_of = nullptr, *cell_count = nullptr, *cell_cursor = nullptr, *scan_tmp = nullptr;
     int *d_cell_start = nullptr, *d_sorted_atom = nullptr;
-    double *d_sx = nullptr, *d_sy = nullptr, *d_sz = nullptr;
     SRec *d_srec = nullptr;
     float4 *d_sloc = nullptr;
     int *d_scell = nullptr;
@@ -294,7 +293,7 @@ __global__ void k_cell_count(DevP D) {
 
 // cell-sorted SoA copies for the full-system prediction pass
 // parts: bit 0 = positions, types and index maps, bit 1 = velocities (sdmd_cuda_prepare sorts them once their upload lands)
-__global__ void k_cell_permute(DevP D, const int *sorted_atom, double *sx, double *sy, double *sz, SRec *srec, float4 *sloc, int *scell,
+__global__ void k_cell_permute(DevP D, const int *sorted_atom, SRec *srec, float4 *sloc, int *scell,
                                int parts) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= D.n) return;
@@ -305,7 +304,6 @@ __global__ void k_cell_permute(DevP D, const int *sorted_atom, double *sx, doubl
         double x = D.x[j], y = D.y[j], z = D.z[j];
         int t = D.type[j];
         int cx = D.cell_idx[3 * j], cy = D.cell_idx[3 * j + 1], cz = D.cell_idx[3 * j + 2];
-        sx[p] = x; sy[p] = y; sz[p] = z;
         // cell-local single-precision copy for the neighbour filter (see d_r0_filter)
         sloc[p] = make_float4((float)(x - cx * D.cellsize[0]), (float)(y - cy * D.cellsize[1]), (float)(z - cz * D.cellsize[2]),
                               __int_as_float(j));
@@ -1246,7 +1244,6 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     TRY(dalloc(c, &c->cell_cursor, (size_t)P.ncell + 1));
     TRY(dalloc(c, &c->scan_tmp, (size_t)P.ncell / SCAN_ITEMS + 4));
     TRY(dalloc(c, &c->d_cell_start, (size_t)P.ncell + 1)); TRY(dalloc(c, &c->d_sorted_atom, n1));
-    TRY(dalloc(c, &c->d_sx, n1)); TRY(dalloc(c, &c->d_sy, n1)); TRY(dalloc(c, &c->d_sz, n1));
     TRY(dalloc(c, &c->d_srec, n1)); TRY(dalloc(c, &c->d_sloc, n1)); TRY(dalloc(c, &c->d_scell, n1));
     TRY(dalloc(c, &c->d_sum, 4));
     P.surv = nullptr; P.surv_n = nullptr; P.surv_np = nullptr;
@@ -1259,7 +1256,7 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
         TRY(dalloc(c, &P.surv, (size_t)R0_SURV_CAP * n1)); TRY(dalloc(c, &P.surv_n, n1)); TRY(dalloc(c, &P.surv_np, n1));
     }
     P.cell_start = c->d_cell_start; P.sorted_atom = c->d_sorted_atom;
-    P.sx = c->d_sx; P.sy = c->d_sy; P.sz = c->d_sz; P.srec = c->d_srec;
+    P.srec = c->d_srec;
     std::vector<int> leaf_atom;
     cbt_leaf_permutation(n, leaf_atom);
     TRY(dupload(c, &c->d_leaf_atom, leaf_atom.data(), (size_t)n));
@@ -1549,7 +1546,7 @@ static int cell_build_impl(sdmd_ctx *c, int parts, bool bump) {
     }
     k_cell_scatter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_cursor, c->d_sorted_atom);
     k_cell_finish<<<grid_for(m, 128), 128, 0, c->stream>>>(c->P, c->d_cell_start, c->d_sorted_atom);
-    k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_sx, c->d_sy, c->d_sz, c->d_srec, c->d_sloc, c->d_scell, parts);
+    k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_srec, c->d_sloc, c->d_scell, parts);
     c->launches += 7;
     if (bump) TRY(bump_epoch(c));
     c->cells_fresh = true;
@@ -1585,7 +1582,7 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
         }
         if (late) {
             CK(cudaStreamWaitEvent(c->stream, late, 0));
-            k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_sx, c->d_sy, c->d_sz, c->d_srec, c->d_sloc, c->d_scell, 2);
+            k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_srec, c->d_sloc, c->d_scell, 2);
             c->launches++;
         }
         k_predict_all_round<<<grid, 128, 0, c->stream>>>(c->P, B, B, nullptr, nullptr, 0, c->npair, c->second, c->bp_time, c->bp_j,

@@ -113,7 +113,6 @@ struct DevP {
     // cell-sorted tiles produced by cell_build (fresh link-list order: descending atom id inside a cell)
     const int *cell_start;   // [ncell + 1], 0-based cell
     const int *sorted_atom;  // [n]
-    const double *sx, *sy, *sz;   // positions alone: what the neighbour filter streams
     const struct SRec *srec;      // full record per sorted position: what the evaluation stage gathers
     // round-0 filter output: per sorted position up to R0_SURV_CAP candidates inside the scan sphere
     unsigned int *surv;      // (sorted position of j) | (scan slot k << 27)
@@ -562,7 +561,7 @@ __device__ inline void d_collision_time_2stage(const DevP &D, const SlotSrc &S, 
                 if (hb_i == j) continue;
                 if ((h0 == j) || (h0 != 0 && (h1 == j || (h1 != 0 && (h2 == j || (h2 != 0 && h3 == j)))))) continue;
                 npair++;
-                double tx = D.sx[p] + shx, ty = D.sy[p] + shy, tz = D.sz[p] + shz;
+                double tx = D.srec[p].x + shx, ty = D.srec[p].y + shy, tz = D.srec[p].z + shz;
                 double rx = me.x - tx, ry = me.y - ty, rz = me.z - tz;
                 double r2 = rx * rx + ry * ry + rz * rz;
                 keep = r2 <= D.cut2;
