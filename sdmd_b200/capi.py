@@ -48,7 +48,7 @@ class SdmdError(RuntimeError):
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile libsdmd_cuda.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     srcs = [PKG / "csrc" / "sdmd_cuda.cu"]
-    deps = srcs + [PKG / "csrc" / "sdmd_dev.cuh", ROOT / "include" / "sdmd_cuda.h"]
+    deps = srcs + [PKG / "csrc" / "sdmd_dev.cuh", PKG / "csrc" / "sdmd_dev_body.cuh", ROOT / "include" / "sdmd_cuda.h"]
     if not force and LIB_PATH.exists() and all(LIB_PATH.stat().st_mtime >= d.stat().st_mtime for d in deps):
         return LIB_PATH
     cmd = ["nvcc", *NVCC_FLAGS, f"-I{ROOT / 'include'}", f"-I{PKG / 'csrc'}", *map(str, srcs), "-o", str(LIB_PATH), "-ldl"]

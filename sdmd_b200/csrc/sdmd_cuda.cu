@@ -581,95 +581,6 @@ __global__ void __launch_bounds__(256) k_advance(DevP D, double dt_arg, int use_
 // kernels: event loop
 // ===================================================================================================
 // loop head: stop conditions + AssignJob (SGThread.c:75,237-259); single thread
-__device__ inline void d_loop_head(const DevP &D, double t_until, i64 iter_limit) {
-    Ctl *c = D.ctl;
-    if (c->stop) return;
-    if (c->error) { c->stop = 1 + SDMD_STOP_ERROR; return; }
-    if (!(c->currenttime <= c->timestep)) { c->stop = 1 + SDMD_STOP_TIME_END; return; }
-    if (c->iterations >= iter_limit) { c->stop = 1 + SDMD_STOP_MAX_ITER; return; }
-    if (D.thermostat_on && c->g_filled - c->g_pos < 16) { c->stop = 1 + SDMD_STOP_NEED_RNG; return; }
-    int target = D.cbt_node[1];
-    c->target = target;
-    c->dt = d_rt(D, target);
-    int p = D.ev_partner[target];
-    c->partner = p > 0 ? p : 0;
-}
-
-// publish the AssignJob result to the block (thread 0, before a barrier)
-__device__ __forceinline__ void d_publish_job(const DevP &D, PredShared &sh) {
-    Ctl *c = D.ctl;
-    int target = c->target, partner = c->partner;
-    sh.atom[0] = target;
-    sh.atom[1] = partner;
-    int type = D.ev_type[target];
-    // candidate gathering may overlap the event unless the event itself edits what gathering reads:
-    // the link list (PCC) or the HB lists / types (HB)
-    sh.gathered = (type != SDMD_EV_PCC && type != SDMD_EV_HB);
-}
-
-// loop body after the advance, executed by the whole CTA: HazardCheck, DoEvent, counters (thread 0) overlapped
-// with the candidate layout of the dirty atoms (warps 1-2), then the CTA-parallel Predict and the warp-assisted
-// UpdateCBT (SGThread.c:80-151).  Precondition: d_publish_job + __syncthreads.
-__device__ inline void d_loop_body_cta(const DevP &D, PredShared &sh, double t_until, sdmd_trace_rec *trace, i64 trace_cap) {
-    Ctl *c = D.ctl;
-    long long t0 = clock64();
-    int spec = sh.gathered;
-    if (threadIdx.x == 0) {
-        int target = sh.atom[0], partner = sh.atom[1];
-        c->currenttime += c->dt;
-        int hazard = (partner > 0 && D.ev_pcounter[target] < D.ev_counter[partner]) ? -1 : 0;  // SGThread.c:224-227
-        if (trace && c->trace_pos < trace_cap) {
-            sdmd_trace_rec r;
-            r.frame = c->frame; r.target = target; r.partner = D.ev_partner[target];
-            r.type = D.ev_type[target]; r.sub = D.ev_sub[target]; r.executed = !hazard; r.pad_ = 0; r.dt = c->dt;
-            trace[c->trace_pos] = r;
-        }
-        c->trace_pos++;
-        c->iterations++;
-        int na;
-        if (!hazard) {
-            c->frame++;
-            d_do_event(D, target, partner);
-            D.ev_counter[target]++;
-            if (partner && !D.is_cons[partner]) D.ev_counter[partner]++;
-            na = partner ? 2 : 1;
-            if (c->currenttime >= t_until) c->stop = 1 + SDMD_STOP_T_UNTIL;
-        } else {
-            na = 1;
-            c->count_recal++;
-        }
-        sh.natoms = na;
-        for (int a = 0; a < na; a++) {
-            int i = sh.atom[a];
-            // ResetTarget for every listed atom first (ToolFunctions.c:504-514)
-            D.ev_type[i] = SDMD_EV_INVD; D.ev_time[i] = SD_INF; D.ev_partner[i] = SDMD_INVALID;
-            // one thermostat draw per predicted atom, in list order
-            sh.gauss[a] = 0;
-            if (D.thermostat_on && !D.is_cons[i]) sh.gauss[a] = d_next_gauss(D);
-        }
-        c->phase_cycles[8] += clock64() - t0;
-    } else if (spec) {
-        d_predict_gather(D, sh, 1, sh.atom[1] > 0 ? 2 : 1);
-    }
-    __syncthreads();
-    long long t1 = d_clock_after(&sh.natoms);
-    if (!spec) {
-        d_predict_gather(D, sh, 1, sh.natoms);
-        __syncthreads();
-    }
-    long long t1b = d_clock_after(&sh.natoms);
-    d_predict_cta(D, sh);
-    long long t2 = clock64();
-    if (threadIdx.x < 32) {
-        d_cbt_update_warp(D, sh, sh.atom[0]);
-        if (sh.natoms > 1) d_cbt_update_warp(D, sh, sh.atom[1]);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        c->phase_cycles[2] += t1 - t0; c->phase_cycles[3] += t1b - t1; c->phase_cycles[6] += d_clock_after(&sh.natoms) - t2; c->phase_cycles[7] += 1;
-    }
-}
-
 // Small systems: the whole loop in ONE persistent CTA (one replica per CTA); no host round trip per event.
 __global__ void __launch_bounds__(256, 1) k_run_cta(DevP Dg, double t_until, i64 iter_limit, sdmd_trace_rec *trace, i64 trace_cap) {
     __shared__ PredShared sh;
@@ -792,7 +703,7 @@ __global__ void k_loop_head_job(DevP D, double t_until, i64 iter_limit, int slot
     d_publish_next_job(D, slot);
 }
 __global__ void __launch_bounds__(256, 2) k_sweep_event(DevP Dg, int slot, i64 seq, double t_until, i64 iter_limit, sdmd_trace_rec *trace, i64 trace_cap) {
-    __shared__ PredShared sh;
+    __shared__ lz1::PredShared sh;
     // programmatic dependent launch: the blocks of the NEXT iteration's launch may already be resident while this one
     // finishes; nothing the previous launch produced is read before this point
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -857,7 +768,7 @@ __global__ void __launch_bounds__(256, 2) k_sweep_event(DevP Dg, int slot, i64 s
         sh.gathered = (s_type0 != SDMD_EV_PCC && s_type0 != SDMD_EV_HB);   // as d_publish_job
     }
     __syncthreads();
-    long long k1 = d_clock_after(&sh.atom[0]);
+    long long k1 = lz1::d_clock_after(&sh.atom[0]);
     // idle warps warm this SM's L1 with what thread 0 is about to read one dependent load at a time ...
     if (threadIdx.x >= 192 && threadIdx.x < 224) {
         int l = threadIdx.x - 192, i = (l & 16) ? job.partner : job.target;
@@ -900,10 +811,10 @@ __global__ void __launch_bounds__(256, 2) k_sweep_event(DevP Dg, int slot, i64 s
         }
         s_sink[lane] = acc;
     }
-    d_loop_body_cta(D, sh, t_until, trace, trace_cap);
+    lz1::d_loop_body_cta(D, sh, t_until, trace, trace_cap);
     if (threadIdx.x == 0) {
         long long k2 = clock64();
-        d_loop_head(D, t_until, iter_limit);
+        lz1::d_loop_head(D, t_until, iter_limit);
         d_publish_next_job(D, slot ^ 1);
         s_ctl.phase_cycles[0] += k1 - k0;               // job pick-up: state to shared memory, own atoms to the new buffer
         s_ctl.phase_cycles[1] += clock64() - k2;        // next AssignJob
