@@ -69,9 +69,6 @@ struct sdmd_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
     cudaStream_t copy_stream = nullptr;  // second stream of sdmd_cuda_prepare (velocities + gaussians overlap the cell build)
     cudaEvent_t ev_copy = nullptr, ev_main = nullptr;
-    // big-N event loop graph
-    cudaGraphExec_t loop_graph = nullptr;
-    int loop_graph_len = 0;
     // NCCL
     void *nccl_lib = nullptr;
     void *nccl_comm = nullptr;
@@ -520,14 +517,7 @@ __global__ void k_cbt_leaves(DevP D, const int *leaf_atom) {
     D.cbt_node[pos] = a;
     D.cbt_leaf[a] = pos;
 }
-// internal nodes [lo, hi) of one tree level: winner = t[left] < t[right] ? left : right (CBT.c:62-67)
-__global__ void k_cbt_level(DevP D, int lo, int hi) {
-    int f = lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= hi) return;
-    int l = D.cbt_node[2 * f], r = D.cbt_node[2 * f + 1];
-    D.cbt_node[f] = (D.ev_time[l] < D.ev_time[r]) ? l : r;
-}
-
+// internal node: winner = t[left] < t[right] ? left : right (CBT.c:62-67)
 // bottom-up tournament inside one subtree per block: root f0 = 2^L + blockIdx.x, internal nodes of relative depth
 // dmax..0, one __syncthreads per level (a block's writes are visible to its own threads after the barrier)
 __global__ void __launch_bounds__(256) k_cbt_subtrees(DevP D, int L, int dmax) {
@@ -1191,7 +1181,6 @@ void sdmd_cuda_destroy(sdmd_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    if (c->loop_graph) cudaGraphExecDestroy(c->loop_graph);
     for (void *p : c->bufs) cudaFree(p);
     if (c->d_trace) cudaFree(c->d_trace);
     if (c->d_xchg) cudaFree(c->d_xchg);
