@@ -366,12 +366,37 @@ __global__ void __launch_bounds__(128, K2_MINBLOCKS) k_predict_all_round(DevP D,
     // re-evaluation rounds are a few thousand atoms with divergent, DRAM-latency-bound paths: give each its own
     // group of QSPREAD lanes so a warp serialises 32/QSPREAD paths instead of 32
     int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    int sub = 0;
     if (round != 0) {
-        if (gtid % QSPREAD) return;
+        sub = gtid % QSPREAD;
         gtid /= QSPREAD; gsz /= QSPREAD;
     }
     for (int p = gtid; p < total; p += gsz) {
         int i = (round == 0) ? D.sorted_atom[p] : queue[p];
+        if (round != 0) {
+            // the lanes of the group first pull everything lane 0 is about to read one dependent load at a time into this
+            // SM's L1 (survivor words -> 64-byte records -> the partners' slots; the atom's own state), in parallel
+            double acc = 0;
+            if (D.surv) {
+                int ps = D.spos[i];
+                int ns = D.surv_n[ps];
+                for (int s = sub; s < ns; s += QSPREAD) {
+                    unsigned w = D.surv[(size_t)ps * R0_SURV_CAP + s];
+                    const SRec *r = &D.srec[w & 0x7ffffffu];
+                    int j = r->atom;
+                    acc += r->x + r->vy + (double)src.partner[j] + (double)src.type[j] + (double)src.pcounter[j] + src.time[j] + src.pot[j] +
+                           (double)src.sub[j] + (double)D.ev_counter[j];
+                }
+                if (sub == 1) acc += (double)D.surv_np[ps] + D.srec[ps].x + D.srec[ps].vy;
+            }
+            if (sub == 2) acc += D.ev_pot[i] + (double)D.ev_sub[i] + (double)D.ev_pcounter[i] + (double)D.ev_counter[i];
+            if (sub == 3) acc += (double)D.cm_off[i] + (double)npair[i] + (double)D.is_cons[i];
+            if (sub == 4 && D.thermostat_on) { i64 gi = g_base + (D.no_cons ? i - 1 : D.ther_rank[i]); acc += D.gauss[gi >= D.g_cap ? gi - D.g_cap : gi]; }
+            if (sub != 0) {
+                if (acc == 1.2345e-300) D.ctl->warnings++;   // keeps the loads alive; never true
+                continue;
+            }
+        }
         Slot cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
         double g = 0;
         if (D.thermostat_on && (D.no_cons || !D.is_cons[i])) {
