@@ -328,6 +328,44 @@ __device__ inline void d_collision_time(const DevP &D, const SlotSrc &S, Self &m
 #define R0_MAXSURV 20
 #define R0_SURV_CAP 32
 #define R0_DUPFLAG 0x80   // survivor entry whose partner's slot points back: resolved in order in stage 2
+// Own-side evaluation of one collision candidate inside the scan sphere: exact distance re-test, step-table walk,
+// discriminant, root (CollisionTime, TimePrediction.c:107-175).  Returns false when the candidate produces no event.
+__device__ __forceinline__ bool d_eval_pair(const DevP &D, const Self &me, int j, int type_j, double xj, double yj, double zj, double vxj,
+                                            double vyj, double vzj, double shx, double shy, double shz, int cm, int type_i, double *t_out,
+                                            double *pot_out, int *sub_out) {
+    Pair pr = d_pair(me.x, me.y, me.z, me.vx, me.vy, me.vz, xj, yj, zj, vxj, vyj, vzj, shx, shy, shz);
+    if (!(pr.r2 <= D.cut2)) return false;
+    FindRes f;
+    if (cm & SDMD_CONSTRAINT_CONNECT) {
+        f = d_find_pair(D, me.i, j, FP_CONSTRAINT, pr.b, pr.r2, 0, 0);
+    } else {
+        int idx = __ldg(&D.coll_index[type_i * SD_NT + type_j]);
+        if (idx < 0) { D.ctl->error = SDMD_ERR_TABLE; return false; }
+        f = d_find_pair_table_fast(D, &D.tables[idx], FP_COLLISION, pr.b, pr.r2, 0, 0);
+        if (f.lowPot == 0 && f.upPot == 0) return false;
+    }
+    int sgn, sub;
+    double d2, pot;
+    if (pr.b < 0 && d_disc(pr, f.lower) > 0) {
+        sgn = -1; d2 = f.lower; pot = f.lowPot;
+        sub = (f.cs == 0) ? SDMD_SUB_CORECOLLI : SDMD_SUB_TBDCAPTR;
+    } else {
+        sgn = 1; d2 = f.upper; pot = f.upPot;
+        sub = SDMD_SUB_INVALID;
+        if (D.method_ding) {
+            if (cm & SDMD_CONSTRAINT_CONNECT) sub = (f.cs == 1) ? SDMD_SUB_WELLBOUNC : SDMD_SUB_TBDESCAP;
+            else {
+                if (f.cs == 1) return false;
+                sub = SDMD_SUB_TBDESCAP;
+            }
+        }
+    }
+    double t = d_time(pr, sgn, d2);
+    if (t < 0) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+    *t_out = t; *pot_out = pot; *sub_out = sub;
+    return true;
+}
+
 __device__ __forceinline__ void d_r0_flush(const DevP &D, const SlotSrc &S, Self &me, Slot &cur, const int *surv_p,
                                            const unsigned char *surv_k, int ns, bool has_cm, int type_i, int hb_i, int h0, int h1,
                                            int h2, int h3) {
@@ -361,35 +399,9 @@ __device__ __forceinline__ void d_r0_flush(const DevP &D, const SlotSrc &S, Self
             if ((h0 == j) || (h0 != 0 && (h1 == j || (h1 != 0 && (h2 == j || (h2 != 0 && h3 == j)))))) continue;
             me.npair++;
         }
-        Pair pr = d_pair(me.x, me.y, me.z, me.vx, me.vy, me.vz, r0.x, r0.y, r1.x, r1.y, r2v.x, r2v.y, shx, shy, shz);
-        if (!(pr.r2 <= D.cut2)) continue;
-        FindRes f;
-        if (cm & SDMD_CONSTRAINT_CONNECT) {
-            f = d_find_pair(D, me.i, j, FP_CONSTRAINT, pr.b, pr.r2, 0, 0);
-        } else {
-            int idx = __ldg(&D.coll_index[type_i * SD_NT + ta.x]);
-            if (idx < 0) { D.ctl->error = SDMD_ERR_TABLE; continue; }
-            f = d_find_pair_table_fast(D, &D.tables[idx], FP_COLLISION, pr.b, pr.r2, 0, 0);
-            if (f.lowPot == 0 && f.upPot == 0) continue;
-        }
-        int sgn, sub;
-        double d2, pot;
-        if (pr.b < 0 && d_disc(pr, f.lower) > 0) {
-            sgn = -1; d2 = f.lower; pot = f.lowPot;
-            sub = (f.cs == 0) ? SDMD_SUB_CORECOLLI : SDMD_SUB_TBDCAPTR;
-        } else {
-            sgn = 1; d2 = f.upper; pot = f.upPot;
-            sub = SDMD_SUB_INVALID;
-            if (D.method_ding) {
-                if (cm & SDMD_CONSTRAINT_CONNECT) sub = (f.cs == 1) ? SDMD_SUB_WELLBOUNC : SDMD_SUB_TBDESCAP;
-                else {
-                    if (f.cs == 1) continue;
-                    sub = SDMD_SUB_TBDESCAP;
-                }
-            }
-        }
-        double t = d_time(pr, sgn, d2);
-        if (t < 0) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+        double t, pot;
+        int sub;
+        if (!d_eval_pair(D, me, j, ta.x, r0.x, r0.y, r1.x, r1.y, r2v.x, r2v.y, shx, shy, shz, cm, type_i, &t, &pot, &sub)) continue;
         d_job_assign(D, cur, j, t, pot, sub, SDMD_EV_COLI);
     }
 }
