@@ -289,13 +289,15 @@ __global__ void k_cell_count(DevP D) {
 }
 
 // cell-sorted SoA copies for the full-system prediction pass
-// parts: bit 0 = positions, types and index maps, bit 1 = velocities (sdmd_cuda_prepare sorts them once their upload lands)
+// parts: bit 0 = positions, types and index maps, bit 1 = velocities (sdmd_cuda_prepare sorts them once their upload lands),
+// bit 2 = also bump the candidate-cache epoch
 __global__ void k_cell_permute(DevP D, const int *sorted_atom, SRec *srec, float4 *sloc, int *scell,
                                int parts) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= D.n) return;
     int j = sorted_atom[p];
     double2 *rp = reinterpret_cast<double2 *>(&srec[p]);
+    if ((parts & 4) && p == 0) D.ctl->cc_epoch++;   // new link list: cached candidate lists are void
     if (parts & 1) {
         D.spos[j] = p;
         double x = D.x[j], y = D.y[j], z = D.z[j];
@@ -1471,9 +1473,8 @@ static int cell_build_impl(sdmd_ctx *c, int parts, bool bump) {
     }
     k_cell_scatter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_cursor, c->d_sorted_atom);
     k_cell_finish<<<grid_for(m, 128), 128, 0, c->stream>>>(c->P, c->d_cell_start, c->d_sorted_atom);
-    k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_srec, c->d_sloc, c->d_scell, parts);
-    c->launches += 7;
-    if (bump) TRY(bump_epoch(c));
+    k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_srec, c->d_sloc, c->d_scell, parts | (bump ? 4 : 0));
+    c->launches += 6;
     c->cells_fresh = true;
     CK(cudaGetLastError());
     return 0;
