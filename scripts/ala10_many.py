@@ -6,7 +6,7 @@ from sdmd_b200 import capi
 from sdmd_b200.hostview import HostView
 n_iter = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 pre = HostView.from_snapshot('tests/golden/ala10_pre.npz')
-for R in (1, 8, 37, 74, 148, 296, 592):
+for R in (int(a) for a in (sys.argv[2].split(",") if len(sys.argv) > 2 else "1,8,37,74,148,296,592".split(","))):
     reps = []
     for k in range(R):
         hv = pre.copy(); hv.timestep = 1e12

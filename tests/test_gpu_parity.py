@@ -170,9 +170,12 @@ def test_round_trip_properties_1m(capi):
     assert np.all(t[1:] > 0)
 
 
-def test_remd_ensemble_gpu_matches_oracle(capi):
+@pytest.mark.parametrize("threads", [256, 128])
+def test_remd_ensemble_gpu_matches_oracle(capi, threads, monkeypatch):
     """Three ala10 replicas on one GPU coupled by the Server.c sweep: exchange log and final states equal the same
-    ensemble run on the CPU oracle."""
+    ensemble run on the CPU oracle.  Both block widths of the many-replica kernel (128 threads is what more than two
+    replicas per SM get) are forced."""
+    monkeypatch.setenv("SDMD_MULTI_THREADS", str(threads))
     from oracle.oracle_py import Oracle
     from sdmd_b200.remd import RemdEnsemble, reduced_temperature
     pre, _, _ = load_case("ala10")
