@@ -53,25 +53,27 @@ def write_gel_gro(path: Path, n: int, a_nm: float = 0.8):
         f.write("%10.5f%10.5f%10.5f\n" % (n * a_nm, n * a_nm, n * a_nm))
 
 
-def write_multi_ala10(path: Path, src: Path, copies_per_axis: int = 2, spacing_nm: float = 2.4, box_nm: float = 9.0):
-    """copies_per_axis^3 translated copies of the reference's ala10.gro; residue numbers restart per chain, which
-    is how the reference's .gro reader tells chains apart (Initialization.c:949-960)."""
+def write_multi_ala10(path: Path, src: Path, copies_per_axis=2, spacing_nm: float = 2.4, box_nm=9.0):
+    """nx*ny*nz translated copies of the reference's ala10.gro (a single int means a cube); residue numbers restart per
+    chain, which is how the reference's .gro reader tells chains apart (Initialization.c:949-960)."""
     lines = src.read_text().splitlines()
     atoms = lines[2:2 + int(lines[1])]
     xyz = np.array([[float(a[20:28]), float(a[28:36]), float(a[36:44])] for a in atoms])
     xyz -= xyz.mean(axis=0)
+    cp = np.array([copies_per_axis] * 3 if np.isscalar(copies_per_axis) else copies_per_axis, dtype=int)
+    box = np.array([box_nm] * 3 if np.isscalar(box_nm) else box_nm, dtype=float)
     out, serial = [], 1
-    for cz in range(copies_per_axis):
-        for cy in range(copies_per_axis):
-            for cx in range(copies_per_axis):
-                shift = (np.array([cx, cy, cz]) + 0.5) * spacing_nm + (box_nm - copies_per_axis * spacing_nm) / 2
+    for cz in range(cp[2]):
+        for cy in range(cp[1]):
+            for cx in range(cp[0]):
+                shift = (np.array([cx, cy, cz]) + 0.5) * spacing_nm + (box - cp * spacing_nm) / 2
                 for a, p in zip(atoms, xyz + shift):
                     out.append("%s%5d%8.3f%8.3f%8.3f" % (a[:15], serial, p[0], p[1], p[2]))
                     serial += 1
     with open(path, "w") as f:
-        f.write("8 x ala10\n%5d\n" % len(out))
+        f.write("%d x ala10\n%5d\n" % (int(cp.prod()), len(out)))
         f.write("\n".join(out) + "\n")
-        f.write("%10.5f%10.5f%10.5f\n" % (box_nm, box_nm, box_nm))
+        f.write("%10.5f%10.5f%10.5f\n" % tuple(box))
 
 
 def prepare_input(work: Path, time_units: float = 1000.0) -> Path:
@@ -100,6 +102,9 @@ def run_case(name: str, work: Path, harness=None, coord=None, max_iter=None, n_g
     inp = prepare_input(work)
     if gel_n and gel_n > 0:
         write_gel_gro(inp / coord, gel_n)
+    elif gel_n and gel_n == -80:
+        # 4 x 4 x 5 chains, N = 4720: past the one-thread-block limit of the device loop (live test only, not a fixture)
+        write_multi_ala10(inp / coord, inp / "ala10.gro", copies_per_axis=(4, 4, 5), box_nm=(10.0, 10.0, 12.5))
     elif gel_n and gel_n < 0:
         write_multi_ala10(inp / coord, inp / "ala10.gro")
     prefix = work / name

@@ -317,3 +317,38 @@ def test_prepare_one_call_equals_stepwise(capi, case):
     assert np.array_equal(a.cbt()[0][1:], b.cbt()[0][1:])
     sa, sb = a.run(max_iter=300, trace_cap=300), b.run(max_iter=300, trace_cap=300)
     assert sa[1].tobytes() == sb[1].tobytes()
+
+
+def test_multichain_protein_past_one_cta_limit_live(capi, tmp_path):
+    """SURVEY C3-like case generated on the spot by the UNMODIFIED reference (oracle/_ref/ref_harness travels with the
+    repository): 80 ala10 chains, N = 4720 > 4096, so the default loop driver is the overlapped sweep + event block —
+    with bonds, several proteins, HB candidates.  Cell list, Predict(all) slots, CBT, energies and a 20 000-iteration
+    trace must equal the reference bit for bit; the other sweep driver must give the same trace."""
+    from oracle.make_golden import REFDIR as ref_dir, run_case
+    if not (ref_dir / "ref_harness").exists():
+        pytest.skip("oracle/_ref/ref_harness not built")
+    n_it = 20000
+    run_case("ala10x80", tmp_path, harness="ref_harness", coord="ala10x80.gro", max_iter=n_it, n_gauss=120000, extra=[], gel_n=-80)
+    pre, post, fin = load_case("ala10x80", src=tmp_path, ext="snap")
+    assert pre.natom == 4720
+    want = ref_trace(fin)
+    assert len(want) == n_it
+    for mode in (0, 3):
+        hv, r = _replica(capi, pre)
+        r.set_loop_mode(mode)
+        r.pbc_full(); r.cell_build()
+        assert np.array_equal(r.celllist(), pre.extra["celllist"])
+        r.predict_all(); r.cbt_build()
+        r.download(hv)
+        assert_fields_equal(hv, post, SLOT_FIELDS, what="after Predict(all): ")
+        assert np.array_equal(r.cbt()[0][1:], post.extra["cbt_node"][1:])
+        assert r.potential_energy() == post.extra["epot"][0]
+        st, tr = r.run(max_iter=n_it, trace_cap=n_it)
+        assert st["error"] == 0 and st["iterations"] == n_it
+        assert_trace_equal(tr, want)
+        r.download(hv)
+        assert_fields_equal(hv, fin, STATE_FIELDS, what="final state: ")
+        assert np.array_equal(r.celllist(), fin.extra["celllist"])
+        assert np.array_equal(r.cbt()[0][1:], fin.extra["cbt_node"][1:])
+        assert r.potential_energy() == fin.extra["epot"][0]
+        r.close()
