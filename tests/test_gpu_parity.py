@@ -319,17 +319,31 @@ def test_prepare_one_call_equals_stepwise(capi, case):
     assert sa[1].tobytes() == sb[1].tobytes()
 
 
-def test_multichain_protein_past_one_cta_limit_live(capi, tmp_path):
+def _live_case(name, **kw):
+    """Run the unmodified reference harness now (short work directory: the reference keeps file names in small fixed
+    buffers) and load its three snapshots."""
+    import shutil
+    import tempfile
+    from pathlib import Path
+    from oracle.make_golden import run_case
+    work = Path(tempfile.mkdtemp(prefix="s", dir="/tmp"))
+    try:
+        run_case(name, work, **kw)
+        return load_case(name, src=work, ext="snap")
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def test_multichain_protein_past_one_cta_limit_live(capi):
     """SURVEY C3-like case generated on the spot by the UNMODIFIED reference (oracle/_ref/ref_harness travels with the
     repository): 80 ala10 chains, N = 4720 > 4096, so the default loop driver is the overlapped sweep + event block —
     with bonds, several proteins, HB candidates.  Cell list, Predict(all) slots, CBT, energies and a 20 000-iteration
     trace must equal the reference bit for bit; the other sweep driver must give the same trace."""
-    from oracle.make_golden import REFDIR as ref_dir, run_case
+    from oracle.make_golden import REFDIR as ref_dir
     if not (ref_dir / "ref_harness").exists():
         pytest.skip("oracle/_ref/ref_harness not built")
     n_it = 20000
-    run_case("ala10x80", tmp_path, harness="ref_harness", coord="ala10x80.gro", max_iter=n_it, n_gauss=120000, extra=[], gel_n=-80)
-    pre, post, fin = load_case("ala10x80", src=tmp_path, ext="snap")
+    pre, post, fin = _live_case("ala10x80", harness="ref_harness", coord="ala10x80.gro", max_iter=n_it, n_gauss=120000, extra=[], gel_n=-80)
     assert pre.natom == 4720
     want = ref_trace(fin)
     assert len(want) == n_it
@@ -352,3 +366,28 @@ def test_multichain_protein_past_one_cta_limit_live(capi, tmp_path):
         assert np.array_equal(r.cbt()[0][1:], fin.extra["cbt_node"][1:])
         assert r.potential_energy() == fin.extra["epot"][0]
         r.close()
+
+
+def test_gel_8000_live_reference(capi):
+    """20^3 GEL lattice (the reference's own CreateGELCoordinate layout) run by the UNMODIFIED -DGEL reference on the spot:
+    N = 8000 takes the overlapped-sweep driver; full-system pass and a 10 000-iteration trace bit for bit."""
+    from oracle.make_golden import REFDIR as ref_dir
+    if not (ref_dir / "ref_harness_gel").exists():
+        pytest.skip("oracle/_ref/ref_harness_gel not built")
+    n_it = 10000
+    pre, post, fin = _live_case("gel20", harness="ref_harness_gel", coord="GEL20.gro", max_iter=n_it, n_gauss=60000, extra=[], gel_n=20)
+    assert pre.natom == 8000
+    hv, r = _replica(capi, pre)
+    r.pbc_full(); r.cell_build()
+    assert np.array_equal(r.celllist(), pre.extra["celllist"])
+    r.predict_all(); r.cbt_build()
+    r.download(hv)
+    assert_fields_equal(hv, post, SLOT_FIELDS, what="after Predict(all): ")
+    want = ref_trace(fin)
+    st, tr = r.run(max_iter=n_it, trace_cap=n_it)
+    assert st["error"] == 0 and st["iterations"] == n_it
+    assert_trace_equal(tr, want)
+    r.download(hv)
+    assert_fields_equal(hv, fin, STATE_FIELDS, what="final state: ")
+    assert np.array_equal(r.celllist(), fin.extra["celllist"])
+    assert r.potential_energy() == fin.extra["epot"][0]
