@@ -93,7 +93,7 @@ def prepare_input(work: Path, time_units: float = 1000.0) -> Path:
     return inp
 
 
-def run_case(name: str, work: Path, harness=None, coord=None, max_iter=None, n_gauss=None, extra=None, gel_n=None):
+def run_case(name: str, work: Path, harness=None, coord=None, max_iter=None, n_gauss=None, extra=None, gel_n=None, gel_a_nm=0.8):
     spec = CASES.get(name)
     if spec is not None:
         harness, coord, max_iter, n_gauss, extra, gel_n = [s if o is None else o for s, o in
@@ -101,7 +101,7 @@ def run_case(name: str, work: Path, harness=None, coord=None, max_iter=None, n_g
     work.mkdir(parents=True, exist_ok=True)
     inp = prepare_input(work)
     if gel_n and gel_n > 0:
-        write_gel_gro(inp / coord, gel_n)
+        write_gel_gro(inp / coord, gel_n, gel_a_nm)
     elif gel_n and gel_n == -80:
         # 4 x 4 x 5 chains, N = 4720: past the one-thread-block limit of the device loop (live test only, not a fixture)
         write_multi_ala10(inp / coord, inp / "ala10.gro", copies_per_axis=(4, 4, 5), box_nm=(10.0, 10.0, 12.5))

@@ -391,3 +391,46 @@ def test_gel_8000_live_reference(capi):
     assert_fields_equal(hv, fin, STATE_FIELDS, what="final state: ")
     assert np.array_equal(r.celllist(), fin.extra["celllist"])
     assert r.potential_energy() == fin.extra["epot"][0]
+
+
+def test_dense_gel_live_reference(capi):
+    """Denser than SURVEY C5's 5 A variant: 14^3 GEL lattice at 4.5 A (about eight atoms per cell, > 200 candidates and ~33
+    atoms inside the scan sphere per atom, so the filter's 32-entry rows overflow and the evaluation falls back to the
+    cell scan), reference run on the spot; full-system pass and 5000 iterations bit for bit."""
+    from oracle.make_golden import REFDIR as ref_dir
+    if not (ref_dir / "ref_harness_gel").exists():
+        pytest.skip("oracle/_ref/ref_harness_gel not built")
+    n_it = 5000
+    pre, post, fin = _live_case("gel14d", harness="ref_harness_gel", coord="GEL14.gro", max_iter=n_it, n_gauss=40000, extra=[], gel_n=14,
+                                gel_a_nm=0.45)
+    assert pre.natom == 2744
+    for mode in (0, 2):
+        hv, r = _replica(capi, pre)
+        r.set_loop_mode(mode)
+        r.pbc_full(); r.cell_build(); r.predict_all(); r.cbt_build()
+        r.download(hv)
+        assert_fields_equal(hv, post, SLOT_FIELDS, what="after Predict(all): ")
+        st, tr = r.run(max_iter=n_it, trace_cap=n_it)
+        assert st["error"] == 0
+        assert_trace_equal(tr, ref_trace(fin))
+        r.download(hv)
+        assert_fields_equal(hv, fin, STATE_FIELDS, what="final state: ")
+        r.close()
+
+
+def test_ala10_300k_iterations_live_reference(capi):
+    """300 000 loop iterations of ala10 (HB formation and breaking included) against a trace the reference produces now."""
+    from oracle.make_golden import REFDIR as ref_dir
+    if not (ref_dir / "ref_harness").exists():
+        pytest.skip("oracle/_ref/ref_harness not built")
+    n_it = 300000
+    pre, post, fin = _live_case("ala10_live", harness="ref_harness", coord="ala10.gro", max_iter=n_it, n_gauss=600000, extra=[], gel_n=0)
+    hv, r = _replica(capi, pre)
+    r.pbc_full(); r.cell_build(); r.predict_all(); r.cbt_build()
+    want = ref_trace(fin)
+    st, tr = r.run(max_iter=n_it, trace_cap=n_it)
+    assert st["error"] == 0 and st["iterations"] == n_it and st["hb"] > 0
+    assert_trace_equal(tr, want)
+    r.download(hv)
+    assert_fields_equal(hv, fin, STATE_FIELDS, what="final state: ")
+    assert r.potential_energy() == fin.extra["epot"][0]
