@@ -1019,6 +1019,7 @@ static void cbt_leaf_permutation(int n, std::vector<int> &leaf_atom) {
     for (int k = 0; k < n; k++) leaf_atom[k] = node[n + k];
 }
 
+static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v);
 int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out) {
     if (!v || !out || v->abi_version != SDMD_ABI_VERSION || v->natom < 1) return set_err(SDMD_ERR_BAD_ARG, "bad host view");
     int ndev = 0;
@@ -1028,6 +1029,12 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     sdmd_ctx *c = new sdmd_ctx();
     c->device = device;
     c->n = v->natom;
+    int rc = create_impl(c, v);
+    if (rc) { sdmd_cuda_destroy(c); return rc; }   // releases whatever had been set up before the failure
+    *out = c;
+    return 0;
+}
+static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
@@ -1043,7 +1050,7 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
         P.box[k] = v->box[k];
         P.cellnum[k] = (int)floor(v->box[k] / v->cutoffr);
         if (P.cellnum[k] < 3) P.cellnum[k] = 3;
-        if (P.cellnum[k] > 65535) { delete c; return set_err(SDMD_ERR_UNSUPPORTED, "more than 65535 cells along one axis"); }
+        if (P.cellnum[k] > 65535) return set_err(SDMD_ERR_UNSUPPORTED, "more than 65535 cells along one axis");
     }
     for (int k = 0; k < 3; k++) P.cellsize[k] = v->box[k] / P.cellnum[k];
     long long ncell = (long long)P.cellnum[0] * P.cellnum[1] * P.cellnum[2];
@@ -1201,28 +1208,27 @@ int sdmd_cuda_create(const struct sdmd_host_view *v, int device, sdmd_ctx **out)
     CK(cudaMemcpyAsync(c->d_ctl, c->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream));
     P.ctl = c->d_ctl;
     CK(cudaStreamSynchronize(c->stream));
-    *out = c;
     return 0;
 }
 
 void sdmd_cuda_destroy(sdmd_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     for (void *p : c->bufs) cudaFree(p);
     if (c->d_trace) cudaFree(c->d_trace);
     if (c->d_xchg) cudaFree(c->d_xchg);
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
     resolve_pending(c);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
-    cudaEventDestroy(c->ev0);
-    cudaEventDestroy(c->ev1);
-    cudaEventDestroy(c->evt0);
-    cudaEventDestroy(c->evt1);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->evt0) cudaEventDestroy(c->evt0);
+    if (c->evt1) cudaEventDestroy(c->evt1);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-    cudaStreamDestroy(c->stream);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 

@@ -434,3 +434,29 @@ def test_ala10_300k_iterations_live_reference(capi):
     r.download(hv)
     assert_fields_equal(hv, fin, STATE_FIELDS, what="final state: ")
     assert r.potential_energy() == fin.extra["epot"][0]
+
+
+def test_error_paths_fail_loudly(capi):
+    """Misuse comes back as an error code + message through the C-ABI, never as a silent no-op."""
+    pre, _, _ = load_case("ala10")
+    with pytest.raises(capi.SdmdError):
+        capi.Replica(pre.copy(), device=4096)                 # no such device
+    bad = pre.copy()
+    bad.box = np.array([1e7, 150.0, 150.0])                   # > 65535 cells along x: rejected, and nothing leaks
+    with pytest.raises(capi.SdmdError):
+        capi.Replica(bad, device=0)
+    hv = pre.copy()
+    r = capi.Replica(hv, device=0)
+    with pytest.raises(capi.SdmdError):
+        r.predict_all()                                       # needs a fresh cell_build
+    r.cell_build()
+    with pytest.raises(capi.SdmdError):
+        r.predict_all()                                       # thermostat on, no gaussians fed
+    with pytest.raises(capi.SdmdError):
+        r.rng_feed(np.zeros(1 << 22))                         # more than the ring holds
+    with pytest.raises(capi.SdmdError):
+        r.set_loop_mode(7)
+    r.rng_feed(pre.extra["gauss"])
+    r.predict_all(); r.cbt_build()
+    st, _ = r.run(max_iter=10)
+    assert st["iterations"] == 10 and st["error"] == 0        # and the context is still usable afterwards
