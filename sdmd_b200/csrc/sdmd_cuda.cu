@@ -1406,7 +1406,7 @@ double sdmd_host_gaussian_libc(void) {
 
 int64_t sdmd_cuda_rng_available(const sdmd_ctx *c) {
     sdmd_ctx *m = const_cast<sdmd_ctx *>(c);
-    if (pull_ctl(m)) return -1;
+    if (need_counters(m)) return -1;   // no round trip when nothing consumed gaussians since the last one
     return c->g_filled - c->h_ctl->g_pos;
 }
 
