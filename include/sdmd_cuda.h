@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SDMD_ABI_VERSION 1
+#define SDMD_ABI_VERSION 2
 
 /* reference constants, DMD.h:25-30 */
 #define SDMD_INFINIT       1E8
@@ -63,7 +63,7 @@ enum sdmd_error {
     SDMD_ERR_NO_DEVICE   = -1,   /* no usable CUDA device / kernel image (never a CPU fallback) */
     SDMD_ERR_CUDA        = -2,   /* a CUDA runtime call failed; see sdmd_cuda_last_error() */
     SDMD_ERR_BAD_ARG     = -3,
-    SDMD_ERR_UNSUPPORTED = -4,   /* feature outside the hot-path scope (walls, CG, tunnels, flow, ...) */
+    SDMD_ERR_UNSUPPORTED = -4,   /* feature outside the hot-path scope (rough walls, moving walls, CG, obstacles, tunnels, flow) */
     SDMD_ERR_TABLE       = -5,   /* a pair needed a potential table that does not exist (FindPair exit, ToolFunctions.c:114-117) */
     SDMD_ERR_STATE       = -6,   /* device-side consistency check failed (link list / event type) */
     SDMD_ERR_NCCL        = -7
@@ -142,6 +142,21 @@ struct sdmd_host_view {
     int32_t *coll_index;              /* [33*33] potentialPairCollision after RightPair resolution (ToolFunctions.c:278-292); -1 = none */
     int32_t *hb_index;                /* [12*33*33] potentialPairHB; -1 = empty entry */
     double  hb_barrier[3];            /* HBPotential.BB_v, SS_v, BS_v (Events.c:1097-1119) */
+
+    /* smooth confining wall (WallExist smooth; ReadWall Initialization.c:1907-1935, WallTime TimePrediction.c:635-737,
+     * WallEvent Events.c:423-499, PBC Events.c:210-216).  wall_kind = SDMD_WALL_NONE when wallExist is "no". */
+    int32_t wall_kind;                /* enum sdmd_wall_kind */
+    int32_t wall_type;                /* wall[0].property->typeofAtom: row of the collision table the wall interacts through */
+    double  wall_pos[3];              /* wall[0].dynamic->coordinate[1..3]: the axis / mid-plane / centre the distance is taken from */
+};
+
+/* wallType (parameter.txt line 11), first letter decides (strncmp(...,1)): which coordinates take part in the wall distance
+ * and which dimensions stay periodic */
+enum sdmd_wall_kind {
+    SDMD_WALL_NONE = 0,
+    SDMD_WALL_PARALLEL = 1,           /* two plates normal to y: distance from y = box_y/2; x and z periodic */
+    SDMD_WALL_CYLINDER = 2,           /* tube along x: distance from the axis (y,z) = box/2; x periodic */
+    SDMD_WALL_SPHERE   = 3            /* cavity centred in the box; nothing periodic */
 };
 
 /* counters mirroring the reference's global tallies (DMD.c:50-61) */
@@ -156,6 +171,7 @@ struct sdmd_run_stats {
     double  currenttime;
     int32_t stop_reason;              /* enum sdmd_stop_reason */
     int32_t error;                    /* first device-side SDMD_ERR_* or 0 */
+    int64_t wall;                     /* walleventsum (Events.c:73-76) */
 };
 
 enum sdmd_stop_reason {

@@ -10,6 +10,12 @@ reference's own inputs and stores what the reference computed as compressed .npz
   gel10        GEL step-potential spheres, 10^3 simple-cubic lattice at 8 A (reference CreateGELCoordinate
                layout, ToolFunctions.c:775-798), 3000 iterations
 
+  ala10x8_wallp  8 ala10 chains between two smooth parallel plates (WallExist smooth / WallType parallel, plates normal
+               to y, 38 A apart; Wall.txt atom type CA because the shipped PHO is only valid in CG mode): WallTime /
+               WallEvent, PBC in x and z only
+  ala10x4_wallc  4 ala10 chains in a smooth cylinder along x (WallType cylinder, diameter 26 A), snapshot after 20000
+               iterations, then 8000 traced
+
 usage: python oracle/make_golden.py [--out tests/golden] [--work oracle/_ref/work] [--only NAME]
 Also importable: run_case(name, workdir) returns the three snapshot paths for ad-hoc (uncommitted) runs.
 """
@@ -37,6 +43,14 @@ CASES = {
     # 8 ala10 chains on a 2x2x2 grid (stand-in for the multi-peptide aggregation config: inter-chain collisions and
     # hydrogen bonds, several proteins, N = 472); 4000 iterations
     "ala10x8": ("ref_harness", "ala10x8.gro", 4000, 16000, [], -8),
+    # smooth confining walls
+    "ala10x8_wallp": ("ref_harness", "ala10x8w.gro", 8000, 40000, [], -8),
+    "ala10x4_wallc": ("ref_harness", "ala10x4c.gro", 8000, 40000, ["--warm", "20000"], -8),
+}
+# name: (WallType, chains per axis, spacing nm, box nm)
+WALLS = {
+    "ala10x8_wallp": ("parallel", (2, 2, 2), 1.9, (5.0, 3.8, 5.0)),
+    "ala10x4_wallc": ("cylinder", (4, 1, 1), 2.0, (8.0, 2.6, 2.6)),
 }
 
 
@@ -76,8 +90,8 @@ def write_multi_ala10(path: Path, src: Path, copies_per_axis=2, spacing_nm: floa
         f.write("%10.5f%10.5f%10.5f\n" % tuple(box))
 
 
-def prepare_input(work: Path, time_units: float = 1000.0) -> Path:
-    """Writable copy of the reference input directory with the run length set."""
+def prepare_input(work: Path, time_units: float = 1000.0, wall_type: str | None = None) -> Path:
+    """Writable copy of the reference input directory with the run length (and a smooth wall) set."""
     src = REFDIR / "input"
     if not src.exists():
         raise FileNotFoundError(f"{src} missing: run `make -C oracle ref` where /root/reference exists")
@@ -88,6 +102,11 @@ def prepare_input(work: Path, time_units: float = 1000.0) -> Path:
     p = inp / "parameter.txt"
     lines = p.read_text().splitlines()
     lines[1] = "Time               %g" % time_units
+    if wall_type:
+        lines[9] = "WallExist?         smooth"
+        lines[10] = "WallType           %s" % wall_type
+        # the wall's atom type must be a valid AtomModel name (Models.c:129-209); the shipped PHO is CG-only
+        (inp / "Library_Ding" / "Wall.txt").write_text("Wall\n   ATOM CA      CA    12.0  N N\n")
     p.write_text("\n".join(lines) + "\n")
     (work / "out").mkdir(parents=True, exist_ok=True)
     return inp
@@ -99,8 +118,11 @@ def run_case(name: str, work: Path, harness=None, coord=None, max_iter=None, n_g
         harness, coord, max_iter, n_gauss, extra, gel_n = [s if o is None else o for s, o in
                                                            zip(spec, (harness, coord, max_iter, n_gauss, extra, gel_n))]
     work.mkdir(parents=True, exist_ok=True)
-    inp = prepare_input(work)
-    if gel_n and gel_n > 0:
+    wall = WALLS.get(name)
+    inp = prepare_input(work, wall_type=wall[0] if wall else None)
+    if wall:
+        write_multi_ala10(inp / coord, inp / "ala10.gro", copies_per_axis=wall[1], spacing_nm=wall[2], box_nm=wall[3])
+    elif gel_n and gel_n > 0:
         write_gel_gro(inp / coord, gel_n, gel_a_nm)
     elif gel_n and gel_n == -80:
         # 4 x 4 x 5 chains, N = 4720: past the one-thread-block limit of the device loop (live test only, not a fixture)

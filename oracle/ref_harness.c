@@ -183,7 +183,8 @@ int main(int argc, const char *argv[]) {
     sdmd_snap_close(s);
 
     long frame0 = frame, recal0 = countReCal;
-    long base[6] = {collisioneventsum, bondeventsum, HBeventsum, HBNeighboreventsum, thermostateventsum, pbcandcrosseventsum};
+    long base[7] = {collisioneventsum, bondeventsum, HBeventsum, HBNeighboreventsum, thermostateventsum, pbcandcrosseventsum,
+                    walleventsum};
     struct sdmd_trace_rec *trace = calloc(max_iter > 0 ? max_iter : 1, sizeof(*trace));
     long iter = run_loop(max_iter, trace, printf_log);
 
@@ -195,7 +196,7 @@ int main(int argc, const char *argv[]) {
     sdmd_snap_put(s, "trace", "u1", trace, (uint64_t)iter * sizeof(*trace));
     int64_t stats[12] = {frame, iter, countReCal - recal0, collisioneventsum - base[0], bondeventsum - base[1],
                          HBeventsum - base[2], HBNeighboreventsum - base[3], thermostateventsum - base[4],
-                         pbcandcrosseventsum - base[5], warningsum, frame0, 0};
+                         pbcandcrosseventsum - base[5], warningsum, frame0, walleventsum - base[6]};
     sdmd_snap_put(s, "stats", "i8", stats, 12);
     epot = CalPotenE(); ekin = CalKinetE();
     sdmd_snap_put(s, "epot", "f8", &epot, 1);

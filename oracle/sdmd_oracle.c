@@ -101,12 +101,25 @@ void oracle_get_stats(const oracle_ctx *c, struct sdmd_run_stats *s) { *s = c->s
 void oracle_set_temperature(oracle_ctx *c, double t) { c->v->target_temperature = t; }
 
 /* ------------------------------------------------------------------------------------------------ */
-/* PBC("full"), Events.c:218-228 (no wall: dim = 3, step = 1) */
+/* which dimensions PBC wraps, Events.c:207-216: all three without a wall; x and z between parallel plates
+ * (dim = 3, step = 2); x only inside a cylinder (dim = 1); none inside a sphere (early return) */
+static int pbc_dim_mask(const struct sdmd_host_view *v) {
+    switch (v->wall_kind) {
+        case SDMD_WALL_PARALLEL: return 1 | 4;
+        case SDMD_WALL_CYLINDER: return 1;
+        case SDMD_WALL_SPHERE: return 0;
+        default: return 7;
+    }
+}
+
+/* PBC("full"), Events.c:218-228 */
 void oracle_pbc_full(oracle_ctx *c) {
     struct sdmd_host_view *v = c->v;
     double *co[3] = {v->x, v->y, v->z};
+    int mask = pbc_dim_mask(v);
     for (int i = 1; i <= c->n; i++)
         for (int k = 0; k < 3; k++) {
+            if (!(mask >> k & 1)) continue;
             if (co[k][i] >= v->box[k]) co[k][i] -= v->box[k];
             else if (co[k][i] < 0) co[k][i] += v->box[k];
         }
@@ -227,7 +240,7 @@ static int find_pair(oracle_ctx *c, int a1, int a2, int mode, double direction, 
         int t1 = v->type[a1];
         if (typeChange == 1) t1 = type_change(t1, 1);
         else if (typeChange == -1) t1 = type_change(t1, 0);
-        idx = v->coll_index[t1 * NT + v->type[a2]];
+        idx = v->coll_index[t1 * NT + (a2 < 0 ? v->wall_type : v->type[a2])];   /* a2 < 0: the wall pseudo-atom, :642-667 */
     } else if (mode == FP_CONSTRAINT) {            /* :68-77 */
         for (int k = v->con_off[a1]; k < v->con_off[a1 + 1]; k++)
             if (v->con_j[k] == a2) { idx = v->con_table[k]; break; }
@@ -572,6 +585,44 @@ static void pcc_time(oracle_ctx *c, int i) {
     job_assign(c, i, 0, &ev, SDMD_EV_PCC);
 }
 
+/* WallTime, TimePrediction.c:635-737, smooth wall, wallDyn "no".  The wall is a pseudo-atom at rest sitting on the
+ * mid-plane / axis / centre; `distance2` is the squared distance from the wall SURFACE, (box_y/2 - r)^2 written the
+ * reference's way; the quadratic itself is solved in the distance r from the centre. */
+static void wall_time(oracle_ctx *c, int i) {
+    const struct sdmd_host_view *v = c->v;
+    struct evt ev;
+    struct par p;
+    init_event(&ev);
+    double pi[3] = {v->x[i], v->y[i], v->z[i]}, si[3] = {v->vx[i], v->vy[i], v->vz[i]};
+    if (v->wall_kind == SDMD_WALL_PARALLEL) { pi[0] = pi[2] = 0; si[0] = si[2] = 0; }   /* :654-656 */
+    else if (v->wall_kind == SDMD_WALL_CYLINDER) { pi[0] = 0; si[0] = 0; }              /* :657-660 */
+    for (int k = 0; k < 3; k++) { p.r_ij[k] = pi[k] - v->wall_pos[k]; p.v_ij[k] = si[k] - 0.0; }
+    p.r_2 = p.r_ij[0] * p.r_ij[0] + p.r_ij[1] * p.r_ij[1] + p.r_ij[2] * p.r_ij[2];
+    p.b_ij = p.r_ij[0] * p.v_ij[0] + p.r_ij[1] * p.v_ij[1] + p.r_ij[2] * p.v_ij[2];
+    p.v_2 = p.v_ij[0] * p.v_ij[0] + p.v_ij[1] * p.v_ij[1] + p.v_ij[2] * p.v_ij[2];
+    double by = v->box[1];
+    double distance2 = by * by * 0.25 + p.r_2 - by * sqrt(p.r_2);                      /* :667 */
+    double accum;
+    p.coreorShell = find_pair(c, i, -1, FP_COLLISION, -1 * p.b_ij, distance2, &p.shortlimit2, &p.longlimit2,
+                              &p.lowerPotential, &p.upperPotential, &accum, 0, 0);
+    if (p.lowerPotential == 0 && p.upperPotential == 0) { c->st.error = SDMD_ERR_STATE; return; }   /* :675-702 exit() */
+    if (p.b_ij < 0 && calc_disc(&p) > 0) {                                               /* towards the centre :704-714 */
+        if (p.coreorShell == 1) return;
+        ev.sub = SDMD_SUB_TBDCAPTR;
+        p.s_time = -1;
+        p.d_ij2 = by * by * 0.25 + p.longlimit2 - by * sqrt(p.longlimit2);
+        ev.potential = p.upperPotential;
+    } else {                                                                             /* towards the wall :716-726 */
+        ev.sub = (p.coreorShell == 0) ? SDMD_SUB_WELLBOUNC : SDMD_SUB_TBDESCAP;
+        p.s_time = 1;
+        p.d_ij2 = by * by * 0.25 + p.shortlimit2 - by * sqrt(p.shortlimit2);
+        ev.potential = p.lowerPotential;
+    }
+    ev.time = calc_time(&p);
+    if (ev.time < 0) ev.time = INF;                                                      /* :729-732 */
+    job_assign(c, i, 0, &ev, SDMD_EV_WALL);
+}
+
 /* Predict, SGThread.c:158-211 (+ ResetTarget, ToolFunctions.c:504-514) */
 void oracle_predict(oracle_ctx *c, const int32_t *renew) {
     struct sdmd_host_view *v = c->v;
@@ -587,6 +638,7 @@ void oracle_predict(oracle_ctx *c, const int32_t *renew) {
         pcc_time(c, i);
         thermostat_time(c, i);
         if (v->hydrogen_bond) { hb_time(c, i); hbn_time(c, i); }
+        if (v->wall_kind) wall_time(c, i);                       /* SGThread.c:183-185 */
     }
 }
 
@@ -831,9 +883,11 @@ static void pcc_event(oracle_ctx *c, int i) {
     struct sdmd_host_view *v = c->v;
     int old[3] = {v->cell_idx[3 * i], v->cell_idx[3 * i + 1], v->cell_idx[3 * i + 2]};
     double *co[3] = {v->x, v->y, v->z};
+    int mask = pbc_dim_mask(v);
     for (int k = 0; k < 3; k++) {
         if (old[k] == 0 || old[k] == c->cellnum[k] - 1) {
             for (int d = 0; d < 3; d++) {
+                if (!(mask >> d & 1)) continue;
                 if (co[d][i] >= v->box[d]) co[d][i] -= v->box[d];
                 else if (co[d][i] < 0) co[d][i] += v->box[d];
             }
@@ -841,6 +895,34 @@ static void pcc_event(oracle_ctx *c, int i) {
         }
     }
     cell_move(c, i, old);
+}
+
+/* WallEvent, Events.c:423-499 (smooth wall): radial velocity kick of the atom alone, the wall has no recoil */
+static void wall_event(oracle_ctx *c, int i) {
+    struct sdmd_host_view *v = c->v;
+    double pi[3] = {v->x[i], v->y[i], v->z[i]}, si[3] = {v->vx[i], v->vy[i], v->vz[i]};
+    double r[3], vv[3];
+    if (v->wall_kind == SDMD_WALL_PARALLEL) { pi[0] = pi[2] = 0; si[0] = si[2] = 0; }
+    else if (v->wall_kind == SDMD_WALL_CYLINDER) { pi[0] = 0; si[0] = 0; }
+    for (int k = 0; k < 3; k++) { r[k] = pi[k] - v->wall_pos[k]; vv[k] = si[k] - 0.0; }
+    double d_ij2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    double b_ij = r[0] * vv[0] + r[1] * vv[1] + r[2] * vv[2];
+    double mass = v->mass[i];
+    double potential = v->ev_potential[i];
+    int s_vel = 0;
+    switch (v->ev_sub[i]) {
+        case SDMD_SUB_WELLBOUNC: s_vel = -1; potential = 0; break;
+        case SDMD_SUB_TBDCAPTR:
+            if (b_ij * b_ij - 2 * d_ij2 * potential / mass <= 0) { potential = 0; s_vel = 1; } else s_vel = -1;
+            break;
+        case SDMD_SUB_TBDESCAP:
+            if (b_ij * b_ij - 2 * d_ij2 * potential / mass <= 0) { potential = 0; s_vel = -1; } else s_vel = 1;
+            break;
+        default: c->st.error = SDMD_ERR_STATE; return;
+    }
+    double phi = (-1 * b_ij + s_vel * sqrt(b_ij * b_ij - 2 * d_ij2 * potential / mass)) / d_ij2;
+    if (phi != phi) { c->st.error = SDMD_ERR_STATE; return; }
+    v->vx[i] = v->vx[i] + phi * r[0]; v->vy[i] = v->vy[i] + phi * r[1]; v->vz[i] = v->vz[i] + phi * r[2];
 }
 
 /* DoEvent, Events.c:25-114 */
@@ -859,6 +941,7 @@ static void do_event(oracle_ctx *c, int i, int j) {
         }
         case SDMD_EV_THER: thermostat_event(c, i); c->st.thermostat++; break;
         case SDMD_EV_PCC: pcc_event(c, i); c->st.pcc++; break;
+        case SDMD_EV_WALL: wall_event(c, i); c->st.wall++; break;
         default: c->st.error = SDMD_ERR_STATE; break;
     }
 }

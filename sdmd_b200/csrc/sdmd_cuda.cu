@@ -152,6 +152,7 @@ __global__ void k_pbc_full(DevP D) {
     double c[3] = {D.x[i], D.y[i], D.z[i]};
 #pragma unroll
     for (int k = 0; k < 3; k++) {
+        if (!(D.pbc_mask >> k & 1)) continue;   // closed by a wall, Events.c:210-216
         if (c[k] >= D.box[k]) c[k] -= D.box[k];
         else if (c[k] < 0) c[k] += D.box[k];
     }
@@ -1061,6 +1062,12 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     P.cut2 *= P.cut2;
     P.cutfull2 = v->cutoffr * v->cutoffr;      // Events.c:1031, ToolFunctions.c:709
     P.thermoF = v->thermoF;
+    if (v->wall_kind < SDMD_WALL_NONE || v->wall_kind > SDMD_WALL_SPHERE) return set_err(SDMD_ERR_BAD_ARG, "bad wall_kind");
+    if (v->wall_kind && (v->wall_type < 1 || v->wall_type > SDMD_NATOMTYPE)) return set_err(SDMD_ERR_BAD_ARG, "bad wall_type");
+    P.wall_kind = v->wall_kind;
+    P.wall_type = v->wall_type;
+    for (int k = 0; k < 3; k++) P.wall_pos[k] = v->wall_pos[k];
+    P.pbc_mask = v->wall_kind == SDMD_WALL_PARALLEL ? 5 : v->wall_kind == SDMD_WALL_CYLINDER ? 1 : v->wall_kind == SDMD_WALL_SPHERE ? 0 : 7;
     P.thermostat_on = v->thermostat_on;
     P.method_ding = v->method_ding;
     P.hydrogen_bond = v->hydrogen_bond;
@@ -1815,6 +1822,7 @@ static void fill_stats(const Ctl *h, struct sdmd_run_stats *s) {
     s->thermostat = h->n_ther; s->pcc = h->n_pcc; s->warnings = h->warnings;
     s->pair_predictions = h->pair_predictions; s->gaussians_used = h->g_pos; s->currenttime = h->currenttime;
     s->stop_reason = h->stop ? h->stop - 1 : 0; s->error = h->error;
+    s->wall = h->n_wall;
 }
 
 int sdmd_cuda_get_stats(sdmd_ctx *c, struct sdmd_run_stats *s) {

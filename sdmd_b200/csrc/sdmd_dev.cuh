@@ -21,7 +21,7 @@ struct Ctl {
     double temperature;        // targetTemperature
     double dt;                 // AssignJob: atomList.timeInr
     i64 frame, iterations, count_recal;
-    i64 n_coli, n_bond, n_hb, n_hbne, n_ther, n_pcc;
+    i64 n_coli, n_bond, n_hb, n_hbne, n_ther, n_pcc, n_wall;
     i64 warnings, pair_predictions;
     i64 g_pos;                 // gaussians consumed (absolute)
     i64 g_filled;              // gaussians fed (absolute)
@@ -72,6 +72,9 @@ struct DevP {
     double cutoffr, cut2, cutfull2, thermoF;
     int thermostat_on, method_ding, hydrogen_bond, gel_mode;
     double hb_barrier[3];
+    int wall_kind, wall_type;  // smooth confining wall (enum sdmd_wall_kind), its row of the collision table
+    int pbc_mask;              // bit k: dimension k is periodic (Events.c:210-216)
+    double wall_pos[3];
     double *x, *y, *z, *vx, *vy, *vz;
     const double *mass;
     int *type;

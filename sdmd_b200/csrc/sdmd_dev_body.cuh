@@ -722,6 +722,44 @@ __device__ __forceinline__ void d_thermostat_time(const DevP &D, Slot &cur, doub
     d_job_assign(D, cur, 0, t, 0, SDMD_SUB_INVALID, SDMD_EV_THER);
 }
 
+// WallTime, TimePrediction.c:635-737 (smooth wall, wallDyn "no"): the wall is a pseudo-atom at rest on the mid-plane /
+// axis / centre (wall_pos); FindPair sees the squared distance from the wall SURFACE, the quadratic is solved in the
+// distance from the centre.  Visited last in Predict (SGThread.c:183-185), no partner.
+__device__ inline void d_wall_time(const DevP &D, const Self &me, Slot &cur) {
+    double px = me.x, py = me.y, pz = me.z, sx = me.vx, sy = me.vy, sz = me.vz;
+    if (D.wall_kind == SDMD_WALL_PARALLEL) { px = 0; pz = 0; sx = 0; sz = 0; }      // :654-656
+    else if (D.wall_kind == SDMD_WALL_CYLINDER) { px = 0; sx = 0; }                  // :657-660
+    Pair p;
+    p.rx = px - D.wall_pos[0]; p.ry = py - D.wall_pos[1]; p.rz = pz - D.wall_pos[2];
+    double vx = sx - 0.0, vy = sy - 0.0, vz = sz - 0.0;
+    p.r2 = p.rx * p.rx + p.ry * p.ry + p.rz * p.rz;
+    p.b = p.rx * vx + p.ry * vy + p.rz * vz;
+    p.v2 = vx * vx + vy * vy + vz * vz;
+    double by = D.box[1];
+    double dist2 = by * by * 0.25 + p.r2 - by * sqrt(p.r2);                           // :667
+    int idx = __ldg(&D.coll_index[me.type * SD_NT + D.wall_type]);
+    if (idx < 0) { D.ctl->error = SDMD_ERR_TABLE; return; }
+    FindRes f = d_find_pair_table(D, &D.tables[idx], FP_COLLISION, -1 * p.b, dist2, 0, 0);
+    if (f.lowPot == 0 && f.upPot == 0) { D.ctl->error = SDMD_ERR_STATE; return; }    // "outside of the wall": exit() :675-702
+    int s, sub;
+    double d2, pot;
+    if (p.b < 0 && d_disc(p, f.lower) > 0) {                                          // towards the centre :704-714
+        if (f.cs == 1) return;
+        sub = SDMD_SUB_TBDCAPTR;
+        s = -1;
+        d2 = by * by * 0.25 + f.upper - by * sqrt(f.upper);
+        pot = f.upPot;
+    } else {                                                                          // towards the wall :716-726
+        sub = (f.cs == 0) ? SDMD_SUB_WELLBOUNC : SDMD_SUB_TBDESCAP;
+        s = 1;
+        d2 = by * by * 0.25 + f.lower - by * sqrt(f.lower);
+        pot = f.lowPot;
+    }
+    double t = d_time(p, s, d2);
+    if (t < 0) t = SD_INF;                                                            // :729-732
+    d_job_assign(D, cur, 0, t, pot, sub, SDMD_EV_WALL);
+}
+
 __device__ __forceinline__ Self d_load_self(const DevP &D, int i) {
     Self me;
     me.i = i;
@@ -781,6 +819,7 @@ __device__ inline Slot d_predict_atom(const DevP &D, const SlotSrc &S, int i, Sl
         d_hb_time(D, S, me, cur, dup_limit);
         d_hbn_time(D, S, me, cur, dup_limit);
     }
+    if (D.wall_kind) d_wall_time(D, me, cur);
     *npair = me.npair;
     if (second) *second = cur.m2;
     return cur;
@@ -1024,6 +1063,34 @@ __device__ inline void d_hb_event(const DevP &D, int i, int j, int ni, int nj) {
     }
 }
 
+// WallEvent, Events.c:423-499 (smooth wall): radial velocity kick of the atom alone
+__device__ inline void d_wall_event(const DevP &D, int i) {
+    double px = D.x[i], py = D.y[i], pz = D.z[i], sx = D.vx[i], sy = D.vy[i], sz = D.vz[i];
+    double tvx = sx, tvy = sy, tvz = sz;
+    if (D.wall_kind == SDMD_WALL_PARALLEL) { px = 0; pz = 0; sx = 0; sz = 0; }
+    else if (D.wall_kind == SDMD_WALL_CYLINDER) { px = 0; sx = 0; }
+    double rx = px - D.wall_pos[0], ry = py - D.wall_pos[1], rz = pz - D.wall_pos[2];
+    double vx = sx - 0.0, vy = sy - 0.0, vz = sz - 0.0;
+    double d2 = rx * rx + ry * ry + rz * rz;
+    double b = rx * vx + ry * vy + rz * vz;
+    double mass = D.mass[i];
+    double pot = D.ev_pot[i];
+    int s_vel = 0;
+    switch (D.ev_sub[i]) {
+        case SDMD_SUB_WELLBOUNC: s_vel = -1; pot = 0; break;
+        case SDMD_SUB_TBDCAPTR:
+            if (b * b - 2 * d2 * pot / mass <= 0) { pot = 0; s_vel = 1; } else s_vel = -1;
+            break;
+        case SDMD_SUB_TBDESCAP:
+            if (b * b - 2 * d2 * pot / mass <= 0) { pot = 0; s_vel = -1; } else s_vel = 1;
+            break;
+        default: D.ctl->error = SDMD_ERR_STATE; return;
+    }
+    double phi = (-1 * b + s_vel * sqrt(b * b - 2 * d2 * pot / mass)) / d2;
+    if (phi != phi) { D.ctl->error = SDMD_ERR_STATE; return; }
+    D.vx[i] = tvx + phi * rx; D.vy[i] = tvy + phi * ry; D.vz[i] = tvz + phi * rz;
+}
+
 // ThermostatEvent (Andersen), Events.c:396-420; RandomVelocity ToolFunctions.c:600-610
 __device__ inline void d_thermostat_event(const DevP &D, int i) {
     double speed[3];
@@ -1059,6 +1126,7 @@ __device__ inline void d_pcc_event(const DevP &D, int i) {
     if (edge) {
 #pragma unroll
         for (int k = 0; k < 3; k++) {
+            if (!(D.pbc_mask >> k & 1)) continue;   // dimensions closed by a wall do not wrap, Events.c:210-216
             if (co[k] >= D.box[k]) co[k] -= D.box[k];
             else if (co[k] < 0) co[k] += D.box[k];
         }
@@ -1100,6 +1168,7 @@ __device__ inline void d_do_event(const DevP &D, int i, int j) {
         }
         case SDMD_EV_THER: d_thermostat_event(D, i); c->n_ther++; break;
         case SDMD_EV_PCC: d_pcc_event(D, i); c->n_pcc++; break;
+        case SDMD_EV_WALL: d_wall_event(D, i); c->n_wall++; break;
         default: c->error = SDMD_ERR_STATE; break;
     }
 }
@@ -1775,6 +1844,11 @@ __device__ inline void d_predict_cta(const DevP &D, PredShared &sh) {
             } else {
                 d_pc_fold(D, sh, a);
                 if (tid == 0) {
+                    if (D.wall_kind) {   // WallTime comes after every other predictor: one more JobAssign on the folded slot
+                        Slot w = sh.result[a];
+                        d_wall_time(D, d_load_self(D, i), w);
+                        sh.result[a] = w;
+                    }
                     d_store_slot(D, i, sh.result[a]);
                     D.ctl->pair_predictions += sh.npair[a];
                     if (D.hydrogen_bond) {

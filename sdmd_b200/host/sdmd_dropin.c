@@ -47,6 +47,7 @@ static void sync_to_reference(void) {
     HBNeighboreventsum = base_counts[4] + st.hb_neighbor;
     thermostateventsum = base_counts[5] + st.thermostat;
     pbcandcrosseventsum = base_counts[6] + st.pcc;
+    walleventsum = base_counts[7] + st.wall;
 }
 
 /* Prepare(), SGThread.c:21-64 */
@@ -59,6 +60,7 @@ static void prepare_cuda(void) {
     int fresh = strcmp("new", neworcontinue) == 0;
     if (fresh) {
         SaveData(sysInfo, fileList);
+        if (strcmp(wallExist, "smooth") == 0) SaveData(wallInfo, fileList);   /* SGThread.c:37 */
 #ifndef GEL
         SDEnergyMin(20000, &atomList);
 #endif
@@ -70,7 +72,7 @@ static void prepare_cuda(void) {
     }
     base_counts[0] = countReCal; base_counts[1] = collisioneventsum; base_counts[2] = bondeventsum;
     base_counts[3] = HBeventsum; base_counts[4] = HBNeighboreventsum; base_counts[5] = thermostateventsum;
-    base_counts[6] = pbcandcrosseventsum;
+    base_counts[6] = pbcandcrosseventsum; base_counts[7] = walleventsum;
 
     int rc = sdmd_glue_flatten(&view);
     if (rc) die("sdmd_glue_flatten (feature outside the hot-path scope?)", rc);

@@ -140,10 +140,19 @@ int sdmd_glue_flatten(struct sdmd_host_view *v) {
 #ifdef GEL
     v->gel_mode = 1;
 #endif
-    /* features that live outside the hot-path scope (walls, obstacles, tunnels, flow, CG) */
-    if (strcmp(wallExist, "no") || obstObj.mark || tunlObj.mark || SphObstObj.mark || flow.mark || CG.mark ||
-        strcmp(wallDyn.mark, "no")) {
+    /* features that live outside the hot-path scope (rough / moving walls, obstacles, tunnels, flow, CG) */
+    if (obstObj.mark || tunlObj.mark || SphObstObj.mark || flow.mark || CG.mark || strcmp(wallDyn.mark, "no")) {
         return SDMD_ERR_UNSUPPORTED;
+    }
+    /* smooth confining wall: the pseudo-atom ReadWall built (Initialization.c:1907-1935) */
+    if (strcmp(wallExist, "no")) {
+        if (strcmp(wallExist, "smooth") || wall == NULL) return SDMD_ERR_UNSUPPORTED;
+        v->wall_kind = strncmp(wallType, "parallel", 1) == 0 ? SDMD_WALL_PARALLEL
+                     : strncmp(wallType, "cylinder", 1) == 0 ? SDMD_WALL_CYLINDER
+                     : strncmp(wallType, "sphere", 1) == 0 ? SDMD_WALL_SPHERE : SDMD_WALL_NONE;
+        if (v->wall_kind == SDMD_WALL_NONE) return SDMD_ERR_UNSUPPORTED;
+        v->wall_type = wall[0].property->typeofAtom;
+        for (int k = 0; k < 3; k++) v->wall_pos[k] = wall[0].dynamic->coordinate[k + 1];
     }
 
     ALLOC(v->x, n + 1); ALLOC(v->y, n + 1); ALLOC(v->z, n + 1);
@@ -291,6 +300,9 @@ void sdmd_snap_put_view(sdmd_snap *s, const struct sdmd_host_view *v) {
     sdmd_snap_put(s, "scalars_i4", "i4", ints, 8);
     sdmd_snap_put(s, "scalars_f8", "f8", dbl, 12);
     sdmd_snap_put(s, "scalars_i8", "i8", i64, 1);
+    int32_t wall_i[2] = {v->wall_kind, v->wall_type};
+    sdmd_snap_put(s, "wall_i4", "i4", wall_i, 2);
+    sdmd_snap_put(s, "wall_f8", "f8", v->wall_pos, 3);
 #define PUT(field, dt, cnt) sdmd_snap_put(s, #field, dt, v->field, cnt)
     PUT(x, "f8", n1); PUT(y, "f8", n1); PUT(z, "f8", n1);
     PUT(vx, "f8", n1); PUT(vy, "f8", n1); PUT(vz, "f8", n1);

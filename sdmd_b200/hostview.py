@@ -13,7 +13,7 @@ from pathlib import Path
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 NT = 33
 NHBCLASS = 12
 MAX_STEPS = 16
@@ -57,6 +57,7 @@ class CHostView(C.Structure):
         ("ntable", C.c_int32), ("tables", C.c_void_p),
         ("coll_index", _P(C.c_int32)), ("hb_index", _P(C.c_int32)),
         ("hb_barrier", C.c_double * 3),
+        ("wall_kind", C.c_int32), ("wall_type", C.c_int32), ("wall_pos", C.c_double * 3),
     ]
 
 
@@ -67,6 +68,7 @@ class CRunStats(C.Structure):
         ("thermostat", C.c_int64), ("pcc", C.c_int64), ("warnings", C.c_int64),
         ("pair_predictions", C.c_int64), ("gaussians_used", C.c_int64),
         ("currenttime", C.c_double), ("stop_reason", C.c_int32), ("error", C.c_int32),
+        ("wall", C.c_int64),
     ]
 
     def as_dict(self):
@@ -136,6 +138,9 @@ class HostView:
         self.gel_mode = 0
         self.frame = 0
         self.hb_barrier = np.zeros(3)
+        self.wall_kind = 0          # enum sdmd_wall_kind: 0 none, 1 parallel plates, 2 cylinder, 3 sphere
+        self.wall_type = 0
+        self.wall_pos = np.zeros(3)
         for name, dt, k in PER_ATOM:
             setattr(self, name, np.zeros(n1 * k, dtype=_NP[dt]))
         for name in ("bond_off", "con_off", "cm_off"):
@@ -159,13 +164,16 @@ class HostView:
         hv.cutoffr, hv.thermoF, hv.target_temperature, hv.currenttime, hv.timestep = (float(v) for v in sf[3:8])
         hv.hb_barrier = sf[8:11].copy()
         hv.frame = int(d["scalars_i8"][0])
+        if "wall_i4" in d:          # absent in snapshots written before the wall fields existed = no wall
+            hv.wall_kind, hv.wall_type = (int(v) for v in d["wall_i4"][:2])
+            hv.wall_pos = np.asarray(d["wall_f8"], dtype=np.float64)[:3].copy()
         for name, dt, _ in PER_ATOM:
             setattr(hv, name, np.ascontiguousarray(d[name], dtype=_NP[dt]).copy())
         for name, dt in OTHER:
             arr = np.ascontiguousarray(d[name], dtype=_NP[dt]).copy()
             setattr(hv, name, arr if arr.size else np.zeros(1, dtype=_NP[dt]))
         hv.tables = np.frombuffer(d["tables"].tobytes(), dtype=STEP_TABLE_DTYPE).copy()
-        known = {n for n, _, _ in PER_ATOM} | {n for n, _ in OTHER} | {"scalars_i4", "scalars_f8", "scalars_i8", "tables"}
+        known = {n for n, _, _ in PER_ATOM} | {n for n, _ in OTHER} | {"scalars_i4", "scalars_f8", "scalars_i8", "tables", "wall_i4", "wall_f8"}
         hv.extra = {k: v for k, v in d.items() if k not in known}
         return hv
 
@@ -184,6 +192,8 @@ class HostView:
             "scalars_f8": np.array([*self.box, self.cutoffr, self.thermoF, self.target_temperature, self.currenttime,
                                     self.timestep, *self.hb_barrier, 0.0]),
             "scalars_i8": np.array([self.frame], dtype=np.int64),
+            "wall_i4": np.array([self.wall_kind, self.wall_type], dtype=np.int32),
+            "wall_f8": np.array(self.wall_pos, dtype=np.float64),
             "tables": np.frombuffer(self.tables.tobytes(), dtype=np.uint8),
         }
         for name, _, _ in PER_ATOM:
@@ -214,6 +224,8 @@ class HostView:
         c.hydrogen_bond, c.gel_mode = int(self.hydrogen_bond), int(self.gel_mode)
         c.frame = int(self.frame)
         c.hb_barrier[:] = [float(v) for v in self.hb_barrier]
+        c.wall_kind, c.wall_type = int(self.wall_kind), int(self.wall_type)
+        c.wall_pos[:] = [float(v) for v in self.wall_pos]
         for name, dt, _ in PER_ATOM:
             arr = getattr(self, name)
             assert arr.flags["C_CONTIGUOUS"] and arr.dtype == _NP[dt], name

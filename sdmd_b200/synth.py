@@ -29,8 +29,12 @@ def gel_table(core=4.0, step_d=6.5, step_e=0.2):
 
 
 def gel_box(n_axis: int, a: float = 8.0, temperature: float = 0.6, seed: int = 1575263273, step_e: float = 0.2,
-            timestep: float = 1e9, jitter: float = 0.0) -> tuple[HostView, np.random.Generator]:
-    """n_axis^3 GEL particles.  Returns (host view, rng) — draw thermostat gaussians from ``rng``."""
+            timestep: float = 1e9, jitter: float = 0.0, wall_pad: float | None = None) -> tuple[HostView, np.random.Generator]:
+    """n_axis^3 GEL particles.  Returns (host view, rng) — draw thermostat gaussians from ``rng``.
+
+    ``wall_pad`` (A) confines the box between two smooth parallel plates normal to y (WallExist smooth / WallType
+    parallel with a GEL-type wall atom, ReadWall Initialization.c:1907-1935): the box grows by ``wall_pad`` on either side
+    in y so the outermost lattice planes sit a/2 + wall_pad from the plates."""
     n = n_axis ** 3
     hv = HostView(n)
     hv.box[:] = n_axis * a
@@ -51,6 +55,12 @@ def gel_box(n_axis: int, a: float = 8.0, temperature: float = 0.6, seed: int = 1
     if jitter:
         for arr in (hv.x, hv.y, hv.z):
             arr[1:] += rng.uniform(-jitter, jitter, n)
+    if wall_pad is not None:
+        hv.box[1] += 2 * wall_pad
+        hv.y[1:] += wall_pad
+        hv.wall_kind = 1
+        hv.wall_type = GEL_TYPE
+        hv.wall_pos[:] = (0.0, hv.box[1] / 2, 0.0)
     hv.mass[1:] = 12.0
     hv.type[1:] = GEL_TYPE
     hv.aa_type[1:] = 21

@@ -79,6 +79,33 @@ def test_dropin_continue_run_matches_reference(tmp_path):
         assert _counter(outs["ref"], key) == _counter(outs["gpu"], key), key
 
 
+@pytest.mark.parametrize("wall_type", ["parallel", "cylinder"])
+def test_dropin_walled_run_matches_reference(tmp_path, wall_type):
+    """BASELINE config 4 (confinement): WallExist smooth, WallType parallel / cylinder, chains of ala10 inside — the
+    drop-in driver must write the same trajectory and counters (wall events included) as the stock binary."""
+    if not (REF / "sDMD_ref").exists() or not DROPIN.exists():
+        pytest.skip("needs oracle/_ref/sDMD_ref and the drop-in driver")
+    from oracle.make_golden import WALLS, prepare_input, write_multi_ala10
+    _, copies, spacing, box = WALLS["ala10x8_wallp" if wall_type == "parallel" else "ala10x4_wallc"]
+    outs = {}
+    for tag, binary in (("ref", REF / "sDMD_ref"), ("gpu", DROPIN)):
+        work = tmp_path / tag
+        work.mkdir()
+        inp = prepare_input(work, time_units=60, wall_type=wall_type)
+        write_multi_ala10(inp / "walled.gro", inp / "ala10.gro", copies_per_axis=copies, spacing_nm=spacing, box_nm=box)
+        r = subprocess.run([str(binary), "-f", "walled.gro", "-i", str(inp), "-o", str(work / "out")],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs[tag] = r.stdout.replace("\r", "\n")
+    for name in ("out_trj.gro", "out_cnt.txt"):
+        a = (tmp_path / "ref" / "out" / name).read_bytes()
+        b = (tmp_path / "gpu" / "out" / name).read_bytes()
+        assert len(a) > 1000 and a == b, name
+    for key in ("collision times", "bond times", "thermostat times", "PBC&CC times", "Wall times"):
+        assert _counter(outs["ref"], key) == _counter(outs["gpu"], key), key
+    assert _counter(outs["gpu"], "Wall times") > 0
+
+
 def test_dropin_remd_with_reference_server(tmp_path):
     """demo/REMD-style run with the reference's own sServer: three replica processes of the drop-in driver (sharing
     the GPU) must log the same temperature walk (out_REMD<id>.txt) and trajectories as three stock sDMD processes."""

@@ -22,7 +22,7 @@ def _replica(capi, pre):
     return hv, r
 
 
-@pytest.mark.parametrize("case", ["ala10", "gel10", "ala10x8"])
+@pytest.mark.parametrize("case", ["ala10", "gel10", "ala10x8", "ala10x8_wallp"])
 def test_cell_build_matches_reference(capi, case):
     pre, post, fin = load_case(case)
     hv, r = _replica(capi, pre)
@@ -34,7 +34,7 @@ def test_cell_build_matches_reference(capi, case):
     assert_fields_equal(hv, pre, ("cell_idx", "x", "y", "z"))
 
 
-@pytest.mark.parametrize("case", ["ala10", "gel10", "ala10x8"])
+@pytest.mark.parametrize("case", ["ala10", "gel10", "ala10x8", "ala10x8_wallp"])
 def test_predict_all_and_cbt_match_reference(capi, case):
     pre, post, fin = load_case(case)
     hv, r = _replica(capi, pre)
@@ -50,7 +50,7 @@ def test_predict_all_and_cbt_match_reference(capi, case):
     assert r.kinetic_energy() == post.extra["ekin"][0]
 
 
-@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8"])
+@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8", "ala10x8_wallp", "ala10x4_wallc"])
 @pytest.mark.parametrize("loop_mode", [0, 2, 3], ids=["one_cta", "sweep_overlapped", "sweep_serial"])
 def test_device_event_loop_matches_reference(capi, case, loop_mode):
     """loop_mode 2 / 3 force the large-system drivers (grid-wide sweep overlapped with / followed by one event block per
@@ -78,6 +78,8 @@ def test_device_event_loop_matches_reference(capi, case, loop_mode):
     got = [st[k] for k in ("frame", "iterations", "count_recal", "collision", "bond", "hb", "hb_neighbor", "thermostat", "pcc")]
     assert got == ref
     assert r.potential_energy() == fin.extra["epot"][0]
+    if "wall" in case:   # smooth confining wall: WallTime in every prediction, WallEvent executed
+        assert st["wall"] == int(fin.extra["stats"][11]) and st["wall"] > 0
 
 
 def test_stepwise_api_matches_run(capi):
@@ -129,6 +131,37 @@ def test_large_gel_box_against_oracle(capi):
         assert sg[k] == so[k], k
     assert np.float64(r.potential_energy()).tobytes() == np.float64(o.potential_energy()).tobytes()
     assert np.float64(r.kinetic_energy()).tobytes() == np.float64(o.kinetic_energy()).tobytes()
+
+
+@pytest.mark.parametrize("n_axis,iters", [(16, 3000), (40, 1500)])
+def test_walled_gel_box_against_oracle(capi, n_axis, iters):
+    """GEL box between two smooth parallel plates (outermost lattice planes inside the wall's potential step): the wall
+    predictor inside the full-system pass (K2 incl. the duplicate fix-point), the one-block loop (N = 4096) and the
+    sweep loop (N = 64000), PBC in x and z only — CUDA vs the CPU oracle, bit for bit."""
+    from oracle.oracle_py import Oracle
+    from sdmd_b200.synth import gel_box
+    hv0, rng = gel_box(n_axis, jitter=0.3, wall_pad=1.2)
+    gauss = rng.standard_normal(hv0.natom + 20 * iters)
+    ho = hv0.copy(); o = Oracle(ho); o.rng_feed(gauss)
+    hg = hv0.copy(); r = capi.Replica(hg, device=0); r.rng_feed(gauss)
+    o.pbc_full(); o.cell_build(); o.predict_all(); o.cbt_build()
+    r.pbc_full(); r.cell_build(); r.predict_all(); r.cbt_build()
+    assert np.array_equal(r.celllist(), o.celllist())
+    r.download(hg)
+    assert_fields_equal(hg, ho, SLOT_FIELDS + ("cell_idx",))
+    assert (ho.ev_type[1:] == 5).sum() > 0          # wall events are scheduled from the start
+    assert r.stats()["pair_predictions"] == o.stats()["pair_predictions"]
+    so, to = o.run(max_iter=iters, trace_cap=iters)
+    sg, tg = r.run(max_iter=iters, trace_cap=iters)
+    assert so["error"] == 0 and sg["error"] == 0
+    assert_trace_equal(tg, to)
+    r.download(hg)
+    assert_fields_equal(hg, ho, STATE_FIELDS)
+    assert np.array_equal(r.celllist(), o.celllist())
+    for k in ("frame", "count_recal", "collision", "thermostat", "pcc", "wall", "pair_predictions", "gaussians_used"):
+        assert sg[k] == so[k], k
+    if n_axis == 16:
+        assert so["wall"] > 0   # (at N = 64000 the first 1500 events are all thermostat / cell crossings)
 
 
 def test_round_trip_properties_1m(capi):

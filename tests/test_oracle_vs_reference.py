@@ -19,7 +19,7 @@ def _prepare(pre):
     return hv, o
 
 
-@pytest.mark.parametrize("case", ["ala10", "gel10", "ala10x8"])
+@pytest.mark.parametrize("case", ["ala10", "gel10", "ala10x8", "ala10x8_wallp"])
 def test_cell_grid_and_link_list(case):
     pre, post, fin = load_case(case)
     hv, o = _prepare(pre)
@@ -32,7 +32,7 @@ def test_cell_grid_and_link_list(case):
     assert_fields_equal(hv, pre, ("cell_idx", "x", "y", "z"))
 
 
-@pytest.mark.parametrize("case", ["ala10", "gel10", "ala10x8"])
+@pytest.mark.parametrize("case", ["ala10", "gel10", "ala10x8", "ala10x8_wallp"])
 def test_predict_all_and_cbt(case):
     pre, post, fin = load_case(case)
     hv, o = _prepare(pre)
@@ -47,7 +47,7 @@ def test_predict_all_and_cbt(case):
     assert o.kinetic_energy() == post.extra["ekin"][0]
 
 
-@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8"])
+@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8", "ala10x8_wallp", "ala10x4_wallc"])
 def test_event_loop_trace(case):
     pre, post, fin = load_case(case)
     hv, o = _prepare(pre)
@@ -69,6 +69,10 @@ def test_event_loop_trace(case):
     assert o.potential_energy() == fin.extra["epot"][0]
     if case == "ala10_hb":
         assert st["hb"] > 0 and st["hb_neighbor"] > 0  # the fixture really exercises the HB paths
+    if "wall" in case:
+        # smooth confining wall: WallTime runs in every prediction, WallEvent a few times
+        assert pre.wall_kind in (1, 2) and st["wall"] == int(ref[11]) and st["wall"] > 0
+        assert (want["type"] == 5).sum() >= st["wall"]
 
 
 @pytest.mark.refbin
