@@ -164,6 +164,50 @@ def test_walled_gel_box_against_oracle(capi, n_axis, iters):
         assert so["wall"] > 0   # (at N = 64000 the first 1500 events are all thermostat / cell crossings)
 
 
+def _tie_box():
+    """8^3 GEL lattice (no jitter) with planted exact ties: a centre atom C and its two lattice neighbours along one axis
+    approach it with mirrored velocities (all values dyadic, so C's two candidate times are the same bits).  The
+    reference keeps the candidate it visits first."""
+    from sdmd_b200.synth import gel_box
+    hv, rng = gel_box(8, jitter=0.0)
+    n = 8
+    planted = []
+    for axis, (cx, cy, cz) in ((0, (3, 2, 2)), (1, (5, 3, 6)), (2, (2, 6, 4)), (0, (6, 6, 1)), (1, (1, 4, 3)), (2, (4, 1, 5)),
+                               (0, (1, 1, 6)), (2, (6, 3, 3))):
+        idx = lambda x, y, z: 1 + x + n * y + n * n * z
+        c = idx(cx, cy, cz)
+        d = [0, 0, 0]; d[axis] = 1
+        a = idx(cx - d[0], cy - d[1], cz - d[2]); b = idx(cx + d[0], cy + d[1], cz + d[2])
+        base = [0.25, 0.125, -0.375]
+        for atom, sgn in ((c, 0), (a, +1), (b, -1)):
+            v = list(base); v[axis] += sgn * 2.0
+            hv.vx[atom], hv.vy[atom], hv.vz[atom] = v
+        planted.append((c, a, b))
+    return hv, rng, planted
+
+
+def test_exact_ties_keep_reference_visiting_order(capi):
+    """Exact ties between two candidates of one atom must go to the one the reference visits first (strict '<', first
+    wins, TimePrediction.c:1142) in the full-system pass, its resolve / re-evaluation rounds and the event loop."""
+    from oracle.oracle_py import Oracle
+    hv0, rng, planted = _tie_box()
+    gauss = rng.standard_normal(hv0.natom + 40000)
+    ho = hv0.copy(); o = Oracle(ho); o.rng_feed(gauss)
+    hg = hv0.copy(); r = capi.Replica(hg, device=0); r.rng_feed(gauss)
+    o.pbc_full(); o.cell_build(); o.predict_all(); o.cbt_build()
+    r.pbc_full(); r.cell_build(); r.predict_all(); r.cbt_build()
+    r.download(hg)
+    assert_fields_equal(hg, ho, SLOT_FIELDS + ("cell_idx",))
+    won = [c for c, a, b in planted if ho.ev_partner[c] in (a, b)]
+    assert len(won) >= 4, won          # the planted pairs really are the earliest events of their centre atoms
+    assert r.stats()["pair_predictions"] == o.stats()["pair_predictions"]
+    so, to = o.run(max_iter=1500, trace_cap=1500)
+    sg, tg = r.run(max_iter=1500, trace_cap=1500)
+    assert_trace_equal(tg, to)
+    r.download(hg)
+    assert_fields_equal(hg, ho, STATE_FIELDS)
+
+
 def test_round_trip_properties_1m(capi):
     """Full size (N = 10^6): size-independent properties instead of an element-wise oracle comparison —
     link list is a permutation with every atom in the cell its coordinates say, CBT root is the global
