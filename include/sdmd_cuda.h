@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SDMD_ABI_VERSION 2
+#define SDMD_ABI_VERSION 3
 
 /* reference constants, DMD.h:25-30 */
 #define SDMD_INFINIT       1E8
@@ -33,6 +33,7 @@ extern "C" {
 #define SDMD_EXTEND_RATIO  0.90
 #define SDMD_MAX_STEPS     16     /* longest shipped table row has 13 steps */
 #define SDMD_NHBCLASS      12     /* potentialPairHB[12][33][33], DMD.h:550 */
+#define SDMD_MAX_OBST      4      /* flat obstruction walls / spherical obstacles the device keeps (each) */
 
 /* connection-map bits, DMD.h:59-63 */
 #define SDMD_BOND_CONNECT        0x01
@@ -148,6 +149,18 @@ struct sdmd_host_view {
     int32_t wall_kind;                /* enum sdmd_wall_kind */
     int32_t wall_type;                /* wall[0].property->typeofAtom: row of the collision table the wall interacts through */
     double  wall_pos[3];              /* wall[0].dynamic->coordinate[1..3]: the axis / mid-plane / centre the distance is taken from */
+
+    /* flat obstruction walls without holes ("Obstruct?" line of parameter.txt, Initialization.c:637-676; pseudo-atoms
+     * built by ReadWall :1981-2012; ObstTime TimePrediction.c:740-829, ObstEvent Events.c:543-619).  Event partner code
+     * -dim - 10 n (TimePrediction.c:823). */
+    int32_t n_obst;                   /* obstObj.num, <= SDMD_MAX_OBST */
+    int32_t n_sphobst;                /* SphObstObj.num, <= SDMD_MAX_OBST */
+    double  obst_pos[SDMD_MAX_OBST][3];   /* obstObj.position[n][1..3]; negative = no plane in that dimension */
+    int32_t obst_type[SDMD_MAX_OBST];     /* obstObj.obst[n].property->typeofAtom */
+    /* hard spherical obstacles ("SphObst?" line, Initialization.c:701-726; SphObstTime TimePrediction.c:1020-1071,
+     * SphObstEvent Events.c:752-796).  Event partner code -1000 n. */
+    double  sphobst_pos[SDMD_MAX_OBST][3];
+    double  sphobst_radius[SDMD_MAX_OBST]; /* SphObstObj.radius[n] (the file gives the diameter) */
 };
 
 /* wallType (parameter.txt line 11), first letter decides (strncmp(...,1)): which coordinates take part in the wall distance
@@ -171,7 +184,7 @@ struct sdmd_run_stats {
     double  currenttime;
     int32_t stop_reason;              /* enum sdmd_stop_reason */
     int32_t error;                    /* first device-side SDMD_ERR_* or 0 */
-    int64_t wall;                     /* walleventsum (Events.c:73-76) */
+    int64_t wall;                     /* walleventsum: wall, obstruction and spherical-obstacle events (Events.c:73-100) */
 };
 
 enum sdmd_stop_reason {

@@ -13,6 +13,8 @@ reference's own inputs and stores what the reference computed as compressed .npz
   ala10x8_wallp  8 ala10 chains between two smooth parallel plates (WallExist smooth / WallType parallel, plates normal
                to y, 38 A apart; Wall.txt atom type CA because the shipped PHO is only valid in CG mode): WallTime /
                WallEvent, PBC in x and z only
+  ala10x8_obst   8 ala10 chains between two flat obstruction walls ("Obstruct? 2 y .. , y ..") and three hard spherical
+               obstacles ("SphObst? 3 ..."), periodic box, snapshot after 20000 iterations, then 8000 traced
   ala10x4_wallc  4 ala10 chains in a smooth cylinder along x (WallType cylinder, diameter 26 A), snapshot after 20000
                iterations, then 8000 traced
 
@@ -46,11 +48,16 @@ CASES = {
     # smooth confining walls
     "ala10x8_wallp": ("ref_harness", "ala10x8w.gro", 8000, 40000, [], -8),
     "ala10x4_wallc": ("ref_harness", "ala10x4c.gro", 8000, 40000, ["--warm", "20000"], -8),
+    "ala10x8_obst": ("ref_harness", "ala10x8o.gro", 8000, 40000, ["--warm", "20000"], -8),
 }
-# name: (WallType, chains per axis, spacing nm, box nm)
+# name: (WallType, chains per axis, spacing nm, box nm[, "Obstruct?" value, "SphObst?" value])
 WALLS = {
     "ala10x8_wallp": ("parallel", (2, 2, 2), 1.9, (5.0, 3.8, 5.0)),
     "ala10x4_wallc": ("cylinder", (4, 1, 1), 2.0, (8.0, 2.6, 2.6)),
+    # two flat obstruction walls normal to y (1.5 A inside the periodic box faces) and three hard spheres of diameter 5 A,
+    # each 0.4 A off the outermost atom of a chain (positions in A, parameter.txt lines 14 and 16); no smooth wall
+    "ala10x8_obst": (None, (2, 2, 2), 1.9, (5.0, 4.2, 5.0), "2 y 1.5 , y 40.5",
+                     "3 19.82 17.45 24.49 5.0 , 26.29 29.64 14.62 5.0 , 31.27 10.75 25.88 5.0"),
 }
 
 
@@ -90,7 +97,8 @@ def write_multi_ala10(path: Path, src: Path, copies_per_axis=2, spacing_nm: floa
         f.write("%10.5f%10.5f%10.5f\n" % tuple(box))
 
 
-def prepare_input(work: Path, time_units: float = 1000.0, wall_type: str | None = None) -> Path:
+def prepare_input(work: Path, time_units: float = 1000.0, wall_type: str | None = None, obst: str | None = None,
+                  sphobst: str | None = None) -> Path:
     """Writable copy of the reference input directory with the run length (and a smooth wall) set."""
     src = REFDIR / "input"
     if not src.exists():
@@ -105,6 +113,11 @@ def prepare_input(work: Path, time_units: float = 1000.0, wall_type: str | None 
     if wall_type:
         lines[9] = "WallExist?         smooth"
         lines[10] = "WallType           %s" % wall_type
+    if obst:
+        lines[13] = "Obstruct?          %s" % obst
+    if sphobst:
+        lines[15] = "SphObst?           %s" % sphobst
+    if wall_type or obst:
         # the wall's atom type must be a valid AtomModel name (Models.c:129-209); the shipped PHO is CG-only
         (inp / "Library_Ding" / "Wall.txt").write_text("Wall\n   ATOM CA      CA    12.0  N N\n")
     p.write_text("\n".join(lines) + "\n")
@@ -119,7 +132,8 @@ def run_case(name: str, work: Path, harness=None, coord=None, max_iter=None, n_g
                                                            zip(spec, (harness, coord, max_iter, n_gauss, extra, gel_n))]
     work.mkdir(parents=True, exist_ok=True)
     wall = WALLS.get(name)
-    inp = prepare_input(work, wall_type=wall[0] if wall else None)
+    inp = prepare_input(work, wall_type=wall[0] if wall else None, obst=wall[4] if wall and len(wall) > 4 else None,
+                        sphobst=wall[5] if wall and len(wall) > 5 else None)
     if wall:
         write_multi_ala10(inp / coord, inp / "ala10.gro", copies_per_axis=wall[1], spacing_nm=wall[2], box_nm=wall[3])
     elif gel_n and gel_n > 0:

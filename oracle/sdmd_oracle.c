@@ -240,7 +240,7 @@ static int find_pair(oracle_ctx *c, int a1, int a2, int mode, double direction, 
         int t1 = v->type[a1];
         if (typeChange == 1) t1 = type_change(t1, 1);
         else if (typeChange == -1) t1 = type_change(t1, 0);
-        idx = v->coll_index[t1 * NT + (a2 < 0 ? v->wall_type : v->type[a2])];   /* a2 < 0: the wall pseudo-atom, :642-667 */
+        idx = v->coll_index[t1 * NT + (a2 == -1 ? v->wall_type : a2 < -1 ? v->obst_type[-a2 - 2] : v->type[a2])];   /* -1: wall pseudo-atom, -2-n: obstruction n */
     } else if (mode == FP_CONSTRAINT) {            /* :68-77 */
         for (int k = v->con_off[a1]; k < v->con_off[a1 + 1]; k++)
             if (v->con_j[k] == a2) { idx = v->con_table[k]; break; }
@@ -623,6 +623,64 @@ static void wall_time(oracle_ctx *c, int i) {
     job_assign(c, i, 0, &ev, SDMD_EV_WALL);
 }
 
+/* ObstTime, TimePrediction.c:740-829, obstruction walls without holes: one-dimensional distance from the plane */
+static void obst_time(oracle_ctx *c, int i) {
+    struct sdmd_host_view *v = c->v;
+    const double pos[3] = {v->x[i], v->y[i], v->z[i]}, spd[3] = {v->vx[i], v->vy[i], v->vz[i]};
+    for (int n = 0; n < v->n_obst; n++) {
+        struct evt ev;
+        struct par p;
+        init_event(&ev);
+        for (int dim = 0; dim < 3; dim++) {
+            if (v->obst_pos[n][dim] < 0) continue;
+            for (int k = 0; k < 3; k++) {
+                double pi = (k == dim) ? pos[k] : 0, pj = (k == dim) ? v->obst_pos[n][k] : 0, si = (k == dim) ? spd[k] : 0;
+                p.r_ij[k] = pi - pj; p.v_ij[k] = si - 0.0;
+            }
+            p.r_2 = p.r_ij[0] * p.r_ij[0] + p.r_ij[1] * p.r_ij[1] + p.r_ij[2] * p.r_ij[2];
+            p.b_ij = p.r_ij[0] * p.v_ij[0] + p.r_ij[1] * p.v_ij[1] + p.r_ij[2] * p.v_ij[2];
+            p.v_2 = p.v_ij[0] * p.v_ij[0] + p.v_ij[1] * p.v_ij[1] + p.v_ij[2] * p.v_ij[2];
+            double accum;
+            p.coreorShell = find_pair(c, i, -2 - n, FP_COLLISION, p.b_ij, p.r_2, &p.shortlimit2, &p.longlimit2,
+                                      &p.lowerPotential, &p.upperPotential, &accum, 0, 0);
+            if (p.lowerPotential == 0 && p.upperPotential == 0) continue;           /* :783-787 */
+            if (p.b_ij < 0) {                                                         /* approaching :789-798 */
+                ev.sub = (p.coreorShell == 0) ? SDMD_SUB_CORECOLLI : SDMD_SUB_TBDCAPTR;
+                p.s_time = -1; p.d_ij2 = p.shortlimit2; ev.potential = p.lowerPotential;
+            } else {                                                                  /* leaving :800-810 */
+                if (p.coreorShell == 1) continue;
+                ev.sub = SDMD_SUB_TBDESCAP;
+                p.s_time = 1; p.d_ij2 = p.longlimit2; ev.potential = p.upperPotential;
+            }
+            ev.time = calc_time(&p);
+            if (ev.time < 0) { c->st.error = SDMD_ERR_STATE; return; }                /* exit(), :813-816 */
+            if (job_assign(c, i, 0, &ev, SDMD_EV_OBST)) v->ev_partner[i] = -1 * (dim + 1) - 10 * n;   /* :820-824 */
+        }
+    }
+}
+
+/* SphObstTime, TimePrediction.c:1020-1071: hard sphere at rest, core collision only */
+static void sphobst_time(oracle_ctx *c, int i) {
+    struct sdmd_host_view *v = c->v;
+    for (int n = 0; n < v->n_sphobst; n++) {
+        struct evt ev;
+        struct par p;
+        init_event(&ev);
+        p.r_ij[0] = v->x[i] - v->sphobst_pos[n][0]; p.r_ij[1] = v->y[i] - v->sphobst_pos[n][1]; p.r_ij[2] = v->z[i] - v->sphobst_pos[n][2];
+        p.v_ij[0] = v->vx[i] - 0.0; p.v_ij[1] = v->vy[i] - 0.0; p.v_ij[2] = v->vz[i] - 0.0;
+        p.r_2 = p.r_ij[0] * p.r_ij[0] + p.r_ij[1] * p.r_ij[1] + p.r_ij[2] * p.r_ij[2];
+        p.b_ij = p.r_ij[0] * p.v_ij[0] + p.r_ij[1] * p.v_ij[1] + p.r_ij[2] * p.v_ij[2];
+        p.v_2 = p.v_ij[0] * p.v_ij[0] + p.v_ij[1] * p.v_ij[1] + p.v_ij[2] * p.v_ij[2];
+        p.shortlimit2 = v->sphobst_radius[n] * v->sphobst_radius[n];
+        if (!(p.b_ij < 0 && calc_disc(&p) > 0)) continue;
+        ev.sub = SDMD_SUB_CORECOLLI;
+        p.s_time = -1; p.d_ij2 = p.shortlimit2; ev.potential = 0;
+        ev.time = calc_time(&p);
+        if (ev.time < 0) { c->st.error = SDMD_ERR_STATE; return; }
+        if (job_assign(c, i, 0, &ev, SDMD_EV_SPHO)) v->ev_partner[i] = -1000 * n;
+    }
+}
+
 /* Predict, SGThread.c:158-211 (+ ResetTarget, ToolFunctions.c:504-514) */
 void oracle_predict(oracle_ctx *c, const int32_t *renew) {
     struct sdmd_host_view *v = c->v;
@@ -639,6 +697,8 @@ void oracle_predict(oracle_ctx *c, const int32_t *renew) {
         thermostat_time(c, i);
         if (v->hydrogen_bond) { hb_time(c, i); hbn_time(c, i); }
         if (v->wall_kind) wall_time(c, i);                       /* SGThread.c:183-185 */
+        if (v->n_obst) obst_time(c, i);                          /* :187-189 */
+        if (v->n_sphobst) sphobst_time(c, i);                    /* :205-207 */
     }
 }
 
@@ -925,6 +985,45 @@ static void wall_event(oracle_ctx *c, int i) {
     v->vx[i] = v->vx[i] + phi * r[0]; v->vy[i] = v->vy[i] + phi * r[1]; v->vz[i] = v->vz[i] + phi * r[2];
 }
 
+/* ObstEvent, Events.c:543-619, and SphObstEvent, Events.c:752-796: the kick along the one-dimensional / radial
+ * separation; the obstacle has no recoil.  sph: spherical obstacle, else obstruction plane (partner code decides which) */
+static void obst_event(oracle_ctx *c, int i, int sph) {
+    struct sdmd_host_view *v = c->v;
+    double r[3], vv[3];
+    const double pos[3] = {v->x[i], v->y[i], v->z[i]}, spd[3] = {v->vx[i], v->vy[i], v->vz[i]};
+    int partner = v->ev_partner[i];
+    if (sph) {
+        int n = partner / -1000;
+        for (int k = 0; k < 3; k++) { r[k] = pos[k] - v->sphobst_pos[n][k]; vv[k] = spd[k] - 0.0; }
+    } else {
+        int n = partner / -10, dim = (partner * -1) % 10 - 1;
+        for (int k = 0; k < 3; k++) {
+            double pi = (k == dim) ? pos[k] : 0, pj = (k == dim) ? v->obst_pos[n][k] : 0, si = (k == dim) ? spd[k] : 0;
+            r[k] = pi - pj; vv[k] = si - 0.0;
+        }
+    }
+    double d_ij2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    double b_ij = r[0] * vv[0] + r[1] * vv[1] + r[2] * vv[2];
+    double mass = v->mass[i];
+    double potential = v->ev_potential[i];
+    int s_vel = 0;
+    switch (v->ev_sub[i]) {
+        case SDMD_SUB_CORECOLLI: s_vel = 1; potential = 0; break;
+        case SDMD_SUB_TBDCAPTR:
+            if (sph) { c->st.error = SDMD_ERR_STATE; return; }
+            if (b_ij * b_ij - 2 * d_ij2 * potential / mass <= 0) { potential = 0; s_vel = 1; } else s_vel = -1;
+            break;
+        case SDMD_SUB_TBDESCAP:
+            if (sph) { c->st.error = SDMD_ERR_STATE; return; }
+            if (b_ij * b_ij - 2 * d_ij2 * potential / mass <= 0) { potential = 0; s_vel = -1; } else s_vel = 1;
+            break;
+        default: c->st.error = SDMD_ERR_STATE; return;
+    }
+    double phi = (-1 * b_ij + s_vel * sqrt(b_ij * b_ij - 2 * d_ij2 * potential / mass)) / d_ij2;
+    if (phi != phi) { c->st.error = SDMD_ERR_STATE; return; }
+    v->vx[i] = v->vx[i] + phi * r[0]; v->vy[i] = v->vy[i] + phi * r[1]; v->vz[i] = v->vz[i] + phi * r[2];
+}
+
 /* DoEvent, Events.c:25-114 */
 static void do_event(oracle_ctx *c, int i, int j) {
     struct sdmd_host_view *v = c->v;
@@ -942,6 +1041,8 @@ static void do_event(oracle_ctx *c, int i, int j) {
         case SDMD_EV_THER: thermostat_event(c, i); c->st.thermostat++; break;
         case SDMD_EV_PCC: pcc_event(c, i); c->st.pcc++; break;
         case SDMD_EV_WALL: wall_event(c, i); c->st.wall++; break;
+        case SDMD_EV_OBST: obst_event(c, i, 0); c->st.wall++; break;
+        case SDMD_EV_SPHO: obst_event(c, i, 1); c->st.wall++; break;
         default: c->st.error = SDMD_ERR_STATE; break;
     }
 }

@@ -1055,7 +1055,7 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     }
     for (int k = 0; k < 3; k++) P.cellsize[k] = v->box[k] / P.cellnum[k];
     long long ncell = (long long)P.cellnum[0] * P.cellnum[1] * P.cellnum[2];
-    if (ncell > (1LL << 30)) { delete c; return set_err(SDMD_ERR_BAD_ARG, "cell grid too large"); }
+    if (ncell > (1LL << 30)) return set_err(SDMD_ERR_BAD_ARG, "cell grid too large");   // the caller releases c
     P.ncell = (int)ncell;
     P.cutoffr = v->cutoffr;
     P.cut2 = v->cutoffr * SDMD_EXTEND_RATIO;  // TimePrediction.c:53-54
@@ -1068,6 +1068,20 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     P.wall_type = v->wall_type;
     for (int k = 0; k < 3; k++) P.wall_pos[k] = v->wall_pos[k];
     P.pbc_mask = v->wall_kind == SDMD_WALL_PARALLEL ? 5 : v->wall_kind == SDMD_WALL_CYLINDER ? 1 : v->wall_kind == SDMD_WALL_SPHERE ? 0 : 7;
+    if (v->n_obst < 0 || v->n_obst > SDMD_MAX_OBST || v->n_sphobst < 0 || v->n_sphobst > SDMD_MAX_OBST)
+        return set_err(SDMD_ERR_UNSUPPORTED, "more obstruction walls / spherical obstacles than SDMD_MAX_OBST");
+    P.n_obst = v->n_obst;
+    P.n_sphobst = v->n_sphobst;
+    for (int n = 0; n < v->n_obst; n++) {
+        if (v->obst_type[n] < 1 || v->obst_type[n] > SDMD_NATOMTYPE) return set_err(SDMD_ERR_BAD_ARG, "bad obst_type");
+        P.obst_type[n] = v->obst_type[n];
+        for (int k = 0; k < 3; k++) P.obst_pos[n][k] = v->obst_pos[n][k];
+    }
+    for (int n = 0; n < v->n_sphobst; n++) {
+        P.sph_r[n] = v->sphobst_radius[n];
+        for (int k = 0; k < 3; k++) P.sph_pos[n][k] = v->sphobst_pos[n][k];
+    }
+    P.single_body = P.wall_kind != 0 || P.n_obst > 0 || P.n_sphobst > 0;
     P.thermostat_on = v->thermostat_on;
     P.method_ding = v->method_ding;
     P.hydrogen_bond = v->hydrogen_bond;

@@ -75,6 +75,10 @@ struct DevP {
     int wall_kind, wall_type;  // smooth confining wall (enum sdmd_wall_kind), its row of the collision table
     int pbc_mask;              // bit k: dimension k is periodic (Events.c:210-216)
     double wall_pos[3];
+    int n_obst, n_sphobst;     // flat obstruction walls / hard spherical obstacles
+    int single_body;           // any of wall / obstruction / sphere present
+    int obst_type[SDMD_MAX_OBST];
+    double obst_pos[SDMD_MAX_OBST][3], sph_pos[SDMD_MAX_OBST][3], sph_r[SDMD_MAX_OBST];
     double *x, *y, *z, *vx, *vy, *vz;
     const double *mass;
     int *type;

@@ -760,6 +760,63 @@ __device__ inline void d_wall_time(const DevP &D, const Self &me, Slot &cur) {
     d_job_assign(D, cur, 0, t, pot, sub, SDMD_EV_WALL);
 }
 
+// ObstTime, TimePrediction.c:740-829 (obstruction walls without holes): one-dimensional distance from the plane,
+// partner code -dim - 10 n
+__device__ inline void d_obst_time(const DevP &D, const Self &me, Slot &cur) {
+    const double pos[3] = {me.x, me.y, me.z}, spd[3] = {me.vx, me.vy, me.vz};
+    for (int n = 0; n < D.n_obst; n++) {
+#pragma unroll 1
+        for (int dim = 0; dim < 3; dim++) {
+            if (D.obst_pos[n][dim] < 0) continue;
+            Pair p;
+            double r[3], v[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                double pi = (k == dim) ? pos[k] : 0, pj = (k == dim) ? D.obst_pos[n][k] : 0, si = (k == dim) ? spd[k] : 0;
+                r[k] = pi - pj; v[k] = si - 0.0;
+            }
+            p.rx = r[0]; p.ry = r[1]; p.rz = r[2];
+            p.r2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+            p.b = r[0] * v[0] + r[1] * v[1] + r[2] * v[2];
+            p.v2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+            int idx = __ldg(&D.coll_index[me.type * SD_NT + D.obst_type[n]]);
+            if (idx < 0) { D.ctl->error = SDMD_ERR_TABLE; return; }
+            FindRes f = d_find_pair_table(D, &D.tables[idx], FP_COLLISION, p.b, p.r2, 0, 0);
+            if (f.lowPot == 0 && f.upPot == 0) continue;                     // :783-787
+            int s, sub;
+            double d2, pot;
+            if (p.b < 0) {                                                    // approaching :789-798
+                sub = (f.cs == 0) ? SDMD_SUB_CORECOLLI : SDMD_SUB_TBDCAPTR;
+                s = -1; d2 = f.lower; pot = f.lowPot;
+            } else {                                                          // leaving :800-810
+                if (f.cs == 1) continue;
+                sub = SDMD_SUB_TBDESCAP;
+                s = 1; d2 = f.upper; pot = f.upPot;
+            }
+            double t = d_time(p, s, d2);
+            if (t < 0) { D.ctl->error = SDMD_ERR_STATE; return; }             // exit(), :813-816
+            if (d_job_assign(D, cur, 0, t, pot, sub, SDMD_EV_OBST)) cur.partner = -1 * (dim + 1) - 10 * n;
+        }
+    }
+}
+
+// SphObstTime, TimePrediction.c:1020-1071: hard sphere at rest, core collision only, partner code -1000 n
+__device__ inline void d_sphobst_time(const DevP &D, const Self &me, Slot &cur) {
+    for (int n = 0; n < D.n_sphobst; n++) {
+        Pair p;
+        p.rx = me.x - D.sph_pos[n][0]; p.ry = me.y - D.sph_pos[n][1]; p.rz = me.z - D.sph_pos[n][2];
+        double vx = me.vx - 0.0, vy = me.vy - 0.0, vz = me.vz - 0.0;
+        p.r2 = p.rx * p.rx + p.ry * p.ry + p.rz * p.rz;
+        p.b = p.rx * vx + p.ry * vy + p.rz * vz;
+        p.v2 = vx * vx + vy * vy + vz * vz;
+        double short2 = D.sph_r[n] * D.sph_r[n];
+        if (!(p.b < 0 && d_disc(p, short2) > 0)) continue;
+        double t = d_time(p, -1, short2);
+        if (t < 0) { D.ctl->error = SDMD_ERR_STATE; return; }
+        if (d_job_assign(D, cur, 0, t, 0, SDMD_SUB_CORECOLLI, SDMD_EV_SPHO)) cur.partner = -1000 * n;
+    }
+}
+
 __device__ __forceinline__ Self d_load_self(const DevP &D, int i) {
     Self me;
     me.i = i;
@@ -819,7 +876,11 @@ __device__ inline Slot d_predict_atom(const DevP &D, const SlotSrc &S, int i, Sl
         d_hb_time(D, S, me, cur, dup_limit);
         d_hbn_time(D, S, me, cur, dup_limit);
     }
-    if (D.wall_kind) d_wall_time(D, me, cur);
+    if (D.single_body) {   // the single-body predictors come last, SGThread.c:183-207
+        if (D.wall_kind) d_wall_time(D, me, cur);
+        if (D.n_obst) d_obst_time(D, me, cur);
+        if (D.n_sphobst) d_sphobst_time(D, me, cur);
+    }
     *npair = me.npair;
     if (second) *second = cur.m2;
     return cur;
@@ -1091,6 +1152,38 @@ __device__ inline void d_wall_event(const DevP &D, int i) {
     D.vx[i] = tvx + phi * rx; D.vy[i] = tvy + phi * ry; D.vz[i] = tvz + phi * rz;
 }
 
+// ObstEvent, Events.c:543-619 / SphObstEvent, Events.c:752-796: kick along the one-dimensional / radial separation
+__device__ inline void d_obst_event(const DevP &D, int i, bool sph) {
+    const double pos[3] = {D.x[i], D.y[i], D.z[i]}, spd[3] = {D.vx[i], D.vy[i], D.vz[i]};
+    double r[3], v[3];
+    int partner = D.ev_partner[i];
+    if (sph) {
+        int n = partner / -1000;
+        if (n < 0 || n >= D.n_sphobst) { D.ctl->error = SDMD_ERR_STATE; return; }
+        for (int k = 0; k < 3; k++) { r[k] = pos[k] - D.sph_pos[n][k]; v[k] = spd[k] - 0.0; }
+    } else {
+        int n = partner / -10, dim = (partner * -1) % 10 - 1;
+        if (n < 0 || n >= D.n_obst || dim < 0 || dim > 2) { D.ctl->error = SDMD_ERR_STATE; return; }
+        for (int k = 0; k < 3; k++) {
+            double pi = (k == dim) ? pos[k] : 0, pj = (k == dim) ? D.obst_pos[n][k] : 0, si = (k == dim) ? spd[k] : 0;
+            r[k] = pi - pj; v[k] = si - 0.0;
+        }
+    }
+    double d2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    double b = r[0] * v[0] + r[1] * v[1] + r[2] * v[2];
+    double mass = D.mass[i];
+    double pot = D.ev_pot[i];
+    int s_vel = 0;
+    int sub = D.ev_sub[i];
+    if (sub == SDMD_SUB_CORECOLLI) { s_vel = 1; pot = 0; }
+    else if (!sph && sub == SDMD_SUB_TBDCAPTR) { if (b * b - 2 * d2 * pot / mass <= 0) { pot = 0; s_vel = 1; } else s_vel = -1; }
+    else if (!sph && sub == SDMD_SUB_TBDESCAP) { if (b * b - 2 * d2 * pot / mass <= 0) { pot = 0; s_vel = -1; } else s_vel = 1; }
+    else { D.ctl->error = SDMD_ERR_STATE; return; }
+    double phi = (-1 * b + s_vel * sqrt(b * b - 2 * d2 * pot / mass)) / d2;
+    if (phi != phi) { D.ctl->error = SDMD_ERR_STATE; return; }
+    D.vx[i] = spd[0] + phi * r[0]; D.vy[i] = spd[1] + phi * r[1]; D.vz[i] = spd[2] + phi * r[2];
+}
+
 // ThermostatEvent (Andersen), Events.c:396-420; RandomVelocity ToolFunctions.c:600-610
 __device__ inline void d_thermostat_event(const DevP &D, int i) {
     double speed[3];
@@ -1169,6 +1262,8 @@ __device__ inline void d_do_event(const DevP &D, int i, int j) {
         case SDMD_EV_THER: d_thermostat_event(D, i); c->n_ther++; break;
         case SDMD_EV_PCC: d_pcc_event(D, i); c->n_pcc++; break;
         case SDMD_EV_WALL: d_wall_event(D, i); c->n_wall++; break;
+        case SDMD_EV_OBST: d_obst_event(D, i, false); c->n_wall++; break;
+        case SDMD_EV_SPHO: d_obst_event(D, i, true); c->n_wall++; break;
         default: c->error = SDMD_ERR_STATE; break;
     }
 }
@@ -1844,9 +1939,12 @@ __device__ inline void d_predict_cta(const DevP &D, PredShared &sh) {
             } else {
                 d_pc_fold(D, sh, a);
                 if (tid == 0) {
-                    if (D.wall_kind) {   // WallTime comes after every other predictor: one more JobAssign on the folded slot
-                        Slot w = sh.result[a];
-                        d_wall_time(D, d_load_self(D, i), w);
+                    if (D.single_body) {   // wall / obstruction / sphere predictors come after every other one: a few more
+                        Slot w = sh.result[a];   // JobAssigns on the folded slot
+                        Self me = d_load_self(D, i);
+                        if (D.wall_kind) d_wall_time(D, me, w);
+                        if (D.n_obst) d_obst_time(D, me, w);
+                        if (D.n_sphobst) d_sphobst_time(D, me, w);
                         sh.result[a] = w;
                     }
                     d_store_slot(D, i, sh.result[a]);

@@ -141,8 +141,24 @@ int sdmd_glue_flatten(struct sdmd_host_view *v) {
     v->gel_mode = 1;
 #endif
     /* features that live outside the hot-path scope (rough / moving walls, obstacles, tunnels, flow, CG) */
-    if (obstObj.mark || tunlObj.mark || SphObstObj.mark || flow.mark || CG.mark || strcmp(wallDyn.mark, "no")) {
-        return SDMD_ERR_UNSUPPORTED;
+    if (tunlObj.mark || flow.mark || CG.mark || strcmp(wallDyn.mark, "no")) return SDMD_ERR_UNSUPPORTED;
+    /* flat obstruction walls (no tunnel, hence no holes) and hard spherical obstacles */
+    if (obstObj.mark) {
+        if (obstObj.num > SDMD_MAX_OBST) return SDMD_ERR_UNSUPPORTED;
+        v->n_obst = obstObj.num;
+        for (int n = 0; n < obstObj.num; n++) {
+            if (obstObj.hole[n]) return SDMD_ERR_UNSUPPORTED;
+            for (int k = 0; k < 3; k++) v->obst_pos[n][k] = obstObj.position[n][k + 1];
+            v->obst_type[n] = obstObj.obst[n].property->typeofAtom;
+        }
+    }
+    if (SphObstObj.mark) {
+        if (SphObstObj.num > SDMD_MAX_OBST) return SDMD_ERR_UNSUPPORTED;
+        v->n_sphobst = SphObstObj.num;
+        for (int n = 0; n < SphObstObj.num; n++) {
+            for (int k = 0; k < 3; k++) v->sphobst_pos[n][k] = SphObstObj.position[n][k + 1];
+            v->sphobst_radius[n] = SphObstObj.radius[n];
+        }
     }
     /* smooth confining wall: the pseudo-atom ReadWall built (Initialization.c:1907-1935) */
     if (strcmp(wallExist, "no")) {
@@ -303,6 +319,10 @@ void sdmd_snap_put_view(sdmd_snap *s, const struct sdmd_host_view *v) {
     int32_t wall_i[2] = {v->wall_kind, v->wall_type};
     sdmd_snap_put(s, "wall_i4", "i4", wall_i, 2);
     sdmd_snap_put(s, "wall_f8", "f8", v->wall_pos, 3);
+    sdmd_snap_put(s, "obst_pos", "f8", v->obst_pos, 3 * (uint64_t)v->n_obst);
+    sdmd_snap_put(s, "obst_type", "i4", v->obst_type, (uint64_t)v->n_obst);
+    sdmd_snap_put(s, "sphobst_pos", "f8", v->sphobst_pos, 3 * (uint64_t)v->n_sphobst);
+    sdmd_snap_put(s, "sphobst_radius", "f8", v->sphobst_radius, (uint64_t)v->n_sphobst);
 #define PUT(field, dt, cnt) sdmd_snap_put(s, #field, dt, v->field, cnt)
     PUT(x, "f8", n1); PUT(y, "f8", n1); PUT(z, "f8", n1);
     PUT(vx, "f8", n1); PUT(vy, "f8", n1); PUT(vz, "f8", n1);

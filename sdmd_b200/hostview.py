@@ -13,7 +13,8 @@ from pathlib import Path
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
+MAX_OBST = 4
 NT = 33
 NHBCLASS = 12
 MAX_STEPS = 16
@@ -58,6 +59,9 @@ class CHostView(C.Structure):
         ("coll_index", _P(C.c_int32)), ("hb_index", _P(C.c_int32)),
         ("hb_barrier", C.c_double * 3),
         ("wall_kind", C.c_int32), ("wall_type", C.c_int32), ("wall_pos", C.c_double * 3),
+        ("n_obst", C.c_int32), ("n_sphobst", C.c_int32),
+        ("obst_pos", C.c_double * (3 * MAX_OBST)), ("obst_type", C.c_int32 * MAX_OBST),
+        ("sphobst_pos", C.c_double * (3 * MAX_OBST)), ("sphobst_radius", C.c_double * MAX_OBST),
     ]
 
 
@@ -141,6 +145,11 @@ class HostView:
         self.wall_kind = 0          # enum sdmd_wall_kind: 0 none, 1 parallel plates, 2 cylinder, 3 sphere
         self.wall_type = 0
         self.wall_pos = np.zeros(3)
+        # flat obstruction walls (position per dimension, negative = none; atom type) and hard spherical obstacles
+        self.obst_pos = np.zeros((0, 3))
+        self.obst_type = np.zeros(0, dtype=np.int32)
+        self.sphobst_pos = np.zeros((0, 3))
+        self.sphobst_radius = np.zeros(0)
         for name, dt, k in PER_ATOM:
             setattr(self, name, np.zeros(n1 * k, dtype=_NP[dt]))
         for name in ("bond_off", "con_off", "cm_off"):
@@ -167,13 +176,19 @@ class HostView:
         if "wall_i4" in d:          # absent in snapshots written before the wall fields existed = no wall
             hv.wall_kind, hv.wall_type = (int(v) for v in d["wall_i4"][:2])
             hv.wall_pos = np.asarray(d["wall_f8"], dtype=np.float64)[:3].copy()
+        if "obst_pos" in d:
+            hv.obst_pos = np.asarray(d["obst_pos"], dtype=np.float64).reshape(-1, 3).copy()
+            hv.obst_type = np.asarray(d["obst_type"], dtype=np.int32).copy()
+            hv.sphobst_pos = np.asarray(d["sphobst_pos"], dtype=np.float64).reshape(-1, 3).copy()
+            hv.sphobst_radius = np.asarray(d["sphobst_radius"], dtype=np.float64).copy()
         for name, dt, _ in PER_ATOM:
             setattr(hv, name, np.ascontiguousarray(d[name], dtype=_NP[dt]).copy())
         for name, dt in OTHER:
             arr = np.ascontiguousarray(d[name], dtype=_NP[dt]).copy()
             setattr(hv, name, arr if arr.size else np.zeros(1, dtype=_NP[dt]))
         hv.tables = np.frombuffer(d["tables"].tobytes(), dtype=STEP_TABLE_DTYPE).copy()
-        known = {n for n, _, _ in PER_ATOM} | {n for n, _ in OTHER} | {"scalars_i4", "scalars_f8", "scalars_i8", "tables", "wall_i4", "wall_f8"}
+        known = {n for n, _, _ in PER_ATOM} | {n for n, _ in OTHER} | {"scalars_i4", "scalars_f8", "scalars_i8", "tables", "wall_i4", "wall_f8",
+                                                                           "obst_pos", "obst_type", "sphobst_pos", "sphobst_radius"}
         hv.extra = {k: v for k, v in d.items() if k not in known}
         return hv
 
@@ -194,6 +209,10 @@ class HostView:
             "scalars_i8": np.array([self.frame], dtype=np.int64),
             "wall_i4": np.array([self.wall_kind, self.wall_type], dtype=np.int32),
             "wall_f8": np.array(self.wall_pos, dtype=np.float64),
+            "obst_pos": np.asarray(self.obst_pos, dtype=np.float64).reshape(-1),
+            "obst_type": np.asarray(self.obst_type, dtype=np.int32),
+            "sphobst_pos": np.asarray(self.sphobst_pos, dtype=np.float64).reshape(-1),
+            "sphobst_radius": np.asarray(self.sphobst_radius, dtype=np.float64),
             "tables": np.frombuffer(self.tables.tobytes(), dtype=np.uint8),
         }
         for name, _, _ in PER_ATOM:
@@ -226,6 +245,16 @@ class HostView:
         c.hb_barrier[:] = [float(v) for v in self.hb_barrier]
         c.wall_kind, c.wall_type = int(self.wall_kind), int(self.wall_type)
         c.wall_pos[:] = [float(v) for v in self.wall_pos]
+        c.n_obst, c.n_sphobst = len(self.obst_type), len(self.sphobst_radius)
+        assert c.n_obst <= MAX_OBST and c.n_sphobst <= MAX_OBST
+        for k, v in enumerate(np.asarray(self.obst_pos, dtype=np.float64).reshape(-1)):
+            c.obst_pos[k] = float(v)
+        for k, v in enumerate(self.obst_type):
+            c.obst_type[k] = int(v)
+        for k, v in enumerate(np.asarray(self.sphobst_pos, dtype=np.float64).reshape(-1)):
+            c.sphobst_pos[k] = float(v)
+        for k, v in enumerate(self.sphobst_radius):
+            c.sphobst_radius[k] = float(v)
         for name, dt, _ in PER_ATOM:
             arr = getattr(self, name)
             assert arr.flags["C_CONTIGUOUS"] and arr.dtype == _NP[dt], name

@@ -37,6 +37,22 @@ def remd_args(port, T, num, rate, rid):
     return ["-REMD", "localhost", str(port), "%lf" % T, str(num), str(int(rate)), str(rid)]
 
 
+def _wait_connected(proc, port, timeout=180.0):
+    import psutil
+    t0 = time.time()
+    while time.time() - t0 < timeout:
+        if proc.poll() is not None:
+            return
+        try:
+            for c in psutil.Process(proc.pid).net_connections(kind="tcp"):
+                if c.status == psutil.CONN_ESTABLISHED and c.raddr and c.raddr.port == port:
+                    return
+        except (psutil.Error, OSError):
+            pass
+        time.sleep(0.02)
+    raise AssertionError("replica did not connect to the exchange server")
+
+
 def run_reference_remd(work: Path, nrep: int, rate: float, time_units: float, server_seed: int, binary=None):
     """Returns the text of out_REMD<id>.txt per replica (SaveRE, DataSave.c:687-700)."""
     port = free_port()
@@ -50,7 +66,10 @@ def run_reference_remd(work: Path, nrep: int, rate: float, time_units: float, se
         T = reduced_temperature(TEMPS_K[r])
         procs.append(subprocess.Popen([str(binary or REF / "sDMD_ref"), "-i", str(inp), "-f", "ala10.gro", "-o", str(d / "out"),
                                        *remd_args(port, T, r + 1, rate, r)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
-        time.sleep(1.0)   # sREMD staggers the replicas the same way (REMDExec.c:133): connection order = replica id
+        # sREMD staggers the replicas by sleep(1 + id) (REMDExec.c:133) so that they connect — lazily, at their first
+        # exchange (REMD.c:150-153) — in replica-id order, which is the order the server sweeps them in.  A fixed sleep is
+        # a race on a busy or cold machine (start-up, CUDA initialisation), so wait for this replica's connection itself.
+        _wait_connected(procs[-1], port)
     for p in procs:
         p.wait(timeout=600)
     try:
