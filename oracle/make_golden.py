@@ -10,6 +10,9 @@ reference's own inputs and stores what the reference computed as compressed .npz
   gel10        GEL step-potential spheres, 10^3 simple-cubic lattice at 8 A (reference CreateGELCoordinate
                layout, ToolFunctions.c:775-798), 3000 iterations
 
+  abeta8       8 x Abeta16-22 (KLVFFAE, synthesised all-atom coordinates) on a 2x2x2 grid, snapshot after 150000
+               iterations, then 8000 traced (BASELINE config 3 in small)
+
   ala10x8_wallp  8 ala10 chains between two smooth parallel plates (WallExist smooth / WallType parallel, plates normal
                to y, 38 A apart; Wall.txt atom type CA because the shipped PHO is only valid in CG mode): WallTime /
                WallEvent, PBC in x and z only
@@ -49,6 +52,14 @@ CASES = {
     "ala10x8_wallp": ("ref_harness", "ala10x8w.gro", 8000, 40000, [], -8),
     "ala10x4_wallc": ("ref_harness", "ala10x4c.gro", 8000, 40000, ["--warm", "20000"], -8),
     "ala10x8_obst": ("ref_harness", "ala10x8o.gro", 8000, 40000, ["--warm", "20000"], -8),
+    # BASELINE config 3 in small: 8 x Abeta16-22 (KLVFFAE; coordinates synthesised by oracle/make_peptide_gro.py, committed as
+    # tests/golden/abeta16_22.gro): charged / aromatic / branched side chains, side-chain hydrogen bonds, CONSTRn tables
+    "abeta8": ("ref_harness", "abeta8.gro", 8000, 40000, ["--warm", "150000"], -8),
+}
+# name: (single-chain .gro under tests/golden, chains per axis, spacing nm, box nm); abeta64 = SURVEY 8d C3 (live tests only)
+PEPTIDES = {
+    "abeta8": ("abeta16_22.gro", (2, 2, 2), 2.0, (6.0, 6.0, 6.0)),
+    "abeta64": ("abeta16_22.gro", (4, 4, 4), 2.5, (10.0, 10.0, 10.0)),
 }
 # name: (WallType, chains per axis, spacing nm, box nm[, "Obstruct?" value, "SphObst?" value])
 WALLS = {
@@ -136,6 +147,9 @@ def run_case(name: str, work: Path, harness=None, coord=None, max_iter=None, n_g
                         sphobst=wall[5] if wall and len(wall) > 5 else None)
     if wall:
         write_multi_ala10(inp / coord, inp / "ala10.gro", copies_per_axis=wall[1], spacing_nm=wall[2], box_nm=wall[3])
+    elif name in PEPTIDES:
+        src, copies, spacing, box = PEPTIDES[name]
+        write_multi_ala10(inp / coord, ROOT / "tests" / "golden" / src, copies_per_axis=copies, spacing_nm=spacing, box_nm=box)
     elif gel_n and gel_n > 0:
         write_gel_gro(inp / coord, gel_n, gel_a_nm)
     elif gel_n and gel_n == -80:

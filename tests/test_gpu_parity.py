@@ -50,7 +50,7 @@ def test_predict_all_and_cbt_match_reference(capi, case):
     assert r.kinetic_energy() == post.extra["ekin"][0]
 
 
-@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8", "ala10x8_wallp", "ala10x4_wallc", "ala10x8_obst"])
+@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8", "ala10x8_wallp", "ala10x4_wallc", "ala10x8_obst", "abeta8"])
 @pytest.mark.parametrize("loop_mode", [0, 2, 3], ids=["one_cta", "sweep_overlapped", "sweep_serial"])
 def test_device_event_loop_matches_reference(capi, case, loop_mode):
     """loop_mode 2 / 3 force the large-system drivers (grid-wide sweep overlapped with / followed by one event block per
@@ -441,6 +441,38 @@ def test_multichain_protein_past_one_cta_limit_live(capi):
         assert_fields_equal(hv, fin, STATE_FIELDS, what="final state: ")
         assert np.array_equal(r.celllist(), fin.extra["celllist"])
         assert np.array_equal(r.cbt()[0][1:], fin.extra["cbt_node"][1:])
+        assert r.potential_energy() == fin.extra["epot"][0]
+        r.close()
+
+
+def test_abeta64_box_live(capi):
+    """BASELINE config 3 generated on the spot by the UNMODIFIED reference: 64 x Abeta16-22 (KLVFFAE, 16 atom
+    types, CONSTRn tables, charged and aromatic side chains) on a 4x4x4 grid in a 100 A box, N = 4608.  Cell list,
+    Predict(all) slots, CBT, energies and a 20 000-iteration trace bit for bit, on both large-system loop drivers."""
+    from oracle.make_golden import REFDIR as ref_dir
+    if not (ref_dir / "ref_harness").exists():
+        pytest.skip("oracle/_ref/ref_harness not built")
+    n_it = 20000
+    pre, post, fin = _live_case("abeta64", harness="ref_harness", coord="abeta64.gro", max_iter=n_it, n_gauss=120000, extra=[], gel_n=-8)
+    assert pre.natom == 64 * 72
+    want = ref_trace(fin)
+    assert len(want) == n_it
+    for mode in (0, 3):
+        hv, r = _replica(capi, pre)
+        r.set_loop_mode(mode)
+        r.pbc_full(); r.cell_build()
+        assert np.array_equal(r.celllist(), pre.extra["celllist"])
+        r.predict_all(); r.cbt_build()
+        r.download(hv)
+        assert_fields_equal(hv, post, SLOT_FIELDS, what="after Predict(all): ")
+        assert np.array_equal(r.cbt()[0][1:], post.extra["cbt_node"][1:])
+        assert r.potential_energy() == post.extra["epot"][0]
+        st, tr = r.run(max_iter=n_it, trace_cap=n_it)
+        assert st["error"] == 0 and st["iterations"] == n_it
+        assert_trace_equal(tr, want)
+        r.download(hv)
+        assert_fields_equal(hv, fin, STATE_FIELDS, what="final state: ")
+        assert np.array_equal(r.celllist(), fin.extra["celllist"])
         assert r.potential_energy() == fin.extra["epot"][0]
         r.close()
 

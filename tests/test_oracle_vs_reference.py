@@ -47,7 +47,7 @@ def test_predict_all_and_cbt(case):
     assert o.kinetic_energy() == post.extra["ekin"][0]
 
 
-@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8", "ala10x8_wallp", "ala10x4_wallc", "ala10x8_obst"])
+@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8", "ala10x8_wallp", "ala10x4_wallc", "ala10x8_obst", "abeta8"])
 def test_event_loop_trace(case):
     pre, post, fin = load_case(case)
     hv, o = _prepare(pre)
@@ -111,6 +111,32 @@ def test_multichain_protein_against_live_reference(tmp_path):
                      extra=[], gel_n=-80)
     pre, post, fin = (HostView.from_snapshot(p) for p in snaps)
     assert pre.natom == 4720
+    hv, o = _prepare(pre)
+    o.pbc_full(); o.cell_build()
+    assert np.array_equal(o.celllist(), pre.extra["celllist"])
+    o.predict_all()
+    assert_fields_equal(hv, post, SLOT_FIELDS, what="after Predict(all): ")
+    o.cbt_build()
+    want = ref_trace(fin)
+    st, tr = o.run(max_iter=len(want), trace_cap=len(want))
+    assert_trace_equal(tr, want)
+    assert_fields_equal(hv, fin, STATE_FIELDS)
+    assert o.potential_energy() == fin.extra["epot"][0]
+
+
+@pytest.mark.refbin
+def test_abeta64_box_against_live_reference(tmp_path):
+    """BASELINE config 3: 64 x Abeta16-22 on a 4x4x4 grid, 25 A spacing, 100 A box (N = 4608; the chain's
+    coordinates are the committed tests/golden/abeta16_22.gro), run by the reference binary here: link list, Predict(all),
+    20 000 iterations."""
+    if not (REFDIR / "ref_harness").exists():
+        pytest.skip("oracle/_ref/ref_harness not built (needs /root/reference at build time)")
+    from oracle.make_golden import run_case
+    from sdmd_b200.hostview import HostView
+    snaps = run_case("abeta64", tmp_path, harness="ref_harness", coord="abeta64.gro", max_iter=20000, n_gauss=120000,
+                     extra=[], gel_n=-8)
+    pre, post, fin = (HostView.from_snapshot(p) for p in snaps)
+    assert pre.natom == 64 * 72 and len(set(pre.type[1:].tolist())) >= 14
     hv, o = _prepare(pre)
     o.pbc_full(); o.cell_build()
     assert np.array_equal(o.celllist(), pre.extra["celllist"])
