@@ -298,7 +298,7 @@ __global__ void k_cell_permute(DevP D, const int *sorted_atom, SRec *srec, float
     if (p >= D.n) return;
     int j = sorted_atom[p];
     double2 *rp = reinterpret_cast<double2 *>(&srec[p]);
-    if ((parts & 4) && p == 0) D.ctl->cc_epoch++;   // new link list: cached candidate lists are void
+    if ((parts & 4) && p == 0) D.ctl->cc_floor = ++D.ctl->cc_epoch;   // new link list: every cached candidate list is void
     if (parts & 1) {
         D.spos[j] = p;
         double x = D.x[j], y = D.y[j], z = D.z[j];
@@ -600,6 +600,33 @@ __global__ void __launch_bounds__(256) k_advance(DevP D, double dt_arg, int use_
 // ===================================================================================================
 // loop head: stop conditions + AssignJob (SGThread.c:75,237-259); single thread
 // Small systems: the whole loop in ONE persistent CTA (one replica per CTA); no host round trip per event.
+// UpdateData + TimeForward (ToolFunctions.c:23-36) by one thread block.  All loads of up to four atoms per thread are issued
+// before the first store: written as `x[i] = x[i] + vx[i] * dt` per component the compiler must keep every load behind the
+// previous store (the arrays may alias), which made each atom four dependent L2 round trips — 4.6 us per 1000 atoms.
+__device__ __forceinline__ void d_advance_cta(const DevP &D, double dt) {
+    const int n = D.n, nt = blockDim.x;
+    double *x = D.x, *y = D.y, *z = D.z, *t = D.ev_time;
+    const double *vx = D.vx, *vy = D.vy, *vz = D.vz;
+    int i = threadIdx.x + 1;
+    for (; i + 3 * nt <= n; i += 4 * nt) {
+        double xa[4], ya[4], za[4], ua[4], va[4], wa[4], ta[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int k = i + u * nt;
+            xa[u] = x[k]; ya[u] = y[k]; za[u] = z[k]; ua[u] = vx[k]; va[u] = vy[k]; wa[u] = vz[k]; ta[u] = t[k];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int k = i + u * nt;
+            x[k] = xa[u] + ua[u] * dt; y[k] = ya[u] + va[u] * dt; z[k] = za[u] + wa[u] * dt; t[k] = ta[u] - dt;
+        }
+    }
+    for (; i <= n; i += nt) {
+        const double x0 = x[i], y0 = y[i], z0 = z[i], u0 = vx[i], v0 = vy[i], w0 = vz[i], t0 = t[i];
+        x[i] = x0 + u0 * dt; y[i] = y0 + v0 * dt; z[i] = z0 + w0 * dt; t[i] = t0 - dt;
+    }
+}
+
 __global__ void __launch_bounds__(256, 1) k_run_cta(DevP Dg, double t_until, i64 iter_limit, sdmd_trace_rec *trace, i64 trace_cap) {
     __shared__ PredShared sh;
     __shared__ Ctl s_ctl;      // the loop state lives in shared memory while the kernel runs (written back on exit)
@@ -621,12 +648,7 @@ __global__ void __launch_bounds__(256, 1) k_run_cta(DevP Dg, double t_until, i64
         if (s_stop) break;
         long long h1 = d_clock_after(&s_stop);
         double dt = s_dt;
-        for (int i = threadIdx.x + 1; i <= D.n; i += blockDim.x) {
-            D.x[i] = D.x[i] + D.vx[i] * dt;
-            D.y[i] = D.y[i] + D.vy[i] * dt;
-            D.z[i] = D.z[i] + D.vz[i] * dt;
-            D.ev_time[i] = D.ev_time[i] - dt;
-        }
+        d_advance_cta(D, dt);
         __syncthreads();
         if (threadIdx.x == 0) { D.ctl->phase_cycles[0] += h1 - h0; D.ctl->phase_cycles[1] += d_clock_after(&s_stop) - h1; }
         d_loop_body_cta(D, sh, t_until, trace, trace_cap);
@@ -673,12 +695,7 @@ __global__ void __launch_bounds__(NT, MINB) k_run_cta_multi(const MultiArg *args
         __syncthreads();
         if (s_stop) break;
         double dt = s_dt;
-        for (int i = threadIdx.x + 1; i <= D.n; i += blockDim.x) {
-            D.x[i] = D.x[i] + D.vx[i] * dt;
-            D.y[i] = D.y[i] + D.vy[i] * dt;
-            D.z[i] = D.z[i] + D.vz[i] * dt;
-            D.ev_time[i] = D.ev_time[i] - dt;
-        }
+        d_advance_cta(D, dt);
         __syncthreads();
         d_loop_body_cta(D, sh, t_until, nullptr, 0);
     }
@@ -1002,7 +1019,10 @@ int sdmd_cuda_device_count(void) {
 }
 
 static inline int grid_for(int n, int block) { return (n + block - 1) / block; }
-#define SDMD_SMALL_N 4096   /* up to here the whole event loop runs in one persistent CTA */
+/* Up to here the whole event loop runs in one persistent CTA.  Its block-wide advance costs ~1.1 us per 1000 atoms (one
+ * SM's L2 bandwidth, ~80 GB/s), the sweep driver a flat ~21 us per iteration (GEL) to ~31 us (proteins): measured
+ * crossover ~7000 atoms for GEL boxes, later for proteins (profiles/r1_loop_crossover.txt). */
+#define SDMD_SMALL_N 8192
 
 // leaf permutation of CreateCBT's sequential InsertCBTRun (CBT.c:86-105): time independent
 static void cbt_leaf_permutation(int n, std::vector<int> &leaf_atom) {
@@ -1159,6 +1179,7 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     {
         size_t rows = P.cc_per_atom ? n1 : 2;
         TRY(dalloc(c, &P.cc_stamp, n1)); TRY(dalloc(c, &P.cc_n, n1));
+        TRY(dalloc(c, &P.cell_epoch, (size_t)P.ncell));
         TRY(dalloc(c, &P.cc_j, (size_t)P.cc_cap * rows)); TRY(dalloc(c, &P.cc_k, (size_t)P.cc_cap * rows));
         TRY(dalloc(c, &P.cc_pass, (size_t)P.cc_cap * rows));
         TRY(dalloc(c, &P.cc_passidx, 32 * rows)); TRY(dalloc(c, &P.cc_npass, rows));
@@ -1226,6 +1247,7 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     c->h_ctl->temperature = v->target_temperature;
     c->h_ctl->frame = v->frame;
     c->h_ctl->cc_epoch = 1;
+    c->h_ctl->cc_floor = 1;
     CK(cudaMemcpyAsync(c->d_ctl, c->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream));
     P.ctl = c->d_ctl;
     CK(cudaStreamSynchronize(c->stream));
@@ -1310,7 +1332,6 @@ int sdmd_cuda_host_unregister(void *ptr) {
 }
 int sdmd_cuda_set_loop_mode(sdmd_ctx *c, int mode) {
     if (mode != SDMD_LOOP_AUTO && mode != SDMD_LOOP_ONE_CTA && mode != SDMD_LOOP_SWEEP && mode != SDMD_LOOP_SWEEP_SERIAL) return set_err(SDMD_ERR_BAD_ARG, "loop mode");
-    if (mode == SDMD_LOOP_ONE_CTA && c->n > SDMD_SMALL_N) return set_err(SDMD_ERR_UNSUPPORTED, "one-CTA loop: system too large");
     c->loop_mode = mode;
     return 0;
 }
@@ -1331,7 +1352,7 @@ static int push_ctl(sdmd_ctx *c) {
     return 0;
 }
 // invalidate every cached candidate list (link list rebuilt / replaced from the host)
-__global__ void k_bump_epoch(Ctl *ctl) { ctl->cc_epoch++; }
+__global__ void k_bump_epoch(Ctl *ctl) { ctl->cc_floor = ++ctl->cc_epoch; }
 static int bump_epoch(sdmd_ctx *c) {   // on the device, in stream order: no host round trip
     k_bump_epoch<<<1, 1, 0, c->stream>>>(c->d_ctl);
     CK(cudaGetLastError());

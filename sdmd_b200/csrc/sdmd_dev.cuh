@@ -31,8 +31,12 @@ struct Ctl {
     int hbnumformed;
     int changed;               // predict_all fix-point flag
     i64 trace_pos;
-    int cc_epoch;              // candidate-list cache epoch: bumped whenever the link list or HB state changes
+    int pad_cc_;
     int live;                  // overlapped sweep: which of the two coordinate/time buffers holds the current state
+    // candidate-list cache: cc_epoch is a tick bumped by every change of the link list or of the HB state; the change stamps
+    // the cells it touched with the new tick (DevP::cell_epoch).  A cached list is valid while its stamp is at least
+    // cc_floor (last wholesale invalidation: new link list) and no cell of its 27-cell neighbourhood carries a later tick.
+    i64 cc_epoch, cc_floor;
     i64 phase_cycles[12];      // clock64() per loop phase (thread 0): head, advance, event, gather, eval, fold, cbt
     // overlapped sweep: AssignJob result per launch parity.  The event block of launch n publishes the job of launch
     // n+1 in the other slot while sweep blocks of launch n may still be reading theirs.
@@ -102,8 +106,10 @@ struct DevP {
     const int *cm_off, *cm_j, *cm_flags;
     const int *cm_table;   // constraint table of a CONSTRAINT_CONNECT entry (resolved from the constr list at create)
     int *cell_cnt;         // atoms per cell, kept in step with the link list
-    // per-atom cache of the 27-cell candidate list (scan order), valid while cc_stamp[i] == ctl->cc_epoch
-    int *cc_stamp, *cc_n, *cc_j;
+    // per-atom cache of the 27-cell candidate list (scan order); validity: see Ctl::cc_epoch
+    i64 *cc_stamp;
+    i64 *cell_epoch;       // per cell: tick of the last change of its membership or of an HB attribute of one of its atoms
+    int *cc_n, *cc_j;
     unsigned char *cc_k, *cc_pass;
     int cc_cap;            // entries per row
     unsigned short *cc_passidx;   // positions (within the row) of entries that pass the free-HB filters, 32 per row

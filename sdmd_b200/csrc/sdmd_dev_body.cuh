@@ -1099,6 +1099,13 @@ __device__ inline void d_list_refresh(const DevP &D, int a, int target) {
 }
 
 // HBEvent, Events.c:275-393
+// HB form / break changes what cached candidate lists recorded about atoms i and j (type, bonded state): every list that
+// can contain them lies within one cell of theirs
+__device__ __forceinline__ void d_touch_cells(const DevP &D, int i, int j) {
+    i64 t = ++D.ctl->cc_epoch;
+    D.cell_epoch[(D.cell_idx[3 * i + 2] * D.cellnum[1] + D.cell_idx[3 * i + 1]) * D.cellnum[0] + D.cell_idx[3 * i]] = t;
+    D.cell_epoch[(D.cell_idx[3 * j + 2] * D.cellnum[1] + D.cell_idx[3 * j + 1]) * D.cellnum[0] + D.cell_idx[3 * j]] = t;
+}
 __device__ inline void d_hb_event(const DevP &D, int i, int j, int ni, int nj) {
     if (D.hb_itype[i] == SDMD_HB_FORM) {
         D.hb_bond[i] = j; D.hb_bond[j] = i;
@@ -1110,7 +1117,7 @@ __device__ inline void d_hb_event(const DevP &D, int i, int j, int ni, int nj) {
         t = ++D.hbn_status[ni]; D.hbn_partner[5 * ni + t] = j;
         t = ++D.hbn_status[nj]; D.hbn_partner[5 * nj + t] = i;
         D.ctl->hbnumformed++;
-        D.ctl->cc_epoch++;
+        d_touch_cells(D, i, j);
     } else if (D.hb_itype[i] == SDMD_HB_BREAK) {
         D.hb_bond[i] = 0; D.hb_bond[j] = 0;
         D.type[i] = d_type_change(D.type[i], 0);
@@ -1120,7 +1127,7 @@ __device__ inline void d_hb_event(const DevP &D, int i, int j, int ni, int nj) {
         --D.hbn_status[ni]; d_list_refresh(D, ni, j);
         --D.hbn_status[nj]; d_list_refresh(D, nj, i);
         D.ctl->hbnumformed--;
-        D.ctl->cc_epoch++;
+        d_touch_cells(D, i, j);
     }
 }
 
@@ -1242,7 +1249,9 @@ __device__ inline void d_pcc_event(const DevP &D, int i) {
     cl[next] = i;
     D.cell_cnt[oldCell]--;
     D.cell_cnt[newCell]++;
-    D.ctl->cc_epoch++;
+    i64 t = ++D.ctl->cc_epoch;   // only lists that look into one of the two cells are stale
+    D.cell_epoch[oldCell] = t;
+    D.cell_epoch[newCell] = t;
 }
 
 // DoEvent, Events.c:25-114
@@ -1421,9 +1430,9 @@ __device__ inline void d_pc_gather_warp(const DevP &D, PredShared &sh, int a) {
     int base = a * PC_MAXC;
     int cx = D.cell_idx[3 * i], cy = D.cell_idx[3 * i + 1], cz = D.cell_idx[3 * i + 2];
     int cap = D.cc_cap;
-    int epoch = D.ctl->cc_epoch;
+    i64 epoch = D.ctl->cc_epoch;
     int row = D.cc_per_atom ? i : a;
-    bool hit = D.cc_per_atom && D.cc_stamp[i] == epoch;
+    i64 stamp = D.cc_per_atom ? D.cc_stamp[i] : -1;
     int role = 0, bonded = 0, itype = 0, nhbne = 0;
     if (D.hydrogen_bond) {
         role = D.hb_role[i];
@@ -1440,6 +1449,9 @@ __device__ inline void d_pc_gather_warp(const DevP &D, PredShared &sh, int a) {
         sh.shift[a][lane][1] = d_shift1(cy, ncy, D.cellnum[1], D.box[1]);
         sh.shift[a][lane][2] = d_shift1(cz, ncz, D.cellnum[2], D.box[2]);
     }
+    // valid while nothing in the 27-cell neighbourhood changed after the list was cached (and no new link list since)
+    bool fresh = lane >= 27 || D.cell_epoch[cell] <= stamp;
+    bool hit = stamp >= D.ctl->cc_floor && __all_sync(0xffffffffu, fresh);
     int ncoll;
     if (hit) {
         ncoll = D.cc_n[i];

@@ -413,9 +413,9 @@ def _live_case(name, **kw):
 
 def test_multichain_protein_past_one_cta_limit_live(capi):
     """SURVEY C3-like case generated on the spot by the UNMODIFIED reference (oracle/_ref/ref_harness travels with the
-    repository): 80 ala10 chains, N = 4720 > 4096, so the default loop driver is the overlapped sweep + event block —
-    with bonds, several proteins, HB candidates.  Cell list, Predict(all) slots, CBT, energies and a 20 000-iteration
-    trace must equal the reference bit for bit; the other sweep driver must give the same trace."""
+    repository): 80 ala10 chains, N = 4720, with bonds, several proteins, HB candidates.  Cell list, Predict(all) slots,
+    CBT, energies and a 20 000-iteration trace must equal the reference bit for bit on the default driver (one persistent
+    thread block up to 8192 atoms) and on both large-system sweep drivers."""
     from oracle.make_golden import REFDIR as ref_dir
     if not (ref_dir / "ref_harness").exists():
         pytest.skip("oracle/_ref/ref_harness not built")
@@ -424,7 +424,7 @@ def test_multichain_protein_past_one_cta_limit_live(capi):
     assert pre.natom == 4720
     want = ref_trace(fin)
     assert len(want) == n_it
-    for mode in (0, 3):
+    for mode in (0, 2, 3):
         hv, r = _replica(capi, pre)
         r.set_loop_mode(mode)
         r.pbc_full(); r.cell_build()
@@ -448,7 +448,7 @@ def test_multichain_protein_past_one_cta_limit_live(capi):
 def test_abeta64_box_live(capi):
     """BASELINE config 3 generated on the spot by the UNMODIFIED reference: 64 x Abeta16-22 (KLVFFAE, 16 atom
     types, CONSTRn tables, charged and aromatic side chains) on a 4x4x4 grid in a 100 A box, N = 4608.  Cell list,
-    Predict(all) slots, CBT, energies and a 20 000-iteration trace bit for bit, on both large-system loop drivers."""
+    Predict(all) slots, CBT, energies and a 20 000-iteration trace bit for bit, on all three loop drivers."""
     from oracle.make_golden import REFDIR as ref_dir
     if not (ref_dir / "ref_harness").exists():
         pytest.skip("oracle/_ref/ref_harness not built")
@@ -457,7 +457,7 @@ def test_abeta64_box_live(capi):
     assert pre.natom == 64 * 72
     want = ref_trace(fin)
     assert len(want) == n_it
-    for mode in (0, 3):
+    for mode in (0, 2, 3):
         hv, r = _replica(capi, pre)
         r.set_loop_mode(mode)
         r.pbc_full(); r.cell_build()
