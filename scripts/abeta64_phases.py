@@ -11,7 +11,7 @@ work = Path(tempfile.mkdtemp(prefix="s", dir="/tmp"))
 snaps = run_case("abeta64", work, harness="ref_harness", coord="abeta64.gro", max_iter=10, n_gauss=400000, extra=[], gel_n=-8)
 pre = HostView.from_snapshot(snaps[0])
 shutil.rmtree(work, ignore_errors=True)
-for mode in (1, 2):
+for mode in (1, 4, 2):
     r = capi.Replica(pre.copy(), device=0)
     r.set_loop_mode(mode)
     r.rng_feed(pre.extra["gauss"])

@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include <dlfcn.h>
+#include <cooperative_groups.h>
 #include "sdmd_dev.cuh"
 
 // ===================================================================================================
@@ -59,6 +60,7 @@ struct sdmd_ctx {
     unsigned long long *d_sum = nullptr;
     bool cells_fresh = false;
     int loop_mode = SDMD_LOOP_AUTO;
+    int cluster_size = 16;     // blocks per cluster of the mid-size loop (16 = B200's non-portable maximum; 8 measured slower above 8000 atoms)
     double *x2 = nullptr, *y2 = nullptr, *z2 = nullptr, *t2 = nullptr;   // second coordinate/time buffer of the overlapped sweep
     bool counters_known = false;         // h_ctl's g_pos / pair_predictions match the device (nothing consumed since the last pull)
     int timing = 1;                      // 0 off, 1 per stage, 2 also the sub-stages of predict_all's fix-up
@@ -664,6 +666,76 @@ struct MultiArg {
     double t_until;
     i64 iter_limit;
 };
+// The same loop for mid-size systems (about 10^3 .. 10^4 atoms) on one thread-block CLUSTER: block 0 is the event block of
+// k_run_cta, the other blocks of the cluster only help with UpdateData/TimeForward, whose cost in one block is one SM's L2
+// bandwidth (~1.1 us per 1000 atoms).  Two cluster barriers per iteration (~380 cycles each, release/acquire at cluster scope,
+// which also drops the L1 lines the other SMs have overwritten): after AssignJob has published dt in block 0's shared memory
+// (read by the helpers through distributed shared memory), and after the advance.
+__global__ void __launch_bounds__(256, 1) k_run_cluster(DevP Dg, double t_until, i64 iter_limit, sdmd_trace_rec *trace, i64 trace_cap) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank(), nblk = cluster.num_blocks();
+    __shared__ PredShared sh;
+    __shared__ Ctl s_ctl;
+    __shared__ double s_dt;
+    __shared__ int s_stop;
+    if (rank == 0)
+        for (int k = threadIdx.x; k < (int)(sizeof(Ctl) / sizeof(int)); k += blockDim.x) ((int *)&s_ctl)[k] = ((const int *)Dg.ctl)[k];
+    __syncthreads();
+    DevP D = Dg;
+    D.ctl = &s_ctl;
+    const double *r_dt = cluster.map_shared_rank(&s_dt, 0);
+    const int *r_stop = cluster.map_shared_rank(&s_stop, 0);
+    for (;;) {
+        long long h0 = clock64();
+        if (rank == 0 && threadIdx.x == 0) {
+            d_loop_head(D, t_until, iter_limit);
+            s_dt = D.ctl->dt;
+            s_stop = D.ctl->stop;
+            if (!s_stop) d_publish_job(D, sh);
+        }
+        cluster.sync();
+        long long h1 = clock64();
+        const int stop = *r_stop;
+        const double dt = *r_dt;
+        if (stop) break;
+        {
+            // this block's share of the atoms, loads of four atoms per thread before the first store (see d_advance_cta)
+            const int n = D.n, nt = (int)(blockDim.x * nblk);
+            double *x = D.x, *y = D.y, *z = D.z, *t = D.ev_time;
+            const double *vx = D.vx, *vy = D.vy, *vz = D.vz;
+            int i = (int)(rank * blockDim.x + threadIdx.x) + 1;
+            for (; i + 3 * nt <= n; i += 4 * nt) {
+                double xa[4], ya[4], za[4], ua[4], va[4], wa[4], ta[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int k = i + u * nt;
+                    xa[u] = x[k]; ya[u] = y[k]; za[u] = z[k]; ua[u] = vx[k]; va[u] = vy[k]; wa[u] = vz[k]; ta[u] = t[k];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int k = i + u * nt;
+                    x[k] = xa[u] + ua[u] * dt; y[k] = ya[u] + va[u] * dt; z[k] = za[u] + wa[u] * dt; t[k] = ta[u] - dt;
+                }
+            }
+            for (; i <= n; i += nt) {
+                const double x0 = x[i], y0 = y[i], z0 = z[i], u0 = vx[i], v0 = vy[i], w0 = vz[i], t0 = t[i];
+                x[i] = x0 + u0 * dt; y[i] = y0 + v0 * dt; z[i] = z0 + w0 * dt; t[i] = t0 - dt;
+            }
+        }
+        cluster.sync();
+        if (rank == 0) {
+            if (threadIdx.x == 0) { D.ctl->phase_cycles[0] += h1 - h0; D.ctl->phase_cycles[1] += clock64() - h1; }
+            d_loop_body_cta(D, sh, t_until, trace, trace_cap);
+        }
+    }
+    cluster.sync();   // block 0's shared memory stays alive until every helper has read the stop flag
+    if (rank == 0) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < (int)(sizeof(Ctl) / sizeof(int)); k += blockDim.x) ((int *)Dg.ctl)[k] = ((const int *)&s_ctl)[k];
+    }
+}
+
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_run_cta_multi(const MultiArg *args) {
     __shared__ PredShared sh;
@@ -1019,10 +1091,14 @@ int sdmd_cuda_device_count(void) {
 }
 
 static inline int grid_for(int n, int block) { return (n + block - 1) / block; }
-/* Up to here the whole event loop runs in one persistent CTA.  Its block-wide advance costs ~1.1 us per 1000 atoms (one
- * SM's L2 bandwidth, ~80 GB/s), the sweep driver a flat ~21 us per iteration (GEL) to ~31 us (proteins): measured
- * crossover ~7000 atoms for GEL boxes, later for proteins (profiles/r1_loop_crossover.txt). */
-#define SDMD_SMALL_N 8192
+/* Loop drivers by system size (profiles/r1_loop_crossover.txt, GEL boxes; us per loop iteration on a B200):
+ *   one block        9.5 @ 512, 12.7 @ 1728, 18 @ 4096: its block-wide advance costs ~1.1 us per 1000 atoms (one SM's L2 bandwidth)
+ *   one cluster (16) 13.9 @ 4096, 14.3 @ 8000, 16.6 @ 32768, 19.0 @ 64000, 24.9 @ 125000
+ *   sweep            a flat 21-22 (GEL) to ~26 (proteins)
+ * SDMD_SMALL_N is the largest system the cluster driver takes in AUTO mode . */
+#define SDMD_SMALL_N 98304
+#define SDMD_ONE_CTA_N 2048   /* up to here: one block; up to SDMD_SMALL_N: one cluster whose other blocks help with the advance */
+#define SDMD_MANY_N 8192      /* run_many: one block per replica */
 
 // leaf permutation of CreateCBT's sequential InsertCBTRun (CBT.c:86-105): time independent
 static void cbt_leaf_permutation(int n, std::vector<int> &leaf_atom) {
@@ -1331,7 +1407,9 @@ int sdmd_cuda_host_unregister(void *ptr) {
     return 0;
 }
 int sdmd_cuda_set_loop_mode(sdmd_ctx *c, int mode) {
-    if (mode != SDMD_LOOP_AUTO && mode != SDMD_LOOP_ONE_CTA && mode != SDMD_LOOP_SWEEP && mode != SDMD_LOOP_SWEEP_SERIAL) return set_err(SDMD_ERR_BAD_ARG, "loop mode");
+    if (mode != SDMD_LOOP_AUTO && mode != SDMD_LOOP_ONE_CTA && mode != SDMD_LOOP_SWEEP && mode != SDMD_LOOP_SWEEP_SERIAL &&
+        mode != SDMD_LOOP_CLUSTER)
+        return set_err(SDMD_ERR_BAD_ARG, "loop mode");
     c->loop_mode = mode;
     return 0;
 }
@@ -1897,7 +1975,22 @@ int sdmd_cuda_run(sdmd_ctx *c, double t_until, int64_t max_iter, struct sdmd_tra
     TRY(push_ctl(c));
     sdmd_trace_rec *dtr = (trace && trace_cap > 0) ? c->d_trace : nullptr;
     cudaEventRecord(c->ev0, c->stream);
-    if (c->loop_mode == SDMD_LOOP_ONE_CTA || (c->loop_mode == SDMD_LOOP_AUTO && c->n <= SDMD_SMALL_N)) {
+    if (c->loop_mode == SDMD_LOOP_CLUSTER || (c->loop_mode == SDMD_LOOP_AUTO && c->n > SDMD_ONE_CTA_N && c->n <= SDMD_SMALL_N)) {
+        c->counters_known = false;
+        if (const char *e = getenv("SDMD_CLUSTER_SIZE")) c->cluster_size = atoi(e);   // measurement knob
+        if (c->cluster_size < 1 || c->cluster_size > 16) return set_err(SDMD_ERR_BAD_ARG, "cluster size");
+        if (c->cluster_size > 8) CK(cudaFuncSetAttribute(k_run_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(c->cluster_size); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = c->cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, k_run_cluster, c->P, t_until, iter_limit, dtr, trace_cap));
+        c->launches++;
+        CK(cudaGetLastError());
+        TRY(pull_ctl(c));
+    } else if (c->loop_mode == SDMD_LOOP_ONE_CTA || (c->loop_mode == SDMD_LOOP_AUTO && c->n <= SDMD_ONE_CTA_N)) {
         c->counters_known = false;
         k_run_cta<<<1, 256, 0, c->stream>>>(c->P, t_until, iter_limit, dtr, trace_cap);
         c->launches++;
@@ -1973,7 +2066,7 @@ int sdmd_cuda_run(sdmd_ctx *c, double t_until, int64_t max_iter, struct sdmd_tra
 }
 
 // Run n replicas (all on the same device) concurrently, one persistent CTA each, until every one of them stops
-// (its own t_until / max_iter / RNG low / end of run).  Systems larger than SDMD_SMALL_N are not eligible.
+// (its own t_until / max_iter / RNG low / end of run).  Systems larger than SDMD_MANY_N are not eligible.
 int sdmd_cuda_run_many(sdmd_ctx **ctxs, int n, const double *t_until, int64_t max_iter, struct sdmd_run_stats *stats) {
     if (n <= 0 || !ctxs) return set_err(SDMD_ERR_BAD_ARG, "run_many: no replicas");
     sdmd_ctx *c0 = ctxs[0];
@@ -1982,7 +2075,7 @@ int sdmd_cuda_run_many(sdmd_ctx **ctxs, int n, const double *t_until, int64_t ma
     for (int k = 0; k < n; k++) {
         sdmd_ctx *c = ctxs[k];
         if (c->device != c0->device) return set_err(SDMD_ERR_BAD_ARG, "run_many: replicas on different devices");
-        if (c->n > SDMD_SMALL_N) return set_err(SDMD_ERR_UNSUPPORTED, "run_many: system too large for the one-CTA loop");
+        if (c->n > SDMD_MANY_N) return set_err(SDMD_ERR_UNSUPPORTED, "run_many: system too large for the one-CTA loop");
         c->cells_fresh = false;
         TRY(pull_ctl(c));
         c->h_ctl->stop = 0;

@@ -51,9 +51,9 @@ def test_predict_all_and_cbt_match_reference(capi, case):
 
 
 @pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8", "ala10x8_wallp", "ala10x4_wallc", "ala10x8_obst", "abeta8"])
-@pytest.mark.parametrize("loop_mode", [0, 2, 3], ids=["one_cta", "sweep_overlapped", "sweep_serial"])
+@pytest.mark.parametrize("loop_mode", [1, 4, 2, 3], ids=["one_cta", "cluster", "sweep_overlapped", "sweep_serial"])
 def test_device_event_loop_matches_reference(capi, case, loop_mode):
-    """loop_mode 2 / 3 force the large-system drivers (grid-wide sweep overlapped with / followed by one event block per
+    """loop_mode 4 forces the mid-size driver (one thread-block cluster) and 2 / 3 force the large-system drivers (grid-wide sweep overlapped with / followed by one event block per
     iteration) onto the protein cases too, so every loop driver is pinned to the reference trace with bonds, HB and
     HB-neighbour events."""
     pre, post, fin = load_case(case)
@@ -424,7 +424,7 @@ def test_multichain_protein_past_one_cta_limit_live(capi):
     assert pre.natom == 4720
     want = ref_trace(fin)
     assert len(want) == n_it
-    for mode in (0, 2, 3):
+    for mode in (0, 1, 2, 3):
         hv, r = _replica(capi, pre)
         r.set_loop_mode(mode)
         r.pbc_full(); r.cell_build()
@@ -457,7 +457,7 @@ def test_abeta64_box_live(capi):
     assert pre.natom == 64 * 72
     want = ref_trace(fin)
     assert len(want) == n_it
-    for mode in (0, 2, 3):
+    for mode in (0, 1, 2, 3):
         hv, r = _replica(capi, pre)
         r.set_loop_mode(mode)
         r.pbc_full(); r.cell_build()
