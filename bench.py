@@ -438,7 +438,9 @@ def cuda_loop(args, dist):
         "iterations_per_s": its / (run_ms * 1e-3), "gpu_launches": launches, "clocks": clocks,
         # one launch per iteration (k_sweep_event): the sweep role streams the 88 B/atom while the event block works; the
         # launch lasts as long as the slower of the two, so the achieved figure is algorithmic bytes over the iteration time
-        "roofline": {"bound": "hbm", "kernel": "k_sweep_event (UpdateData+TimeForward sweep overlapped with the event block, one launch per iteration)",
+        "roofline": {"bound": "hbm", "kernel": ("k_sweep_event (UpdateData+TimeForward sweep overlapped with the event block, one launch per iteration)"
+                                                if n > 98304 else "k_run_cluster (one persistent cluster of 16 CTAs: block 0 runs the events, all advance)"
+                                                if n > 2048 else "k_run_cta (one persistent CTA)"),
                      "achieved": alg / (per_it_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": alg / (per_it_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg, "kernel_ms": per_it_ms, "kernel_share_of_step": 1.0,
