@@ -80,7 +80,13 @@ def write_gel_gro(path: Path, n: int, a_nm: float = 0.8):
         for i in range(n):
             for j in range(n):
                 for m in range(n):
-                    f.write("%5iGEL%5s%5i%8.3f%8.3f%8.3f\n" % (k, "GEL", k, (m + 0.5) * a_nm, (j + 0.5) * a_nm, (i + 0.5) * a_nm))
+                    if n ** 3 < 10000:
+                        f.write("%5iGEL%5s%5i%8.3f%8.3f%8.3f\n" % (k, "GEL", k, (m + 0.5) * a_nm, (j + 0.5) * a_nm, (i + 0.5) * a_nm))
+                    else:
+                        # five-digit serials run into the atom-name column of the fixed-width layout; the reader itself
+                        # (Initialization.c:906, "%i%5c%5c%s") only needs a free-format residue number, two 5-character name
+                        # fields and a whitespace-separated serial
+                        f.write("%d%-5s%-5s %d %8.3f%8.3f%8.3f\n" % (k, "GEL", "GEL", k, (m + 0.5) * a_nm, (j + 0.5) * a_nm, (i + 0.5) * a_nm))
                     k += 1
         f.write("%10.5f%10.5f%10.5f\n" % (n * a_nm, n * a_nm, n * a_nm))
 

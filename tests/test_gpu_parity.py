@@ -502,6 +502,37 @@ def test_gel_8000_live_reference(capi):
     assert r.potential_energy() == fin.extra["epot"][0]
 
 
+def test_gel_42875_live_reference(capi):
+    """The largest box the UNMODIFIED reference can hold: its (N+1)^2 connectionMap is sized in `int` arithmetic
+    (Initialization.c:976), so N <= 46339; 35^3 = 42875 GEL atoms (7.4 GB of lazily zeroed map), run on the spot.  Cell list,
+    full-system pass (several thousand duplicate copies to resolve) and a 5000-iteration trace bit for bit on the cluster
+    driver (AUTO at this size) and on the overlapped-sweep driver."""
+    from oracle.make_golden import REFDIR as ref_dir
+    if not (ref_dir / "ref_harness_gel").exists():
+        pytest.skip("oracle/_ref/ref_harness_gel not built")
+    n_it = 5000
+    pre, post, fin = _live_case("gel35", harness="ref_harness_gel", coord="GEL35.gro", max_iter=n_it, n_gauss=80000, extra=[], gel_n=35)
+    assert pre.natom == 42875
+    want = ref_trace(fin)
+    for mode in (0, 2):
+        hv, r = _replica(capi, pre)
+        r.set_loop_mode(mode)
+        r.pbc_full(); r.cell_build()
+        assert np.array_equal(r.celllist(), pre.extra["celllist"])
+        r.predict_all(); r.cbt_build()
+        r.download(hv)
+        assert_fields_equal(hv, post, SLOT_FIELDS, what="after Predict(all): ")
+        assert np.array_equal(r.cbt()[0][1:], post.extra["cbt_node"][1:])
+        st, tr = r.run(max_iter=n_it, trace_cap=n_it)
+        assert st["error"] == 0 and st["iterations"] == n_it
+        assert_trace_equal(tr, want)
+        r.download(hv)
+        assert_fields_equal(hv, fin, STATE_FIELDS, what="final state: ")
+        assert np.array_equal(r.celllist(), fin.extra["celllist"])
+        assert r.potential_energy() == fin.extra["epot"][0]
+        r.close()
+
+
 def test_dense_gel_live_reference(capi):
     """Denser than SURVEY C5's 5 A variant: 14^3 GEL lattice at 4.5 A (about eight atoms per cell, > 200 candidates and ~33
     atoms inside the scan sphere per atom, so the filter's 32-entry rows overflow and the evaluation falls back to the

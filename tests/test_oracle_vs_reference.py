@@ -150,6 +150,30 @@ def test_abeta64_box_against_live_reference(tmp_path):
     assert o.potential_energy() == fin.extra["epot"][0]
 
 
+@pytest.mark.refbin
+def test_gel_42875_against_live_reference(tmp_path):
+    """35^3 GEL atoms: the largest system the reference's int-sized (N+1)^2 connectionMap allows (N <= 46339), run here by the
+    -DGEL reference binary; link list, Predict(all) and 5000 iterations."""
+    if not (REFDIR / "ref_harness_gel").exists():
+        pytest.skip("oracle/_ref/ref_harness_gel not built (needs /root/reference at build time)")
+    from oracle.make_golden import run_case
+    from sdmd_b200.hostview import HostView
+    snaps = run_case("gel35", tmp_path, harness="ref_harness_gel", coord="GEL35.gro", max_iter=5000, n_gauss=80000,
+                     extra=[], gel_n=35)
+    pre, post, fin = (HostView.from_snapshot(p) for p in snaps)
+    assert pre.natom == 42875
+    hv, o = _prepare(pre)
+    o.pbc_full(); o.cell_build()
+    assert np.array_equal(o.celllist(), pre.extra["celllist"])
+    o.predict_all()
+    assert_fields_equal(hv, post, SLOT_FIELDS, what="after Predict(all): ")
+    o.cbt_build()
+    want = ref_trace(fin)
+    st, tr = o.run(max_iter=len(want), trace_cap=len(want))
+    assert_trace_equal(tr, want)
+    assert_fields_equal(hv, fin, STATE_FIELDS)
+
+
 def test_remd_rearrange_rule():
     """Server.c:145-192: sequential, order dependent, pair (1,2) tried from both sides (hand-computed cases)."""
     # i=0 (num 1) meets num 2: dE=(2-1/.6)(-20+10)<0 -> swap.  i=1 (now num 1) meets j=0 (num 2): dE=+3.33 -> one
