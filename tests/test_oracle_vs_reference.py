@@ -158,9 +158,16 @@ def test_gel_42875_against_live_reference(tmp_path):
         pytest.skip("oracle/_ref/ref_harness_gel not built (needs /root/reference at build time)")
     from oracle.make_golden import run_case
     from sdmd_b200.hostview import HostView
-    snaps = run_case("gel35", tmp_path, harness="ref_harness_gel", coord="GEL35.gro", max_iter=5000, n_gauss=80000,
-                     extra=[], gel_n=35)
-    pre, post, fin = (HostView.from_snapshot(p) for p in snaps)
+    import shutil
+    import tempfile
+    from pathlib import Path
+    work = Path(tempfile.mkdtemp(prefix="s", dir="/tmp"))   # short path: the reference keeps file names in small fixed buffers
+    try:
+        snaps = run_case("gel35", work, harness="ref_harness_gel", coord="GEL35.gro", max_iter=5000, n_gauss=80000,
+                         extra=[], gel_n=35)
+        pre, post, fin = (HostView.from_snapshot(p) for p in snaps)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
     assert pre.natom == 42875
     hv, o = _prepare(pre)
     o.pbc_full(); o.cell_build()
