@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SDMD_ABI_VERSION 3
+#define SDMD_ABI_VERSION 4
 
 /* reference constants, DMD.h:25-30 */
 #define SDMD_INFINIT       1E8
@@ -161,6 +161,15 @@ struct sdmd_host_view {
      * SphObstEvent Events.c:752-796).  Event partner code -1000 n. */
     double  sphobst_pos[SDMD_MAX_OBST][3];
     double  sphobst_radius[SDMD_MAX_OBST]; /* SphObstObj.radius[n] (the file gives the diameter) */
+
+    /* tunnels through obstruction walls ("Tunnel?" line, Initialization.c:678-699; pseudo-atom built by ReadWall :2014-2049;
+     * TunnelTime TimePrediction.c:832-930, TunnelEvent Events.c:621-682, EnterTunnel ToolFunctions.c:921-952).  Event partner
+     * code -10000 n.  obst_hole[n] != 0: obstruction wall n sits at a tunnel mouth (obstObj.hole). */
+    int32_t n_tunnel;                 /* tunlObj.num, <= SDMD_MAX_OBST */
+    int32_t tunnel_type;              /* tunlObj.tunnel.property->typeofAtom */
+    double  tunnel_pos[SDMD_MAX_OBST][4];  /* tunlObj.position[n][0..3]: x of the two mouths, then y, z of the axis */
+    double  tunnel_diameter[SDMD_MAX_OBST];
+    int32_t obst_hole[SDMD_MAX_OBST];
 };
 
 /* wallType (parameter.txt line 11), first letter decides (strncmp(...,1)): which coordinates take part in the wall distance

@@ -18,6 +18,8 @@ reference's own inputs and stores what the reference computed as compressed .npz
                WallEvent, PBC in x and z only
   ala10x8_obst   8 ala10 chains between two flat obstruction walls ("Obstruct? 2 y .. , y ..") and three hard spherical
                obstacles ("SphObst? 3 ..."), periodic box, snapshot after 20000 iterations, then 8000 traced
+  ala10x4_tunnel 4 ala10 chains, two of them inside a tunnel between two holed obstruction walls ("Tunnel? 1 ..."), snapshot
+               after 60000 iterations, then 8000 traced
   ala10x4_wallc  4 ala10 chains in a smooth cylinder along x (WallType cylinder, diameter 26 A), snapshot after 20000
                iterations, then 8000 traced
 
@@ -55,6 +57,7 @@ CASES = {
     # BASELINE config 3 in small: 8 x Abeta16-22 (KLVFFAE; coordinates synthesised by oracle/make_peptide_gro.py, committed as
     # tests/golden/abeta16_22.gro): charged / aromatic / branched side chains, side-chain hydrogen bonds, CONSTRn tables
     "abeta8": ("ref_harness", "abeta8.gro", 8000, 40000, ["--warm", "150000"], -8),
+    "ala10x4_tunnel": ("ref_harness", "ala10x4t.gro", 8000, 40000, ["--warm", "60000"], -8),
 }
 # name: (single-chain .gro under tests/golden, chains per axis, spacing nm, box nm); abeta64 = SURVEY 8d C3 (live tests only)
 PEPTIDES = {
@@ -69,6 +72,9 @@ WALLS = {
     # each 0.4 A off the outermost atom of a chain (positions in A, parameter.txt lines 14 and 16); no smooth wall
     "ala10x8_obst": (None, (2, 2, 2), 1.9, (5.0, 4.2, 5.0), "2 y 1.5 , y 40.5",
                      "3 19.82 17.45 24.49 5.0 , 26.29 29.64 14.62 5.0 , 31.27 10.75 25.88 5.0"),
+    # a tunnel of diameter 24 A along x between two obstruction walls (x = 20 A and 60 A, the walls have holes at its mouths):
+    # two of the four chains sit inside the tunnel, two in the open space on either side
+    "ala10x4_tunnel": (None, (4, 1, 1), 2.0, (8.0, 2.6, 2.6), "2 x 20.0 , x 60.0", None, "1 20.0 60.0 13.0 13.0 24.0"),
 }
 
 
@@ -115,7 +121,7 @@ def write_multi_ala10(path: Path, src: Path, copies_per_axis=2, spacing_nm: floa
 
 
 def prepare_input(work: Path, time_units: float = 1000.0, wall_type: str | None = None, obst: str | None = None,
-                  sphobst: str | None = None) -> Path:
+                  sphobst: str | None = None, tunnel: str | None = None) -> Path:
     """Writable copy of the reference input directory with the run length (and a smooth wall) set."""
     src = REFDIR / "input"
     if not src.exists():
@@ -134,6 +140,8 @@ def prepare_input(work: Path, time_units: float = 1000.0, wall_type: str | None 
         lines[13] = "Obstruct?          %s" % obst
     if sphobst:
         lines[15] = "SphObst?           %s" % sphobst
+    if tunnel:
+        lines[14] = "Tunnel?            %s" % tunnel
     if wall_type or obst:
         # the wall's atom type must be a valid AtomModel name (Models.c:129-209); the shipped PHO is CG-only
         (inp / "Library_Ding" / "Wall.txt").write_text("Wall\n   ATOM CA      CA    12.0  N N\n")
@@ -150,7 +158,7 @@ def run_case(name: str, work: Path, harness=None, coord=None, max_iter=None, n_g
     work.mkdir(parents=True, exist_ok=True)
     wall = WALLS.get(name)
     inp = prepare_input(work, wall_type=wall[0] if wall else None, obst=wall[4] if wall and len(wall) > 4 else None,
-                        sphobst=wall[5] if wall and len(wall) > 5 else None)
+                        sphobst=wall[5] if wall and len(wall) > 5 else None, tunnel=wall[6] if wall and len(wall) > 6 else None)
     if wall:
         write_multi_ala10(inp / coord, inp / "ala10.gro", copies_per_axis=wall[1], spacing_nm=wall[2], box_nm=wall[3])
     elif name in PEPTIDES:

@@ -240,7 +240,7 @@ static int find_pair(oracle_ctx *c, int a1, int a2, int mode, double direction, 
         int t1 = v->type[a1];
         if (typeChange == 1) t1 = type_change(t1, 1);
         else if (typeChange == -1) t1 = type_change(t1, 0);
-        idx = v->coll_index[t1 * NT + (a2 == -1 ? v->wall_type : a2 < -1 ? v->obst_type[-a2 - 2] : v->type[a2])];   /* -1: wall pseudo-atom, -2-n: obstruction n */
+        idx = v->coll_index[t1 * NT + (a2 == -1 ? v->wall_type : a2 == -100 ? v->tunnel_type : a2 < -1 ? v->obst_type[-a2 - 2] : v->type[a2])];   /* -1: wall pseudo-atom, -2-n: obstruction n, -100: tunnel */
     } else if (mode == FP_CONSTRAINT) {            /* :68-77 */
         for (int k = v->con_off[a1]; k < v->con_off[a1 + 1]; k++)
             if (v->con_j[k] == a2) { idx = v->con_table[k]; break; }
@@ -623,7 +623,79 @@ static void wall_time(oracle_ctx *c, int i) {
     job_assign(c, i, 0, &ev, SDMD_EV_WALL);
 }
 
-/* ObstTime, TimePrediction.c:740-829, obstruction walls without holes: one-dimensional distance from the plane */
+/* FindPotWellWidth, ToolFunctions.c:954-970: squared range of the pair potential of (type_i, type_j) */
+static double pot_well_width(const struct sdmd_host_view *v, int type_i, int type_j) {
+    int idx = v->coll_index[type_i * NT + type_j];
+    if (idx < 0) return 0;
+    const struct sdmd_step_table *t = &v->tables[idx];
+    if (t->dmax2 > 0) return t->dmax2;
+    return t->nstep > 0 ? t->d2[t->nstep - 1] : 0;
+}
+
+/* EnterTunnel, ToolFunctions.c:921-952: will the atom be inside a tunnel mouth's cross-section after `time`? */
+static int enter_tunnel(oracle_ctx *c, double time, int i) {
+    const struct sdmd_host_view *v = c->v;
+    for (int n = 0; n < v->n_tunnel; n++) {
+        double radius2 = v->tunnel_diameter[n] * 0.5;
+        radius2 *= radius2;
+        double shift2 = pot_well_width(v, v->tunnel_type, v->type[i]);
+        double py = v->y[i], pz = v->z[i];
+        py += v->vy[i] * time;
+        pz += v->vz[i] * time;
+        double r1 = v->tunnel_pos[n][1] - v->tunnel_pos[n][1], r2 = py - v->tunnel_pos[n][2], r3 = pz - v->tunnel_pos[n][3];
+        double r_2 = r1 * r1 + r2 * r2 + r3 * r3;
+        double distance2 = radius2 + shift2 - 2 * sqrt(radius2 * shift2);
+        if (r_2 <= distance2) return 1;
+    }
+    return 0;
+}
+
+/* TunnelTime, TimePrediction.c:832-930: inside a tunnel the wall distance is taken from the tunnel's axis (y, z) */
+static void tunnel_time(oracle_ctx *c, int i) {
+    struct sdmd_host_view *v = c->v;
+    int idx = v->coll_index[v->type[i] * NT + v->tunnel_type];
+    if (idx < 0) { c->st.error = SDMD_ERR_TABLE; return; }
+    double distanceShift2 = v->tables[idx].dmin2;
+    double extraRange = sqrt(pot_well_width(v, v->tunnel_type, v->type[i]));
+    double pos0 = v->x[i], spd0 = v->vx[i];
+    for (int n = 0; n < v->n_tunnel; n++) {
+        struct evt ev;
+        struct par p;
+        double radius2 = v->tunnel_diameter[n] / 2;
+        radius2 *= radius2;
+        init_event(&ev);
+        p.r_ij[0] = v->tunnel_pos[n][1] - v->tunnel_pos[n][1]; p.r_ij[1] = v->y[i] - v->tunnel_pos[n][2]; p.r_ij[2] = v->z[i] - v->tunnel_pos[n][3];
+        p.v_ij[0] = 0 - 0.0; p.v_ij[1] = v->vy[i] - 0.0; p.v_ij[2] = v->vz[i] - 0.0;
+        p.r_2 = p.r_ij[0] * p.r_ij[0] + p.r_ij[1] * p.r_ij[1] + p.r_ij[2] * p.r_ij[2];
+        p.b_ij = p.r_ij[0] * p.v_ij[0] + p.r_ij[1] * p.v_ij[1] + p.r_ij[2] * p.v_ij[2];
+        p.v_2 = p.v_ij[0] * p.v_ij[0] + p.v_ij[1] * p.v_ij[1] + p.v_ij[2] * p.v_ij[2];
+        if (p.r_2 > radius2 + distanceShift2 - 2 * sqrt(radius2 * distanceShift2) + ZERO) continue;   /* outside the tunnel */
+        double distance2 = radius2 + p.r_2 - 2 * sqrt(p.r_2 * radius2);
+        double accum;
+        p.coreorShell = find_pair(c, i, -100, FP_COLLISION, -1 * p.b_ij, distance2, &p.shortlimit2, &p.longlimit2,
+                                  &p.lowerPotential, &p.upperPotential, &accum, 0, 0);
+        if (p.lowerPotential == 0 && p.upperPotential == 0) { c->st.error = SDMD_ERR_STATE; return; }   /* exit(), :880-884 */
+        if (p.b_ij < 0 && calc_disc(&p) > 0) {
+            if (p.coreorShell == 1) continue;
+            ev.sub = SDMD_SUB_TBDCAPTR;
+            p.s_time = -1;
+            p.d_ij2 = radius2 + p.longlimit2 - 2 * sqrt(p.longlimit2 * radius2);
+            ev.potential = p.upperPotential;
+        } else {
+            ev.sub = (p.coreorShell == 0) ? SDMD_SUB_WELLBOUNC : SDMD_SUB_TBDESCAP;
+            p.s_time = 1;
+            p.d_ij2 = radius2 + p.shortlimit2 - 2 * sqrt(p.shortlimit2 * radius2);
+            ev.potential = p.lowerPotential;
+        }
+        ev.time = calc_time(&p);
+        double futurePos = pos0 + spd0 * ev.time;                                          /* :912-917 */
+        if (futurePos < v->tunnel_pos[n][0] - extraRange || futurePos > v->tunnel_pos[n][1] + extraRange) continue;
+        if (ev.time < 0) ev.time = INF;
+        if (job_assign(c, i, 0, &ev, SDMD_EV_TUNL)) v->ev_partner[i] = -10000 * n;
+    }
+}
+
+/* ObstTime, TimePrediction.c:740-829, obstruction walls: one-dimensional distance from the plane */
 static void obst_time(oracle_ctx *c, int i) {
     struct sdmd_host_view *v = c->v;
     const double pos[3] = {v->x[i], v->y[i], v->z[i]}, spd[3] = {v->vx[i], v->vy[i], v->vz[i]};
@@ -654,7 +726,9 @@ static void obst_time(oracle_ctx *c, int i) {
             }
             ev.time = calc_time(&p);
             if (ev.time < 0) { c->st.error = SDMD_ERR_STATE; return; }                /* exit(), :813-816 */
-            if (job_assign(c, i, 0, &ev, SDMD_EV_OBST)) v->ev_partner[i] = -1 * (dim + 1) - 10 * n;   /* :820-824 */
+            /* at the next collision the atom would already be in the hole: the prediction is void, :818-824 */
+            if (!(v->obst_hole[n] && enter_tunnel(c, ev.time, i)) && job_assign(c, i, 0, &ev, SDMD_EV_OBST))
+                v->ev_partner[i] = -1 * (dim + 1) - 10 * n;
         }
     }
 }
@@ -698,6 +772,7 @@ void oracle_predict(oracle_ctx *c, const int32_t *renew) {
         if (v->hydrogen_bond) { hb_time(c, i); hbn_time(c, i); }
         if (v->wall_kind) wall_time(c, i);                       /* SGThread.c:183-185 */
         if (v->n_obst) obst_time(c, i);                          /* :187-189 */
+        if (v->n_tunnel) tunnel_time(c, i);                      /* :197-199 */
         if (v->n_sphobst) sphobst_time(c, i);                    /* :205-207 */
     }
 }
@@ -1024,6 +1099,32 @@ static void obst_event(oracle_ctx *c, int i, int sph) {
     v->vx[i] = v->vx[i] + phi * r[0]; v->vy[i] = v->vy[i] + phi * r[1]; v->vz[i] = v->vz[i] + phi * r[2];
 }
 
+/* TunnelEvent, Events.c:621-682: WallEvent's kick with the separation taken from the tunnel's axis */
+static void tunnel_event(oracle_ctx *c, int i) {
+    struct sdmd_host_view *v = c->v;
+    int n = v->ev_partner[i] / -10000;
+    double r[3] = {v->tunnel_pos[n][1] - v->tunnel_pos[n][1], v->y[i] - v->tunnel_pos[n][2], v->z[i] - v->tunnel_pos[n][3]};
+    double vv[3] = {0 - 0.0, v->vy[i] - 0.0, v->vz[i] - 0.0};
+    double d_ij2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    double b_ij = r[0] * vv[0] + r[1] * vv[1] + r[2] * vv[2];
+    double mass = v->mass[i];
+    double potential = v->ev_potential[i];
+    int s_vel = 0;
+    switch (v->ev_sub[i]) {
+        case SDMD_SUB_WELLBOUNC: s_vel = -1; potential = 0; break;
+        case SDMD_SUB_TBDCAPTR:
+            if (b_ij * b_ij - 2 * d_ij2 * potential / mass <= 0) { potential = 0; s_vel = 1; } else s_vel = -1;
+            break;
+        case SDMD_SUB_TBDESCAP:
+            if (b_ij * b_ij - 2 * d_ij2 * potential / mass <= 0) { potential = 0; s_vel = -1; } else s_vel = 1;
+            break;
+        default: c->st.error = SDMD_ERR_STATE; return;
+    }
+    double phi = (-1 * b_ij + s_vel * sqrt(b_ij * b_ij - 2 * d_ij2 * potential / mass)) / d_ij2;
+    if (phi != phi) { c->st.error = SDMD_ERR_STATE; return; }
+    v->vx[i] = v->vx[i] + phi * r[0]; v->vy[i] = v->vy[i] + phi * r[1]; v->vz[i] = v->vz[i] + phi * r[2];
+}
+
 /* DoEvent, Events.c:25-114 */
 static void do_event(oracle_ctx *c, int i, int j) {
     struct sdmd_host_view *v = c->v;
@@ -1042,6 +1143,7 @@ static void do_event(oracle_ctx *c, int i, int j) {
         case SDMD_EV_PCC: pcc_event(c, i); c->st.pcc++; break;
         case SDMD_EV_WALL: wall_event(c, i); c->st.wall++; break;
         case SDMD_EV_OBST: obst_event(c, i, 0); c->st.wall++; break;
+        case SDMD_EV_TUNL: tunnel_event(c, i); c->st.wall++; break;
         case SDMD_EV_SPHO: obst_event(c, i, 1); c->st.wall++; break;
         default: c->st.error = SDMD_ERR_STATE; break;
     }

@@ -1177,7 +1177,16 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
         P.sph_r[n] = v->sphobst_radius[n];
         for (int k = 0; k < 3; k++) P.sph_pos[n][k] = v->sphobst_pos[n][k];
     }
-    P.single_body = P.wall_kind != 0 || P.n_obst > 0 || P.n_sphobst > 0;
+    if (v->n_tunnel < 0 || v->n_tunnel > SDMD_MAX_OBST) return set_err(SDMD_ERR_UNSUPPORTED, "more tunnels than SDMD_MAX_OBST");
+    if (v->n_tunnel && (v->tunnel_type < 1 || v->tunnel_type > SDMD_NATOMTYPE)) return set_err(SDMD_ERR_BAD_ARG, "bad tunnel_type");
+    P.n_tunnel = v->n_tunnel;
+    P.tunnel_type = v->tunnel_type;
+    for (int n = 0; n < v->n_tunnel; n++) {
+        P.tun_diam[n] = v->tunnel_diameter[n];
+        for (int k = 0; k < 4; k++) P.tun_pos[n][k] = v->tunnel_pos[n][k];
+    }
+    for (int n = 0; n < v->n_obst; n++) P.obst_hole[n] = v->obst_hole[n];
+    P.single_body = P.wall_kind != 0 || P.n_obst > 0 || P.n_sphobst > 0 || P.n_tunnel > 0;
     P.thermostat_on = v->thermostat_on;
     P.method_ding = v->method_ding;
     P.hydrogen_bond = v->hydrogen_bond;

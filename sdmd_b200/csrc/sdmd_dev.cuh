@@ -80,6 +80,9 @@ struct DevP {
     int pbc_mask;              // bit k: dimension k is periodic (Events.c:210-216)
     double wall_pos[3];
     int n_obst, n_sphobst;     // flat obstruction walls / hard spherical obstacles
+    int n_tunnel, tunnel_type; // tunnels through (holed) obstruction walls
+    int obst_hole[SDMD_MAX_OBST];
+    double tun_pos[SDMD_MAX_OBST][4], tun_diam[SDMD_MAX_OBST];
     int single_body;           // any of wall / obstruction / sphere present
     int obst_type[SDMD_MAX_OBST];
     double obst_pos[SDMD_MAX_OBST][3], sph_pos[SDMD_MAX_OBST][3], sph_r[SDMD_MAX_OBST];

@@ -760,7 +760,73 @@ __device__ inline void d_wall_time(const DevP &D, const Self &me, Slot &cur) {
     d_job_assign(D, cur, 0, t, pot, sub, SDMD_EV_WALL);
 }
 
-// ObstTime, TimePrediction.c:740-829 (obstruction walls without holes): one-dimensional distance from the plane,
+// FindPotWellWidth, ToolFunctions.c:954-970: squared range of the pair potential of (type_i, type_j)
+__device__ __forceinline__ double d_pot_well_width(const DevP &D, int type_i, int type_j) {
+    int idx = __ldg(&D.coll_index[type_i * SD_NT + type_j]);
+    if (idx < 0) return 0;
+    const sdmd_step_table *t = &D.tables[idx];
+    if (t->dmax2 > 0) return t->dmax2;
+    return t->nstep > 0 ? t->d2[t->nstep - 1] : 0;
+}
+
+// EnterTunnel, ToolFunctions.c:921-952: will the atom be inside a tunnel mouth's cross-section after `time`?
+__device__ inline bool d_enter_tunnel(const DevP &D, const Self &me, double time) {
+    for (int n = 0; n < D.n_tunnel; n++) {
+        double radius2 = D.tun_diam[n] * 0.5;
+        radius2 *= radius2;
+        double shift2 = d_pot_well_width(D, D.tunnel_type, me.type);
+        double py = me.y, pz = me.z;
+        py += me.vy * time;
+        pz += me.vz * time;
+        double r1 = D.tun_pos[n][1] - D.tun_pos[n][1], r2 = py - D.tun_pos[n][2], r3 = pz - D.tun_pos[n][3];
+        double r_2 = r1 * r1 + r2 * r2 + r3 * r3;
+        double distance2 = radius2 + shift2 - 2 * sqrt(radius2 * shift2);
+        if (r_2 <= distance2) return true;
+    }
+    return false;
+}
+
+// TunnelTime, TimePrediction.c:832-930: inside a tunnel the wall distance is taken from the tunnel's axis (y, z); partner
+// code -10000 n
+__device__ inline void d_tunnel_time(const DevP &D, const Self &me, Slot &cur) {
+    int idx = __ldg(&D.coll_index[me.type * SD_NT + D.tunnel_type]);
+    if (idx < 0) { D.ctl->error = SDMD_ERR_TABLE; return; }
+    const double shift2 = D.tables[idx].dmin2;
+    const double extraRange = sqrt(d_pot_well_width(D, D.tunnel_type, me.type));
+    for (int n = 0; n < D.n_tunnel; n++) {
+        double radius2 = D.tun_diam[n] / 2;
+        radius2 *= radius2;
+        Pair p;
+        p.rx = D.tun_pos[n][1] - D.tun_pos[n][1]; p.ry = me.y - D.tun_pos[n][2]; p.rz = me.z - D.tun_pos[n][3];
+        double vx = 0 - 0.0, vy = me.vy - 0.0, vz = me.vz - 0.0;
+        p.r2 = p.rx * p.rx + p.ry * p.ry + p.rz * p.rz;
+        p.b = p.rx * vx + p.ry * vy + p.rz * vz;
+        p.v2 = vx * vx + vy * vy + vz * vz;
+        if (p.r2 > radius2 + shift2 - 2 * sqrt(radius2 * shift2) + SD_ZERO) continue;   // outside the tunnel
+        double dist2 = radius2 + p.r2 - 2 * sqrt(p.r2 * radius2);
+        FindRes f = d_find_pair_table(D, &D.tables[idx], FP_COLLISION, -1 * p.b, dist2, 0, 0);
+        if (f.lowPot == 0 && f.upPot == 0) { D.ctl->error = SDMD_ERR_STATE; return; }    // exit(), :880-884
+        int s, sub;
+        double d2, pot;
+        if (p.b < 0 && d_disc(p, f.lower) > 0) {
+            if (f.cs == 1) continue;
+            sub = SDMD_SUB_TBDCAPTR; s = -1;
+            d2 = radius2 + f.upper - 2 * sqrt(f.upper * radius2);
+            pot = f.upPot;
+        } else {
+            sub = (f.cs == 0) ? SDMD_SUB_WELLBOUNC : SDMD_SUB_TBDESCAP; s = 1;
+            d2 = radius2 + f.lower - 2 * sqrt(f.lower * radius2);
+            pot = f.lowPot;
+        }
+        double t = d_time(p, s, d2);
+        double futurePos = me.x + me.vx * t;                                              // :912-917
+        if (futurePos < D.tun_pos[n][0] - extraRange || futurePos > D.tun_pos[n][1] + extraRange) continue;
+        if (t < 0) t = SD_INF;
+        if (d_job_assign(D, cur, 0, t, pot, sub, SDMD_EV_TUNL)) cur.partner = -10000 * n;
+    }
+}
+
+// ObstTime, TimePrediction.c:740-829 (obstruction walls): one-dimensional distance from the plane,
 // partner code -dim - 10 n
 __device__ inline void d_obst_time(const DevP &D, const Self &me, Slot &cur) {
     const double pos[3] = {me.x, me.y, me.z}, spd[3] = {me.vx, me.vy, me.vz};
@@ -795,7 +861,9 @@ __device__ inline void d_obst_time(const DevP &D, const Self &me, Slot &cur) {
             }
             double t = d_time(p, s, d2);
             if (t < 0) { D.ctl->error = SDMD_ERR_STATE; return; }             // exit(), :813-816
-            if (d_job_assign(D, cur, 0, t, pot, sub, SDMD_EV_OBST)) cur.partner = -1 * (dim + 1) - 10 * n;
+            // at the next collision the atom would already be in the hole: the prediction is void, :818-824
+            if (!(D.obst_hole[n] && d_enter_tunnel(D, me, t)) && d_job_assign(D, cur, 0, t, pot, sub, SDMD_EV_OBST))
+                cur.partner = -1 * (dim + 1) - 10 * n;
         }
     }
 }
@@ -879,6 +947,7 @@ __device__ inline Slot d_predict_atom(const DevP &D, const SlotSrc &S, int i, Sl
     if (D.single_body) {   // the single-body predictors come last, SGThread.c:183-207
         if (D.wall_kind) d_wall_time(D, me, cur);
         if (D.n_obst) d_obst_time(D, me, cur);
+        if (D.n_tunnel) d_tunnel_time(D, me, cur);
         if (D.n_sphobst) d_sphobst_time(D, me, cur);
     }
     *npair = me.npair;
@@ -1191,6 +1260,33 @@ __device__ inline void d_obst_event(const DevP &D, int i, bool sph) {
     D.vx[i] = spd[0] + phi * r[0]; D.vy[i] = spd[1] + phi * r[1]; D.vz[i] = spd[2] + phi * r[2];
 }
 
+// TunnelEvent, Events.c:621-682: WallEvent's kick with the separation taken from the tunnel's axis
+__device__ inline void d_tunnel_event(const DevP &D, int i) {
+    int n = D.ev_partner[i] / -10000;
+    if (n < 0 || n >= D.n_tunnel) { D.ctl->error = SDMD_ERR_STATE; return; }
+    double tvx = D.vx[i], tvy = D.vy[i], tvz = D.vz[i];
+    double rx = D.tun_pos[n][1] - D.tun_pos[n][1], ry = D.y[i] - D.tun_pos[n][2], rz = D.z[i] - D.tun_pos[n][3];
+    double vx = 0 - 0.0, vy = tvy - 0.0, vz = tvz - 0.0;
+    double d2 = rx * rx + ry * ry + rz * rz;
+    double b = rx * vx + ry * vy + rz * vz;
+    double mass = D.mass[i];
+    double pot = D.ev_pot[i];
+    int s_vel = 0;
+    switch (D.ev_sub[i]) {
+        case SDMD_SUB_WELLBOUNC: s_vel = -1; pot = 0; break;
+        case SDMD_SUB_TBDCAPTR:
+            if (b * b - 2 * d2 * pot / mass <= 0) { pot = 0; s_vel = 1; } else s_vel = -1;
+            break;
+        case SDMD_SUB_TBDESCAP:
+            if (b * b - 2 * d2 * pot / mass <= 0) { pot = 0; s_vel = -1; } else s_vel = 1;
+            break;
+        default: D.ctl->error = SDMD_ERR_STATE; return;
+    }
+    double phi = (-1 * b + s_vel * sqrt(b * b - 2 * d2 * pot / mass)) / d2;
+    if (phi != phi) { D.ctl->error = SDMD_ERR_STATE; return; }
+    D.vx[i] = tvx + phi * rx; D.vy[i] = tvy + phi * ry; D.vz[i] = tvz + phi * rz;
+}
+
 // ThermostatEvent (Andersen), Events.c:396-420; RandomVelocity ToolFunctions.c:600-610
 __device__ inline void d_thermostat_event(const DevP &D, int i) {
     double speed[3];
@@ -1272,6 +1368,7 @@ __device__ inline void d_do_event(const DevP &D, int i, int j) {
         case SDMD_EV_PCC: d_pcc_event(D, i); c->n_pcc++; break;
         case SDMD_EV_WALL: d_wall_event(D, i); c->n_wall++; break;
         case SDMD_EV_OBST: d_obst_event(D, i, false); c->n_wall++; break;
+        case SDMD_EV_TUNL: d_tunnel_event(D, i); c->n_wall++; break;
         case SDMD_EV_SPHO: d_obst_event(D, i, true); c->n_wall++; break;
         default: c->error = SDMD_ERR_STATE; break;
     }
@@ -1956,6 +2053,7 @@ __device__ inline void d_predict_cta(const DevP &D, PredShared &sh) {
                         Self me = d_load_self(D, i);
                         if (D.wall_kind) d_wall_time(D, me, w);
                         if (D.n_obst) d_obst_time(D, me, w);
+                        if (D.n_tunnel) d_tunnel_time(D, me, w);
                         if (D.n_sphobst) d_sphobst_time(D, me, w);
                         sh.result[a] = w;
                     }

@@ -141,15 +141,24 @@ int sdmd_glue_flatten(struct sdmd_host_view *v) {
     v->gel_mode = 1;
 #endif
     /* features that live outside the hot-path scope (rough / moving walls, obstacles, tunnels, flow, CG) */
-    if (tunlObj.mark || flow.mark || CG.mark || strcmp(wallDyn.mark, "no")) return SDMD_ERR_UNSUPPORTED;
-    /* flat obstruction walls (no tunnel, hence no holes) and hard spherical obstacles */
+    if (flow.mark || CG.mark || strcmp(wallDyn.mark, "no")) return SDMD_ERR_UNSUPPORTED;
+    /* flat obstruction walls, tunnels through them, hard spherical obstacles */
     if (obstObj.mark) {
         if (obstObj.num > SDMD_MAX_OBST) return SDMD_ERR_UNSUPPORTED;
         v->n_obst = obstObj.num;
         for (int n = 0; n < obstObj.num; n++) {
-            if (obstObj.hole[n]) return SDMD_ERR_UNSUPPORTED;
+            v->obst_hole[n] = obstObj.hole[n];
             for (int k = 0; k < 3; k++) v->obst_pos[n][k] = obstObj.position[n][k + 1];
             v->obst_type[n] = obstObj.obst[n].property->typeofAtom;
+        }
+    }
+    if (tunlObj.mark) {
+        if (tunlObj.num > SDMD_MAX_OBST) return SDMD_ERR_UNSUPPORTED;
+        v->n_tunnel = tunlObj.num;
+        v->tunnel_type = tunlObj.tunnel.property->typeofAtom;
+        for (int n = 0; n < tunlObj.num; n++) {
+            for (int k = 0; k < 4; k++) v->tunnel_pos[n][k] = tunlObj.position[n][k];
+            v->tunnel_diameter[n] = tunlObj.diameter[n];
         }
     }
     if (SphObstObj.mark) {
@@ -323,6 +332,10 @@ void sdmd_snap_put_view(sdmd_snap *s, const struct sdmd_host_view *v) {
     sdmd_snap_put(s, "obst_type", "i4", v->obst_type, (uint64_t)v->n_obst);
     sdmd_snap_put(s, "sphobst_pos", "f8", v->sphobst_pos, 3 * (uint64_t)v->n_sphobst);
     sdmd_snap_put(s, "sphobst_radius", "f8", v->sphobst_radius, (uint64_t)v->n_sphobst);
+    sdmd_snap_put(s, "tunnel_pos", "f8", v->tunnel_pos, 4 * (uint64_t)v->n_tunnel);
+    sdmd_snap_put(s, "tunnel_diameter", "f8", v->tunnel_diameter, (uint64_t)v->n_tunnel);
+    sdmd_snap_put(s, "tunnel_i4", "i4", &v->tunnel_type, 1);
+    sdmd_snap_put(s, "obst_hole", "i4", v->obst_hole, (uint64_t)v->n_obst);
 #define PUT(field, dt, cnt) sdmd_snap_put(s, #field, dt, v->field, cnt)
     PUT(x, "f8", n1); PUT(y, "f8", n1); PUT(z, "f8", n1);
     PUT(vx, "f8", n1); PUT(vy, "f8", n1); PUT(vz, "f8", n1);

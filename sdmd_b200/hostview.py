@@ -13,7 +13,7 @@ from pathlib import Path
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_OBST = 4
 NT = 33
 NHBCLASS = 12
@@ -62,6 +62,8 @@ class CHostView(C.Structure):
         ("n_obst", C.c_int32), ("n_sphobst", C.c_int32),
         ("obst_pos", C.c_double * (3 * MAX_OBST)), ("obst_type", C.c_int32 * MAX_OBST),
         ("sphobst_pos", C.c_double * (3 * MAX_OBST)), ("sphobst_radius", C.c_double * MAX_OBST),
+        ("n_tunnel", C.c_int32), ("tunnel_type", C.c_int32),
+        ("tunnel_pos", C.c_double * (4 * MAX_OBST)), ("tunnel_diameter", C.c_double * MAX_OBST), ("obst_hole", C.c_int32 * MAX_OBST),
     ]
 
 
@@ -150,6 +152,11 @@ class HostView:
         self.obst_type = np.zeros(0, dtype=np.int32)
         self.sphobst_pos = np.zeros((0, 3))
         self.sphobst_radius = np.zeros(0)
+        # tunnels through obstruction walls: (x0, x1, y, z) per tunnel, diameter, wall atom type; holed obstruction walls
+        self.tunnel_pos = np.zeros((0, 4))
+        self.tunnel_diameter = np.zeros(0)
+        self.tunnel_type = 0
+        self.obst_hole = np.zeros(0, dtype=np.int32)
         for name, dt, k in PER_ATOM:
             setattr(self, name, np.zeros(n1 * k, dtype=_NP[dt]))
         for name in ("bond_off", "con_off", "cm_off"):
@@ -181,6 +188,11 @@ class HostView:
             hv.obst_type = np.asarray(d["obst_type"], dtype=np.int32).copy()
             hv.sphobst_pos = np.asarray(d["sphobst_pos"], dtype=np.float64).reshape(-1, 3).copy()
             hv.sphobst_radius = np.asarray(d["sphobst_radius"], dtype=np.float64).copy()
+        if "tunnel_pos" in d:
+            hv.tunnel_pos = np.asarray(d["tunnel_pos"], dtype=np.float64).reshape(-1, 4).copy()
+            hv.tunnel_diameter = np.asarray(d["tunnel_diameter"], dtype=np.float64).copy()
+            hv.tunnel_type = int(d["tunnel_i4"][0])
+            hv.obst_hole = np.asarray(d["obst_hole"], dtype=np.int32).copy()
         for name, dt, _ in PER_ATOM:
             setattr(hv, name, np.ascontiguousarray(d[name], dtype=_NP[dt]).copy())
         for name, dt in OTHER:
@@ -188,7 +200,8 @@ class HostView:
             setattr(hv, name, arr if arr.size else np.zeros(1, dtype=_NP[dt]))
         hv.tables = np.frombuffer(d["tables"].tobytes(), dtype=STEP_TABLE_DTYPE).copy()
         known = {n for n, _, _ in PER_ATOM} | {n for n, _ in OTHER} | {"scalars_i4", "scalars_f8", "scalars_i8", "tables", "wall_i4", "wall_f8",
-                                                                           "obst_pos", "obst_type", "sphobst_pos", "sphobst_radius"}
+                                                                           "obst_pos", "obst_type", "sphobst_pos", "sphobst_radius",
+                                                                           "tunnel_pos", "tunnel_diameter", "tunnel_i4", "obst_hole"}
         hv.extra = {k: v for k, v in d.items() if k not in known}
         return hv
 
@@ -213,6 +226,10 @@ class HostView:
             "obst_type": np.asarray(self.obst_type, dtype=np.int32),
             "sphobst_pos": np.asarray(self.sphobst_pos, dtype=np.float64).reshape(-1),
             "sphobst_radius": np.asarray(self.sphobst_radius, dtype=np.float64),
+            "tunnel_pos": np.asarray(self.tunnel_pos, dtype=np.float64).reshape(-1),
+            "tunnel_diameter": np.asarray(self.tunnel_diameter, dtype=np.float64),
+            "tunnel_i4": np.array([self.tunnel_type], dtype=np.int32),
+            "obst_hole": np.asarray(self.obst_hole, dtype=np.int32),
             "tables": np.frombuffer(self.tables.tobytes(), dtype=np.uint8),
         }
         for name, _, _ in PER_ATOM:
@@ -255,6 +272,14 @@ class HostView:
             c.sphobst_pos[k] = float(v)
         for k, v in enumerate(self.sphobst_radius):
             c.sphobst_radius[k] = float(v)
+        c.n_tunnel, c.tunnel_type = len(self.tunnel_diameter), int(self.tunnel_type)
+        assert c.n_tunnel <= MAX_OBST
+        for k, v in enumerate(np.asarray(self.tunnel_pos, dtype=np.float64).reshape(-1)):
+            c.tunnel_pos[k] = float(v)
+        for k, v in enumerate(self.tunnel_diameter):
+            c.tunnel_diameter[k] = float(v)
+        for k, v in enumerate(self.obst_hole):
+            c.obst_hole[k] = int(v)
         for name, dt, _ in PER_ATOM:
             arr = getattr(self, name)
             assert arr.flags["C_CONTIGUOUS"] and arr.dtype == _NP[dt], name

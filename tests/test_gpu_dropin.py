@@ -79,22 +79,22 @@ def test_dropin_continue_run_matches_reference(tmp_path):
         assert _counter(outs["ref"], key) == _counter(outs["gpu"], key), key
 
 
-@pytest.mark.parametrize("wall_type", ["parallel", "cylinder", "obstacles"])
+@pytest.mark.parametrize("wall_type", ["parallel", "cylinder", "obstacles", "tunnel"])
 def test_dropin_walled_run_matches_reference(tmp_path, wall_type):
     """BASELINE config 4 (confinement): WallExist smooth with WallType parallel / cylinder, or flat obstruction walls plus
-    hard spherical obstacles, chains of ala10 inside — the drop-in driver must write the same trajectory and counters
+    hard spherical obstacles, or a tunnel between two holed obstruction walls, chains of ala10 inside — the drop-in driver must write the same trajectory and counters
     (wall events included) as the stock binary."""
     if not (REF / "sDMD_ref").exists() or not DROPIN.exists():
         pytest.skip("needs oracle/_ref/sDMD_ref and the drop-in driver")
     from oracle.make_golden import WALLS, prepare_input, write_multi_ala10
-    spec = WALLS[{"parallel": "ala10x8_wallp", "cylinder": "ala10x4_wallc", "obstacles": "ala10x8_obst"}[wall_type]]
+    spec = WALLS[{"parallel": "ala10x8_wallp", "cylinder": "ala10x4_wallc", "obstacles": "ala10x8_obst", "tunnel": "ala10x4_tunnel"}[wall_type]]
     _, copies, spacing, box = spec[:4]
     outs = {}
     for tag, binary in (("ref", REF / "sDMD_ref"), ("gpu", DROPIN)):
         work = tmp_path / tag
         work.mkdir()
         inp = prepare_input(work, time_units=60, wall_type=spec[0], obst=spec[4] if len(spec) > 4 else None,
-                            sphobst=spec[5] if len(spec) > 5 else None)
+                            sphobst=spec[5] if len(spec) > 5 else None, tunnel=spec[6] if len(spec) > 6 else None)
         write_multi_ala10(inp / "walled.gro", inp / "ala10.gro", copies_per_axis=copies, spacing_nm=spacing, box_nm=box)
         r = subprocess.run([str(binary), "-f", "walled.gro", "-i", str(inp), "-o", str(work / "out")],
                            capture_output=True, text=True, timeout=600)
