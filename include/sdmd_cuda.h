@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SDMD_ABI_VERSION 4
+#define SDMD_ABI_VERSION 5
 
 /* reference constants, DMD.h:25-30 */
 #define SDMD_INFINIT       1E8
@@ -170,6 +170,17 @@ struct sdmd_host_view {
     double  tunnel_pos[SDMD_MAX_OBST][4];  /* tunlObj.position[n][0..3]: x of the two mouths, then y, z of the axis */
     double  tunnel_diameter[SDMD_MAX_OBST];
     int32_t obst_hole[SDMD_MAX_OBST];
+
+    /* flow ("Flow" line of parameter.txt, Initialization.c:562-633; CreateFlow :2056-2068): 1 = constant drift velocity,
+     * 2 = constant force.  Both act where the Andersen thermostat redraws a velocity (ThermostatEvent, Events.c:396-420) and
+     * in CalKinetE (ToolFunctions.c:626-656).  3 = charge sources: not supported (SDMD_ERR_UNSUPPORTED from the glue). */
+    int32_t flow_mark;                /* flow.mark */
+    int32_t pad_flow_;
+    double  flow_v[3];                /* flow.constV.v[1..3] */
+    double *flow_a;                   /* flow.force.a[i][1..3], 3 per atom; may be NULL (= 0) */
+    double *flow_time_rec;            /* flow.force.timeRec[i] (mutable); may be NULL when flow_mark == 0 */
+    double *protein_mass;             /* per atom: protein[proteinNum].mass of its chain (CalculateMass, Initialization.c:1557-1567,
+                                         counts hydrogens as 1); only read by CalKinetE when flow_mark >= 2; may be NULL otherwise */
 };
 
 /* wallType (parameter.txt line 11), first letter decides (strncmp(...,1)): which coordinates take part in the wall distance

@@ -20,6 +20,7 @@ reference's own inputs and stores what the reference computed as compressed .npz
                obstacles ("SphObst? 3 ..."), periodic box, snapshot after 20000 iterations, then 8000 traced
   ala10x4_tunnel 4 ala10 chains, two of them inside a tunnel between two holed obstruction walls ("Tunnel? 1 ..."), snapshot
                after 60000 iterations, then 8000 traced
+  ala10_flowv / ala10_flowf  ala10 with "Flow velocity ..." / "Flow force ..." (drift terms of ThermostatEvent and CalKinetE)
   ala10x4_wallc  4 ala10 chains in a smooth cylinder along x (WallType cylinder, diameter 26 A), snapshot after 20000
                iterations, then 8000 traced
 
@@ -58,7 +59,12 @@ CASES = {
     # tests/golden/abeta16_22.gro): charged / aromatic / branched side chains, side-chain hydrogen bonds, CONSTRn tables
     "abeta8": ("ref_harness", "abeta8.gro", 8000, 40000, ["--warm", "150000"], -8),
     "ala10x4_tunnel": ("ref_harness", "ala10x4t.gro", 8000, 40000, ["--warm", "60000"], -8),
+    # flow terms in ThermostatEvent / CalKinetE: constant drift velocity, constant force
+    "ala10_flowv": ("ref_harness", "ala10.gro", 6000, 16000, [], 0),
+    "ala10_flowf": ("ref_harness", "ala10.gro", 6000, 16000, ["--warm", "20000"], 0),
 }
+# "Flow" line of parameter.txt: constant drift velocity (A per time unit) / constant force (pN)
+FLOWS = {"ala10_flowv": "velocity 0.02 0.0 0.01", "ala10_flowf": "force 5.0 0.0 0.0"}
 # name: (single-chain .gro under tests/golden, chains per axis, spacing nm, box nm); abeta64 = SURVEY 8d C3 (live tests only)
 PEPTIDES = {
     "abeta8": ("abeta16_22.gro", (2, 2, 2), 2.0, (6.0, 6.0, 6.0)),
@@ -121,7 +127,7 @@ def write_multi_ala10(path: Path, src: Path, copies_per_axis=2, spacing_nm: floa
 
 
 def prepare_input(work: Path, time_units: float = 1000.0, wall_type: str | None = None, obst: str | None = None,
-                  sphobst: str | None = None, tunnel: str | None = None) -> Path:
+                  sphobst: str | None = None, tunnel: str | None = None, flow: str | None = None) -> Path:
     """Writable copy of the reference input directory with the run length (and a smooth wall) set."""
     src = REFDIR / "input"
     if not src.exists():
@@ -142,6 +148,8 @@ def prepare_input(work: Path, time_units: float = 1000.0, wall_type: str | None 
         lines[15] = "SphObst?           %s" % sphobst
     if tunnel:
         lines[14] = "Tunnel?            %s" % tunnel
+    if flow:
+        lines[12] = "Flow               %s" % flow
     if wall_type or obst:
         # the wall's atom type must be a valid AtomModel name (Models.c:129-209); the shipped PHO is CG-only
         (inp / "Library_Ding" / "Wall.txt").write_text("Wall\n   ATOM CA      CA    12.0  N N\n")
@@ -158,7 +166,8 @@ def run_case(name: str, work: Path, harness=None, coord=None, max_iter=None, n_g
     work.mkdir(parents=True, exist_ok=True)
     wall = WALLS.get(name)
     inp = prepare_input(work, wall_type=wall[0] if wall else None, obst=wall[4] if wall and len(wall) > 4 else None,
-                        sphobst=wall[5] if wall and len(wall) > 5 else None, tunnel=wall[6] if wall and len(wall) > 6 else None)
+                        sphobst=wall[5] if wall and len(wall) > 5 else None, tunnel=wall[6] if wall and len(wall) > 6 else None,
+                        flow=FLOWS.get(name))
     if wall:
         write_multi_ala10(inp / coord, inp / "ala10.gro", copies_per_axis=wall[1], spacing_nm=wall[2], box_nm=wall[3])
     elif name in PEPTIDES:

@@ -1007,10 +1007,13 @@ static void thermostat_event(oracle_ctx *c, int i) {
         do {
             double variance = v->target_temperature / v->mass[i];
             speed[k] = next_gauss(c) * sqrt(variance) + 0;
-            speed[k] += 0.0;
+            /* flow terms, Events.c:408-410 (netV only exists with charge sources) */
+            double a = v->flow_a ? v->flow_a[3 * i + k] : 0.0, rec = v->flow_time_rec ? v->flow_time_rec[i] : 0.0;
+            speed[k] += v->flow_v[k] + 0.0 + a * (c->st.currenttime - rec);
         } while (speed[k] == 0 && !c->st.error);
     }
     v->vx[i] = speed[0]; v->vy[i] = speed[1]; v->vz[i] = speed[2];
+    if (v->flow_time_rec) v->flow_time_rec[i] = c->st.currenttime;                       /* :418 */
 }
 
 /* PBCandCrossCellEvent, Events.c:248-272 (+ PBC("part") :230-238) */
@@ -1243,10 +1246,27 @@ double oracle_potential_energy(oracle_ctx *c) {
 double oracle_kinetic_energy(oracle_ctx *c) {
     const struct sdmd_host_view *v = c->v;
     double TKE = 0;
-    for (int i = 1; i <= c->n; i++) {
-        double t[3] = {v->vx[i] - 0.0, v->vy[i] - 0.0, v->vz[i] - 0.0};
-        double s = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
-        TKE += 0.5 * v->mass[i] * s;
+    if (v->flow_mark < 2) {                                     /* ToolFunctions.c:630-636: relative to the drift velocity */
+        for (int i = 1; i <= c->n; i++) {
+            double t[3] = {v->vx[i] - v->flow_v[0], v->vy[i] - v->flow_v[1], v->vz[i] - v->flow_v[2]};
+            double s = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+            TKE += 0.5 * v->mass[i] * s;
+        }
+    } else {                                                    /* :637-649: relative to each protein's centre of mass (CalCOMV :613-623) */
+        int i = 1;
+        while (i <= c->n) {
+            int j = i;
+            double pm = v->protein_mass ? v->protein_mass[i] : 0, net[3] = {0, 0, 0};     /* CalculateMass, Initialization.c:1557-1567 */
+            while (j <= c->n && v->protein_num[j] == v->protein_num[i]) j++;
+            for (int n = i; n < j; n++) { net[0] += v->vx[n] * v->mass[n]; net[1] += v->vy[n] * v->mass[n]; net[2] += v->vz[n] * v->mass[n]; }
+            for (int k = 0; k < 3; k++) net[k] /= pm;
+            for (int n = i; n < j; n++) {
+                double t[3] = {v->vx[n] - net[0], v->vy[n] - net[1], v->vz[n] - net[2]};
+                double s = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+                TKE += 0.5 * v->mass[n] * s;
+            }
+            i = j;
+        }
     }
     return TKE;
 }

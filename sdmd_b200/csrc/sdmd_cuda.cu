@@ -1063,16 +1063,33 @@ __global__ void k_potential_energy_multi(const MultiArg *args, double *out) { ou
 __global__ void k_ke_terms(DevP D, double *terms) {
     int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (i > D.n) return;
-    double a = D.vx[i] - 0.0, b = D.vy[i] - 0.0, c = D.vz[i] - 0.0;   // CalKinetE, ToolFunctions.c:631-635
+    double a = D.vx[i] - D.flow_v[0], b = D.vy[i] - D.flow_v[1], c = D.vz[i] - D.flow_v[2];   // CalKinetE, ToolFunctions.c:631-635
     double s = a * a + b * b + c * c;
     terms[i - 1] = 0.5 * D.mass[i] * s;
 }
 __global__ void k_kinetic_energy(DevP D, double *out) {
     double TKE = 0;
-    for (int i = 1; i <= D.n; i++) {
-        double a = D.vx[i] - 0.0, b = D.vy[i] - 0.0, c = D.vz[i] - 0.0;
-        double s = a * a + b * b + c * c;
-        TKE += 0.5 * D.mass[i] * s;
+    if (D.flow_mark < 2) {                     // relative to the drift velocity, ToolFunctions.c:630-636
+        for (int i = 1; i <= D.n; i++) {
+            double a = D.vx[i] - D.flow_v[0], b = D.vy[i] - D.flow_v[1], c = D.vz[i] - D.flow_v[2];
+            double s = a * a + b * b + c * c;
+            TKE += 0.5 * D.mass[i] * s;
+        }
+    } else {                                   // relative to each chain's centre of mass, :637-649 + CalCOMV :613-623
+        int i = 1;
+        while (i <= D.n) {
+            int j = i;
+            while (j <= D.n && D.protein[j] == D.protein[i]) j++;
+            double pm = D.protein_mass ? D.protein_mass[i] : 0, nx = 0, ny = 0, nz = 0;
+            for (int n = i; n < j; n++) { nx += D.vx[n] * D.mass[n]; ny += D.vy[n] * D.mass[n]; nz += D.vz[n] * D.mass[n]; }
+            nx /= pm; ny /= pm; nz /= pm;
+            for (int n = i; n < j; n++) {
+                double a = D.vx[n] - nx, b = D.vy[n] - ny, c = D.vz[n] - nz;
+                double s = a * a + b * b + c * c;
+                TKE += 0.5 * D.mass[n] * s;
+            }
+            i = j;
+        }
     }
     *out = TKE;
 }
@@ -1208,6 +1225,16 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     TRY(dupload(c, &P.x, v->x, n1)); TRY(dupload(c, &P.y, v->y, n1)); TRY(dupload(c, &P.z, v->z, n1));
     TRY(dupload(c, &P.vx, v->vx, n1)); TRY(dupload(c, &P.vy, v->vy, n1)); TRY(dupload(c, &P.vz, v->vz, n1));
     TRY(dupload(c, (double **)&P.mass, v->mass, n1));
+    if (v->flow_mark < 0 || v->flow_mark > 2) return set_err(SDMD_ERR_UNSUPPORTED, "flow type (charge sources are not supported)");
+    P.flow_mark = v->flow_mark;
+    for (int k = 0; k < 3; k++) P.flow_v[k] = v->flow_v[k];
+    if (v->flow_mark) {
+        if (v->flow_a) TRY(dupload(c, (double **)&P.flow_a, v->flow_a, 3 * n1));
+        if (v->flow_time_rec) TRY(dupload(c, &P.flow_time_rec, v->flow_time_rec, n1));
+        else TRY(dalloc(c, &P.flow_time_rec, n1));
+        if (v->protein_mass) TRY(dupload(c, (double **)&P.protein_mass, v->protein_mass, n1));
+        else if (v->flow_mark >= 2) return set_err(SDMD_ERR_BAD_ARG, "flow_mark >= 2 needs protein_mass");
+    }
     TRY(dupload(c, &P.type, v->type, n1));
     TRY(dupload(c, (int **)&P.aa_type, v->aa_type, n1));
     TRY(dupload(c, (int **)&P.protein, v->protein_num, n1));
@@ -1479,6 +1506,7 @@ int sdmd_cuda_download(sdmd_ctx *c, struct sdmd_host_view *v) {
     DL(hbn_partner, hbn_partner, 5 * n1); DL(hbn_partner_num, hbn_pnum, n1); DL(hbn_status, hbn_status, n1);
     DL(ev_time, ev_time, n1); DL(ev_potential, ev_pot, n1); DL(ev_partner, ev_partner, n1);
     DL(ev_type, ev_type, n1); DL(ev_sub, ev_sub, n1); DL(cell_idx, cell_idx, 3 * n1);
+    if (c->P.flow_time_rec) { DL(flow_time_rec, flow_time_rec, n1); }
 #undef DL
     if (v->ev_counter) CK(cudaMemcpyAsync(v->ev_counter, c->P.ev_counter, n1 * 8, cudaMemcpyDeviceToHost, c->stream));
     if (v->ev_pcounter) CK(cudaMemcpyAsync(v->ev_pcounter, c->P.ev_pcounter, n1 * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1924,7 +1952,7 @@ int sdmd_cuda_potential_energy(sdmd_ctx *c, double *e) {
 int sdmd_cuda_kinetic_energy(sdmd_ctx *c, double *e) {
     CK(cudaSetDevice(c->device));
     double *d = (double *)(c->d_sum + 1);
-    if (c->n <= 2048) {
+    if (c->n <= 2048 || c->P.flow_mark >= 2) {   // per-chain centre-of-mass terms: serial kernel
         k_kinetic_energy<<<1, 1, 0, c->stream>>>(c->P, d);
         c->launches++;
     } else {

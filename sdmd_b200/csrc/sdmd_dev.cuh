@@ -80,6 +80,11 @@ struct DevP {
     int pbc_mask;              // bit k: dimension k is periodic (Events.c:210-216)
     double wall_pos[3];
     int n_obst, n_sphobst;     // flat obstruction walls / hard spherical obstacles
+    int flow_mark;             // 1 constant drift velocity, 2 constant force (ThermostatEvent / CalKinetE terms)
+    double flow_v[3];
+    const double *flow_a;      // 3 per atom or NULL
+    double *flow_time_rec;     // per atom or NULL
+    const double *protein_mass;
     int n_tunnel, tunnel_type; // tunnels through (holed) obstruction walls
     int obst_hole[SDMD_MAX_OBST];
     double tun_pos[SDMD_MAX_OBST][4], tun_diam[SDMD_MAX_OBST];

@@ -1294,12 +1294,15 @@ __device__ inline void d_thermostat_event(const DevP &D, int i) {
     double sd = sqrt(variance);
 #pragma unroll 1
     for (int k = 0; k < 3; k++) {
+        // flow terms, Events.c:408-410 (netV only exists with charge sources)
+        const double a = D.flow_a ? D.flow_a[3 * i + k] : 0.0, rec = D.flow_time_rec ? D.flow_time_rec[i] : 0.0;
         do {
             speed[k] = d_next_gauss(D) * sd + 0;
-            speed[k] += 0.0;
+            speed[k] += D.flow_v[k] + 0.0 + a * (D.ctl->currenttime - rec);
         } while (speed[k] == 0 && !D.ctl->error);
     }
     D.vx[i] = speed[0]; D.vy[i] = speed[1]; D.vz[i] = speed[2];
+    if (D.flow_time_rec) D.flow_time_rec[i] = D.ctl->currenttime;   // :418
 }
 
 __device__ __forceinline__ int d_cell_of(const DevP &D, double x, double y, double z, int idx[3]) {

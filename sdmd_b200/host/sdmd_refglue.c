@@ -80,6 +80,7 @@ void sdmd_glue_gather_dynamic(struct sdmd_host_view *v) {
         v->ev_type[i] = (uint8_t)d->event.eventType;
         v->ev_sub[i] = (uint8_t)d->event.subEventType;
         for (int k = 0; k < 3; k++) v->cell_idx[3 * i + k] = d->cellIndex[k + 1];
+        if (v->flow_time_rec && flow.force.timeRec) v->flow_time_rec[i] = flow.force.timeRec[i];
     }
 }
 
@@ -120,6 +121,7 @@ void sdmd_glue_scatter_dynamic(const struct sdmd_host_view *v) {
         d->event.eventType = (enum EEventType)v->ev_type[i];
         d->event.subEventType = (enum EInteractionType)v->ev_sub[i];
         for (int k = 0; k < 3; k++) d->cellIndex[k + 1] = v->cell_idx[3 * i + k];
+        if (v->flow_time_rec && flow.force.timeRec) flow.force.timeRec[i] = v->flow_time_rec[i];
     }
 }
 
@@ -141,7 +143,9 @@ int sdmd_glue_flatten(struct sdmd_host_view *v) {
     v->gel_mode = 1;
 #endif
     /* features that live outside the hot-path scope (rough / moving walls, obstacles, tunnels, flow, CG) */
-    if (flow.mark || CG.mark || strcmp(wallDyn.mark, "no")) return SDMD_ERR_UNSUPPORTED;
+    if (flow.mark > 2 || CG.mark || strcmp(wallDyn.mark, "no")) return SDMD_ERR_UNSUPPORTED;
+    v->flow_mark = flow.mark;
+    for (int k = 0; k < 3; k++) v->flow_v[k] = flow.constV.v[k + 1];
     /* flat obstruction walls, tunnels through them, hard spherical obstacles */
     if (obstObj.mark) {
         if (obstObj.num > SDMD_MAX_OBST) return SDMD_ERR_UNSUPPORTED;
@@ -189,6 +193,11 @@ int sdmd_glue_flatten(struct sdmd_host_view *v) {
     ALLOC(v->ev_time, n + 1); ALLOC(v->ev_potential, n + 1); ALLOC(v->ev_partner, n + 1);
     ALLOC(v->ev_counter, n + 1); ALLOC(v->ev_pcounter, n + 1); ALLOC(v->ev_type, n + 1); ALLOC(v->ev_sub, n + 1);
     ALLOC(v->cell_idx, 3 * (n + 1));
+    ALLOC(v->flow_a, 3 * (n + 1)); ALLOC(v->flow_time_rec, n + 1); ALLOC(v->protein_mass, n + 1);
+    for (int i = 1; i <= n; i++) v->protein_mass[i] = protein[atom[i].property->sequence.proteinNum].mass;
+    if (flow.force.a)
+        for (int i = 1; i <= n; i++)
+            for (int k = 0; k < 3; k++) v->flow_a[3 * i + k] = flow.force.a[i][k + 1];
     sdmd_glue_gather_dynamic(v);
 
     struct pool pool = {0};
@@ -274,7 +283,7 @@ void sdmd_glue_free(struct sdmd_host_view *v) {
     free(v->hb_bond); free(v->hb_neighbor); free(v->hb_role); free(v->hb_itype);
     free(v->hbn_partner); free(v->hbn_partner_num); free(v->hbn_status);
     free(v->ev_time); free(v->ev_potential); free(v->ev_partner); free(v->ev_counter); free(v->ev_pcounter);
-    free(v->ev_type); free(v->ev_sub); free(v->cell_idx);
+    free(v->ev_type); free(v->ev_sub); free(v->cell_idx); free(v->flow_a); free(v->flow_time_rec); free(v->protein_mass);
     free(v->bond_off); free(v->bond_j); free(v->bond_dmin2); free(v->bond_dmax2);
     free(v->con_off); free(v->con_j); free(v->con_table);
     free(v->cm_off); free(v->cm_j); free(v->cm_flags);
@@ -346,6 +355,10 @@ void sdmd_snap_put_view(sdmd_snap *s, const struct sdmd_host_view *v) {
     PUT(ev_time, "f8", n1); PUT(ev_potential, "f8", n1); PUT(ev_partner, "i4", n1);
     PUT(ev_counter, "i8", n1); PUT(ev_pcounter, "i8", n1); PUT(ev_type, "u1", n1); PUT(ev_sub, "u1", n1);
     PUT(cell_idx, "i4", 3 * n1);
+    PUT(flow_a, "f8", 3 * n1); PUT(flow_time_rec, "f8", n1); PUT(protein_mass, "f8", n1);
+    int32_t flow_i[1] = {v->flow_mark};
+    sdmd_snap_put(s, "flow_i4", "i4", flow_i, 1);
+    sdmd_snap_put(s, "flow_f8", "f8", v->flow_v, 3);
     PUT(bond_off, "i4", n1 + 1); PUT(bond_j, "i4", v->bond_off[n + 1]);
     PUT(bond_dmin2, "f8", v->bond_off[n + 1]); PUT(bond_dmax2, "f8", v->bond_off[n + 1]);
     PUT(con_off, "i4", n1 + 1); PUT(con_j, "i4", v->con_off[n + 1]); PUT(con_table, "i4", v->con_off[n + 1]);

@@ -13,7 +13,7 @@ from pathlib import Path
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_OBST = 4
 NT = 33
 NHBCLASS = 12
@@ -64,6 +64,8 @@ class CHostView(C.Structure):
         ("sphobst_pos", C.c_double * (3 * MAX_OBST)), ("sphobst_radius", C.c_double * MAX_OBST),
         ("n_tunnel", C.c_int32), ("tunnel_type", C.c_int32),
         ("tunnel_pos", C.c_double * (4 * MAX_OBST)), ("tunnel_diameter", C.c_double * MAX_OBST), ("obst_hole", C.c_int32 * MAX_OBST),
+        ("flow_mark", C.c_int32), ("pad_flow_", C.c_int32), ("flow_v", C.c_double * 3),
+        ("flow_a", _P(C.c_double)), ("flow_time_rec", _P(C.c_double)), ("protein_mass", _P(C.c_double)),
     ]
 
 
@@ -93,10 +95,11 @@ PER_ATOM = [
     ("hbn_partner", "i4", 5), ("hbn_partner_num", "i4", 1), ("hbn_status", "i4", 1),
     ("ev_time", "f8", 1), ("ev_potential", "f8", 1), ("ev_partner", "i4", 1), ("ev_counter", "i8", 1),
     ("ev_pcounter", "i8", 1), ("ev_type", "u1", 1), ("ev_sub", "u1", 1), ("cell_idx", "i4", 3),
+    ("flow_a", "f8", 3), ("flow_time_rec", "f8", 1), ("protein_mass", "f8", 1),
 ]
 MUTABLE = ["x", "y", "z", "vx", "vy", "vz", "type", "hb_bond", "hb_itype", "hbn_partner", "hbn_partner_num",
            "hbn_status", "ev_time", "ev_potential", "ev_partner", "ev_counter", "ev_pcounter", "ev_type", "ev_sub",
-           "cell_idx"]
+           "cell_idx", "flow_time_rec"]
 OTHER = [
     ("bond_off", "i4"), ("bond_j", "i4"), ("bond_dmin2", "f8"), ("bond_dmax2", "f8"),
     ("con_off", "i4"), ("con_j", "i4"), ("con_table", "i4"),
@@ -157,6 +160,8 @@ class HostView:
         self.tunnel_diameter = np.zeros(0)
         self.tunnel_type = 0
         self.obst_hole = np.zeros(0, dtype=np.int32)
+        self.flow_mark = 0          # 0 none, 1 constant drift velocity, 2 constant force
+        self.flow_v = np.zeros(3)
         for name, dt, k in PER_ATOM:
             setattr(self, name, np.zeros(n1 * k, dtype=_NP[dt]))
         for name in ("bond_off", "con_off", "cm_off"):
@@ -194,14 +199,18 @@ class HostView:
             hv.tunnel_type = int(d["tunnel_i4"][0])
             hv.obst_hole = np.asarray(d["obst_hole"], dtype=np.int32).copy()
         for name, dt, _ in PER_ATOM:
-            setattr(hv, name, np.ascontiguousarray(d[name], dtype=_NP[dt]).copy())
+            if name in d:               # arrays added later (flow_*) are absent in older snapshots: keep the zeros
+                setattr(hv, name, np.ascontiguousarray(d[name], dtype=_NP[dt]).copy())
+        if "flow_f8" in d:
+            hv.flow_mark = int(d["flow_i4"][0])
+            hv.flow_v = np.asarray(d["flow_f8"], dtype=np.float64)[:3].copy()
         for name, dt in OTHER:
             arr = np.ascontiguousarray(d[name], dtype=_NP[dt]).copy()
             setattr(hv, name, arr if arr.size else np.zeros(1, dtype=_NP[dt]))
         hv.tables = np.frombuffer(d["tables"].tobytes(), dtype=STEP_TABLE_DTYPE).copy()
         known = {n for n, _, _ in PER_ATOM} | {n for n, _ in OTHER} | {"scalars_i4", "scalars_f8", "scalars_i8", "tables", "wall_i4", "wall_f8",
                                                                            "obst_pos", "obst_type", "sphobst_pos", "sphobst_radius",
-                                                                           "tunnel_pos", "tunnel_diameter", "tunnel_i4", "obst_hole"}
+                                                                           "tunnel_pos", "tunnel_diameter", "tunnel_i4", "obst_hole", "flow_i4", "flow_f8"}
         hv.extra = {k: v for k, v in d.items() if k not in known}
         return hv
 
@@ -230,6 +239,8 @@ class HostView:
             "tunnel_diameter": np.asarray(self.tunnel_diameter, dtype=np.float64),
             "tunnel_i4": np.array([self.tunnel_type], dtype=np.int32),
             "obst_hole": np.asarray(self.obst_hole, dtype=np.int32),
+            "flow_i4": np.array([self.flow_mark], dtype=np.int32),
+            "flow_f8": np.asarray(self.flow_v, dtype=np.float64),
             "tables": np.frombuffer(self.tables.tobytes(), dtype=np.uint8),
         }
         for name, _, _ in PER_ATOM:
@@ -272,6 +283,8 @@ class HostView:
             c.sphobst_pos[k] = float(v)
         for k, v in enumerate(self.sphobst_radius):
             c.sphobst_radius[k] = float(v)
+        c.flow_mark = int(self.flow_mark)
+        c.flow_v[:] = [float(v) for v in self.flow_v]
         c.n_tunnel, c.tunnel_type = len(self.tunnel_diameter), int(self.tunnel_type)
         assert c.n_tunnel <= MAX_OBST
         for k, v in enumerate(np.asarray(self.tunnel_pos, dtype=np.float64).reshape(-1)):

@@ -109,6 +109,30 @@ def test_dropin_walled_run_matches_reference(tmp_path, wall_type):
     assert _counter(outs["gpu"], "Wall times") > 0
 
 
+@pytest.mark.parametrize("flow", ["velocity 0.02 0.0 0.01", "force 5.0 0.0 0.0"], ids=["velocity", "force"])
+def test_dropin_flow_run_matches_reference(tmp_path, flow):
+    """"Flow velocity ..." / "Flow force ..." (drift terms in ThermostatEvent and in the temperature CalKinetE reports): the
+    drop-in driver writes the same trajectory, energies and counters as the stock binary."""
+    if not (REF / "sDMD_ref").exists() or not DROPIN.exists():
+        pytest.skip("needs oracle/_ref/sDMD_ref and the drop-in driver")
+    from oracle.make_golden import prepare_input
+    outs = {}
+    for tag, binary in (("ref", REF / "sDMD_ref"), ("gpu", DROPIN)):
+        work = tmp_path / tag
+        work.mkdir()
+        inp = prepare_input(work, time_units=150, flow=flow)
+        r = subprocess.run([str(binary), "-f", "ala10.gro", "-i", str(inp), "-o", str(work / "out")],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs[tag] = r.stdout.replace("\r", "\n")
+    for name in ("out_trj.gro", "out_cnt.txt"):
+        a = (tmp_path / "ref" / "out" / name).read_bytes()
+        b = (tmp_path / "gpu" / "out" / name).read_bytes()
+        assert len(a) > 1000 and a == b, name
+    for key in ("collision times", "bond times", "thermostat times", "PBC&CC times"):
+        assert _counter(outs["ref"], key) == _counter(outs["gpu"], key), key
+
+
 def test_dropin_remd_with_reference_server(tmp_path):
     """demo/REMD-style run with the reference's own sServer: three replica processes of the drop-in driver (sharing
     the GPU) must log the same temperature walk (out_REMD<id>.txt) and trajectories as three stock sDMD processes."""

@@ -47,7 +47,7 @@ def test_predict_all_and_cbt(case):
     assert o.kinetic_energy() == post.extra["ekin"][0]
 
 
-@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8", "ala10x8_wallp", "ala10x4_wallc", "ala10x8_obst", "abeta8", "ala10x4_tunnel"])
+@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8", "ala10x8_wallp", "ala10x4_wallc", "ala10x8_obst", "abeta8", "ala10x4_tunnel", "ala10_flowv", "ala10_flowf"])
 def test_event_loop_trace(case):
     pre, post, fin = load_case(case)
     hv, o = _prepare(pre)
@@ -73,6 +73,12 @@ def test_event_loop_trace(case):
         # smooth confining wall: WallTime runs in every prediction, WallEvent a few times
         assert pre.wall_kind in (1, 2) and st["wall"] == int(ref[11]) and st["wall"] > 0
         assert (want["type"] == 5).sum() >= st["wall"]
+    if "flow" in case:
+        # drift velocity / constant force: extra terms where the thermostat redraws a velocity, CalKinetE relative to the drift
+        # (flowv) or to the chain's centre of mass (flowf), timeRec bookkeeping
+        assert pre.flow_mark == (1 if case.endswith("v") else 2) and st["thermostat"] > 10
+        assert o.kinetic_energy() == fin.extra["ekin"][0]
+        assert_fields_equal(hv, fin, ("flow_time_rec",))
     if "tunnel" in case:
         # tunnel between two holed obstruction walls: TunnelTime / TunnelEvent, EnterTunnel in ObstTime
         assert len(pre.tunnel_diameter) == 1 and list(pre.obst_hole) == [1, 1] and st["wall"] == int(ref[11])
