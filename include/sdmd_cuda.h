@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SDMD_ABI_VERSION 5
+#define SDMD_ABI_VERSION 6
 
 /* reference constants, DMD.h:25-30 */
 #define SDMD_INFINIT       1E8
@@ -34,6 +34,7 @@ extern "C" {
 #define SDMD_MAX_STEPS     16     /* longest shipped table row has 13 steps */
 #define SDMD_NHBCLASS      12     /* potentialPairHB[12][33][33], DMD.h:550 */
 #define SDMD_MAX_OBST      4      /* flat obstruction walls / spherical obstacles the device keeps (each) */
+#define SDMD_MAX_CHARGE    8      /* charge sources incl. their periodic images */
 
 /* connection-map bits, DMD.h:59-63 */
 #define SDMD_BOND_CONNECT        0x01
@@ -173,7 +174,8 @@ struct sdmd_host_view {
 
     /* flow ("Flow" line of parameter.txt, Initialization.c:562-633; CreateFlow :2056-2068): 1 = constant drift velocity,
      * 2 = constant force.  Both act where the Andersen thermostat redraws a velocity (ThermostatEvent, Events.c:396-420) and
-     * in CalKinetE (ToolFunctions.c:626-656).  3 = charge sources: not supported (SDMD_ERR_UNSUPPORTED from the glue). */
+     * in CalKinetE (ToolFunctions.c:626-656).  3 = charge sources (ChargeTime TimePrediction.c:933-1017, ChargeEvent
+     * Events.c:685-749, partner code -100 n; with `-COM` ThermostatEvent adds the chain's centre-of-mass velocity). */
     int32_t flow_mark;                /* flow.mark */
     int32_t pad_flow_;
     double  flow_v[3];                /* flow.constV.v[1..3] */
@@ -181,6 +183,11 @@ struct sdmd_host_view {
     double *flow_time_rec;            /* flow.force.timeRec[i] (mutable); may be NULL when flow_mark == 0 */
     double *protein_mass;             /* per atom: protein[proteinNum].mass of its chain (CalculateMass, Initialization.c:1557-1567,
                                          counts hydrogens as 1); only read by CalKinetE when flow_mark >= 2; may be NULL otherwise */
+    double *charge;                   /* property->charge per atom (InitializeCharge, Initialization.c:2092-2141); may be NULL */
+    int32_t n_charge;                 /* charge sources ChargeTime loops over (its totalCNum, TimePrediction.c:936), <= SDMD_MAX_CHARGE */
+    int32_t charge_com;               /* chargeAA[COM] (command-line -COM) */
+    double  charge_pos[SDMD_MAX_CHARGE][3], charge_vel[SDMD_MAX_CHARGE][3];
+    double  charge_potgrad[SDMD_MAX_CHARGE], charge_gap[SDMD_MAX_CHARGE];
 };
 
 /* wallType (parameter.txt line 11), first letter decides (strncmp(...,1)): which coordinates take part in the wall distance

@@ -62,9 +62,13 @@ CASES = {
     # flow terms in ThermostatEvent / CalKinetE: constant drift velocity, constant force
     "ala10_flowv": ("ref_harness", "ala10.gro", 6000, 16000, [], 0),
     "ala10_flowf": ("ref_harness", "ala10.gro", 6000, 16000, ["--warm", "20000"], 0),
+    # one charge source (+ its periodic image), -COM: ChargeTime / ChargeEvent, centre-of-mass term in ThermostatEvent
+    "ala10_charge": ("ref_harness", "ala10.gro", 8000, 20000, ["--warm", "20000"], 0),
 }
 # "Flow" line of parameter.txt: constant drift velocity (A per time unit) / constant force (pN)
-FLOWS = {"ala10_flowv": "velocity 0.02 0.0 0.01", "ala10_flowf": "force 5.0 0.0 0.0"}
+FLOWS = {"ala10_flowv": "velocity 0.02 0.0 0.01", "ala10_flowf": "force 5.0 0.0 0.0",
+         "ala10_charge": "charge 1 : 100.0 75.0 75.0 0.05 0.2"}
+SDMD_ARGS = {"ala10_charge": ["-COM"]}      # extra command-line switches of the reference
 # name: (single-chain .gro under tests/golden, chains per axis, spacing nm, box nm); abeta64 = SURVEY 8d C3 (live tests only)
 PEPTIDES = {
     "abeta8": ("abeta16_22.gro", (2, 2, 2), 2.0, (6.0, 6.0, 6.0)),
@@ -182,7 +186,7 @@ def run_case(name: str, work: Path, harness=None, coord=None, max_iter=None, n_g
         write_multi_ala10(inp / coord, inp / "ala10.gro")
     prefix = work / name
     cmd = [str(REFDIR / harness), str(prefix), str(max_iter), str(n_gauss), *extra, "--",
-           "-f", coord, "-i", str(inp), "-o", str(work / "out")]
+           "-f", coord, "-i", str(inp), "-o", str(work / "out"), *SDMD_ARGS.get(name, [])]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"{' '.join(cmd)} failed ({r.returncode}):\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")

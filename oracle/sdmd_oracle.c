@@ -733,6 +733,44 @@ static void obst_time(oracle_ctx *c, int i) {
     }
 }
 
+/* ChargeTime, TimePrediction.c:933-1017: concentric potential steps of width `gap` around each charge source */
+static void charge_time(oracle_ctx *c, int i) {
+    struct sdmd_host_view *v = c->v;
+    if (!v->charge || !v->charge[i]) return;
+    double charge = v->charge[i];
+    int flag = 0;
+    for (int cn = 0; cn < v->n_charge; cn++) {
+        if (v->x[i] > v->charge_pos[cn][0] - ZERO) continue;
+        if (v->charge_pos[cn][0] < v->box[0]) flag = 1;                               /* :948-956 */
+        else if (!(flag == 0 && v->charge_pos[cn][0] > v->box[0])) break;
+        struct evt ev;
+        struct par p;
+        init_event(&ev);
+        p.r_ij[0] = v->x[i] - v->charge_pos[cn][0]; p.r_ij[1] = v->y[i] - v->charge_pos[cn][1]; p.r_ij[2] = v->z[i] - v->charge_pos[cn][2];
+        p.v_ij[0] = v->vx[i] - v->charge_vel[cn][0]; p.v_ij[1] = v->vy[i] - v->charge_vel[cn][1]; p.v_ij[2] = v->vz[i] - v->charge_vel[cn][2];
+        p.r_2 = p.r_ij[0] * p.r_ij[0] + p.r_ij[1] * p.r_ij[1] + p.r_ij[2] * p.r_ij[2];
+        p.b_ij = p.r_ij[0] * p.v_ij[0] + p.r_ij[1] * p.v_ij[1] + p.r_ij[2] * p.v_ij[2];
+        p.v_2 = p.v_ij[0] * p.v_ij[0] + p.v_ij[1] * p.v_ij[1] + p.v_ij[2] * p.v_ij[2];
+        int gapNum = sqrt(p.r_2) / v->charge_gap[cn];
+        double gap2 = v->charge_gap[cn] * v->charge_gap[cn];
+        double distance2 = gapNum * gapNum * gap2;
+        if (p.b_ij < 0 && p.r_2 < distance2 + ZERO) gapNum--;
+        else if (p.b_ij > 0 && p.r_2 > (gapNum + 1) * (gapNum + 1) * gap2 - ZERO) gapNum++;
+        p.upperPotential = v->charge_potgrad[cn] * charge;
+        p.longlimit2 = (gapNum + 1) * (gapNum + 1) * gap2;
+        p.lowerPotential = -1 * v->charge_potgrad[cn] * charge;
+        p.shortlimit2 = gapNum * gapNum * gap2;
+        if (p.b_ij < 0 && calc_disc(&p) > 0) {
+            p.s_time = -1; p.d_ij2 = p.shortlimit2; ev.potential = p.lowerPotential; ev.sub = SDMD_SUB_TBDCAPTR;
+        } else {
+            p.s_time = 1; p.d_ij2 = p.longlimit2; ev.potential = p.upperPotential; ev.sub = SDMD_SUB_TBDESCAP;
+        }
+        ev.time = calc_time(&p);
+        if (ev.time < 0) ev.time = INF;
+        if (job_assign(c, i, 0, &ev, SDMD_EV_CHRG)) v->ev_partner[i] = -100 * cn;
+    }
+}
+
 /* SphObstTime, TimePrediction.c:1020-1071: hard sphere at rest, core collision only */
 static void sphobst_time(oracle_ctx *c, int i) {
     struct sdmd_host_view *v = c->v;
@@ -773,6 +811,7 @@ void oracle_predict(oracle_ctx *c, const int32_t *renew) {
         if (v->wall_kind) wall_time(c, i);                       /* SGThread.c:183-185 */
         if (v->n_obst) obst_time(c, i);                          /* :187-189 */
         if (v->n_tunnel) tunnel_time(c, i);                      /* :197-199 */
+        if (v->flow_mark == 3) charge_time(c, i);                /* :201-203 */
         if (v->n_sphobst) sphobst_time(c, i);                    /* :205-207 */
     }
 }
@@ -1003,13 +1042,21 @@ static void hb_event(oracle_ctx *c, int i, int j, int ni, int nj) {
 static void thermostat_event(oracle_ctx *c, int i) {
     struct sdmd_host_view *v = c->v;
     double speed[3];
+    double netV[3] = {0, 0, 0};
+    if (v->charge_com && v->flow_mark == 3) {       /* CalCOMV of the atom's chain from the raw velocities, Events.c:400-402 */
+        int a = i, b = i;
+        while (a > 1 && v->protein_num[a - 1] == v->protein_num[i]) a--;
+        while (b < c->n && v->protein_num[b + 1] == v->protein_num[i]) b++;
+        for (int n = a; n <= b; n++) { netV[0] += v->vx[n] * v->mass[n]; netV[1] += v->vy[n] * v->mass[n]; netV[2] += v->vz[n] * v->mass[n]; }
+        for (int k = 0; k < 3; k++) netV[k] /= v->protein_mass[i];
+    }
     for (int k = 0; k < 3; k++) {
         do {
             double variance = v->target_temperature / v->mass[i];
             speed[k] = next_gauss(c) * sqrt(variance) + 0;
-            /* flow terms, Events.c:408-410 (netV only exists with charge sources) */
+            /* flow terms, Events.c:408-410 */
             double a = v->flow_a ? v->flow_a[3 * i + k] : 0.0, rec = v->flow_time_rec ? v->flow_time_rec[i] : 0.0;
-            speed[k] += v->flow_v[k] + 0.0 + a * (c->st.currenttime - rec);
+            speed[k] += v->flow_v[k] + netV[k] + a * (c->st.currenttime - rec);
         } while (speed[k] == 0 && !c->st.error);
     }
     v->vx[i] = speed[0]; v->vy[i] = speed[1]; v->vz[i] = speed[2];
@@ -1102,6 +1149,31 @@ static void obst_event(oracle_ctx *c, int i, int sph) {
     v->vx[i] = v->vx[i] + phi * r[0]; v->vy[i] = v->vy[i] + phi * r[1]; v->vz[i] = v->vz[i] + phi * r[2];
 }
 
+/* ChargeEvent, Events.c:685-749 */
+static void charge_event(oracle_ctx *c, int i) {
+    struct sdmd_host_view *v = c->v;
+    int cn = v->ev_partner[i] / -100;
+    double r[3] = {v->x[i] - v->charge_pos[cn][0], v->y[i] - v->charge_pos[cn][1], v->z[i] - v->charge_pos[cn][2]};
+    double vv[3] = {v->vx[i] - v->charge_vel[cn][0], v->vy[i] - v->charge_vel[cn][1], v->vz[i] - v->charge_vel[cn][2]};
+    double d_ij2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    double b_ij = r[0] * vv[0] + r[1] * vv[1] + r[2] * vv[2];
+    double mass = v->mass[i];
+    double potential = v->ev_potential[i];
+    int s_vel = 0;
+    switch (v->ev_sub[i]) {
+        case SDMD_SUB_TBDCAPTR:
+            if (b_ij * b_ij - 2 * d_ij2 * potential / mass <= 0) { potential = 0; s_vel = 1; } else s_vel = -1;
+            break;
+        case SDMD_SUB_TBDESCAP:
+            if (b_ij * b_ij - 2 * d_ij2 * potential / mass <= 0) { potential = 0; s_vel = -1; } else s_vel = 1;
+            break;
+        default: c->st.error = SDMD_ERR_STATE; return;
+    }
+    double phi = (-1 * b_ij + s_vel * sqrt(b_ij * b_ij - 2 * d_ij2 * potential / mass)) / d_ij2;
+    if (phi != phi) { c->st.error = SDMD_ERR_STATE; return; }
+    v->vx[i] = v->vx[i] + phi * r[0]; v->vy[i] = v->vy[i] + phi * r[1]; v->vz[i] = v->vz[i] + phi * r[2];
+}
+
 /* TunnelEvent, Events.c:621-682: WallEvent's kick with the separation taken from the tunnel's axis */
 static void tunnel_event(oracle_ctx *c, int i) {
     struct sdmd_host_view *v = c->v;
@@ -1147,6 +1219,7 @@ static void do_event(oracle_ctx *c, int i, int j) {
         case SDMD_EV_WALL: wall_event(c, i); c->st.wall++; break;
         case SDMD_EV_OBST: obst_event(c, i, 0); c->st.wall++; break;
         case SDMD_EV_TUNL: tunnel_event(c, i); c->st.wall++; break;
+        case SDMD_EV_CHRG: charge_event(c, i); break;                       /* no counter, Events.c:93-95 */
         case SDMD_EV_SPHO: obst_event(c, i, 1); c->st.wall++; break;
         default: c->st.error = SDMD_ERR_STATE; break;
     }

@@ -1203,7 +1203,7 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
         for (int k = 0; k < 4; k++) P.tun_pos[n][k] = v->tunnel_pos[n][k];
     }
     for (int n = 0; n < v->n_obst; n++) P.obst_hole[n] = v->obst_hole[n];
-    P.single_body = P.wall_kind != 0 || P.n_obst > 0 || P.n_sphobst > 0 || P.n_tunnel > 0;
+    P.single_body = P.wall_kind != 0 || P.n_obst > 0 || P.n_sphobst > 0 || P.n_tunnel > 0 || v->flow_mark == 3;
     P.thermostat_on = v->thermostat_on;
     P.method_ding = v->method_ding;
     P.hydrogen_bond = v->hydrogen_bond;
@@ -1225,7 +1225,19 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     TRY(dupload(c, &P.x, v->x, n1)); TRY(dupload(c, &P.y, v->y, n1)); TRY(dupload(c, &P.z, v->z, n1));
     TRY(dupload(c, &P.vx, v->vx, n1)); TRY(dupload(c, &P.vy, v->vy, n1)); TRY(dupload(c, &P.vz, v->vz, n1));
     TRY(dupload(c, (double **)&P.mass, v->mass, n1));
-    if (v->flow_mark < 0 || v->flow_mark > 2) return set_err(SDMD_ERR_UNSUPPORTED, "flow type (charge sources are not supported)");
+    if (v->flow_mark < 0 || v->flow_mark > 3) return set_err(SDMD_ERR_BAD_ARG, "flow type");
+    if (v->n_charge < 0 || v->n_charge > SDMD_MAX_CHARGE) return set_err(SDMD_ERR_UNSUPPORTED, "more charge sources than SDMD_MAX_CHARGE");
+    if (v->flow_mark == 3) {
+        if (!v->charge) return set_err(SDMD_ERR_BAD_ARG, "flow_mark 3 needs per-atom charges");
+        TRY(dupload(c, (double **)&P.charge, v->charge, n1));
+        P.n_charge = v->n_charge;
+        P.charge_com = v->charge_com;
+        for (int q = 0; q < v->n_charge; q++) {
+            for (int k = 0; k < 3; k++) { P.chg_pos[q][k] = v->charge_pos[q][k]; P.chg_vel[q][k] = v->charge_vel[q][k]; }
+            P.chg_grad[q] = v->charge_potgrad[q];
+            P.chg_gap[q] = v->charge_gap[q];
+        }
+    }
     P.flow_mark = v->flow_mark;
     for (int k = 0; k < 3; k++) P.flow_v[k] = v->flow_v[k];
     if (v->flow_mark) {

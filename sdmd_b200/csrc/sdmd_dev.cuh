@@ -85,6 +85,9 @@ struct DevP {
     const double *flow_a;      // 3 per atom or NULL
     double *flow_time_rec;     // per atom or NULL
     const double *protein_mass;
+    const double *charge;      // per atom or NULL (charge sources: flow_mark == 3)
+    int n_charge, charge_com;
+    double chg_pos[SDMD_MAX_CHARGE][3], chg_vel[SDMD_MAX_CHARGE][3], chg_grad[SDMD_MAX_CHARGE], chg_gap[SDMD_MAX_CHARGE];
     int n_tunnel, tunnel_type; // tunnels through (holed) obstruction walls
     int obst_hole[SDMD_MAX_OBST];
     double tun_pos[SDMD_MAX_OBST][4], tun_diam[SDMD_MAX_OBST];

@@ -868,6 +868,39 @@ __device__ inline void d_obst_time(const DevP &D, const Self &me, Slot &cur) {
     }
 }
 
+// ChargeTime, TimePrediction.c:933-1017: concentric potential steps of width `gap` around each charge source, partner code -100 n
+__device__ inline void d_charge_time(const DevP &D, const Self &me, Slot &cur) {
+    if (!D.charge) return;
+    const double charge = D.charge[me.i];
+    if (!charge) return;
+    int flag = 0;
+    for (int cn = 0; cn < D.n_charge; cn++) {
+        if (me.x > D.chg_pos[cn][0] - SD_ZERO) continue;
+        if (D.chg_pos[cn][0] < D.box[0]) flag = 1;                                   // :948-956
+        else if (!(flag == 0 && D.chg_pos[cn][0] > D.box[0])) break;
+        Pair p;
+        p.rx = me.x - D.chg_pos[cn][0]; p.ry = me.y - D.chg_pos[cn][1]; p.rz = me.z - D.chg_pos[cn][2];
+        double vx = me.vx - D.chg_vel[cn][0], vy = me.vy - D.chg_vel[cn][1], vz = me.vz - D.chg_vel[cn][2];
+        p.r2 = p.rx * p.rx + p.ry * p.ry + p.rz * p.rz;
+        p.b = p.rx * vx + p.ry * vy + p.rz * vz;
+        p.v2 = vx * vx + vy * vy + vz * vz;
+        int gapNum = (int)(sqrt(p.r2) / D.chg_gap[cn]);
+        const double gap2 = D.chg_gap[cn] * D.chg_gap[cn];
+        const double distance2 = (gapNum * gapNum) * gap2;
+        if (p.b < 0 && p.r2 < distance2 + SD_ZERO) gapNum--;
+        else if (p.b > 0 && p.r2 > ((gapNum + 1) * (gapNum + 1)) * gap2 - SD_ZERO) gapNum++;
+        const double upPot = D.chg_grad[cn] * charge, long2 = ((gapNum + 1) * (gapNum + 1)) * gap2;
+        const double lowPot = -1 * D.chg_grad[cn] * charge, short2 = (gapNum * gapNum) * gap2;
+        int s, sub;
+        double d2, pot;
+        if (p.b < 0 && d_disc(p, short2) > 0) { s = -1; d2 = short2; pot = lowPot; sub = SDMD_SUB_TBDCAPTR; }
+        else { s = 1; d2 = long2; pot = upPot; sub = SDMD_SUB_TBDESCAP; }
+        double t = d_time(p, s, d2);
+        if (t < 0) t = SD_INF;
+        if (d_job_assign(D, cur, 0, t, pot, sub, SDMD_EV_CHRG)) cur.partner = -100 * cn;
+    }
+}
+
 // SphObstTime, TimePrediction.c:1020-1071: hard sphere at rest, core collision only, partner code -1000 n
 __device__ inline void d_sphobst_time(const DevP &D, const Self &me, Slot &cur) {
     for (int n = 0; n < D.n_sphobst; n++) {
@@ -948,6 +981,7 @@ __device__ inline Slot d_predict_atom(const DevP &D, const SlotSrc &S, int i, Sl
         if (D.wall_kind) d_wall_time(D, me, cur);
         if (D.n_obst) d_obst_time(D, me, cur);
         if (D.n_tunnel) d_tunnel_time(D, me, cur);
+        if (D.flow_mark == 3) d_charge_time(D, me, cur);
         if (D.n_sphobst) d_sphobst_time(D, me, cur);
     }
     *npair = me.npair;
@@ -1260,6 +1294,32 @@ __device__ inline void d_obst_event(const DevP &D, int i, bool sph) {
     D.vx[i] = spd[0] + phi * r[0]; D.vy[i] = spd[1] + phi * r[1]; D.vz[i] = spd[2] + phi * r[2];
 }
 
+// ChargeEvent, Events.c:685-749
+__device__ inline void d_charge_event(const DevP &D, int i) {
+    int cn = D.ev_partner[i] / -100;
+    if (cn < 0 || cn >= D.n_charge) { D.ctl->error = SDMD_ERR_STATE; return; }
+    double tvx = D.vx[i], tvy = D.vy[i], tvz = D.vz[i];
+    double rx = D.x[i] - D.chg_pos[cn][0], ry = D.y[i] - D.chg_pos[cn][1], rz = D.z[i] - D.chg_pos[cn][2];
+    double vx = tvx - D.chg_vel[cn][0], vy = tvy - D.chg_vel[cn][1], vz = tvz - D.chg_vel[cn][2];
+    double d2 = rx * rx + ry * ry + rz * rz;
+    double b = rx * vx + ry * vy + rz * vz;
+    double mass = D.mass[i];
+    double pot = D.ev_pot[i];
+    int s_vel = 0;
+    switch (D.ev_sub[i]) {
+        case SDMD_SUB_TBDCAPTR:
+            if (b * b - 2 * d2 * pot / mass <= 0) { pot = 0; s_vel = 1; } else s_vel = -1;
+            break;
+        case SDMD_SUB_TBDESCAP:
+            if (b * b - 2 * d2 * pot / mass <= 0) { pot = 0; s_vel = -1; } else s_vel = 1;
+            break;
+        default: D.ctl->error = SDMD_ERR_STATE; return;
+    }
+    double phi = (-1 * b + s_vel * sqrt(b * b - 2 * d2 * pot / mass)) / d2;
+    if (phi != phi) { D.ctl->error = SDMD_ERR_STATE; return; }
+    D.vx[i] = tvx + phi * rx; D.vy[i] = tvy + phi * ry; D.vz[i] = tvz + phi * rz;
+}
+
 // TunnelEvent, Events.c:621-682: WallEvent's kick with the separation taken from the tunnel's axis
 __device__ inline void d_tunnel_event(const DevP &D, int i) {
     int n = D.ev_partner[i] / -10000;
@@ -1292,13 +1352,21 @@ __device__ inline void d_thermostat_event(const DevP &D, int i) {
     double speed[3];
     double variance = D.ctl->temperature / D.mass[i];
     double sd = sqrt(variance);
+    double netV[3] = {0, 0, 0};
+    if (D.charge_com && D.flow_mark == 3) {   // CalCOMV of the atom's chain from the raw velocities, Events.c:400-402
+        int a = i, b = i;
+        while (a > 1 && D.protein[a - 1] == D.protein[i]) a--;
+        while (b < D.n && D.protein[b + 1] == D.protein[i]) b++;
+        for (int n = a; n <= b; n++) { netV[0] += D.vx[n] * D.mass[n]; netV[1] += D.vy[n] * D.mass[n]; netV[2] += D.vz[n] * D.mass[n]; }
+        for (int k = 0; k < 3; k++) netV[k] /= D.protein_mass[i];
+    }
 #pragma unroll 1
     for (int k = 0; k < 3; k++) {
-        // flow terms, Events.c:408-410 (netV only exists with charge sources)
+        // flow terms, Events.c:408-410
         const double a = D.flow_a ? D.flow_a[3 * i + k] : 0.0, rec = D.flow_time_rec ? D.flow_time_rec[i] : 0.0;
         do {
             speed[k] = d_next_gauss(D) * sd + 0;
-            speed[k] += D.flow_v[k] + 0.0 + a * (D.ctl->currenttime - rec);
+            speed[k] += D.flow_v[k] + netV[k] + a * (D.ctl->currenttime - rec);
         } while (speed[k] == 0 && !D.ctl->error);
     }
     D.vx[i] = speed[0]; D.vy[i] = speed[1]; D.vz[i] = speed[2];
@@ -1372,6 +1440,7 @@ __device__ inline void d_do_event(const DevP &D, int i, int j) {
         case SDMD_EV_WALL: d_wall_event(D, i); c->n_wall++; break;
         case SDMD_EV_OBST: d_obst_event(D, i, false); c->n_wall++; break;
         case SDMD_EV_TUNL: d_tunnel_event(D, i); c->n_wall++; break;
+        case SDMD_EV_CHRG: d_charge_event(D, i); break;   // no counter, Events.c:93-95
         case SDMD_EV_SPHO: d_obst_event(D, i, true); c->n_wall++; break;
         default: c->error = SDMD_ERR_STATE; break;
     }
@@ -2057,6 +2126,7 @@ __device__ inline void d_predict_cta(const DevP &D, PredShared &sh) {
                         if (D.wall_kind) d_wall_time(D, me, w);
                         if (D.n_obst) d_obst_time(D, me, w);
                         if (D.n_tunnel) d_tunnel_time(D, me, w);
+                        if (D.flow_mark == 3) d_charge_time(D, me, w);
                         if (D.n_sphobst) d_sphobst_time(D, me, w);
                         sh.result[a] = w;
                     }

@@ -143,7 +143,18 @@ int sdmd_glue_flatten(struct sdmd_host_view *v) {
     v->gel_mode = 1;
 #endif
     /* features that live outside the hot-path scope (rough / moving walls, obstacles, tunnels, flow, CG) */
-    if (flow.mark > 2 || CG.mark || strcmp(wallDyn.mark, "no")) return SDMD_ERR_UNSUPPORTED;
+    if (CG.mark || strcmp(wallDyn.mark, "no")) return SDMD_ERR_UNSUPPORTED;
+    if (flow.mark == 3) {
+        int total = flow.charge.PBCMark ? flow.charge.num : flow.charge.num / 2;     /* TimePrediction.c:936 */
+        if (total > SDMD_MAX_CHARGE) return SDMD_ERR_UNSUPPORTED;
+        v->n_charge = total;
+        v->charge_com = chargeAA[COM];
+        for (int n = 0; n < total; n++) {
+            for (int k = 0; k < 3; k++) { v->charge_pos[n][k] = flow.charge.position[n][k + 1]; v->charge_vel[n][k] = flow.charge.velocity[n][k + 1]; }
+            v->charge_potgrad[n] = flow.charge.potGrad[n];
+            v->charge_gap[n] = flow.charge.gap[n];
+        }
+    }
     v->flow_mark = flow.mark;
     for (int k = 0; k < 3; k++) v->flow_v[k] = flow.constV.v[k + 1];
     /* flat obstruction walls, tunnels through them, hard spherical obstacles */
@@ -194,7 +205,11 @@ int sdmd_glue_flatten(struct sdmd_host_view *v) {
     ALLOC(v->ev_counter, n + 1); ALLOC(v->ev_pcounter, n + 1); ALLOC(v->ev_type, n + 1); ALLOC(v->ev_sub, n + 1);
     ALLOC(v->cell_idx, 3 * (n + 1));
     ALLOC(v->flow_a, 3 * (n + 1)); ALLOC(v->flow_time_rec, n + 1); ALLOC(v->protein_mass, n + 1);
-    for (int i = 1; i <= n; i++) v->protein_mass[i] = protein[atom[i].property->sequence.proteinNum].mass;
+    ALLOC(v->charge, n + 1);
+    for (int i = 1; i <= n; i++) {
+        v->protein_mass[i] = protein[atom[i].property->sequence.proteinNum].mass;
+        v->charge[i] = atom[i].property->charge;
+    }
     if (flow.force.a)
         for (int i = 1; i <= n; i++)
             for (int k = 0; k < 3; k++) v->flow_a[3 * i + k] = flow.force.a[i][k + 1];
@@ -283,7 +298,7 @@ void sdmd_glue_free(struct sdmd_host_view *v) {
     free(v->hb_bond); free(v->hb_neighbor); free(v->hb_role); free(v->hb_itype);
     free(v->hbn_partner); free(v->hbn_partner_num); free(v->hbn_status);
     free(v->ev_time); free(v->ev_potential); free(v->ev_partner); free(v->ev_counter); free(v->ev_pcounter);
-    free(v->ev_type); free(v->ev_sub); free(v->cell_idx); free(v->flow_a); free(v->flow_time_rec); free(v->protein_mass);
+    free(v->ev_type); free(v->ev_sub); free(v->cell_idx); free(v->flow_a); free(v->flow_time_rec); free(v->protein_mass); free(v->charge);
     free(v->bond_off); free(v->bond_j); free(v->bond_dmin2); free(v->bond_dmax2);
     free(v->con_off); free(v->con_j); free(v->con_table);
     free(v->cm_off); free(v->cm_j); free(v->cm_flags);
@@ -355,9 +370,15 @@ void sdmd_snap_put_view(sdmd_snap *s, const struct sdmd_host_view *v) {
     PUT(ev_time, "f8", n1); PUT(ev_potential, "f8", n1); PUT(ev_partner, "i4", n1);
     PUT(ev_counter, "i8", n1); PUT(ev_pcounter, "i8", n1); PUT(ev_type, "u1", n1); PUT(ev_sub, "u1", n1);
     PUT(cell_idx, "i4", 3 * n1);
-    PUT(flow_a, "f8", 3 * n1); PUT(flow_time_rec, "f8", n1); PUT(protein_mass, "f8", n1);
-    int32_t flow_i[1] = {v->flow_mark};
-    sdmd_snap_put(s, "flow_i4", "i4", flow_i, 1);
+    PUT(flow_a, "f8", 3 * n1); PUT(flow_time_rec, "f8", n1); PUT(protein_mass, "f8", n1); PUT(charge, "f8", n1);
+    int32_t flow_i[2] = {v->flow_mark, v->charge_com};
+    sdmd_snap_put(s, "flow_i4", "i4", flow_i, 2);
+    double csrc[SDMD_MAX_CHARGE][8];
+    for (int q = 0; q < v->n_charge; q++) {
+        for (int k = 0; k < 3; k++) { csrc[q][k] = v->charge_pos[q][k]; csrc[q][3 + k] = v->charge_vel[q][k]; }
+        csrc[q][6] = v->charge_potgrad[q]; csrc[q][7] = v->charge_gap[q];
+    }
+    sdmd_snap_put(s, "charge_src", "f8", csrc, 8 * (uint64_t)v->n_charge);
     sdmd_snap_put(s, "flow_f8", "f8", v->flow_v, 3);
     PUT(bond_off, "i4", n1 + 1); PUT(bond_j, "i4", v->bond_off[n + 1]);
     PUT(bond_dmin2, "f8", v->bond_off[n + 1]); PUT(bond_dmax2, "f8", v->bond_off[n + 1]);

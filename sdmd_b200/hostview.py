@@ -13,7 +13,8 @@ from pathlib import Path
 
 import numpy as np
 
-ABI_VERSION = 5
+ABI_VERSION = 6
+MAX_CHARGE = 8
 MAX_OBST = 4
 NT = 33
 NHBCLASS = 12
@@ -66,6 +67,9 @@ class CHostView(C.Structure):
         ("tunnel_pos", C.c_double * (4 * MAX_OBST)), ("tunnel_diameter", C.c_double * MAX_OBST), ("obst_hole", C.c_int32 * MAX_OBST),
         ("flow_mark", C.c_int32), ("pad_flow_", C.c_int32), ("flow_v", C.c_double * 3),
         ("flow_a", _P(C.c_double)), ("flow_time_rec", _P(C.c_double)), ("protein_mass", _P(C.c_double)),
+        ("charge", _P(C.c_double)), ("n_charge", C.c_int32), ("charge_com", C.c_int32),
+        ("charge_pos", C.c_double * (3 * MAX_CHARGE)), ("charge_vel", C.c_double * (3 * MAX_CHARGE)),
+        ("charge_potgrad", C.c_double * MAX_CHARGE), ("charge_gap", C.c_double * MAX_CHARGE),
     ]
 
 
@@ -95,7 +99,7 @@ PER_ATOM = [
     ("hbn_partner", "i4", 5), ("hbn_partner_num", "i4", 1), ("hbn_status", "i4", 1),
     ("ev_time", "f8", 1), ("ev_potential", "f8", 1), ("ev_partner", "i4", 1), ("ev_counter", "i8", 1),
     ("ev_pcounter", "i8", 1), ("ev_type", "u1", 1), ("ev_sub", "u1", 1), ("cell_idx", "i4", 3),
-    ("flow_a", "f8", 3), ("flow_time_rec", "f8", 1), ("protein_mass", "f8", 1),
+    ("flow_a", "f8", 3), ("flow_time_rec", "f8", 1), ("protein_mass", "f8", 1), ("charge", "f8", 1),
 ]
 MUTABLE = ["x", "y", "z", "vx", "vy", "vz", "type", "hb_bond", "hb_itype", "hbn_partner", "hbn_partner_num",
            "hbn_status", "ev_time", "ev_potential", "ev_partner", "ev_counter", "ev_pcounter", "ev_type", "ev_sub",
@@ -162,6 +166,8 @@ class HostView:
         self.obst_hole = np.zeros(0, dtype=np.int32)
         self.flow_mark = 0          # 0 none, 1 constant drift velocity, 2 constant force
         self.flow_v = np.zeros(3)
+        self.charge_com = 0
+        self.charge_src = np.zeros((0, 8))   # per charge source: position (3), velocity (3), potential gradient, gap
         for name, dt, k in PER_ATOM:
             setattr(self, name, np.zeros(n1 * k, dtype=_NP[dt]))
         for name in ("bond_off", "con_off", "cm_off"):
@@ -204,13 +210,16 @@ class HostView:
         if "flow_f8" in d:
             hv.flow_mark = int(d["flow_i4"][0])
             hv.flow_v = np.asarray(d["flow_f8"], dtype=np.float64)[:3].copy()
+        if "charge_src" in d:
+            hv.charge_src = np.asarray(d["charge_src"], dtype=np.float64).reshape(-1, 8).copy()
+            hv.charge_com = int(d["flow_i4"][1]) if len(d["flow_i4"]) > 1 else 0
         for name, dt in OTHER:
             arr = np.ascontiguousarray(d[name], dtype=_NP[dt]).copy()
             setattr(hv, name, arr if arr.size else np.zeros(1, dtype=_NP[dt]))
         hv.tables = np.frombuffer(d["tables"].tobytes(), dtype=STEP_TABLE_DTYPE).copy()
         known = {n for n, _, _ in PER_ATOM} | {n for n, _ in OTHER} | {"scalars_i4", "scalars_f8", "scalars_i8", "tables", "wall_i4", "wall_f8",
                                                                            "obst_pos", "obst_type", "sphobst_pos", "sphobst_radius",
-                                                                           "tunnel_pos", "tunnel_diameter", "tunnel_i4", "obst_hole", "flow_i4", "flow_f8"}
+                                                                           "tunnel_pos", "tunnel_diameter", "tunnel_i4", "obst_hole", "flow_i4", "flow_f8", "charge_src"}
         hv.extra = {k: v for k, v in d.items() if k not in known}
         return hv
 
@@ -239,7 +248,8 @@ class HostView:
             "tunnel_diameter": np.asarray(self.tunnel_diameter, dtype=np.float64),
             "tunnel_i4": np.array([self.tunnel_type], dtype=np.int32),
             "obst_hole": np.asarray(self.obst_hole, dtype=np.int32),
-            "flow_i4": np.array([self.flow_mark], dtype=np.int32),
+            "flow_i4": np.array([self.flow_mark, self.charge_com], dtype=np.int32),
+            "charge_src": np.asarray(self.charge_src, dtype=np.float64).reshape(-1),
             "flow_f8": np.asarray(self.flow_v, dtype=np.float64),
             "tables": np.frombuffer(self.tables.tobytes(), dtype=np.uint8),
         }
@@ -284,6 +294,13 @@ class HostView:
         for k, v in enumerate(self.sphobst_radius):
             c.sphobst_radius[k] = float(v)
         c.flow_mark = int(self.flow_mark)
+        cs = np.asarray(self.charge_src, dtype=np.float64).reshape(-1, 8)
+        assert len(cs) <= MAX_CHARGE
+        c.n_charge, c.charge_com = len(cs), int(self.charge_com)
+        for n, row in enumerate(cs):
+            for k in range(3):
+                c.charge_pos[3 * n + k] = float(row[k]); c.charge_vel[3 * n + k] = float(row[3 + k])
+            c.charge_potgrad[n] = float(row[6]); c.charge_gap[n] = float(row[7])
         c.flow_v[:] = [float(v) for v in self.flow_v]
         c.n_tunnel, c.tunnel_type = len(self.tunnel_diameter), int(self.tunnel_type)
         assert c.n_tunnel <= MAX_OBST

@@ -109,9 +109,11 @@ def test_dropin_walled_run_matches_reference(tmp_path, wall_type):
     assert _counter(outs["gpu"], "Wall times") > 0
 
 
-@pytest.mark.parametrize("flow", ["velocity 0.02 0.0 0.01", "force 5.0 0.0 0.0"], ids=["velocity", "force"])
+@pytest.mark.parametrize("flow", ["velocity 0.02 0.0 0.01", "force 5.0 0.0 0.0", "charge 1 : 100.0 75.0 75.0 0.05 0.2"],
+                         ids=["velocity", "force", "charge"])
 def test_dropin_flow_run_matches_reference(tmp_path, flow):
-    """"Flow velocity ..." / "Flow force ..." (drift terms in ThermostatEvent and in the temperature CalKinetE reports): the
+    """"Flow velocity ..." / "Flow force ..." / "Flow charge ..." (drift terms in ThermostatEvent and in the temperature CalKinetE
+    reports; charge sources with their own predictor and event): the
     drop-in driver writes the same trajectory, energies and counters as the stock binary."""
     if not (REF / "sDMD_ref").exists() or not DROPIN.exists():
         pytest.skip("needs oracle/_ref/sDMD_ref and the drop-in driver")
@@ -121,7 +123,8 @@ def test_dropin_flow_run_matches_reference(tmp_path, flow):
         work = tmp_path / tag
         work.mkdir()
         inp = prepare_input(work, time_units=150, flow=flow)
-        r = subprocess.run([str(binary), "-f", "ala10.gro", "-i", str(inp), "-o", str(work / "out")],
+        extra = ["-COM"] if flow.startswith("charge") else []      # charge sources: also the centre-of-mass thermostat term
+        r = subprocess.run([str(binary), "-f", "ala10.gro", "-i", str(inp), "-o", str(work / "out"), *extra],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         outs[tag] = r.stdout.replace("\r", "\n")

@@ -50,7 +50,7 @@ def test_predict_all_and_cbt_match_reference(capi, case):
     assert r.kinetic_energy() == post.extra["ekin"][0]
 
 
-@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8", "ala10x8_wallp", "ala10x4_wallc", "ala10x8_obst", "abeta8", "ala10x4_tunnel", "ala10_flowv", "ala10_flowf"])
+@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8", "ala10x8_wallp", "ala10x4_wallc", "ala10x8_obst", "abeta8", "ala10x4_tunnel", "ala10_flowv", "ala10_flowf", "ala10_charge"])
 @pytest.mark.parametrize("loop_mode", [1, 4, 2, 3], ids=["one_cta", "cluster", "sweep_overlapped", "sweep_serial"])
 def test_device_event_loop_matches_reference(capi, case, loop_mode):
     """loop_mode 4 forces the mid-size driver (one thread-block cluster) and 2 / 3 force the large-system drivers (grid-wide sweep overlapped with / followed by one event block per
@@ -78,6 +78,8 @@ def test_device_event_loop_matches_reference(capi, case, loop_mode):
     got = [st[k] for k in ("frame", "iterations", "count_recal", "collision", "bond", "hb", "hb_neighbor", "thermostat", "pcc")]
     assert got == ref
     assert r.potential_energy() == fin.extra["epot"][0]
+    if "charge" in case:   # charge sources: ChargeTime / ChargeEvent, centre-of-mass term of ThermostatEvent (-COM)
+        assert r.kinetic_energy() == fin.extra["ekin"][0] and (tr["type"] == 8).sum() > 0
     if "flow" in case:   # drift velocity / constant force terms of ThermostatEvent and CalKinetE
         assert r.kinetic_energy() == fin.extra["ekin"][0]
         assert_fields_equal(hv, fin, ("flow_time_rec",))

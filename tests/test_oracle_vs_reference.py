@@ -47,7 +47,7 @@ def test_predict_all_and_cbt(case):
     assert o.kinetic_energy() == post.extra["ekin"][0]
 
 
-@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8", "ala10x8_wallp", "ala10x4_wallc", "ala10x8_obst", "abeta8", "ala10x4_tunnel", "ala10_flowv", "ala10_flowf"])
+@pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8", "ala10x8_wallp", "ala10x4_wallc", "ala10x8_obst", "abeta8", "ala10x4_tunnel", "ala10_flowv", "ala10_flowf", "ala10_charge"])
 def test_event_loop_trace(case):
     pre, post, fin = load_case(case)
     hv, o = _prepare(pre)
@@ -73,6 +73,11 @@ def test_event_loop_trace(case):
         # smooth confining wall: WallTime runs in every prediction, WallEvent a few times
         assert pre.wall_kind in (1, 2) and st["wall"] == int(ref[11]) and st["wall"] > 0
         assert (want["type"] == 5).sum() >= st["wall"]
+    if "charge" in case:
+        # charge source + periodic image, -COM: ChargeTime / ChargeEvent (partner code -100 n), centre-of-mass term in ThermostatEvent
+        assert pre.flow_mark == 3 and pre.charge_com == 1 and len(pre.charge_src) == 2
+        assert ((want["type"] == 8) & (want["executed"] == 1)).sum() > 0
+        assert o.kinetic_energy() == fin.extra["ekin"][0]
     if "flow" in case:
         # drift velocity / constant force: extra terms where the thermostat redraws a velocity, CalKinetE relative to the drift
         # (flowv) or to the chain's centre of mass (flowf), timeRec bookkeeping
