@@ -1158,6 +1158,8 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     size_t n1 = (size_t)n + 1;
     DevP &P = c->P;
     memset(&P, 0, sizeof(P));
+    SingleBody SB;
+    memset(&SB, 0, sizeof(SB));
     P.n = n;
     // CreateCell, Initialization.c:1060-1073
     for (int k = 0; k < 3; k++) {
@@ -1187,22 +1189,22 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     P.n_sphobst = v->n_sphobst;
     for (int n = 0; n < v->n_obst; n++) {
         if (v->obst_type[n] < 1 || v->obst_type[n] > SDMD_NATOMTYPE) return set_err(SDMD_ERR_BAD_ARG, "bad obst_type");
-        P.obst_type[n] = v->obst_type[n];
-        for (int k = 0; k < 3; k++) P.obst_pos[n][k] = v->obst_pos[n][k];
+        SB.obst_type[n] = v->obst_type[n];
+        for (int k = 0; k < 3; k++) SB.obst_pos[n][k] = v->obst_pos[n][k];
     }
     for (int n = 0; n < v->n_sphobst; n++) {
-        P.sph_r[n] = v->sphobst_radius[n];
-        for (int k = 0; k < 3; k++) P.sph_pos[n][k] = v->sphobst_pos[n][k];
+        SB.sph_r[n] = v->sphobst_radius[n];
+        for (int k = 0; k < 3; k++) SB.sph_pos[n][k] = v->sphobst_pos[n][k];
     }
     if (v->n_tunnel < 0 || v->n_tunnel > SDMD_MAX_OBST) return set_err(SDMD_ERR_UNSUPPORTED, "more tunnels than SDMD_MAX_OBST");
     if (v->n_tunnel && (v->tunnel_type < 1 || v->tunnel_type > SDMD_NATOMTYPE)) return set_err(SDMD_ERR_BAD_ARG, "bad tunnel_type");
     P.n_tunnel = v->n_tunnel;
     P.tunnel_type = v->tunnel_type;
     for (int n = 0; n < v->n_tunnel; n++) {
-        P.tun_diam[n] = v->tunnel_diameter[n];
-        for (int k = 0; k < 4; k++) P.tun_pos[n][k] = v->tunnel_pos[n][k];
+        SB.tun_diam[n] = v->tunnel_diameter[n];
+        for (int k = 0; k < 4; k++) SB.tun_pos[n][k] = v->tunnel_pos[n][k];
     }
-    for (int n = 0; n < v->n_obst; n++) P.obst_hole[n] = v->obst_hole[n];
+    for (int n = 0; n < v->n_obst; n++) SB.obst_hole[n] = v->obst_hole[n];
     P.single_body = P.wall_kind != 0 || P.n_obst > 0 || P.n_sphobst > 0 || P.n_tunnel > 0 || v->flow_mark == 3;
     P.thermostat_on = v->thermostat_on;
     P.method_ding = v->method_ding;
@@ -1233,9 +1235,9 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
         P.n_charge = v->n_charge;
         P.charge_com = v->charge_com;
         for (int q = 0; q < v->n_charge; q++) {
-            for (int k = 0; k < 3; k++) { P.chg_pos[q][k] = v->charge_pos[q][k]; P.chg_vel[q][k] = v->charge_vel[q][k]; }
-            P.chg_grad[q] = v->charge_potgrad[q];
-            P.chg_gap[q] = v->charge_gap[q];
+            for (int k = 0; k < 3; k++) { SB.chg_pos[q][k] = v->charge_pos[q][k]; SB.chg_vel[q][k] = v->charge_vel[q][k]; }
+            SB.chg_grad[q] = v->charge_potgrad[q];
+            SB.chg_gap[q] = v->charge_gap[q];
         }
     }
     P.flow_mark = v->flow_mark;
@@ -1247,6 +1249,7 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
         if (v->protein_mass) TRY(dupload(c, (double **)&P.protein_mass, v->protein_mass, n1));
         else if (v->flow_mark >= 2) return set_err(SDMD_ERR_BAD_ARG, "flow_mark >= 2 needs protein_mass");
     }
+    if (P.single_body) TRY(dupload(c, (SingleBody **)&P.sb, &SB, 1));
     TRY(dupload(c, &P.type, v->type, n1));
     TRY(dupload(c, (int **)&P.aa_type, v->aa_type, n1));
     TRY(dupload(c, (int **)&P.protein, v->protein_num, n1));

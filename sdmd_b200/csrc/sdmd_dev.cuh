@@ -69,6 +69,15 @@ struct __align__(16) SRec {
     unsigned cxy, cz;            // cell index: x | y << 16, z
 };
 
+// Obstruction walls, tunnels, spherical obstacles, charge sources: rarely present, so their tables live in device memory
+// instead of the kernel parameter block (the sweep driver launches once per loop iteration and pays for every parameter byte)
+struct SingleBody {
+    int obst_type[SDMD_MAX_OBST], obst_hole[SDMD_MAX_OBST];
+    double obst_pos[SDMD_MAX_OBST][3], sph_pos[SDMD_MAX_OBST][3], sph_r[SDMD_MAX_OBST];
+    double tun_pos[SDMD_MAX_OBST][4], tun_diam[SDMD_MAX_OBST];
+    double chg_pos[SDMD_MAX_CHARGE][3], chg_vel[SDMD_MAX_CHARGE][3], chg_grad[SDMD_MAX_CHARGE], chg_gap[SDMD_MAX_CHARGE];
+};
+
 struct DevP {
     int n, ncell;
     int cellnum[3];
@@ -87,13 +96,9 @@ struct DevP {
     const double *protein_mass;
     const double *charge;      // per atom or NULL (charge sources: flow_mark == 3)
     int n_charge, charge_com;
-    double chg_pos[SDMD_MAX_CHARGE][3], chg_vel[SDMD_MAX_CHARGE][3], chg_grad[SDMD_MAX_CHARGE], chg_gap[SDMD_MAX_CHARGE];
     int n_tunnel, tunnel_type; // tunnels through (holed) obstruction walls
-    int obst_hole[SDMD_MAX_OBST];
-    double tun_pos[SDMD_MAX_OBST][4], tun_diam[SDMD_MAX_OBST];
     int single_body;           // any of wall / obstruction / sphere present
-    int obst_type[SDMD_MAX_OBST];
-    double obst_pos[SDMD_MAX_OBST][3], sph_pos[SDMD_MAX_OBST][3], sph_r[SDMD_MAX_OBST];
+    const struct SingleBody *sb;   // geometry tables of the single-body predictors (device memory; NULL when single_body == 0)
     double *x, *y, *z, *vx, *vy, *vz;
     const double *mass;
     int *type;

@@ -772,13 +772,13 @@ __device__ __forceinline__ double d_pot_well_width(const DevP &D, int type_i, in
 // EnterTunnel, ToolFunctions.c:921-952: will the atom be inside a tunnel mouth's cross-section after `time`?
 __device__ inline bool d_enter_tunnel(const DevP &D, const Self &me, double time) {
     for (int n = 0; n < D.n_tunnel; n++) {
-        double radius2 = D.tun_diam[n] * 0.5;
+        double radius2 = D.sb->tun_diam[n] * 0.5;
         radius2 *= radius2;
         double shift2 = d_pot_well_width(D, D.tunnel_type, me.type);
         double py = me.y, pz = me.z;
         py += me.vy * time;
         pz += me.vz * time;
-        double r1 = D.tun_pos[n][1] - D.tun_pos[n][1], r2 = py - D.tun_pos[n][2], r3 = pz - D.tun_pos[n][3];
+        double r1 = D.sb->tun_pos[n][1] - D.sb->tun_pos[n][1], r2 = py - D.sb->tun_pos[n][2], r3 = pz - D.sb->tun_pos[n][3];
         double r_2 = r1 * r1 + r2 * r2 + r3 * r3;
         double distance2 = radius2 + shift2 - 2 * sqrt(radius2 * shift2);
         if (r_2 <= distance2) return true;
@@ -794,10 +794,10 @@ __device__ inline void d_tunnel_time(const DevP &D, const Self &me, Slot &cur) {
     const double shift2 = D.tables[idx].dmin2;
     const double extraRange = sqrt(d_pot_well_width(D, D.tunnel_type, me.type));
     for (int n = 0; n < D.n_tunnel; n++) {
-        double radius2 = D.tun_diam[n] / 2;
+        double radius2 = D.sb->tun_diam[n] / 2;
         radius2 *= radius2;
         Pair p;
-        p.rx = D.tun_pos[n][1] - D.tun_pos[n][1]; p.ry = me.y - D.tun_pos[n][2]; p.rz = me.z - D.tun_pos[n][3];
+        p.rx = D.sb->tun_pos[n][1] - D.sb->tun_pos[n][1]; p.ry = me.y - D.sb->tun_pos[n][2]; p.rz = me.z - D.sb->tun_pos[n][3];
         double vx = 0 - 0.0, vy = me.vy - 0.0, vz = me.vz - 0.0;
         p.r2 = p.rx * p.rx + p.ry * p.ry + p.rz * p.rz;
         p.b = p.rx * vx + p.ry * vy + p.rz * vz;
@@ -820,7 +820,7 @@ __device__ inline void d_tunnel_time(const DevP &D, const Self &me, Slot &cur) {
         }
         double t = d_time(p, s, d2);
         double futurePos = me.x + me.vx * t;                                              // :912-917
-        if (futurePos < D.tun_pos[n][0] - extraRange || futurePos > D.tun_pos[n][1] + extraRange) continue;
+        if (futurePos < D.sb->tun_pos[n][0] - extraRange || futurePos > D.sb->tun_pos[n][1] + extraRange) continue;
         if (t < 0) t = SD_INF;
         if (d_job_assign(D, cur, 0, t, pot, sub, SDMD_EV_TUNL)) cur.partner = -10000 * n;
     }
@@ -833,19 +833,19 @@ __device__ inline void d_obst_time(const DevP &D, const Self &me, Slot &cur) {
     for (int n = 0; n < D.n_obst; n++) {
 #pragma unroll 1
         for (int dim = 0; dim < 3; dim++) {
-            if (D.obst_pos[n][dim] < 0) continue;
+            if (D.sb->obst_pos[n][dim] < 0) continue;
             Pair p;
             double r[3], v[3];
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                double pi = (k == dim) ? pos[k] : 0, pj = (k == dim) ? D.obst_pos[n][k] : 0, si = (k == dim) ? spd[k] : 0;
+                double pi = (k == dim) ? pos[k] : 0, pj = (k == dim) ? D.sb->obst_pos[n][k] : 0, si = (k == dim) ? spd[k] : 0;
                 r[k] = pi - pj; v[k] = si - 0.0;
             }
             p.rx = r[0]; p.ry = r[1]; p.rz = r[2];
             p.r2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
             p.b = r[0] * v[0] + r[1] * v[1] + r[2] * v[2];
             p.v2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
-            int idx = __ldg(&D.coll_index[me.type * SD_NT + D.obst_type[n]]);
+            int idx = __ldg(&D.coll_index[me.type * SD_NT + D.sb->obst_type[n]]);
             if (idx < 0) { D.ctl->error = SDMD_ERR_TABLE; return; }
             FindRes f = d_find_pair_table(D, &D.tables[idx], FP_COLLISION, p.b, p.r2, 0, 0);
             if (f.lowPot == 0 && f.upPot == 0) continue;                     // :783-787
@@ -862,7 +862,7 @@ __device__ inline void d_obst_time(const DevP &D, const Self &me, Slot &cur) {
             double t = d_time(p, s, d2);
             if (t < 0) { D.ctl->error = SDMD_ERR_STATE; return; }             // exit(), :813-816
             // at the next collision the atom would already be in the hole: the prediction is void, :818-824
-            if (!(D.obst_hole[n] && d_enter_tunnel(D, me, t)) && d_job_assign(D, cur, 0, t, pot, sub, SDMD_EV_OBST))
+            if (!(D.sb->obst_hole[n] && d_enter_tunnel(D, me, t)) && d_job_assign(D, cur, 0, t, pot, sub, SDMD_EV_OBST))
                 cur.partner = -1 * (dim + 1) - 10 * n;
         }
     }
@@ -875,22 +875,22 @@ __device__ inline void d_charge_time(const DevP &D, const Self &me, Slot &cur) {
     if (!charge) return;
     int flag = 0;
     for (int cn = 0; cn < D.n_charge; cn++) {
-        if (me.x > D.chg_pos[cn][0] - SD_ZERO) continue;
-        if (D.chg_pos[cn][0] < D.box[0]) flag = 1;                                   // :948-956
-        else if (!(flag == 0 && D.chg_pos[cn][0] > D.box[0])) break;
+        if (me.x > D.sb->chg_pos[cn][0] - SD_ZERO) continue;
+        if (D.sb->chg_pos[cn][0] < D.box[0]) flag = 1;                                   // :948-956
+        else if (!(flag == 0 && D.sb->chg_pos[cn][0] > D.box[0])) break;
         Pair p;
-        p.rx = me.x - D.chg_pos[cn][0]; p.ry = me.y - D.chg_pos[cn][1]; p.rz = me.z - D.chg_pos[cn][2];
-        double vx = me.vx - D.chg_vel[cn][0], vy = me.vy - D.chg_vel[cn][1], vz = me.vz - D.chg_vel[cn][2];
+        p.rx = me.x - D.sb->chg_pos[cn][0]; p.ry = me.y - D.sb->chg_pos[cn][1]; p.rz = me.z - D.sb->chg_pos[cn][2];
+        double vx = me.vx - D.sb->chg_vel[cn][0], vy = me.vy - D.sb->chg_vel[cn][1], vz = me.vz - D.sb->chg_vel[cn][2];
         p.r2 = p.rx * p.rx + p.ry * p.ry + p.rz * p.rz;
         p.b = p.rx * vx + p.ry * vy + p.rz * vz;
         p.v2 = vx * vx + vy * vy + vz * vz;
-        int gapNum = (int)(sqrt(p.r2) / D.chg_gap[cn]);
-        const double gap2 = D.chg_gap[cn] * D.chg_gap[cn];
+        int gapNum = (int)(sqrt(p.r2) / D.sb->chg_gap[cn]);
+        const double gap2 = D.sb->chg_gap[cn] * D.sb->chg_gap[cn];
         const double distance2 = (gapNum * gapNum) * gap2;
         if (p.b < 0 && p.r2 < distance2 + SD_ZERO) gapNum--;
         else if (p.b > 0 && p.r2 > ((gapNum + 1) * (gapNum + 1)) * gap2 - SD_ZERO) gapNum++;
-        const double upPot = D.chg_grad[cn] * charge, long2 = ((gapNum + 1) * (gapNum + 1)) * gap2;
-        const double lowPot = -1 * D.chg_grad[cn] * charge, short2 = (gapNum * gapNum) * gap2;
+        const double upPot = D.sb->chg_grad[cn] * charge, long2 = ((gapNum + 1) * (gapNum + 1)) * gap2;
+        const double lowPot = -1 * D.sb->chg_grad[cn] * charge, short2 = (gapNum * gapNum) * gap2;
         int s, sub;
         double d2, pot;
         if (p.b < 0 && d_disc(p, short2) > 0) { s = -1; d2 = short2; pot = lowPot; sub = SDMD_SUB_TBDCAPTR; }
@@ -905,12 +905,12 @@ __device__ inline void d_charge_time(const DevP &D, const Self &me, Slot &cur) {
 __device__ inline void d_sphobst_time(const DevP &D, const Self &me, Slot &cur) {
     for (int n = 0; n < D.n_sphobst; n++) {
         Pair p;
-        p.rx = me.x - D.sph_pos[n][0]; p.ry = me.y - D.sph_pos[n][1]; p.rz = me.z - D.sph_pos[n][2];
+        p.rx = me.x - D.sb->sph_pos[n][0]; p.ry = me.y - D.sb->sph_pos[n][1]; p.rz = me.z - D.sb->sph_pos[n][2];
         double vx = me.vx - 0.0, vy = me.vy - 0.0, vz = me.vz - 0.0;
         p.r2 = p.rx * p.rx + p.ry * p.ry + p.rz * p.rz;
         p.b = p.rx * vx + p.ry * vy + p.rz * vz;
         p.v2 = vx * vx + vy * vy + vz * vz;
-        double short2 = D.sph_r[n] * D.sph_r[n];
+        double short2 = D.sb->sph_r[n] * D.sb->sph_r[n];
         if (!(p.b < 0 && d_disc(p, short2) > 0)) continue;
         double t = d_time(p, -1, short2);
         if (t < 0) { D.ctl->error = SDMD_ERR_STATE; return; }
@@ -1270,12 +1270,12 @@ __device__ inline void d_obst_event(const DevP &D, int i, bool sph) {
     if (sph) {
         int n = partner / -1000;
         if (n < 0 || n >= D.n_sphobst) { D.ctl->error = SDMD_ERR_STATE; return; }
-        for (int k = 0; k < 3; k++) { r[k] = pos[k] - D.sph_pos[n][k]; v[k] = spd[k] - 0.0; }
+        for (int k = 0; k < 3; k++) { r[k] = pos[k] - D.sb->sph_pos[n][k]; v[k] = spd[k] - 0.0; }
     } else {
         int n = partner / -10, dim = (partner * -1) % 10 - 1;
         if (n < 0 || n >= D.n_obst || dim < 0 || dim > 2) { D.ctl->error = SDMD_ERR_STATE; return; }
         for (int k = 0; k < 3; k++) {
-            double pi = (k == dim) ? pos[k] : 0, pj = (k == dim) ? D.obst_pos[n][k] : 0, si = (k == dim) ? spd[k] : 0;
+            double pi = (k == dim) ? pos[k] : 0, pj = (k == dim) ? D.sb->obst_pos[n][k] : 0, si = (k == dim) ? spd[k] : 0;
             r[k] = pi - pj; v[k] = si - 0.0;
         }
     }
@@ -1299,8 +1299,8 @@ __device__ inline void d_charge_event(const DevP &D, int i) {
     int cn = D.ev_partner[i] / -100;
     if (cn < 0 || cn >= D.n_charge) { D.ctl->error = SDMD_ERR_STATE; return; }
     double tvx = D.vx[i], tvy = D.vy[i], tvz = D.vz[i];
-    double rx = D.x[i] - D.chg_pos[cn][0], ry = D.y[i] - D.chg_pos[cn][1], rz = D.z[i] - D.chg_pos[cn][2];
-    double vx = tvx - D.chg_vel[cn][0], vy = tvy - D.chg_vel[cn][1], vz = tvz - D.chg_vel[cn][2];
+    double rx = D.x[i] - D.sb->chg_pos[cn][0], ry = D.y[i] - D.sb->chg_pos[cn][1], rz = D.z[i] - D.sb->chg_pos[cn][2];
+    double vx = tvx - D.sb->chg_vel[cn][0], vy = tvy - D.sb->chg_vel[cn][1], vz = tvz - D.sb->chg_vel[cn][2];
     double d2 = rx * rx + ry * ry + rz * rz;
     double b = rx * vx + ry * vy + rz * vz;
     double mass = D.mass[i];
@@ -1325,7 +1325,7 @@ __device__ inline void d_tunnel_event(const DevP &D, int i) {
     int n = D.ev_partner[i] / -10000;
     if (n < 0 || n >= D.n_tunnel) { D.ctl->error = SDMD_ERR_STATE; return; }
     double tvx = D.vx[i], tvy = D.vy[i], tvz = D.vz[i];
-    double rx = D.tun_pos[n][1] - D.tun_pos[n][1], ry = D.y[i] - D.tun_pos[n][2], rz = D.z[i] - D.tun_pos[n][3];
+    double rx = D.sb->tun_pos[n][1] - D.sb->tun_pos[n][1], ry = D.y[i] - D.sb->tun_pos[n][2], rz = D.z[i] - D.sb->tun_pos[n][3];
     double vx = 0 - 0.0, vy = tvy - 0.0, vz = tvz - 0.0;
     double d2 = rx * rx + ry * ry + rz * rz;
     double b = rx * vx + ry * vy + rz * vz;
