@@ -1,0 +1,59 @@
+"""Occupancy sweep of the two round-0 kernels of the full-system Predict (K2): the same source compiled with
+different `__launch_bounds__` minimum-blocks (-DK2_MINBLOCKS / -DK2F_MINBLOCKS), each timed with
+scripts/k2_breakdown.py's CUDA-event breakdown on the 1M-atom box.
+
+Build the variants on the CPU box first (they travel with the snapshot under build/variants/):
+    python scripts/k2_variants.py build
+then on the GPU:
+    python scripts/k2_variants.py run > gpurun_out/k2_variants.txt
+"""
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+VDIR = ROOT / "build" / "variants"
+VARIANTS = [(4, 5), (5, 5), (6, 5), (8, 5), (6, 6), (6, 8), (5, 6)]   # (evaluation kernel, filter kernel)
+
+CHILD = """
+import sys
+from pathlib import Path
+sys.path.insert(0, '.')
+from sdmd_b200 import capi
+capi.LIB_PATH = Path(sys.argv[1])
+sys.argv = ['k2_breakdown.py']
+exec(open('scripts/k2_breakdown.py').read())
+"""
+
+
+def so_path(k2, k2f):
+    return VDIR / f"lib_k2_{k2}_f{k2f}.so"
+
+
+def build():
+    sys.path.insert(0, str(ROOT))
+    from sdmd_b200 import capi
+    VDIR.mkdir(parents=True, exist_ok=True)
+    procs = []
+    for k2, k2f in VARIANTS:
+        cmd = ["nvcc", *capi.NVCC_FLAGS, "-Xptxas", "-v", f"-DK2_MINBLOCKS={k2}", f"-DK2F_MINBLOCKS={k2f}", f"-I{ROOT / 'include'}",
+               f"-I{ROOT / 'sdmd_b200' / 'csrc'}", str(ROOT / "sdmd_b200" / "csrc" / "sdmd_cuda.cu"), "-o", str(so_path(k2, k2f)), "-ldl"]
+        procs.append(subprocess.Popen(cmd, stdout=open(VDIR / f"ptxas_{k2}_{k2f}.log", "w"), stderr=subprocess.STDOUT))
+    for p in procs:
+        if p.wait():
+            raise SystemExit("nvcc failed")
+
+
+def run():
+    for k2, k2f in VARIANTS:
+        so = so_path(k2, k2f)
+        if not so.exists():
+            print(f"missing {so}")
+            continue
+        print(f"=== K2_MINBLOCKS={k2} K2F_MINBLOCKS={k2f}", flush=True)
+        r = subprocess.run([sys.executable, "-c", CHILD, str(so)], cwd=ROOT, capture_output=True, text=True, timeout=300)
+        print(r.stdout + r.stderr[-2000:], flush=True)
+
+
+if __name__ == "__main__":
+    {"build": build, "run": run}[sys.argv[1]]()
