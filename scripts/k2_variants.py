@@ -3,7 +3,7 @@ different `__launch_bounds__` minimum-blocks (-DK2_MINBLOCKS / -DK2F_MINBLOCKS),
 scripts/k2_breakdown.py's CUDA-event breakdown on the 1M-atom box.
 
 Build the variants on the CPU box first (they travel with the snapshot under build/variants/):
-    python scripts/k2_variants.py build
+    python scripts/k2_variants.py build            # or: build base=-DK2_DIRECT=0,-DK2_LEAN=0 d2=-DK2_DIRECT=2
 then on the GPU:
     python scripts/k2_variants.py run > gpurun_out/k2_variants.txt
 """
@@ -26,31 +26,27 @@ exec(open('scripts/k2_breakdown.py').read())
 """
 
 
-def so_path(k2, k2f):
-    return VDIR / f"lib_k2_{k2}_f{k2f}.so"
-
-
 def build():
+    """No further arguments: the launch-bounds sweep.  Otherwise each argument is `name=-DFLAG=V,-DFLAG2=W` (one variant)."""
     sys.path.insert(0, str(ROOT))
     from sdmd_b200 import capi
     VDIR.mkdir(parents=True, exist_ok=True)
+    jobs = [(f"k2_{k2}_f{k2f}", [f"-DK2_MINBLOCKS={k2}", f"-DK2F_MINBLOCKS={k2f}"]) for k2, k2f in VARIANTS]
+    if len(sys.argv) > 2:
+        jobs = [(a.split("=", 1)[0], [f for f in a.split("=", 1)[1].split(",") if f]) for a in sys.argv[2:]]
     procs = []
-    for k2, k2f in VARIANTS:
-        cmd = ["nvcc", *capi.NVCC_FLAGS, "-Xptxas", "-v", f"-DK2_MINBLOCKS={k2}", f"-DK2F_MINBLOCKS={k2f}", f"-I{ROOT / 'include'}",
-               f"-I{ROOT / 'sdmd_b200' / 'csrc'}", str(ROOT / "sdmd_b200" / "csrc" / "sdmd_cuda.cu"), "-o", str(so_path(k2, k2f)), "-ldl"]
-        procs.append(subprocess.Popen(cmd, stdout=open(VDIR / f"ptxas_{k2}_{k2f}.log", "w"), stderr=subprocess.STDOUT))
+    for name, flags in jobs:
+        cmd = ["nvcc", *capi.NVCC_FLAGS, "-Xptxas", "-v", *flags, f"-I{ROOT / 'include'}",
+               f"-I{ROOT / 'sdmd_b200' / 'csrc'}", str(ROOT / "sdmd_b200" / "csrc" / "sdmd_cuda.cu"), "-o", str(VDIR / f"lib_{name}.so"), "-ldl"]
+        procs.append(subprocess.Popen(cmd, stdout=open(VDIR / f"ptxas_{name}.log", "w"), stderr=subprocess.STDOUT))
     for p in procs:
         if p.wait():
             raise SystemExit("nvcc failed")
 
 
 def run():
-    for k2, k2f in VARIANTS:
-        so = so_path(k2, k2f)
-        if not so.exists():
-            print(f"missing {so}")
-            continue
-        print(f"=== K2_MINBLOCKS={k2} K2F_MINBLOCKS={k2f}", flush=True)
+    for so in sorted(VDIR.glob("lib_*.so")):      # whatever was built: the sweep above or hand-built experiment variants
+        print(f"=== {so.stem}", flush=True)
         r = subprocess.run([sys.executable, "-c", CHILD, str(so)], cwd=ROOT, capture_output=True, text=True, timeout=300)
         print(r.stdout + r.stderr[-2000:], flush=True)
 

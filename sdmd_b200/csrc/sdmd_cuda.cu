@@ -364,9 +364,14 @@ __global__ void __launch_bounds__(256, K2F_MINBLOCKS) k_predict_all_filter(DevP 
 #ifndef K2_MINBLOCKS
 #define K2_MINBLOCKS 6
 #endif
-__global__ void __launch_bounds__(128, K2_MINBLOCKS) k_predict_all_round(DevP D, SlotBuf src, SlotBuf dst, const int *queue, const int *nqueue_ptr,
-                                                           int round, int *npair, double *second, double *bp_time, int *bp_j,
+#ifndef K2_MINBLOCKS_LEAN
+#define K2_MINBLOCKS_LEAN 5   // 96 registers, no spills (6 blocks: 80 registers with spills, measured 3 % slower)
+#endif
+template <bool LEAN>
+__global__ void __launch_bounds__(128, LEAN ? K2_MINBLOCKS_LEAN : K2_MINBLOCKS) k_predict_all_round(DevP D, SlotBuf src, SlotBuf dst, const int *queue, const int *nqueue_ptr,
+                                                           int round_arg, int *npair, double *second, double *bp_time, int *bp_j,
                                                            int *pcount, int *pwho, unsigned long long *pair_sum, i64 g_base) {
+    const int round = LEAN ? 0 : round_arg;   // the lean instance is only ever launched for round 0
     int total = (round == 0) ? D.n : *nqueue_ptr;
     // re-evaluation rounds are a few thousand atoms with divergent, DRAM-latency-bound paths: give each its own
     // group of QSPREAD lanes so a warp serialises 32/QSPREAD paths instead of 32
@@ -411,8 +416,8 @@ __global__ void __launch_bounds__(128, K2_MINBLOCKS) k_predict_all_round(DevP D,
         int np = 0;
         double m2 = SD_INF;
         PairBest pb;
-        if (round == 0) cur = d_predict_atom<true, true>(D, as_src(src), i, cur, g, 0, &np, &m2, &pb, D.surv ? p : -1);
-        else cur = d_predict_atom<true, false>(D, as_src(src), i, cur, g, i, &np, nullptr, nullptr, D.surv ? D.spos[i] : -1);
+        if (round == 0) cur = d_predict_atom<true, true, LEAN>(D, as_src(src), i, cur, g, 0, &np, &m2, &pb, D.surv ? p : -1);
+        else cur = d_predict_atom<true, false, LEAN>(D, as_src(src), i, cur, g, i, &np, nullptr, nullptr, D.surv ? D.spos[i] : -1);
         dst.time[i] = cur.time; dst.pot[i] = cur.pot; dst.partner[i] = cur.partner; dst.pcounter[i] = cur.pcounter;
         dst.type[i] = (uint8_t)cur.type; dst.sub[i] = (uint8_t)cur.sub;
         if (round == 0) {
@@ -1690,8 +1695,15 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
             k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_srec, c->d_sloc, c->d_scell, 2);
             c->launches++;
         }
-        k_predict_all_round<<<grid, 128, 0, c->stream>>>(c->P, B, B, nullptr, nullptr, 0, c->npair, c->second, c->bp_time, c->bp_j,
-                                                         c->pcount, c->pwho, c->d_sum, g_base);
+        // systems without bonds, hydrogen bonds and single-body sources (the GEL boxes) run the instance with those
+        // predictors compiled out
+        const bool lean = K2_LEAN && c->P.gel_mode && !c->P.hydrogen_bond && !c->P.single_body;
+        if (lean)
+            k_predict_all_round<true><<<grid, 128, 0, c->stream>>>(c->P, B, B, nullptr, nullptr, 0, c->npair, c->second, c->bp_time, c->bp_j,
+                                                                   c->pcount, c->pwho, c->d_sum, g_base);
+        else
+            k_predict_all_round<false><<<grid, 128, 0, c->stream>>>(c->P, B, B, nullptr, nullptr, 0, c->npair, c->second, c->bp_time, c->bp_j,
+                                                                    c->pcount, c->pwho, c->d_sum, g_base);
         c->launches++;
     }
     int rounds = 0, requeued = 0;
@@ -1712,7 +1724,7 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
             int burst = (slot == 0) ? 2 : 3;
             for (int r = 0; r < burst && slot + 1 < NQ; r++, slot++) {
                 Timer t4(c, slot == 0 ? "fixup_round1" : "fixup_later", 2);
-                k_predict_all_round<<<qgrid, 128, 0, c->stream>>>(c->P, B, C, qa, c->nqueue + slot, slot + 1, c->npair, c->second, c->bp_time,
+                k_predict_all_round<false><<<qgrid, 128, 0, c->stream>>>(c->P, B, C, qa, c->nqueue + slot, slot + 1, c->npair, c->second, c->bp_time,
                                                                   c->bp_j, c->pcount, c->pwho, c->d_sum, g_base);
                 k_predict_all_commit<<<qgrid, 256, 0, c->stream>>>(c->P, B, C, qa, c->nqueue + slot, qb, c->nqueue + slot + 1);
                 c->launches += 2;

@@ -325,6 +325,17 @@ __device__ inline void d_collision_time(const DevP &D, const SlotSrc &S, Self &m
 //   stage 2  the expensive step-table walk + quadratic root, run on the compacted survivors only.
 // Candidates are still folded in exact scan order, so the result is the sequential one; the split only removes
 // the per-candidate divergence that left ~9 of 32 lanes active in the fused loop.
+// round-0 evaluation variants (measured in profiles/r1_summary.md, session 4):
+//   K2_DIRECT  1 = round 0 evaluates straight from the filter's survivor row (no staging in local arrays), 2 = same with the
+//              next record prefetched (slower: 14 more live registers)
+//   K2_LEAN    1 = systems without bonds / hydrogen bonds / single-body sources get a kernel instance with those predictors
+//              compiled out; it fits 5 blocks per SM without spilling
+#ifndef K2_DIRECT
+#define K2_DIRECT 1
+#endif
+#ifndef K2_LEAN
+#define K2_LEAN 1
+#endif
 #define R0_MAXSURV 20
 #define R0_SURV_CAP 32
 #define R0_DUPFLAG 0x80   // survivor entry whose partner's slot points back: resolved in order in stage 2
@@ -538,6 +549,57 @@ __device__ inline void d_collision_time_from_list(const DevP &D, const SlotSrc &
         hb_i = D.hb_bond[i];
         if (D.hydrogen_bond) { h0 = D.hbn_partner[5 * i + 1]; h1 = D.hbn_partner[5 * i + 2]; h2 = D.hbn_partner[5 * i + 3]; h3 = D.hbn_partner[5 * i + 4]; }
     }
+#if K2_DIRECT
+    if (!DUP) {
+        // round 0 has no tagged entries: evaluate straight from the filter's list (no staging through local arrays),
+        // the next entry's record in flight while the current one is evaluated
+        const bool seam = me.cx == 0 || me.cy == 0 || me.cz == 0 || me.cx == D.cellnum[0] - 1 || me.cy == D.cellnum[1] - 1 ||
+                          me.cz == D.cellnum[2] - 1;
+        if (ns > 0) {
+            unsigned v = __ldg(in);
+            const double2 *rp = reinterpret_cast<const double2 *>(&D.srec[v & 0x7ffffffu]);
+            double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2v = __ldg(rp + 2);
+            int2 ta = __ldg(reinterpret_cast<const int2 *>(rp + 3));
+            for (int s = 0; s < ns; s++) {
+                unsigned vc = v;
+                double2 c0 = r0, c1 = r1, c2 = r2v;
+                int2 tc = ta;
+#if K2_DIRECT == 2
+                if (s + 1 < ns) {
+                    v = __ldg(in + s + 1);
+                    rp = reinterpret_cast<const double2 *>(&D.srec[v & 0x7ffffffu]);
+                    r0 = __ldg(rp); r1 = __ldg(rp + 1); r2v = __ldg(rp + 2);
+                    ta = __ldg(reinterpret_cast<const int2 *>(rp + 3));
+                }
+#endif
+                int j = tc.y;
+                double shx = 0, shy = 0, shz = 0;
+                if (seam) {
+                    int ncx, ncy, ncz;
+                    d_neighbor_cell(D, me.cx, me.cy, me.cz, (int)(vc >> 27), &ncx, &ncy, &ncz);
+                    shx = d_shift1(me.cx, ncx, D.cellnum[0], D.box[0]);
+                    shy = d_shift1(me.cy, ncy, D.cellnum[1], D.box[1]);
+                    shz = d_shift1(me.cz, ncz, D.cellnum[2], D.box[2]);
+                }
+                int cm = has_cm ? d_cm_flags(D, i, j) : 0;
+                double t, pot;
+                int sub;
+                if (d_eval_pair(D, me, j, tc.x, c0.x, c0.y, c1.x, c1.y, c2.x, c2.y, shx, shy, shz, cm, type_i, &t, &pot, &sub))
+                    d_job_assign(D, cur, j, t, pot, sub, SDMD_EV_COLI);
+#if K2_DIRECT != 2
+                if (s + 1 < ns) {
+                    v = __ldg(in + s + 1);
+                    rp = reinterpret_cast<const double2 *>(&D.srec[v & 0x7ffffffu]);
+                    r0 = __ldg(rp); r1 = __ldg(rp + 1); r2v = __ldg(rp + 2);
+                    ta = __ldg(reinterpret_cast<const int2 *>(rp + 3));
+                }
+#endif
+            }
+        }
+        me.npair += D.surv_np[p_self];
+        return;
+    }
+#endif
     int surv_p[R0_MAXSURV];
     unsigned char surv_k[R0_MAXSURV];
     int ndup = 0;
@@ -959,12 +1021,14 @@ __device__ __forceinline__ Slot d_reset_slot(double pot, int sub, i64 pcounter) 
 // one atom of Predict, SGThread.c:162-208, executed by a single thread in reference order.
 // SORTED selects the cell-sorted tiles for the 27-cell scan (fresh link list only).
 struct PairBest { double bp_time, sp_time; int bp_j; };
-template <bool SORTED, bool R0 = false>
+// LEAN: the caller guarantees a system without bonds, hydrogen bonds and single-body sources (gel_mode, !hydrogen_bond,
+// !single_body — uniform per system), so those predictors are compiled out of the kernel instance.
+template <bool SORTED, bool R0 = false, bool LEAN = false>
 __device__ inline Slot d_predict_atom(const DevP &D, const SlotSrc &S, int i, Slot cur, double gauss, int dup_limit, int *npair,
                                       double *second = nullptr, PairBest *pb = nullptr, int surv_pos = -1) {
     if (!D.no_cons && D.is_cons[i]) { cur.time = SD_INF; return cur; }
     Self me = (SORTED && surv_pos >= 0) ? d_load_self_sorted(D, surv_pos) : d_load_self(D, i);
-    if (!D.gel_mode) d_bond_time(D, S, me, cur, dup_limit);
+    if (!LEAN && !D.gel_mode) d_bond_time(D, S, me, cur, dup_limit);
     if (R0 && surv_pos >= 0 && D.surv_n[surv_pos] >= 0) d_collision_time_from_list<false>(D, S, me, cur, surv_pos, 0);
     else if (R0) d_collision_time_2stage<false>(D, S, me, cur, 0);
     else if (SORTED && surv_pos >= 0 && D.surv_n[surv_pos] >= 0) d_collision_time_from_list<true>(D, S, me, cur, surv_pos, dup_limit);
