@@ -336,6 +336,16 @@ __device__ inline void d_collision_time(const DevP &D, const SlotSrc &S, Self &m
 #ifndef K2_LEAN
 #define K2_LEAN 1
 #endif
+//   K2_STREAM  1 = the survivor rows (read once) are loaded with the evict-first hint (`ld.global.cs`) so they do not push the
+//              64-byte records, which every neighbour re-reads, out of L2: measured 5 % SLOWER (301 vs 287 us), left off
+#ifndef K2_STREAM
+#define K2_STREAM 0
+#endif
+#if K2_STREAM
+#define K2_LD_ROW(p) __ldcs(p)
+#else
+#define K2_LD_ROW(p) __ldg(p)
+#endif
 #define R0_MAXSURV 20
 #define R0_SURV_CAP 32
 #define R0_DUPFLAG 0x80   // survivor entry whose partner's slot points back: resolved in order in stage 2
@@ -556,7 +566,7 @@ __device__ inline void d_collision_time_from_list(const DevP &D, const SlotSrc &
         const bool seam = me.cx == 0 || me.cy == 0 || me.cz == 0 || me.cx == D.cellnum[0] - 1 || me.cy == D.cellnum[1] - 1 ||
                           me.cz == D.cellnum[2] - 1;
         if (ns > 0) {
-            unsigned v = __ldg(in);
+            unsigned v = K2_LD_ROW(in);
             const double2 *rp = reinterpret_cast<const double2 *>(&D.srec[v & 0x7ffffffu]);
             double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2v = __ldg(rp + 2);
             int2 ta = __ldg(reinterpret_cast<const int2 *>(rp + 3));
@@ -566,7 +576,7 @@ __device__ inline void d_collision_time_from_list(const DevP &D, const SlotSrc &
                 int2 tc = ta;
 #if K2_DIRECT == 2
                 if (s + 1 < ns) {
-                    v = __ldg(in + s + 1);
+                    v = K2_LD_ROW(in + s + 1);
                     rp = reinterpret_cast<const double2 *>(&D.srec[v & 0x7ffffffu]);
                     r0 = __ldg(rp); r1 = __ldg(rp + 1); r2v = __ldg(rp + 2);
                     ta = __ldg(reinterpret_cast<const int2 *>(rp + 3));
@@ -588,7 +598,7 @@ __device__ inline void d_collision_time_from_list(const DevP &D, const SlotSrc &
                     d_job_assign(D, cur, j, t, pot, sub, SDMD_EV_COLI);
 #if K2_DIRECT != 2
                 if (s + 1 < ns) {
-                    v = __ldg(in + s + 1);
+                    v = K2_LD_ROW(in + s + 1);
                     rp = reinterpret_cast<const double2 *>(&D.srec[v & 0x7ffffffu]);
                     r0 = __ldg(rp); r1 = __ldg(rp + 1); r2v = __ldg(rp + 2);
                     ta = __ldg(reinterpret_cast<const int2 *>(rp + 3));
