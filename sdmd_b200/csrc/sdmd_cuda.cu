@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(128, LEAN ? K2_MINBLOCKS_LEAN : K2_MINBLOCKS) 
                 int ps = D.spos[i];
                 int ns = D.surv_n[ps];
                 for (int s = sub; s < ns; s += QSPREAD) {
-                    unsigned w = D.surv[(size_t)ps * R0_SURV_CAP + s];
+                    unsigned w = D.surv[(size_t)ps * D.surv_cap + s];
                     const SRec *r = &D.srec[w & 0x7ffffffu];
                     int j = r->atom;
                     acc += r->x + r->vy + (double)src.partner[j] + (double)src.type[j] + (double)src.pcounter[j] + src.time[j] + src.pot[j] +
@@ -1363,6 +1363,14 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     for (int k = 0; k < 3; k++) P.cellsize_f[k] = (float)P.cellsize[k];
     P.sloc = c->d_sloc; P.scell = c->d_scell;
     if (n < (1 << 27)) {
+        // row size: a sparse bond-free box (the GEL lattices: ~4 atoms expected inside the scan sphere) gets 64-byte rows, which
+        // halves the footprint the evaluation kernel streams through L2 (287 -> 275 us at 1M atoms); longer lists overflow
+        // into the exact in-kernel re-scan either way
+        {
+            double vol = P.box[0] * P.box[1] * P.box[2];
+            double expected = vol > 0 ? (double)n / vol * (4.0 / 3.0) * 3.14159265358979 * P.cut2 * sqrt(P.cut2) : 1e9;
+            P.surv_cap = (P.gel_mode && !P.hydrogen_bond && expected <= 6.0) ? 16 : R0_SURV_CAP;
+        }
         TRY(dalloc(c, &P.surv, (size_t)R0_SURV_CAP * n1)); TRY(dalloc(c, &P.surv_n, n1)); TRY(dalloc(c, &P.surv_np, n1));
     }
     P.cell_start = c->d_cell_start; P.sorted_atom = c->d_sorted_atom;

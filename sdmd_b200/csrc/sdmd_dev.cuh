@@ -145,6 +145,7 @@ struct DevP {
     const struct SRec *srec;      // full record per sorted position: what the evaluation stage gathers
     // round-0 filter output: per sorted position up to R0_SURV_CAP candidates inside the scan sphere
     unsigned int *surv;      // (sorted position of j) | (scan slot k << 27)
+    int surv_cap;            // entries per row: 16 for sparse bond-free boxes, else R0_SURV_CAP (chosen at create)
     int *surv_n;             // count, or -1 when the list overflowed (atom re-scanned in the evaluation kernel)
     int *surv_np;            // pair evaluations counted by the filter
     int *spos;               // sorted position of every atom (inverse of sorted_atom)

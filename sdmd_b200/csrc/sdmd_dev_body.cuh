@@ -347,7 +347,9 @@ __device__ inline void d_collision_time(const DevP &D, const SlotSrc &S, Self &m
 #define K2_LD_ROW(p) __ldg(p)
 #endif
 #define R0_MAXSURV 20
-#define R0_SURV_CAP 32
+#ifndef R0_SURV_CAP
+#define R0_SURV_CAP 32   // most entries per survivor row (128 B; DevP::surv_cap is the row size in use); a longer list marks the row overflowed -> exact in-kernel fallback
+#endif
 #define R0_DUPFLAG 0x80   // survivor entry whose partner's slot points back: resolved in order in stage 2
 // Own-side evaluation of one collision candidate inside the scan sphere: exact distance re-test, step-table walk,
 // discriminant, root (CollisionTime, TimePrediction.c:107-175).  Returns false when the candidate produces no event.
@@ -496,7 +498,8 @@ __device__ inline void d_r0_filter(const DevP &D, int p_self) {
     int h0 = 0, h1 = 0, h2 = 0, h3 = 0;
     if (D.hydrogen_bond) { hb_i = D.hb_bond[i]; h0 = D.hbn_partner[5 * i + 1]; h1 = D.hbn_partner[5 * i + 2]; h2 = D.hbn_partner[5 * i + 3]; h3 = D.hbn_partner[5 * i + 4]; }
     bool need_j = has_cm || hb_i != 0 || h0 != 0;
-    unsigned int *out = D.surv + (size_t)p_self * R0_SURV_CAP;
+    const int cap = D.surv_cap;
+    unsigned int *out = D.surv + (size_t)p_self * cap;
     int ns = 0, npair = 0;
     int cx = 0, cy = 0, cz = 0;
     // neighbour cells by arithmetic (a per-cell table of the 27 ids costs a dependent load per cell and 108 B/cell of
@@ -535,12 +538,12 @@ __device__ inline void d_r0_filter(const DevP &D, int p_self) {
             float rx = mx - q.x, ry = my - q.y, rz = mz - q.z;
             float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
             if (r2 <= cut2) {
-                if (ns < R0_SURV_CAP) out[ns] = (unsigned)p | ((unsigned)k << 27);
+                if (ns < cap) out[ns] = (unsigned)p | ((unsigned)k << 27);
                 ns++;
             }
         }
     }
-    D.surv_n[p_self] = (ns <= R0_SURV_CAP) ? ns : -1;
+    D.surv_n[p_self] = (ns <= cap) ? ns : -1;
     D.surv_np[p_self] = npair;
 }
 
@@ -550,7 +553,7 @@ __device__ inline void d_r0_filter(const DevP &D, int p_self) {
 template <bool DUP>
 __device__ inline void d_collision_time_from_list(const DevP &D, const SlotSrc &S, Self &me, Slot &cur, int p_self, int dup_limit) {
     int ns = D.surv_n[p_self];
-    const unsigned int *in = D.surv + (size_t)p_self * R0_SURV_CAP;
+    const unsigned int *in = D.surv + (size_t)p_self * D.surv_cap;
     int i = me.i;
     bool has_cm = me.cm1 > me.cm0;
     int type_i = me.type;
