@@ -205,13 +205,16 @@ struct sdmd_run_stats {
     int64_t iterations;               /* loop iterations incl. hazard-denied */
     int64_t count_recal;              /* countReCal */
     int64_t collision, bond, hb, hb_neighbor, thermostat, pcc;
-    int64_t warnings;                 /* warningsum */
+    int64_t warnings;                 /* warningsum: FindPair's too-small / too-large warnings (ToolFunctions.c:127-139,171-178,203-210);
+                                       * the too-small one is suppressed while a tunnel exists, like the reference's */
     int64_t pair_predictions;         /* CalculateParameters-equivalent evaluations */
     int64_t gaussians_used;           /* thermostat RNG samples consumed */
     double  currenttime;
     int32_t stop_reason;              /* enum sdmd_stop_reason */
     int32_t error;                    /* first device-side SDMD_ERR_* or 0 */
     int64_t wall;                     /* walleventsum: wall, obstruction and spherical-obstacle events (Events.c:73-100) */
+    int64_t error_prints;             /* "!!ERROR!!" messages the reference would have printed and carried on from (negative
+                                       * predicted time, bond long-/short-error: TimePrediction.c:168-173,240-269); NOT in warningsum */
 };
 
 enum sdmd_stop_reason {

@@ -262,7 +262,8 @@ static int find_pair(oracle_ctx *c, int a1, int a2, int mode, double direction, 
 
     if (dist2 < t->dmin2 - ZERO) {                 /* :119-139 */
         *lowerLimit = INF; *upperLimit = INF; *accum = INF; *lowerPot = 0; *upperPot = 0;
-        if (!(mode == FP_NEIGHBOR && v->hb_bond[a2] == 0) && !(mode == FP_HB && v->hb_bond[a1] == 0)) c->st.warnings++;
+        /* :127-130: counted only while wallDyn is "no" (always, here) and no tunnel exists */
+        if (!(mode == FP_NEIGHBOR && v->hb_bond[a2] == 0) && !(mode == FP_HB && v->hb_bond[a1] == 0) && !v->n_tunnel) c->st.warnings++;
         return coreorShell;
     }
     *lowerLimit = t->dmin2;                        /* :141-142 */
@@ -404,7 +405,7 @@ static void collision_time(oracle_ctx *c, int i) {
                 }
             }
             ev.time = calc_time(&p);
-            if (ev.time < 0) c->st.warnings++; /* reference prints an error and carries on, :168-173 */
+            if (ev.time < 0) c->st.error_prints++; /* reference prints an error and carries on, :168-173 */
             job_assign(c, i, j, &ev, SDMD_EV_COLI);
         }
     }
@@ -423,7 +424,7 @@ static void bond_time(oracle_ctx *c, int i) {
         p.shortlimit2 = v->bond_dmin2[k];
         calc_params(c, i, j, &p);
         if (p.r_2 - p.longlimit2 > ZERO) {           /* :240-253 */
-            c->st.warnings++;
+            c->st.error_prints++;
             if (p.b_ij >= 0) {
                 ev.sub = SDMD_SUB_WELLBOUNC;
                 ev.time = 1e-16 * i * j;
@@ -431,7 +432,7 @@ static void bond_time(oracle_ctx *c, int i) {
                 continue;
             }
         } else if (p.shortlimit2 - p.r_2 > ZERO) {   /* :255-269 */
-            c->st.warnings++;
+            c->st.error_prints++;
             if (p.b_ij < 0) {
                 ev.sub = SDMD_SUB_CORECOLLI;
                 ev.time = 1e-16 * i * j;
@@ -442,7 +443,7 @@ static void bond_time(oracle_ctx *c, int i) {
         if (p.b_ij < 0 && calc_disc(&p) > 0) { p.s_time = -1; p.d_ij2 = p.shortlimit2; ev.sub = SDMD_SUB_CORECOLLI; }
         else { p.s_time = 1; p.d_ij2 = p.longlimit2; ev.sub = SDMD_SUB_WELLBOUNC; }
         ev.time = calc_time(&p);
-        if (ev.time < 0) { c->st.warnings++; ev.time = INF; }
+        if (ev.time < 0) { c->st.error_prints++; ev.time = INF; }
         job_assign(c, i, j, &ev, SDMD_EV_BOND);
     }
 }
@@ -484,7 +485,7 @@ static void hb_time(oracle_ctx *c, int i) {
             if (v->method_ding) ev.sub = (p.coreorShell == 1) ? SDMD_SUB_TBDHBBRIK : SDMD_SUB_TBDESCAP;
         }
         ev.time = calc_time(&p);
-        if (ev.time < 0) { c->st.warnings++; ev.time = INF; }
+        if (ev.time < 0) { c->st.error_prints++; ev.time = INF; }
         job_assign(c, i, j, &ev, SDMD_EV_HB);
     } else if ((v->hb_role[i] == 'A' || v->hb_role[i] == 'D' || v->hb_role[i] == 'S') && v->hb_bond[i] == 0) {
         double cut2 = v->cutoffr * SDMD_EXTEND_RATIO;
@@ -511,7 +512,7 @@ static void hb_time(oracle_ctx *c, int i) {
                     p.s_time = -1; p.d_ij2 = p.shortlimit2; ev.potential = p.lowerPotential; ev.sub = SDMD_SUB_TBDHBFORM;
                 } else continue;
                 ev.time = calc_time(&p);
-                if (ev.time < 0) { c->st.warnings++; ev.time = INF; }
+                if (ev.time < 0) { c->st.error_prints++; ev.time = INF; }
                 job_assign(c, i, j, &ev, SDMD_EV_HB);
             }
         }
@@ -546,7 +547,7 @@ static void hbn_time(oracle_ctx *c, int i) {
             if (v->method_ding) ev.sub = (p.coreorShell == 1) ? SDMD_SUB_WELLBOUNC : SDMD_SUB_TBDESCAP;
         }
         ev.time = calc_time(&p);
-        if (ev.time < 0) { c->st.warnings++; ev.time = INF; }
+        if (ev.time < 0) { c->st.error_prints++; ev.time = INF; }
         if (job_assign(c, i, j, &ev, SDMD_EV_HBNE)) { v->hbn_partner_num[i] = n; flag = 1; }
     }
 }

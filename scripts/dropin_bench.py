@@ -34,7 +34,7 @@ def run(binary, tu):
     return dt, ev, recal, (work / "out" / "out_trj.gro").read_bytes()
 
 
-for name, binary in (("reference sDMD (1 CPU core)", REFDIR / "sDMD_ref"), ("drop-in sDMD_cuda (B200)", ROOT / "sdmd_b200" / "host" / "_build" / "sDMD_cuda")):
+for name, binary in (("reference sDMD (1 CPU core)", REFDIR / "sDMD_ref"), ("drop-in sDMD_cuda (B200)", ROOT / "sdmd_b200" / "host" / "_build" / "sDMD_cuda_fixedseed")):
     a = run(binary, t_short)
     b = run(binary, t_long)
     ev, it, dt = b[1] - a[1], (b[1] + b[2]) - (a[1] + a[2]), b[0] - a[0]

@@ -2007,7 +2007,7 @@ static void fill_stats(const Ctl *h, struct sdmd_run_stats *s) {
     s->thermostat = h->n_ther; s->pcc = h->n_pcc; s->warnings = h->warnings;
     s->pair_predictions = h->pair_predictions; s->gaussians_used = h->g_pos; s->currenttime = h->currenttime;
     s->stop_reason = h->stop ? h->stop - 1 : 0; s->error = h->error;
-    s->wall = h->n_wall;
+    s->wall = h->n_wall; s->error_prints = h->error_prints;
 }
 
 int sdmd_cuda_get_stats(sdmd_ctx *c, struct sdmd_run_stats *s) {

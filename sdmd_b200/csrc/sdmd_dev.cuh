@@ -23,6 +23,7 @@ struct Ctl {
     i64 frame, iterations, count_recal;
     i64 n_coli, n_bond, n_hb, n_hbne, n_ther, n_pcc, n_wall;
     i64 warnings, pair_predictions;
+    i64 error_prints;          // "!!ERROR!!" prints the reference carries on from (not part of warningsum)
     i64 g_pos;                 // gaussians consumed (absolute)
     i64 g_filled;              // gaussians fed (absolute)
     int target, partner;       // AssignJob result

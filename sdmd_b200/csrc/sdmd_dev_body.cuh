@@ -100,7 +100,7 @@ __device__ inline FindRes d_find_pair_table(const DevP &D, const sdmd_step_table
     double tol = dir * SD_ZERO;
     if (dist2 < t->dmin2 - SD_ZERO) {  // :119-139
         r.lower = SD_INF; r.upper = SD_INF; r.accum = SD_INF; r.lowPot = 0; r.upPot = 0;
-        if (!(mode == FP_NEIGHBOR && bond_a2 == 0) && !(mode == FP_HB && bond_a1 == 0)) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+        if (!(mode == FP_NEIGHBOR && bond_a2 == 0) && !(mode == FP_HB && bond_a1 == 0) && !D.n_tunnel)   /* :127-130: not under tunnels */ atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
         return r;
     }
     r.lower = t->dmin2;
@@ -299,7 +299,7 @@ __device__ inline void d_collision_candidate(const DevP &D, Self &me, Slot &cur,
         }
     }
     double t = d_time(p, s, d2);
-    if (t < 0) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);  // :168-173 prints and carries on
+    if (t < 0) atomicAdd((unsigned long long *)&D.ctl->error_prints, 1ULL);  // :168-173 prints and carries on
     d_job_assign(D, cur, j, t, pot, sub, SDMD_EV_COLI);
 }
 
@@ -384,7 +384,7 @@ __device__ __forceinline__ bool d_eval_pair(const DevP &D, const Self &me, int j
         }
     }
     double t = d_time(pr, sgn, d2);
-    if (t < 0) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+    if (t < 0) atomicAdd((unsigned long long *)&D.ctl->error_prints, 1ULL);
     *t_out = t; *pot_out = pot; *sub_out = sub;
     return true;
 }
@@ -646,13 +646,13 @@ __device__ inline void d_bond_time(const DevP &D, const SlotSrc &S, Self &me, Sl
         Pair p = d_pair_atoms(D, i, j);
         me.npair++;
         if (p.r2 - long2 > SD_ZERO) {  // :240-253
-            atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+            atomicAdd((unsigned long long *)&D.ctl->error_prints, 1ULL);
             if (p.b >= 0) {
                 d_job_assign(D, cur, j, 1e-16 * i * j, 0, SDMD_SUB_WELLBOUNC, SDMD_EV_BOND);
                 continue;
             }
         } else if (short2 - p.r2 > SD_ZERO) {  // :255-269
-            atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+            atomicAdd((unsigned long long *)&D.ctl->error_prints, 1ULL);
             if (p.b < 0) {
                 d_job_assign(D, cur, j, 1e-16 * i * j, 0, SDMD_SUB_CORECOLLI, SDMD_EV_BOND);
                 continue;
@@ -663,7 +663,7 @@ __device__ inline void d_bond_time(const DevP &D, const SlotSrc &S, Self &me, Sl
         if (p.b < 0 && d_disc(p, short2) > 0) { s = -1; d2 = short2; sub = SDMD_SUB_CORECOLLI; }
         else { s = 1; d2 = long2; sub = SDMD_SUB_WELLBOUNC; }
         double t = d_time(p, s, d2);
-        if (t < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); t = SD_INF; }
+        if (t < 0) { atomicAdd((unsigned long long *)&D.ctl->error_prints, 1ULL); t = SD_INF; }
         d_job_assign(D, cur, j, t, 0, sub, SDMD_EV_BOND);
     }
 }
@@ -707,7 +707,7 @@ __device__ inline void d_hb_time(const DevP &D, const SlotSrc &S, Self &me, Slot
             if (D.method_ding) sub = (f.cs == 1) ? SDMD_SUB_TBDHBBRIK : SDMD_SUB_TBDESCAP;
         }
         double t = d_time(p, s, d2);
-        if (t < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); t = SD_INF; }
+        if (t < 0) { atomicAdd((unsigned long long *)&D.ctl->error_prints, 1ULL); t = SD_INF; }
         d_job_assign(D, cur, j, t, pot, sub, SDMD_EV_HB);
     } else if ((role == 'A' || role == 'D' || role == 'S') && bonded == 0) {
         for (int k = 0; k < 27; k++) {
@@ -732,7 +732,7 @@ __device__ inline void d_hb_time(const DevP &D, const SlotSrc &S, Self &me, Slot
                 FindRes f = d_find_pair(D, i, j, FP_HB, p.b, p.r2, 0, 0);
                 if (!(p.b < 0 && f.cs == 1 && d_disc(p, f.lower) > 0)) continue;
                 double t = d_time(p, -1, f.lower);
-                if (t < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); t = SD_INF; }
+                if (t < 0) { atomicAdd((unsigned long long *)&D.ctl->error_prints, 1ULL); t = SD_INF; }
                 d_job_assign(D, cur, j, t, f.lowPot, SDMD_SUB_TBDHBFORM, SDMD_EV_HB);
             }
         }
@@ -766,7 +766,7 @@ __device__ inline void d_hbn_time(const DevP &D, const SlotSrc &S, Self &me, Slo
             if (D.method_ding) sub = (f.cs == 1) ? SDMD_SUB_WELLBOUNC : SDMD_SUB_TBDESCAP;
         }
         double t = d_time(p, s, d2);
-        if (t < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); t = SD_INF; }
+        if (t < 0) { atomicAdd((unsigned long long *)&D.ctl->error_prints, 1ULL); t = SD_INF; }
         if (d_job_assign(D, cur, j, t, pot, sub, SDMD_EV_HBNE)) { D.hbn_pnum[i] = n; flag = 1; }
     }
 }
@@ -1605,7 +1605,7 @@ __device__ __forceinline__ FindRes d_find_pair_table_fast(const DevP &D, const s
     if (dmin2 == 0) D.ctl->error = SDMD_ERR_TABLE;   // fatal in the reference, ToolFunctions.c:114-117
     if (dist2 < dmin2 - SD_ZERO) {
         r.lower = SD_INF; r.upper = SD_INF; r.accum = SD_INF; r.lowPot = 0; r.upPot = 0;
-        if (!(mode == FP_NEIGHBOR && bond_a2 == 0) && !(mode == FP_HB && bond_a1 == 0)) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+        if (!(mode == FP_NEIGHBOR && bond_a2 == 0) && !(mode == FP_HB && bond_a1 == 0) && !D.n_tunnel)   /* :127-130: not under tunnels */ atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
         return r;
     }
     int kk = ns;
@@ -1860,7 +1860,7 @@ __device__ __forceinline__ void d_pc_eval_coll(const DevP &D, PredShared &sh, in
                 }
                 if (!none) {
                     time = d_time(pr, s, d2);
-                    if (time < 0) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+                    if (time < 0) atomicAdd((unsigned long long *)&D.ctl->error_prints, 1ULL);
                     if (time > 0) flag |= CF_VALID;
                 }
             }
@@ -1902,10 +1902,10 @@ __device__ inline void d_pc_eval(const DevP &D, PredShared &sh, int a, int p, co
             double long2 = D.bond_dmax2[k], short2 = D.bond_dmin2[k];
             bool done = false;
             if (pr.r2 - long2 > SD_ZERO) {
-                atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+                atomicAdd((unsigned long long *)&D.ctl->error_prints, 1ULL);
                 if (pr.b >= 0) { time = 1e-16 * i * j; sub = SDMD_SUB_WELLBOUNC; done = true; }
             } else if (short2 - pr.r2 > SD_ZERO) {
-                atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);
+                atomicAdd((unsigned long long *)&D.ctl->error_prints, 1ULL);
                 if (pr.b < 0) { time = 1e-16 * i * j; sub = SDMD_SUB_CORECOLLI; done = true; }
             }
             if (!done) {
@@ -1913,7 +1913,7 @@ __device__ inline void d_pc_eval(const DevP &D, PredShared &sh, int a, int p, co
                 if (pr.b < 0 && d_disc(pr, short2) > 0) { s = -1; d2 = short2; sub = SDMD_SUB_CORECOLLI; }
                 else { s = 1; d2 = long2; sub = SDMD_SUB_WELLBOUNC; }
                 time = d_time(pr, s, d2);
-                if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); time = SD_INF; }
+                if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->error_prints, 1ULL); time = SD_INF; }
             }
             pot = 0;
             if (time > 0) flag |= CF_VALID;
@@ -1928,7 +1928,7 @@ __device__ inline void d_pc_eval(const DevP &D, PredShared &sh, int a, int p, co
                 if (D.method_ding) sub = (f.cs == 1) ? SDMD_SUB_TBDHBBRIK : SDMD_SUB_TBDESCAP;
             }
             time = d_time(pr, s, d2);
-            if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); time = SD_INF; }
+            if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->error_prints, 1ULL); time = SD_INF; }
             if (time > 0) flag |= CF_VALID;
         } else if (kind == CK_HBFREE) {
             if (pr.r2 <= D.cut2 && d_check_pair_match(D, i, j) >= 0) {
@@ -1936,7 +1936,7 @@ __device__ inline void d_pc_eval(const DevP &D, PredShared &sh, int a, int p, co
                 if (pr.b < 0 && f.cs == 1 && d_disc(pr, f.lower) > 0) {
                     time = d_time(pr, -1, f.lower);
                     pot = f.lowPot; sub = SDMD_SUB_TBDHBFORM;
-                    if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); time = SD_INF; }
+                    if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->error_prints, 1ULL); time = SD_INF; }
                     if (time > 0) flag |= CF_VALID;
                 }
             }
@@ -1956,7 +1956,7 @@ __device__ inline void d_pc_eval(const DevP &D, PredShared &sh, int a, int p, co
                 if (D.method_ding) sub = (f.cs == 1) ? SDMD_SUB_WELLBOUNC : SDMD_SUB_TBDESCAP;
             }
             time = d_time(pr, s, d2);
-            if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL); time = SD_INF; }
+            if (time < 0) { atomicAdd((unsigned long long *)&D.ctl->error_prints, 1ULL); time = SD_INF; }
             if (time > 0) flag |= CF_VALID;
         }
     }

@@ -61,6 +61,7 @@ static void prepare_cuda(void) {
     if (fresh) {
         SaveData(sysInfo, fileList);
         if (strcmp(wallExist, "smooth") == 0) SaveData(wallInfo, fileList);   /* SGThread.c:37 */
+        if (obstObj.mark) SaveData(obstInfo, fileList);                       /* SGThread.c:38 (CG: refused by the glue) */
 #ifndef GEL
         SDEnergyMin(20000, &atomList);
 #endif

@@ -80,7 +80,7 @@ class CRunStats(C.Structure):
         ("thermostat", C.c_int64), ("pcc", C.c_int64), ("warnings", C.c_int64),
         ("pair_predictions", C.c_int64), ("gaussians_used", C.c_int64),
         ("currenttime", C.c_double), ("stop_reason", C.c_int32), ("error", C.c_int32),
-        ("wall", C.c_int64),
+        ("wall", C.c_int64), ("error_prints", C.c_int64),
     ]
 
     def as_dict(self):

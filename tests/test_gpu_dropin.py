@@ -8,7 +8,9 @@ import pytest
 
 ROOT = Path(__file__).resolve().parents[1]
 REF = ROOT / "oracle" / "_ref"
-DROPIN = ROOT / "sdmd_b200" / "host" / "_build" / "sDMD_cuda"
+# the fixed-seed build (-DDEBUG_RANDOM, like oracle/_ref/sDMD_ref): byte-for-byte comparisons need the same seed on both sides;
+# the production binary sDMD_cuda seeds from time(NULL) like upstream
+DROPIN = ROOT / "sdmd_b200" / "host" / "_build" / "sDMD_cuda_fixedseed"
 
 pytestmark = pytest.mark.gpu
 
@@ -56,27 +58,34 @@ def _set_param(work, line_no, text):
     p.write_text("\n".join(lines) + "\n")
 
 
-def test_dropin_continue_run_matches_reference(tmp_path):
+@pytest.mark.parametrize("first_leg,second_leg", [("ref", "gpu"), ("gpu", "gpu"), ("gpu", "ref")],
+                         ids=["ref_then_dropin", "dropin_then_dropin", "dropin_then_ref"])
+def test_dropin_continue_run_matches_reference(tmp_path, first_leg, second_leg):
     """`continue` runs (parameter.txt line 1, the annealing schedule of demo/Folding/fold.bash): 100 time units new,
-    then continued to 200 from savedData.dat — the drop-in's second leg must write what the reference's writes."""
+    then continued to 200 from savedData.dat.  Every combination of who writes the checkpoint and who resumes from it —
+    stock -> drop-in, drop-in -> drop-in (a savedData.dat the GPU driver wrote, read back by the GPU driver) and
+    drop-in -> stock — must end with the files the all-stock pair of runs writes."""
     if not (REF / "sDMD_ref").exists() or not DROPIN.exists():
         pytest.skip("needs oracle/_ref/sDMD_ref and the drop-in driver")
+    binaries = {"ref": REF / "sDMD_ref", "gpu": DROPIN}
     outs = {}
-    for tag, binary in (("ref", REF / "sDMD_ref"), ("gpu", DROPIN)):
+    for tag, legs in (("want", ("ref", "ref")), ("got", (first_leg, second_leg))):
         work = tmp_path / tag
-        _run(REF / "sDMD_ref", work, 100)          # identical first leg from the stock binary
+        _run(binaries[legs[0]], work, 100)
         _set_param(work, 0, "Continue?          continue")
         _set_param(work, 1, "Time               200")
-        r = subprocess.run([str(binary), "-f", "ala10.gro", "-i", str(work / "input"), "-o", str(work / "out")],
+        r = subprocess.run([str(binaries[legs[1]]), "-f", "ala10.gro", "-i", str(work / "input"), "-o", str(work / "out")],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         outs[tag] = r.stdout.replace("\r", "\n")
+    # (savedData.dat itself holds raw heap pointers of the writing process — two stock runs already differ in it — so what is
+    # compared is everything the resumed run derives from it)
     for name in ("out_trj.gro", "out_cnt.txt"):
-        a = (tmp_path / "ref" / "out" / name).read_bytes()
-        b = (tmp_path / "gpu" / "out" / name).read_bytes()
+        a = (tmp_path / "want" / "out" / name).read_bytes()
+        b = (tmp_path / "got" / "out" / name).read_bytes()
         assert len(a) > 1000 and a == b, name
     for key in ("collision times", "bond times", "thermostat times", "PBC&CC times"):
-        assert _counter(outs["ref"], key) == _counter(outs["gpu"], key), key
+        assert _counter(outs["want"], key) == _counter(outs["got"], key), key
 
 
 @pytest.mark.parametrize("wall_type", ["parallel", "cylinder", "obstacles", "tunnel"])
@@ -104,6 +113,14 @@ def test_dropin_walled_run_matches_reference(tmp_path, wall_type):
         a = (tmp_path / "ref" / "out" / name).read_bytes()
         b = (tmp_path / "gpu" / "out" / name).read_bytes()
         assert len(a) > 1000 and a == b, name
+    # the same SET of output files (WallInfo.dat / ObstInfo.dat of Prepare(), SGThread.c:37-38, are read by the analysis tools:
+    # analysis/SystemInformation.c:373-383) with the same bytes; the log carries wall-clock stamps and is left out
+    names = lambda tag: sorted(p.name for p in (tmp_path / tag / "out").iterdir())
+    assert names("ref") == names("gpu")
+    for name in names("ref"):
+        if name.endswith("Info.dat"):
+            assert (tmp_path / "ref" / "out" / name).read_bytes() == (tmp_path / "gpu" / "out" / name).read_bytes(), name
+    assert any(n.endswith("Info.dat") for n in names("ref"))
     for key in ("collision times", "bond times", "thermostat times", "PBC&CC times", "Wall times"):
         assert _counter(outs["ref"], key) == _counter(outs["gpu"], key), key
     assert _counter(outs["gpu"], "Wall times") > 0

@@ -77,6 +77,7 @@ def test_device_event_loop_matches_reference(capi, case, loop_mode):
     ref = [int(v) for v in fin.extra["stats"][:9]]
     got = [st[k] for k in ("frame", "iterations", "count_recal", "collision", "bond", "hb", "hb_neighbor", "thermostat", "pcc")]
     assert got == ref
+    assert st["warnings"] == int(fin.extra["stats"][9])   # warningsum
     assert r.potential_energy() == fin.extra["epot"][0]
     if "charge" in case:   # charge sources: ChargeTime / ChargeEvent, centre-of-mass term of ThermostatEvent (-COM)
         assert r.kinetic_energy() == fin.extra["ekin"][0] and (tr["type"] == 8).sum() > 0
@@ -250,6 +251,41 @@ def test_round_trip_properties_1m(capi):
     assert mutual.sum() > 1000
     assert np.array_equal(t[mutual].view(np.int64), t[p[mutual]].view(np.int64))
     assert np.all(t[1:] > 0)
+
+
+@pytest.mark.parametrize("n_axis,a,jitter,step_e", [
+    (100, 8.0, 0.3, 0.2),      # THE bench box (bench.py pass1m / loop: gel_box(100, a=8.0, jitter=0.3), default seed)
+    (100, 8.0, 0.3, -0.2),     # same box, attractive well (e = -0.2)
+    (80, 5.0, 0.3, 0.2),       # C5's second density at 512 000 atoms: ~6 atoms per cell, ~160 candidates, ~18 in the scan sphere
+    (100, 5.0, 0.3, -0.2),     # ... and at 10^6 atoms with the well
+    (72, 4.4, 0.15, 0.2),      # denser still (373 248 atoms, ~28 in the scan sphere): survivor lists past their capacity at scale
+], ids=["bench_1m_a8", "bench_1m_a8_well", "dense_512k_a5", "dense_1m_a5_well", "overflow_373k_a4.4"])
+def test_full_size_pass_elementwise_against_oracle(capi, n_axis, a, jitter, step_e):
+    """The configurations the bench numbers are quoted on, element by element against the CPU oracle on identical inputs:
+    PBC + link list (reference byte layout), every event slot after Predict(all) (time / potential bits, partner, type,
+    sub-type, partnerCounter), the whole tournament tree, and the pair-evaluation count (TimePrediction.c:105)."""
+    from oracle.oracle_py import Oracle
+    from sdmd_b200.synth import gel_box
+    hv0, rng = gel_box(n_axis, a=a, jitter=jitter, step_e=step_e)
+    n = hv0.natom
+    gauss = rng.standard_normal(n)
+    ho = hv0.copy(); o = Oracle(ho); o.rng_feed(gauss)
+    hg = hv0.copy(); r = capi.Replica(hg, device=0); r.rng_feed(gauss)
+    o.pbc_full(); o.cell_build(); o.predict_all(); o.cbt_build()
+    r.pbc_full(); r.cell_build(); r.predict_all(); r.cbt_build()
+    assert np.array_equal(r.celllist(), o.celllist())
+    r.download(hg)
+    assert_fields_equal(hg, ho, SLOT_FIELDS + ("cell_idx", "x", "y", "z"), what="after Predict(all): ")
+    gn, gl = r.cbt()
+    on, ol = o.cbt()
+    assert np.array_equal(gn[1:], on[1:]) and np.array_equal(gl[1:], ol[1:])
+    sg, so = r.stats(), o.stats()
+    assert sg["pair_predictions"] == so["pair_predictions"] and so["pair_predictions"] > 20 * n
+    assert sg["gaussians_used"] == so["gaussians_used"] == n
+    assert sg["warnings"] == so["warnings"]
+    if n_axis == 100 and a == 8.0 and step_e == 0.2:
+        assert so["pair_predictions"] == 41027204      # the count bench.py's two arms report for this box
+    r.close(); o.close()
 
 
 @pytest.mark.parametrize("threads", [256, 128])
@@ -560,6 +596,31 @@ def test_dense_gel_live_reference(capi):
         assert_trace_equal(tr, ref_trace(fin))
         r.download(hv)
         assert_fields_equal(hv, fin, STATE_FIELDS, what="final state: ")
+        r.close()
+
+
+def test_warningsum_live_reference(capi):
+    """`warningsum`: 8^3 GEL atoms 3.95 A apart (inside the 4.0 A hard core) make FindPair warn for every nearest-neighbour
+    evaluation (ToolFunctions.c:119-139); `stats.warnings` of the CUDA path equals the reference's counter after Predict(all)
+    plus 2000 loop iterations, on the one-block and the overlapped-sweep driver."""
+    from oracle.make_golden import REFDIR as ref_dir
+    if not (ref_dir / "ref_harness_gel").exists():
+        pytest.skip("oracle/_ref/ref_harness_gel not built")
+    n_it = 2000
+    pre, post, fin = _live_case("gel8w", harness="ref_harness_gel", coord="GEL8.gro", max_iter=n_it, n_gauss=20000, extra=[], gel_n=8,
+                                gel_a_nm=0.395)
+    for mode in (0, 2):
+        hv, r = _replica(capi, pre)
+        r.set_loop_mode(mode)
+        r.pbc_full(); r.cell_build(); r.predict_all(); r.cbt_build()
+        r.download(hv)
+        assert_fields_equal(hv, post, SLOT_FIELDS, what="after Predict(all): ")
+        assert r.stats()["warnings"] == 6 * 512
+        assert r.potential_energy() == post.extra["epot"][0]   # the harness calls CalPotenE here too: 3 * 512 more warnings
+        st, tr = r.run(max_iter=n_it, trace_cap=n_it)
+        assert st["error"] == 0
+        assert_trace_equal(tr, ref_trace(fin))
+        assert st["warnings"] == int(fin.extra["stats"][9]) > 9 * 512
         r.close()
 
 

@@ -66,6 +66,7 @@ def test_event_loop_trace(case):
     got = [st[k] for k in ("frame", "iterations", "count_recal", "collision", "bond", "hb", "hb_neighbor", "thermostat", "pcc")]
     got[0] = st["frame"]  # absolute frame counter
     assert got == [int(v) for v in ref[:9]]
+    assert st["warnings"] == int(ref[9])              # warningsum (0 in every shipped fixture; see test_warningsum_against_live_reference)
     assert o.potential_energy() == fin.extra["epot"][0]
     if case == "ala10_hb":
         assert st["hb"] > 0 and st["hb_neighbor"] > 0  # the fixture really exercises the HB paths
@@ -194,6 +195,39 @@ def test_gel_42875_against_live_reference(tmp_path):
     st, tr = o.run(max_iter=len(want), trace_cap=len(want))
     assert_trace_equal(tr, want)
     assert_fields_equal(hv, fin, STATE_FIELDS)
+
+
+@pytest.mark.refbin
+def test_warningsum_against_live_reference():
+    """`warningsum` (DMD.c:61): an 8^3 GEL lattice at 3.95 A puts every nearest neighbour inside the 4.0 A hard core, so
+    FindPair's too-small warning (ToolFunctions.c:119-139) fires for each of them in Predict(all) and again in every
+    re-prediction; the oracle's `warnings` must equal the reference's count, and its negative-time / bond-error prints
+    (`error_prints`, "!!ERROR!!" lines that never touch warningsum) stay out of it."""
+    if not (REFDIR / "ref_harness_gel").exists():
+        pytest.skip("oracle/_ref/ref_harness_gel not built (needs /root/reference at build time)")
+    from oracle.make_golden import run_case
+    from sdmd_b200.hostview import HostView
+    import shutil
+    import tempfile
+    from pathlib import Path
+    work = Path(tempfile.mkdtemp(prefix="s", dir="/tmp"))
+    try:
+        snaps = run_case("gel8w", work, harness="ref_harness_gel", coord="GEL8.gro", max_iter=2000, n_gauss=20000,
+                         extra=[], gel_n=8, gel_a_nm=0.395)
+        pre, post, fin = (HostView.from_snapshot(p) for p in snaps)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+    hv, o = _prepare(pre)
+    o.pbc_full(); o.cell_build(); o.predict_all()
+    assert_fields_equal(hv, post, SLOT_FIELDS, what="after Predict(all): ")
+    assert o.stats()["warnings"] == 6 * 512
+    assert o.potential_energy() == post.extra["epot"][0]   # the harness calls CalPotenE here too: 3 * 512 more warnings (ToolFunctions.c:684-752)
+    o.cbt_build()
+    want = ref_trace(fin)
+    st, tr = o.run(max_iter=len(want), trace_cap=len(want))
+    assert_trace_equal(tr, want)
+    assert_fields_equal(hv, fin, STATE_FIELDS)
+    assert st["warnings"] == int(fin.extra["stats"][9]) > 6 * 512
 
 
 def test_remd_rearrange_rule():
