@@ -34,14 +34,8 @@ def build():
     jobs = [(f"k2_{k2}_f{k2f}", [f"-DK2_MINBLOCKS={k2}", f"-DK2F_MINBLOCKS={k2f}"]) for k2, k2f in VARIANTS]
     if len(sys.argv) > 2:
         jobs = [(a.split("=", 1)[0], [f for f in a.split("=", 1)[1].split(",") if f]) for a in sys.argv[2:]]
-    procs = []
-    for name, flags in jobs:
-        cmd = ["nvcc", *capi.NVCC_FLAGS, "-Xptxas", "-v", *flags, f"-I{ROOT / 'include'}",
-               f"-I{ROOT / 'sdmd_b200' / 'csrc'}", str(ROOT / "sdmd_b200" / "csrc" / "sdmd_cuda.cu"), "-o", str(VDIR / f"lib_{name}.so"), "-ldl"]
-        procs.append(subprocess.Popen(cmd, stdout=open(VDIR / f"ptxas_{name}.log", "w"), stderr=subprocess.STDOUT))
-    for p in procs:
-        if p.wait():
-            raise SystemExit("nvcc failed")
+    for name, flags in jobs:      # every translation unit with the variant's flags (capi.build compiles them in parallel)
+        capi.build(extra_flags=flags, out=VDIR / f"lib_{name}.so")
 
 
 def run():

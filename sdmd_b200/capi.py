@@ -45,20 +45,59 @@ class SdmdError(RuntimeError):
     pass
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile libsdmd_cuda.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [PKG / "csrc" / "sdmd_cuda.cu"]
-    deps = srcs + [PKG / "csrc" / "sdmd_dev.cuh", PKG / "csrc" / "sdmd_dev_body.cuh", ROOT / "include" / "sdmd_cuda.h"]
-    if not force and LIB_PATH.exists() and all(LIB_PATH.stat().st_mtime >= d.stat().st_mtime for d in deps):
-        return LIB_PATH
-    cmd = ["nvcc", *NVCC_FLAGS, f"-I{ROOT / 'include'}", f"-I{PKG / 'csrc'}", *map(str, srcs), "-o", str(LIB_PATH), "-ldl"]
+CSRC = PKG / "csrc"
+SOURCES = ["sdmd_cuda.cu", "sdmd_k2_tile.cu"]            # one object per translation unit, rebuilt only when it (or a header) changed
+HEADERS = [CSRC / "sdmd_dev.cuh", CSRC / "sdmd_dev_body.cuh", CSRC / "sdmd_host.h", ROOT / "include" / "sdmd_cuda.h"]
+OBJ_DIR = ROOT / "build" / "obj"
+PTXAS_LOG = ROOT / "profiles" / "ptxas"                  # registers / spills / shared memory per kernel, tracked (one file per TU)
+
+
+def _compile_tu(name: str, extra_flags=()) -> tuple[str, int, str]:
+    obj = OBJ_DIR / (name + ".o")
+    cmd = ["nvcc", *[f for f in NVCC_FLAGS if f != "-shared"], "-Xptxas", "-v", *extra_flags, f"-I{ROOT / 'include'}", f"-I{CSRC}",
+           "-c", str(CSRC / name), "-o", str(obj)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return " ".join(cmd), r.returncode, r.stdout + r.stderr
+
+
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: Path | None = None) -> Path:
+    """Compile libsdmd_cuda.so in-tree for sm_100a (nvcc cross-compiles without a GPU).  `extra_flags` / `out` build a named
+    variant (scripts/k2_variants.py) without touching the shipped library or the object cache."""
+    from concurrent.futures import ThreadPoolExecutor
+    lib_path = out or LIB_PATH
+    variant = bool(extra_flags) or out is not None
+    OBJ_DIR.mkdir(parents=True, exist_ok=True)
+    newest_hdr = max(h.stat().st_mtime for h in HEADERS if h.exists())
+    stale = []
+    for name in SOURCES:
+        obj = OBJ_DIR / (name + ".o")
+        if force or variant or not obj.exists() or obj.stat().st_mtime < max(newest_hdr, (CSRC / name).stat().st_mtime):
+            stale.append(name)
+    if not stale and lib_path.exists() and all(lib_path.stat().st_mtime >= (OBJ_DIR / (n + ".o")).stat().st_mtime for n in SOURCES):
+        return lib_path
+    with ThreadPoolExecutor(len(SOURCES)) as ex:
+        results = list(ex.map(lambda n: (n, *_compile_tu(n, extra_flags)), stale))
+    for name, cmd, rc, log in results:
+        if verbose or rc:
+            print(cmd)
+            print(log)
+        if rc:
+            raise SdmdError(f"nvcc failed building {name}")
+        if not variant:
+            PTXAS_LOG.mkdir(parents=True, exist_ok=True)
+            keep = [ln for ln in log.splitlines() if "ptxas info" in ln or "Compiling entry" in ln or "Function properties" in ln or "bytes stack frame" in ln]
+            (PTXAS_LOG / (name + ".txt")).write_text("\n".join(keep) + "\n")
+    cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *[str(OBJ_DIR / (n + ".o")) for n in SOURCES], "-o", str(lib_path), "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:
         print(" ".join(cmd))
         print(r.stdout, r.stderr)
     if r.returncode:
-        raise SdmdError("nvcc failed building libsdmd_cuda.so")
-    return LIB_PATH
+        raise SdmdError("nvcc failed linking libsdmd_cuda.so")
+    if variant:                                           # the cache now holds variant objects: force a rebuild next time
+        for n in SOURCES:
+            (OBJ_DIR / (n + ".o")).unlink(missing_ok=True)
+    return lib_path
 
 
 _lib = None

@@ -12,6 +12,7 @@
 #include <dlfcn.h>
 #include <cooperative_groups.h>
 #include "sdmd_dev.cuh"
+#include "sdmd_host.h"
 
 // ===================================================================================================
 // host context
@@ -325,12 +326,6 @@ __global__ void k_cell_permute(DevP D, const int *sorted_atom, SRec *srec, float
 // ===================================================================================================
 // kernels: full-system prediction (K2)
 // ===================================================================================================
-struct SlotBuf {
-    double *time, *pot;
-    int *partner;
-    i64 *pcounter;
-    uint8_t *type, *sub;
-};
 __device__ __forceinline__ SlotSrc as_src(const SlotBuf &b) {
     SlotSrc S;
     S.time = b.time; S.pot = b.pot; S.partner = b.partner; S.pcounter = b.pcounter; S.type = b.type; S.sub = b.sub;
@@ -438,7 +433,7 @@ __global__ void __launch_bounds__(128, LEAN ? K2_MINBLOCKS_LEAN : K2_MINBLOCKS) 
 }
 
 // scan slot (0..26) of neighbour cell offset (dx,dy,dz), inverse of the DMD.c:118-120 tables
-__constant__ int c_kinv[27] = {14, 11, 23, 12, 10, 17, 22, 16, 24, 13, 9, 19, 8, 0, 1, 20, 2, 6, 21, 15, 25, 18, 3, 5, 26, 4, 7};
+static __constant__ int c_kinv[27] = {14, 11, 23, 12, 10, 17, 22, 16, 24, 13, 9, 19, 8, 0, 1, 20, 2, 6, 21, 15, 25, 18, 3, 5, 26, 4, 7};
 __device__ __forceinline__ int d_scan_slot(const DevP &D, int i, int a) {
     int k = 0;
 #pragma unroll
@@ -1362,7 +1357,11 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     P.cut2_f32 = nextafterf((float)(P.cut2 * (1.0 + 1e-4)), INFINITY);
     for (int k = 0; k < 3; k++) P.cellsize_f[k] = (float)P.cellsize[k];
     P.sloc = c->d_sloc; P.scell = c->d_scell;
-    if (n < (1 << 27)) {
+    {
+        int trc = sdmd_k2_tile_configure(P, c->device);   // bond-free systems: round 0 as one tile kernel, no survivor rows in HBM
+        if (trc < 0) return set_err(SDMD_ERR_CUDA, "tile kernel configuration", cudaGetLastError());
+    }
+    if (n < (1 << 27) && !P.tile_tx) {
         // row size: a sparse bond-free box (the GEL lattices: ~4 atoms expected inside the scan sphere) gets 64-byte rows, which
         // halves the footprint the evaluation kernel streams through L2 (287 -> 275 us at 1M atoms); longer lists overflow
         // into the exact in-kernel re-scan either way
@@ -1694,7 +1693,8 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
     CK(cudaMemsetAsync(c->d_sum, 0, sizeof(unsigned long long), c->stream));
     {
         Timer t(c, "predict_all");
-        if (c->P.surv) {
+        const bool tile = c->P.tile_tx > 0;
+        if (c->P.surv && !tile) {
             k_predict_all_filter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P);
             c->launches++;
         }
@@ -1706,7 +1706,10 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
         // systems without bonds, hydrogen bonds and single-body sources (the GEL boxes) run the instance with those
         // predictors compiled out
         const bool lean = K2_LEAN && c->P.gel_mode && !c->P.hydrogen_bond && !c->P.single_body;
-        if (lean)
+        if (tile) {
+            Round0Out ro = {c->npair, c->second, c->bp_time, c->bp_j, c->pcount, c->pwho};
+            if (sdmd_k2_tile_launch(c->P, B, ro, g_base, c->stream)) return set_err(SDMD_ERR_CUDA, "k_predict_all_tile", cudaGetLastError());
+        } else if (lean)
             k_predict_all_round<true><<<grid, 128, 0, c->stream>>>(c->P, B, B, nullptr, nullptr, 0, c->npair, c->second, c->bp_time, c->bp_j,
                                                                    c->pcount, c->pwho, c->d_sum, g_base);
         else

@@ -53,6 +53,14 @@ struct SlotSrc {
     const uint8_t *type, *sub;
 };
 
+// one set of event-slot arrays (the live ones or a relaxation buffer of the full-system pass)
+struct SlotBuf {
+    double *time, *pot;
+    int *partner;
+    i64 *pcounter;
+    uint8_t *type, *sub;
+};
+
 struct Slot {
     double time, pot;
     double m2;      // value of the best candidate that did NOT win (used by the full-system pass)
@@ -157,6 +165,9 @@ struct DevP {
     const int *scell;
     float cut2_f32;          // cut2 * (1 + 1e-4), rounded up: superset sphere of the single-precision test
     float cellsize_f[3];
+    // round 0 as one tile kernel (sdmd_k2_tile.cu): own cells per thread block, halo capacity in atoms, dynamic shared memory
+    int tile_tx, tile_ty, tile_tz, tile_hcap, tile_smem;
+    float tile_cut2f;        // superset sphere of the tile kernel's single-precision test (tile-relative coordinates)
     // Overlapped sweep (large-system loop): while the grid-wide UpdateData/TimeForward sweep of event n is still
     // running, the event block already works on event n.  x/y/z/ev_time above are then the buffer the sweep WRITES;
     // lz_* is the buffer it reads (state before the sweep).  The event block reads every atom other than the event's

@@ -10,9 +10,9 @@ __device__ __forceinline__ double d_rt(const DevP &D, int j) { return d_lz(D, j)
 __device__ __forceinline__ double d_stime(const DevP &D, const SlotSrc &S, int j) { return S.time == D.ev_time ? d_rt(D, j) : S.time[j]; }
 
 // neighbour-cell offsets, DMD.c:118-120
-__constant__ int c_offx[27] = {0, 1, 0, 0, 0, 1, 1, 1, -1, 0, 0, 0, -1, -1, -1, 0, 0, 1, -1, 1, -1, -1, -1, 1, 1, 1, -1};
-__constant__ int c_offy[27] = {0, 0, 1, 0, 1, 0, 1, 1, 0, -1, 0, -1, 0, -1, -1, -1, 1, 0, 0, -1, 1, -1, 1, -1, 1, -1, 1};
-__constant__ int c_offz[27] = {0, 0, 0, 1, 1, 1, 0, 1, 0, 0, -1, -1, -1, 0, -1, 1, -1, -1, 1, 0, 0, 1, -1, -1, -1, 1, 1};
+static __constant__ int c_offx[27] = {0, 1, 0, 0, 0, 1, 1, 1, -1, 0, 0, 0, -1, -1, -1, 0, 0, 1, -1, 1, -1, -1, -1, 1, 1, 1, -1};
+static __constant__ int c_offy[27] = {0, 0, 1, 0, 1, 0, 1, 1, 0, -1, 0, -1, 0, -1, -1, -1, 1, 0, 0, -1, 1, -1, 1, -1, 1, -1, 1};
+static __constant__ int c_offz[27] = {0, 0, 0, 1, 1, 1, 0, 1, 0, 0, -1, -1, -1, 0, -1, 1, -1, -1, 1, 0, 0, 1, -1, -1, -1, 1, 1};
 
 enum { FP_COLLISION = 0, FP_CONSTRAINT = 1, FP_HB = 2, FP_NEIGHBOR = 3 };
 
@@ -480,7 +480,7 @@ __device__ inline void d_collision_time_2stage(const DevP &D, const SlotSrc &S, 
 // cell-sorted tiles; survivors go to HBM in scan order (they are few: ~6 of ~41 candidates at 8 A spacing).
 // neighbour-cell offsets of scan slot k (DMD.c:118-120) as floats: the loop counter is warp-uniform, so these are
 // constant-bank operands
-__constant__ float c_koff[27][3] = {
+static __constant__ float c_koff[27][3] = {
     {0, 0, 0},   {1, 0, 0},   {0, 1, 0},   {0, 0, 1},   {0, 1, 1},   {1, 0, 1},  {1, 1, 0},   {1, 1, 1},   {-1, 0, 0},
     {0, -1, 0},  {0, 0, -1},  {0, -1, -1}, {-1, 0, -1}, {-1, -1, 0}, {-1, -1, -1}, {0, -1, 1}, {0, 1, -1},  {1, 0, -1},
     {-1, 0, 1},  {1, -1, 0},  {-1, 1, 0},  {-1, -1, 1}, {-1, 1, -1}, {1, -1, -1}, {1, 1, -1},  {1, -1, 1},  {-1, 1, 1}};
