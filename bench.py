@@ -12,9 +12,15 @@ Workloads (``--workload``):
           ExchangeRate 50; one step = run to the next exchange boundary + CalPotenE + exchange (NCCL all-gather);
           metric = REMD replica-events/s (sum over replicas).
 
-``--impl reference`` times the reference's CPU implementation of the same path on the host cores: the oracle
-port (oracle/sdmd_oracle.c, pinned bit-exact against the reference) for the 1M box — the reference itself
-cannot allocate its (N+1)^2 connectionMap there — and the compiled reference (oracle/_ref) for ala10.
+The default line also carries two sub-records measured in the same run: ``loop`` (events/s of the device-resident loop on
+the same 1M box) and ``remd`` (ala10, one replica per rank, temperatures of demo/REMD/REMDConfig.txt, NCCL exchange every
+50 tu: replica-events/s, events per rank, microseconds per exchange and a parity bit — the (num, T) walk of every rank
+against the same ensemble run in ONE process with the Server.c sweep on the host).
+
+``--impl reference`` times the reference's CPU implementation of the same path on the host cores, one worker process per
+rank of the launch (rank 0 starts them all): the UNMODIFIED reference itself — oracle/_ref/ref_bench_gel for the 1M box
+(its dense connectionMap answered by a zero window, see oracle/ref_bench.c), sDMD_ref + sServer for the remd sub-record —
+or, where oracle/_ref is absent, the oracle port (oracle/sdmd_oracle.c, pinned bit-exact against the reference at 10^6 atoms).
 """
 from __future__ import annotations
 
@@ -130,6 +136,16 @@ class Dist:
         t = self._tensor([x])
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return float(t.item())
+
+    def gather_vec(self, vals, world: int):
+        """Every rank contributes a short float vector; returns the list of all of them (all-reduce of a zero-padded matrix)."""
+        if self.world == 1:
+            return [list(vals)]
+        m = [[0.0] * len(vals) for _ in range(world)]
+        m[self.rank] = [float(v) for v in vals]
+        t = self._tensor(m)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [[float(x) for x in row] for row in t.cpu().tolist()]
 
     def bcast_bytes(self, b: bytes | None, n: int) -> bytes:
         if self.world == 1:
@@ -288,9 +304,12 @@ def cuda_pass(args, dist):
     if tf.exists():
         try:
             t = json.loads(tf.read_text())
-            if int(t.get("natom", 0)) == n:
-                roof["traffic"] = float(t["k_predict_all_filter"]) + float(t["k_predict_all_round_round0"])
+            tile = os.environ.get("SDMD_K2_TILE", "") == "1"
+            names = ["k_predict_all_tile"] if tile else ["k_predict_all_filter", "k_predict_all_round<1>"]
+            if int(t.get("natom", 0)) == n and all(k in t["kernels"] for k in names):
+                roof["traffic"] = sum(float(t["kernels"][k]["dram_bytes"]) for k in names)
                 roof["traffic_source"] = t.get("source", "profiles/ncu_traffic.json")
+                roof["traffic_kernels"] = names
         except Exception:
             pass
     step_ms = ms / args.steps
@@ -312,17 +331,24 @@ def cuda_pass(args, dist):
         "predict_all_rounds": kst["predict_all_rounds"][0] / max(kst["predict_all_rounds"][1], 1),
         "extra": extra,
     }
-    if dist.rank == 0 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_pass_baseline(args)
+    out["loop"] = {"metric": "DMD events/s", "value": extra["loop_events_per_s_1M"], "unit": "events/s",
+                   "iterations_per_s": extra["loop_iterations_per_s_1M"], "natom": n,
+                   "sample": "2048 loop iterations of the device-resident event loop on the same box (sdmd_cuda_run, host wall clock "
+                             "around the call, stats read back); `--workload loop` times it on its own with the sweep's roofline"}
     rep.close()
+    if not args.no_remd:
+        r = remd_subrecord(args, dist)
+        if dist.rank == 0:
+            out["remd"] = r
+    if dist.rank == 0 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_pass_baseline(args, gpu_pairs_per_pass=int(round(pairs / max(args.steps, 1))))
     return out
 
 
-def cpu_pass_baseline(args, n_axis=None, steps=1):
-    """The oracle port (reference algorithm, plain C, 1 thread) on the same synthetic box."""
+def port_pass(n_axis, rank=0, steps=1):
+    """The oracle port (reference algorithm, plain C, 1 thread) on the bench box of `rank`: (pairs per pass, best seconds)."""
     from oracle.oracle_py import Oracle
-    n_axis = n_axis or args.n_axis
-    hv, gauss = make_box(n_axis, 0)
+    hv, gauss = make_box(n_axis, rank)
     o = Oracle(hv)
     t_best, pairs = None, 0
     for _ in range(steps):
@@ -334,47 +360,114 @@ def cpu_pass_baseline(args, n_axis=None, steps=1):
         dt = time.perf_counter() - t0
         pairs = o.stats()["pair_predictions"] - p0
         t_best = dt if t_best is None else min(t_best, dt)
-    return {"value": pairs / t_best, "unit": "pairs/s", "cores": 1, "kind": "port",
-            "sample": f"one full-system pass over the same {hv.natom}-atom box ({pairs} pair evaluations, {t_best:.2f} s); the "
-                      "reference itself cannot allocate its (N+1)^2 connectionMap at this size, the port is pinned bit-exact to it",
-            "seconds": t_best}
+    o.close()
+    return pairs, t_best
+
+
+REF_BENCH = ROOT / "oracle" / "_ref" / "ref_bench_gel"
+
+
+def reference_pass_workers(n_axis, workers, passes, warm=1):
+    """`workers` processes of the UNMODIFIED reference (oracle/_ref/ref_bench_gel), each timing `warm + passes` full-system
+    passes over the same n_axis^3 GEL box (8 A lattice, 0.3 A jitter; the reference draws its own velocities).  Returns
+    (seconds per timed pass for every worker, pair evaluations per pass counted by the pinned port on worker 0's state)."""
+    import shutil
+    import tempfile
+    sys.path.insert(0, str(ROOT))
+    from oracle.make_golden import prepare_input
+    from oracle.oracle_py import Oracle
+    from tests import ref_bench as rb             # test infrastructure around oracle/_ref, used by this CPU leg only
+    write_jittered_gel_gro = rb.write_jittered_gel_gro
+    work = Path(tempfile.mkdtemp(prefix="s", dir="/tmp"))
+    try:
+        inp = prepare_input(work, time_units=10.0)
+        gro = f"GEL{n_axis}.gro"
+        write_jittered_gel_gro(inp / gro, n_axis, 0.8, 0.03, 1575263273)
+        procs = []
+        for w in range(workers):
+            (work / f"out{w}").mkdir()
+            cmd = [str(REF_BENCH), str(warm + passes), "-"] + ([str(work / "state.bin")] if w == 0 else []) + \
+                  ["--", "-f", gro, "-i", str(inp), "-o", str(work / f"out{w}")]
+            procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, cwd=work))
+        secs = []
+        for pr in procs:
+            out = pr.communicate()[0].decode(errors="replace")
+            if pr.returncode != 0:
+                raise RuntimeError("ref_bench_gel failed")
+            s = [float(ln.split()[3]) for ln in out.splitlines() if ln.startswith("pass ")]
+            secs.append(s[warm:])
+        # the reference keeps no evaluation counter: the port (pinned bit-exact to the reference at this size) counts the pair
+        # evaluations of the very pass worker 0 ran, from the state that worker dumped
+        hv, g = rb.view_from_state(work / "state.bin", work)
+        o = Oracle(hv); o.rng_feed(g); o.pbc_full(); o.cell_build(); o.predict_all()
+        pairs = o.stats()["pair_predictions"]
+        o.close()
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+    return secs, pairs
+
+
+def cpu_pass_baseline(args, gpu_pairs_per_pass=None):
+    """CPU baseline of the default workload on one host core: the unmodified reference when oracle/_ref holds it, and the
+    port on the very box the GPU timed (which also pins the pair count of the GPU arm)."""
+    pairs, t_port = port_pass(args.n_axis, 0, 1)
+    port = {"value": pairs / t_port, "unit": "pairs/s", "cores": 1, "kind": "port", "seconds": t_port, "pairs_per_pass": pairs}
+    if gpu_pairs_per_pass is not None:
+        port["gpu_pairs_per_pass"] = gpu_pairs_per_pass
+        port["pair_count_equal"] = bool(gpu_pairs_per_pass == pairs)
+        if gpu_pairs_per_pass != pairs:
+            raise SystemExit(f"bench: GPU pair count {gpu_pairs_per_pass} != CPU port {pairs} on the same box")
+    if REF_BENCH.exists():
+        secs, rpairs = reference_pass_workers(args.n_axis, 1, passes=3, warm=1)
+        t = min(secs[0])
+        return {"value": rpairs / t, "unit": "pairs/s", "cores": 1, "kind": "reference", "seconds": t,
+                "sample": f"3 full-system passes (after 1 warm-up pass) of the unmodified -DGEL reference over a {args.n_axis}^3-atom box of the same "
+                          f"lattice (oracle/_ref/ref_bench_gel: PBC+LinkList+Predict(all)+CreateCBT, {rpairs} pair evaluations per pass, best "
+                          f"{t:.2f} s); its dense connectionMap is answered by a zero window (oracle/ref_bench.c)",
+                "port": port}
+    port["sample"] = (f"one full-system pass over the same {args.n_axis ** 3}-atom box ({pairs} pair evaluations, {t_port:.2f} s) with the oracle "
+                      "port, pinned bit-exact to the reference at this size; oracle/_ref/ref_bench_gel is absent")
+    return port
 
 
 def reference_pass(args, dist):
+    """--impl reference: one CPU worker per rank of the launch (rank 0 starts them all), each on its own host core."""
     if dist.rank != 0:
         return None
-    t0 = time.perf_counter()
-    per = []
-    pairs = 0
-    from oracle.oracle_py import Oracle
-    hv, gauss = make_box(args.n_axis, 0)
-    o = Oracle(hv)
-    for k in range(args.warmup + args.steps):
-        hv.reset_slots()
-        o.rng_feed(gauss)
-        p0 = o.stats()["pair_predictions"]
-        t1 = time.perf_counter()
-        o.pbc_full(); o.cell_build(); o.predict_all(); o.cbt_build()
-        dt = time.perf_counter() - t1
-        if k >= args.warmup:
-            per.append(dt)
-            pairs += o.stats()["pair_predictions"] - p0
-        if time.perf_counter() - t0 > 150 and len(per) >= 1:
-            break
-    tot = sum(per)
-    v = pairs / tot
-    return {
-        "impl": "reference", "metric": "pair time-predictions/s", "value": v, "unit": "pairs/s", "n_gpus": dist.world,
-        "steps": len(per), "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(per), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C5(i) synthetic 1M-particle GEL hard-sphere+step box: full-system pass PBC+LinkList+Predict(all)+CreateCBT",
-                   "natom_per_gpu": hv.natom},
-        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": 1, "kind": "port",
-                         "sample": f"{len(per)} full passes over the {hv.natom}-atom box; reference algorithm restated in C "
-                                   "(oracle/sdmd_oracle.c), single thread like the reference"},
+    W = dist.world
+    cores = os.cpu_count() or 1
+    cfg = {"workload": "C5(i) synthetic 1M-particle GEL hard-sphere+step box: full-system pass PBC+LinkList+Predict(all)+CreateCBT",
+           "natom_per_gpu": args.n_axis ** 3, "lattice": f"{args.n_axis}^3 simple cubic, a=8.0 A, jitter 0.3 A", "T_reduced": 0.6,
+           "cutoff_A": 9.0, "parallelism": f"replicas x{W} (one independent box per CPU worker, no exchange)",
+           "l2": "n/a (host cores)"}
+    if REF_BENCH.exists():
+        secs, pairs = reference_pass_workers(args.n_axis, W, passes=args.steps, warm=max(1, min(args.warmup, 2)))
+        per_worker = [sum(s) for s in secs]
+        tot = max(per_worker)
+        nsteps = len(secs[0])
+        v = W * pairs * nsteps / tot
+        kind, sample = "reference", (f"{W} process(es) of the unmodified -DGEL reference (oracle/_ref/ref_bench_gel), {nsteps} timed passes each "
+                                     f"over a {args.n_axis}^3-atom box; {pairs} pair evaluations per pass (counted by the pinned port)")
+    else:
+        import multiprocessing as mp
+        with mp.get_context("spawn").Pool(W) as pool:
+            res = pool.starmap(port_pass, [(args.n_axis, r, args.steps) for r in range(W)])
+        pairs = res[0][0]
+        tot = max(t for _, t in res) * args.steps
+        nsteps = args.steps
+        v = sum(p for p, _ in res) * nsteps / tot
+        kind, sample = "port", f"{W} process(es) of the oracle port, best of {nsteps} passes each (oracle/_ref absent)"
+    out = {
+        "impl": "reference", "metric": "pair time-predictions/s", "value": v, "unit": "pairs/s", "n_gpus": W,
+        "steps": nsteps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / nsteps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": min(W, cores), "kind": kind, "sample": sample, "host_cores": cores},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_remd:
+        out["remd"] = reference_remd_server(args, W)
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -480,6 +573,145 @@ def remd_ladder_K(n):
     if n <= len(REMD_TEMPS_K):
         return list(REMD_TEMPS_K[:n])
     return [float("%.2f" % t) for t in np.geomspace(REMD_TEMPS_K[0], REMD_TEMPS_K[-1], n)]
+
+
+REMD_SERVER_SEED = 12345
+REMD_GAUSS = 400000          # thermostat draws fed to every replica up front (a 50 tu period of ala10 uses a few thousand)
+
+
+def _ala10_replica(capi, replica_id, device):
+    """ala10 replica `replica_id` ready to run: temperature of the demo ladder, its own glibc rand() thermostat stream."""
+    import ctypes
+    hv = ala10_view(replica_id)
+    rep = capi.Replica(hv, device=device)
+    rep.set_timing(0)
+    ctypes.CDLL("libc.so.6").srand(1575263273 + replica_id)
+    rep.rng_fill_libc(hv.natom + REMD_GAUSS)
+    rep.pbc_full(); rep.cell_build(); rep.predict_all(); rep.cbt_build()
+    return hv, rep
+
+
+def remd_subrecord(args, dist):
+    """BASELINE configs[1] inside the default run: one ala10 replica per rank, exchange every --exchange-rate tu through
+    sdmd_remd_exchange_energy (CalPotenE on the device -> NCCL all-gather of 32 B per rank -> replicated Server.c sweep).
+    The walk of (num, T) over all ranks is compared with the same ensemble run in one process on rank 0's GPU."""
+    from sdmd_b200 import capi
+    from sdmd_b200.remd import RemdEnsemble
+    W, periods, rate = dist.world, args.remd_periods, float(args.exchange_rate)
+    hv, rep = _ala10_replica(capi, dist.rank, dist.local_rank)
+    if W > 1:
+        uid = capi.nccl_unique_id() if dist.rank == 0 else None
+        uid = dist.bcast_bytes(uid, 128)
+        rep.remd_init(W, dist.rank, uid, server_seed=REMD_SERVER_SEED)
+    else:
+        rep.remd_seed_server(REMD_SERVER_SEED)
+    state = {"num": dist.rank + 1, "T": hv.target_temperature, "next": rate}
+    walk, xchg_s = [], []
+
+    def period():
+        st, _ = rep.run(t_until=state["next"])
+        if st["stop_reason"] != 1:
+            raise SystemExit(f"remd sub-record: unexpected stop {st['stop_reason']} (thermostat stream exhausted?)")
+        t0 = time.perf_counter()
+        state["num"], state["T"], _e = rep.remd_exchange_energy(state["num"], state["T"])
+        xchg_s.append(time.perf_counter() - t0)
+        state["next"] += rate
+        walk.append((state["num"], state["T"]))
+        return st
+
+    period()                                            # warm-up period (also the first, lazily connecting, collective)
+    f0 = rep.stats()["frame"]
+    xchg_s.clear()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(periods):
+        st = period()
+    rep.synchronize()
+    dt = time.perf_counter() - t0
+    dist.barrier()
+    dt = dist.max(dt)
+    mine = float(st["frame"] - f0)
+    per_rank = dist.gather_vec([mine], W)               # events of every rank during the timed periods
+    walks = dist.gather_vec([v for nt in walk for v in nt], W)
+    xs = dist.max(float(np.mean(xchg_s)))
+    rep.close()
+    out = {"metric": "REMD replica-events/s", "value": sum(r[0] for r in per_rank) / dt, "unit": "events/s", "replicas": W,
+           "periods_timed": periods, "exchange_rate_tu": rate, "temperatures_K": REMD_TEMPS_K[:W], "seconds": dt,
+           "events_per_rank": [int(r[0]) for r in per_rank], "us_per_exchange": 1e6 * xs,
+           "exchange": "sdmd_remd_exchange_energy: CalPotenE on the device written into the send record, ncclAllGather of 32 B per rank, "
+                       "replicated Server.c:145-192 sweep" if W > 1 else "single replica: CalPotenE + sweep over one entry, no collective",
+           "limit": "the period lasts as long as the hottest replica (most events per 50 tu) needs"}
+    if dist.rank == 0:
+        # parity: the same replicas in ONE process, coupled by the host-side sweep (tests pin that ensemble to the reference's sServer)
+        reps = []
+        for r in range(W):
+            _, rr = _ala10_replica(capi, r, dist.local_rank)
+            reps.append(rr)
+        ens = RemdEnsemble(reps, [reduced_T(REMD_TEMPS_K[r]) for r in range(W)], rate, server_seed=REMD_SERVER_SEED)
+        for _ in range(periods + 1):
+            ens.step()
+        want = [[v for rec in ens.log[r] for v in (rec[2], rec[1])] for r in range(W)]
+        got = [list(w) for w in walks]
+        out["parity"] = bool(all(len(a) == len(b) and all(float(x) == float(y) for x, y in zip(a, b)) for a, b in zip(got, want)))
+        out["walk_num"] = [[int(w[2 * k]) for k in range(periods + 1)] for w in got]
+        out["swaps_seen"] = int(sum(1 for r in range(W) for k in range(periods + 1) if int(got[r][2 * k]) != r + 1))
+        for rr in reps:
+            rr.close()
+    return out
+
+
+def reference_remd_server(args, W):
+    """Reference arm of the remd sub-record: W unmodified sDMD processes coupled through the reference's own sServer, on the
+    host cores; start-up (parsing, SDEnergyMin, first Predict) is measured by a 0.05-time-unit run and subtracted."""
+    ref = ROOT / "oracle" / "_ref"
+    if not (ref / "sDMD_ref").exists() or not (ref / "sServer").exists():
+        return {"unavailable": "oracle/_ref/sDMD_ref or sServer not built"}
+    import shutil
+    import socket
+    import tempfile
+    rate = float(args.exchange_rate)
+    tu_full = rate * (args.remd_periods + 1) + 1.0
+
+    def run_all(time_units):
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        server = subprocess.Popen([str(ref / "sServer"), str(port), str(W), str(REMD_SERVER_SEED)], stdout=subprocess.DEVNULL,
+                                  stderr=subprocess.DEVNULL)
+        time.sleep(0.2)
+        procs, dirs = [], []
+        t0 = time.perf_counter()
+        for r in range(W):
+            d = Path(tempfile.mkdtemp(prefix=f"sr{r}_", dir="/tmp"))
+            shutil.copytree(ref / "input", d / "input")
+            lines = (ref / "demo_REMD" / "parameter.txt").read_text().splitlines()
+            lines[1] = "Time               %g" % time_units
+            (d / "input" / "parameter.txt").write_text("\n".join(lines) + "\n")
+            (d / "out").mkdir()
+            procs.append(subprocess.Popen([str(ref / "sDMD_ref"), "-i", str(d / "input"), "-f", "ala10.gro", "-o", str(d / "out"), "-REMD", "localhost",
+                                           str(port), "%lf" % reduced_T(REMD_TEMPS_K[r % len(REMD_TEMPS_K)]), str(r + 1), str(int(rate)), str(r)],
+                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))
+            dirs.append(d)
+        events = 0
+        for pr in procs:
+            out, _ = pr.communicate()
+            for line in out.replace("\r", "\n").splitlines():
+                if line.startswith("Calculate event times:"):
+                    events += int(line.split(":")[1])
+        dt = time.perf_counter() - t0
+        try:
+            server.wait(timeout=20)
+        except subprocess.TimeoutExpired:
+            server.kill()
+        for d in dirs:
+            shutil.rmtree(d, ignore_errors=True)
+        return events, dt
+
+    ev0, t_start = run_all(0.05)
+    ev1, t_full = run_all(tu_full)
+    dt = max(t_full - t_start, 1e-9)
+    return {"metric": "REMD replica-events/s", "value": (ev1 - ev0) / dt, "unit": "events/s", "replicas": W, "seconds": dt,
+            "cores": min(W, os.cpu_count() or 1), "kind": "reference", "exchange_rate_tu": rate, "temperatures_K": REMD_TEMPS_K[:W],
+            "sample": f"{W} unmodified sDMD_ref processes + the reference's sServer, {tu_full:g} time units each; start-up ({t_start:.2f} s) "
+                      "measured by a 0.05-time-unit run and subtracted"}
 
 
 def cuda_remd_many(args, dist):
@@ -699,6 +931,8 @@ def main():
     ap.add_argument("--exchange-rate", type=float, default=50.0)
     ap.add_argument("--replicas-per-gpu", type=int, default=1, help="remd workload: independent REMD ensembles packed on each GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-remd", action="store_true", help="default workload: skip the remd sub-record")
+    ap.add_argument("--remd-periods", type=int, default=3, help="timed exchange periods of the remd sub-record (one more runs as warm-up)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
 

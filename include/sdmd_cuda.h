@@ -354,6 +354,11 @@ int  sdmd_host_glibc_rand(uint32_t seed, int64_t n, uint32_t *out);
 /* ReplicaExchange: all-gather (E, T, num) of every rank over NCCL, run the replicated sweep with the
  * shared server seed stream, return this rank's new (T, num). */
 int  sdmd_remd_exchange(sdmd_ctx *ctx, double epot, struct sdmd_remd_temp *T, uint32_t reserved);
+/* The same with CalPotenE fused in (REMD.c:98 + 135-192 in one call): the energy is computed on the device and written
+ * straight into the all-gather's send record — no device->host->device hop in front of the collective.  natom <= 2048.
+ * *epot (may be NULL) returns the energy this replica contributed.  Both calls fail with SDMD_ERR_STATE when
+ * sdmd_remd_seed_server has not been called for the context. */
+int  sdmd_remd_exchange_energy(sdmd_ctx *ctx, struct sdmd_remd_temp *T, double *epot);
 
 /* ---- measurement helpers ------------------------------------------------------------------------- */
 /* average device time (ms) of the last launch of each named kernel, measured with CUDA events on the

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 #include <dlfcn.h>
@@ -48,7 +49,7 @@ struct sdmd_ctx {
     int *npair = nullptr, *pcount = nullptr, *pwho = nullptr, *queue_a = nullptr, *queue_b = nullptr, *nqueue = nullptr;
     double *second = nullptr, *bp_time = nullptr;
     int *bp_j = nullptr;
-    int *cell_of = nullptr, *cell_count = nullptr, *cell_cursor = nullptr, *scan_tmp = nullptr;
+    int *cell_of = nullptr, *cell_count = nullptr, *cell_rank = nullptr, *cell_tmp = nullptr, *scan_tmp = nullptr;
     int *d_cell_start = nullptr, *d_sorted_atom = nullptr;
     SRec *d_srec = nullptr;
     float4 *d_sloc = nullptr;
@@ -61,6 +62,8 @@ struct sdmd_ctx {
     unsigned long long *d_sum = nullptr;
     bool cells_fresh = false;
     int loop_mode = SDMD_LOOP_AUTO;
+    int fix_grid = 0;
+    i64 pa_base[3] = {0, 0, 0};
     int cluster_size = 16;     // blocks per cluster of the mid-size loop (16 = B200's non-portable maximum; 8 measured slower above 8000 atoms)
     double *x2 = nullptr, *y2 = nullptr, *z2 = nullptr, *t2 = nullptr;   // second coordinate/time buffer of the overlapped sweep
     bool counters_known = false;         // h_ctl's g_pos / pair_predictions match the device (nothing consumed since the last pull)
@@ -76,7 +79,7 @@ struct sdmd_ctx {
     void *nccl_lib = nullptr;
     void *nccl_comm = nullptr;
     int nranks = 1, rank = 0;
-    void *d_xchg = nullptr;
+    void *d_xchg = nullptr, *h_xchg = nullptr;   // exchange records: device (all ranks + own send slot), pinned host mirror
 };
 
 template <typename T>
@@ -159,18 +162,22 @@ __global__ void k_pbc_full(DevP D) {
         if (c[k] >= D.box[k]) c[k] -= D.box[k];
         else if (c[k] < 0) c[k] += D.box[k];
     }
-    D.x[i] = c[0]; D.y[i] = c[1]; D.z[i] = c[2];
+    // only what moved is written back (nothing at all for a box that is already wrapped: 24 B per atom instead of 48)
+    if (c[0] != D.x[i]) D.x[i] = c[0];
+    if (c[1] != D.y[i]) D.y[i] = c[1];
+    if (c[2] != D.z[i]) D.z[i] = c[2];
 }
 
 // LinkList("full") step 1, Events.c:129-150: cell index per atom + histogram
-__global__ void k_cell_index(DevP D, int *cell_of, int *cell_count) {
+// (the histogram's atomicAdd also hands every atom its arrival rank inside the cell, so the scatter needs no second atomic)
+__global__ void k_cell_index(DevP D, int *cell_of, int *cell_count, int *arrival) {
     int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (i > D.n) return;
     int idx[3];
     int cell = d_cell_of(D, D.x[i], D.y[i], D.z[i], idx);
     D.cell_idx[3 * i] = idx[0]; D.cell_idx[3 * i + 1] = idx[1]; D.cell_idx[3 * i + 2] = idx[2];
     cell_of[i] = cell;
-    atomicAdd(&cell_count[cell], 1);
+    arrival[i] = atomicAdd(&cell_count[cell], 1);
 }
 
 // exclusive scan of cell_count[0..m) -> cell_start[0..m], 2048 items per block:
@@ -219,7 +226,9 @@ __global__ void __launch_bounds__(512) k_scan_local(const int *in, int *out, int
     }
     if (threadIdx.x == 0) block_sum[blockIdx.x] = total;
 }
-__global__ void __launch_bounds__(512) k_scan_finish(int *out, int *cursor, const int *block_sum, int m, int nb) {
+// k_scan_finish / k_scan_add also publish the occupancy of every cell (DevP::cell_cnt), the list head of the EMPTY cells
+// (k_cell_place writes the heads of the others) and clear the histogram for the next build.
+__global__ void __launch_bounds__(512) k_scan_finish(DevP D, int *out, int *count, const int *block_sum, int m, int nb) {
     __shared__ int red[16];
     __shared__ int s_off;
     int part = 0;
@@ -232,14 +241,21 @@ __global__ void __launch_bounds__(512) k_scan_finish(int *out, int *cursor, cons
         int s = 0;
         for (int q = 0; q < 16; q++) s += red[q];
         s_off = s;
-        if ((int)blockIdx.x == nb - 1) { int tot = s + block_sum[nb - 1]; out[m] = tot; cursor[m] = tot; }
+        if ((int)blockIdx.x == nb - 1) out[m] = s + block_sum[nb - 1];
     }
     __syncthreads();
     int off = s_off;
-    int t0 = blockIdx.x * SCAN_ITEMS + threadIdx.x * 4;
 #pragma unroll
-    for (int q = 0; q < 4; q++)
-        if (t0 + q < m) { int v = out[t0 + q] + off; out[t0 + q] = v; cursor[t0 + q] = v; }
+    for (int q = 0; q < 4; q++) {      // consecutive threads, consecutive cells
+        int t = blockIdx.x * SCAN_ITEMS + q * 512 + threadIdx.x;
+        if (t < m) {
+            out[t] += off;
+            int cnt = count[t];
+            count[t] = 0;
+            D.cell_cnt[t] = cnt;
+            if (cnt == 0) D.celllist[D.n + t + 1] = 0;
+        }
+    }
 }
 __global__ void k_scan_blocks(int *block_sum, int nb) {
     // single thread block; nb is small (<= a few thousand)
@@ -257,30 +273,61 @@ __global__ void k_scan_add(int *out, const int *block_sum, int m, int nb) {
     if (t < m) out[t] += block_sum[t / SCAN_ITEMS];
     if (t == 0) out[m] = block_sum[nb];
 }
-
-__global__ void k_cell_scatter(DevP D, const int *cell_of, int *cursor, int *sorted_atom) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (i > D.n) return;
-    int pos = atomicAdd(&cursor[cell_of[i]], 1);
-    sorted_atom[pos] = i;
+__global__ void k_scan_add_cells(DevP D, int *out, int *count, const int *block_sum, int m, int nb) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < m) {
+        out[t] += block_sum[t / SCAN_ITEMS];
+        int cnt = count[t];
+        count[t] = 0;
+        D.cell_cnt[t] = cnt;
+        if (cnt == 0) D.celllist[D.n + t + 1] = 0;
+    }
+    if (t == 0) out[m] = block_sum[nb];
 }
 
-// per cell: order the segment by descending atom id (= the reference's head-insertion order of a fresh
-// LinkList("full"), Events.c:152-153) and emit the reference-format link list
-__global__ void k_cell_finish(DevP D, const int *cell_start, int *sorted_atom) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= D.ncell) return;
-    int p0 = cell_start[c], p1 = cell_start[c + 1];
-    for (int a = p0 + 1; a < p1; a++) {  // insertion sort, segments are short
-        int v = sorted_atom[a];
-        int b = a - 1;
-        while (b >= p0 && sorted_atom[b] < v) { sorted_atom[b + 1] = sorted_atom[b]; b--; }
-        sorted_atom[b + 1] = v;
+// atoms of a cell side by side, in arrival order
+__global__ void k_cell_scatter(DevP D, const int *cell_of, const int *arrival, const int *cell_start, int *unordered) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i > D.n) return;
+    unordered[cell_start[cell_of[i]] + arrival[i]] = i;
+}
+
+// Every atom finds its final place itself: a fresh LinkList("full") inserts atoms 1..N at the head of their cell's list
+// (Events.c:152-153), so inside a cell the list runs by descending atom id — the rank of an atom is the number of cell mates
+// with a larger id, its successor the largest smaller id.  One pass then writes the reference-format link list and the
+// cell-sorted working set (what k_cell_finish + k_cell_permute did in two passes with a serial sort per cell).
+// parts: as k_cell_permute
+__global__ void k_cell_place(DevP D, const int *cell_of, const int *cell_start, const int *unordered, int *sorted_atom, SRec *srec, float4 *sloc,
+                             int *scell, int parts) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i > D.n) return;
+    if ((parts & 4) && i == 1) D.ctl->cc_floor = ++D.ctl->cc_epoch;   // new link list: every cached candidate list is void
+    const int c = cell_of[i];
+    const int s0 = cell_start[c], s1 = cell_start[c + 1];
+    int rank = 0, next = 0;
+    for (int s = s0; s < s1; s++) {
+        int j = unordered[s];
+        rank += j > i;
+        if (j < i && j > next) next = j;
     }
-    int *cl = D.celllist;
-    D.cell_cnt[c] = p1 - p0;
-    cl[D.n + c + 1] = (p1 > p0) ? sorted_atom[p0] : 0;
-    for (int a = p0; a < p1; a++) cl[sorted_atom[a]] = (a + 1 < p1) ? sorted_atom[a + 1] : 0;
+    const int p = s0 + rank;
+    sorted_atom[p] = i;
+    D.spos[i] = p;
+    D.celllist[i] = next;
+    if (rank == 0) D.celllist[D.n + c + 1] = i;
+    double x = D.x[i], y = D.y[i], z = D.z[i];
+    int t = D.type[i];
+    int cx = D.cell_idx[3 * i], cy = D.cell_idx[3 * i + 1], cz = D.cell_idx[3 * i + 2];
+    double2 *rp = reinterpret_cast<double2 *>(&srec[p]);
+    // cell-local single-precision copy for the neighbour filter (see d_r0_filter)
+    sloc[p] = make_float4((float)(x - cx * D.cellsize[0]), (float)(y - cy * D.cellsize[1]), (float)(z - cz * D.cellsize[2]), __int_as_float(i));
+    scell[p] = c;
+    rp[0] = make_double2(x, y);
+    *reinterpret_cast<int4 *>(rp + 3) = make_int4(t, i, (int)((unsigned)cx | ((unsigned)cy << 16)), cz);
+    if (parts & 2) {
+        rp[1] = make_double2(z, D.vx[i]);
+        rp[2] = make_double2(D.vy[i], D.vz[i]);
+    } else srec[p].z = z;
 }
 
 // occupancy of every cell from an uploaded link list
@@ -362,73 +409,79 @@ __global__ void __launch_bounds__(256, K2F_MINBLOCKS) k_predict_all_filter(DevP 
 #ifndef K2_MINBLOCKS_LEAN
 #define K2_MINBLOCKS_LEAN 5   // 96 registers, no spills (6 blocks: 80 registers with spills, measured 3 % slower)
 #endif
+// round 0: every atom, no duplicate source (one thread per cell-sorted atom)
 template <bool LEAN>
-__global__ void __launch_bounds__(128, LEAN ? K2_MINBLOCKS_LEAN : K2_MINBLOCKS) k_predict_all_round(DevP D, SlotBuf src, SlotBuf dst, const int *queue, const int *nqueue_ptr,
-                                                           int round_arg, int *npair, double *second, double *bp_time, int *bp_j,
-                                                           int *pcount, int *pwho, unsigned long long *pair_sum, i64 g_base) {
-    const int round = LEAN ? 0 : round_arg;   // the lean instance is only ever launched for round 0
-    int total = (round == 0) ? D.n : *nqueue_ptr;
-    // re-evaluation rounds are a few thousand atoms with divergent, DRAM-latency-bound paths: give each its own
-    // group of QSPREAD lanes so a warp serialises 32/QSPREAD paths instead of 32
-    int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    int sub = 0;
-    if (round != 0) {
-        sub = gtid % QSPREAD;
-        gtid /= QSPREAD; gsz /= QSPREAD;
+__global__ void __launch_bounds__(128, LEAN ? K2_MINBLOCKS_LEAN : K2_MINBLOCKS) k_predict_all_round(DevP D, SlotBuf dst, int *npair, double *second, double *bp_time, int *bp_j,
+                                                           int *pcount, int *pwho, i64 g_base) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= D.n) return;
+    int i = D.sorted_atom[p];
+    Slot cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
+    double g = 0;
+    if (D.thermostat_on && (D.no_cons || !D.is_cons[i])) {
+        i64 gi = g_base + (D.no_cons ? i - 1 : D.ther_rank[i]);   // g_base < g_cap (host reduces it), rank < n <= g_cap
+        g = D.gauss[gi >= D.g_cap ? gi - D.g_cap : gi];
     }
+    int np = 0;
+    double m2 = SD_INF;
+    PairBest pb;
+    pb.bp_time = SD_INF; pb.sp_time = SD_INF; pb.bp_j = 0;
+    SlotSrc none = {};
+    cur = d_predict_atom<true, true, LEAN>(D, none, i, cur, g, 0, &np, &m2, &pb, D.surv ? p : -1);
+    dst.time[i] = cur.time; dst.pot[i] = cur.pot; dst.partner[i] = cur.partner; dst.pcounter[i] = cur.pcounter;
+    dst.type[i] = (uint8_t)cur.type; dst.sub[i] = (uint8_t)cur.sub;
+    npair[i] = np;
+    // a partner-less winner is settled against its best PAIR candidate instead (see k_predict_all_resolve)
+    bool pairwin = cur.partner > 0;
+    second[i] = pairwin ? m2 : pb.sp_time;
+    bp_time[i] = pb.bp_time;
+    bp_j[i] = pb.bp_j;
+    // who points at whom: count and remember one lower-index pointer per atom
+    if (cur.partner > i) { atomicAdd(&pcount[cur.partner], 1); pwho[cur.partner] = i; }
+}
+
+// One re-evaluation round over the queued atoms, `src` -> `dst`.  The paths diverge and are chains of dependent DRAM reads, so
+// each queued atom gets a group of QSPREAD lanes: lane 0 evaluates, the others first pull everything lane 0 is about to read one
+// dependent load at a time into this SM's L1 (survivor words -> 64-byte records -> the partners' slots; the atom's own state).
+__device__ __forceinline__ void d_requeue_round(const DevP &D, const SlotBuf &src, const SlotBuf &dst, const int *queue, int total, int *npair,
+                                                unsigned long long *pair_sum, i64 g_base, int gtid, int gsz) {
+    const int sub = gtid % QSPREAD;
+    gtid /= QSPREAD; gsz /= QSPREAD;
     for (int p = gtid; p < total; p += gsz) {
-        int i = (round == 0) ? D.sorted_atom[p] : queue[p];
-        if (round != 0) {
-            // the lanes of the group first pull everything lane 0 is about to read one dependent load at a time into this
-            // SM's L1 (survivor words -> 64-byte records -> the partners' slots; the atom's own state), in parallel
-            double acc = 0;
-            if (D.surv) {
-                int ps = D.spos[i];
-                int ns = D.surv_n[ps];
-                for (int s = sub; s < ns; s += QSPREAD) {
-                    unsigned w = D.surv[(size_t)ps * D.surv_cap + s];
-                    const SRec *r = &D.srec[w & 0x7ffffffu];
-                    int j = r->atom;
-                    acc += r->x + r->vy + (double)src.partner[j] + (double)src.type[j] + (double)src.pcounter[j] + src.time[j] + src.pot[j] +
-                           (double)src.sub[j] + (double)D.ev_counter[j];
-                }
-                if (sub == 1) acc += (double)D.surv_np[ps] + D.srec[ps].x + D.srec[ps].vy;
+        int i = queue[p];
+        double acc = 0;
+        if (D.surv) {
+            int ps = D.spos[i];
+            int ns = D.surv_n[ps];
+            for (int s = sub; s < ns; s += QSPREAD) {
+                unsigned w = D.surv[(size_t)ps * D.surv_cap + s];
+                const SRec *r = &D.srec[w & 0x7ffffffu];
+                int j = r->atom;
+                acc += r->x + r->vy + (double)src.partner[j] + (double)src.type[j] + (double)src.pcounter[j] + src.time[j] + src.pot[j] +
+                       (double)src.sub[j] + (double)D.ev_counter[j];
             }
-            if (sub == 2) acc += D.ev_pot[i] + (double)D.ev_sub[i] + (double)D.ev_pcounter[i] + (double)D.ev_counter[i];
-            if (sub == 3) acc += (double)D.cm_off[i] + (double)npair[i] + (double)D.is_cons[i];
-            if (sub == 4 && D.thermostat_on) { i64 gi = g_base + (D.no_cons ? i - 1 : D.ther_rank[i]); acc += D.gauss[gi >= D.g_cap ? gi - D.g_cap : gi]; }
-            if (sub != 0) {
-                if (acc == 1.2345e-300) D.ctl->warnings++;   // keeps the loads alive; never true
-                continue;
-            }
+            if (sub == 1) acc += (double)D.surv_np[ps] + D.srec[ps].x + D.srec[ps].vy;
+        }
+        if (sub == 2) acc += D.ev_pot[i] + (double)D.ev_sub[i] + (double)D.ev_pcounter[i] + (double)D.ev_counter[i];
+        if (sub == 3) acc += (double)D.cm_off[i] + (double)npair[i] + (double)D.is_cons[i];
+        if (sub == 4 && D.thermostat_on) { i64 gi = g_base + (D.no_cons ? i - 1 : D.ther_rank[i]); acc += D.gauss[gi >= D.g_cap ? gi - D.g_cap : gi]; }
+        if (sub != 0) {
+            if (acc == 1.2345e-300) D.ctl->error_prints++;   // keeps the loads alive; never true
+            continue;
         }
         Slot cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
         double g = 0;
         if (D.thermostat_on && (D.no_cons || !D.is_cons[i])) {
-            i64 gi = g_base + (D.no_cons ? i - 1 : D.ther_rank[i]);   // g_base < g_cap (host reduces it), rank < n <= g_cap
+            i64 gi = g_base + (D.no_cons ? i - 1 : D.ther_rank[i]);
             g = D.gauss[gi >= D.g_cap ? gi - D.g_cap : gi];
         }
         int np = 0;
-        double m2 = SD_INF;
-        PairBest pb;
-        if (round == 0) cur = d_predict_atom<true, true, LEAN>(D, as_src(src), i, cur, g, 0, &np, &m2, &pb, D.surv ? p : -1);
-        else cur = d_predict_atom<true, false, LEAN>(D, as_src(src), i, cur, g, i, &np, nullptr, nullptr, D.surv ? D.spos[i] : -1);
+        cur = d_predict_atom<true, false, false>(D, as_src(src), i, cur, g, i, &np, nullptr, nullptr, D.surv ? D.spos[i] : -1);
         dst.time[i] = cur.time; dst.pot[i] = cur.pot; dst.partner[i] = cur.partner; dst.pcounter[i] = cur.pcounter;
         dst.type[i] = (uint8_t)cur.type; dst.sub[i] = (uint8_t)cur.sub;
-        if (round == 0) {
-            npair[i] = np;
-            // a partner-less winner is settled against its best PAIR candidate instead (see k_predict_all_resolve)
-            bool pairwin = cur.partner > 0;
-            second[i] = pairwin ? m2 : pb.sp_time;
-            bp_time[i] = pb.bp_time;
-            bp_j[i] = pb.bp_j;
-            // who points at whom: count and remember one lower-index pointer per atom
-            if (cur.partner > i) { atomicAdd(&pcount[cur.partner], 1); pwho[cur.partner] = i; }
-        } else {
-            int old = npair[i];
-            npair[i] = np;
-            if (np != old) atomicAdd(pair_sum, (unsigned long long)(long long)(np - old));
-        }
+        int old = npair[i];
+        npair[i] = np;
+        if (np != old) atomicAdd(pair_sum, (unsigned long long)(long long)(np - old));
     }
 }
 
@@ -512,27 +565,71 @@ __global__ void k_predict_all_resolve(DevP D, SlotBuf b, const int *pcount, cons
         v = (unsigned long long)np;
     }
     for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(pair_sum, v);
+    __shared__ unsigned long long wsum[8];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; w++) t += wsum[w];
+        if (t) atomicAdd(pair_sum, t);
+    }
 }
 
 // commit round r: move re-evaluated slots into the current buffer, queue dependants of changed slots
-__global__ void k_predict_all_commit(DevP D, SlotBuf cur, SlotBuf nxt, const int *queue, const int *nqueue_ptr, int *queue_next,
-                                     int *nqueue_next) {
-    int nqueue = *nqueue_ptr;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nqueue; p += gridDim.x * blockDim.x) {
-    int i = queue[p];
-    // all twelve loads up front (no short-circuit: each would be its own DRAM round trip)
-    long long ct = __double_as_longlong(cur.time[i]), nt = __double_as_longlong(nxt.time[i]);
-    long long cp = __double_as_longlong(cur.pot[i]), np = __double_as_longlong(nxt.pot[i]);
-    int oldp = cur.partner[i], newp = nxt.partner[i];
-    i64 cc = cur.pcounter[i], nc = nxt.pcounter[i];
-    uint8_t cty = cur.type[i], nty = nxt.type[i], csb = cur.sub[i], nsb = nxt.sub[i];
-    bool same = (ct == nt) & (cp == np) & (oldp == newp) & (cc == nc) & (cty == nty) & (csb == nsb);
-    if (same) continue;
-    cur.time[i] = __longlong_as_double(nt); cur.pot[i] = __longlong_as_double(np); cur.partner[i] = newp; cur.pcounter[i] = nc;
-    cur.type[i] = nty; cur.sub[i] = nsb;
-    if (oldp > i) queue_next[atomicAdd(nqueue_next, 1)] = oldp;
-    if (newp > i && newp != oldp) queue_next[atomicAdd(nqueue_next, 1)] = newp;
+__device__ __forceinline__ void d_requeue_commit(const SlotBuf &cur, const SlotBuf &nxt, const int *queue, int nqueue, int *queue_next,
+                                                 int *nqueue_next, int gtid, int gsz) {
+    for (int p = gtid; p < nqueue; p += gsz) {
+        int i = queue[p];
+        // all twelve loads up front (no short-circuit: each would be its own DRAM round trip)
+        long long ct = __double_as_longlong(cur.time[i]), nt = __double_as_longlong(nxt.time[i]);
+        long long cp = __double_as_longlong(cur.pot[i]), np = __double_as_longlong(nxt.pot[i]);
+        int oldp = cur.partner[i], newp = nxt.partner[i];
+        i64 cc = cur.pcounter[i], nc = nxt.pcounter[i];
+        uint8_t cty = cur.type[i], nty = nxt.type[i], csb = cur.sub[i], nsb = nxt.sub[i];
+        bool same = (ct == nt) & (cp == np) & (oldp == newp) & (cc == nc) & (cty == nty) & (csb == nsb);
+        if (same) continue;
+        cur.time[i] = __longlong_as_double(nt); cur.pot[i] = __longlong_as_double(np); cur.partner[i] = newp; cur.pcounter[i] = nc;
+        cur.type[i] = nty; cur.sub[i] = nsb;
+        if (oldp > i) queue_next[atomicAdd(nqueue_next, 1)] = oldp;
+        if (newp > i && newp != oldp) queue_next[atomicAdd(nqueue_next, 1)] = newp;
+    }
+}
+
+// The re-evaluation rounds run to their fixed point on the device: one persistent cooperative grid, a grid-wide barrier
+// between evaluating a round and committing it, no look from the host in between.  Afterwards thread 0 books the pass into the
+// control block: evaluation count (summed by k_predict_all_resolve and the rounds), thermostat draws, queue statistics.
+#define FIX_NQ 16   // queue-length slots, one per round; the slots are recycled when a dependency chain is longer than that
+__global__ void __launch_bounds__(128, K2_MINBLOCKS) k_predict_all_fixpoint(DevP D, SlotBuf B, SlotBuf C, int *qa, int *qb, int *nqueue, int *npair,
+                                                                             unsigned long long *pair_sum, i64 g_base, i64 draws, int qcap) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    int slot = 0, rounds = 0, first = -1;
+    bool overflow = false;
+    for (;;) {
+        const int nq = nqueue[slot];
+        if (first < 0) first = nq;
+        if (nq == 0) break;
+        if (nq > qcap) { overflow = true; break; }
+        d_requeue_round(D, B, C, qa, nq, npair, pair_sum, g_base, gtid, gsz);
+        grid.sync();
+        d_requeue_commit(B, C, qa, nq, qb, nqueue + slot + 1, gtid, gsz);
+        grid.sync();
+        int *t = qa; qa = qb; qb = t;
+        slot++; rounds++;
+        if (slot + 1 >= FIX_NQ) {   // very long dependency chain: recycle the slots, keep the last queue
+            const int last = nqueue[slot];
+            grid.sync();
+            if (gtid == 0) { nqueue[0] = last; for (int k = 1; k < FIX_NQ; k++) nqueue[k] = 0; }
+            grid.sync();
+            slot = 0;
+        }
+    }
+    if (gtid == 0) {
+        Ctl *c = D.ctl;
+        c->pair_predictions += (i64)*pair_sum;
+        c->g_pos += draws;
+        c->pa_passes++; c->pa_rounds += rounds; c->pa_requeued += first;
+        if (overflow) c->error = SDMD_ERR_STATE;
     }
 }
 
@@ -1345,12 +1442,19 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     TRY(dalloc(c, &c->c_pcounter, n1)); TRY(dalloc(c, &c->c_type, n1)); TRY(dalloc(c, &c->c_sub, n1));
     TRY(dalloc(c, &c->npair, n1)); TRY(dalloc(c, &c->pcount, n1)); TRY(dalloc(c, &c->pwho, n1));
     TRY(dalloc(c, &c->queue_a, 2 * n1 + 2)); TRY(dalloc(c, &c->queue_b, 2 * n1 + 2)); TRY(dalloc(c, &c->nqueue, 32)); TRY(dalloc(c, &c->second, n1)); TRY(dalloc(c, &c->bp_time, n1)); TRY(dalloc(c, &c->bp_j, n1));
+    c->d_sum = reinterpret_cast<unsigned long long *>(c->nqueue + FIX_NQ);   // zeroed together with the queue lengths
     TRY(dalloc(c, &c->cell_of, n1)); TRY(dalloc(c, &c->cell_count, (size_t)P.ncell + 1));
-    TRY(dalloc(c, &c->cell_cursor, (size_t)P.ncell + 1));
+    TRY(dalloc(c, &c->cell_rank, n1)); TRY(dalloc(c, &c->cell_tmp, n1));
     TRY(dalloc(c, &c->scan_tmp, (size_t)P.ncell / SCAN_ITEMS + 4));
     TRY(dalloc(c, &c->d_cell_start, (size_t)P.ncell + 1)); TRY(dalloc(c, &c->d_sorted_atom, n1));
     TRY(dalloc(c, &c->d_srec, n1)); TRY(dalloc(c, &c->d_sloc, n1)); TRY(dalloc(c, &c->d_scell, n1));
-    TRY(dalloc(c, &c->d_sum, 4));
+    {
+        int per_sm = 0, sms = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_predict_all_fixpoint, 128, 0));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+        c->fix_grid = per_sm * sms;        // the cooperative grid of the fix-up rounds: every block resident
+        if (c->fix_grid <= 0) return set_err(SDMD_ERR_CUDA, "cooperative grid size");
+    }
     P.surv = nullptr; P.surv_n = nullptr; P.surv_np = nullptr;
     TRY(dalloc(c, &P.spos, n1));
     P.cut2_loose = P.cut2 * (1.0 + 1e-9);
@@ -1393,13 +1497,16 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     return 0;
 }
 
+static void remd_forget(sdmd_ctx *c);
 void sdmd_cuda_destroy(sdmd_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (void *p : c->bufs) cudaFree(p);
     if (c->d_trace) cudaFree(c->d_trace);
+    remd_forget(c);
     if (c->d_xchg) cudaFree(c->d_xchg);
+    if (c->h_xchg) cudaFreeHost(c->h_xchg);
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
     resolve_pending(c);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -1430,13 +1537,31 @@ double sdmd_cuda_kernel_ms(const sdmd_ctx *c, const char *name) {
 }
 int sdmd_cuda_kernel_stats(const sdmd_ctx *c, const char *name, double *total_ms, int64_t *count) {
     resolve_pending(const_cast<sdmd_ctx *>(c));
+    if (!strcmp(name, "predict_all_rounds") || !strcmp(name, "predict_all_requeued")) {
+        // booked on the device by the fix-up kernel (no host look inside the pass): totals since the last reset
+        sdmd_ctx *m = const_cast<sdmd_ctx *>(c);
+        Ctl h;
+        if (cudaMemcpyAsync(&h, m->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, m->stream) != cudaSuccess || cudaStreamSynchronize(m->stream) != cudaSuccess)
+            return set_err(SDMD_ERR_CUDA, "kernel_stats", cudaGetLastError());
+        *total_ms = (double)((name[12] == 'r' && name[13] == 'o') ? h.pa_rounds - m->pa_base[1] : h.pa_requeued - m->pa_base[2]);
+        *count = h.pa_passes - m->pa_base[0];
+        return 0;
+    }
     auto it = c->kstat.find(name);
     if (it == c->kstat.end()) { *total_ms = 0; *count = 0; return 0; }
     *total_ms = it->second.ms;
     *count = it->second.n;
     return 0;
 }
-void sdmd_cuda_reset_kernel_stats(sdmd_ctx *c) { resolve_pending(c); c->kstat.clear(); c->launches = 0; }
+void sdmd_cuda_reset_kernel_stats(sdmd_ctx *c) {
+    resolve_pending(c);
+    c->kstat.clear();
+    c->launches = 0;
+    Ctl h;
+    if (cudaMemcpyAsync(&h, c->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c->stream) == cudaSuccess && cudaStreamSynchronize(c->stream) == cudaSuccess) {
+        c->pa_base[0] = h.pa_passes; c->pa_base[1] = h.pa_rounds; c->pa_base[2] = h.pa_requeued;
+    }
+}
 // device-time bracket on the context's stream for callers (bench.py): begin records, end synchronises
 int sdmd_cuda_timer_begin(sdmd_ctx *c) {
     CK(cudaSetDevice(c->device));
@@ -1490,6 +1615,18 @@ static int pull_ctl(sdmd_ctx *c) {
 static int need_counters(sdmd_ctx *c) { return c->counters_known ? 0 : pull_ctl(c); }
 static int push_ctl(sdmd_ctx *c) {
     CK(cudaMemcpyAsync(c->d_ctl, c->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+// Gaussian cursor / fill mark of the device control block, by VALUE in stream order.  (An asynchronous copy out of the pinned
+// host mirror would read it when the copy executes, and the host moves its own cursor on as soon as a full-system pass is
+// queued — the pass advances the device cursor itself.)
+__global__ void k_set_rng_cursor(Ctl *ctl, i64 g_pos, i64 g_filled, int which) {
+    if (which & 1) ctl->g_pos = g_pos;
+    if (which & 2) ctl->g_filled = g_filled;
+}
+static int set_rng_cursor(sdmd_ctx *c, int which) {
+    k_set_rng_cursor<<<1, 1, 0, c->stream>>>(c->d_ctl, c->h_ctl->g_pos, c->h_ctl->g_filled, which);
+    CK(cudaGetLastError());
     return 0;
 }
 // invalidate every cached candidate list (link list rebuilt / replaced from the host)
@@ -1606,7 +1743,7 @@ int sdmd_cuda_rng_feed(sdmd_ctx *c, const double *g, int64_t n) {
     if (n > first) CK(cudaMemcpyAsync(c->d_gauss, g + first, (n - first) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     c->g_filled += n;
     c->h_ctl->g_filled = c->g_filled;
-    CK(cudaMemcpyAsync(&c->d_ctl->g_filled, &c->h_ctl->g_filled, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+    TRY(set_rng_cursor(c, 2));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -1616,7 +1753,7 @@ int sdmd_cuda_rng_seek(sdmd_ctx *c, int64_t pos) {
     TRY(need_counters(c));
     if (pos < 0 || pos > c->g_filled || c->g_filled - pos > c->P.g_cap) return set_err(SDMD_ERR_BAD_ARG, "rng_seek out of range");
     c->h_ctl->g_pos = pos;
-    CK(cudaMemcpyAsync(&c->d_ctl->g_pos, &c->h_ctl->g_pos, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+    TRY(set_rng_cursor(c, 1));
     return 0;
 }
 
@@ -1626,8 +1763,7 @@ int sdmd_cuda_rng_reset(sdmd_ctx *c) {
     c->g_filled = 0;
     c->h_ctl->g_filled = 0;
     c->h_ctl->g_pos = 0;
-    CK(cudaMemcpyAsync(&c->d_ctl->g_filled, &c->h_ctl->g_filled, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(&c->d_ctl->g_pos, &c->h_ctl->g_pos, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+    TRY(set_rng_cursor(c, 3));
     return 0;
 }
 
@@ -1650,22 +1786,21 @@ int sdmd_cuda_pbc_full(sdmd_ctx *c) {
 static int cell_build_impl(sdmd_ctx *c, int parts, bool bump) {
     Timer t(c, "cell_build");
     int n = c->n, m = c->P.ncell;
-    CK(cudaMemsetAsync(c->cell_count, 0, ((size_t)m + 1) * sizeof(int), c->stream));
-    k_cell_index<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_count);
+    // (the histogram is all zero here: zero-filled at create, cleared again by the scan of the previous build)
+    k_cell_index<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_count, c->cell_rank);
     int nb = (m + SCAN_ITEMS - 1) / SCAN_ITEMS;
     k_scan_local<<<nb, 512, 0, c->stream>>>(c->cell_count, c->d_cell_start, c->scan_tmp, m);
     if (nb <= SCAN_DIRECT_BLOCKS) {
-        k_scan_finish<<<nb, 512, 0, c->stream>>>(c->d_cell_start, c->cell_cursor, c->scan_tmp, m, nb);
+        k_scan_finish<<<nb, 512, 0, c->stream>>>(c->P, c->d_cell_start, c->cell_count, c->scan_tmp, m, nb);
         c->launches -= 1;
     } else {
         k_scan_blocks<<<1, 32, 0, c->stream>>>(c->scan_tmp, nb);
-        k_scan_add<<<grid_for(m, 256), 256, 0, c->stream>>>(c->d_cell_start, c->scan_tmp, m, nb);
-        CK(cudaMemcpyAsync(c->cell_cursor, c->d_cell_start, ((size_t)m + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+        k_scan_add_cells<<<grid_for(m, 256), 256, 0, c->stream>>>(c->P, c->d_cell_start, c->cell_count, c->scan_tmp, m, nb);
     }
-    k_cell_scatter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_cursor, c->d_sorted_atom);
-    k_cell_finish<<<grid_for(m, 128), 128, 0, c->stream>>>(c->P, c->d_cell_start, c->d_sorted_atom);
-    k_cell_permute<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_sorted_atom, c->d_srec, c->d_sloc, c->d_scell, parts | (bump ? 4 : 0));
-    c->launches += 6;
+    k_cell_scatter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_rank, c->d_cell_start, c->cell_tmp);
+    k_cell_place<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->d_cell_start, c->cell_tmp, c->d_sorted_atom, c->d_srec, c->d_sloc,
+                                                         c->d_scell, parts | (bump ? 4 : 0));
+    c->launches += 5;
     c->cells_fresh = true;
     CK(cudaGetLastError());
     return 0;
@@ -1687,10 +1822,8 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
     SlotBuf B = {c->b_time, c->b_pot, c->b_partner, c->b_pcounter, c->b_type, c->b_sub};
     SlotBuf C = {c->c_time, c->c_pot, c->c_partner, c->c_pcounter, c->c_type, c->c_sub};
     int grid = grid_for(n, 128), grid1 = grid_for(n, 256);
-    const int NQ = 16;   // queue-length slots, one per relaxation round
     CK(cudaMemsetAsync(c->pcount, 0, ((size_t)n + 1) * sizeof(int), c->stream));
-    CK(cudaMemsetAsync(c->nqueue, 0, NQ * sizeof(int), c->stream));
-    CK(cudaMemsetAsync(c->d_sum, 0, sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->nqueue, 0, (FIX_NQ + 2) * sizeof(int), c->stream));   // queue lengths and, behind them, the evaluation-count sum
     {
         Timer t(c, "predict_all");
         const bool tile = c->P.tile_tx > 0;
@@ -1710,15 +1843,11 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
             Round0Out ro = {c->npair, c->second, c->bp_time, c->bp_j, c->pcount, c->pwho};
             if (sdmd_k2_tile_launch(c->P, B, ro, g_base, c->stream)) return set_err(SDMD_ERR_CUDA, "k_predict_all_tile", cudaGetLastError());
         } else if (lean)
-            k_predict_all_round<true><<<grid, 128, 0, c->stream>>>(c->P, B, B, nullptr, nullptr, 0, c->npair, c->second, c->bp_time, c->bp_j,
-                                                                   c->pcount, c->pwho, c->d_sum, g_base);
+            k_predict_all_round<true><<<grid, 128, 0, c->stream>>>(c->P, B, c->npair, c->second, c->bp_time, c->bp_j, c->pcount, c->pwho, g_base);
         else
-            k_predict_all_round<false><<<grid, 128, 0, c->stream>>>(c->P, B, B, nullptr, nullptr, 0, c->npair, c->second, c->bp_time, c->bp_j,
-                                                                    c->pcount, c->pwho, c->d_sum, g_base);
+            k_predict_all_round<false><<<grid, 128, 0, c->stream>>>(c->P, B, c->npair, c->second, c->bp_time, c->bp_j, c->pcount, c->pwho, g_base);
         c->launches++;
     }
-    int rounds = 0, requeued = 0;
-    struct { int nq[16]; unsigned long long sum; } h;
     {
         Timer t2(c, "predict_all_fixup");
         {
@@ -1726,49 +1855,23 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
             k_predict_all_resolve<<<grid1, 256, 0, c->stream>>>(c->P, B, c->pcount, c->pwho, c->second, c->bp_time, c->bp_j, c->queue_a,
                                                                 c->nqueue, c->npair, c->d_sum);
         }
-        c->launches++;
-        int *qa = c->queue_a, *qb = c->queue_b;
-        int qgrid = 148 * 4;
-        int slot = 0;
-        for (;;) {
-            // a few relaxation rounds back to back (queue lengths stay on the device), then one look at the result
-            int burst = (slot == 0) ? 2 : 3;
-            for (int r = 0; r < burst && slot + 1 < NQ; r++, slot++) {
-                Timer t4(c, slot == 0 ? "fixup_round1" : "fixup_later", 2);
-                k_predict_all_round<false><<<qgrid, 128, 0, c->stream>>>(c->P, B, C, qa, c->nqueue + slot, slot + 1, c->npair, c->second, c->bp_time,
-                                                                  c->bp_j, c->pcount, c->pwho, c->d_sum, g_base);
-                k_predict_all_commit<<<qgrid, 256, 0, c->stream>>>(c->P, B, C, qa, c->nqueue + slot, qb, c->nqueue + slot + 1);
-                c->launches += 2;
-                std::swap(qa, qb);
-            }
-            CK(cudaMemcpyAsync(h.nq, c->nqueue, NQ * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaMemcpyAsync(&h.sum, c->d_sum, sizeof(h.sum), cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaStreamSynchronize(c->stream));
-            requeued = h.nq[0];
-            for (int k = 0; k <= slot; k++)
-                if (h.nq[k] > 2 * n) return set_err(SDMD_ERR_STATE, "predict_all queue overflow");
-            rounds = 0;
-            for (int k = 0; k < slot; k++) rounds += h.nq[k] > 0;
-            if (h.nq[slot] == 0) break;
-            if (slot + 1 >= NQ) {   // very long dependency chain: restart the slot counter, keep the last queue
-                int last = h.nq[slot];
-                CK(cudaMemsetAsync(c->nqueue, 0, NQ * sizeof(int), c->stream));
-                CK(cudaMemcpyAsync(c->nqueue, &last, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-                slot = 0;
-            }
+        {
+            Timer t4(c, "fixup_rounds", 2);
+            DevP P = c->P;
+            int *qa = c->queue_a, *qb = c->queue_b, *nq = c->nqueue, *npair = c->npair;
+            unsigned long long *sum = c->d_sum;
+            i64 gb = g_base, draws = need;
+            int qcap = 2 * n;
+            void *args[] = {&P, &B, &C, &qa, &qb, &nq, &npair, &sum, &gb, &draws, &qcap};
+            CK(cudaLaunchCooperativeKernel((const void *)k_predict_all_fixpoint, dim3(c->fix_grid), dim3(128), args, 0, c->stream));
         }
+        c->launches += 2;
     }
-    // the relaxed buffer becomes the live slot arrays (pointer swap, no copy)
+    // the relaxed buffer becomes the live slot arrays (pointer swap, no copy); the host keeps its own copy of the gaussian cursor,
+    // the evaluation counter lives on the device
     std::swap(c->P.ev_time, c->b_time); std::swap(c->P.ev_pot, c->b_pot); std::swap(c->P.ev_partner, c->b_partner);
     std::swap(c->P.ev_pcounter, c->b_pcounter); std::swap(c->P.ev_type, c->b_type); std::swap(c->P.ev_sub, c->b_sub);
     c->h_ctl->g_pos = g_pos0 + need;
-    c->h_ctl->pair_predictions += (i64)h.sum;
-    CK(cudaMemcpyAsync(&c->d_ctl->g_pos, &c->h_ctl->g_pos, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(&c->d_ctl->pair_predictions, &c->h_ctl->pair_predictions, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
-    c->kstat["predict_all_rounds"].ms += rounds;
-    c->kstat["predict_all_rounds"].n++;
-    c->kstat["predict_all_requeued"].ms += requeued;
-    c->kstat["predict_all_requeued"].n++;
     CK(cudaGetLastError());
     return 0;
 }
@@ -1857,8 +1960,7 @@ int sdmd_cuda_prepare(sdmd_ctx *c, const double *x, const double *y, const doubl
     c->g_filled = n_gauss;                              // fresh thermostat stream: drop what was fed before
     c->h_ctl->g_filled = n_gauss;
     c->h_ctl->g_pos = 0;
-    CK(cudaMemcpyAsync(&c->d_ctl->g_filled, &c->h_ctl->g_filled, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(&c->d_ctl->g_pos, &c->h_ctl->g_pos, sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+    TRY(set_rng_cursor(c, 3));
     k_pbc_full<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->P);
     c->launches++;
     TRY(cell_build_impl(c, 1, true));
@@ -2292,7 +2394,8 @@ int sdmd_remd_nccl_init(sdmd_ctx *c, int nranks, int rank, const unsigned char i
     if (rc) return set_err(SDMD_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclCommInitRank");
     c->nranks = nranks;
     c->rank = rank;
-    if (!c->d_xchg) CK(cudaMalloc(&c->d_xchg, (size_t)(nranks + 1) * 32));
+    if (c->d_xchg) { cudaFree(c->d_xchg); c->d_xchg = nullptr; }          // sized for the new communicator on first use
+    if (c->h_xchg) { cudaFreeHost(c->h_xchg); c->h_xchg = nullptr; }
     return 0;
 }
 
@@ -2322,7 +2425,17 @@ struct GlibcRand {
         return res;
     }
 };
+// one replicated server stream per replica context (seeded by sdmd_remd_seed_server, dropped by sdmd_cuda_destroy)
 static std::map<sdmd_ctx *, GlibcRand> g_server_rng;
+static std::mutex g_server_rng_mu;
+static void remd_forget(sdmd_ctx *c) {      // called by sdmd_cuda_destroy
+    {
+        std::lock_guard<std::mutex> lk(g_server_rng_mu);
+        g_server_rng.erase(c);
+    }
+    if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+    c->nccl_comm = nullptr;
+}
 
 // the restated generator by itself (tests compare it with libc rand() for 10^6 draws)
 int sdmd_host_glibc_rand(uint32_t seed, int64_t n, uint32_t *out) {
@@ -2333,35 +2446,63 @@ int sdmd_host_glibc_rand(uint32_t seed, int64_t n, uint32_t *out) {
 }
 
 int sdmd_remd_seed_server(sdmd_ctx *c, uint32_t seed) {  // srand(seed) of sServer, Server.c:57-58
+    std::lock_guard<std::mutex> lk(g_server_rng_mu);
     g_server_rng[c].seed(seed);
     return 0;
+}
+
+// {E, T, num} of this replica straight into the all-gather's send record: CalPotenE (ToolFunctions.c:684-752) by the same
+// serial device function as sdmd_cuda_potential_energy, so the energy never visits the host before the exchange
+struct XchgRec { double e; double T; int32_t num; int32_t pad; double pad2; };
+static_assert(sizeof(XchgRec) == 32, "exchange record is 32 bytes");
+__global__ void k_xchg_fill(DevP D, XchgRec *rec, double T, int num) {
+    rec->e = d_potential_energy(D);
+    rec->T = T; rec->num = num; rec->pad = 0; rec->pad2 = 0;
 }
 
 // ReplicaExchange (REMD.c:135-192) + collect/rearrange/distribute (Server.c:121-211) without the server:
 // every rank all-gathers {E, T, num}, runs the identical sweep with an identically seeded stream and keeps
 // its own entry.
-int sdmd_remd_exchange(sdmd_ctx *c, double epot, struct sdmd_remd_temp *T, uint32_t /*unused*/) {
+// `epot` NULL: the energy is computed on the device and written straight into the send record (systems the serial energy
+// kernel covers, natom <= 2048 — every REMD demo); otherwise *epot is what the caller computed.  On return *epot_out (if given)
+// holds this replica's energy as it went into the exchange.
+static int remd_exchange_impl(sdmd_ctx *c, const double *epot, struct sdmd_remd_temp *T, double *epot_out) {
     CK(cudaSetDevice(c->device));
+    typedef XchgRec Rec;
     int R = c->nranks;
-    struct Rec { double e; double T; int32_t num; int32_t pad; double pad2; };
-    static_assert(sizeof(Rec) == 32, "exchange record is 32 bytes");
-    std::vector<Rec> all(R);
-    Rec mine = {epot, T->T, T->num, 0, 0.0};
-    if (R == 1 || !c->nccl_comm) {
-        all[0] = mine;
+    GlibcRand *rngp = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_server_rng_mu);
+        auto it = g_server_rng.find(c);
+        if (it != g_server_rng.end()) rngp = &it->second;
+    }
+    if (!rngp) return set_err(SDMD_ERR_STATE, "remd_exchange: sdmd_remd_seed_server has not been called for this replica");
+    if (!epot && c->n > 2048) return set_err(SDMD_ERR_BAD_ARG, "remd_exchange: device-side energy needs natom <= 2048; pass the energy");
+    if (!c->d_xchg) CK(cudaMalloc(&c->d_xchg, (size_t)(R + 1) * sizeof(Rec)));
+    if (!c->h_xchg) CK(cudaMallocHost(&c->h_xchg, (size_t)(R + 1) * sizeof(Rec)));
+    Rec *all = (Rec *)c->h_xchg;
+    Rec *d_send = (Rec *)c->d_xchg + R, *d_recv = (Rec *)c->d_xchg;
+    if (epot) {
+        all[R] = Rec{*epot, T->T, T->num, 0, 0.0};
+        CK(cudaMemcpyAsync(d_send, &all[R], sizeof(Rec), cudaMemcpyHostToDevice, c->stream));
     } else {
-        Rec *d_send = (Rec *)c->d_xchg + R, *d_recv = (Rec *)c->d_xchg;
-        CK(cudaMemcpyAsync(d_send, &mine, sizeof(Rec), cudaMemcpyHostToDevice, c->stream));
+        k_xchg_fill<<<1, 1, 0, c->stream>>>(c->P, d_send, T->T, T->num);
+        c->launches++;
+    }
+    if (R == 1 || !c->nccl_comm) {
+        CK(cudaMemcpyAsync(all, d_send, sizeof(Rec), cudaMemcpyDeviceToHost, c->stream));
+    } else {
         int rc = g_nccl.AllGather(d_send, d_recv, sizeof(Rec), /*ncclChar*/ 0, c->nccl_comm, c->stream);
         if (rc) return set_err(SDMD_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclAllGather");
-        CK(cudaMemcpyAsync(all.data(), d_recv, sizeof(Rec) * R, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemcpyAsync(all, d_recv, sizeof(Rec) * R, cudaMemcpyDeviceToHost, c->stream));
     }
+    CK(cudaStreamSynchronize(c->stream));
+    if (epot_out) *epot_out = all[c->rank].e;
+    GlibcRand &rng = *rngp;
     std::vector<double> e(R);
     std::vector<sdmd_remd_temp> t(R);
     for (int k = 0; k < R; k++) { e[k] = all[k].e; t[k].num = all[k].num; t[k].pad_ = 0; t[k].T = all[k].T; }
     // draw lazily: copy the generator, count how many the sweep used, then advance the real one
-    GlibcRand &rng = g_server_rng[c];
     GlibcRand probe = rng;
     std::vector<double> u(2 * R + 2);
     for (auto &x : u) x = 0 + (double)probe.next() / ((double)2147483647 / (1 - 0));  // RANDOMVALUE(0,1), Server.c:16-18
@@ -2372,5 +2513,7 @@ int sdmd_remd_exchange(sdmd_ctx *c, double epot, struct sdmd_remd_temp *T, uint3
     TRY(sdmd_cuda_set_temperature(c, T->T));
     return 0;
 }
+int sdmd_remd_exchange(sdmd_ctx *c, double epot, struct sdmd_remd_temp *T, uint32_t /*unused*/) { return remd_exchange_impl(c, &epot, T, nullptr); }
+int sdmd_remd_exchange_energy(sdmd_ctx *c, struct sdmd_remd_temp *T, double *epot) { return remd_exchange_impl(c, nullptr, T, epot); }
 
 }  // extern "C"

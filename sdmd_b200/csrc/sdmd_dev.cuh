@@ -24,6 +24,7 @@ struct Ctl {
     i64 n_coli, n_bond, n_hb, n_hbne, n_ther, n_pcc, n_wall;
     i64 warnings, pair_predictions;
     i64 error_prints;          // "!!ERROR!!" prints the reference carries on from (not part of warningsum)
+    i64 pa_passes, pa_rounds, pa_requeued;   // full-system passes: count, re-evaluation rounds, atoms queued by the resolve stage
     i64 g_pos;                 // gaussians consumed (absolute)
     i64 g_filled;              // gaussians fed (absolute)
     int target, partner;       // AssignJob result

@@ -288,6 +288,48 @@ def test_full_size_pass_elementwise_against_oracle(capi, n_axis, a, jitter, step
     r.close(); o.close()
 
 
+def test_full_size_pass_against_the_reference_itself(capi):
+    """10^6 atoms against the UNMODIFIED reference, not its restatement: oracle/_ref/ref_bench_gel runs PBC + LinkList +
+    Predict(all) + CreateCBT of the -DGEL build on a jittered 100^3 lattice (its (N+1)^2 connectionMap answered by a zero window,
+    oracle/ref_bench.c) and dumps what it started from; the CUDA path runs the same pass on that state and must reproduce every
+    event slot the reference wrote — time and potential bits, partner, type, sub-type, partnerCounter."""
+    from tests import ref_bench
+    if not ref_bench.available():
+        pytest.skip("oracle/_ref/ref_bench_gel not built")
+    hv, gauss, slots, _ = ref_bench.run(100)
+    n = hv.natom
+    assert n == 1000000 and len(slots) == n
+    r = capi.Replica(hv, device=0)
+    r.rng_feed(gauss)
+    r.pbc_full(); r.cell_build(); r.predict_all(); r.cbt_build()
+    r.download(hv)
+    assert np.array_equal(hv.ev_time[1:].view(np.int64), slots["time"].view(np.int64))
+    assert np.array_equal(hv.ev_potential[1:].view(np.int64), slots["potential"].view(np.int64))
+    assert np.array_equal(hv.ev_partner[1:], slots["partner"])
+    assert np.array_equal(hv.ev_type[1:].astype(np.int32), slots["type"]) and np.array_equal(hv.ev_sub[1:].astype(np.int32), slots["sub"])
+    assert np.array_equal(hv.ev_pcounter[1:], slots["pcounter"])
+    assert (slots["partner"] > 0).sum() > 100000 and r.stats()["pair_predictions"] > 40 * n
+    r.close()
+
+
+def test_remd_exchange_with_fused_energy(capi):
+    """sdmd_remd_exchange_energy: CalPotenE computed on the device and written straight into the exchange record; with one rank
+    the sweep leaves (num, T) alone and the energy that went in equals sdmd_cuda_potential_energy bit for bit.  An unseeded
+    server stream is an error, not garbage."""
+    pre, _, _ = load_case("ala10")
+    hv, r = _replica(capi, pre)
+    r.cell_build(); r.predict_all(); r.cbt_build()
+    r.run(max_iter=2000)
+    with pytest.raises(capi.SdmdError):
+        r.remd_exchange_energy(1, hv.target_temperature)
+    r.remd_seed_server(99)
+    num, T, e = r.remd_exchange_energy(1, hv.target_temperature)
+    assert (num, T) == (1, hv.target_temperature)
+    assert np.float64(e).tobytes() == np.float64(r.potential_energy()).tobytes()
+    assert r.remd_exchange(e, 1, hv.target_temperature) == (1, hv.target_temperature)
+    r.close()
+
+
 @pytest.mark.parametrize("threads", [256, 128])
 def test_remd_ensemble_gpu_matches_oracle(capi, threads, monkeypatch):
     """Three ala10 replicas on one GPU coupled by the Server.c sweep: exchange log and final states equal the same

@@ -198,6 +198,28 @@ def test_gel_42875_against_live_reference(tmp_path):
 
 
 @pytest.mark.refbin
+@pytest.mark.parametrize("n_axis", [20, 100])
+def test_full_system_pass_against_the_reference_itself(n_axis):
+    """The oracle port against the UNMODIFIED reference at the bench size (10^6 atoms; 8000 as the quick case): ref_bench_gel
+    runs the -DGEL reference's own PBC + LinkList + Predict(all) + CreateCBT (dense connectionMap answered by a zero window,
+    oracle/ref_bench.c); every event slot of the port's pass over the same start state must equal the reference's, bit for bit.
+    This is what pins the port — bench.py's pair counter and the GPU tests' oracle — at the size the numbers are quoted on."""
+    from tests import ref_bench
+    if not ref_bench.available():
+        pytest.skip("oracle/_ref/ref_bench_gel not built (needs /root/reference at build time)")
+    hv, gauss, slots, _ = ref_bench.run(n_axis)
+    o = Oracle(hv)
+    o.rng_feed(gauss)
+    o.pbc_full(); o.cell_build(); o.predict_all(); o.cbt_build()
+    assert np.array_equal(hv.ev_time[1:].view(np.int64), slots["time"].view(np.int64))
+    assert np.array_equal(hv.ev_potential[1:].view(np.int64), slots["potential"].view(np.int64))
+    assert np.array_equal(hv.ev_partner[1:], slots["partner"])
+    assert np.array_equal(hv.ev_type[1:].astype(np.int32), slots["type"]) and np.array_equal(hv.ev_sub[1:].astype(np.int32), slots["sub"])
+    assert np.array_equal(hv.ev_pcounter[1:], slots["pcounter"])
+    assert (slots["partner"] > 0).sum() > 0.1 * hv.natom
+
+
+@pytest.mark.refbin
 def test_warningsum_against_live_reference():
     """`warningsum` (DMD.c:61): an 8^3 GEL lattice at 3.95 A puts every nearest neighbour inside the 4.0 A hard core, so
     FindPair's too-small warning (ToolFunctions.c:119-139) fires for each of them in Predict(all) and again in every
