@@ -637,7 +637,9 @@ def remd_subrecord(args, dist):
     rep.close()
     out = {"metric": "REMD replica-events/s", "value": sum(r[0] for r in per_rank) / dt, "unit": "events/s", "replicas": W,
            "periods_timed": periods, "exchange_rate_tu": rate, "temperatures_K": REMD_TEMPS_K[:W], "seconds": dt,
-           "events_per_rank": [int(r[0]) for r in per_rank], "us_per_exchange": 1e6 * xs,
+           "events_per_rank": [int(r[0]) for r in per_rank], "us_per_exchange_call": 1e6 * xs,
+           "us_per_exchange_note": "mean time inside sdmd_remd_exchange_energy on the slowest rank's clock: CalPotenE kernel + collective + sweep, "
+                                   "INCLUDING the wait for the last replica to reach the boundary",
            "exchange": "sdmd_remd_exchange_energy: CalPotenE on the device written into the send record, ncclAllGather of 32 B per rank, "
                        "replicated Server.c:145-192 sweep" if W > 1 else "single replica: CalPotenE + sweep over one entry, no collective",
            "limit": "the period lasts as long as the hottest replica (most events per 50 tu) needs"}
@@ -936,6 +938,11 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
 
+    # the contract is ONE JSON line on stdout: anything a library prints there (NCCL's version banner, the reference's own
+    # progress output) goes to stderr instead; the real stdout comes back for the final line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     dist = Dist(args.gpus, backend="gloo" if args.impl == "reference" else None)
     try:
         if args.impl == "reference":
@@ -943,6 +950,8 @@ def main():
         else:
             out = {"pass1m": cuda_pass, "loop": cuda_loop, "remd": cuda_remd}[args.workload](args, dist)
         if dist.rank == 0 and out is not None:
+            sys.stdout.flush()
+            os.dup2(real_stdout, 1)
             print(json.dumps(out))
             sys.stdout.flush()
     finally:

@@ -359,6 +359,11 @@ int  sdmd_remd_exchange(sdmd_ctx *ctx, double epot, struct sdmd_remd_temp *T, ui
  * *epot (may be NULL) returns the energy this replica contributed.  Both calls fail with SDMD_ERR_STATE when
  * sdmd_remd_seed_server has not been called for the context. */
 int  sdmd_remd_exchange_energy(sdmd_ctx *ctx, struct sdmd_remd_temp *T, double *epot);
+/* End of this replica's run: the (E = 0, T = 0) sentinel of REMD.c:119-122.  The reference's server goes on serving the replicas
+ * that are still running and skips the ones that left (Server.c:108-113,125); a collective needs every rank in every round, so
+ * this call keeps contributing the sentinel — one all-gather per round of the others — until every replica has finished.
+ * Call it once after the last sdmd_cuda_run of a replica that took part in sdmd_remd_exchange*. */
+int  sdmd_remd_finish(sdmd_ctx *ctx);
 
 /* ---- measurement helpers ------------------------------------------------------------------------- */
 /* average device time (ms) of the last launch of each named kernel, measured with CUDA events on the

@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "sdmd_cuda_cbt_update", "sdmd_cuda_assign_job", "sdmd_cuda_advance", "sdmd_cuda_add_time", "sdmd_cuda_hazard_check",
     "sdmd_cuda_cell_move", "sdmd_cuda_do_event", "sdmd_cuda_potential_energy", "sdmd_cuda_kinetic_energy",
     "sdmd_cuda_run", "sdmd_cuda_run_many", "sdmd_cuda_potential_energy_many", "sdmd_cuda_get_stats", "sdmd_cuda_set_temperature",
-    "sdmd_remd_rearrange", "sdmd_remd_nccl_unique_id", "sdmd_remd_nccl_init", "sdmd_remd_seed_server", "sdmd_remd_exchange", "sdmd_remd_exchange_energy", "sdmd_host_glibc_rand",
+    "sdmd_remd_rearrange", "sdmd_remd_nccl_unique_id", "sdmd_remd_nccl_init", "sdmd_remd_seed_server", "sdmd_remd_exchange", "sdmd_remd_exchange_energy", "sdmd_remd_finish", "sdmd_host_glibc_rand",
     "sdmd_cuda_kernel_ms", "sdmd_cuda_kernel_stats", "sdmd_cuda_reset_kernel_stats", "sdmd_cuda_set_timing", "sdmd_cuda_set_loop_mode",
     "sdmd_cuda_launch_count", "sdmd_cuda_stream", "sdmd_cuda_phase_cycles",
 ]
@@ -158,6 +158,7 @@ def lib():
     L.sdmd_remd_seed_server.argtypes = [vp, C.c_uint32]
     L.sdmd_remd_exchange.argtypes = [vp, C.c_double, C.POINTER(CRemdTemp), C.c_uint32]
     L.sdmd_remd_exchange_energy.argtypes = [vp, C.POINTER(CRemdTemp), dp]
+    L.sdmd_remd_finish.argtypes = [vp]
     L.sdmd_host_glibc_rand.argtypes = [C.c_uint32, C.c_int64, C.POINTER(C.c_uint32)]
     L.sdmd_cuda_kernel_ms.argtypes = [vp, C.c_char_p]
     L.sdmd_cuda_kernel_ms.restype = C.c_double
@@ -382,6 +383,8 @@ class Replica:
         e = C.c_double()
         _check(self.L.sdmd_remd_exchange_energy(self.h, C.byref(t), C.byref(e)), "remd_exchange_energy")
         return t.num, t.T, e.value
+
+    def remd_finish(self): _check(self.L.sdmd_remd_finish(self.h), "remd_finish")
 
     def remd_exchange(self, epot, num, T):
         t = CRemdTemp(int(num), 0, float(T))

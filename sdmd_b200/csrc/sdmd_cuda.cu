@@ -38,6 +38,7 @@ struct sdmd_ctx {
     cudaStream_t stream = nullptr;
     DevP P;
     Ctl *d_ctl = nullptr;
+    Ctl *d_ctl_scratch = nullptr;   // counters of the re-evaluation rounds of Predict(all) (see k_predict_all_fixpoint)
     Ctl *h_ctl = nullptr;  // pinned
     std::vector<void *> bufs;
     int n = 0;
@@ -599,7 +600,10 @@ __device__ __forceinline__ void d_requeue_commit(const SlotBuf &cur, const SlotB
 // between evaluating a round and committing it, no look from the host in between.  Afterwards thread 0 books the pass into the
 // control block: evaluation count (summed by k_predict_all_resolve and the rounds), thermostat draws, queue statistics.
 #define FIX_NQ 16   // queue-length slots, one per round; the slots are recycled when a dependency chain is longer than that
-__global__ void __launch_bounds__(128, K2_MINBLOCKS) k_predict_all_fixpoint(DevP D, SlotBuf B, SlotBuf C, int *qa, int *qb, int *nqueue, int *npair,
+// `Dq` is `D` with the control block replaced by a scratch one: a re-evaluated atom repeats FindPair calls round 0 already
+// made for it (the pairs a copy skips never warn: the partner predicted an event for them), so the warning / error-print
+// counters of the rounds go to the scratch block and only its error flag is carried over.
+__global__ void __launch_bounds__(128, K2_MINBLOCKS) k_predict_all_fixpoint(DevP D, DevP Dq, SlotBuf B, SlotBuf C, int *qa, int *qb, int *nqueue, int *npair,
                                                                              unsigned long long *pair_sum, i64 g_base, i64 draws, int qcap) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
@@ -610,7 +614,7 @@ __global__ void __launch_bounds__(128, K2_MINBLOCKS) k_predict_all_fixpoint(DevP
         if (first < 0) first = nq;
         if (nq == 0) break;
         if (nq > qcap) { overflow = true; break; }
-        d_requeue_round(D, B, C, qa, nq, npair, pair_sum, g_base, gtid, gsz);
+        d_requeue_round(Dq, B, C, qa, nq, npair, pair_sum, g_base, gtid, gsz);
         grid.sync();
         d_requeue_commit(B, C, qa, nq, qb, nqueue + slot + 1, gtid, gsz);
         grid.sync();
@@ -630,6 +634,8 @@ __global__ void __launch_bounds__(128, K2_MINBLOCKS) k_predict_all_fixpoint(DevP
         c->g_pos += draws;
         c->pa_passes++; c->pa_rounds += rounds; c->pa_requeued += first;
         if (overflow) c->error = SDMD_ERR_STATE;
+        if (Dq.ctl->error && !c->error) c->error = Dq.ctl->error;
+        Dq.ctl->error = 0;
     }
 }
 
@@ -1079,7 +1085,7 @@ __global__ void k_cell_move(DevP D, int atom) { d_pcc_event(D, atom); }
 // running sum over all of them in atom order, so the ORDER is part of the result: WRITE = false counts the non-zero
 // addends, WRITE = true stores them (adding +-0.0 never changes a sum that started at +0.0, so zeros are dropped).
 template <bool WRITE>
-__device__ inline int d_potential_terms(const DevP &D, int i, double *out) {
+__device__ inline int d_potential_terms(const DevP &D, int i, double *out, int cap = 0x7fffffff) {
     int cnt = 0;
     double accum = 0;
     int cx = D.cell_idx[3 * i], cy = D.cell_idx[3 * i + 1], cz = D.cell_idx[3 * i + 2];
@@ -1102,7 +1108,7 @@ __device__ inline int d_potential_terms(const DevP &D, int i, double *out) {
                 if (D.hb_bond[ai] == aj) {
                     mode = FP_HB;
                     double bar = d_hb_barrier(D, ai, aj);
-                    if (bar != 0) { if (WRITE) out[cnt] = -bar; cnt++; }     // TPE -= HBBarrier(...)
+                    if (bar != 0) { if (WRITE && cnt < cap) out[cnt] = -bar; cnt++; }     // TPE -= HBBarrier(...)
                 } else if (cm & SDMD_CONSTRAINT_CONNECT) mode = FP_CONSTRAINT;
                 else if (d_neighbor_connected(D, ai, aj)) {
                     if (D.hb_neighbor[D.hb_bond[ai]] == aj) { int s = ai; ai = aj; aj = s; }
@@ -1112,24 +1118,29 @@ __device__ inline int d_potential_terms(const DevP &D, int i, double *out) {
                 double wx = D.vx[ai] - D.vx[aj], wy = D.vy[ai] - D.vy[aj], wz = D.vz[ai] - D.vz[aj];
                 double direction = rx * wx + ry * wy + rz * wz;
                 accum = d_find_pair(D, ai, aj, mode, direction, d2, hbp, 0).accum;
-                if (accum < SD_INF / 2 && accum != 0) { if (WRITE) out[cnt] = accum; cnt++; }
+                if (accum < SD_INF / 2 && accum != 0) { if (WRITE && cnt < cap) out[cnt] = accum; cnt++; }
             }
         }
     }
     return cnt;
 }
 
-// small systems: one thread walks everything in order
+// small systems (natom <= 2048): the threads of ONE block walk the atoms' neighbourhoods side by side, each atom's addends go to
+// its row of DevP::pe_terms in CalPotenE's visiting order, then thread 0 adds them up atom by atom, addend by addend — the
+// reference's summation order, hence its bits.  ONE walk per atom: FindPair's warnings count once, like CalPotenE's.
+// Returns the energy in thread 0.
+#define PE_ROW 64
 __device__ inline double d_potential_energy(const DevP &D) {
+    for (int i = threadIdx.x + 1; i <= D.n; i += blockDim.x)
+        D.pe_cnt[i] = d_potential_terms<true>(D, i, D.pe_terms + (size_t)i * PE_ROW, PE_ROW);
+    __syncthreads();
     double TPE = 0;
-    double buf[64];
-    for (int i = 1; i <= D.n; i++) {
-        int cnt = d_potential_terms<false>(D, i, nullptr);
-        if (cnt <= 64) {
-            d_potential_terms<true>(D, i, buf);
-            for (int k = 0; k < cnt; k++) TPE += buf[k];
-        } else {
-            D.ctl->error = SDMD_ERR_STATE;   // more addends than any physical neighbourhood produces
+    if (threadIdx.x == 0) {
+        for (int i = 1; i <= D.n; i++) {
+            int cnt = D.pe_cnt[i];
+            if (cnt > PE_ROW) { D.ctl->error = SDMD_ERR_STATE; continue; }   // more addends than any physical neighbourhood produces
+            const double *row = D.pe_terms + (size_t)i * PE_ROW;
+            for (int k = 0; k < cnt; k++) TPE += row[k];
         }
     }
     return TPE;
@@ -1154,8 +1165,14 @@ __global__ void k_ordered_sum(const double *terms, const int *total_ptr, long lo
     }
     if (lane == 0) *out = s;
 }
-__global__ void k_potential_energy(DevP D, double *out) { *out = d_potential_energy(D); }
-__global__ void k_potential_energy_multi(const MultiArg *args, double *out) { out[blockIdx.x] = d_potential_energy(args[blockIdx.x].P); }
+__global__ void k_potential_energy(DevP D, double *out) {
+    double e = d_potential_energy(D);
+    if (threadIdx.x == 0) *out = e;
+}
+__global__ void k_potential_energy_multi(const MultiArg *args, double *out) {
+    double e = d_potential_energy(args[blockIdx.x].P);
+    if (threadIdx.x == 0) out[blockIdx.x] = e;
+}
 // CalKinetE, ToolFunctions.c:626-656 (flow.mark < 2, constV = 0); ordered sum
 __global__ void k_ke_terms(DevP D, double *terms) {
     int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
@@ -1483,6 +1500,9 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     TRY(dupload(c, &c->d_leaf_atom, leaf_atom.data(), (size_t)n));
 
     TRY(dalloc(c, &c->d_ctl, 1));
+    TRY(dalloc(c, &c->d_ctl_scratch, 1));
+    P.pe_terms = nullptr; P.pe_cnt = nullptr;
+    if (n <= 2048) { TRY(dalloc(c, &P.pe_terms, n1 * 64)); TRY(dalloc(c, &P.pe_cnt, n1)); }
     CK(cudaMallocHost((void **)&c->h_ctl, sizeof(Ctl)));
     memset(c->h_ctl, 0, sizeof(Ctl));
     c->h_ctl->currenttime = v->currenttime;
@@ -1857,12 +1877,13 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
         }
         {
             Timer t4(c, "fixup_rounds", 2);
-            DevP P = c->P;
+            DevP P = c->P, Pq = c->P;
+            Pq.ctl = c->d_ctl_scratch;
             int *qa = c->queue_a, *qb = c->queue_b, *nq = c->nqueue, *npair = c->npair;
             unsigned long long *sum = c->d_sum;
             i64 gb = g_base, draws = need;
             int qcap = 2 * n;
-            void *args[] = {&P, &B, &C, &qa, &qb, &nq, &npair, &sum, &gb, &draws, &qcap};
+            void *args[] = {&P, &Pq, &B, &C, &qa, &qb, &nq, &npair, &sum, &gb, &draws, &qcap};
             CK(cudaLaunchCooperativeKernel((const void *)k_predict_all_fixpoint, dim3(c->fix_grid), dim3(128), args, 0, c->stream));
         }
         c->launches += 2;
@@ -2058,7 +2079,7 @@ int sdmd_cuda_potential_energy(sdmd_ctx *c, double *e) {
     double *d = (double *)(c->d_sum + 1);
     int n = c->n;
     if (n <= 2048) {
-        k_potential_energy<<<1, 1, 0, c->stream>>>(c->P, d);
+        k_potential_energy<<<1, 128, 0, c->stream>>>(c->P, d);
         c->launches++;
     } else {
         // ordered parallel form: per-atom addend lists (count -> exclusive scan -> write), then one in-order sum
@@ -2067,7 +2088,9 @@ int sdmd_cuda_potential_energy(sdmd_ctx *c, double *e) {
         int nb = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
         int *blk = nullptr;
         CK(cudaMalloc((void **)&blk, ((size_t)nb + 2) * sizeof(int)));
-        k_pe_count<<<grid_for(n, 128), 128, 0, c->stream>>>(c->P, cnt);
+        DevP Pq = c->P;
+        Pq.ctl = c->d_ctl_scratch;      // the counting walk repeats the FindPair calls of the writing walk: its warnings go to the scratch block
+        k_pe_count<<<grid_for(n, 128), 128, 0, c->stream>>>(Pq, cnt);
         k_scan_local<<<nb, 512, 0, c->stream>>>(cnt, off, blk, n);
         k_scan_blocks<<<1, 32, 0, c->stream>>>(blk, nb);
         k_scan_add<<<grid_for(n, 256), 256, 0, c->stream>>>(off, blk, n, nb);
@@ -2307,7 +2330,7 @@ int sdmd_cuda_potential_energy_many(sdmd_ctx **ctxs, int n, double *energy) {
     CK(cudaMalloc((void **)&d_args, sizeof(MultiArg) * n));
     CK(cudaMalloc((void **)&d_out, sizeof(double) * n));
     CK(cudaMemcpyAsync(d_args, args.data(), sizeof(MultiArg) * n, cudaMemcpyHostToDevice, c0->stream));
-    k_potential_energy_multi<<<n, 1, 0, c0->stream>>>(d_args, d_out);
+    k_potential_energy_multi<<<n, 128, 0, c0->stream>>>(d_args, d_out);
     c0->launches++;
     CK(cudaMemcpyAsync(energy, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, c0->stream));
     CK(cudaStreamSynchronize(c0->stream));
@@ -2456,8 +2479,8 @@ int sdmd_remd_seed_server(sdmd_ctx *c, uint32_t seed) {  // srand(seed) of sServ
 struct XchgRec { double e; double T; int32_t num; int32_t pad; double pad2; };
 static_assert(sizeof(XchgRec) == 32, "exchange record is 32 bytes");
 __global__ void k_xchg_fill(DevP D, XchgRec *rec, double T, int num) {
-    rec->e = d_potential_energy(D);
-    rec->T = T; rec->num = num; rec->pad = 0; rec->pad2 = 0;
+    double e = d_potential_energy(D);
+    if (threadIdx.x == 0) { rec->e = e; rec->T = T; rec->num = num; rec->pad = 0; rec->pad2 = 0; }
 }
 
 // ReplicaExchange (REMD.c:135-192) + collect/rearrange/distribute (Server.c:121-211) without the server:
@@ -2466,7 +2489,7 @@ __global__ void k_xchg_fill(DevP D, XchgRec *rec, double T, int num) {
 // `epot` NULL: the energy is computed on the device and written straight into the send record (systems the serial energy
 // kernel covers, natom <= 2048 — every REMD demo); otherwise *epot is what the caller computed.  On return *epot_out (if given)
 // holds this replica's energy as it went into the exchange.
-static int remd_exchange_impl(sdmd_ctx *c, const double *epot, struct sdmd_remd_temp *T, double *epot_out) {
+static int remd_exchange_impl(sdmd_ctx *c, const double *epot, struct sdmd_remd_temp *T, double *epot_out, int *active_out = nullptr) {
     CK(cudaSetDevice(c->device));
     typedef XchgRec Rec;
     int R = c->nranks;
@@ -2486,7 +2509,7 @@ static int remd_exchange_impl(sdmd_ctx *c, const double *epot, struct sdmd_remd_
         all[R] = Rec{*epot, T->T, T->num, 0, 0.0};
         CK(cudaMemcpyAsync(d_send, &all[R], sizeof(Rec), cudaMemcpyHostToDevice, c->stream));
     } else {
-        k_xchg_fill<<<1, 1, 0, c->stream>>>(c->P, d_send, T->T, T->num);
+        k_xchg_fill<<<1, 128, 0, c->stream>>>(c->P, d_send, T->T, T->num);
         c->launches++;
     }
     if (R == 1 || !c->nccl_comm) {
@@ -2501,7 +2524,9 @@ static int remd_exchange_impl(sdmd_ctx *c, const double *epot, struct sdmd_remd_
     GlibcRand &rng = *rngp;
     std::vector<double> e(R);
     std::vector<sdmd_remd_temp> t(R);
-    for (int k = 0; k < R; k++) { e[k] = all[k].e; t[k].num = all[k].num; t[k].pad_ = 0; t[k].T = all[k].T; }
+    int active = 0;
+    for (int k = 0; k < R; k++) { e[k] = all[k].e; t[k].num = all[k].num; t[k].pad_ = 0; t[k].T = all[k].T; active += all[k].T != 0; }
+    if (active_out) *active_out = active;
     // draw lazily: copy the generator, count how many the sweep used, then advance the real one
     GlibcRand probe = rng;
     std::vector<double> u(2 * R + 2);
@@ -2510,8 +2535,23 @@ static int remd_exchange_impl(sdmd_ctx *c, const double *epot, struct sdmd_remd_
     TRY(sdmd_remd_rearrange(e.data(), t.data(), R, u.data(), (int)u.size(), &used, nullptr, nullptr));
     for (int k = 0; k < used; k++) rng.next();
     *T = t[c->rank];
-    TRY(sdmd_cuda_set_temperature(c, T->T));
+    if (T->T != 0) TRY(sdmd_cuda_set_temperature(c, T->T));
     return 0;
+}
+// End of a replica's run (REMD.c:119-122 + Server.c:108-113): the reference's replica sends the server a (E = 0, T = 0) sentinel
+// and leaves; the server keeps serving rounds to the replicas still running and skips the ones that left.  A collective needs
+// every rank in every round, so a replica that is done keeps contributing its sentinel — one all-gather per round of the
+// others — until every entry is a sentinel (the server's CheckEnd); the sweep skips sentinels exactly like Server.c:150-153,
+// and every rank keeps drawing the same server stream.
+int sdmd_remd_finish(sdmd_ctx *c) {
+    if (c->nranks <= 1 || !c->nccl_comm) return 0;
+    for (;;) {
+        double zero = 0;
+        struct sdmd_remd_temp t = {0, 0, 0.0};
+        int active = 0;
+        TRY(remd_exchange_impl(c, &zero, &t, nullptr, &active));
+        if (active == 0) return 0;
+    }
 }
 int sdmd_remd_exchange(sdmd_ctx *c, double epot, struct sdmd_remd_temp *T, uint32_t /*unused*/) { return remd_exchange_impl(c, &epot, T, nullptr); }
 int sdmd_remd_exchange_energy(sdmd_ctx *c, struct sdmd_remd_temp *T, double *epot) { return remd_exchange_impl(c, nullptr, T, epot); }

@@ -149,6 +149,8 @@ struct DevP {
     const int *ther_rank;  // index of the gaussian atom i consumes in a full pass
     int no_cons;           // no constrained atom at all: ther_rank[i] == i - 1
     Ctl *ctl;
+    double *pe_terms;      // CalPotenE addends, 64 per atom (natom <= 2048 only, else NULL)
+    int *pe_cnt;
     // cell-sorted tiles produced by cell_build (fresh link-list order: descending atom id inside a cell)
     const int *cell_start;   // [ncell + 1], 0-based cell
     const int *sorted_atom;  // [n]

@@ -77,7 +77,9 @@ static void prepare_cuda(void) {
 
     int rc = sdmd_glue_flatten(&view);
     if (rc) die("sdmd_glue_flatten (feature outside the hot-path scope?)", rc);
-    rc = sdmd_cuda_create(&view, 0, &ctx);
+    /* one replica per process; the REMD launcher places replica id on GPU id % G (sREMD_cuda.c) */
+    const char *dev = getenv("SDMD_CUDA_DEVICE");
+    rc = sdmd_cuda_create(&view, dev ? atoi(dev) : 0, &ctx);
     if (rc) die("sdmd_cuda_create", rc);
     int cn[3];
     double cs[3];
@@ -132,9 +134,43 @@ void SingleThread(void) {
     sdmd_cuda_destroy(ctx);
 }
 
+/* NCCL exchange (sREMD_cuda's default): the replicas of the run form one communicator, rank = replica id.  Rank 0 creates the
+ * ncclUniqueId and publishes it through the file the launcher named; the others wait for it. */
+static int nccl_mode(void) { const char *e = getenv("SDMD_REMD_NCCL"); return e && e[0] == '1'; }
+static void nccl_join(void) {
+    const char *sr = getenv("SDMD_REMD_NRANKS"), *sk = getenv("SDMD_REMD_RANK"), *path = getenv("SDMD_REMD_ID_FILE"), *ss = getenv("SDMD_REMD_SEED");
+    if (!sr || !sk || !path || !ss) { printf("!!ERROR!!: SDMD_REMD_NCCL needs SDMD_REMD_NRANKS / _RANK / _ID_FILE / _SEED (set by sREMD_cuda)\n"); exit(EXIT_FAILURE); }
+    int nranks = atoi(sr), rank = atoi(sk), rc;
+    unsigned char id[128];
+    if (rank == 0) {
+        if ((rc = sdmd_remd_nccl_unique_id(id))) die("sdmd_remd_nccl_unique_id", rc);
+        char tmp[1100];
+        snprintf(tmp, sizeof(tmp), "%s.tmp", path);
+        FILE *f = fopen(tmp, "wb");
+        if (!f || fwrite(id, 1, 128, f) != 128) { printf("!!ERROR!!: cannot write %s\n", tmp); exit(EXIT_FAILURE); }
+        fclose(f);
+        rename(tmp, path);                                   /* atomic: readers never see a partial id */
+    } else {
+        for (int tries = 0;; tries++) {
+            FILE *f = fopen(path, "rb");
+            if (f) {
+                size_t got = fread(id, 1, 128, f);
+                fclose(f);
+                if (got == 128) break;
+            }
+            if (tries > 6000) { printf("!!ERROR!!: no NCCL id from replica 0 in %s\n", path); exit(EXIT_FAILURE); }
+            usleep(10000);
+        }
+    }
+    if ((rc = sdmd_remd_nccl_init(ctx, nranks, rank, id))) die("sdmd_remd_nccl_init", rc);
+    if ((rc = sdmd_remd_seed_server(ctx, (uint32_t)strtoul(ss, NULL, 10)))) die("sdmd_remd_seed_server", rc);
+}
+
 /* REMD(), REMD.c:24-126 */
 void REMD(void) {
     prepare_cuda();
+    const int nccl = nccl_mode();
+    if (nccl) nccl_join();
     int outputRate = REMDInfo.REMD_OutputRate;
     int rate = ((int)(currenttime / outputRate) + 1) * outputRate;      /* REMD.c:32 */
     struct sdmd_run_stats st;
@@ -146,19 +182,34 @@ void REMD(void) {
         if (currenttime >= outputrecord) save_outputs();                 /* REMD.c:88-95 */
         if (currenttime >= rate) {                                       /* REMD.c:97-104 */
             double potenEnergy;
-            int rc = sdmd_cuda_potential_energy(ctx, &potenEnergy);
-            if (rc) die("potential_energy", rc);
-            ReplicaExchange(&potenEnergy, &REMDInfo.REMD_Temperature, REMDInfo.REMD_ServerName, &REMDInfo.REMD_PortNum);
-            targetTemperature = REMDInfo.REMD_Temperature.T;
-            sdmd_cuda_set_temperature(ctx, targetTemperature);
+            int rc;
+            if (nccl) {
+                /* CalPotenE + ReplicaExchange + the server's sweep in one call: energy computed on the device into the send
+                 * record, ncclAllGather, replicated Server.c:145-192 sweep; the new temperature is set on the device inside */
+                struct sdmd_remd_temp t = {REMDInfo.REMD_Temperature.num, 0, REMDInfo.REMD_Temperature.T};
+                if ((rc = sdmd_remd_exchange_energy(ctx, &t, &potenEnergy))) die("sdmd_remd_exchange_energy", rc);
+                REMDInfo.REMD_Temperature.num = t.num;
+                REMDInfo.REMD_Temperature.T = t.T;
+                targetTemperature = t.T;
+            } else {
+                if ((rc = sdmd_cuda_potential_energy(ctx, &potenEnergy))) die("potential_energy", rc);
+                ReplicaExchange(&potenEnergy, &REMDInfo.REMD_Temperature, REMDInfo.REMD_ServerName, &REMDInfo.REMD_PortNum);
+                targetTemperature = REMDInfo.REMD_Temperature.T;
+                sdmd_cuda_set_temperature(ctx, targetTemperature);
+            }
             SaveData(RE, fileList);
             rate += outputRate;
         }
     }
     sync_to_reference();
     warningsum += st.warnings;
-    tmpDouble = 0.0;                                                     /* REMD.c:119-122 */
-    REMDInfo.REMD_Temperature.T = 0.0;
-    ReplicaExchange(&tmpDouble, &REMDInfo.REMD_Temperature, REMDInfo.REMD_ServerName, &REMDInfo.REMD_PortNum);
+    if (nccl) {                                                          /* the sentinel of REMD.c:119-122, as a collective */
+        int rc = sdmd_remd_finish(ctx);
+        if (rc) die("sdmd_remd_finish", rc);
+    } else {
+        tmpDouble = 0.0;
+        REMDInfo.REMD_Temperature.T = 0.0;
+        ReplicaExchange(&tmpDouble, &REMDInfo.REMD_Temperature, REMDInfo.REMD_ServerName, &REMDInfo.REMD_PortNum);
+    }
     sdmd_cuda_destroy(ctx);
 }

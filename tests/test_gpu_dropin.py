@@ -167,3 +167,47 @@ def test_dropin_remd_with_reference_server(tmp_path):
         a = (tmp_path / "r" / f"ref{k}" / "out").glob("out_trj*")
         b = (tmp_path / "g" / f"ref{k}" / "out").glob("out_trj*")
         assert next(a).read_bytes() == next(b).read_bytes()
+
+
+def _device_count():
+    from sdmd_b200 import capi
+    return int(capi.lib().sdmd_cuda_device_count())
+
+
+@pytest.mark.parametrize("nrep", [2, 4, 8])
+def test_remd_launcher_nccl_matches_reference_server(tmp_path, nrep):
+    """The C launcher (sREMD_cuda, role of REMDExec.c) with its default exchange — one NCCL communicator over the replicas, one
+    GPU each, CalPotenE + all-gather + replicated Server.c sweep inside sdmd_remd_exchange_energy — against the stock binaries
+    coupled through the reference's sServer with the same server seed: every replica's temperature walk (out_REMD<id>.txt) and
+    trajectory must be identical.  Needs one GPU per replica (run with `gpurun --gpus N`); skipped on smaller boxes."""
+    launcher = DROPIN.parent / "sREMD_cuda"
+    if not (REF / "sServer").exists() or not DROPIN.exists() or not launcher.exists():
+        pytest.skip("needs oracle/_ref and the drop-in driver + launcher")
+    if _device_count() < nrep:
+        pytest.skip(f"needs {nrep} GPUs")
+    from tests.remd_ref import TEMPS_K, run_reference_remd
+    rate, tu, seed = 5.0, 40.0, 99
+    ref_logs, _ = run_reference_remd(tmp_path / "r", nrep, rate, tu, seed)
+    work = tmp_path / "g"
+    work.mkdir()
+    shutil.copytree(REF / "input", work / "input")
+    lines = (REF / "demo_REMD" / "parameter.txt").read_text().splitlines()
+    lines[1] = "Time               %g" % tu
+    (work / "input" / "parameter.txt").write_text("\n".join(lines) + "\n")
+    (work / "out").mkdir()
+    (work / "REMDConfig.txt").write_text("#REPLICA EXCHANGE MD CONFIGURATION FILE\n"
+                                         f"ReplicaNum              = {nrep}\n"
+                                         "Temperatures            = " + " ".join("%g" % t for t in TEMPS_K[:nrep]) + "\n"
+                                         "SocketPort              = 20202\n"
+                                         f"ExchangeRate            = {int(rate)}\n")
+    r = subprocess.run([str(launcher), "-f", "REMDConfig.txt", "-args", "-i", str(work / "input"), "-f", "ala10.gro", "-o", str(work / "out"), "-end",
+                        "-seed", str(seed), "-exe", str(DROPIN)], cwd=work, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:] + "".join((work / f"outputData_{k}.txt").read_text()[-800:] for k in range(nrep))
+    for k in range(nrep):
+        got = list((work / "out").glob(f"out_REMD*{k}.txt"))
+        assert len(got) == 1, sorted(p.name for p in (work / "out").iterdir())
+        assert got[0].read_text() == ref_logs[k], k
+        a = next((tmp_path / "r" / f"ref{k}" / "out").glob("out_trj*"))
+        b = next((work / "out").glob(f"out_trj*{k}.gro"))
+        assert a.read_bytes() == b.read_bytes(), k
+    assert any(len(set(ln.split()[2] for ln in log.splitlines())) > 1 for log in ref_logs)      # somebody actually swapped
