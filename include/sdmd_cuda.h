@@ -381,11 +381,13 @@ int  sdmd_cuda_synchronize(sdmd_ctx *ctx);
 int  sdmd_cuda_host_register(void *ptr, size_t bytes);
 int  sdmd_cuda_host_unregister(void *ptr);
 /* How sdmd_cuda_run drives the loop: AUTO = one persistent thread block for natom <= 2048, CLUSTER = one persistent
- * thread-block cluster (block 0 runs the events, the others help with UpdateData/TimeForward) up to 98304, otherwise SWEEP = one launch
- * per iteration in which the grid-wide UpdateData/TimeForward sweep and the event-execution block run side by side
- * (the event block applies the sweep's arithmetic on the fly to what it reads).  SWEEP_SERIAL runs the sweep and the
- * event block one after the other.  Results are identical; tests force all of them. */
-enum sdmd_loop_mode { SDMD_LOOP_AUTO = 0, SDMD_LOOP_ONE_CTA = 1, SDMD_LOOP_SWEEP = 2, SDMD_LOOP_SWEEP_SERIAL = 3, SDMD_LOOP_CLUSTER = 4 };
+ * thread-block cluster (block 0 runs the events, the others help with UpdateData/TimeForward) up to 98304, otherwise SWEEP = ONE
+ * cooperative launch for the whole run, one block per SM: block 0 executes the events, the others sweep
+ * UpdateData/TimeForward over all atoms side by side with it (the event block applies the sweep's arithmetic on the fly to
+ * what it reads), a grid-wide barrier per iteration.  SWEEP_LAUNCH is the same overlap with one launch per iteration,
+ * SWEEP_SERIAL runs the sweep and the event block one after the other.  Results are identical; tests force all of them. */
+enum sdmd_loop_mode { SDMD_LOOP_AUTO = 0, SDMD_LOOP_ONE_CTA = 1, SDMD_LOOP_SWEEP = 2, SDMD_LOOP_SWEEP_SERIAL = 3, SDMD_LOOP_CLUSTER = 4,
+                      SDMD_LOOP_SWEEP_LAUNCH = 5 };
 int  sdmd_cuda_set_loop_mode(sdmd_ctx *ctx, int mode);
 void sdmd_cuda_set_timing(sdmd_ctx *ctx, int on);   /* CUDA-event brackets per stage (asynchronous, resolved on query): 0 off, 1 default, 2 also predict_all's fix-up sub-stages */
 int64_t sdmd_cuda_launch_count(const sdmd_ctx *ctx);

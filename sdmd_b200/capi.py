@@ -365,7 +365,7 @@ class Replica:
     def phase_cycles(self):
         out = (C.c_int64 * 12)()
         _check(self.L.sdmd_cuda_phase_cycles(self.h, out), "phase_cycles")
-        names = ["head", "advance", "event", "gather", "eval", "fold", "cbt", "iterations", "event_thread0", "x9",
+        names = ["head", "advance", "event", "gather", "eval", "fold", "cbt", "iterations", "event_thread0", "wait_sweep",
                  "x10", "x11"]
         return dict(zip(names, out[:12]))
 

@@ -737,10 +737,15 @@ __global__ void __launch_bounds__(256, 1) k_run_cta(DevP Dg, double t_until, i64
     __shared__ Ctl s_ctl;      // the loop state lives in shared memory while the kernel runs (written back on exit)
     __shared__ double s_dt;
     __shared__ int s_stop;
+    // the replica descriptor goes to shared memory once: a per-thread `DevP D = Dg` is a 1 KB local-memory copy per thread
+    // (256 KB per block, more than L1 holds), and every D.field of the loop below would be a local load
+    __shared__ DevP s_D;
     for (int k = threadIdx.x; k < (int)(sizeof(Ctl) / sizeof(int)); k += blockDim.x) ((int *)&s_ctl)[k] = ((const int *)Dg.ctl)[k];
+    for (int k = threadIdx.x; k < (int)(sizeof(DevP) / sizeof(int)); k += blockDim.x) ((int *)&s_D)[k] = ((const int *)&Dg)[k];
     __syncthreads();
-    DevP D = Dg;
-    D.ctl = &s_ctl;
+    if (threadIdx.x == 0) s_D.ctl = &s_ctl;
+    __syncthreads();
+    const DevP &D = s_D;
     for (;;) {
         long long h0 = clock64();
         if (threadIdx.x == 0) {
@@ -782,11 +787,14 @@ __global__ void __launch_bounds__(256, 1) k_run_cluster(DevP Dg, double t_until,
     __shared__ Ctl s_ctl;
     __shared__ double s_dt;
     __shared__ int s_stop;
+    __shared__ DevP s_D;       // see k_run_cta
     if (rank == 0)
         for (int k = threadIdx.x; k < (int)(sizeof(Ctl) / sizeof(int)); k += blockDim.x) ((int *)&s_ctl)[k] = ((const int *)Dg.ctl)[k];
+    for (int k = threadIdx.x; k < (int)(sizeof(DevP) / sizeof(int)); k += blockDim.x) ((int *)&s_D)[k] = ((const int *)&Dg)[k];
     __syncthreads();
-    DevP D = Dg;
-    D.ctl = &s_ctl;
+    if (threadIdx.x == 0) s_D.ctl = &s_ctl;
+    __syncthreads();
+    const DevP &D = s_D;
     const double *r_dt = cluster.map_shared_rank(&s_dt, 0);
     const int *r_stop = cluster.map_shared_rank(&s_stop, 0);
     for (;;) {
@@ -885,10 +893,13 @@ __global__ void __launch_bounds__(256, 1) k_event_exec(DevP Dg, double t_until, 
     __shared__ PredShared sh;
     __shared__ Ctl s_ctl;      // loop state in shared memory while the block works, written back at the end
     if (Dg.ctl->stop) return;
+    __shared__ DevP s_D;       // see k_run_cta
     for (int k = threadIdx.x; k < (int)(sizeof(Ctl) / sizeof(int)); k += blockDim.x) ((int *)&s_ctl)[k] = ((const int *)Dg.ctl)[k];
+    for (int k = threadIdx.x; k < (int)(sizeof(DevP) / sizeof(int)); k += blockDim.x) ((int *)&s_D)[k] = ((const int *)&Dg)[k];
     __syncthreads();
-    DevP D = Dg;
-    D.ctl = &s_ctl;
+    if (threadIdx.x == 0) s_D.ctl = &s_ctl;
+    __syncthreads();
+    const DevP &D = s_D;
     if (threadIdx.x == 0) d_publish_job(D, sh);
     __syncthreads();
     d_loop_body_cta(D, sh, t_until, trace, trace_cap);
@@ -1032,6 +1043,206 @@ __global__ void __launch_bounds__(256, 2) k_sweep_event(DevP Dg, int slot, i64 s
     }
     __syncthreads();
     for (int k = threadIdx.x; k < (int)(sizeof(Ctl) / sizeof(int)); k += blockDim.x) ((int *)Dg.ctl)[k] = ((const int *)&s_ctl)[k];
+}
+
+// The same overlapped iteration as k_sweep_event, but the whole loop in ONE cooperative launch (SGThread.c:75-152 never leaves
+// the device): one block per SM, block 0 is the event block, the others sweep.  The two coordinate / event-time buffers swap
+// roles every iteration (Dg describes iteration parity 0: read lz_*, write x/y/z/ev_time).  No grid-wide barrier is needed:
+//   * a sweep thread only ever touches its own atoms (the same ones every iteration), so sweep blocks do not depend on each
+//     other; what they wait for is the NEXT job — (dt, target, partner), published by the event block in the control block's
+//     per-parity slot with the iteration number written last (release) — and that also orders the event block's own writes of
+//     the two event atoms in front of the sweep that reads them;
+//   * the event block of iteration n + 1 reads other atoms from the buffer sweep n wrote, so every sweep block counts itself
+//     done (one release-add per block and iteration) and the event block checks the count before it goes on — by then the sweep
+//     (14 us) has long finished, the check is one load.
+// The event block keeps the loop state in shared memory for the whole run.  One block per SM lets the event role keep its
+// working set in registers (no spills); the sweep role makes up for the smaller grid with several atoms in flight per thread.
+#ifndef SWEEP_UNROLL
+#define SWEEP_UNROLL 2   // atoms in flight per sweep thread: 2 keeps the sweep (~20 us) just under the event block without flooding the memory system (scripts/loop_variants.py)
+#endif
+__device__ __forceinline__ long long ld_acquire_i64(const long long *p) {
+    long long v;
+    asm volatile("ld.acquire.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_i64(long long *p, long long v) {
+    asm volatile("st.release.gpu.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__global__ void __launch_bounds__(256, 1) k_run_sweep(DevP Dg, i64 seq0, unsigned long long *sweep_done, double t_until, i64 iter_limit,
+                                                       sdmd_trace_rec *trace, i64 trace_cap) {
+    __shared__ lz1::PredShared sh;
+    __shared__ Ctl s_ctl;
+    __shared__ int s_type0;
+    __shared__ volatile double s_sink[64];
+    __shared__ Ctl::Job s_job;
+    const bool ev = blockIdx.x == 0;
+    const unsigned long long nsweep = gridDim.x - 1;
+    // The event role sees the replica through a descriptor in SHARED memory, one per buffer parity, built once: a per-thread copy
+    // of the ~1 KB parameter block every iteration (what `DevP D = Dg; D.x = ...` compiles to) is 256 KB of local-memory traffic
+    // per event.  Per iteration only dt / target / partner change (thread 0, three stores).
+    __shared__ DevP s_D[2];
+    if (ev) {
+        for (int k = threadIdx.x; k < (int)(sizeof(Ctl) / sizeof(int)); k += blockDim.x) ((int *)&s_ctl)[k] = ((const int *)Dg.ctl)[k];
+        for (int k = threadIdx.x; k < (int)(sizeof(DevP) / sizeof(int)); k += blockDim.x) {
+            int w = ((const int *)&Dg)[k];
+            ((int *)&s_D[0])[k] = w; ((int *)&s_D[1])[k] = w;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_D[0].ctl = &s_ctl; s_D[1].ctl = &s_ctl;
+            // parity 1 reads what parity 0 writes and the other way round
+            s_D[1].x = const_cast<double *>(Dg.lz_x); s_D[1].y = const_cast<double *>(Dg.lz_y); s_D[1].z = const_cast<double *>(Dg.lz_z);
+            s_D[1].ev_time = const_cast<double *>(Dg.lz_t);
+            s_D[1].lz_x = Dg.x; s_D[1].lz_y = Dg.y; s_D[1].lz_z = Dg.z; s_D[1].lz_t = Dg.ev_time;
+        }
+        __syncthreads();
+    }
+    i64 seq = seq0;                                          // iteration number of the job this trip executes
+    for (int r = 0;; r ^= 1) {
+        // this iteration reads buffer r and writes buffer r ^ 1
+        Ctl::Job job;
+        if (ev) {
+            job = s_ctl.job[r];
+            // everything sweep (seq - 1) wrote must be there before this iteration reads it
+            if (threadIdx.x == 0 && seq > seq0) {
+                const unsigned long long want = nsweep * (unsigned long long)(seq - seq0);
+                long long w0 = clock64();
+                while ((unsigned long long)ld_acquire_i64(reinterpret_cast<const long long *>(sweep_done)) < want) __nanosleep(20);
+                s_ctl.phase_cycles[9] += clock64() - w0;     // waiting for the sweep: ~one load unless the sweep is the slower side
+            }
+            __syncthreads();
+        } else {
+            static_assert(sizeof(Ctl::Job) == 32 && offsetof(Ctl::Job, seq) == 8, "job slot: dt, seq, target, partner, go, pad");
+            if (threadIdx.x == 0) {
+                const long long *slot = reinterpret_cast<const long long *>(&Dg.ctl->job[r]);
+                while (ld_acquire_i64(slot + 1) != seq) __nanosleep(20);              // the iteration number is written last
+                long long w[4] = {__ldcg(slot), seq, __ldcg(slot + 2), __ldcg(slot + 3)};
+                memcpy(&s_job, w, 32);
+            }
+            __syncthreads();
+            job = s_job;
+        }
+        if (!job.go) break;
+        if (!ev) {
+            const double dt = job.dt;
+            const int a = job.target, b = job.partner, n = Dg.n;
+            struct { const double *lz_x, *lz_y, *lz_z, *lz_t, *vx, *vy, *vz; double *x, *y, *z, *ev_time; } D;
+            D.lz_x = r ? Dg.x : Dg.lz_x; D.lz_y = r ? Dg.y : Dg.lz_y; D.lz_z = r ? Dg.z : Dg.lz_z; D.lz_t = r ? Dg.ev_time : Dg.lz_t;
+            D.x = r ? const_cast<double *>(Dg.lz_x) : Dg.x; D.y = r ? const_cast<double *>(Dg.lz_y) : Dg.y;
+            D.z = r ? const_cast<double *>(Dg.lz_z) : Dg.z; D.ev_time = r ? const_cast<double *>(Dg.lz_t) : Dg.ev_time;
+            D.vx = Dg.vx; D.vy = Dg.vy; D.vz = Dg.vz;
+            const int stride = (gridDim.x - 1) * blockDim.x;
+            for (int i0 = (blockIdx.x - 1) * blockDim.x + threadIdx.x + 1; i0 <= n; i0 += SWEEP_UNROLL * stride) {
+                double x[SWEEP_UNROLL], y[SWEEP_UNROLL], z[SWEEP_UNROLL], t[SWEEP_UNROLL], vx[SWEEP_UNROLL], vy[SWEEP_UNROLL], vz[SWEEP_UNROLL];
+#pragma unroll
+                for (int q = 0; q < SWEEP_UNROLL; q++) {
+                    int i = i0 + q * stride;
+                    if (i <= n) {
+                        // streaming (evict-first) accesses: the sweep must not push the event block's working set out of L2
+                        x[q] = __ldcs(&D.lz_x[i]); y[q] = __ldcs(&D.lz_y[i]); z[q] = __ldcs(&D.lz_z[i]); t[q] = __ldcs(&D.lz_t[i]);
+                        vx[q] = __ldcs(&D.vx[i]); vy[q] = __ldcs(&D.vy[i]); vz[q] = __ldcs(&D.vz[i]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < SWEEP_UNROLL; q++) {
+                    int i = i0 + q * stride;
+                    if (i <= n && i != a && i != b) {
+                        __stcs(&D.x[i], x[q] + vx[q] * dt); __stcs(&D.y[i], y[q] + vy[q] * dt); __stcs(&D.z[i], z[q] + vz[q] * dt);
+                        __stcs(&D.ev_time[i], t[q] - dt);
+                    }
+                }
+            }
+            __syncthreads();                                  // this block's share of sweep `seq` is written ...
+            if (threadIdx.x == 0) { __threadfence(); atomicAdd(sweep_done, 1ULL); }   // ... and counted (release)
+        } else {
+            long long k0 = clock64();
+            const DevP &D = s_D[r];
+            if (threadIdx.x >= 128 && threadIdx.x < 136) {
+                int q = (threadIdx.x - 128) >> 2, f = (threadIdx.x - 128) & 3;
+                int i = q ? job.partner : job.target;
+                if (i > 0) {
+                    const double *src = f == 0 ? D.lz_x : f == 1 ? D.lz_y : f == 2 ? D.lz_z : D.lz_t;
+                    double v = src[i];
+                    // the event's own atoms move to the new buffer now (same arithmetic as the sweep)
+                    if (f == 0) v = v + D.vx[i] * job.dt; else if (f == 1) v = v + D.vy[i] * job.dt; else if (f == 2) v = v + D.vz[i] * job.dt; else v = v - job.dt;
+                    double *dst = f == 0 ? D.x : f == 1 ? D.y : f == 2 ? D.z : D.ev_time;
+                    dst[i] = v;
+                }
+            }
+            if (threadIdx.x == 160) s_type0 = D.ev_type[job.target];
+            if (threadIdx.x == 0) { s_D[r].lz_dt = job.dt; s_D[r].lz_a = job.target; s_D[r].lz_b = job.partner; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s_ctl.live = r ^ 1;
+                sh.atom[0] = job.target;
+                sh.atom[1] = job.partner;
+                sh.gathered = (s_type0 != SDMD_EV_PCC && s_type0 != SDMD_EV_HB);   // as d_publish_job
+            }
+            __syncthreads();
+            long long k1 = lz1::d_clock_after(&sh.atom[0]);
+            // idle warps warm this SM's L1 with what thread 0 is about to read one dependent load at a time ...
+            if (threadIdx.x >= 192 && threadIdx.x < 224) {
+                int l = threadIdx.x - 192, i = (l & 16) ? job.partner : job.target;
+                double v = 0;
+                if (i > 0) {
+                    switch (l & 15) {
+                        case 0: v = D.mass[i]; break;
+                        case 1: v = (double)D.ev_counter[i]; break;
+                        case 2: v = (double)D.ev_pcounter[i]; break;
+                        case 3: v = (double)D.is_cons[i]; break;
+                        case 4: v = (double)D.ev_partner[i]; break;
+                        case 5: v = (double)D.ev_sub[i]; break;
+                        case 6: v = D.vx[i]; break;
+                        case 7: v = D.vy[i]; break;
+                        case 8: v = D.vz[i]; break;
+                        case 9: v = D.ev_pot[i]; break;
+                        case 10: v = (double)D.cell_idx[3 * i]; break;
+                        case 11: v = (double)D.type[i]; break;
+                        case 12: v = D.gauss[s_ctl.g_pos % D.g_cap]; break;
+                        case 13: v = D.gauss[(s_ctl.g_pos + 4) % D.g_cap]; break;
+                        case 14: v = (double)D.cbt_leaf[i]; break;
+                        default: break;
+                    }
+                }
+                s_sink[32 + l] = v;
+            }
+            if (threadIdx.x >= 224) {
+                // ... and walk the tournament-tree paths of the event's atoms now (leaf -> siblings -> their times)
+                int lane = threadIdx.x - 224;
+                double acc = 0;
+                for (int q = 0; q < 2; q++) {
+                    int i = q ? job.partner : job.target;
+                    if (i <= 0) continue;
+                    int child = D.cbt_leaf[i] >> lane;
+                    if (child > 1) {
+                        int sib = D.cbt_node[child ^ 1];
+                        acc += (double)D.cbt_node[child >> 1] + D.lz_t[sib] + (double)D.ev_partner[sib];
+                    }
+                }
+                s_sink[lane] = acc;
+            }
+            lz1::d_loop_body_cta(D, sh, t_until, trace, trace_cap);
+            if (threadIdx.x == 0) {
+                long long k2 = clock64();
+                lz1::d_loop_head(D, t_until, iter_limit);
+                d_publish_next_job(D, r ^ 1);
+                // for the sweep blocks: payload first, the iteration number last (release) — it also publishes the event block's
+                // writes of this iteration's two atoms
+                const Ctl::Job &nj = s_ctl.job[r ^ 1];
+                Ctl::Job *slot = &Dg.ctl->job[r ^ 1];
+                slot->dt = nj.dt; slot->target = nj.target; slot->partner = nj.partner; slot->go = nj.go; slot->pad_ = 0;
+                st_release_i64(reinterpret_cast<long long *>(&slot->seq), nj.seq);
+                s_ctl.phase_cycles[0] += k1 - k0;
+                s_ctl.phase_cycles[1] += clock64() - k2;
+            }
+            __syncthreads();
+        }
+        seq++;
+    }
+    if (ev) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < (int)(sizeof(Ctl) / sizeof(int)); k += blockDim.x) ((int *)Dg.ctl)[k] = ((const int *)&s_ctl)[k];
+    }
 }
 
 // ---- single-step kernels behind the per-function C-ABI ----
@@ -1616,7 +1827,7 @@ int sdmd_cuda_host_unregister(void *ptr) {
 }
 int sdmd_cuda_set_loop_mode(sdmd_ctx *c, int mode) {
     if (mode != SDMD_LOOP_AUTO && mode != SDMD_LOOP_ONE_CTA && mode != SDMD_LOOP_SWEEP && mode != SDMD_LOOP_SWEEP_SERIAL &&
-        mode != SDMD_LOOP_CLUSTER)
+        mode != SDMD_LOOP_CLUSTER && mode != SDMD_LOOP_SWEEP_LAUNCH)
         return set_err(SDMD_ERR_BAD_ARG, "loop mode");
     c->loop_mode = mode;
     return 0;
@@ -2211,8 +2422,32 @@ int sdmd_cuda_run(sdmd_ctx *c, double t_until, int64_t max_iter, struct sdmd_tra
             TRY(pull_ctl(c));
             if (c->h_ctl->stop) break;
         }
+    } else if (c->loop_mode != SDMD_LOOP_SWEEP_LAUNCH) {
+        // overlapped sweep, the whole loop in one cooperative launch: one block per SM, block 0 the event block (k_run_sweep)
+        size_t n1 = (size_t)c->n + 1;
+        if (!c->x2) { TRY(dalloc(c, &c->x2, n1)); TRY(dalloc(c, &c->y2, n1)); TRY(dalloc(c, &c->z2, n1)); TRY(dalloc(c, &c->t2, n1)); }
+        DevP Pw = c->P;      // parity 0: reads the live arrays, writes the spare ones
+        Pw.x = c->x2; Pw.y = c->y2; Pw.z = c->z2; Pw.ev_time = c->t2;
+        Pw.lz_x = c->P.x; Pw.lz_y = c->P.y; Pw.lz_z = c->P.z; Pw.lz_t = c->P.ev_time;
+        Pw.lz_on = 1;
+        c->counters_known = false;
+        k_loop_head_job<<<1, 1, 0, c->stream>>>(c->P, t_until, iter_limit, 0);
+        int sms = 0;
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+        i64 seq0 = c->h_ctl->iterations;        // iteration number of the first job (k_loop_head_job publishes it in slot 0)
+        unsigned long long *done = c->d_sum + 3;  // scratch counter: sweep blocks x iterations finished
+        CK(cudaMemsetAsync(done, 0, sizeof(*done), c->stream));
+        void *args[] = {&Pw, &seq0, &done, &t_until, &iter_limit, &dtr, &trace_cap};
+        // cooperative launch: every block must be resident (they wait on each other through memory), nothing else is used of it
+        CK(cudaLaunchCooperativeKernel((const void *)k_run_sweep, dim3(sms), dim3(256), args, 0, c->stream));
+        c->launches += 2;
+        CK(cudaGetLastError());
+        TRY(pull_ctl(c));
+        if (c->h_ctl->live == 1) {   // the state ended up in the spare buffer: it becomes the live one
+            std::swap(c->P.x, c->x2); std::swap(c->P.y, c->y2); std::swap(c->P.z, c->z2); std::swap(c->P.ev_time, c->t2);
+        }
     } else {
-        // overlapped sweep: one launch per iteration, event block and sweep blocks side by side (k_sweep_event)
+        // the same overlap with one launch per iteration (k_sweep_event), kept for comparison: its rate follows the host
         size_t n1 = (size_t)c->n + 1;
         if (!c->x2) { TRY(dalloc(c, &c->x2, n1)); TRY(dalloc(c, &c->y2, n1)); TRY(dalloc(c, &c->z2, n1)); TRY(dalloc(c, &c->t2, n1)); }
         DevP Pw[2];   // Pw[r]: reads buffer r, writes buffer r ^ 1; buffer 0 = the live arrays at entry

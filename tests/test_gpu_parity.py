@@ -51,7 +51,7 @@ def test_predict_all_and_cbt_match_reference(capi, case):
 
 
 @pytest.mark.parametrize("case", ["ala10", "ala10_hb", "gel10", "ala10x8", "ala10x8_wallp", "ala10x4_wallc", "ala10x8_obst", "abeta8", "ala10x4_tunnel", "ala10_flowv", "ala10_flowf", "ala10_charge"])
-@pytest.mark.parametrize("loop_mode", [1, 4, 2, 3], ids=["one_cta", "cluster", "sweep_overlapped", "sweep_serial"])
+@pytest.mark.parametrize("loop_mode", [1, 4, 2, 5, 3], ids=["one_cta", "cluster", "sweep_persistent", "sweep_per_launch", "sweep_serial"])
 def test_device_event_loop_matches_reference(capi, case, loop_mode):
     """loop_mode 4 forces the mid-size driver (one thread-block cluster) and 2 / 3 force the large-system drivers (grid-wide sweep overlapped with / followed by one event block per
     iteration) onto the protein cases too, so every loop driver is pinned to the reference trace with bonds, HB and
