@@ -1693,7 +1693,7 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
         int trc = sdmd_k2_tile_configure(P, c->device);   // bond-free systems: round 0 as one tile kernel, no survivor rows in HBM
         if (trc < 0) return set_err(SDMD_ERR_CUDA, "tile kernel configuration", cudaGetLastError());
     }
-    if (n < (1 << 27) && !P.tile_tx) {
+    if (n < (1 << 27) && P.tile_mode != 1) {
         // row size: a sparse bond-free box (the GEL lattices: ~4 atoms expected inside the scan sphere) gets 64-byte rows, which
         // halves the footprint the evaluation kernel streams through L2 (287 -> 275 us at 1M atoms); longer lists overflow
         // into the exact in-kernel re-scan either way
@@ -2058,7 +2058,7 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
     {
         Timer t(c, "predict_all");
         const bool tile = c->P.tile_tx > 0;
-        if (c->P.surv && !tile) {
+        if (c->P.surv && c->P.tile_mode != 1) {
             k_predict_all_filter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P);
             c->launches++;
         }

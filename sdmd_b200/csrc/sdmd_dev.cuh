@@ -169,7 +169,7 @@ struct DevP {
     float cut2_f32;          // cut2 * (1 + 1e-4), rounded up: superset sphere of the single-precision test
     float cellsize_f[3];
     // round 0 as one tile kernel (sdmd_k2_tile.cu): own cells per thread block, halo capacity in atoms, dynamic shared memory
-    int tile_tx, tile_ty, tile_tz, tile_hcap, tile_smem;
+    int tile_tx, tile_ty, tile_tz, tile_hcap, tile_smem, tile_mode;
     float tile_cut2f;        // superset sphere of the tile kernel's single-precision test (tile-relative coordinates)
     // Overlapped sweep (large-system loop): while the grid-wide UpdateData/TimeForward sweep of event n is still
     // running, the event block already works on event n.  x/y/z/ev_time above are then the buffer the sweep WRITES;

@@ -418,18 +418,183 @@ __global__ void __launch_bounds__(TILE_NT, TILE_MINBLOCKS) k_predict_all_tile(De
 }
 
 // ----------------------------------------------------------------------------------------------------------------------
+// Variant 2 (SDMD_K2_TILE=2): the neighbour filter stays the stand-alone kernel (k_predict_all_filter: survivor rows in HBM, in
+// visiting order), only the EVALUATION becomes a tile kernel.  The 64-byte records of a block's halo are staged by TMA exactly
+// as above; a thread then walks its atom's survivor row in order and evaluates every survivor from shared memory — no gather
+// from HBM/L2 per survivor, which is what the stand-alone evaluation kernel waits on (long-scoreboard stalls).  The fold is the
+// sequential one (JobAssign per survivor in visiting order), so no visiting ranks are needed.
+__global__ void __launch_bounds__(TILE_NT, TILE_MINBLOCKS) k_predict_all_evaltile(DevP D, SlotBuf dst, Round0Out out, i64 g_base) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int TX = D.tile_tx, TY = D.tile_ty, TZ = D.tile_tz;
+    const int HX = TX + 2, HY = TY + 2, HZ = TZ + 2, HXY = HX * HY, HC = HXY * HZ;
+    const int HCAP = D.tile_hcap;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem);
+    int *misc = reinterpret_cast<int *>(smem + 8);
+    SRec *rec = reinterpret_cast<SRec *>(smem + 16);
+    int *lbeg = reinterpret_cast<int *>(rec + HCAP);
+    int *gbeg = lbeg + HC + 1;
+    int *rowoff = gbeg + HC;
+    int *rowbeg = rowoff + TY * TZ + 1;
+    int *rowh = rowbeg + TY * TZ;
+
+    const int nx = D.cellnum[0], ny = D.cellnum[1], nz = D.cellnum[2];
+    const int ntx = (nx + TX - 1) / TX, nty = (ny + TY - 1) / TY;
+    const int bid = blockIdx.x;
+    const int x0 = (bid % ntx) * TX, y0 = ((bid / ntx) % nty) * TY, z0 = (bid / (ntx * nty)) * TZ;
+    const int TXe = min(TX, nx - x0), TYe = min(TY, ny - y0), TZe = min(TZ, nz - z0);
+    const bool seam = x0 == 0 || y0 == 0 || z0 == 0 || x0 + TXe == nx || y0 + TYe == ny || z0 + TZe == nz;
+
+    if (tid == 0) mbar_init(bar, 1);
+    for (int row = warp; row < HY * HZ; row += TILE_WARPS) {
+        const int hz = row / HY, hy = row - hz * HY;
+        int gy = y0 - 1 + hy, gz = z0 - 1 + hz;
+        if (gy < 0) gy += ny; else if (gy >= ny) gy -= ny;
+        if (gz < 0) gz += nz; else if (gz >= nz) gz -= nz;
+        const bool rowok = hy <= TYe + 1 && hz <= TZe + 1;
+        for (int hx = lane; hx < HX; hx += 32) {
+            int c0 = 0, c1 = 0;
+            if (rowok && hx <= TXe + 1) {
+                int gx = x0 - 1 + hx;
+                if (gx < 0) gx += nx; else if (gx >= nx) gx -= nx;
+                int g = (gz * ny + gy) * nx + gx;
+                c0 = __ldg(&D.cell_start[g]);
+                c1 = __ldg(&D.cell_start[g + 1]);
+            }
+            gbeg[row * HX + hx] = c0;
+            lbeg[row * HX + hx] = c1 - c0;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int per = (HC + 31) / 32, h0 = lane * per, h1 = min(HC, h0 + per);
+        int s = 0;
+        for (int h = h0; h < h1; h++) s += lbeg[h];
+        int inc = s;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += t;
+        }
+        int run = inc - s;
+        for (int h = h0; h < h1; h++) { int c = lbeg[h]; lbeg[h] = run; run += c; }
+        int total = __shfl_sync(0xffffffffu, inc, 31);
+        if (lane == 0) {
+            lbeg[HC] = total;
+            misc[0] = total;
+            if (total <= HCAP) mbar_expect_tx(bar, (unsigned)total * 64u);
+        }
+    }
+    __syncthreads();
+    const bool staged = misc[0] <= HCAP;
+    if (staged) {
+        for (int row = tid; row < HY * HZ; row += TILE_NT) {
+            const int hz = row / HY, hy = row - hz * HY;
+            if (hy > TYe + 1 || hz > TZe + 1) continue;
+            int hrow = row * HX;
+            int hs = hrow;
+            for (int h = hrow + 1; h <= hrow + TXe + 2; h++) {
+                bool brk = (h == hrow + TXe + 2) || (gbeg[h] != gbeg[hs] + (lbeg[h] - lbeg[hs]));
+                if (brk) {
+                    int cnt = lbeg[h] - lbeg[hs];
+                    if (cnt > 0) bulk_g2s(rec + lbeg[hs], D.srec + gbeg[hs], (unsigned)cnt * 64u, bar);
+                    hs = h;
+                }
+            }
+        }
+    }
+    if (tid == TILE_NT - 1) {
+        int acc = 0, r = 0;
+        for (int hz = 1; hz <= TZe; hz++)
+            for (int hy = 1; hy <= TYe; hy++, r++) {
+                int h1 = (hz * HY + hy) * HX + 1;
+                rowoff[r] = acc;
+                rowbeg[r] = h1;                              // first own halo cell of the row
+                rowh[r] = h1 - 1;
+                acc += lbeg[h1 + TXe] - lbeg[h1];
+            }
+        rowoff[r] = acc;
+        misc[1] = acc;
+    }
+    if (staged) mbar_wait(bar, 0);
+    __syncthreads();
+    const int nown = misc[1];
+    const int nrow = TYe * TZe;
+    const int cap = D.surv_cap;
+    SlotSrc none = {};
+    for (int a = tid; a < nown; a += TILE_NT) {
+        int r = 0;
+        while (r + 1 < nrow && rowoff[r + 1] <= a) r++;
+        const int h1 = rowbeg[r];
+        const int pos_in_row = a - rowoff[r];
+        const int p_glob = gbeg[h1] + pos_in_row;             // own cells of a row are contiguous in the sorted arrays
+        const int ns = D.surv_n[p_glob];
+        double g = 0;
+        int i;
+        Slot cur;
+        PairBest pb;
+        int np = 0;
+        if (!staged || ns < 0) {
+            // halo too large for the staging buffer, or a survivor row that overflowed: the exact scan from HBM
+            i = D.sorted_atom[p_glob];
+            cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
+            if (D.thermostat_on) { i64 gi = g_base + (i - 1); g = D.gauss[gi >= D.g_cap ? gi - D.g_cap : gi]; }
+            double m2 = SD_INF;
+            cur = d_predict_atom<true, true, true>(D, none, i, cur, g, 0, &np, &m2, &pb, p_glob);
+            d_round0_store(D, dst, out, i, cur, pb, np);
+            continue;
+        }
+        const int p_self = lbeg[h1] + pos_in_row;
+        const SRec &rs = rec[p_self];
+        Self me = d_self_from_rec(D, rs);
+        i = me.i;
+        const int h_self = h1 + ((int)(rs.cxy & 0xffffu) - x0);
+        cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
+        const unsigned *row = D.surv + (size_t)p_glob * cap;
+        for (int s = 0; s < ns; s++) {
+            const unsigned w = __ldg(&row[s]);
+            const int k = (int)(w >> 27);
+            // DMD.c:118-120 offsets of scan slot k, 2 bits per slot (value + 1)
+            const unsigned long long PX = 0xa80894054a959ULL, PY = 0x2222160111a665ULL, PZ = 0x28096084059a95ULL;
+            const int dx = (int)((PX >> (2 * k)) & 3) - 1, dy = (int)((PY >> (2 * k)) & 3) - 1, dz = (int)((PZ >> (2 * k)) & 3) - 1;
+            const int hj = h_self + dx + dy * HX + dz * HXY;
+            const int q = lbeg[hj] + ((int)(w & 0x7ffffffu) - gbeg[hj]);
+            const SRec &rq = rec[q];
+            double shx = 0, shy = 0, shz = 0;
+            if (seam) {
+                const int cjx = (int)(rq.cxy & 0xffffu), cjy = (int)(rq.cxy >> 16), cjz = (int)rq.cz;
+                shx = d_shift1_sel(me.cx, cjx, D.cellnum[0], D.box[0]);
+                shy = d_shift1_sel(me.cy, cjy, D.cellnum[1], D.box[1]);
+                shz = d_shift1_sel(me.cz, cjz, D.cellnum[2], D.box[2]);
+            }
+            double t, pot;
+            int sub;
+            if (d_eval_pair(D, me, rq.atom, rq.type, rq.x, rq.y, rq.z, rq.vx, rq.vy, rq.vz, shx, shy, shz, 0, me.type, &t, &pot, &sub))
+                d_job_assign(D, cur, rq.atom, t, pot, sub, SDMD_EV_COLI);
+        }
+        pb.bp_time = cur.bp_time; pb.sp_time = cur.sp_time; pb.bp_j = cur.bp_j;
+        d_pcc_time(D, me, cur);
+        if (D.thermostat_on) {
+            i64 gi = g_base + (i - 1);
+            d_thermostat_time(D, cur, D.gauss[gi >= D.g_cap ? gi - D.g_cap : gi]);
+        }
+        d_round0_store(D, dst, out, i, cur, pb, D.surv_np[p_glob]);
+    }
+}
+
 static size_t tile_smem_bytes(int tx, int ty, int tz, int hcap) {
     size_t hc = (size_t)(tx + 2) * (ty + 2) * (tz + 2);
     return 16 + (size_t)hcap * 80 + sizeof(WarpPool) * TILE_WARPS + (2 * hc + 1 + 3 * (size_t)ty * tz + 1) * sizeof(int) + 16;
 }
 
 int sdmd_k2_tile_configure(DevP &P, int device) {
-    P.tile_tx = P.tile_ty = P.tile_tz = P.tile_hcap = P.tile_smem = 0;
+    P.tile_tx = P.tile_ty = P.tile_tz = P.tile_hcap = P.tile_smem = P.tile_mode = 0;
     // Opt-in (SDMD_K2_TILE=1) while it is slower than the two-kernel path: bit-exact on every GEL parity case and 158 MB of
     // DRAM traffic per launch at 10^6 atoms (two-kernel path: 391 MB), but 430 us against 284 us — the kernel is bound by
     // instruction issue at two blocks per SM (profiles/r2_k2_tile.md), not by memory.
     const char *env = getenv("SDMD_K2_TILE");
-    if (!(env && env[0] == '1')) return 1;
+    P.tile_mode = (env && (env[0] == '1' || env[0] == '2')) ? env[0] - '0' : 0;     // 1: fused tile kernel, 2: filter kernel + evaluation tile kernel
+    if (!P.tile_mode) return 1;
     if (!(P.gel_mode && !P.hydrogen_bond && !P.single_body && P.no_cons)) return 1;   // bonds / HB / walls / constrained atoms: two-kernel path
     if (P.n >= (1 << 27) || !P.sloc) return 1;
     const int nx = P.cellnum[0], ny = P.cellnum[1], nz = P.cellnum[2];
@@ -468,12 +633,14 @@ int sdmd_k2_tile_configure(DevP &P, int device) {
     double margin = 1e-4 * P.cut2 + 64.0 * 5.9604644775390625e-08 * L * sqrt(P.cut2);
     P.tile_cut2f = nextafterf((float)(P.cut2 + margin), INFINITY);
     if (cudaFuncSetAttribute(k_predict_all_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, P.tile_smem) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_predict_all_evaltile, cudaFuncAttributeMaxDynamicSharedMemorySize, P.tile_smem) != cudaSuccess) return -1;
     return 0;
 }
 
 int sdmd_k2_tile_launch(const DevP &P, SlotBuf dst, Round0Out out, long long g_base, cudaStream_t stream) {
     const int ntx = (P.cellnum[0] + P.tile_tx - 1) / P.tile_tx, nty = (P.cellnum[1] + P.tile_ty - 1) / P.tile_ty,
               ntz = (P.cellnum[2] + P.tile_tz - 1) / P.tile_tz;
-    k_predict_all_tile<<<ntx * nty * ntz, TILE_NT, P.tile_smem, stream>>>(P, dst, out, g_base);
+    if (P.tile_mode == 2) k_predict_all_evaltile<<<ntx * nty * ntz, TILE_NT, P.tile_smem, stream>>>(P, dst, out, g_base);
+    else k_predict_all_tile<<<ntx * nty * ntz, TILE_NT, P.tile_smem, stream>>>(P, dst, out, g_base);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
