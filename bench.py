@@ -388,12 +388,14 @@ def reference_pass_workers(n_axis, workers, passes, warm=1):
             (work / f"out{w}").mkdir()
             cmd = [str(REF_BENCH), str(warm + passes), "-"] + ([str(work / "state.bin")] if w == 0 else []) + \
                   ["--", "-f", gro, "-i", str(inp), "-o", str(work / f"out{w}")]
-            procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, cwd=work))
+            # stdout to a file: the reference prints megabytes while reading a 10^6-atom box, and a worker blocked on a full pipe
+            # would not run side by side with the others
+            procs.append(subprocess.Popen(cmd, stdout=open(work / f"stdout{w}.txt", "wb"), stderr=subprocess.DEVNULL, cwd=work))
         secs = []
-        for pr in procs:
-            out = pr.communicate()[0].decode(errors="replace")
-            if pr.returncode != 0:
+        for w, pr in enumerate(procs):
+            if pr.wait(timeout=1800) != 0:
                 raise RuntimeError("ref_bench_gel failed")
+            out = (work / f"stdout{w}.txt").read_bytes().decode(errors="replace")
             s = [float(ln.split()[3]) for ln in out.splitlines() if ln.startswith("pass ")]
             secs.append(s[warm:])
         # the reference keeps no evaluation counter: the port (pinned bit-exact to the reference at this size) counts the pair
@@ -688,14 +690,16 @@ def reference_remd_server(args, W):
             lines[1] = "Time               %g" % time_units
             (d / "input" / "parameter.txt").write_text("\n".join(lines) + "\n")
             (d / "out").mkdir()
+            # stdout to a FILE: the replicas wait for each other at every exchange, so one of them blocked on a full pipe
+            # (the reference prints its progress continuously) would stall all of them
             procs.append(subprocess.Popen([str(ref / "sDMD_ref"), "-i", str(d / "input"), "-f", "ala10.gro", "-o", str(d / "out"), "-REMD", "localhost",
                                            str(port), "%lf" % reduced_T(REMD_TEMPS_K[r % len(REMD_TEMPS_K)]), str(r + 1), str(int(rate)), str(r)],
-                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))
+                                          stdout=open(d / "stdout.txt", "w"), stderr=subprocess.DEVNULL))
             dirs.append(d)
         events = 0
-        for pr in procs:
-            out, _ = pr.communicate()
-            for line in out.replace("\r", "\n").splitlines():
+        for pr, d in zip(procs, dirs):
+            pr.wait(timeout=900)
+            for line in (d / "stdout.txt").read_text(errors="replace").replace("\r", "\n").splitlines():
                 if line.startswith("Calculate event times:"):
                     events += int(line.split(":")[1])
         dt = time.perf_counter() - t0
@@ -888,12 +892,15 @@ def reference_remd(args, dist):
             lines[2] = "T(reduced)         %g" % reduced_T(ladder[r % len(ladder)])
             p.write_text("\n".join(lines) + "\n")
             (d / "out").mkdir()
+            # stdout to a file: a process blocked on a full pipe (the reference prints its progress continuously) would not run
+            # side by side with the others
             procs.append(subprocess.Popen([str(ref), "-f", "ala10.gro", "-i", str(d / "input"), "-o", str(d / "out")],
-                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))
+                                          stdout=open(d / "stdout.txt", "w"), stderr=subprocess.DEVNULL))
             dirs.append(d)
         events = 0
-        for p in procs:
-            out, _ = p.communicate()
+        for p, d in zip(procs, dirs):
+            p.wait(timeout=1800)
+            out = (d / "stdout.txt").read_text(errors="replace")
             for line in out.replace("\r", "\n").splitlines():
                 if line.startswith("Calculate event times:"):
                     events += int(line.split(":")[1])
