@@ -15,6 +15,6 @@ for it in range(8):
     r.rng_seek(0)
     r.pbc_full(); r.cell_build(); r.predict_all(); r.cbt_build()
 r.synchronize()
-for k in ("cell_build", "predict_all", "predict_all_fixup", "fixup_resolve", "fixup_round1", "fixup_later", "cbt_build"):
+for k in ("cell_build", "k1_index", "k1_scan", "k1_scatter", "k1_place", "predict_all", "predict_all_fixup", "fixup_resolve", "fixup_rounds", "cbt_build"):
     v = r.kernel_stats(k)
     print(f"{k:28s} total {v[0]:9.4f} ms  n={v[1]:4d}  avg {v[0]/max(v[1],1)*1e3:9.2f} us")

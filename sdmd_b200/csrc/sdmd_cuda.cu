@@ -2018,19 +2018,25 @@ static int cell_build_impl(sdmd_ctx *c, int parts, bool bump) {
     Timer t(c, "cell_build");
     int n = c->n, m = c->P.ncell;
     // (the histogram is all zero here: zero-filled at create, cleared again by the scan of the previous build)
-    k_cell_index<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_count, c->cell_rank);
+    { Timer t2(c, "k1_index", 2); k_cell_index<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_count, c->cell_rank); }
     int nb = (m + SCAN_ITEMS - 1) / SCAN_ITEMS;
-    k_scan_local<<<nb, 512, 0, c->stream>>>(c->cell_count, c->d_cell_start, c->scan_tmp, m);
-    if (nb <= SCAN_DIRECT_BLOCKS) {
-        k_scan_finish<<<nb, 512, 0, c->stream>>>(c->P, c->d_cell_start, c->cell_count, c->scan_tmp, m, nb);
-        c->launches -= 1;
-    } else {
-        k_scan_blocks<<<1, 32, 0, c->stream>>>(c->scan_tmp, nb);
-        k_scan_add_cells<<<grid_for(m, 256), 256, 0, c->stream>>>(c->P, c->d_cell_start, c->cell_count, c->scan_tmp, m, nb);
+    {
+        Timer t2(c, "k1_scan", 2);
+        k_scan_local<<<nb, 512, 0, c->stream>>>(c->cell_count, c->d_cell_start, c->scan_tmp, m);
+        if (nb <= SCAN_DIRECT_BLOCKS) {
+            k_scan_finish<<<nb, 512, 0, c->stream>>>(c->P, c->d_cell_start, c->cell_count, c->scan_tmp, m, nb);
+            c->launches -= 1;
+        } else {
+            k_scan_blocks<<<1, 32, 0, c->stream>>>(c->scan_tmp, nb);
+            k_scan_add_cells<<<grid_for(m, 256), 256, 0, c->stream>>>(c->P, c->d_cell_start, c->cell_count, c->scan_tmp, m, nb);
+        }
     }
-    k_cell_scatter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_rank, c->d_cell_start, c->cell_tmp);
-    k_cell_place<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->d_cell_start, c->cell_tmp, c->d_sorted_atom, c->d_srec, c->d_sloc,
-                                                         c->d_scell, parts | (bump ? 4 : 0));
+    { Timer t2(c, "k1_scatter", 2); k_cell_scatter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_rank, c->d_cell_start, c->cell_tmp); }
+    {
+        Timer t2(c, "k1_place", 2);
+        k_cell_place<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->d_cell_start, c->cell_tmp, c->d_sorted_atom, c->d_srec, c->d_sloc,
+                                                             c->d_scell, parts | (bump ? 4 : 0));
+    }
     c->launches += 5;
     c->cells_fresh = true;
     CK(cudaGetLastError());
