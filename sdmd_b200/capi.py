@@ -46,7 +46,7 @@ class SdmdError(RuntimeError):
 
 
 CSRC = PKG / "csrc"
-SOURCES = ["sdmd_cuda.cu", "sdmd_k2_tile.cu"]            # one object per translation unit, rebuilt only when it (or a header) changed
+SOURCES = ["sdmd_cuda.cu", "sdmd_k2_tile.cu", "sdmd_k2_rows.cu"]            # one object per translation unit, rebuilt only when it (or a header) changed
 HEADERS = [CSRC / "sdmd_dev.cuh", CSRC / "sdmd_dev_body.cuh", CSRC / "sdmd_host.h", ROOT / "include" / "sdmd_cuda.h"]
 OBJ_DIR = ROOT / "build" / "obj"
 PTXAS_LOG = ROOT / "profiles" / "ptxas"                  # registers / spills / shared memory per kernel, tracked (one file per TU)

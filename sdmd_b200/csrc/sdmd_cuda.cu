@@ -486,6 +486,111 @@ __device__ __forceinline__ void d_requeue_round(const DevP &D, const SlotBuf &sr
     }
 }
 
+// The same round for bond-free systems whose survivor rows come from sdmd_k2_rows.cu (DevP::rows_mode): ONE WARP per queued atom.
+// Lane s takes survivor s: record gather, the partner's slot (is it a CheckDuplication source?), the ordinary evaluation — all
+// side by side; the results are parked in shared memory in visiting order (rank of the survivor word) and lane 0 replays the
+// scan over them exactly like the sequential code does (copy where the partner's slot points back and undercuts the running best,
+// TimePrediction.c:1101-1117, otherwise JobAssign).  A queued atom then costs ~6 dependent memory round trips instead of ~50.
+struct RqRes {
+    double t, pot, tj, dpot;
+    long long cntj;
+    int j, sub, dsub, flags;     // flags: 1 = the ordinary evaluation produced an event, 2 = the partner's slot points back at me
+};
+// G lanes per queued atom: 16 when the survivor rows hold 16 entries (twice the atoms in flight), else the whole warp.
+template <int G>
+__device__ __forceinline__ void d_requeue_round_rows(const DevP &D, const SlotBuf &src, const SlotBuf &dst, const int *queue, int total, int *npair,
+                                                     unsigned long long *pair_sum, i64 g_base, int gtid, int gsz, RqRes *res_warp) {
+    const int sub = gtid & (G - 1), gid = gtid / G, ng = gsz / G;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (0xffffu << (gtid & 16));
+    RqRes *res = res_warp + (G == 32 ? 0 : (gtid & 16));
+    for (int p = gid; p < total; p += ng) {
+        const int i = queue[p];
+        // everything addressed by the atom id alone travels together ...
+        const int ps = D.spos[i];
+        const double st_pot = D.ev_pot[i];
+        const int st_sub = D.ev_sub[i];
+        const i64 st_pc = D.ev_pcounter[i];
+        const int np_old = npair[i];
+        double g = 0;
+        if (D.thermostat_on) { i64 gi = g_base + i - 1; g = D.gauss[gi >= D.g_cap ? gi - D.g_cap : gi]; }
+        // ... then everything addressed by the sorted position
+        const int ns = D.surv_n[ps];
+        const int np0 = D.surv_np[ps];
+        const unsigned wraw = D.surv[(size_t)ps * D.surv_cap + sub];     // (G <= surv_cap: inside the row)
+        Self me = d_load_self_sorted(D, ps);
+        if (ns < 0) {   // overflowed row: the generic serial path
+            if (sub == 0) {
+                Slot cur = d_reset_slot(st_pot, st_sub, st_pc);
+                int np = 0;
+                cur = d_predict_atom<true, false, false>(D, as_src(src), i, cur, g, i, &np, nullptr, nullptr, ps);
+                dst.time[i] = cur.time; dst.pot[i] = cur.pot; dst.partner[i] = cur.partner; dst.pcounter[i] = cur.pcounter;
+                dst.type[i] = (uint8_t)cur.type; dst.sub[i] = (uint8_t)cur.sub;
+                npair[i] = np;
+                if (np != np_old) atomicAdd(pair_sum, (unsigned long long)(long long)(np - np_old));
+            }
+            __syncwarp(gmask);
+            continue;
+        }
+        const unsigned w = sub < ns ? wraw : 0xffffffffu;
+        int rank = 0;           // visiting order = ascending survivor word (all words of a row differ)
+        for (int s = 0; s < ns; s++) rank += __shfl_sync(gmask, w, s, G) < w;
+        if (sub < ns) {
+            const double2 *rp = reinterpret_cast<const double2 *>(&D.srec[w & 0x7ffffffu]);
+            const double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2v = __ldg(rp + 2);
+            const int2 ta = __ldg(reinterpret_cast<const int2 *>(rp + 3));
+            const int j = ta.y;
+            RqRes r;
+            r.flags = 0; r.j = j; r.t = 0; r.pot = 0; r.sub = 0;
+            // the partner's slot: all fields requested at once, used only when it points back at me
+            const int s_partner = src.partner[j];
+            const int s_type = src.type[j];
+            const i64 s_pc = src.pcounter[j];
+            r.tj = src.time[j]; r.dpot = src.pot[j]; r.dsub = src.sub[j];
+            r.cntj = D.ev_counter[j];
+            if (j < i && s_partner == i && s_type == SDMD_EV_COLI && s_pc == me.counter) r.flags = 2;
+            double shx = 0, shy = 0, shz = 0;
+            const bool seam = me.cx == 0 || me.cy == 0 || me.cz == 0 || me.cx == D.cellnum[0] - 1 || me.cy == D.cellnum[1] - 1 ||
+                              me.cz == D.cellnum[2] - 1;
+            if (seam) {
+                int ncx, ncy, ncz;
+                d_neighbor_cell(D, me.cx, me.cy, me.cz, (int)(w >> 27), &ncx, &ncy, &ncz);
+                shx = d_shift1(me.cx, ncx, D.cellnum[0], D.box[0]);
+                shy = d_shift1(me.cy, ncy, D.cellnum[1], D.box[1]);
+                shz = d_shift1(me.cz, ncz, D.cellnum[2], D.box[2]);
+            }
+            double t, pot;
+            int sb;
+            if (d_eval_pair(D, me, j, ta.x, r0.x, r0.y, r1.x, r1.y, r2v.x, r2v.y, shx, shy, shz, 0, me.type, &t, &pot, &sb)) {
+                r.flags |= 1; r.t = t; r.pot = pot; r.sub = sb;
+            }
+            res[rank] = r;
+        }
+        __syncwarp(gmask);
+        if (sub == 0) {
+            Slot cur = d_reset_slot(st_pot, st_sub, st_pc);
+            int np = np0;
+            for (int s = 0; s < ns; s++) {
+                const RqRes q = res[s];
+                if ((q.flags & 2) && cur.time > q.tj) {     // CheckDuplication fires: the slot is copied, the pair is not evaluated
+                    cur.partner = q.j; cur.pot = q.dpot; cur.sub = q.dsub; cur.time = q.tj; cur.type = SDMD_EV_COLI; cur.pcounter = q.cntj;
+                    np--;
+                    continue;
+                }
+                if ((q.flags & 1) && q.t > 0 && cur.time > q.t) {   // JobAssign, TimePrediction.c:1140-1158
+                    cur.pot = q.pot; cur.sub = q.sub; cur.time = q.t; cur.type = SDMD_EV_COLI; cur.partner = q.j; cur.pcounter = q.cntj;
+                }
+            }
+            d_pcc_time(D, me, cur);
+            if (D.thermostat_on) d_thermostat_time(D, cur, g);
+            dst.time[i] = cur.time; dst.pot[i] = cur.pot; dst.partner[i] = cur.partner; dst.pcounter[i] = cur.pcounter;
+            dst.type[i] = (uint8_t)cur.type; dst.sub[i] = (uint8_t)cur.sub;
+            npair[i] = np;
+            if (np != np_old) atomicAdd(pair_sum, (unsigned long long)(long long)(np - np_old));
+        }
+        __syncwarp(gmask);
+    }
+}
+
 // scan slot (0..26) of neighbour cell offset (dx,dy,dz), inverse of the DMD.c:118-120 tables
 static __constant__ int c_kinv[27] = {14, 11, 23, 12, 10, 17, 22, 16, 24, 13, 9, 19, 8, 0, 1, 20, 2, 6, 21, 15, 25, 18, 3, 5, 26, 4, 7};
 __device__ __forceinline__ int d_scan_slot(const DevP &D, int i, int a) {
@@ -607,6 +712,7 @@ __global__ void __launch_bounds__(128, K2_MINBLOCKS) k_predict_all_fixpoint(DevP
                                                                              unsigned long long *pair_sum, i64 g_base, i64 draws, int qcap) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    __shared__ RqRes rq_res[4][32];
     int slot = 0, rounds = 0, first = -1;
     bool overflow = false;
     for (;;) {
@@ -614,10 +720,20 @@ __global__ void __launch_bounds__(128, K2_MINBLOCKS) k_predict_all_fixpoint(DevP
         if (first < 0) first = nq;
         if (nq == 0) break;
         if (nq > qcap) { overflow = true; break; }
-        d_requeue_round(Dq, B, C, qa, nq, npair, pair_sum, g_base, gtid, gsz);
+        const long long c0 = clock64();
+        if (D.rows_mode && D.surv_cap == 16) d_requeue_round_rows<16>(Dq, B, C, qa, nq, npair, pair_sum, g_base, gtid, gsz, rq_res[threadIdx.x >> 5]);
+        else if (D.rows_mode) d_requeue_round_rows<32>(Dq, B, C, qa, nq, npair, pair_sum, g_base, gtid, gsz, rq_res[threadIdx.x >> 5]);
+        else d_requeue_round(Dq, B, C, qa, nq, npair, pair_sum, g_base, gtid, gsz);
+        const long long c1 = clock64();
         grid.sync();
+        const long long c2 = clock64();
         d_requeue_commit(B, C, qa, nq, qb, nqueue + slot + 1, gtid, gsz);
+        const long long c3 = clock64();
         grid.sync();
+        if (gtid == 0) {    // block 0's view of a round: evaluate, barrier, commit, barrier (Replica.phase_cycles: x10/x11 and the loop's slots 8/9 are reused)
+            Ctl *c = D.ctl;
+            c->phase_cycles[8] += c1 - c0; c->phase_cycles[9] += c2 - c1; c->phase_cycles[10] += c3 - c2; c->phase_cycles[11] += clock64() - c3;
+        }
         int *t = qa; qa = qb; qb = t;
         slot++; rounds++;
         if (slot + 1 >= FIX_NQ) {   // very long dependency chain: recycle the slots, keep the last queue
@@ -1706,6 +1822,16 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     }
     P.cell_start = c->d_cell_start; P.sorted_atom = c->d_sorted_atom;
     P.srec = c->d_srec;
+    P.cm_empty = (ncm == 0);
+    P.uni_table = -1;
+    if (!P.hydrogen_bond) {     // (atom types only change through hydrogen bonds)
+        bool same = true;
+        for (int i = 2; i <= n && same; i++) same = v->type[i] == v->type[1];
+        int idx = same ? v->coll_index[v->type[1] * SD_NT + v->type[1]] : -1;
+        if (idx >= 0 && v->tables[idx].nstep <= 2 && v->tables[idx].dmax2 == 0 && v->tables[idx].dmin2 != 0) P.uni_table = idx;
+    }
+    P.rows_mode = 0;
+    if (P.surv) sdmd_k2_rows_configure(P);   // bond-free systems: row-batched filter + cp.async evaluation (sdmd_k2_rows.cu)
     std::vector<int> leaf_atom;
     cbt_leaf_permutation(n, leaf_atom);
     TRY(dupload(c, &c->d_leaf_atom, leaf_atom.data(), (size_t)n));
@@ -2064,7 +2190,12 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
     {
         Timer t(c, "predict_all");
         const bool tile = c->P.tile_tx > 0;
-        if (c->P.surv && c->P.tile_mode != 1) {
+        if (c->P.rows_mode) {
+            Timer tf(c, "k2_filter", 2);
+            if (sdmd_k2_rows_filter_launch(c->P, c->stream)) return set_err(SDMD_ERR_CUDA, "k_r0_filter_rows", cudaGetLastError());
+            c->launches++;
+        } else if (c->P.surv && c->P.tile_mode != 1) {
+            Timer tf(c, "k2_filter", 2);
             k_predict_all_filter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P);
             c->launches++;
         }
@@ -2076,7 +2207,11 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
         // systems without bonds, hydrogen bonds and single-body sources (the GEL boxes) run the instance with those
         // predictors compiled out
         const bool lean = K2_LEAN && c->P.gel_mode && !c->P.hydrogen_bond && !c->P.single_body;
-        if (tile) {
+        Timer te(c, "k2_eval", 2);
+        if (c->P.rows_mode) {
+            Round0Out ro = {c->npair, c->second, c->bp_time, c->bp_j, c->pcount, c->pwho};
+            if (sdmd_k2_rows_eval_launch(c->P, B, ro, g_base, c->stream)) return set_err(SDMD_ERR_CUDA, "k_r0_eval_rows", cudaGetLastError());
+        } else if (tile) {
             Round0Out ro = {c->npair, c->second, c->bp_time, c->bp_j, c->pcount, c->pwho};
             if (sdmd_k2_tile_launch(c->P, B, ro, g_base, c->stream)) return set_err(SDMD_ERR_CUDA, "k_predict_all_tile", cudaGetLastError());
         } else if (lean)

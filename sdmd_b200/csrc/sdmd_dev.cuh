@@ -179,6 +179,10 @@ struct DevP {
     const double *lz_x, *lz_y, *lz_z, *lz_t;
     double lz_dt;
     int lz_on, lz_a, lz_b;
+    // round 0 by sdmd_k2_rows.cu: survivor rows are written in row order, not in visiting order (re-evaluation rounds sort them)
+    int rows_mode;
+    int cm_empty;            // the connection map has no entry at all (no bond, no constraint)
+    int uni_table;           // >= 0: every atom has the same type; its collision table (index) has <= 2 steps and no dmax2.  Else -1
 };
 
 #define SDMD_LZ 0

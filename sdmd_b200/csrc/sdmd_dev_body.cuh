@@ -616,6 +616,16 @@ __device__ inline void d_collision_time_from_list(const DevP &D, const SlotSrc &
     int surv_p[R0_MAXSURV];
     unsigned char surv_k[R0_MAXSURV];
     int ndup = 0;
+    unsigned wl[R0_SURV_CAP];
+    if (D.rows_mode) {   // the row filter (sdmd_k2_rows.cu) writes survivors in row order: bring them into visiting order (ascending word)
+        for (int s = 0; s < ns; s++) {
+            unsigned v = in[s];
+            int k = s;
+            while (k > 0 && wl[k - 1] > v) { wl[k] = wl[k - 1]; k--; }
+            wl[k] = v;
+        }
+        in = wl;
+    }
     for (int s0 = 0; s0 < ns; s0 += R0_MAXSURV) {
         int m = ns - s0 < R0_MAXSURV ? ns - s0 : R0_MAXSURV;
         for (int s = 0; s < m; s++) {

@@ -16,3 +16,10 @@ struct Round0Out {
 // usable for this system, 1 when it is not (the two-kernel path stays), < 0 on a CUDA error.
 int sdmd_k2_tile_configure(DevP &P, int device);
 int sdmd_k2_tile_launch(const DevP &P, SlotBuf dst, Round0Out out, long long g_base, cudaStream_t stream);
+
+// sdmd_k2_rows.cu: round 0 for bond-free systems as a row-batched filter (predicated independent loads, survivors in row order)
+// plus an evaluation kernel that gathers survivor records by cp.async and folds them order-independently.
+// configure: 0 when usable for this system (sets DevP::rows_mode), 1 when not (the kernels of sdmd_cuda.cu stay).
+int sdmd_k2_rows_configure(DevP &P);
+int sdmd_k2_rows_filter_launch(const DevP &P, cudaStream_t stream);
+int sdmd_k2_rows_eval_launch(const DevP &P, SlotBuf dst, Round0Out out, long long g_base, cudaStream_t stream);
