@@ -292,20 +292,22 @@ def cuda_pass(args, dist):
     per_launch_ms = pa_ms / max(pa_n, 1)
     alg_bytes = 88.0 * n  # 56 B own state read + 32 B slot written per atom
     achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_predict_all_filter + k_predict_all_round (round 0 of the full-system Predict)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    rows = os.environ.get("SDMD_K2_ROWS", "1") != "0" and os.environ.get("SDMD_K2_TILE", "") not in ("1", "2")
+    roof = {"bound": "hbm", "kernel": ("k_r0_filter_rows + k_r0_eval_rows" if rows else "k_predict_all_filter + k_predict_all_round") + " (round 0 of the full-system Predict)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
             "kernel_ms": per_launch_ms, "kernel_share_of_step": pa_ms / ms if ms else None,
             "pairs_per_s_kernel": (pairs / max(pa_n, 1)) / (per_launch_ms * 1e-3),
-            "note": "HBM fraction as north_star asks; the stage is latency bound, not HBM bound: ~41 candidate distance tests "
-                    "(single-precision superset filter) + ~6 double-precision root solves per atom behind dependent gathers; "
-                    "ncu: issue slots 56 % / 46 % busy, FP64 pipe 17 % in the evaluation kernel, see profiles/"}
+            "note": "HBM fraction as north_star asks; the stage is not HBM bound: ~41 candidate distance tests (single-precision "
+                    "superset filter, instruction-issue bound: issue slots 69 % busy) + ~6 double-precision root solves per atom "
+                    "(evaluation kernel: issue 44 %, FP64 pipe 23 %, warps wait on their first loads); see profiles/r2_summary.md"}
     # dram__bytes_read+write per launch of the two kernels from the committed `ncu --set full` capture, if recorded
     tf = ROOT / "profiles" / "ncu_traffic.json"
     if tf.exists():
         try:
             t = json.loads(tf.read_text())
             tile = os.environ.get("SDMD_K2_TILE", "") == "1"
-            names = ["k_predict_all_tile"] if tile else ["k_predict_all_filter", "k_predict_all_round<1>"]
+            names = ["k_predict_all_tile"] if tile else (["k_r0_filter_rows", "k_r0_eval_rows<1>"] if rows else ["k_predict_all_filter", "k_predict_all_round<1>"])
             if int(t.get("natom", 0)) == n and all(k in t["kernels"] for k in names):
                 roof["traffic"] = sum(float(t["kernels"][k]["dram_bytes"]) for k in names)
                 roof["traffic_source"] = t.get("source", "profiles/ncu_traffic.json")

@@ -45,9 +45,28 @@
 #define RE_NB 4           // survivor records gathered per round trip (RE_NB * 64 B of shared memory per thread)
 #endif
 
+// Streaming L2 prefetch.  Both kernels walk the cell-sorted arrays front to back, one atom per thread, and every warp starts
+// with a chain of first-touch DRAM loads (ncu: ~45 % of the evaluation kernel's stall samples sit on its first three loads, with
+// only ~18 warps per SM to hide them).  Each thread therefore asks L2 for the lines the thread PF atoms further on will open with;
+// PF is about twice the atoms in flight on the whole GPU.  The neighbour records an atom gathers lie within one cell plane
+// (~n^(2/3) positions) of it, so the same stream makes those gathers L2 hits.
+#ifndef RF_PF
+#define RF_PF 0
+#endif
+#ifndef RE_PF
+#define RE_PF 0
+#endif
+__device__ __forceinline__ void r0_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __global__ void __launch_bounds__(RF_NT, RF_MINB) k_r0_filter_rows(DevP D) {
     const int p_self = blockIdx.x * RF_NT + threadIdx.x;
     if (p_self >= D.n) return;
+#if RF_PF
+    if (p_self + RF_PF < D.n) {
+        r0_prefetch_l2(&D.sloc[p_self + RF_PF]);
+        if ((threadIdx.x & 7) == 0) r0_prefetch_l2(&D.scell[p_self + RF_PF]);
+    }
+#endif
     const float4 me = __ldg(&D.sloc[p_self]);
     const int c = __ldg(&D.scell[p_self]);
     const int nx = D.cellnum[0], ny = D.cellnum[1], nz = D.cellnum[2], nxy = nx * ny;
@@ -166,6 +185,15 @@ __global__ void __launch_bounds__(RE_NT, RE_MINB) k_r0_eval_rows(DevP D, SlotBuf
     const int tid = threadIdx.x, lane = tid & 31;
     const int p = blockIdx.x * RE_NT + tid;
     const bool live = p < D.n;                       // (every lane of a warp takes part in the gathers)
+#if RE_PF
+    if (p + RE_PF < D.n) {
+        const char *rec = reinterpret_cast<const char *>(&D.srec[p + RE_PF]);
+        r0_prefetch_l2(rec); r0_prefetch_l2(rec + 32);
+        const char *rw = reinterpret_cast<const char *>(D.surv + (size_t)(p + RE_PF) * D.surv_cap);
+        r0_prefetch_l2(rw); r0_prefetch_l2(rw + 32);
+        if ((tid & 7) == 0) { r0_prefetch_l2(&D.surv_n[p + RE_PF]); r0_prefetch_l2(&D.surv_np[p + RE_PF]); }
+    }
+#endif
     const int pc = live ? p : D.n - 1;
     const uint4 *row = reinterpret_cast<const uint4 *>(D.surv + (size_t)pc * D.surv_cap);
     const int ns_raw = __ldg(&D.surv_n[pc]);
@@ -177,10 +205,6 @@ __global__ void __launch_bounds__(RE_NT, RE_MINB) k_r0_eval_rows(DevP D, SlotBuf
 #else
     const int nmax = ns;
 #endif
-    if (nmax > 0) {   // first gather on its way before anything else is touched
-        const unsigned ww[4] = {0 < ns ? w4.x : R0_NOWORD, 1 < ns ? w4.y : R0_NOWORD, 2 < ns ? w4.z : R0_NOWORD, 3 < ns ? w4.w : R0_NOWORD};
-        r0_gather_batch(D, ww, sbase, lane);
-    }
     Self me;
     {
         const double2 *rp = reinterpret_cast<const double2 *>(&D.srec[pc]);
@@ -191,8 +215,20 @@ __global__ void __launch_bounds__(RE_NT, RE_MINB) k_r0_eval_rows(DevP D, SlotBuf
         me.cx = (int)((unsigned)q.z & 0xffffu); me.cy = (int)((unsigned)q.z >> 16); me.cz = q.w;
         me.counter = 0; me.npair = 0; me.type = q.x; me.cm0 = 0; me.cm1 = 0;
     }
-    const int i = me.i;
+    double tb_dmin2 = 0, tb_d0 = 0, tb_d1 = 0, tb_e0 = 0, tb_e1 = 0;
+    int tb_ns = 0;
+    if (FAST) {
+        const sdmd_step_table *tb = &D.tables[D.uni_table];
+        tb_dmin2 = __ldg(&tb->dmin2); tb_ns = __ldg(&tb->nstep);
+        tb_d0 = __ldg(&tb->d2[0]); tb_e0 = __ldg(&tb->e[0]); tb_d1 = __ldg(&tb->d2[1]); tb_e1 = __ldg(&tb->e[1]);
+    }
     const int np = __ldg(&D.surv_np[pc]);
+    // every load above is independent of the others and in flight by now; the first gather needs the row's words
+    if (nmax > 0) {
+        const unsigned ww[4] = {0 < ns ? w4.x : R0_NOWORD, 1 < ns ? w4.y : R0_NOWORD, 2 < ns ? w4.z : R0_NOWORD, 3 < ns ? w4.w : R0_NOWORD};
+        r0_gather_batch(D, ww, sbase, lane);
+    }
+    const int i = me.i;
     double g = 0;
     if (D.thermostat_on) { i64 gi = g_base + i - 1; g = __ldg(&D.gauss[gi >= D.g_cap ? gi - D.g_cap : gi]); }
     // partnerCounter survives ResetTarget (ToolFunctions.c:504-514): the stale value stays in the slot of a partner-less winner.
@@ -201,13 +237,6 @@ __global__ void __launch_bounds__(RE_NT, RE_MINB) k_r0_eval_rows(DevP D, SlotBuf
     i64 pc1 = 0;
     const bool seam = me.cx == 0 || me.cy == 0 || me.cz == 0 || me.cx == D.cellnum[0] - 1 || me.cy == D.cellnum[1] - 1 ||
                       me.cz == D.cellnum[2] - 1;
-    double tb_dmin2 = 0, tb_d0 = 0, tb_d1 = 0, tb_e0 = 0, tb_e1 = 0;
-    int tb_ns = 0;
-    if (FAST) {
-        const sdmd_step_table *tb = &D.tables[D.uni_table];
-        tb_dmin2 = __ldg(&tb->dmin2); tb_ns = __ldg(&tb->nstep);
-        tb_d0 = __ldg(&tb->d2[0]); tb_e0 = __ldg(&tb->e[0]); tb_d1 = __ldg(&tb->d2[1]); tb_e1 = __ldg(&tb->e[1]);
-    }
     // fold state: lexicographic minimum of (time, visiting rank) and the second smallest time
     double t1 = SD_INF, m2 = SD_INF, pot1 = 0;
     unsigned w1 = 0xffffffffu;
