@@ -288,7 +288,8 @@ int  sdmd_cuda_pbc_full(sdmd_ctx *ctx);
 /* LinkList("full") Events.c:121-156 — GPU counting sort; also produces the cell-sorted SoA tiles */
 int  sdmd_cuda_cell_build(sdmd_ctx *ctx);
 /* Prepare()'s Predict over all atoms, SGThread.c:47-52 → Predict SGThread.c:158-211.
- * Consumes natom gaussians when the thermostat is on. */
+ * Consumes one gaussian per non-constrained atom when the thermostat is on (constrained atoms skip ThermostatTime,
+ * SGThread.c:165-168). */
 int  sdmd_cuda_predict_all(sdmd_ctx *ctx);
 /* Predict(renewList) SGThread.c:158-211; renew_list follows the reference layout:
  * [0] = count, [1..count] = atom ids, 0-terminated */

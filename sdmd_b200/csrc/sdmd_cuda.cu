@@ -51,6 +51,9 @@ struct sdmd_ctx {
     double *second = nullptr, *bp_time = nullptr;
     int *bp_j = nullptr;
     int *cell_of = nullptr, *cell_count = nullptr, *cell_rank = nullptr, *cell_tmp = nullptr, *scan_tmp = nullptr;
+    int n_draws = 0;
+    unsigned long long *scan_state = nullptr;      // single-pass scan of the cell histogram: one word per block of 2048 cells
+    unsigned *scan_ticket = nullptr, scan_ticket_base = 0, scan_epoch = 0;
     int *d_cell_start = nullptr, *d_sorted_atom = nullptr;
     SRec *d_srec = nullptr;
     float4 *d_sloc = nullptr;
@@ -286,6 +289,64 @@ __global__ void k_scan_add_cells(DevP D, int *out, int *count, const int *block_
     if (t == 0) out[m] = block_sum[nb];
 }
 
+// The same scan in ONE launch: a block scans its 2048 counts, publishes its total and sums the totals of the blocks in front of
+// it.  `state[b]` = epoch << 32 | total; the epoch changes with every build, so the array never has to be cleared.  (A
+// decoupled look-back over running prefixes was measured first: 16 us, the same as the two launches — ten dependent hops.)  Blocks take their number from a ticket counter (a block only ever waits for
+// blocks that started before it).  Also does what k_scan_finish does: cell occupancy, heads of the empty cells, histogram
+// cleared for the next build.  Two dependent launches (16 us at 667 k cells) become one (~6 us).
+__global__ void __launch_bounds__(512) k_scan_cells(DevP D, int *count, int *out, unsigned long long *state, unsigned *ticket, unsigned ticket_base,
+                                                    unsigned epoch, int m, int nb) {
+    __shared__ int s_b, s_prefix;
+    if (threadIdx.x == 0) s_b = (int)(atomicAdd(ticket, 1u) - ticket_base);
+    __syncthreads();
+    const int b = s_b;
+    const int t0 = b * SCAN_ITEMS + threadIdx.x * 4;
+    int v[4];
+    if (t0 + 3 < m) {
+        const int4 q = *reinterpret_cast<const int4 *>(count + t0);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[q] = (t0 + q < m) ? count[t0 + q] : 0;
+    }
+    int total;
+    int ex = d_block_scan_excl(v[0] + v[1] + v[2] + v[3], &total);
+    // publish my total, then add up the totals of all blocks in front of me (one word per thread and 512 blocks): no block waits
+    // for another block's PREFIX, so there is no chain of hops — every block is one round trip behind the slowest local scan
+    volatile unsigned long long *st = state;
+    if (threadIdx.x == 0) st[b] = ((unsigned long long)epoch << 32) | (unsigned)total;
+    int part = 0;
+    for (int q = threadIdx.x; q < b; q += 512) {
+        unsigned long long w;
+        do { w = st[q]; } while ((unsigned)(w >> 32) != epoch);
+        part += (int)(unsigned)(w & 0xffffffffu);
+    }
+    __shared__ int red[16];
+#pragma unroll
+    for (int off = 16; off; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int sum = 0;
+        for (int q = 0; q < 16; q++) sum += red[q];
+        s_prefix = sum;
+        if (b == nb - 1) out[m] = sum + total;
+    }
+    __syncthreads();
+    ex += s_prefix;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int t = t0 + q;
+        if (t < m) {
+            out[t] = ex;
+            ex += v[q];
+            count[t] = 0;
+            D.cell_cnt[t] = v[q];
+            if (v[q] == 0) D.celllist[D.n + t + 1] = 0;
+        }
+    }
+}
+
 // atoms of a cell side by side, in arrival order
 __global__ void k_cell_scatter(DevP D, const int *cell_of, const int *arrival, const int *cell_start, int *unordered) {
     int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
@@ -318,7 +379,9 @@ __global__ void k_cell_place(DevP D, const int *cell_of, const int *cell_start, 
     if (rank == 0) D.celllist[D.n + c + 1] = i;
     double x = D.x[i], y = D.y[i], z = D.z[i];
     int t = D.type[i];
-    int cx = D.cell_idx[3 * i], cy = D.cell_idx[3 * i + 1], cz = D.cell_idx[3 * i + 2];
+    // cell index triple from the cell id (three loads fewer per atom; the stage is bound by its load / store instruction count)
+    const int nxy = D.cellnum[0] * D.cellnum[1];
+    const int cz = c / nxy, crem = c - cz * nxy, cy = crem / D.cellnum[0], cx = crem - cy * D.cellnum[0];
     double2 *rp = reinterpret_cast<double2 *>(&srec[p]);
     // cell-local single-precision copy for the neighbour filter (see d_r0_filter)
     sloc[p] = make_float4((float)(x - cx * D.cellsize[0]), (float)(y - cy * D.cellsize[1]), (float)(z - cz * D.cellsize[2]), __int_as_float(i));
@@ -496,13 +559,17 @@ struct RqRes {
     long long cntj;
     int j, sub, dsub, flags;     // flags: 1 = the ordinary evaluation produced an event, 2 = the partner's slot points back at me
 };
-// G lanes per queued atom: 16 when the survivor rows hold 16 entries (twice the atoms in flight), else the whole warp.
+// G lanes per queued atom, CAP = 2 G entries per survivor row (8 lanes for 16-entry rows, 16 for 32-entry rows): a queued atom is
+// one chain of dependent round trips, so what counts is how many chains are in flight.
 template <int G>
 __device__ __forceinline__ void d_requeue_round_rows(const DevP &D, const SlotBuf &src, const SlotBuf &dst, const int *queue, int total, int *npair,
-                                                     unsigned long long *pair_sum, i64 g_base, int gtid, int gsz, RqRes *res_warp) {
+                                                     unsigned long long *pair_sum, i64 g_base, int gtid, int gsz, RqRes *res_warp, unsigned *w_warp) {
+    constexpr int CAP = 2 * G;
     const int sub = gtid & (G - 1), gid = gtid / G, ng = gsz / G;
-    const unsigned gmask = G == 32 ? 0xffffffffu : (0xffffu << (gtid & 16));
-    RqRes *res = res_warp + (G == 32 ? 0 : (gtid & 16));
+    const int goff = (gtid & 31) & ~(G - 1);                   // first lane of my group inside the warp
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << goff;
+    RqRes *res = res_warp + (goff / G) * CAP;
+    unsigned *wl = w_warp + (goff / G) * CAP;
     for (int p = gid; p < total; p += ng) {
         const int i = queue[p];
         // everything addressed by the atom id alone travels together ...
@@ -516,7 +583,8 @@ __device__ __forceinline__ void d_requeue_round_rows(const DevP &D, const SlotBu
         // ... then everything addressed by the sorted position
         const int ns = D.surv_n[ps];
         const int np0 = D.surv_np[ps];
-        const unsigned wraw = D.surv[(size_t)ps * D.surv_cap + sub];     // (G <= surv_cap: inside the row)
+        const unsigned *row = D.surv + (size_t)ps * D.surv_cap;
+        const unsigned wraw0 = row[sub], wraw1 = row[sub + G];     // (CAP == surv_cap: inside the row)
         Self me = d_load_self_sorted(D, ps);
         if (ns < 0) {   // overflowed row: the generic serial path
             if (sub == 0) {
@@ -531,10 +599,15 @@ __device__ __forceinline__ void d_requeue_round_rows(const DevP &D, const SlotBu
             __syncwarp(gmask);
             continue;
         }
-        const unsigned w = sub < ns ? wraw : 0xffffffffu;
-        int rank = 0;           // visiting order = ascending survivor word (all words of a row differ)
-        for (int s = 0; s < ns; s++) rank += __shfl_sync(gmask, w, s, G) < w;
-        if (sub < ns) {
+        wl[sub] = sub < ns ? wraw0 : 0xffffffffu;
+        wl[sub + G] = sub + G < ns ? wraw1 : 0xffffffffu;
+        __syncwarp(gmask);
+        const bool seam = me.cx == 0 || me.cy == 0 || me.cz == 0 || me.cx == D.cellnum[0] - 1 || me.cy == D.cellnum[1] - 1 ||
+                          me.cz == D.cellnum[2] - 1;
+        for (int s = sub; s < ns; s += G) {
+            const unsigned w = s == sub ? wraw0 : wraw1;
+            int rank = 0;           // visiting order = ascending survivor word (all words of a row differ)
+            for (int k = 0; k < ns; k++) rank += wl[k] < w;
             const double2 *rp = reinterpret_cast<const double2 *>(&D.srec[w & 0x7ffffffu]);
             const double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2v = __ldg(rp + 2);
             const int2 ta = __ldg(reinterpret_cast<const int2 *>(rp + 3));
@@ -549,8 +622,6 @@ __device__ __forceinline__ void d_requeue_round_rows(const DevP &D, const SlotBu
             r.cntj = D.ev_counter[j];
             if (j < i && s_partner == i && s_type == SDMD_EV_COLI && s_pc == me.counter) r.flags = 2;
             double shx = 0, shy = 0, shz = 0;
-            const bool seam = me.cx == 0 || me.cy == 0 || me.cz == 0 || me.cx == D.cellnum[0] - 1 || me.cy == D.cellnum[1] - 1 ||
-                              me.cz == D.cellnum[2] - 1;
             if (seam) {
                 int ncx, ncy, ncz;
                 d_neighbor_cell(D, me.cx, me.cy, me.cz, (int)(w >> 27), &ncx, &ncy, &ncz);
@@ -712,7 +783,8 @@ __global__ void __launch_bounds__(128, K2_MINBLOCKS) k_predict_all_fixpoint(DevP
                                                                              unsigned long long *pair_sum, i64 g_base, i64 draws, int qcap) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    __shared__ RqRes rq_res[4][32];
+    __shared__ RqRes rq_res[4][64];
+    __shared__ unsigned rq_w[4][64];
     int slot = 0, rounds = 0, first = -1;
     bool overflow = false;
     for (;;) {
@@ -721,8 +793,8 @@ __global__ void __launch_bounds__(128, K2_MINBLOCKS) k_predict_all_fixpoint(DevP
         if (nq == 0) break;
         if (nq > qcap) { overflow = true; break; }
         const long long c0 = clock64();
-        if (D.rows_mode && D.surv_cap == 16) d_requeue_round_rows<16>(Dq, B, C, qa, nq, npair, pair_sum, g_base, gtid, gsz, rq_res[threadIdx.x >> 5]);
-        else if (D.rows_mode) d_requeue_round_rows<32>(Dq, B, C, qa, nq, npair, pair_sum, g_base, gtid, gsz, rq_res[threadIdx.x >> 5]);
+        if (D.rows_mode && D.surv_cap == 16) d_requeue_round_rows<8>(Dq, B, C, qa, nq, npair, pair_sum, g_base, gtid, gsz, rq_res[threadIdx.x >> 5], rq_w[threadIdx.x >> 5]);
+        else if (D.rows_mode && D.surv_cap == 32) d_requeue_round_rows<16>(Dq, B, C, qa, nq, npair, pair_sum, g_base, gtid, gsz, rq_res[threadIdx.x >> 5], rq_w[threadIdx.x >> 5]);
         else d_requeue_round(Dq, B, C, qa, nq, npair, pair_sum, g_base, gtid, gsz);
         const long long c1 = clock64();
         grid.sync();
@@ -1777,6 +1849,7 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     int r = 0;
     for (int i = 1; i <= n; i++) { rank[i] = r; if (!v->is_cons[i]) r++; }
     P.no_cons = (r == n);   // nobody is constrained: draw index of atom i is simply i - 1
+    c->n_draws = r;         // gaussians a full-system pass consumes: constrained atoms skip ThermostatTime (SGThread.c:165-168)
     TRY(dupload(c, (int **)&P.ther_rank, rank.data(), n1));
 
     // scratch
@@ -1790,6 +1863,7 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     TRY(dalloc(c, &c->cell_of, n1)); TRY(dalloc(c, &c->cell_count, (size_t)P.ncell + 1));
     TRY(dalloc(c, &c->cell_rank, n1)); TRY(dalloc(c, &c->cell_tmp, n1));
     TRY(dalloc(c, &c->scan_tmp, (size_t)P.ncell / SCAN_ITEMS + 4));
+    TRY(dalloc(c, &c->scan_state, (size_t)P.ncell / SCAN_ITEMS + 4)); TRY(dalloc(c, &c->scan_ticket, 4));
     TRY(dalloc(c, &c->d_cell_start, (size_t)P.ncell + 1)); TRY(dalloc(c, &c->d_sorted_atom, n1));
     TRY(dalloc(c, &c->d_srec, n1)); TRY(dalloc(c, &c->d_sloc, n1)); TRY(dalloc(c, &c->d_scell, n1));
     {
@@ -2148,14 +2222,10 @@ static int cell_build_impl(sdmd_ctx *c, int parts, bool bump) {
     int nb = (m + SCAN_ITEMS - 1) / SCAN_ITEMS;
     {
         Timer t2(c, "k1_scan", 2);
-        k_scan_local<<<nb, 512, 0, c->stream>>>(c->cell_count, c->d_cell_start, c->scan_tmp, m);
-        if (nb <= SCAN_DIRECT_BLOCKS) {
-            k_scan_finish<<<nb, 512, 0, c->stream>>>(c->P, c->d_cell_start, c->cell_count, c->scan_tmp, m, nb);
-            c->launches -= 1;
-        } else {
-            k_scan_blocks<<<1, 32, 0, c->stream>>>(c->scan_tmp, nb);
-            k_scan_add_cells<<<grid_for(m, 256), 256, 0, c->stream>>>(c->P, c->d_cell_start, c->cell_count, c->scan_tmp, m, nb);
-        }
+        c->scan_epoch = (c->scan_epoch + 1) & 0x3fffffffu;
+        if (c->scan_epoch == 0) c->scan_epoch = 1;      // (0 is what a never-written state word carries)
+        k_scan_cells<<<nb, 512, 0, c->stream>>>(c->P, c->cell_count, c->d_cell_start, c->scan_state, c->scan_ticket, c->scan_ticket_base, c->scan_epoch, m, nb);
+        c->scan_ticket_base += (unsigned)nb;
     }
     { Timer t2(c, "k1_scatter", 2); k_cell_scatter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_rank, c->d_cell_start, c->cell_tmp); }
     {
@@ -2163,7 +2233,7 @@ static int cell_build_impl(sdmd_ctx *c, int parts, bool bump) {
         k_cell_place<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->d_cell_start, c->cell_tmp, c->d_sorted_atom, c->d_srec, c->d_sloc,
                                                              c->d_scell, parts | (bump ? 4 : 0));
     }
-    c->launches += 5;
+    c->launches += 4;      // index, scan, scatter, place
     c->cells_fresh = true;
     CK(cudaGetLastError());
     return 0;
@@ -2178,7 +2248,7 @@ int sdmd_cuda_cell_build(sdmd_ctx *c) {
 static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
     int n = c->n;
     i64 need = 0;
-    if (c->P.thermostat_on) need = n;  // one draw per predicted atom, TimePrediction.c:591
+    if (c->P.thermostat_on) need = c->n_draws;  // one draw per predicted, non-constrained atom (SGThread.c:165-168, TimePrediction.c:591)
     if (c->g_filled - c->h_ctl->g_pos < need) return set_err(SDMD_ERR_BAD_ARG, "predict_all: not enough gaussians fed");
     i64 g_pos0 = c->h_ctl->g_pos;
     i64 g_base = g_pos0 % c->P.g_cap;       // ring offset of the first draw

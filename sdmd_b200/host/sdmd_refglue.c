@@ -135,6 +135,9 @@ int sdmd_glue_flatten(struct sdmd_host_view *v) {
     v->cutoffr = cutoffr;
     v->thermoF = thermoF;
     v->thermostat_on = strcmp(thermostatType, "no") != 0;
+    /* ThermostatEvent redraws velocities only for a type starting with 'A' (Events.c:404); any other string still schedules
+     * Ther_Event but leaves the velocities alone — not a mode the device implements, so refuse it instead of diverging */
+    if (v->thermostat_on && strncmp(thermostatType, "Andersen", 1) != 0) return SDMD_ERR_UNSUPPORTED;
     v->method_ding = strncmp(Methodtype, "Ding", 1) == 0;
 #ifdef HYDROGEN_BOND
     v->hydrogen_bond = 1;
