@@ -233,8 +233,39 @@ int sdmd_glue_flatten(struct sdmd_host_view *v) {
         v->is_cons[i] = strcmp(p->extraProperty[1], "_CONS") == 0;
         for (struct ConstraintStr *b = p->bond; b; b = b->next) nb++;
         for (struct ConstraintStr *c = p->constr; c; c = c->next) nc++;
-        for (int j = 1; j <= n; j++)
-            if (connectionMap[i][j] & (BOND_CONNECT | CONSTRAINT_CONNECT)) ncm++;
+    }
+    /* Sparse rows of connectionMap (no O(N^2) scan of the dense matrix).  A BOND / CONSTRAINT bit is only ever set
+     * for a pair that sits in a bond or constraint list (Initialization.c:1176-1214, 1413, 1458), on either side; so the
+     * candidates of row i are the partners of i's lists plus every atom that lists i, and the bits are read from the matrix
+     * for those pairs only.  Rows come out in ascending j like the dense scan.  SDMD_GLUE_CHECK_CM=1 compares with the full scan. */
+    int *cand_off = NULL, *cand = NULL;
+    ALLOC(cand_off, n + 2);
+    for (int i = 1; i <= n; i++) {
+        struct PropertyStr *p = atom[i].property;
+        for (struct ConstraintStr *b = p->bond; b; b = b->next) if (b->connection >= 1 && b->connection <= n) { cand_off[i + 1]++; cand_off[b->connection + 1]++; }
+        for (struct ConstraintStr *c = p->constr; c; c = c->next) if (c->connection >= 1 && c->connection <= n) { cand_off[i + 1]++; cand_off[c->connection + 1]++; }
+    }
+    for (int i = 1; i <= n + 1; i++) cand_off[i] += cand_off[i - 1];      /* row i = [cand_off[i], cand_off[i + 1]) */
+    ALLOC(cand, cand_off[n + 1] + 1);
+    {
+        int *fill = NULL;
+        ALLOC(fill, n + 2);
+        for (int i = 1; i <= n; i++) {
+            struct PropertyStr *p = atom[i].property;
+            for (struct ConstraintStr *b = p->bond; b; b = b->next) if (b->connection >= 1 && b->connection <= n) {
+                cand[cand_off[i] + fill[i]++] = b->connection; cand[cand_off[b->connection] + fill[b->connection]++] = i; }
+            for (struct ConstraintStr *c = p->constr; c; c = c->next) if (c->connection >= 1 && c->connection <= n) {
+                cand[cand_off[i] + fill[i]++] = c->connection; cand[cand_off[c->connection] + fill[c->connection]++] = i; }
+        }
+        free(fill);
+    }
+    for (int i = 1; i <= n; i++) {      /* sort every row (insertion sort: rows hold a handful of entries), drop repeats, keep flagged pairs */
+        int *r = cand + cand_off[i], m = cand_off[i + 1] - cand_off[i], u = 0;
+        for (int a = 1; a < m; a++) { int key = r[a], b = a; while (b > 0 && r[b - 1] > key) { r[b] = r[b - 1]; b--; } r[b] = key; }
+        for (int a = 0; a < m; a++)
+            if ((a == 0 || r[a] != r[a - 1]) && (connectionMap[i][r[a]] & (BOND_CONNECT | CONSTRAINT_CONNECT))) r[u++] = r[a];
+        for (int a = u; a < m; a++) r[a] = 0;       /* 0 terminates the kept part of the row */
+        ncm += u;
     }
     ALLOC(v->bond_j, nb + 1); ALLOC(v->bond_dmin2, nb + 1); ALLOC(v->bond_dmax2, nb + 1);
     ALLOC(v->con_j, nc + 1); ALLOC(v->con_table, nc + 1);
@@ -256,10 +287,21 @@ int sdmd_glue_flatten(struct sdmd_host_view *v) {
             nc++;
         }
         v->cm_off[i] = ncm;
-        for (int j = 1; j <= n; j++) {
-            int f = connectionMap[i][j] & (BOND_CONNECT | CONSTRAINT_CONNECT);
-            if (f) { v->cm_j[ncm] = j; v->cm_flags[ncm] = f; ncm++; }
+        for (int a = cand_off[i]; a < cand_off[i + 1] && cand[a]; a++) {
+            v->cm_j[ncm] = cand[a]; v->cm_flags[ncm] = connectionMap[i][cand[a]] & (BOND_CONNECT | CONSTRAINT_CONNECT); ncm++;
         }
+    }
+    free(cand); free(cand_off);
+    if (getenv("SDMD_GLUE_CHECK_CM")) {      /* the dense scan the sparse construction replaces, as a cross-check */
+        int k = 0, bad = 0;
+        for (int i = 1; i <= n && !bad; i++)
+            for (int j = 1; j <= n; j++) {
+                int f = connectionMap[i][j] & (BOND_CONNECT | CONSTRAINT_CONNECT);
+                if (!f) continue;
+                if (k >= ncm || v->cm_j[k] != j || v->cm_flags[k] != f || k < v->cm_off[i] - 0) { bad = 1; break; }
+                k++;
+            }
+        if (bad || k != ncm) { fprintf(stderr, "sdmd glue: sparse connection rows differ from the dense connectionMap\n"); return SDMD_ERR_STATE; }
     }
     v->bond_off[n + 1] = nb; v->bond_off[0] = 0;
     v->con_off[n + 1] = nc;  v->con_off[0] = 0;

@@ -1,5 +1,6 @@
 """GPU: the reference's own driver with the hot path on the GPU (sdmd_b200/host/_build/sDMD_cuda) must write the
 same trajectory and connection map, byte for byte, as the unmodified reference binary on the same input."""
+import os
 import shutil
 import subprocess
 from pathlib import Path
@@ -13,6 +14,9 @@ REF = ROOT / "oracle" / "_ref"
 DROPIN = ROOT / "sdmd_b200" / "host" / "_build" / "sDMD_cuda_fixedseed"
 
 pytestmark = pytest.mark.gpu
+
+# every drop-in run of this module also cross-checks the glue's sparse connection rows against the dense connectionMap scan
+os.environ["SDMD_GLUE_CHECK_CM"] = "1"
 
 
 def _run(binary, work: Path, time_units):
