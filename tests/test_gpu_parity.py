@@ -214,6 +214,55 @@ def test_exact_ties_keep_reference_visiting_order(capi):
     assert_fields_equal(hg, ho, STATE_FIELDS)
 
 
+@pytest.mark.parametrize("variant", ["cell_by_cell_kernels", "two_types", "three_step_table", "ties_cell_by_cell"])
+def test_round0_paths_against_oracle(capi, variant, monkeypatch):
+    """Round 0 of the full-system pass has several code paths for bond-free boxes; each one must give the oracle's bits:
+    the row-batched filter + cp.async evaluation of sdmd_k2_rows.cu with the step table in registers (default, every other GEL
+    test), its generic table walk (two atom types / a table of three steps: DevP::uni_table = -1), and the cell-by-cell filter +
+    ordered evaluation of sdmd_cuda.cu (SDMD_K2_ROWS=0)."""
+    from oracle.oracle_py import Oracle
+    from sdmd_b200.hostview import NT, STEP_TABLE_DTYPE
+    from sdmd_b200.synth import GEL_TYPE, gel_box
+    if variant in ("cell_by_cell_kernels", "ties_cell_by_cell"):
+        monkeypatch.setenv("SDMD_K2_ROWS", "0")
+    if variant == "ties_cell_by_cell":
+        hv0, rng, _ = _tie_box()
+    else:
+        hv0, rng = gel_box(32, a=6.5, jitter=0.4, seed=77)
+    n = hv0.natom
+    if variant == "two_types":
+        other = 31
+        t = np.zeros(3, dtype=STEP_TABLE_DTYPE)
+        t[0] = hv0.tables[0]
+        for k, (core, d, e) in enumerate([(3.6, 6.0, -0.3), (3.8, 6.2, 0.25)], start=1):
+            t[k]["dmin2"] = core * core; t[k]["nstep"] = 1; t[k]["d2"][0] = d * d; t[k]["e"][0] = e; t[k]["acc"][0] = e
+        hv0.tables = t
+        hv0.type[1::3] = other
+        hv0.coll_index[other * NT + other] = 1
+        hv0.coll_index[other * NT + GEL_TYPE] = 2
+        hv0.coll_index[GEL_TYPE * NT + other] = 2
+    if variant == "three_step_table":
+        t = hv0.tables.copy()
+        t[0]["nstep"] = 3
+        for k, (d, e) in enumerate([(5.0, 0.4), (6.0, -0.2), (7.0, 0.1)]):
+            t[0]["d2"][k] = d * d; t[0]["e"][k] = e
+        t[0]["acc"][0] = 0.4; t[0]["acc"][1] = 0.2; t[0]["acc"][2] = 0.3
+        hv0.tables = t
+    gauss = rng.standard_normal(n + 20000)
+    ho = hv0.copy(); o = Oracle(ho); o.rng_feed(gauss)
+    hg = hv0.copy(); r = capi.Replica(hg, device=0); r.rng_feed(gauss)
+    o.pbc_full(); o.cell_build(); o.predict_all(); o.cbt_build()
+    r.pbc_full(); r.cell_build(); r.predict_all(); r.cbt_build()
+    r.download(hg)
+    assert_fields_equal(hg, ho, SLOT_FIELDS + ("cell_idx",), what=variant + " after Predict(all): ")
+    assert r.stats()["pair_predictions"] == o.stats()["pair_predictions"]
+    assert r.stats()["warnings"] == o.stats()["warnings"]
+    so, to = o.run(max_iter=800, trace_cap=800)
+    sg, tg = r.run(max_iter=800, trace_cap=800)
+    assert_trace_equal(tg, to)
+    r.close(); o.close()
+
+
 def test_round_trip_properties_1m(capi):
     """Full size (N = 10^6): size-independent properties instead of an element-wise oracle comparison —
     link list is a permutation with every atom in the cell its coordinates say, CBT root is the global
