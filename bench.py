@@ -182,9 +182,9 @@ def cuda_pass(args, dist):
     rep = capi.Replica(hv, device=dist.local_rank)
     rep.rng_feed(gauss)
 
-    def one_pass():
+    def one_pass():     # Prepare() of the reference on the resident state: PBC + LinkList + Predict(all) + CreateCBT, one C-ABI call
         rep.rng_seek(0)
-        rep.pbc_full(); rep.cell_build(); rep.predict_all(); rep.cbt_build()
+        rep.prepare_resident()
 
     # -------- device-resident timing (`value`) --------
     sampler = ClockSampler(dist.local_rank)

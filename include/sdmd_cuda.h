@@ -303,6 +303,10 @@ int  sdmd_cuda_cbt_build(sdmd_ctx *ctx);
  * Arrays are 1-based (natom+1 entries); page-locked host memory (sdmd_host_register) makes the copies asynchronous. */
 int  sdmd_cuda_prepare(sdmd_ctx *ctx, const double *x, const double *y, const double *z, const double *vx,
                        const double *vy, const double *vz, const double *gauss, int64_t n_gauss);
+/* Prepare() SGThread.c:44-62 on the state that is already on the device: PBC("full"), LinkList("full"), Predict(all),
+ * CreateCBT in one call (PBC rides along with the cell-index kernel; the thermostat stream continues where it stands).
+ * Same results as pbc_full + cell_build + predict_all + cbt_build. */
+int  sdmd_cuda_prepare_resident(sdmd_ctx *ctx);
 int  sdmd_cuda_cbt_update(sdmd_ctx *ctx, const int32_t *renew_list);
 /* AssignJob SGThread.c:237-259: target = CBT.node[1], dt = its event time, partner (0 if none) */
 int  sdmd_cuda_assign_job(sdmd_ctx *ctx, int32_t *target, int32_t *partner, double *dt, int32_t *renew_list);

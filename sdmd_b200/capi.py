@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "sdmd_cuda_download_celllist", "sdmd_cuda_download_cbt",
     "sdmd_cuda_rng_feed", "sdmd_cuda_rng_fill_libc", "sdmd_cuda_rng_available", "sdmd_cuda_rng_seek", "sdmd_cuda_rng_reset", "sdmd_host_gaussian_libc",
     "sdmd_cuda_timer_begin", "sdmd_cuda_timer_end", "sdmd_cuda_synchronize", "sdmd_cuda_host_register", "sdmd_cuda_host_unregister",
-    "sdmd_cuda_pbc_full", "sdmd_cuda_cell_build", "sdmd_cuda_predict_all", "sdmd_cuda_predict", "sdmd_cuda_cbt_build", "sdmd_cuda_prepare",
+    "sdmd_cuda_pbc_full", "sdmd_cuda_cell_build", "sdmd_cuda_predict_all", "sdmd_cuda_predict", "sdmd_cuda_cbt_build", "sdmd_cuda_prepare", "sdmd_cuda_prepare_resident",
     "sdmd_cuda_cbt_update", "sdmd_cuda_assign_job", "sdmd_cuda_advance", "sdmd_cuda_add_time", "sdmd_cuda_hazard_check",
     "sdmd_cuda_cell_move", "sdmd_cuda_do_event", "sdmd_cuda_potential_energy", "sdmd_cuda_kinetic_energy",
     "sdmd_cuda_run", "sdmd_cuda_run_many", "sdmd_cuda_potential_energy_many", "sdmd_cuda_get_stats", "sdmd_cuda_set_temperature",
@@ -120,6 +120,7 @@ def lib():
     L.sdmd_cuda_upload_coords.argtypes = [vp] + [dp] * 6
     L.sdmd_cuda_upload_celllist.argtypes = [vp, i32p]
     L.sdmd_cuda_prepare.argtypes = [vp] + [dp] * 7 + [C.c_int64]
+    L.sdmd_cuda_prepare_resident.argtypes = [vp]
     L.sdmd_cuda_download.argtypes = [vp, C.POINTER(CHostView)]
     L.sdmd_cuda_download_slots.argtypes = [vp, dp, dp, i32p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]
     L.sdmd_cuda_download_celllist.argtypes = [vp, i32p]
@@ -235,6 +236,10 @@ class Replica:
         hv = hv or self.hv
         g = np.ascontiguousarray(gauss, dtype=np.float64)
         _check(self.L.sdmd_cuda_prepare(self.h, _dp(hv.x), _dp(hv.y), _dp(hv.z), _dp(hv.vx), _dp(hv.vy), _dp(hv.vz), _dp(g), len(g)), "prepare")
+
+    def prepare_resident(self):
+        """Prepare() on the state already in HBM: PBC + LinkList + Predict(all) + CreateCBT in one call."""
+        _check(self.L.sdmd_cuda_prepare_resident(self.h), "prepare_resident")
 
     def upload_celllist(self, cl):
         cl = np.ascontiguousarray(cl, dtype=np.int32)

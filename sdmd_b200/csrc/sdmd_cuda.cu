@@ -174,11 +174,27 @@ __global__ void k_pbc_full(DevP D) {
 
 // LinkList("full") step 1, Events.c:129-150: cell index per atom + histogram
 // (the histogram's atomicAdd also hands every atom its arrival rank inside the cell, so the scatter needs no second atomic)
+// PBC: PBC("full") (Events.c:218-228) applied on the way — what k_pbc_full does, without reading the coordinates twice
+template <bool PBC>
 __global__ void k_cell_index(DevP D, int *cell_of, int *cell_count, int *arrival) {
+    SDMD_PDL_ENTRY();
     int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (i > D.n) return;
     int idx[3];
-    int cell = d_cell_of(D, D.x[i], D.y[i], D.z[i], idx);
+    double x = D.x[i], y = D.y[i], z = D.z[i];
+    if (PBC) {
+        double c[3] = {x, y, z};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (!(D.pbc_mask >> k & 1)) continue;   // closed by a wall, Events.c:210-216
+            if (c[k] >= D.box[k]) c[k] -= D.box[k];
+            else if (c[k] < 0) c[k] += D.box[k];
+        }
+        if (c[0] != x) D.x[i] = x = c[0];
+        if (c[1] != y) D.y[i] = y = c[1];
+        if (c[2] != z) D.z[i] = z = c[2];
+    }
+    int cell = d_cell_of(D, x, y, z, idx);
     D.cell_idx[3 * i] = idx[0]; D.cell_idx[3 * i + 1] = idx[1]; D.cell_idx[3 * i + 2] = idx[2];
     cell_of[i] = cell;
     arrival[i] = atomicAdd(&cell_count[cell], 1);
@@ -296,6 +312,7 @@ __global__ void k_scan_add_cells(DevP D, int *out, int *count, const int *block_
 // cleared for the next build.  Two dependent launches (16 us at 667 k cells) become one (~6 us).
 __global__ void __launch_bounds__(512) k_scan_cells(DevP D, int *count, int *out, unsigned long long *state, unsigned *ticket, unsigned ticket_base,
                                                     unsigned epoch, int m, int nb) {
+    SDMD_PDL_ENTRY();
     __shared__ int s_b, s_prefix;
     if (threadIdx.x == 0) s_b = (int)(atomicAdd(ticket, 1u) - ticket_base);
     __syncthreads();
@@ -349,6 +366,7 @@ __global__ void __launch_bounds__(512) k_scan_cells(DevP D, int *count, int *out
 
 // atoms of a cell side by side, in arrival order
 __global__ void k_cell_scatter(DevP D, const int *cell_of, const int *arrival, const int *cell_start, int *unordered) {
+    SDMD_PDL_ENTRY();
     int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (i > D.n) return;
     unordered[cell_start[cell_of[i]] + arrival[i]] = i;
@@ -361,6 +379,7 @@ __global__ void k_cell_scatter(DevP D, const int *cell_of, const int *arrival, c
 // parts: as k_cell_permute
 __global__ void k_cell_place(DevP D, const int *cell_of, const int *cell_start, const int *unordered, int *sorted_atom, SRec *srec, float4 *sloc,
                              int *scell, int parts) {
+    SDMD_PDL_ENTRY();
     int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (i > D.n) return;
     if ((parts & 4) && i == 1) D.ctl->cc_floor = ++D.ctl->cc_epoch;   // new link list: every cached candidate list is void
@@ -680,6 +699,7 @@ __device__ __forceinline__ int d_scan_slot(const DevP &D, int i, int a) {
 // settle atoms with a single lower-index pointer, queue the ambiguous ones
 __global__ void k_predict_all_resolve(DevP D, SlotBuf b, const int *pcount, const int *pwho, const double *second, const double *bp_time,
                                       const int *bp_j, int *queue, int *nqueue, int *npair, unsigned long long *pair_sum) {
+    SDMD_PDL_ENTRY();
     int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     int copy = 0;
     int cnt = (i <= D.n) ? pcount[i] : 0;
@@ -831,6 +851,7 @@ __global__ void __launch_bounds__(128, K2_MINBLOCKS) k_predict_all_fixpoint(DevP
 // kernels: tournament tree (K5), advance (K4)
 // ===================================================================================================
 __global__ void k_cbt_leaves(DevP D, const int *leaf_atom) {
+    SDMD_PDL_ENTRY();
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= D.n) return;
     int a = leaf_atom[k];
@@ -842,6 +863,7 @@ __global__ void k_cbt_leaves(DevP D, const int *leaf_atom) {
 // bottom-up tournament inside one subtree per block: root f0 = 2^L + blockIdx.x, internal nodes of relative depth
 // dmax..0, one __syncthreads per level (a block's writes are visible to its own threads after the barrier)
 __global__ void __launch_bounds__(256) k_cbt_subtrees(DevP D, int L, int dmax) {
+    SDMD_PDL_ENTRY();
     int f0 = (1 << L) + blockIdx.x;
     if (f0 >= D.n) return;
     for (int d = dmax; d >= 0; d--) {
@@ -859,6 +881,7 @@ __global__ void __launch_bounds__(256) k_cbt_subtrees(DevP D, int L, int dmax) {
 }
 // the levels above the subtree roots (nodes 1 .. 2^L - 1), one block
 __global__ void __launch_bounds__(256) k_cbt_top(DevP D, int L) {
+    SDMD_PDL_ENTRY();
     for (int lv = L - 1; lv >= 0; lv--) {
         int base = 1 << lv;
         for (int t = threadIdx.x; t < base; t += blockDim.x) {
@@ -2214,24 +2237,33 @@ int sdmd_cuda_pbc_full(sdmd_ctx *c) {
     return 0;
 }
 
-static int cell_build_impl(sdmd_ctx *c, int parts, bool bump) {
+static int cell_build_impl(sdmd_ctx *c, int parts, bool bump, bool pbc = false) {
     Timer t(c, "cell_build");
     int n = c->n, m = c->P.ncell;
     // (the histogram is all zero here: zero-filled at create, cleared again by the scan of the previous build)
-    { Timer t2(c, "k1_index", 2); k_cell_index<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_count, c->cell_rank); }
+    {
+        Timer t2(c, "k1_index", 2);
+        if (pbc) CK(sdmd_launch_pdl(k_cell_index<true>, dim3(grid_for(n, 256)), dim3(256), c->stream, c->P, c->cell_of, c->cell_count, c->cell_rank));
+        else CK(sdmd_launch_pdl(k_cell_index<false>, dim3(grid_for(n, 256)), dim3(256), c->stream, c->P, c->cell_of, c->cell_count, c->cell_rank));
+    }
     int nb = (m + SCAN_ITEMS - 1) / SCAN_ITEMS;
     {
         Timer t2(c, "k1_scan", 2);
         c->scan_epoch = (c->scan_epoch + 1) & 0x3fffffffu;
         if (c->scan_epoch == 0) c->scan_epoch = 1;      // (0 is what a never-written state word carries)
-        k_scan_cells<<<nb, 512, 0, c->stream>>>(c->P, c->cell_count, c->d_cell_start, c->scan_state, c->scan_ticket, c->scan_ticket_base, c->scan_epoch, m, nb);
+        CK(sdmd_launch_pdl(k_scan_cells, dim3(nb), dim3(512), c->stream, c->P, c->cell_count, c->d_cell_start, c->scan_state, c->scan_ticket, c->scan_ticket_base,
+                           c->scan_epoch, m, nb));
         c->scan_ticket_base += (unsigned)nb;
     }
-    { Timer t2(c, "k1_scatter", 2); k_cell_scatter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->cell_rank, c->d_cell_start, c->cell_tmp); }
+    {
+        Timer t2(c, "k1_scatter", 2);
+        CK(sdmd_launch_pdl(k_cell_scatter, dim3(grid_for(n, 256)), dim3(256), c->stream, c->P, (const int *)c->cell_of, (const int *)c->cell_rank,
+                           (const int *)c->d_cell_start, c->cell_tmp));
+    }
     {
         Timer t2(c, "k1_place", 2);
-        k_cell_place<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->cell_of, c->d_cell_start, c->cell_tmp, c->d_sorted_atom, c->d_srec, c->d_sloc,
-                                                             c->d_scell, parts | (bump ? 4 : 0));
+CK(sdmd_launch_pdl(k_cell_place, dim3(grid_for(n, 256)), dim3(256), c->stream, c->P, (const int *)c->cell_of, (const int *)c->d_cell_start,
+                           (const int *)c->cell_tmp, c->d_sorted_atom, c->d_srec, c->d_sloc, c->d_scell, parts | (bump ? 4 : 0)));
     }
     c->launches += 4;      // index, scan, scatter, place
     c->cells_fresh = true;
@@ -2255,14 +2287,16 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
     SlotBuf B = {c->b_time, c->b_pot, c->b_partner, c->b_pcounter, c->b_type, c->b_sub};
     SlotBuf C = {c->c_time, c->c_pot, c->c_partner, c->c_pcounter, c->c_type, c->c_sub};
     int grid = grid_for(n, 128), grid1 = grid_for(n, 256);
-    CK(cudaMemsetAsync(c->pcount, 0, ((size_t)n + 1) * sizeof(int), c->stream));
-    CK(cudaMemsetAsync(c->nqueue, 0, (FIX_NQ + 2) * sizeof(int), c->stream));   // queue lengths and, behind them, the evaluation-count sum
+    if (!c->P.rows_mode) {    // (the row filter clears both itself: no memset between the kernels of the pass)
+        CK(cudaMemsetAsync(c->pcount, 0, ((size_t)n + 1) * sizeof(int), c->stream));
+        CK(cudaMemsetAsync(c->nqueue, 0, (FIX_NQ + 2) * sizeof(int), c->stream));   // queue lengths and, behind them, the evaluation-count sum
+    }
     {
         Timer t(c, "predict_all");
         const bool tile = c->P.tile_tx > 0;
         if (c->P.rows_mode) {
             Timer tf(c, "k2_filter", 2);
-            if (sdmd_k2_rows_filter_launch(c->P, c->stream)) return set_err(SDMD_ERR_CUDA, "k_r0_filter_rows", cudaGetLastError());
+            if (sdmd_k2_rows_filter_launch(c->P, c->pcount, c->nqueue, FIX_NQ + 2, c->stream)) return set_err(SDMD_ERR_CUDA, "k_r0_filter_rows", cudaGetLastError());
             c->launches++;
         } else if (c->P.surv && c->P.tile_mode != 1) {
             Timer tf(c, "k2_filter", 2);
@@ -2294,8 +2328,8 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
         Timer t2(c, "predict_all_fixup");
         {
             Timer t3(c, "fixup_resolve", 2);
-            k_predict_all_resolve<<<grid1, 256, 0, c->stream>>>(c->P, B, c->pcount, c->pwho, c->second, c->bp_time, c->bp_j, c->queue_a,
-                                                                c->nqueue, c->npair, c->d_sum);
+CK(sdmd_launch_pdl(k_predict_all_resolve, dim3(grid1), dim3(256), c->stream, c->P, B, (const int *)c->pcount, (const int *)c->pwho,
+                               (const double *)c->second, (const double *)c->bp_time, (const int *)c->bp_j, c->queue_a, c->nqueue, c->npair, c->d_sum));
         }
         {
             Timer t4(c, "fixup_rounds", 2);
@@ -2354,7 +2388,7 @@ int sdmd_cuda_cbt_build(sdmd_ctx *c) {
     CK(cudaSetDevice(c->device));
     Timer t(c, "cbt_build");
     int n = c->n;
-    k_cbt_leaves<<<grid_for(n, 256), 256, 0, c->stream>>>(c->P, c->d_leaf_atom);
+    CK(sdmd_launch_pdl(k_cbt_leaves, dim3(grid_for(n, 256)), dim3(256), c->stream, c->P, (const int *)c->d_leaf_atom));
     c->launches++;
     if (n > 1) {
         // internal nodes 1..n-1: subtrees of height <= 11 bottom-up in one launch, then the few levels above them
@@ -2362,10 +2396,10 @@ int sdmd_cuda_cbt_build(sdmd_ctx *c) {
         while ((2 << depth) <= n - 1) depth++;          // level of the deepest internal node
         int L = depth > 10 ? depth - 10 : 0;
         int nsub = 1 << L;
-        k_cbt_subtrees<<<nsub, 256, 0, c->stream>>>(c->P, L, depth - L);
+        CK(sdmd_launch_pdl(k_cbt_subtrees, dim3(nsub), dim3(256), c->stream, c->P, L, depth - L));
         c->launches++;
         if (L > 0) {
-            k_cbt_top<<<1, 256, 0, c->stream>>>(c->P, L);
+            CK(sdmd_launch_pdl(k_cbt_top, dim3(1), dim3(256), c->stream, c->P, L));
             c->launches++;
         }
     }
@@ -2404,10 +2438,18 @@ int sdmd_cuda_prepare(sdmd_ctx *c, const double *x, const double *y, const doubl
     c->h_ctl->g_filled = n_gauss;
     c->h_ctl->g_pos = 0;
     TRY(set_rng_cursor(c, 3));
-    k_pbc_full<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->P);
-    c->launches++;
-    TRY(cell_build_impl(c, 1, true));
+    TRY(cell_build_impl(c, 1, true, true));
     TRY(predict_all_impl(c, c->ev_copy));
+    return sdmd_cuda_cbt_build(c);
+}
+
+// The same on the state that is already in HBM: PBC("full") + LinkList("full") + Predict(all) + CreateCBT = the reference's
+// Prepare() (SGThread.c:44-62) as one call; the thermostat stream continues where it stands.
+int sdmd_cuda_prepare_resident(sdmd_ctx *c) {
+    CK(cudaSetDevice(c->device));
+    TRY(need_counters(c));
+    TRY(cell_build_impl(c, 3, true, true));
+    TRY(predict_all_impl(c, nullptr));
     return sdmd_cuda_cbt_build(c);
 }
 

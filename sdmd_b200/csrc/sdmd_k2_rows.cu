@@ -59,9 +59,13 @@
 #endif
 __device__ __forceinline__ void r0_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-__global__ void __launch_bounds__(RF_NT, RF_MINB) k_r0_filter_rows(DevP D) {
+__global__ void __launch_bounds__(RF_NT, RF_MINB) k_r0_filter_rows(DevP D, int *pcount, int *zero, int nzero) {
+    SDMD_PDL_ENTRY();
     const int p_self = blockIdx.x * RF_NT + threadIdx.x;
+    if (p_self < nzero) zero[p_self] = 0;
+    if (p_self == 0) pcount[0] = 0;
     if (p_self >= D.n) return;
+    pcount[p_self + 1] = 0;             // (indexed by atom id 1..n; the evaluation kernel counts into it)
 #if RF_PF
     if (p_self + RF_PF < D.n) {
         r0_prefetch_l2(&D.sloc[p_self + RF_PF]);
@@ -183,6 +187,7 @@ template <bool FAST>
 __global__ void __launch_bounds__(RE_NT, RE_MINB) k_r0_eval_rows(DevP D, SlotBuf dst, Round0Out out, i64 g_base) {
     // thread-private strips: entry e, 16-byte part q of thread t at [(e * 4 + q) * RE_NT + t] (conflict-free 16-byte accesses)
     __shared__ double2 strip[RE_NB * 4 * RE_NT];
+    SDMD_PDL_ENTRY();
     const int tid = threadIdx.x, lane = tid & 31;
     const int p = blockIdx.x * RE_NT + tid;
     const bool live = p < D.n;                       // (every lane of a warp takes part in the gathers)
@@ -394,14 +399,15 @@ int sdmd_k2_rows_configure(DevP &P) {
     return 0;
 }
 
-int sdmd_k2_rows_filter_launch(const DevP &P, cudaStream_t stream) {
-    k_r0_filter_rows<<<(P.n + RF_NT - 1) / RF_NT, RF_NT, 0, stream>>>(P);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+int sdmd_k2_rows_filter_launch(const DevP &P, int *pcount, int *zero, int nzero, cudaStream_t stream) {
+    if (nzero > P.n) return -1;
+    return sdmd_launch_pdl(k_r0_filter_rows, dim3((P.n + RF_NT - 1) / RF_NT), dim3(RF_NT), stream, P, pcount, zero, nzero) == cudaSuccess ? 0 : -1;
 }
 
 int sdmd_k2_rows_eval_launch(const DevP &P, SlotBuf dst, Round0Out out, long long g_base, cudaStream_t stream) {
-    if (P.uni_table >= 0) k_r0_eval_rows<true><<<(P.n + RE_NT - 1) / RE_NT, RE_NT, 0, stream>>>(P, dst, out, g_base);
-    else
-        k_r0_eval_rows<false><<<(P.n + RE_NT - 1) / RE_NT, RE_NT, 0, stream>>>(P, dst, out, g_base);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    const dim3 grid((P.n + RE_NT - 1) / RE_NT), block(RE_NT);
+    const i64 gb = g_base;
+    cudaError_t e = P.uni_table >= 0 ? sdmd_launch_pdl(k_r0_eval_rows<true>, grid, block, stream, P, dst, out, gb)
+                                     : sdmd_launch_pdl(k_r0_eval_rows<false>, grid, block, stream, P, dst, out, gb);
+    return e == cudaSuccess ? 0 : -1;
 }

@@ -526,6 +526,15 @@ def test_prepare_one_call_equals_stepwise(capi, case):
     assert np.array_equal(a.cbt()[0][1:], b.cbt()[0][1:])
     sa, sb = a.run(max_iter=300, trace_cap=300), b.run(max_iter=300, trace_cap=300)
     assert sa[1].tobytes() == sb[1].tobytes()
+    # ... and Prepare() on the resident state (sdmd_cuda_prepare_resident) == the four stage calls, from where the run stopped
+    pa0, pb0 = a.stats()["pair_predictions"], b.stats()["pair_predictions"]
+    a.pbc_full(); a.cell_build(); a.predict_all(); a.cbt_build()
+    b.prepare_resident()
+    a.download(ha); b.download(hb)
+    assert_fields_equal(hb, ha, tuple(SLOT_FIELDS) + ("x", "y", "z", "vx", "vy", "vz", "cell_idx"))
+    assert np.array_equal(a.celllist(), b.celllist())
+    assert np.array_equal(a.cbt()[0][1:], b.cbt()[0][1:])
+    assert a.stats()["pair_predictions"] - pa0 == b.stats()["pair_predictions"] - pb0 > 0
 
 
 def _live_case(name, **kw):
