@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SDMD_ABI_VERSION 6
+#define SDMD_ABI_VERSION 7
 
 /* reference constants, DMD.h:25-30 */
 #define SDMD_INFINIT       1E8
@@ -188,6 +188,13 @@ struct sdmd_host_view {
     int32_t charge_com;               /* chargeAA[COM] (command-line -COM) */
     double  charge_pos[SDMD_MAX_CHARGE][3], charge_vel[SDMD_MAX_CHARGE][3];
     double  charge_potgrad[SDMD_MAX_CHARGE], charge_gap[SDMD_MAX_CHARGE];
+
+    /* hydrogen-bond tallies the reference prints with -HBn and stores in savedData.dat (DataSave.c:461-470, 574): HBnumformed and
+     * alphaHBformed (Events.c:296-311,352-389).  hb_name: 1 where property->name is "H", 2 where it is "O", else 0 — what
+     * CheckAlphaHB (Events.c:1121-1128) looks at; may be NULL (no alpha tally). */
+    uint8_t *hb_name;
+    int32_t hb_num_formed;            /* HBnumformed at the start of the run */
+    int32_t alpha_hb_formed;          /* alphaHBformed at the start of the run */
 };
 
 /* wallType (parameter.txt line 11), first letter decides (strncmp(...,1)): which coordinates take part in the wall distance
@@ -215,6 +222,8 @@ struct sdmd_run_stats {
     int64_t wall;                     /* walleventsum: wall, obstruction and spherical-obstacle events (Events.c:73-100) */
     int64_t error_prints;             /* "!!ERROR!!" messages the reference would have printed and carried on from (negative
                                        * predicted time, bond long-/short-error: TimePrediction.c:168-173,240-269); NOT in warningsum */
+    int64_t hb_num_formed;            /* HBnumformed: hydrogen bonds in existence now (Events.c:345,384) */
+    int64_t alpha_hb_formed;          /* alphaHBformed: those between backbone H and O four residues apart (CheckAlphaHB, Events.c:1121-1128) */
 };
 
 enum sdmd_stop_reason {

@@ -8,7 +8,6 @@
  * Known, deliberate deviations (none reachable on the shipped inputs):
  *  - FindElemInList's unbounded scan (ToolFunctions.c:1078-1084) can run past neighborPartner[4] into the
  *    next struct members; here the scan stops at index 4.
- *  - alphaHBformed bookkeeping (Events.c:310-311,363-364,386-389) needs atom names and only feeds a warning.
  *  - fatal paths of the reference (exit(EXIT_FAILURE)) set stats.error instead of exiting.
  */
 #include <math.h>
@@ -67,6 +66,9 @@ oracle_ctx *oracle_create(struct sdmd_host_view *v) {
     c->celllist = calloc((size_t)c->n + c->ncell + 1, sizeof(int32_t));
     c->st.currenttime = v->currenttime;
     c->st.frame = v->frame;
+    c->hbnumformed = v->hb_num_formed;
+    c->st.hb_num_formed = v->hb_num_formed;
+    c->st.alpha_hb_formed = v->alpha_hb_formed;
     return c;
 }
 
@@ -1014,6 +1016,13 @@ static void list_refresh(struct sdmd_host_view *v, int a, int target) {
     }
 }
 
+/* CheckAlphaHB, Events.c:1121-1128 (hb_name: 1 = "H", 2 = "O") */
+static int check_alpha_hb(const struct sdmd_host_view *v, int i, int j) {
+    if (!v->hb_name || v->protein_num[i] != v->protein_num[j]) return 0;
+    int ni = v->hb_name[i], nj = v->hb_name[j];
+    return (ni == 1 && nj == 2 && v->aa_num[j] == v->aa_num[i] - 4) || (ni == 2 && nj == 1 && v->aa_num[i] == v->aa_num[j] - 4);
+}
+
 /* HBEvent, Events.c:275-393 */
 static void hb_event(oracle_ctx *c, int i, int j, int ni, int nj) {
     struct sdmd_host_view *v = c->v;
@@ -1026,7 +1035,9 @@ static void hb_event(oracle_ctx *c, int i, int j, int ni, int nj) {
         t = ++v->hbn_status[j];  v->hbn_partner[5 * j + t] = v->hb_neighbor[i];
         t = ++v->hbn_status[ni]; v->hbn_partner[5 * ni + t] = j;
         t = ++v->hbn_status[nj]; v->hbn_partner[5 * nj + t] = i;
+        if (check_alpha_hb(v, i, j)) c->st.alpha_hb_formed++;    /* Events.c:310-311 */
         c->hbnumformed++;
+        c->st.hb_num_formed = c->hbnumformed;
     } else if (v->hb_itype[i] == SDMD_HB_BREAK) {
         v->hb_bond[i] = 0; v->hb_bond[j] = 0;
         v->type[i] = type_change(v->type[i], 0);
@@ -1035,7 +1046,10 @@ static void hb_event(oracle_ctx *c, int i, int j, int ni, int nj) {
         --v->hbn_status[j];  list_refresh(v, j, v->hb_neighbor[i]);
         --v->hbn_status[ni]; list_refresh(v, ni, j);
         --v->hbn_status[nj]; list_refresh(v, nj, i);
+        if (check_alpha_hb(v, i, j)) c->st.alpha_hb_formed--;    /* Events.c:363-364 */
         c->hbnumformed--;
+        c->st.hb_num_formed = c->hbnumformed;
+        if (c->st.hb_num_formed < c->st.alpha_hb_formed) c->st.warnings++;   /* Events.c:386-389 */
     }
 }
 

@@ -1794,6 +1794,8 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     TRY(dupload(c, &P.hb_bond, v->hb_bond, n1));
     TRY(dupload(c, (int **)&P.hb_neighbor, v->hb_neighbor, n1));
     TRY(dupload(c, (uint8_t **)&P.hb_role, v->hb_role, n1));
+    P.hb_name = nullptr;
+    if (v->hb_name) TRY(dupload(c, (uint8_t **)&P.hb_name, v->hb_name, n1));
     TRY(dupload(c, &P.hb_itype, v->hb_itype, n1));
     TRY(dupload(c, &P.hbn_partner, v->hbn_partner, 5 * n1));
     TRY(dupload(c, &P.hbn_pnum, v->hbn_partner_num, n1));
@@ -1943,6 +1945,8 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     c->h_ctl->timestep = v->timestep;
     c->h_ctl->temperature = v->target_temperature;
     c->h_ctl->frame = v->frame;
+    c->h_ctl->hbnumformed = v->hb_num_formed;
+    c->h_ctl->alphaformed = v->alpha_hb_formed;
     c->h_ctl->cc_epoch = 1;
     c->h_ctl->cc_floor = 1;
     CK(cudaMemcpyAsync(c->d_ctl, c->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream));
@@ -2600,6 +2604,7 @@ static void fill_stats(const Ctl *h, struct sdmd_run_stats *s) {
     s->pair_predictions = h->pair_predictions; s->gaussians_used = h->g_pos; s->currenttime = h->currenttime;
     s->stop_reason = h->stop ? h->stop - 1 : 0; s->error = h->error;
     s->wall = h->n_wall; s->error_prints = h->error_prints;
+    s->hb_num_formed = h->hbnumformed; s->alpha_hb_formed = h->alphaformed;
 }
 
 int sdmd_cuda_get_stats(sdmd_ctx *c, struct sdmd_run_stats *s) {

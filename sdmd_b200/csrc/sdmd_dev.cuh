@@ -30,7 +30,8 @@ struct Ctl {
     int target, partner;       // AssignJob result
     int stop;                  // 0 = running, else 1 + sdmd_stop_reason
     int error;
-    int hbnumformed;
+    int hbnumformed;           // HBnumformed
+    int alphaformed;           // alphaHBformed (Events.c:310-311,363-364)
     int changed;               // predict_all fix-point flag
     i64 trace_pos;
     int pad_cc_;
@@ -117,6 +118,7 @@ struct DevP {
     int *hb_bond;
     const int *hb_neighbor;
     const uint8_t *hb_role;
+    const uint8_t *hb_name;    // 1 = "H", 2 = "O" (CheckAlphaHB, Events.c:1121-1128), NULL: no alpha tally
     uint8_t *hb_itype;
     int *hbn_partner, *hbn_pnum, *hbn_status;
     double *ev_time, *ev_pot;

@@ -1296,6 +1296,12 @@ __device__ __forceinline__ void d_touch_cells(const DevP &D, int i, int j) {
     D.cell_epoch[(D.cell_idx[3 * i + 2] * D.cellnum[1] + D.cell_idx[3 * i + 1]) * D.cellnum[0] + D.cell_idx[3 * i]] = t;
     D.cell_epoch[(D.cell_idx[3 * j + 2] * D.cellnum[1] + D.cell_idx[3 * j + 1]) * D.cellnum[0] + D.cell_idx[3 * j]] = t;
 }
+// CheckAlphaHB, Events.c:1121-1128: backbone H and O of one chain, the O four residues in front of the H
+__device__ __forceinline__ bool d_check_alpha_hb(const DevP &D, int i, int j) {
+    if (!D.hb_name || D.protein[i] != D.protein[j]) return false;
+    int ni = D.hb_name[i], nj = D.hb_name[j];
+    return (ni == 1 && nj == 2 && D.aa_num[j] == D.aa_num[i] - 4) || (ni == 2 && nj == 1 && D.aa_num[i] == D.aa_num[j] - 4);
+}
 __device__ inline void d_hb_event(const DevP &D, int i, int j, int ni, int nj) {
     if (D.hb_itype[i] == SDMD_HB_FORM) {
         D.hb_bond[i] = j; D.hb_bond[j] = i;
@@ -1306,6 +1312,7 @@ __device__ inline void d_hb_event(const DevP &D, int i, int j, int ni, int nj) {
         t = ++D.hbn_status[j];  D.hbn_partner[5 * j + t] = D.hb_neighbor[i];
         t = ++D.hbn_status[ni]; D.hbn_partner[5 * ni + t] = j;
         t = ++D.hbn_status[nj]; D.hbn_partner[5 * nj + t] = i;
+        if (d_check_alpha_hb(D, i, j)) D.ctl->alphaformed++;
         D.ctl->hbnumformed++;
         d_touch_cells(D, i, j);
     } else if (D.hb_itype[i] == SDMD_HB_BREAK) {
@@ -1316,7 +1323,9 @@ __device__ inline void d_hb_event(const DevP &D, int i, int j, int ni, int nj) {
         --D.hbn_status[j];  d_list_refresh(D, j, D.hb_neighbor[i]);
         --D.hbn_status[ni]; d_list_refresh(D, ni, j);
         --D.hbn_status[nj]; d_list_refresh(D, nj, i);
+        if (d_check_alpha_hb(D, i, j)) D.ctl->alphaformed--;
         D.ctl->hbnumformed--;
+        if (D.ctl->hbnumformed < D.ctl->alphaformed) atomicAdd((unsigned long long *)&D.ctl->warnings, 1ULL);   // Events.c:386-389
         d_touch_cells(D, i, j);
     }
 }

@@ -48,6 +48,8 @@ static void sync_to_reference(void) {
     thermostateventsum = base_counts[5] + st.thermostat;
     pbcandcrosseventsum = base_counts[6] + st.pcc;
     walleventsum = base_counts[7] + st.wall;
+    HBnumformed = (int)st.hb_num_formed;          /* what SaveHB prints (-HBn) and SaveDAT stores, DataSave.c:461-470, 573-574 */
+    alphaHBformed = (int)st.alpha_hb_formed;
 }
 
 /* Prepare(), SGThread.c:21-64 */

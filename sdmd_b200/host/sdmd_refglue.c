@@ -134,6 +134,8 @@ int sdmd_glue_flatten(struct sdmd_host_view *v) {
     for (int k = 0; k < 3; k++) v->box[k] = boxDimension[k + 1];
     v->cutoffr = cutoffr;
     v->thermoF = thermoF;
+    v->hb_num_formed = HBnumformed;
+    v->alpha_hb_formed = alphaHBformed;
     v->thermostat_on = strcmp(thermostatType, "no") != 0;
     /* ThermostatEvent redraws velocities only for a type starting with 'A' (Events.c:404); any other string still schedules
      * Ther_Event but leaves the velocities alone — not a mode the device implements, so refuse it instead of diverging */
@@ -202,7 +204,7 @@ int sdmd_glue_flatten(struct sdmd_host_view *v) {
     ALLOC(v->vx, n + 1); ALLOC(v->vy, n + 1); ALLOC(v->vz, n + 1);
     ALLOC(v->mass, n + 1); ALLOC(v->type, n + 1); ALLOC(v->aa_type, n + 1);
     ALLOC(v->protein_num, n + 1); ALLOC(v->aa_num, n + 1); ALLOC(v->is_cons, n + 1);
-    ALLOC(v->hb_bond, n + 1); ALLOC(v->hb_neighbor, n + 1); ALLOC(v->hb_role, n + 1); ALLOC(v->hb_itype, n + 1);
+    ALLOC(v->hb_bond, n + 1); ALLOC(v->hb_neighbor, n + 1); ALLOC(v->hb_role, n + 1); ALLOC(v->hb_itype, n + 1); ALLOC(v->hb_name, n + 1);
     ALLOC(v->hbn_partner, 5 * (n + 1)); ALLOC(v->hbn_partner_num, n + 1); ALLOC(v->hbn_status, n + 1);
     ALLOC(v->ev_time, n + 1); ALLOC(v->ev_potential, n + 1); ALLOC(v->ev_partner, n + 1);
     ALLOC(v->ev_counter, n + 1); ALLOC(v->ev_pcounter, n + 1); ALLOC(v->ev_type, n + 1); ALLOC(v->ev_sub, n + 1);
@@ -231,6 +233,7 @@ int sdmd_glue_flatten(struct sdmd_host_view *v) {
         v->protein_num[i] = p->sequence.proteinNum;
         v->aa_num[i] = p->sequence.aminoacidNum;
         v->is_cons[i] = strcmp(p->extraProperty[1], "_CONS") == 0;
+        v->hb_name[i] = strcmp(p->name, "H") == 0 ? 1 : (strcmp(p->name, "O") == 0 ? 2 : 0);   /* CheckAlphaHB, Events.c:1121-1128 */
         for (struct ConstraintStr *b = p->bond; b; b = b->next) nb++;
         for (struct ConstraintStr *c = p->constr; c; c = c->next) nc++;
     }
@@ -340,7 +343,7 @@ int sdmd_glue_flatten(struct sdmd_host_view *v) {
 void sdmd_glue_free(struct sdmd_host_view *v) {
     free(v->x); free(v->y); free(v->z); free(v->vx); free(v->vy); free(v->vz);
     free(v->mass); free(v->type); free(v->aa_type); free(v->protein_num); free(v->aa_num); free(v->is_cons);
-    free(v->hb_bond); free(v->hb_neighbor); free(v->hb_role); free(v->hb_itype);
+    free(v->hb_bond); free(v->hb_neighbor); free(v->hb_role); free(v->hb_itype); free(v->hb_name);
     free(v->hbn_partner); free(v->hbn_partner_num); free(v->hbn_status);
     free(v->ev_time); free(v->ev_potential); free(v->ev_partner); free(v->ev_counter); free(v->ev_pcounter);
     free(v->ev_type); free(v->ev_sub); free(v->cell_idx); free(v->flow_a); free(v->flow_time_rec); free(v->protein_mass); free(v->charge);
@@ -410,7 +413,7 @@ void sdmd_snap_put_view(sdmd_snap *s, const struct sdmd_host_view *v) {
     PUT(vx, "f8", n1); PUT(vy, "f8", n1); PUT(vz, "f8", n1);
     PUT(mass, "f8", n1); PUT(type, "i4", n1); PUT(aa_type, "i4", n1);
     PUT(protein_num, "i4", n1); PUT(aa_num, "i4", n1); PUT(is_cons, "u1", n1);
-    PUT(hb_bond, "i4", n1); PUT(hb_neighbor, "i4", n1); PUT(hb_role, "u1", n1); PUT(hb_itype, "u1", n1);
+    PUT(hb_bond, "i4", n1); PUT(hb_neighbor, "i4", n1); PUT(hb_role, "u1", n1); PUT(hb_itype, "u1", n1); PUT(hb_name, "u1", n1);
     PUT(hbn_partner, "i4", 5 * n1); PUT(hbn_partner_num, "i4", n1); PUT(hbn_status, "i4", n1);
     PUT(ev_time, "f8", n1); PUT(ev_potential, "f8", n1); PUT(ev_partner, "i4", n1);
     PUT(ev_counter, "i8", n1); PUT(ev_pcounter, "i8", n1); PUT(ev_type, "u1", n1); PUT(ev_sub, "u1", n1);
@@ -418,6 +421,8 @@ void sdmd_snap_put_view(sdmd_snap *s, const struct sdmd_host_view *v) {
     PUT(flow_a, "f8", 3 * n1); PUT(flow_time_rec, "f8", n1); PUT(protein_mass, "f8", n1); PUT(charge, "f8", n1);
     int32_t flow_i[2] = {v->flow_mark, v->charge_com};
     sdmd_snap_put(s, "flow_i4", "i4", flow_i, 2);
+    int32_t hb_i[2] = {v->hb_num_formed, v->alpha_hb_formed};
+    sdmd_snap_put(s, "hb_i4", "i4", hb_i, 2);
     double csrc[SDMD_MAX_CHARGE][8];
     for (int q = 0; q < v->n_charge; q++) {
         for (int k = 0; k < 3; k++) { csrc[q][k] = v->charge_pos[q][k]; csrc[q][3 + k] = v->charge_vel[q][k]; }

@@ -13,7 +13,7 @@ from pathlib import Path
 
 import numpy as np
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_CHARGE = 8
 MAX_OBST = 4
 NT = 33
@@ -70,6 +70,7 @@ class CHostView(C.Structure):
         ("charge", _P(C.c_double)), ("n_charge", C.c_int32), ("charge_com", C.c_int32),
         ("charge_pos", C.c_double * (3 * MAX_CHARGE)), ("charge_vel", C.c_double * (3 * MAX_CHARGE)),
         ("charge_potgrad", C.c_double * MAX_CHARGE), ("charge_gap", C.c_double * MAX_CHARGE),
+        ("hb_name", _P(C.c_uint8)), ("hb_num_formed", C.c_int32), ("alpha_hb_formed", C.c_int32),
     ]
 
 
@@ -81,6 +82,7 @@ class CRunStats(C.Structure):
         ("pair_predictions", C.c_int64), ("gaussians_used", C.c_int64),
         ("currenttime", C.c_double), ("stop_reason", C.c_int32), ("error", C.c_int32),
         ("wall", C.c_int64), ("error_prints", C.c_int64),
+        ("hb_num_formed", C.c_int64), ("alpha_hb_formed", C.c_int64),
     ]
 
     def as_dict(self):
@@ -100,6 +102,7 @@ PER_ATOM = [
     ("ev_time", "f8", 1), ("ev_potential", "f8", 1), ("ev_partner", "i4", 1), ("ev_counter", "i8", 1),
     ("ev_pcounter", "i8", 1), ("ev_type", "u1", 1), ("ev_sub", "u1", 1), ("cell_idx", "i4", 3),
     ("flow_a", "f8", 3), ("flow_time_rec", "f8", 1), ("protein_mass", "f8", 1), ("charge", "f8", 1),
+    ("hb_name", "u1", 1),
 ]
 MUTABLE = ["x", "y", "z", "vx", "vy", "vz", "type", "hb_bond", "hb_itype", "hbn_partner", "hbn_partner_num",
            "hbn_status", "ev_time", "ev_potential", "ev_partner", "ev_counter", "ev_pcounter", "ev_type", "ev_sub",
@@ -167,6 +170,8 @@ class HostView:
         self.flow_mark = 0          # 0 none, 1 constant drift velocity, 2 constant force
         self.flow_v = np.zeros(3)
         self.charge_com = 0
+        self.hb_num_formed = 0      # HBnumformed / alphaHBformed at the start of the run
+        self.alpha_hb_formed = 0
         self.charge_src = np.zeros((0, 8))   # per charge source: position (3), velocity (3), potential gradient, gap
         for name, dt, k in PER_ATOM:
             setattr(self, name, np.zeros(n1 * k, dtype=_NP[dt]))
@@ -207,6 +212,8 @@ class HostView:
         for name, dt, _ in PER_ATOM:
             if name in d:               # arrays added later (flow_*) are absent in older snapshots: keep the zeros
                 setattr(hv, name, np.ascontiguousarray(d[name], dtype=_NP[dt]).copy())
+        if "hb_i4" in d:
+            hv.hb_num_formed, hv.alpha_hb_formed = (int(v) for v in d["hb_i4"][:2])
         if "flow_f8" in d:
             hv.flow_mark = int(d["flow_i4"][0])
             hv.flow_v = np.asarray(d["flow_f8"], dtype=np.float64)[:3].copy()
@@ -219,7 +226,7 @@ class HostView:
         hv.tables = np.frombuffer(d["tables"].tobytes(), dtype=STEP_TABLE_DTYPE).copy()
         known = {n for n, _, _ in PER_ATOM} | {n for n, _ in OTHER} | {"scalars_i4", "scalars_f8", "scalars_i8", "tables", "wall_i4", "wall_f8",
                                                                            "obst_pos", "obst_type", "sphobst_pos", "sphobst_radius",
-                                                                           "tunnel_pos", "tunnel_diameter", "tunnel_i4", "obst_hole", "flow_i4", "flow_f8", "charge_src"}
+                                                                           "tunnel_pos", "tunnel_diameter", "tunnel_i4", "obst_hole", "flow_i4", "flow_f8", "charge_src", "hb_i4"}
         hv.extra = {k: v for k, v in d.items() if k not in known}
         return hv
 
@@ -249,6 +256,7 @@ class HostView:
             "tunnel_i4": np.array([self.tunnel_type], dtype=np.int32),
             "obst_hole": np.asarray(self.obst_hole, dtype=np.int32),
             "flow_i4": np.array([self.flow_mark, self.charge_com], dtype=np.int32),
+            "hb_i4": np.array([self.hb_num_formed, self.alpha_hb_formed], dtype=np.int32),
             "charge_src": np.asarray(self.charge_src, dtype=np.float64).reshape(-1),
             "flow_f8": np.asarray(self.flow_v, dtype=np.float64),
             "tables": np.frombuffer(self.tables.tobytes(), dtype=np.uint8),
@@ -294,6 +302,7 @@ class HostView:
         for k, v in enumerate(self.sphobst_radius):
             c.sphobst_radius[k] = float(v)
         c.flow_mark = int(self.flow_mark)
+        c.hb_num_formed, c.alpha_hb_formed = int(self.hb_num_formed), int(self.alpha_hb_formed)
         cs = np.asarray(self.charge_src, dtype=np.float64).reshape(-1, 8)
         assert len(cs) <= MAX_CHARGE
         c.n_charge, c.charge_com = len(cs), int(self.charge_com)

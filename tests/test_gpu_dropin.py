@@ -27,7 +27,8 @@ def _run(binary, work: Path, time_units):
     lines[1] = "Time               %g" % time_units
     p.write_text("\n".join(lines) + "\n")
     (work / "out").mkdir()
-    r = subprocess.run([str(binary), "-f", "ala10.gro", "-i", str(work / "input"), "-o", str(work / "out")],
+    # every optional per-dump output the reference offers: potential / kinetic energy, temperature, hydrogen-bond tallies
+    r = subprocess.run([str(binary), "-f", "ala10.gro", "-i", str(work / "input"), "-o", str(work / "out"), "-pot", "-kin", "-tem", "-HBn"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return r.stdout.replace("\r", "\n")
@@ -49,6 +50,17 @@ def test_dropin_driver_writes_identical_outputs(tmp_path):
         a = (tmp_path / "ref" / "out" / name).read_bytes()
         b = (tmp_path / "gpu" / "out" / name).read_bytes()
         assert len(a) > 1000 and a == b, name
+    # the per-dump outputs (-pot -kin -tem -HBn): same set of files, same bytes; the HB file carries HBnumformed and alphaHBformed
+    def _outputs(d):      # (savedData.dat holds a time stamp-dependent seed, timeEvaluation.dat wall-clock times, the log the command line)
+        return sorted(p.name for p in d.iterdir() if p.is_file() and not p.name.startswith(("savedData", "timeEvaluation")) and "log" not in p.name.lower())
+    ref_files, gpu_files = _outputs(tmp_path / "ref" / "out"), _outputs(tmp_path / "gpu" / "out")
+    assert ref_files == gpu_files and len(ref_files) >= 6, (ref_files, gpu_files)
+    for name in ref_files:
+        if name == "SysInfo.dat":      # raw structs with heap pointers in them (PropertyStr, ConstraintStr: DataSave.c:225-256)
+            continue
+        assert (tmp_path / "ref" / "out" / name).read_bytes() == (tmp_path / "gpu" / "out" / name).read_bytes(), name
+    hb = [ln.split() for ln in (tmp_path / "gpu" / "out" / next(n for n in gpu_files if "HB" in n)).read_text().splitlines() if ln and ln[0].isdigit()]
+    assert max(int(r[1]) for r in hb) > 0, "no hydrogen bond was ever formed in the run: the HB tallies are not exercised"
     for key in ("ReCalculate times", "collision times", "bond times", "HB times", "HB Neighbor times", "thermostat times",
                 "PBC&CC times"):
         assert _counter(ref_out, key) == _counter(gpu_out, key), key
