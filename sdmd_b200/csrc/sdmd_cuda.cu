@@ -351,6 +351,16 @@ __global__ void __launch_bounds__(512) k_scan_cells(DevP D, int *count, int *out
     }
     __syncthreads();
     ex += s_prefix;
+    if (t0 + 3 < m) {       // four consecutive cells per thread: one 16-byte store per array
+        const int e1 = ex + v[0], e2 = e1 + v[1], e3 = e2 + v[2];
+        *reinterpret_cast<int4 *>(out + t0) = make_int4(ex, e1, e2, e3);
+        *reinterpret_cast<int4 *>(count + t0) = make_int4(0, 0, 0, 0);
+        *reinterpret_cast<int4 *>(D.cell_cnt + t0) = make_int4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (v[q] == 0) D.celllist[D.n + t0 + q + 1] = 0;
+        return;
+    }
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int t = t0 + q;
