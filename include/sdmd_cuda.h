@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SDMD_ABI_VERSION 7
+#define SDMD_ABI_VERSION 8
 
 /* reference constants, DMD.h:25-30 */
 #define SDMD_INFINIT       1E8
@@ -195,6 +195,14 @@ struct sdmd_host_view {
     uint8_t *hb_name;
     int32_t hb_num_formed;            /* HBnumformed at the start of the run */
     int32_t alpha_hb_formed;          /* alphaHBformed at the start of the run */
+
+    /* moving smooth wall ("WallDyn compress | expand | pulse", Initialization.c:1937-1978): the wall surface follows
+     * boxDimension, which DoWallDyn (Events.c:502-540, sdmd_cuda_wall_dyn_step) changes once per time unit and WallTime's retry
+     * (TimePrediction.c:675-697) pushes back out when it finds an atom outside.  wall_dyn = 0: static walls. */
+    int32_t wall_dyn;                 /* strcmp(wallDyn.mark, "no") != 0 */
+    int32_t wall_dyn_touch;           /* wallDyn.touch */
+    double  wall_dyn_step;            /* wallDyn.step */
+    double  wall_dyn_orig_box[3];     /* wallDyn.origBoxDim[1..3] */
 };
 
 /* wallType (parameter.txt line 11), first letter decides (strncmp(...,1)): which coordinates take part in the wall distance
@@ -316,6 +324,20 @@ int  sdmd_cuda_prepare(sdmd_ctx *ctx, const double *x, const double *y, const do
  * CreateCBT in one call (PBC rides along with the cell-index kernel; the thermostat stream continues where it stands).
  * Same results as pbc_full + cell_build + predict_all + cbt_build. */
 int  sdmd_cuda_prepare_resident(sdmd_ctx *ctx);
+/* DoWallDyn Events.c:502-540, called by the host loop where the reference calls it (SGThread.c:129, after an executed event) once
+ * currenttime has reached wd->cur_time: advances the box edges by one step (pulse: turns around first where the reference does),
+ * bumps the event counter of every atom whose pending event is a wall event, ends the motion ("compress" / "expand" reached).
+ * In/out: the reference's wallDyn fields; `box` returns the box edges afterwards.  sdmd_cuda_wall_dyn_state reads the edges and the
+ * retry tally as WallTime left them (they change during sdmd_cuda_run). */
+struct sdmd_wall_dyn {
+    int32_t mode;                     /* 0 "no", 1 "compress", 2 "expand", 3 "pulse" */
+    int32_t sign, touch, pad_;
+    double  size, rate, step, cur_time;
+    double  orig_box[3];
+    double  box[3];
+};
+int  sdmd_cuda_wall_dyn_step(sdmd_ctx *ctx, struct sdmd_wall_dyn *wd);
+int  sdmd_cuda_wall_dyn_state(sdmd_ctx *ctx, double box[3], int32_t *touch);
 int  sdmd_cuda_cbt_update(sdmd_ctx *ctx, const int32_t *renew_list);
 /* AssignJob SGThread.c:237-259: target = CBT.node[1], dt = its event time, partner (0 if none) */
 int  sdmd_cuda_assign_job(sdmd_ctx *ctx, int32_t *target, int32_t *partner, double *dt, int32_t *renew_list);

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "sdmd_cuda_rng_feed", "sdmd_cuda_rng_fill_libc", "sdmd_cuda_rng_available", "sdmd_cuda_rng_seek", "sdmd_cuda_rng_reset", "sdmd_host_gaussian_libc",
     "sdmd_cuda_timer_begin", "sdmd_cuda_timer_end", "sdmd_cuda_synchronize", "sdmd_cuda_host_register", "sdmd_cuda_host_unregister",
     "sdmd_cuda_pbc_full", "sdmd_cuda_cell_build", "sdmd_cuda_predict_all", "sdmd_cuda_predict", "sdmd_cuda_cbt_build", "sdmd_cuda_prepare", "sdmd_cuda_prepare_resident",
-    "sdmd_cuda_cbt_update", "sdmd_cuda_assign_job", "sdmd_cuda_advance", "sdmd_cuda_add_time", "sdmd_cuda_hazard_check",
+    "sdmd_cuda_cbt_update", "sdmd_cuda_wall_dyn_step", "sdmd_cuda_wall_dyn_state", "sdmd_cuda_assign_job", "sdmd_cuda_advance", "sdmd_cuda_add_time", "sdmd_cuda_hazard_check",
     "sdmd_cuda_cell_move", "sdmd_cuda_do_event", "sdmd_cuda_potential_energy", "sdmd_cuda_kinetic_energy",
     "sdmd_cuda_run", "sdmd_cuda_run_many", "sdmd_cuda_potential_energy_many", "sdmd_cuda_get_stats", "sdmd_cuda_set_temperature",
     "sdmd_remd_rearrange", "sdmd_remd_nccl_unique_id", "sdmd_remd_nccl_init", "sdmd_remd_seed_server", "sdmd_remd_exchange", "sdmd_remd_exchange_energy", "sdmd_remd_finish", "sdmd_host_glibc_rand",

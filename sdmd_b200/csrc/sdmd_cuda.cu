@@ -163,8 +163,8 @@ __global__ void k_pbc_full(DevP D) {
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         if (!(D.pbc_mask >> k & 1)) continue;   // closed by a wall, Events.c:210-216
-        if (c[k] >= D.box[k]) c[k] -= D.box[k];
-        else if (c[k] < 0) c[k] += D.box[k];
+        if (c[k] >= d_box(D, k)) c[k] -= d_box(D, k);
+        else if (c[k] < 0) c[k] += d_box(D, k);
     }
     // only what moved is written back (nothing at all for a box that is already wrapped: 24 B per atom instead of 48)
     if (c[0] != D.x[i]) D.x[i] = c[0];
@@ -187,8 +187,8 @@ __global__ void k_cell_index(DevP D, int *cell_of, int *cell_count, int *arrival
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             if (!(D.pbc_mask >> k & 1)) continue;   // closed by a wall, Events.c:210-216
-            if (c[k] >= D.box[k]) c[k] -= D.box[k];
-            else if (c[k] < 0) c[k] += D.box[k];
+            if (c[k] >= d_box(D, k)) c[k] -= d_box(D, k);
+            else if (c[k] < 0) c[k] += d_box(D, k);
         }
         if (c[0] != x) D.x[i] = x = c[0];
         if (c[1] != y) D.y[i] = y = c[1];
@@ -654,9 +654,9 @@ __device__ __forceinline__ void d_requeue_round_rows(const DevP &D, const SlotBu
             if (seam) {
                 int ncx, ncy, ncz;
                 d_neighbor_cell(D, me.cx, me.cy, me.cz, (int)(w >> 27), &ncx, &ncy, &ncz);
-                shx = d_shift1(me.cx, ncx, D.cellnum[0], D.box[0]);
-                shy = d_shift1(me.cy, ncy, D.cellnum[1], D.box[1]);
-                shz = d_shift1(me.cz, ncz, D.cellnum[2], D.box[2]);
+                shx = d_shift1(me.cx, ncx, D.cellnum[0], d_box(D, 0));
+                shy = d_shift1(me.cy, ncy, D.cellnum[1], d_box(D, 1));
+                shz = d_shift1(me.cz, ncz, D.cellnum[2], d_box(D, 2));
             }
             double t, pot;
             int sb;
@@ -1487,6 +1487,27 @@ __global__ void k_predict_list_n(DevP D, const int *list, int cnt) {
         D.ctl->pair_predictions += np;
     }
 }
+// Predict(all) in the reference's own order by one thread: for systems with a moving wall, where a prediction (WallTime's retry)
+// changes the box every later prediction sees — small confined systems, SGThread.c:47-52,158-211
+__global__ void k_predict_all_serial(DevP D) {
+    SlotSrc S = d_live_slots(D);
+    for (int i = 1; i <= D.n; i++) { D.ev_type[i] = SDMD_EV_INVD; D.ev_time[i] = SD_INF; D.ev_partner[i] = SDMD_INVALID; }
+    for (int i = 1; i <= D.n; i++) {
+        Slot cur = d_reset_slot(D.ev_pot[i], D.ev_sub[i], D.ev_pcounter[i]);
+        double g = 0;
+        if (D.thermostat_on && !D.is_cons[i]) g = d_next_gauss(D);
+        int np = 0;
+        cur = d_predict_atom<false>(D, S, i, cur, g, 0x7fffffff, &np);
+        d_store_slot(D, i, cur);
+        D.ctl->pair_predictions += np;
+    }
+    D.ctl->pa_passes++;
+}
+// DoWallDyn, Events.c:528-532: a wall event predicted against the old wall position is stale
+__global__ void k_wall_counter_bump(DevP D) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i <= D.n && D.ev_type[i] == SDMD_EV_WALL) D.ev_counter[i]++;
+}
 __global__ void k_cbt_update(DevP D, int a0, int a1) {
     if (a0 > 0) d_cbt_update_run(D, a0);
     if (a1 > 0) d_cbt_update_run(D, a1);
@@ -1525,9 +1546,9 @@ __device__ inline int d_potential_terms(const DevP &D, int i, double *out, int c
     for (int n = 0; n < 27; n++) {
         int nx = cx + c_offx[n], ny = cy + c_offy[n], nz = cz + c_offz[n];
         double shx = 0, shy = 0, shz = 0;
-        if (nx < 0) { nx = D.cellnum[0] - 1; shx = -1 * D.box[0]; } else if (nx >= D.cellnum[0]) { nx = 0; shx = D.box[0]; }
-        if (ny < 0) { ny = D.cellnum[1] - 1; shy = -1 * D.box[1]; } else if (ny >= D.cellnum[1]) { ny = 0; shy = D.box[1]; }
-        if (nz < 0) { nz = D.cellnum[2] - 1; shz = -1 * D.box[2]; } else if (nz >= D.cellnum[2]) { nz = 0; shz = D.box[2]; }
+        if (nx < 0) { nx = D.cellnum[0] - 1; shx = -1 * d_box(D, 0); } else if (nx >= D.cellnum[0]) { nx = 0; shx = d_box(D, 0); }
+        if (ny < 0) { ny = D.cellnum[1] - 1; shy = -1 * d_box(D, 1); } else if (ny >= D.cellnum[1]) { ny = 0; shy = d_box(D, 1); }
+        if (nz < 0) { nz = D.cellnum[2] - 1; shz = -1 * d_box(D, 2); } else if (nz >= D.cellnum[2]) { nz = 0; shz = d_box(D, 2); }
         int cell = nz * D.cellnum[0] * D.cellnum[1] + ny * D.cellnum[0] + nx;
         for (int pair = D.celllist[D.n + cell + 1]; pair != 0; pair = D.celllist[pair]) {
             if (pair <= i) continue;
@@ -1751,6 +1772,10 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
         for (int k = 0; k < 4; k++) SB.tun_pos[n][k] = v->tunnel_pos[n][k];
     }
     for (int n = 0; n < v->n_obst; n++) SB.obst_hole[n] = v->obst_hole[n];
+    P.wall_dyn = (v->wall_dyn != 0 && v->wall_kind != 0) ? 1 : 0;
+    P.wd_active = P.wall_dyn;
+    P.wd_step = v->wall_dyn_step;
+    P.wd_orig_y = v->wall_dyn_orig_box[1];
     P.single_body = P.wall_kind != 0 || P.n_obst > 0 || P.n_sphobst > 0 || P.n_tunnel > 0 || v->flow_mark == 3;
     P.thermostat_on = v->thermostat_on;
     P.method_ding = v->method_ding;
@@ -1956,6 +1981,8 @@ static int create_impl(sdmd_ctx *c, const struct sdmd_host_view *v) {
     c->h_ctl->temperature = v->target_temperature;
     c->h_ctl->frame = v->frame;
     c->h_ctl->hbnumformed = v->hb_num_formed;
+    for (int k = 0; k < 3; k++) c->h_ctl->dbox[k] = v->box[k];
+    c->h_ctl->wd_touch = v->wall_dyn_touch;
     c->h_ctl->alphaformed = v->alpha_hb_formed;
     c->h_ctl->cc_epoch = 1;
     c->h_ctl->cc_floor = 1;
@@ -2297,6 +2324,15 @@ static int predict_all_impl(sdmd_ctx *c, cudaEvent_t late) {
     if (c->P.thermostat_on) need = c->n_draws;  // one draw per predicted, non-constrained atom (SGThread.c:165-168, TimePrediction.c:591)
     if (c->g_filled - c->h_ctl->g_pos < need) return set_err(SDMD_ERR_BAD_ARG, "predict_all: not enough gaussians fed");
     i64 g_pos0 = c->h_ctl->g_pos;
+    if (c->P.wall_dyn) {      // moving wall: a prediction can change the box the next one sees -> the reference's order, one thread
+        Timer t(c, "predict_all");
+        k_predict_all_serial<<<1, 1, 0, c->stream>>>(c->P);
+        c->launches++;
+        c->h_ctl->g_pos = g_pos0 + need;
+        c->counters_known = false;
+        CK(cudaGetLastError());
+        return 0;
+    }
     i64 g_base = g_pos0 % c->P.g_cap;       // ring offset of the first draw
     SlotBuf B = {c->b_time, c->b_pot, c->b_partner, c->b_pcounter, c->b_type, c->b_sub};
     SlotBuf C = {c->c_time, c->c_pot, c->c_partner, c->c_pcounter, c->c_type, c->c_sub};
@@ -2465,6 +2501,51 @@ int sdmd_cuda_prepare_resident(sdmd_ctx *c) {
     TRY(cell_build_impl(c, 3, true, true));
     TRY(predict_all_impl(c, nullptr));
     return sdmd_cuda_cbt_build(c);
+}
+
+// DoWallDyn, Events.c:502-540 (the arithmetic in the reference's order; `box` are boxDimension[1..3])
+int sdmd_cuda_wall_dyn_step(sdmd_ctx *c, struct sdmd_wall_dyn *wd) {
+    CK(cudaSetDevice(c->device));
+    if (!wd) return set_err(SDMD_ERR_BAD_ARG, "wall_dyn_step: null argument");
+    if (!c->P.wall_dyn) return set_err(SDMD_ERR_STATE, "wall_dyn_step: the context was created without a moving wall");
+    TRY(pull_ctl(c));
+    Ctl *h = c->h_ctl;
+    double *box = h->dbox;
+    wd->touch = h->wd_touch;
+    const double currenttime = h->currenttime;
+    if (wd->mode != 0 && currenttime >= wd->cur_time) {
+        if (wd->mode == 3) {                                                                   // "pulse", :504-514
+            if ((wd->orig_box[1] - box[1] >= wd->size) || (wd->orig_box[1] == box[1])) {
+                wd->sign *= -1;
+                wd->touch = 0;
+            } else if (fabs(box[1] + (int)(currenttime / wd->rate + 1) * wd->size - (currenttime - 1) * wd->step - wd->orig_box[1]) <= wd->step &&
+                       wd->touch >= 5) {
+                wd->sign *= -1;
+                wd->touch = 0;
+            }
+        }
+        wd->cur_time += 1;
+        if (c->P.wall_kind == SDMD_WALL_PARALLEL) box[1] += wd->sign * wd->step;               // :518-527
+        else if (c->P.wall_kind == SDMD_WALL_CYLINDER) { box[1] += wd->sign * wd->step; box[2] += wd->sign * wd->step; }
+        else { box[0] += wd->sign * wd->step; box[1] += wd->sign * wd->step; box[2] += wd->sign * wd->step; }
+        k_wall_counter_bump<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->P);                 // :529-533
+        c->launches++;
+        if (((wd->orig_box[1] - box[1] >= wd->size) && wd->mode == 1) || ((wd->orig_box[1] - box[1] <= wd->step) && wd->mode == 2)) wd->mode = 0;   // :535-538
+        h->wd_touch = wd->touch;
+        CK(cudaMemcpyAsync(c->d_ctl->dbox, h->dbox, sizeof(h->dbox), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(&c->d_ctl->wd_touch, &h->wd_touch, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        c->P.wd_active = wd->mode != 0;       // once the motion has ended WallTime no longer retries (strcmp(wallDyn.mark, "no"), TimePrediction.c:678)
+    }
+    for (int k = 0; k < 3; k++) wd->box[k] = box[k];
+    CK(cudaGetLastError());
+    return 0;
+}
+int sdmd_cuda_wall_dyn_state(sdmd_ctx *c, double box[3], int32_t *touch) {
+    CK(cudaSetDevice(c->device));
+    TRY(pull_ctl(c));
+    for (int k = 0; k < 3; k++) box[k] = c->P.wall_dyn ? c->h_ctl->dbox[k] : c->P.box[k];
+    if (touch) *touch = c->h_ctl->wd_touch;
+    return 0;
 }
 
 int sdmd_cuda_cbt_update(sdmd_ctx *c, const int32_t *renew) {

@@ -40,6 +40,10 @@ struct Ctl {
     // the cells it touched with the new tick (DevP::cell_epoch).  A cached list is valid while its stamp is at least
     // cc_floor (last wholesale invalidation: new link list) and no cell of its 27-cell neighbourhood carries a later tick.
     i64 cc_epoch, cc_floor;
+    // moving walls (WallDyn): the box edges WallTime / PBCShift see, changed by DoWallDyn (host, once per time unit) and by
+    // WallTime's own retry when an atom is found outside the wall (TimePrediction.c:675-697)
+    double dbox[3];
+    int wd_touch, wd_pad_;     // wallDyn.touch
     i64 phase_cycles[12];      // clock64() per loop phase (thread 0): head, advance, event, gather, eval, fold, cbt
     // overlapped sweep: AssignJob result per launch parity.  The event block of launch n publishes the job of launch
     // n+1 in the other slot while sweep blocks of launch n may still be reading theirs.
@@ -184,6 +188,9 @@ struct DevP {
     // round 0 by sdmd_k2_rows.cu: survivor rows are written in row order, not in visiting order (re-evaluation rounds sort them)
     int rows_mode;
     int cm_empty;            // the connection map has no entry at all (no bond, no constraint)
+    int wall_dyn;            // moving walls: the box lives in Ctl::dbox (d_box)
+    int wd_active;           // the motion is still on (wallDyn.mark != "no"): WallTime may push the box back out
+    double wd_step, wd_orig_y;   // wallDyn.step, wallDyn.origBoxDim[2]
     int uni_table;           // >= 0: every atom has the same type; its collision table (index) has <= 2 steps and no dmax2.  Else -1
 };
 

@@ -6,6 +6,8 @@ __device__ __forceinline__ double d_rx(const DevP &D, int j) { return d_lz(D, j)
 __device__ __forceinline__ double d_ry(const DevP &D, int j) { return d_lz(D, j) ? D.lz_y[j] + D.vy[j] * D.lz_dt : D.y[j]; }
 __device__ __forceinline__ double d_rz(const DevP &D, int j) { return d_lz(D, j) ? D.lz_z[j] + D.vz[j] * D.lz_dt : D.z[j]; }
 __device__ __forceinline__ double d_rt(const DevP &D, int j) { return d_lz(D, j) ? D.lz_t[j] - D.lz_dt : D.ev_time[j]; }
+// box edge k: a kernel parameter, except under moving walls (WallDyn), where DoWallDyn and WallTime change it during the run
+__device__ __forceinline__ double d_box(const DevP &D, int k) { return D.wall_dyn ? D.ctl->dbox[k] : D.box[k]; }
 // event time of another atom's slot: the live slots go through d_rt, the relaxation buffers of Predict(all) do not
 __device__ __forceinline__ double d_stime(const DevP &D, const SlotSrc &S, int j) { return S.time == D.ev_time ? d_rt(D, j) : S.time[j]; }
 
@@ -190,9 +192,9 @@ __device__ __forceinline__ Pair d_pair(double xi, double yi, double zi, double v
 }
 __device__ inline Pair d_pair_atoms(const DevP &D, int i, int j) {
     const int *ci = &D.cell_idx[3 * i], *cj = &D.cell_idx[3 * j];
-    double shx = d_shift1(ci[0], cj[0], D.cellnum[0], D.box[0]);
-    double shy = d_shift1(ci[1], cj[1], D.cellnum[1], D.box[1]);
-    double shz = d_shift1(ci[2], cj[2], D.cellnum[2], D.box[2]);
+    double shx = d_shift1(ci[0], cj[0], D.cellnum[0], d_box(D, 0));
+    double shy = d_shift1(ci[1], cj[1], D.cellnum[1], d_box(D, 1));
+    double shz = d_shift1(ci[2], cj[2], D.cellnum[2], d_box(D, 2));
     return d_pair(d_rx(D, i), d_ry(D, i), d_rz(D, i), D.vx[i], D.vy[i], D.vz[i], d_rx(D, j), d_ry(D, j), d_rz(D, j), D.vx[j], D.vy[j], D.vz[j], shx, shy, shz);
 }
 // CalculateDisc :1092-1094 / CalculateTime :1096-1099
@@ -251,9 +253,9 @@ __device__ __forceinline__ int d_neighbor_cell(const DevP &D, int cx, int cy, in
 __device__ __forceinline__ int d_neighbor(const DevP &D, int cx, int cy, int cz, int k, double *shx, double *shy, double *shz) {
     int ncx, ncy, ncz;
     int cell = d_neighbor_cell(D, cx, cy, cz, k, &ncx, &ncy, &ncz);
-    *shx = d_shift1(cx, ncx, D.cellnum[0], D.box[0]);
-    *shy = d_shift1(cy, ncy, D.cellnum[1], D.box[1]);
-    *shz = d_shift1(cz, ncz, D.cellnum[2], D.box[2]);
+    *shx = d_shift1(cx, ncx, D.cellnum[0], d_box(D, 0));
+    *shy = d_shift1(cy, ncy, D.cellnum[1], d_box(D, 1));
+    *shz = d_shift1(cz, ncz, D.cellnum[2], d_box(D, 2));
     return cell;
 }
 
@@ -308,9 +310,9 @@ __device__ inline void d_collision_time(const DevP &D, const SlotSrc &S, Self &m
     for (int k = 0; k < 27; k++) {
         int ncx, ncy, ncz;
         int cell = d_neighbor_cell(D, me.cx, me.cy, me.cz, k, &ncx, &ncy, &ncz);
-        double shx = d_shift1(me.cx, ncx, D.cellnum[0], D.box[0]);
-        double shy = d_shift1(me.cy, ncy, D.cellnum[1], D.box[1]);
-        double shz = d_shift1(me.cz, ncz, D.cellnum[2], D.box[2]);
+        double shx = d_shift1(me.cx, ncx, D.cellnum[0], d_box(D, 0));
+        double shy = d_shift1(me.cy, ncy, D.cellnum[1], d_box(D, 1));
+        double shz = d_shift1(me.cz, ncz, D.cellnum[2], d_box(D, 2));
         for (int j = D.celllist[D.n + cell + 1]; j; j = D.celllist[j]) {
             if (j == me.i) continue;
             if (d_check_dup(D, S, cur, me.i, me.counter, j, SDMD_EV_COLI, dup_limit)) continue;
@@ -405,9 +407,9 @@ __device__ __forceinline__ void d_r0_flush(const DevP &D, const SlotSrc &S, Self
         if (seam) {
             int ncx, ncy, ncz;
             d_neighbor_cell(D, me.cx, me.cy, me.cz, k, &ncx, &ncy, &ncz);
-            shx = d_shift1(me.cx, ncx, D.cellnum[0], D.box[0]);
-            shy = d_shift1(me.cy, ncy, D.cellnum[1], D.box[1]);
-            shz = d_shift1(me.cz, ncz, D.cellnum[2], D.box[2]);
+            shx = d_shift1(me.cx, ncx, D.cellnum[0], d_box(D, 0));
+            shy = d_shift1(me.cy, ncy, D.cellnum[1], d_box(D, 1));
+            shz = d_shift1(me.cz, ncz, D.cellnum[2], d_box(D, 2));
         }
         int cm = has_cm ? d_cm_flags(D, me.i, j) : 0;
         if (surv_k[s] & R0_DUPFLAG) {
@@ -444,9 +446,9 @@ __device__ inline void d_collision_time_2stage(const DevP &D, const SlotSrc &S, 
     for (int k = 0; k < 27; k++) {
         int ncx, ncy, ncz;
         int cell = d_neighbor_cell(D, me.cx, me.cy, me.cz, k, &ncx, &ncy, &ncz);
-        double shx = d_shift1(me.cx, ncx, D.cellnum[0], D.box[0]);
-        double shy = d_shift1(me.cy, ncy, D.cellnum[1], D.box[1]);
-        double shz = d_shift1(me.cz, ncz, D.cellnum[2], D.box[2]);
+        double shx = d_shift1(me.cx, ncx, D.cellnum[0], d_box(D, 0));
+        double shy = d_shift1(me.cy, ncy, D.cellnum[1], d_box(D, 1));
+        double shz = d_shift1(me.cz, ncz, D.cellnum[2], d_box(D, 2));
         int p1 = D.cell_start[cell + 1];
         for (int p = D.cell_start[cell]; p < p1; p++) {
             int j = D.sorted_atom[p];
@@ -590,9 +592,9 @@ __device__ inline void d_collision_time_from_list(const DevP &D, const SlotSrc &
                 if (seam) {
                     int ncx, ncy, ncz;
                     d_neighbor_cell(D, me.cx, me.cy, me.cz, (int)(vc >> 27), &ncx, &ncy, &ncz);
-                    shx = d_shift1(me.cx, ncx, D.cellnum[0], D.box[0]);
-                    shy = d_shift1(me.cy, ncy, D.cellnum[1], D.box[1]);
-                    shz = d_shift1(me.cz, ncz, D.cellnum[2], D.box[2]);
+                    shx = d_shift1(me.cx, ncx, D.cellnum[0], d_box(D, 0));
+                    shy = d_shift1(me.cy, ncy, D.cellnum[1], d_box(D, 1));
+                    shz = d_shift1(me.cz, ncz, D.cellnum[2], d_box(D, 2));
                 }
                 int cm = has_cm ? d_cm_flags(D, i, j) : 0;
                 double t, pot;
@@ -820,12 +822,24 @@ __device__ inline void d_wall_time(const DevP &D, const Self &me, Slot &cur) {
     p.r2 = p.rx * p.rx + p.ry * p.ry + p.rz * p.rz;
     p.b = p.rx * vx + p.ry * vy + p.rz * vz;
     p.v2 = vx * vx + vy * vy + vz * vz;
-    double by = D.box[1];
-    double dist2 = by * by * 0.25 + p.r2 - by * sqrt(p.r2);                           // :667
     int idx = __ldg(&D.coll_index[me.type * SD_NT + D.wall_type]);
     if (idx < 0) { D.ctl->error = SDMD_ERR_TABLE; return; }
-    FindRes f = d_find_pair_table(D, &D.tables[idx], FP_COLLISION, -1 * p.b, dist2, 0, 0);
-    if (f.lowPot == 0 && f.upPot == 0) { D.ctl->error = SDMD_ERR_STATE; return; }    // "outside of the wall": exit() :675-702
+    double by;
+    FindRes f;
+    for (;;) {                                                                        // ReCal, :641
+        by = d_box(D, 1);
+        double dist2 = by * by * 0.25 + p.r2 - by * sqrt(p.r2);                       // :667
+        f = d_find_pair_table(D, &D.tables[idx], FP_COLLISION, -1 * p.b, dist2, 0, 0);
+        if (!(f.lowPot == 0 && f.upPot == 0)) break;
+        // outside of the wall: under a moving wall the box is pushed back out by one step and the prediction repeated (:675-697)
+        if (!D.wd_active) { D.ctl->error = SDMD_ERR_STATE; return; }                  // exit() :699-701
+        Ctl *c = D.ctl;
+        c->wd_touch++;
+        if (D.wall_kind == SDMD_WALL_PARALLEL) c->dbox[1] += D.wd_step;
+        else if (D.wall_kind == SDMD_WALL_CYLINDER) { c->dbox[1] += D.wd_step; c->dbox[2] += D.wd_step; }
+        else { c->dbox[0] += D.wd_step; c->dbox[1] += D.wd_step; c->dbox[2] += D.wd_step; }
+        if (c->dbox[1] > D.wd_orig_y) { c->error = SDMD_ERR_STATE; return; }          // "cannot be expanded beyond the original": exit() :691-694
+    }
     int s, sub;
     double d2, pot;
     if (p.b < 0 && d_disc(p, f.lower) > 0) {                                          // towards the centre :704-714
@@ -961,8 +975,8 @@ __device__ inline void d_charge_time(const DevP &D, const Self &me, Slot &cur) {
     int flag = 0;
     for (int cn = 0; cn < D.n_charge; cn++) {
         if (me.x > D.sb->chg_pos[cn][0] - SD_ZERO) continue;
-        if (D.sb->chg_pos[cn][0] < D.box[0]) flag = 1;                                   // :948-956
-        else if (!(flag == 0 && D.sb->chg_pos[cn][0] > D.box[0])) break;
+        if (D.sb->chg_pos[cn][0] < d_box(D, 0)) flag = 1;                                   // :948-956
+        else if (!(flag == 0 && D.sb->chg_pos[cn][0] > d_box(D, 0))) break;
         Pair p;
         p.rx = me.x - D.sb->chg_pos[cn][0]; p.ry = me.y - D.sb->chg_pos[cn][1]; p.rz = me.z - D.sb->chg_pos[cn][2];
         double vx = me.vx - D.sb->chg_vel[cn][0], vy = me.vy - D.sb->chg_vel[cn][1], vz = me.vz - D.sb->chg_vel[cn][2];
@@ -1157,9 +1171,9 @@ __device__ inline double d_hb_energy_change(const DevP &D, int i, int skipAtom, 
     for (int k = 0; k < 27; k++) {
         int ncx, ncy, ncz;
         int cell = d_neighbor_cell(D, cx, cy, cz, k, &ncx, &ncy, &ncz);
-        double shx = d_shift1(cx, ncx, D.cellnum[0], D.box[0]);
-        double shy = d_shift1(cy, ncy, D.cellnum[1], D.box[1]);
-        double shz = d_shift1(cz, ncz, D.cellnum[2], D.box[2]);
+        double shx = d_shift1(cx, ncx, D.cellnum[0], d_box(D, 0));
+        double shy = d_shift1(cy, ncy, D.cellnum[1], d_box(D, 1));
+        double shz = d_shift1(cz, ncz, D.cellnum[2], d_box(D, 2));
         for (int j = D.celllist[D.n + cell + 1]; j; j = D.celllist[j]) {
             if (j == i || j == skipAtom) continue;
             int cm = d_cm_flags(D, i, j);
@@ -1190,8 +1204,8 @@ __device__ inline void d_image_of(const DevP &D, int a, int b, double pos[3]) {
     for (int k = 0; k < 3; k++) {
         int ca = D.cell_idx[3 * a + k], cb = D.cell_idx[3 * b + k];
         if (ca != cb) {
-            if (ca == 0 && cb == D.cellnum[k] - 1) pos[k] -= D.box[k];
-            else if (ca == D.cellnum[k] - 1 && cb == 0) pos[k] += D.box[k];
+            if (ca == 0 && cb == D.cellnum[k] - 1) pos[k] -= d_box(D, k);
+            else if (ca == D.cellnum[k] - 1 && cb == 0) pos[k] += d_box(D, k);
         }
     }
 }
@@ -1490,8 +1504,8 @@ __device__ inline void d_pcc_event(const DevP &D, int i) {
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             if (!(D.pbc_mask >> k & 1)) continue;   // dimensions closed by a wall do not wrap, Events.c:210-216
-            if (co[k] >= D.box[k]) co[k] -= D.box[k];
-            else if (co[k] < 0) co[k] += D.box[k];
+            if (co[k] >= d_box(D, k)) co[k] -= d_box(D, k);
+            else if (co[k] < 0) co[k] += d_box(D, k);
         }
         D.x[i] = co[0]; D.y[i] = co[1]; D.z[i] = co[2];
     }
@@ -1710,9 +1724,9 @@ __device__ inline void d_pc_gather_warp(const DevP &D, PredShared &sh, int a) {
     if (lane < 27) {
         int ncx, ncy, ncz;
         cell = d_neighbor_cell(D, cx, cy, cz, lane, &ncx, &ncy, &ncz);
-        sh.shift[a][lane][0] = d_shift1(cx, ncx, D.cellnum[0], D.box[0]);
-        sh.shift[a][lane][1] = d_shift1(cy, ncy, D.cellnum[1], D.box[1]);
-        sh.shift[a][lane][2] = d_shift1(cz, ncz, D.cellnum[2], D.box[2]);
+        sh.shift[a][lane][0] = d_shift1(cx, ncx, D.cellnum[0], d_box(D, 0));
+        sh.shift[a][lane][1] = d_shift1(cy, ncy, D.cellnum[1], d_box(D, 1));
+        sh.shift[a][lane][2] = d_shift1(cz, ncz, D.cellnum[2], d_box(D, 2));
     }
     // valid while nothing in the 27-cell neighbourhood changed after the list was cached (and no new link list since)
     bool fresh = lane >= 27 || D.cell_epoch[cell] <= stamp;

@@ -48,6 +48,14 @@ static void sync_to_reference(void) {
     thermostateventsum = base_counts[5] + st.thermostat;
     pbcandcrosseventsum = base_counts[6] + st.pcc;
     walleventsum = base_counts[7] + st.wall;
+    if (strcmp(wallExist, "no")) {                /* moving wall: the box edges WallTime's retry may have changed, wallDyn.touch */
+        double box[3];
+        int32_t touch = 0;
+        if (sdmd_cuda_wall_dyn_state(ctx, box, &touch) == 0 && view.wall_dyn) {
+            for (int k = 0; k < 3; k++) boxDimension[k + 1] = box[k];
+            wallDyn.touch = touch;
+        }
+    }
     HBnumformed = (int)st.hb_num_formed;          /* what SaveHB prints (-HBn) and SaveDAT stores, DataSave.c:461-470, 573-574 */
     alphaHBformed = (int)st.alpha_hb_formed;
 }
@@ -107,6 +115,23 @@ static void save_outputs(void) {
     outputrecord += outputrate;
 }
 
+/* DoWallDyn() where SingleThreadRun calls it (SGThread.c:129): after the executed event that carried currenttime to wallDyn.curTime */
+static int wall_dyn_mode(void) {
+    return strcmp(wallDyn.mark, "compress") == 0 ? 1 : strcmp(wallDyn.mark, "expand") == 0 ? 2 : strcmp(wallDyn.mark, "pulse") == 0 ? 3 : 0;
+}
+static void wall_dyn_step(void) {
+    struct sdmd_wall_dyn wd;
+    memset(&wd, 0, sizeof(wd));
+    wd.mode = wall_dyn_mode(); wd.sign = wallDyn.sign; wd.touch = wallDyn.touch;
+    wd.size = wallDyn.size; wd.rate = wallDyn.rate; wd.step = wallDyn.step; wd.cur_time = wallDyn.curTime;
+    for (int k = 0; k < 3; k++) wd.orig_box[k] = wallDyn.origBoxDim[k + 1];
+    int rc = sdmd_cuda_wall_dyn_step(ctx, &wd);
+    if (rc) die("sdmd_cuda_wall_dyn_step", rc);
+    wallDyn.sign = wd.sign; wallDyn.touch = wd.touch; wallDyn.curTime = wd.cur_time;
+    for (int k = 0; k < 3; k++) boxDimension[k + 1] = wd.box[k];
+    if (wd.mode == 0) sprintf(wallDyn.mark, "no");
+}
+
 /* run to `boundary`; returns the stop reason once it is TIME_END or T_UNTIL */
 static int run_to(double boundary, struct sdmd_run_stats *st, double *gap) {
     const int64_t chunk = 200000;        /* gaussians generated ahead per refill */
@@ -130,7 +155,15 @@ void SingleThread(void) {
     struct sdmd_run_stats st;
     memset(&st, 0, sizeof(st));
     double gap = 0;
-    while (run_to(outputrecord, &st, &gap) == SDMD_STOP_T_UNTIL) save_outputs();   /* SGThread.c:132-139 */
+    for (;;) {
+        /* the next thing the host has to do: a dump (SGThread.c:132-139) or, under a moving wall, DoWallDyn (SGThread.c:129) */
+        int dyn = strcmp(wallDyn.mark, "no") != 0;
+        double boundary = (dyn && wallDyn.curTime < outputrecord) ? wallDyn.curTime : outputrecord;
+        int reason = run_to(boundary, &st, &gap);
+        if (dyn && currenttime >= wallDyn.curTime) wall_dyn_step();
+        if (reason != SDMD_STOP_T_UNTIL) break;
+        if (currenttime >= outputrecord) save_outputs();
+    }
     sync_to_reference();
     warningsum += st.warnings;
     sdmd_cuda_destroy(ctx);

@@ -148,7 +148,13 @@ int sdmd_glue_flatten(struct sdmd_host_view *v) {
     v->gel_mode = 1;
 #endif
     /* features that live outside the hot-path scope (rough / moving walls, obstacles, tunnels, flow, CG) */
-    if (CG.mark || strcmp(wallDyn.mark, "no")) return SDMD_ERR_UNSUPPORTED;
+    if (CG.mark) return SDMD_ERR_UNSUPPORTED;
+    if (strcmp(wallDyn.mark, "no")) {            /* moving wall: Initialization.c:1937-1978 has filled wallDyn */
+        v->wall_dyn = 1;
+        v->wall_dyn_touch = wallDyn.touch;
+        v->wall_dyn_step = wallDyn.step;
+        for (int k = 0; k < 3; k++) v->wall_dyn_orig_box[k] = wallDyn.origBoxDim[k + 1];
+    }
     if (flow.mark == 3) {
         int total = flow.charge.PBCMark ? flow.charge.num : flow.charge.num / 2;     /* TimePrediction.c:936 */
         if (total > SDMD_MAX_CHARGE) return SDMD_ERR_UNSUPPORTED;

@@ -13,7 +13,7 @@ from pathlib import Path
 
 import numpy as np
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_CHARGE = 8
 MAX_OBST = 4
 NT = 33
@@ -71,6 +71,7 @@ class CHostView(C.Structure):
         ("charge_pos", C.c_double * (3 * MAX_CHARGE)), ("charge_vel", C.c_double * (3 * MAX_CHARGE)),
         ("charge_potgrad", C.c_double * MAX_CHARGE), ("charge_gap", C.c_double * MAX_CHARGE),
         ("hb_name", _P(C.c_uint8)), ("hb_num_formed", C.c_int32), ("alpha_hb_formed", C.c_int32),
+        ("wall_dyn", C.c_int32), ("wall_dyn_touch", C.c_int32), ("wall_dyn_step", C.c_double), ("wall_dyn_orig_box", C.c_double * 3),
     ]
 
 

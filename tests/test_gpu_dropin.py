@@ -142,6 +142,39 @@ def test_dropin_walled_run_matches_reference(tmp_path, wall_type):
     assert _counter(outs["gpu"], "Wall times") > 0
 
 
+@pytest.mark.parametrize("mark", ["compress", "pulse", "expand"])
+def test_dropin_moving_wall_matches_reference(tmp_path, mark):
+    """"WallDyn compress | pulse | expand" (moving smooth wall: DoWallDyn Events.c:502-540 once per time unit, WallTime's retry
+    TimePrediction.c:675-697 when an atom is found outside): the drop-in driver writes the same trajectory — box edges in every
+    frame included — and the same counters as the stock binary."""
+    if not (REF / "sDMD_ref").exists() or not DROPIN.exists():
+        pytest.skip("needs oracle/_ref/sDMD_ref and the drop-in driver")
+    from oracle.make_golden import WALLS, prepare_input, write_multi_ala10
+    spec = WALLS["ala10x8_wallp"]
+    outs = {}
+    for tag, binary in (("ref", REF / "sDMD_ref"), ("gpu", DROPIN)):
+        work = tmp_path / tag
+        work.mkdir()
+        inp = prepare_input(work, time_units=80, wall_type=spec[0])
+        p = inp / "parameter.txt"
+        lines = p.read_text().splitlines()
+        lines[11] = "WallDyn            " + mark
+        p.write_text("\n".join(lines) + "\n")
+        write_multi_ala10(inp / "walled.gro", inp / "ala10.gro", copies_per_axis=spec[1], spacing_nm=spec[2], box_nm=spec[3])
+        r = subprocess.run([str(binary), "-f", "walled.gro", "-i", str(inp), "-o", str(work / "out"), "-Wsz", "5", "-Wrt", "20"],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs[tag] = r.stdout.replace("\r", "\n")
+    for name in ("out_trj.gro", "out_cnt.txt"):
+        a = (tmp_path / "ref" / "out" / name).read_bytes()
+        b = (tmp_path / "gpu" / "out" / name).read_bytes()
+        assert len(a) > 1000 and a == b, name
+    boxes = {ln for ln in (tmp_path / "gpu" / "out" / "out_trj.gro").read_text().splitlines() if len(ln.split()) == 3 and ln.startswith("   ")}
+    assert len(boxes) > (3 if mark != "expand" else 0), boxes          # the box really moved ("expand" from the original size ends after one step)
+    for key in ("collision times", "bond times", "thermostat times", "PBC&CC times", "Wall times"):
+        assert _counter(outs["ref"], key) == _counter(outs["gpu"], key), key
+
+
 @pytest.mark.parametrize("flow", ["velocity 0.02 0.0 0.01", "force 5.0 0.0 0.0", "charge 1 : 100.0 75.0 75.0 0.05 0.2"],
                          ids=["velocity", "force", "charge"])
 def test_dropin_flow_run_matches_reference(tmp_path, flow):
