@@ -213,7 +213,11 @@ void REMD(void) {
     double gap = 0;
     for (;;) {
         double boundary = outputrecord < rate ? outputrecord : (double)rate;
-        if (run_to(boundary, &st, &gap) != SDMD_STOP_T_UNTIL) break;
+        int dyn = strcmp(wallDyn.mark, "no") != 0;                       /* moving wall: DoWallDyn, REMD.c:85 */
+        if (dyn && wallDyn.curTime < boundary) boundary = wallDyn.curTime;
+        int reason = run_to(boundary, &st, &gap);
+        if (dyn && currenttime >= wallDyn.curTime) wall_dyn_step();
+        if (reason != SDMD_STOP_T_UNTIL) break;
         if (currenttime >= outputrecord) save_outputs();                 /* REMD.c:88-95 */
         if (currenttime >= rate) {                                       /* REMD.c:97-104 */
             double potenEnergy;
