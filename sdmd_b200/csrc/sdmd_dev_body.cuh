@@ -6,6 +6,17 @@ __device__ __forceinline__ double d_rx(const DevP &D, int j) { return d_lz(D, j)
 __device__ __forceinline__ double d_ry(const DevP &D, int j) { return d_lz(D, j) ? D.lz_y[j] + D.vy[j] * D.lz_dt : D.y[j]; }
 __device__ __forceinline__ double d_rz(const DevP &D, int j) { return d_lz(D, j) ? D.lz_z[j] + D.vz[j] * D.lz_dt : D.z[j]; }
 __device__ __forceinline__ double d_rt(const DevP &D, int j) { return d_lz(D, j) ? D.lz_t[j] - D.lz_dt : D.ev_time[j]; }
+__device__ __forceinline__ void d_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// everything the evaluation of a collision candidate reads of its partner, asked into this SM's L1 ahead of time
+__device__ __forceinline__ void d_prefetch_atom(const DevP &D, int j) {
+#if SDMD_LZ
+    if (D.lz_on) { d_prefetch_l1(&D.lz_x[j]); d_prefetch_l1(&D.lz_y[j]); d_prefetch_l1(&D.lz_z[j]); }
+    else
+#endif
+    { d_prefetch_l1(&D.x[j]); d_prefetch_l1(&D.y[j]); d_prefetch_l1(&D.z[j]); }
+    d_prefetch_l1(&D.vx[j]); d_prefetch_l1(&D.vy[j]); d_prefetch_l1(&D.vz[j]);
+    d_prefetch_l1(&D.ev_partner[j]); d_prefetch_l1(&D.ev_type[j]); d_prefetch_l1(&D.ev_pcounter[j]); d_prefetch_l1(&D.type[j]);
+}
 // box edge k: a kernel parameter, except under moving walls (WallDyn), where DoWallDyn and WallTime change it during the run
 __device__ __forceinline__ double d_box(const DevP &D, int k) { return D.wall_dyn ? D.ctl->dbox[k] : D.box[k]; }
 // event time of another atom's slot: the live slots go through d_rt, the relaxation buffers of Predict(all) do not
@@ -1762,6 +1773,9 @@ __device__ inline void d_pc_gather_warp(const DevP &D, PredShared &sh, int a) {
                     }
                     D.cc_j[w] = j; D.cc_k[w] = (unsigned char)lane; D.cc_pass[w] = pass;
                     w++;
+#if SDMD_LZ
+                    d_prefetch_atom(D, j);      // (large systems: see the end of this function)
+#endif
                 }
             }
             __syncwarp();
@@ -1829,6 +1843,14 @@ __device__ inline void d_pc_gather_warp(const DevP &D, PredShared &sh, int a) {
             sh.cj[p] = hp; sh.ckind[p] = CK_HBNE; sh.caux[p] = (unsigned char)n;
         }
     }
+#if SDMD_LZ
+    // Large systems: the state of the candidates sits in DRAM and the evaluation phase would meet it as two dependent round trips
+    // (list entry -> the partner's coordinates, velocities and slot).  The layout warp asks for all of it now, while thread 0 is still
+    // executing the event, so the evaluating threads find it in this SM's L1.
+    // (a list that had to be rebuilt above has asked for them entry by entry already)
+    if (hit)
+        for (int p = lane; p < ncoll; p += 32) d_prefetch_atom(D, D.cc_j[row * cap + p]);
+#endif
 }
 
 // ---- phase B: own-side evaluation of one candidate entry (any thread) ----
