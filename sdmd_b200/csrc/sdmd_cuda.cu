@@ -52,6 +52,8 @@ struct sdmd_ctx {
     int *bp_j = nullptr;
     int *cell_of = nullptr, *cell_count = nullptr, *cell_rank = nullptr, *cell_tmp = nullptr, *scan_tmp = nullptr;
     int n_draws = 0;
+    void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};   // grow-on-demand device buffers of the occasional calls (no cudaMalloc per call)
+    size_t scratch_bytes[4] = {0, 0, 0, 0};
     unsigned long long *scan_state = nullptr;      // single-pass scan of the cell histogram: one word per block of 2048 cells
     unsigned *scan_ticket = nullptr, scan_ticket_base = 0, scan_epoch = 0;
     int *d_cell_start = nullptr, *d_sorted_atom = nullptr;
@@ -95,6 +97,18 @@ static int dalloc(sdmd_ctx *c, T **p, size_t count) {
     if (e != cudaSuccess) return set_err(SDMD_ERR_CUDA, "cudaMemset", e);
     c->bufs.push_back(q);
     *p = (T *)q;
+    return 0;
+}
+// slot: 0 renew list / block sums, 1 energy addends, 2 replica descriptors, 3 per-replica results
+static int scratch_get(sdmd_ctx *c, int slot, size_t bytes, void **out) {
+    if (c->scratch_bytes[slot] < bytes) {
+        if (c->scratch[slot]) { cudaStreamSynchronize(c->stream); cudaFree(c->scratch[slot]); c->scratch[slot] = nullptr; c->scratch_bytes[slot] = 0; }
+        size_t want = bytes + bytes / 2 + 256;
+        cudaError_t e = cudaMalloc(&c->scratch[slot], want);
+        if (e != cudaSuccess) return set_err(SDMD_ERR_CUDA, "cudaMalloc (scratch)", e);
+        c->scratch_bytes[slot] = want;
+    }
+    *out = c->scratch[slot];
     return 0;
 }
 template <typename T>
@@ -1998,6 +2012,7 @@ void sdmd_cuda_destroy(sdmd_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (void *p : c->bufs) cudaFree(p);
+    for (int k = 0; k < 4; k++) if (c->scratch[k]) cudaFree(c->scratch[k]);
     if (c->d_trace) cudaFree(c->d_trace);
     remd_forget(c);
     if (c->d_xchg) cudaFree(c->d_xchg);
@@ -2417,13 +2432,12 @@ int sdmd_cuda_predict(sdmd_ctx *c, const int32_t *renew) {
     // the event loop only ever lists one or two atoms (SGThread.c:238-251); longer lists take the generic serial kernel
     if (cnt > 2) {
         int *d_list = nullptr;
-        CK(cudaMalloc((void **)&d_list, sizeof(int) * cnt));
+        TRY(scratch_get(c, 0, sizeof(int) * cnt, (void **)&d_list));
         CK(cudaMemcpyAsync(d_list, renew + 1, sizeof(int) * cnt, cudaMemcpyHostToDevice, c->stream));
         c->counters_known = false;
         k_predict_list_n<<<1, 1, 0, c->stream>>>(c->P, d_list, cnt);
         c->launches++;
         CK(cudaStreamSynchronize(c->stream));
-        cudaFree(d_list);
         CK(cudaGetLastError());
         return 0;
     }
@@ -2646,7 +2660,7 @@ int sdmd_cuda_potential_energy(sdmd_ctx *c, double *e) {
         int *off = c->pcount;                        // scratch int[n+1]
         int nb = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
         int *blk = nullptr;
-        CK(cudaMalloc((void **)&blk, ((size_t)nb + 2) * sizeof(int)));
+        TRY(scratch_get(c, 0, ((size_t)nb + 2) * sizeof(int), (void **)&blk));
         DevP Pq = c->P;
         Pq.ctl = c->d_ctl_scratch;      // the counting walk repeats the FindPair calls of the writing walk: its warnings go to the scratch block
         k_pe_count<<<grid_for(n, 128), 128, 0, c->stream>>>(Pq, cnt);
@@ -2657,14 +2671,12 @@ int sdmd_cuda_potential_energy(sdmd_ctx *c, double *e) {
         CK(cudaMemcpyAsync(&total, off + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         double *terms = nullptr;
-        CK(cudaMalloc((void **)&terms, ((size_t)total + 32) * sizeof(double)));
+        TRY(scratch_get(c, 1, ((size_t)total + 32) * sizeof(double), (void **)&terms));
         k_pe_write<<<grid_for(n, 128), 128, 0, c->stream>>>(c->P, off, terms);
         k_ordered_sum<<<1, 32, 0, c->stream>>>(terms, nullptr, total, d);
         c->launches += 6;
         CK(cudaMemcpyAsync(e, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        cudaFree(terms);
-        cudaFree(blk);
         return 0;
     }
     CK(cudaMemcpyAsync(e, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -2871,7 +2883,7 @@ int sdmd_cuda_run_many(sdmd_ctx **ctxs, int n, const double *t_until, int64_t ma
         args[k].iter_limit = (max_iter > (1LL << 61)) ? (1LL << 62) : c->h_ctl->iterations + max_iter;
     }
     MultiArg *d_args = nullptr;
-    CK(cudaMalloc((void **)&d_args, sizeof(MultiArg) * n));
+    TRY(scratch_get(c0, 2, sizeof(MultiArg) * n, (void **)&d_args));
     CK(cudaMemcpyAsync(d_args, args.data(), sizeof(MultiArg) * n, cudaMemcpyHostToDevice, c0->stream));
     cudaEventRecord(c0->ev0, c0->stream);
     for (int k = 0; k < n; k++) ctxs[k]->counters_known = false;
@@ -2892,7 +2904,6 @@ int sdmd_cuda_run_many(sdmd_ctx **ctxs, int n, const double *t_until, int64_t ma
     cudaEventElapsedTime(&ms, c0->ev0, c0->ev1);
     c0->kstat["run_many"].ms += ms;
     c0->kstat["run_many"].n++;
-    cudaFree(d_args);
     int rc = 0;
     for (int k = 0; k < n; k++) {
         TRY(pull_ctl(ctxs[k]));
@@ -2911,15 +2922,13 @@ int sdmd_cuda_potential_energy_many(sdmd_ctx **ctxs, int n, double *energy) {
     for (int k = 0; k < n; k++) { CK(cudaStreamSynchronize(ctxs[k]->stream)); args[k].P = ctxs[k]->P; args[k].t_until = 0; args[k].iter_limit = 0; }
     MultiArg *d_args = nullptr;
     double *d_out = nullptr;
-    CK(cudaMalloc((void **)&d_args, sizeof(MultiArg) * n));
-    CK(cudaMalloc((void **)&d_out, sizeof(double) * n));
+    TRY(scratch_get(c0, 2, sizeof(MultiArg) * n, (void **)&d_args));
+    TRY(scratch_get(c0, 3, sizeof(double) * n, (void **)&d_out));
     CK(cudaMemcpyAsync(d_args, args.data(), sizeof(MultiArg) * n, cudaMemcpyHostToDevice, c0->stream));
     k_potential_energy_multi<<<n, 128, 0, c0->stream>>>(d_args, d_out);
     c0->launches++;
     CK(cudaMemcpyAsync(energy, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, c0->stream));
     CK(cudaStreamSynchronize(c0->stream));
-    cudaFree(d_args);
-    cudaFree(d_out);
     return 0;
 }
 
