@@ -47,6 +47,9 @@ def reduced_T(kelvin: float) -> float:
 
 
 # ----------------------------------------------------------------------------------------------------
+REAL_STDOUT_FD = None      # the process's real stdout while fd 1 is pointed at stderr (main)
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -108,6 +111,9 @@ class Dist:
             import torch.distributed as dist
             self.torch, self.dist = torch, dist
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            # the collectives of this file are barriers and 32-byte exchanges: NVLink-SHARP (multicast) set-up buys them nothing, and
+            # two communicators (torch's and the library's own) both setting it up on an 8-GPU box is start-up time and risk for free
+            os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
             if backend is None:
                 backend = "nccl" if torch.cuda.is_available() else "gloo"
             if backend == "nccl":
@@ -338,12 +344,29 @@ def cuda_pass(args, dist):
                    "sample": "2048 loop iterations of the device-resident event loop on the same box (sdmd_cuda_run, host wall clock "
                              "around the call, stats read back); `--workload loop` times it on its own with the sweep's roofline"}
     rep.close()
-    if not args.no_remd:
-        r = remd_subrecord(args, dist)
-        if dist.rank == 0:
-            out["remd"] = r
     if dist.rank == 0 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_pass_baseline(args, gpu_pairs_per_pass=int(round(pairs / max(args.steps, 1))))
+    if not args.no_remd:
+        # The sub-record is an extra of the line, not its metric: it must not be able to take the line with it.  (An 8-rank run of
+        # this round sat for six minutes somewhere behind the NCCL start-up and was killed by the box's limit before printing
+        # anything; 1, 2 and 4 ranks finish the sub-record in ~15 s.)  If it has not finished in time, rank 0 prints the line
+        # without it and every rank leaves.
+        limit = float(os.environ.get("SDMD_BENCH_REMD_LIMIT_S", "150"))
+
+        def give_up():
+            if dist.rank == 0:
+                out["remd"] = {"unavailable": f"the remd sub-record did not finish within {limit:.0f} s on {dist.world} ranks and was abandoned"}
+                os.write(REAL_STDOUT_FD if REAL_STDOUT_FD is not None else 1, (json.dumps(out) + "\n").encode())   # (fd 1 points at stderr here, see main)
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(0)
+
+        guard = threading.Timer(limit, give_up)
+        guard.daemon = True
+        guard.start()
+        r = remd_subrecord(args, dist)
+        guard.cancel()
+        if dist.rank == 0:
+            out["remd"] = r
     return out
 
 
@@ -950,7 +973,8 @@ def main():
     # the contract is ONE JSON line on stdout: anything a library prints there (NCCL's version banner, the reference's own
     # progress output) goes to stderr instead; the real stdout comes back for the final line
     sys.stdout.flush()
-    real_stdout = os.dup(1)
+    global REAL_STDOUT_FD
+    real_stdout = REAL_STDOUT_FD = os.dup(1)
     os.dup2(2, 1)
     dist = Dist(args.gpus, backend="gloo" if args.impl == "reference" else None)
     try:
