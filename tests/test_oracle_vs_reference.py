@@ -4,8 +4,14 @@ The committed fixtures under tests/golden/ were produced by oracle/make_golden.p
 itself (oracle/_ref/ref_harness).  When the compiled reference is present the longest case is also
 re-generated on this machine and compared, so the pin does not depend on the fixtures alone.
 """
+import os
+
 import numpy as np
 import pytest
+
+# the live harness runs of this module flatten the reference's globals through the glue (sdmd_refglue.c): have it cross-check its
+# sparse connection rows against the dense connectionMap scan every time
+os.environ["SDMD_GLUE_CHECK_CM"] = "1"
 
 from oracle.oracle_py import Oracle, remd_rearrange
 from tests.util import (REFDIR, SLOT_FIELDS, STATE_FIELDS, assert_fields_equal, assert_trace_equal, bits_equal,
