@@ -50,6 +50,27 @@ def reduced_T(kelvin: float) -> float:
 REAL_STDOUT_FD = None      # the process's real stdout while fd 1 is pointed at stderr (main)
 
 
+def run_guarded(fn, limit_s, line, key, why):
+    """Run `fn()`; if it has not returned after `limit_s` seconds, print `line` (the bench line built so far, rank 0 only; None on
+    the other ranks) with `line[key] = {"unavailable": why}` on the process's real stdout and leave the process with exit code 0."""
+    def give_up():
+        if line is not None:
+            line[key] = {"unavailable": why}
+            os.write(REAL_STDOUT_FD if REAL_STDOUT_FD is not None else 1, (json.dumps(line) + "\n").encode())   # (fd 1 may point at stderr, see main)
+        try:
+            sys.stdout.flush(); sys.stderr.flush()
+        finally:
+            os._exit(0)
+
+    guard = threading.Timer(limit_s, give_up)
+    guard.daemon = True
+    guard.start()
+    try:
+        return fn()
+    finally:
+        guard.cancel()
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -352,19 +373,8 @@ def cuda_pass(args, dist):
         # anything; 1, 2 and 4 ranks finish the sub-record in ~15 s.)  If it has not finished in time, rank 0 prints the line
         # without it and every rank leaves.
         limit = float(os.environ.get("SDMD_BENCH_REMD_LIMIT_S", "150"))
-
-        def give_up():
-            if dist.rank == 0:
-                out["remd"] = {"unavailable": f"the remd sub-record did not finish within {limit:.0f} s on {dist.world} ranks and was abandoned"}
-                os.write(REAL_STDOUT_FD if REAL_STDOUT_FD is not None else 1, (json.dumps(out) + "\n").encode())   # (fd 1 points at stderr here, see main)
-            sys.stdout.flush(); sys.stderr.flush()
-            os._exit(0)
-
-        guard = threading.Timer(limit, give_up)
-        guard.daemon = True
-        guard.start()
-        r = remd_subrecord(args, dist)
-        guard.cancel()
+        r = run_guarded(lambda: remd_subrecord(args, dist), limit, out if dist.rank == 0 else None, "remd",
+                        f"the remd sub-record did not finish within {limit:.0f} s on {dist.world} ranks and was abandoned")
         if dist.rank == 0:
             out["remd"] = r
     return out

@@ -64,3 +64,29 @@ def test_remd_rearrange_matches_oracle(lib_path):
             T[int(rng.integers(n))] = 0.0  # a finished replica
         u = rng.uniform(0, 1, 2 * n + 2)
         assert capi.remd_rearrange(e, nums, T, u) == oracle_rr(e, nums, T, u)
+
+
+def test_bench_guard_prints_the_line_and_leaves(tmp_path):
+    """bench.run_guarded: a sub-record that does not come back must not take the bench line with it — the line is printed on the
+    real stdout with the sub-record marked unavailable, exit code 0; a sub-record that does come back is returned untouched."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    prog = (
+        "import os, sys, time, json\n"
+        f"sys.path.insert(0, {str(root)!r})\n"
+        "import bench\n"
+        "bench.REAL_STDOUT_FD = os.dup(1)\n"
+        "os.dup2(2, 1)\n"                                      # like bench.main: library chatter goes to stderr
+        "line = {'metric': 'm', 'value': 1.0}\n"
+        "assert bench.run_guarded(lambda: {'ok': 1}, 5.0, line, 'remd', 'late') == {'ok': 1}\n"
+        "bench.run_guarded(lambda: time.sleep(30), 0.3, line, 'remd', 'did not finish')\n"
+        "os.write(bench.REAL_STDOUT_FD, b'NOT REACHED\\n')\n")
+    r = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["value"] == 1.0 and d["remd"] == {"unavailable": "did not finish"}
