@@ -68,7 +68,10 @@ CASES = {
 # "Flow" line of parameter.txt: constant drift velocity (A per time unit) / constant force (pN)
 FLOWS = {"ala10_flowv": "velocity 0.02 0.0 0.01", "ala10_flowf": "force 5.0 0.0 0.0",
          "ala10_charge": "charge 1 : 100.0 75.0 75.0 0.05 0.2"}
-SDMD_ARGS = {"ala10_charge": ["-COM"]}      # extra command-line switches of the reference
+SDMD_ARGS = {"ala10_charge": ["-COM"],      # extra command-line switches of the reference
+             "ala10x8_wallp_compress": ["-Wsz", "5", "-Wrt", "4"], "ala10x8_wallp_pulse": ["-Wsz", "2", "-Wrt", "3"]}
+# moving smooth wall ("WallDyn" line of parameter.txt; the wall travels -Wsz A in -Wrt time units): live cases only
+WALLDYN = {"ala10x8_wallp_compress": "compress", "ala10x8_wallp_pulse": "pulse"}
 # name: (single-chain .gro under tests/golden, chains per axis, spacing nm, box nm); abeta64 = SURVEY 8d C3 (live tests only)
 PEPTIDES = {
     "abeta8": ("abeta16_22.gro", (2, 2, 2), 2.0, (6.0, 6.0, 6.0)),
@@ -77,6 +80,8 @@ PEPTIDES = {
 # name: (WallType, chains per axis, spacing nm, box nm[, "Obstruct?" value, "SphObst?" value])
 WALLS = {
     "ala10x8_wallp": ("parallel", (2, 2, 2), 1.9, (5.0, 3.8, 5.0)),
+    "ala10x8_wallp_compress": ("parallel", (2, 2, 2), 1.9, (5.0, 3.8, 5.0)),
+    "ala10x8_wallp_pulse": ("parallel", (2, 2, 2), 1.9, (5.0, 3.8, 5.0)),
     "ala10x4_wallc": ("cylinder", (4, 1, 1), 2.0, (8.0, 2.6, 2.6)),
     # two flat obstruction walls normal to y (1.5 A inside the periodic box faces) and three hard spheres of diameter 5 A,
     # each 0.4 A off the outermost atom of a chain (positions in A, parameter.txt lines 14 and 16); no smooth wall
@@ -131,7 +136,7 @@ def write_multi_ala10(path: Path, src: Path, copies_per_axis=2, spacing_nm: floa
 
 
 def prepare_input(work: Path, time_units: float = 1000.0, wall_type: str | None = None, obst: str | None = None,
-                  sphobst: str | None = None, tunnel: str | None = None, flow: str | None = None) -> Path:
+                  sphobst: str | None = None, tunnel: str | None = None, flow: str | None = None, wall_dyn: str | None = None) -> Path:
     """Writable copy of the reference input directory with the run length (and a smooth wall) set."""
     src = REFDIR / "input"
     if not src.exists():
@@ -146,6 +151,8 @@ def prepare_input(work: Path, time_units: float = 1000.0, wall_type: str | None 
     if wall_type:
         lines[9] = "WallExist?         smooth"
         lines[10] = "WallType           %s" % wall_type
+    if wall_dyn:
+        lines[11] = "WallDyn            %s" % wall_dyn
     if obst:
         lines[13] = "Obstruct?          %s" % obst
     if sphobst:
@@ -171,7 +178,7 @@ def run_case(name: str, work: Path, harness=None, coord=None, max_iter=None, n_g
     wall = WALLS.get(name)
     inp = prepare_input(work, wall_type=wall[0] if wall else None, obst=wall[4] if wall and len(wall) > 4 else None,
                         sphobst=wall[5] if wall and len(wall) > 5 else None, tunnel=wall[6] if wall and len(wall) > 6 else None,
-                        flow=FLOWS.get(name))
+                        flow=FLOWS.get(name), wall_dyn=WALLDYN.get(name))
     if wall:
         write_multi_ala10(inp / coord, inp / "ala10.gro", copies_per_axis=wall[1], spacing_nm=wall[2], box_nm=wall[3])
     elif name in PEPTIDES:

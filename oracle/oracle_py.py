@@ -16,6 +16,12 @@ HERE = Path(__file__).resolve().parent
 _lib = None
 
 
+class CWallDyn(C.Structure):      # struct sdmd_wall_dyn (include/sdmd_cuda.h): the reference's wallDyn fields + the box edges
+    _fields_ = [("mode", C.c_int32), ("sign", C.c_int32), ("touch", C.c_int32), ("pad_", C.c_int32),
+                ("size", C.c_double), ("rate", C.c_double), ("step", C.c_double), ("cur_time", C.c_double),
+                ("orig_box", C.c_double * 3), ("box", C.c_double * 3)]
+
+
 def build(force: bool = False) -> Path:
     so = HERE / "liboracle.so"
     src = HERE / "sdmd_oracle.c"
@@ -55,6 +61,10 @@ def lib():
         L.oracle_kinetic_energy.argtypes = [vp]
         L.oracle_get_stats.argtypes = [vp, C.POINTER(CRunStats)]
         L.oracle_set_temperature.argtypes = [vp, C.c_double]
+        L.oracle_set_wall_dyn.argtypes = [vp, C.POINTER(CWallDyn)]
+        L.oracle_set_wall_dyn.restype = None
+        L.oracle_get_wall_dyn.argtypes = [vp, C.POINTER(CWallDyn)]
+        L.oracle_get_wall_dyn.restype = None
         L.oracle_remd_rearrange.restype = C.c_int
         L.oracle_remd_rearrange.argtypes = [C.POINTER(C.c_double), C.POINTER(CRemdTemp), C.c_int, C.POINTER(C.c_double),
                                             C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -78,6 +88,19 @@ class Oracle:
         self.cellnum = np.array(cn[:], dtype=np.int32)
         self.cellsize = np.array(cs[:])
         self.ncell = int(np.prod(self.cellnum))
+        if "wall_dyn_i4" in hv.extra and int(hv.extra["wall_dyn_i4"][0]):      # moving wall: wallDyn.* as the reference harness dumped it
+            wi, wf = hv.extra["wall_dyn_i4"], hv.extra["wall_dyn_f8"]
+            self.set_wall_dyn(int(wi[0]), int(wi[1]), int(wi[2]), *(float(v) for v in wf[:4]), [float(v) for v in wf[4:7]])
+
+    def set_wall_dyn(self, mode, sign, touch, size, rate, step, cur_time, orig_box):
+        wd = CWallDyn(mode=mode, sign=sign, touch=touch, size=size, rate=rate, step=step, cur_time=cur_time)
+        wd.orig_box[:] = orig_box
+        self.L.oracle_set_wall_dyn(self.h, C.byref(wd))
+
+    def wall_dyn(self) -> dict:
+        wd = CWallDyn()
+        self.L.oracle_get_wall_dyn(self.h, C.byref(wd))
+        return {"mode": wd.mode, "sign": wd.sign, "touch": wd.touch, "cur_time": wd.cur_time, "box": list(wd.box)}
 
     def close(self):
         if self.h:

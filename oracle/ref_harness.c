@@ -88,6 +88,7 @@ static long run_loop(long max_iter, struct sdmd_trace_rec *trace, int printf_log
             if (renewList[0] == 2 && strcmp(partner->property->extraProperty[1], "_CONS")) partner->dynamic->event.counter++;
             Predict(renewList, thisList);
             UpdateCBT(renewList);
+            if (strcmp(wallDyn.mark, "no")) DoWallDyn();                                  /* SGThread.c:129 */
         } else {
             if (printf_log) printf(", denied, self/partner changed!\n");
             renewList[0] = 1;
@@ -99,6 +100,17 @@ static long run_loop(long max_iter, struct sdmd_trace_rec *trace, int printf_log
         }
     }
     return iter;
+}
+
+void DoWallDyn(void);
+/* moving wall: wallDyn.* and the current box edges next to the view */
+static void put_wall_dyn(sdmd_snap *s) {
+    int32_t wi[3] = {strcmp(wallDyn.mark, "compress") == 0 ? 1 : strcmp(wallDyn.mark, "expand") == 0 ? 2 : strcmp(wallDyn.mark, "pulse") == 0 ? 3 : 0,
+                     wallDyn.sign, wallDyn.touch};
+    double wf[10] = {wallDyn.size, wallDyn.rate, wallDyn.step, wallDyn.curTime, wallDyn.origBoxDim[1], wallDyn.origBoxDim[2], wallDyn.origBoxDim[3],
+                     boxDimension[1], boxDimension[2], boxDimension[3]};
+    sdmd_snap_put(s, "wall_dyn_i4", "i4", wi, 3);
+    sdmd_snap_put(s, "wall_dyn_f8", "f8", wf, 10);
 }
 
 int main(int argc, const char *argv[]) {
@@ -160,6 +172,7 @@ int main(int argc, const char *argv[]) {
     sdmd_snap *s = sdmd_snap_open(path);
     sdmd_snap_put_view(s, &view);
     put_cbt_and_cells(s);
+    put_wall_dyn(s);
     sdmd_snap_put(s, "gauss", "f8", gauss, n_gauss);
     sdmd_snap_put(s, "warm", "i4", &warm_flag, 1);
     sdmd_snap_close(s);
@@ -193,6 +206,7 @@ int main(int argc, const char *argv[]) {
     s = sdmd_snap_open(path);
     sdmd_snap_put_view(s, &view);
     put_cbt_and_cells(s);
+    put_wall_dyn(s);
     sdmd_snap_put(s, "trace", "u1", trace, (uint64_t)iter * sizeof(*trace));
     int64_t stats[12] = {frame, iter, countReCal - recal0, collisioneventsum - base[0], bondeventsum - base[1],
                          HBeventsum - base[2], HBNeighboreventsum - base[3], thermostateventsum - base[4],

@@ -40,6 +40,7 @@ struct oracle_ctx {
     int64_t g_n, g_cap, g_pos;
     struct sdmd_run_stats st;
     int hbnumformed;
+    struct sdmd_wall_dyn wd; /* moving wall (wallDyn.*); wd.mode == 0: none */
     int target, partner; /* AssignJob result */
     double time_inr;
 };
@@ -603,12 +604,22 @@ static void wall_time(oracle_ctx *c, int i) {
     p.r_2 = p.r_ij[0] * p.r_ij[0] + p.r_ij[1] * p.r_ij[1] + p.r_ij[2] * p.r_ij[2];
     p.b_ij = p.r_ij[0] * p.v_ij[0] + p.r_ij[1] * p.v_ij[1] + p.r_ij[2] * p.v_ij[2];
     p.v_2 = p.v_ij[0] * p.v_ij[0] + p.v_ij[1] * p.v_ij[1] + p.v_ij[2] * p.v_ij[2];
-    double by = v->box[1];
-    double distance2 = by * by * 0.25 + p.r_2 - by * sqrt(p.r_2);                      /* :667 */
-    double accum;
-    p.coreorShell = find_pair(c, i, -1, FP_COLLISION, -1 * p.b_ij, distance2, &p.shortlimit2, &p.longlimit2,
-                              &p.lowerPotential, &p.upperPotential, &accum, 0, 0);
-    if (p.lowerPotential == 0 && p.upperPotential == 0) { c->st.error = SDMD_ERR_STATE; return; }   /* :675-702 exit() */
+    double by, accum;
+    for (;;) {                                                                           /* ReCal, :641 */
+        by = v->box[1];
+        double distance2 = by * by * 0.25 + p.r_2 - by * sqrt(p.r_2);                  /* :667 */
+        p.coreorShell = find_pair(c, i, -1, FP_COLLISION, -1 * p.b_ij, distance2, &p.shortlimit2, &p.longlimit2,
+                                  &p.lowerPotential, &p.upperPotential, &accum, 0, 0);
+        if (!(p.lowerPotential == 0 && p.upperPotential == 0)) break;
+        if (!c->wd.mode) { c->st.error = SDMD_ERR_STATE; return; }                       /* :699-701 exit() */
+        /* moving wall: the atom is outside -> the box is pushed back out by one step and the prediction repeated, :678-697 */
+        double *box = c->v->box;
+        c->wd.touch++;
+        if (v->wall_kind == SDMD_WALL_PARALLEL) box[1] += c->wd.step;
+        else if (v->wall_kind == SDMD_WALL_CYLINDER) { box[1] += c->wd.step; box[2] += c->wd.step; }
+        else { box[0] += c->wd.step; box[1] += c->wd.step; box[2] += c->wd.step; }
+        if (box[1] > c->wd.orig_box[1]) { c->st.error = SDMD_ERR_STATE; return; }        /* :691-694 exit() */
+    }
     if (p.b_ij < 0 && calc_disc(&p) > 0) {                                               /* towards the centre :704-714 */
         if (p.coreorShell == 1) return;
         ev.sub = SDMD_SUB_TBDCAPTR;
@@ -1241,6 +1252,38 @@ static void do_event(oracle_ctx *c, int i, int j) {
 }
 
 /* SingleThreadRun, SGThread.c:67-156 */
+/* moving wall: wallDyn.* of the reference; box edges are the host view's box[] */
+void oracle_set_wall_dyn(oracle_ctx *c, const struct sdmd_wall_dyn *wd) { c->wd = *wd; }
+void oracle_get_wall_dyn(const oracle_ctx *c, struct sdmd_wall_dyn *wd) {
+    *wd = c->wd;
+    for (int k = 0; k < 3; k++) wd->box[k] = c->v->box[k];
+}
+/* DoWallDyn, Events.c:502-540 */
+static void do_wall_dyn(oracle_ctx *c) {
+    struct sdmd_host_view *v = c->v;
+    struct sdmd_wall_dyn *wd = &c->wd;
+    double *box = v->box;
+    const double currenttime = c->st.currenttime;
+    if (!(currenttime >= wd->cur_time)) return;
+    if (wd->mode == 3) {                                                                  /* "pulse", :504-514 */
+        if ((wd->orig_box[1] - box[1] >= wd->size) || (wd->orig_box[1] == box[1])) {
+            wd->sign *= -1;
+            wd->touch = 0;
+        } else if (fabs(box[1] + (int)(currenttime / wd->rate + 1) * wd->size - (currenttime - 1) * wd->step - wd->orig_box[1]) <= wd->step &&
+                   wd->touch >= 5) {
+            wd->sign *= -1;
+            wd->touch = 0;
+        }
+    }
+    wd->cur_time += 1;
+    if (v->wall_kind == SDMD_WALL_PARALLEL) box[1] += wd->sign * wd->step;                /* :518-527 */
+    else if (v->wall_kind == SDMD_WALL_CYLINDER) { box[1] += wd->sign * wd->step; box[2] += wd->sign * wd->step; }
+    else { box[0] += wd->sign * wd->step; box[1] += wd->sign * wd->step; box[2] += wd->sign * wd->step; }
+    for (int i = 1; i <= c->n; i++)                                                       /* :529-533 */
+        if (v->ev_type[i] == SDMD_EV_WALL) v->ev_counter[i]++;
+    if (((wd->orig_box[1] - box[1] >= wd->size) && wd->mode == 1) || ((wd->orig_box[1] - box[1] <= wd->step) && wd->mode == 2)) wd->mode = 0;   /* :535-538 */
+}
+
 int oracle_run(oracle_ctx *c, double t_until, int64_t max_iter, struct sdmd_trace_rec *trace, int64_t trace_cap,
                struct sdmd_run_stats *stats) {
     struct sdmd_host_view *v = c->v;
@@ -1273,6 +1316,7 @@ int oracle_run(oracle_ctx *c, double t_until, int64_t max_iter, struct sdmd_trac
             if (partner && !v->is_cons[partner]) v->ev_counter[partner]++;
             oracle_predict(c, renew);
             oracle_cbt_update(c, renew);
+            if (c->wd.mode) do_wall_dyn(c);                                              /* SGThread.c:129 */
             if (c->st.currenttime >= t_until) { c->st.stop_reason = SDMD_STOP_T_UNTIL; break; }
         } else {
             renew[0] = 1; renew[2] = 0; renew[3] = 0;

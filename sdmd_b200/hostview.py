@@ -171,6 +171,10 @@ class HostView:
         self.flow_mark = 0          # 0 none, 1 constant drift velocity, 2 constant force
         self.flow_v = np.zeros(3)
         self.charge_com = 0
+        self.wall_dyn = 0           # moving wall (WallDyn): on / wallDyn.touch / wallDyn.step / wallDyn.origBoxDim
+        self.wall_dyn_touch = 0
+        self.wall_dyn_step = 0.0
+        self.wall_dyn_orig_box = np.zeros(3)
         self.hb_num_formed = 0      # HBnumformed / alphaHBformed at the start of the run
         self.alpha_hb_formed = 0
         self.charge_src = np.zeros((0, 8))   # per charge source: position (3), velocity (3), potential gradient, gap
@@ -215,6 +219,12 @@ class HostView:
                 setattr(hv, name, np.ascontiguousarray(d[name], dtype=_NP[dt]).copy())
         if "hb_i4" in d:
             hv.hb_num_formed, hv.alpha_hb_formed = (int(v) for v in d["hb_i4"][:2])
+        if "wall_dyn_i4" in d:      # (written by oracle/ref_harness.c; the arrays also stay in `extra` for Oracle.set_wall_dyn)
+            wi, wf = d["wall_dyn_i4"], d["wall_dyn_f8"]
+            hv.wall_dyn = int(wi[0] != 0)
+            hv.wall_dyn_touch = int(wi[2])
+            hv.wall_dyn_step = float(wf[2])
+            hv.wall_dyn_orig_box = np.asarray(wf[4:7], dtype=np.float64).copy()
         if "flow_f8" in d:
             hv.flow_mark = int(d["flow_i4"][0])
             hv.flow_v = np.asarray(d["flow_f8"], dtype=np.float64)[:3].copy()
@@ -304,6 +314,8 @@ class HostView:
             c.sphobst_radius[k] = float(v)
         c.flow_mark = int(self.flow_mark)
         c.hb_num_formed, c.alpha_hb_formed = int(self.hb_num_formed), int(self.alpha_hb_formed)
+        c.wall_dyn, c.wall_dyn_touch, c.wall_dyn_step = int(self.wall_dyn), int(self.wall_dyn_touch), float(self.wall_dyn_step)
+        c.wall_dyn_orig_box[:] = [float(v) for v in self.wall_dyn_orig_box]
         cs = np.asarray(self.charge_src, dtype=np.float64).reshape(-1, 8)
         assert len(cs) <= MAX_CHARGE
         c.n_charge, c.charge_com = len(cs), int(self.charge_com)
@@ -335,6 +347,7 @@ class HostView:
 
     def sync_scalars_from_c(self):
         if self._c is not None:
+            self.box = np.array(self._c.box[:], dtype=np.float64)      # (a moving wall changes the box edges)
             self.currenttime = self._c.currenttime
             self.frame = self._c.frame
             self.target_temperature = self._c.target_temperature

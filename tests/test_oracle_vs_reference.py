@@ -272,3 +272,35 @@ def test_remd_rearrange_rule():
     # a finished replica (T == 0) is skipped entirely
     nums3, _, used3, _, _ = remd_rearrange([-10.0, 0.0, -30.0], [1, 2, 3], [0.5, 0.0, 0.7], [0.5])
     assert nums3 == [1, 2, 3] and used3 == 0
+
+
+@pytest.mark.refbin
+@pytest.mark.parametrize("case", ["ala10x8_wallp_compress", "ala10x8_wallp_pulse"])
+def test_moving_wall_against_live_reference(tmp_path, case):
+    """"WallDyn compress" / "WallDyn pulse" (8 ala10 chains between smooth plates that move): DoWallDyn (Events.c:502-540) once per
+    time unit inside the loop, WallTime's retry (TimePrediction.c:675-697) when an atom ends up outside — event trace, final
+    state, final box edges and wallDyn bookkeeping of the oracle against the reference harness run here."""
+    if not (REFDIR / "ref_harness").exists():
+        pytest.skip("oracle/_ref/ref_harness not built (needs /root/reference at build time)")
+    from oracle.make_golden import run_case
+    from sdmd_b200.hostview import HostView
+    snaps = run_case(case, tmp_path, harness="ref_harness", coord="ala10x8w.gro", max_iter=40000, n_gauss=200000, extra=[], gel_n=-8)
+    pre, post, fin = (HostView.from_snapshot(p) for p in snaps)
+    assert pre.wall_dyn == 1 and pre.extra["wall_dyn_i4"][0] in (1, 3)
+    hv, o = _prepare(pre)
+    o.pbc_full(); o.cell_build()
+    o.predict_all()
+    assert_fields_equal(hv, post, SLOT_FIELDS, what="after Predict(all): ")
+    o.cbt_build()
+    want = ref_trace(fin)
+    st, tr = o.run(max_iter=len(want), trace_cap=len(want))
+    assert_trace_equal(tr, want)
+    assert_fields_equal(hv, fin, STATE_FIELDS)
+    wd = o.wall_dyn()
+    wi, wf = fin.extra["wall_dyn_i4"], fin.extra["wall_dyn_f8"]
+    assert bits_equal(np.array(wd["box"]), np.asarray(wf[7:10]))                # boxDimension after the run
+    assert (wd["mode"], wd["sign"], wd["touch"]) == tuple(int(v) for v in wi[:3]) and wd["cur_time"] == float(wf[3])
+    moved = abs(wf[8] - pre.extra["wall_dyn_f8"][8])
+    # DoWallDyn ran several times, the wall was hit, and either it travelled or WallTime's retry pushed it back out (the chains fill
+    # the slit, so a compression step of 1.25 A leaves atoms outside: every step is undone by a retry, touch counts them)
+    assert wd["cur_time"] >= 3 and st["wall"] > 0 and (moved > 0.5 or wd["touch"] > 0), (wd, moved, st["wall"])
