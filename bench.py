@@ -50,6 +50,17 @@ def reduced_T(kelvin: float) -> float:
 REAL_STDOUT_FD = None      # the process's real stdout while fd 1 is pointed at stderr (main)
 
 
+def ensure_built(capi, dist):
+    """The shared library is built by __graft_entry__.build() and travels with the tree; a bench rank never recompiles behind the
+    back of the others (time stamps of a copied tree are no basis for N ranks to start N nvcc runs on one box).  Only when the
+    library is missing does local rank 0 build it, the others wait."""
+    if capi.LIB_PATH.exists() and os.environ.get("SDMD_BENCH_BUILD", "") != "1":
+        return
+    if dist.local_rank == 0:
+        capi.build()
+    dist.barrier()
+
+
 def run_guarded(fn, limit_s, line, key, why):
     """Run `fn()`; if it has not returned after `limit_s` seconds, print `line` (the bench line built so far, rank 0 only; None on
     the other ranks) with `line[key] = {"unavailable": why}` on the process's real stdout and leave the process with exit code 0."""
@@ -77,14 +88,19 @@ class ClockSampler(threading.Thread):
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, active: bool = True):
         super().__init__(daemon=True)
         self.gpu = gpu_index
         self.samples = []
         self.stop_flag = threading.Event()
         self.proc = None
+        # only the rank that prints the line samples: one nvidia-smi loop per box, not one per rank (every query takes the
+        # driver's global lock; eight of them polling at 100 ms on an 8-GPU board are a load on every CUDA call of every rank)
+        self.active = active
 
     def run(self):
+        if not self.active:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
@@ -202,7 +218,7 @@ def make_box(n_axis, rank):
 
 def cuda_pass(args, dist):
     from sdmd_b200 import capi
-    capi.build()
+    ensure_built(capi, dist)
     n_axis = args.n_axis
     hv, gauss = make_box(n_axis, dist.rank)
     n = hv.natom
@@ -214,7 +230,7 @@ def cuda_pass(args, dist):
         rep.prepare_resident()
 
     # -------- device-resident timing (`value`) --------
-    sampler = ClockSampler(dist.local_rank)
+    sampler = ClockSampler(dist.local_rank, active=dist.rank == 0)
     sampler.start()
     t_w = time.perf_counter()
     nwarm = 0
@@ -515,7 +531,7 @@ LOOP_ITERS = 256
 
 def cuda_loop(args, dist):
     from sdmd_b200 import capi
-    capi.build()
+    ensure_built(capi, dist)
     hv, gauss = make_box(args.n_axis, dist.rank)
     n = hv.natom
     rng = np.random.default_rng(99 + dist.rank)
@@ -530,7 +546,7 @@ def cuda_loop(args, dist):
         st, _ = rep.run(max_iter=LOOP_ITERS)       # device -> host: sdmd_run_stats
         return st
 
-    sampler = ClockSampler(dist.local_rank)
+    sampler = ClockSampler(dist.local_rank, active=dist.rank == 0)
     sampler.start()
     for _ in range(args.warmup):
         one_step()
@@ -760,7 +776,7 @@ def cuda_remd_many(args, dist):
     CalPotenE for all of them in one launch, the Server.c sweep on the host.  GPUs hold independent ensembles."""
     from sdmd_b200 import capi
     from sdmd_b200.remd import RemdEnsemble
-    capi.build()
+    ensure_built(capi, dist)
     R = args.replicas_per_gpu
     temps_K = remd_ladder_K(R)
     rate = float(args.exchange_rate)
@@ -797,7 +813,7 @@ def cuda_remd_many(args, dist):
     f0, it0 = totals()
     fed[0] = 0
     l0 = sum(r.launch_count() for r in reps)
-    sampler = ClockSampler(dist.local_rank)
+    sampler = ClockSampler(dist.local_rank, active=dist.rank == 0)
     sampler.start()
     dist.barrier()
     t0 = time.perf_counter()
@@ -837,7 +853,7 @@ def cuda_remd(args, dist):
     if args.replicas_per_gpu > 1:
         return cuda_remd_many(args, dist)
     from sdmd_b200 import capi
-    capi.build()
+    ensure_built(capi, dist)
     hv = ala10_view(dist.rank)
     rep = capi.Replica(hv, device=dist.local_rank)
     if dist.world > 1:
@@ -871,7 +887,7 @@ def cuda_remd(args, dist):
     rep.reset_kernel_stats()
     f0 = rep.stats()["frame"]
     it0 = rep.stats()["iterations"]
-    sampler = ClockSampler(dist.local_rank)
+    sampler = ClockSampler(dist.local_rank, active=dist.rank == 0)
     sampler.start()
     dist.barrier()
     t0 = time.perf_counter()
