@@ -50,6 +50,15 @@ def reduced_T(kelvin: float) -> float:
 REAL_STDOUT_FD = None      # the process's real stdout while fd 1 is pointed at stderr (main)
 
 
+_T0 = time.perf_counter()
+
+
+def mark(dist, what):
+    """Progress marker on stderr (every rank): where a run is, should it ever sit somewhere."""
+    sys.stderr.write(f"[bench r{dist.rank}/{dist.world} +{time.perf_counter() - _T0:6.1f}s] {what}\n")
+    sys.stderr.flush()
+
+
 def ensure_built(capi, dist):
     """The shared library is built by __graft_entry__.build() and travels with the tree; a bench rank never recompiles behind the
     back of the others (time stamps of a copied tree are no basis for N ranks to start N nvcc runs on one box).  Only when the
@@ -224,6 +233,7 @@ def cuda_pass(args, dist):
     n = hv.natom
     rep = capi.Replica(hv, device=dist.local_rank)
     rep.rng_feed(gauss)
+    mark(dist, "replica created")
 
     def one_pass():     # Prepare() of the reference on the resident state: PBC + LinkList + Predict(all) + CreateCBT, one C-ABI call
         rep.rng_seek(0)
@@ -245,6 +255,7 @@ def cuda_pass(args, dist):
     for _ in range(args.steps):
         one_pass()
     ms = rep.timer_end()
+    mark(dist, "device-resident passes timed")
     dist.barrier()
     ms = dist.max(ms)
     launches = rep.launch_count()
@@ -282,6 +293,7 @@ def cuda_pass(args, dist):
         one_e2e()
     rep.synchronize()
     e2e_serial_s = dist.max(time.perf_counter() - t0)
+    mark(dist, "end-to-end passes (one at a time) timed")
     e2e_serial_pairs = dist.sum(float(rep.stats()["pair_predictions"] - pairs0))
 
     # The same K steps with two of them in flight: a second replica context (own stream, own device buffers) driven by a
@@ -309,6 +321,7 @@ def cuda_pass(args, dist):
         t.join()
     rep.synchronize(); rep2.synchronize()
     e2e_s = dist.max(time.perf_counter() - t0)
+    mark(dist, "end-to-end passes (two in flight) timed")
     e2e_pairs = dist.sum(float(rep.stats()["pair_predictions"] + rep2.stats()["pair_predictions"] - p0))
     rep2.close()
     for a in host + [g_host]:
@@ -381,8 +394,10 @@ def cuda_pass(args, dist):
                    "sample": "2048 loop iterations of the device-resident event loop on the same box (sdmd_cuda_run, host wall clock "
                              "around the call, stats read back); `--workload loop` times it on its own with the sweep's roofline"}
     rep.close()
+    mark(dist, "extras done, pass replica closed")
     if dist.rank == 0 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_pass_baseline(args, gpu_pairs_per_pass=int(round(pairs / max(args.steps, 1))))
+        mark(dist, "CPU baseline done")
     if not args.no_remd:
         # The sub-record is an extra of the line, not its metric: it must not be able to take the line with it.  (An 8-rank run of
         # this round sat for six minutes somewhere behind the NCCL start-up and was killed by the box's limit before printing
@@ -656,6 +671,7 @@ def remd_subrecord(args, dist):
         uid = capi.nccl_unique_id() if dist.rank == 0 else None
         uid = dist.bcast_bytes(uid, 128)
         rep.remd_init(W, dist.rank, uid, server_seed=REMD_SERVER_SEED)
+        mark(dist, "remd: NCCL communicator of the library initialised")
     else:
         rep.remd_seed_server(REMD_SERVER_SEED)
     state = {"num": dist.rank + 1, "T": hv.target_temperature, "next": rate}
@@ -673,6 +689,7 @@ def remd_subrecord(args, dist):
         return st
 
     period()                                            # warm-up period (also the first, lazily connecting, collective)
+    mark(dist, "remd: warm-up period and first exchange done")
     f0 = rep.stats()["frame"]
     xchg_s.clear()
     dist.barrier()
@@ -688,6 +705,7 @@ def remd_subrecord(args, dist):
     walks = dist.gather_vec([v for nt in walk for v in nt], W)
     xs = dist.max(float(np.mean(xchg_s)))
     rep.close()
+    mark(dist, "remd: timed periods done")
     out = {"metric": "REMD replica-events/s", "value": sum(r[0] for r in per_rank) / dt, "unit": "events/s", "replicas": W,
            "periods_timed": periods, "exchange_rate_tu": rate, "temperatures_K": REMD_TEMPS_K[:W], "seconds": dt,
            "events_per_rank": [int(r[0]) for r in per_rank], "us_per_exchange_call": 1e6 * xs,
