@@ -160,6 +160,7 @@ class Dist:
             # the collectives of this file are barriers and 32-byte exchanges: NVLink-SHARP (multicast) set-up buys them nothing, and
             # two communicators (torch's and the library's own) both setting it up on an 8-GPU box is start-up time and risk for free
             os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+            os.environ.setdefault("NCCL_DEBUG", "WARN")      # (NCCL's own warnings and errors on stderr, next to the progress markers)
             if backend is None:
                 backend = "nccl" if torch.cuda.is_available() else "gloo"
             if backend == "nccl":
