@@ -304,3 +304,26 @@ def test_moving_wall_against_live_reference(tmp_path, case):
     # DoWallDyn ran several times, the wall was hit, and either it travelled or WallTime's retry pushed it back out (the chains fill
     # the slit, so a compression step of 1.25 A leaves atoms outside: every step is undone by a retry, touch counts them)
     assert wd["cur_time"] >= 3 and st["wall"] > 0 and (moved > 0.5 or wd["touch"] > 0), (wd, moved, st["wall"])
+
+
+@pytest.mark.refbin
+@pytest.mark.parametrize("case,kw", [
+    ("ala10", dict(harness="ref_harness", coord="ala10.gro", max_iter=500, n_gauss=4000, extra=[], gel_n=0)),
+    ("ala10x8", dict(harness="ref_harness", coord="ala10x8.gro", max_iter=500, n_gauss=8000, extra=[], gel_n=-8)),
+    ("ala10x80", dict(harness="ref_harness", coord="ala10x80.gro", max_iter=500, n_gauss=40000, extra=[], gel_n=-80)),
+], ids=["ala10", "ala10x8", "ala10x80"])
+def test_grid_sdenergymin_equals_the_reference(tmp_path, case, kw, monkeypatch):
+    """SDEnergyMin with the linear-time neighbour search (sdmd_b200/host/sdmd_sdmin.c) against the reference's own
+    (ToolFunctions.c:325-491): the same harness built with either, same input — every dump (relaxed coordinates, the rand()-drawn
+    thermostat stream that follows the relaxation's draws, slots, trace, final state) must be byte-identical, and so must the
+    MiniEnergy.gro the function writes."""
+    if not (REFDIR / "ref_harness_sdmin").exists():
+        pytest.skip("oracle/_ref/ref_harness_sdmin not built (needs /root/reference at build time)")
+    from oracle.make_golden import run_case
+    monkeypatch.setenv("SDMD_FAST_SDMIN", "1")          # the grid search also below its automatic threshold of 8192 atoms
+    want = run_case(case, tmp_path / "ref", **kw)
+    got = run_case(case, tmp_path / "grid", **dict(kw, harness="ref_harness_sdmin"))
+    for a, b in zip(want, got):
+        assert a.read_bytes() == b.read_bytes(), a.name
+    mini = [p.read_bytes() for p in (tmp_path / "ref" / "input" / "MiniEnergy.gro", tmp_path / "grid" / "input" / "MiniEnergy.gro")]
+    assert len(mini[0]) > 1000 and mini[0] == mini[1]
